@@ -1,0 +1,154 @@
+"""ctypes binding of oracle/_ref/libwebp_ref.so (the unmodified reference + oracle/reftool.c helpers).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, bench.py (cpu_baseline and --impl reference legs, corpus
+generation) and __graft_entry__.smoke(). The product package libwebp_b200 never imports this module.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libwebp_ref.so")
+
+# WEBP_CSP_MODE (src/webp/decode.h:150-163)
+MODE_RGB, MODE_RGBA, MODE_BGR, MODE_BGRA, MODE_ARGB = 0, 1, 2, 3, 4
+MODE_rgbA, MODE_bgrA, MODE_Argb = 7, 8, 9
+MODE_YUV, MODE_YUVA = 11, 12
+BPP = {0: 3, 1: 4, 2: 3, 3: 4, 4: 4, 7: 4, 8: 4, 9: 4}
+
+FLAG_BYPASS_FILTER, FLAG_NO_FANCY, FLAG_THREADS, FLAG_FLIP = 1, 2, 4, 8
+
+
+class EncCfg(C.Structure):
+    """Mirror of ReftEncCfg (oracle/reftool.c); -1 keeps the encoder default."""
+    _fields_ = [("quality", C.c_float), ("method", C.c_int), ("segments", C.c_int), ("filter_type", C.c_int),
+                ("filter_strength", C.c_int), ("filter_sharpness", C.c_int), ("partitions", C.c_int),
+                ("low_memory", C.c_int), ("alpha_filtering", C.c_int), ("alpha_quality", C.c_int),
+                ("sns_strength", C.c_int)]
+
+    def __init__(self, quality=75.0, method=4, **kw):
+        super().__init__()
+        for name, _ in self._fields_:
+            setattr(self, name, -1)
+        self.quality, self.method = quality, method
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+# The corpus configurations of BASELINE.json / SURVEY.md 8(d).
+def cfg_simple_1part(quality=75.0):      # config 2: 1 segment, simple filter, 1 token partition
+    return EncCfg(quality, 4, segments=1, filter_type=0, partitions=0)
+
+
+def cfg_normal_8part(quality=75.0):      # config 3: 4 segments, normal filter, 8 token partitions
+    return EncCfg(quality, 4, segments=4, filter_type=1, partitions=3, low_memory=1)
+
+
+def cfg_default(quality=80.0):           # config 4: cwebp defaults at q80 (4 segments, strong filter)
+    return EncCfg(quality, 4)
+
+
+_lib = None
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError(f"{LIB_PATH} missing: run `make -C oracle ref` where /root/reference exists")
+        L = C.CDLL(LIB_PATH)
+        L.reft_synth.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_void_p]
+        L.reft_encode.restype = C.c_size_t
+        L.reft_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(EncCfg), C.POINTER(C.c_void_p)]
+        L.reft_free.argtypes = [C.c_void_p]
+        L.reft_encode_corpus.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.POINTER(EncCfg), C.c_int,
+                                         C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.reft_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
+        L.reft_features.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int)]
+        L.reft_decode_bench.restype = C.c_double
+        L.reft_decode_bench.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.reft_set_simd.argtypes = [C.c_int]
+        _lib = L
+    return _lib
+
+
+def synth(w, h, seed, alpha=False):
+    bpp = 4 if alpha else 3
+    out = np.empty((h, w, bpp), np.uint8)
+    lib().reft_synth(w, h, seed, bpp, out.ctypes.data)
+    return out
+
+
+def encode(pix, cfg):
+    h, w, bpp = pix.shape
+    pix = np.ascontiguousarray(pix)
+    p = C.c_void_p()
+    n = lib().reft_encode(pix.ctypes.data, w, h, bpp, C.byref(cfg), C.byref(p))
+    if n == 0:
+        raise RuntimeError("reference encoder failed")
+    data = C.string_at(p, n)
+    lib().reft_free(p)
+    return data
+
+
+def encode_corpus(n, w, h, cfg, seed0=1, alpha=False, nthreads=None):
+    """n synthetic images (seed0+k) -> list of .webp byte strings, encoded on nthreads host threads."""
+    nthreads = nthreads or (os.cpu_count() or 1)
+    outs = (C.c_void_p * n)()
+    sizes = (C.c_size_t * n)()
+    rc = lib().reft_encode_corpus(n, w, h, 4 if alpha else 3, seed0, C.byref(cfg), nthreads, outs, sizes)
+    res = []
+    for i in range(n):
+        if outs[i]:
+            res.append(C.string_at(outs[i], sizes[i]))
+            lib().reft_free(outs[i])
+    if rc != 0 or len(res) != n:
+        raise RuntimeError("reference encoder failed on the corpus")
+    return res
+
+
+def features(data):
+    f = (C.c_int * 5)()
+    st = lib().reft_features(data, len(data), f)
+    return st, dict(width=f[0], height=f[1], has_alpha=f[2], has_animation=f[3], format=f[4])
+
+
+def decode(data, csp=MODE_RGBA, flags=0, simd=True, stride=None):
+    """Reference WebPDecode. Returns (status, ndarray): (h, stride) bytes for RGB modes (visible part is
+    [:, :w*bpp]); for MODE_YUV a flat y|u|v array with tight strides."""
+    L = lib()
+    L.reft_set_simd(1 if simd else 0)
+    st, f = features(data)
+    if st != 0:
+        return st, None
+    w, h = f["width"], f["height"]
+    if csp in (MODE_YUV, MODE_YUVA):
+        n = w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2) + (w * h if csp == MODE_YUVA else 0)
+        out = np.zeros(n, np.uint8)
+        st = L.reft_decode(data, len(data), csp, flags, out.ctypes.data, n, 0)
+    else:
+        stride = stride or w * BPP[csp]
+        out = np.zeros((h, stride), np.uint8)
+        st = L.reft_decode(data, len(data), csp, flags, out.ctypes.data, out.size, stride)
+    L.reft_set_simd(1)
+    return st, (out if st == 0 else None)
+
+
+def decode_bench(datas, nthreads, csp=MODE_RGBA, passes=1, simd=True):
+    """The CPU baseline of BASELINE.md section 3. Returns dict(seconds, mpix_per_pass, mpix_s, errors)."""
+    L = lib()
+    L.reft_set_simd(1 if simd else 0)
+    n = len(datas)
+    arr = (C.c_char_p * n)(*datas)
+    sizes = (C.c_size_t * n)(*[len(d) for d in datas])
+    mpix, errs = C.c_double(), C.c_int()
+    sec = L.reft_decode_bench(arr, sizes, n, nthreads, csp, passes, C.byref(mpix), C.byref(errs))
+    L.reft_set_simd(1)
+    return dict(seconds=sec, mpix_per_pass=mpix.value, mpix_s=mpix.value * passes / max(sec, 1e-12),
+                errors=errs.value, threads=nthreads)
