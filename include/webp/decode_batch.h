@@ -1,0 +1,102 @@
+/* webp/decode_batch.h -- batched entry points of libwebp_b200 (new; no counterpart in the reference).
+ *
+ * The reference decodes one image per call on one host thread (WebPDecode, src/dec/webp_dec.c:752, which
+ * loops VP8ParseIntraModeRow / VP8DecodeMB / VP8ProcessRow per macroblock row, src/dec/vp8_dec.c:646-674).
+ * Here the unit of work is a batch: every stage runs as one CUDA kernel over all images of the batch, and
+ * WebPDecode() is the batch of one. Per-item semantics (status codes, output buffer contract, options) are
+ * those of WebPDecode. Images are independent, so a multi-GPU caller shards the item array by index and
+ * gives each shard to one device (one process or host thread per device); there is no collective.
+ *
+ * Plain C ABI: pointers and sizes only. This is the surface a binding of the reference's language would
+ * wrap. */
+#ifndef WEBP_WEBP_DECODE_BATCH_H_
+#define WEBP_WEBP_DECODE_BATCH_H_
+
+#include "./decode.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WEBP_BATCH_ABI_VERSION 0x0100
+
+typedef struct WebPBatchItem {
+  const uint8_t* data;       /* one complete .webp file (RIFF or bare VP8), host memory */
+  size_t data_size;
+  WebPDecoderConfig* config; /* as for WebPDecode(); `input` is filled, `output` describes the destination */
+  VP8StatusCode status;      /* out: per-item result, same codes WebPDecode() would return */
+} WebPBatchItem;
+
+typedef enum WebPBatchMemory {
+  WEBP_BATCH_HOST = 0,  /* config->output is host memory, exactly as for WebPDecode() */
+  WEBP_BATCH_DEVICE = 1 /* decoded pixels stay in device memory owned by the batch (see WebPBatchOutput) */
+} WebPBatchMemory;
+
+typedef struct WebPBatchOptions {
+  int device;                /* CUDA device ordinal, -1 = the calling thread's current device */
+  WebPBatchMemory output;    /* where decoded pixels end up */
+  size_t scratch_bytes;      /* cap on device scratch per wave (0 = default: 40% of free memory) */
+  uint32_t pad[8];
+} WebPBatchOptions;
+
+WEBP_EXTERN int WebPBatchOptionsInitInternal(WebPBatchOptions*, int);
+static WEBP_INLINE int WebPBatchOptionsInit(WebPBatchOptions* o) {
+  return WebPBatchOptionsInitInternal(o, WEBP_BATCH_ABI_VERSION);
+}
+
+/* One-shot: parse, upload, decode, and (WEBP_BATCH_HOST) download. Returns VP8_STATUS_OK when every item
+ * decoded, else the first failing item's status; items[i].status always holds the per-item code. One bad
+ * image never poisons the others. `options` may be NULL (device -1, host output). */
+WEBP_EXTERN VP8StatusCode WebPDecodeBatch(WebPBatchItem* items, int num_items, const WebPBatchOptions* options);
+
+/* Resident form, for callers that keep compressed data and pixels on the device between steps:
+ *   WebPBatchCreate   parses containers on the host, allocates device memory, uploads the compressed bytes
+ *   WebPBatchDecode   runs the kernels (can be repeated; inputs stay resident), waits for completion
+ *   WebPBatchDownload copies the pixels into every item's config->output (host memory)
+ *   WebPBatchOutput   device address + layout of item i's pixels
+ *   WebPBatchDestroy  releases everything
+ * `items` must stay valid for the lifetime of the batch. */
+typedef struct WebPBatch WebPBatch;
+
+WEBP_EXTERN WebPBatch* WebPBatchCreate(WebPBatchItem* items, int num_items, const WebPBatchOptions* options,
+                                       VP8StatusCode* status);
+WEBP_EXTERN VP8StatusCode WebPBatchDecode(WebPBatch* batch);
+WEBP_EXTERN VP8StatusCode WebPBatchDownload(WebPBatch* batch);
+WEBP_EXTERN void WebPBatchDestroy(WebPBatch* batch);
+
+typedef struct WebPBatchPlane {
+  void* y_or_rgba; /* device pointer: RGB-family pixels, or the Y plane for MODE_YUV */
+  void* u;
+  void* v;
+  int stride, uv_stride;
+  int width, height;
+} WebPBatchPlane;
+WEBP_EXTERN int WebPBatchOutput(const WebPBatch* batch, int index, WebPBatchPlane* plane);
+
+/* Per-stage device time of the last WebPBatchDecode() on this batch, from CUDA events recorded on the
+ * batch's own stream around each kernel (milliseconds; `launches` = kernels launched). */
+typedef struct WebPBatchTimings {
+  float total_ms;
+  float modes_ms;    /* header + intra-mode parse (partition 0) */
+  float tokens_ms;   /* coefficient token parse (incl. zeroing the coefficient planes) */
+  float recon_ms;    /* dequantised IDCT/WHT + intra prediction wavefront */
+  float filter_ms;   /* in-loop deblocking wavefront */
+  float emit_ms;     /* upsample + YUV->RGB (or plane copy) */
+  int launches;
+  uint32_t pad[5];
+} WebPBatchTimings;
+WEBP_EXTERN int WebPBatchGetTimings(const WebPBatch* batch, WebPBatchTimings* t);
+
+/* Page-locked host memory for inputs/outputs (plain malloc works too, just slower over PCIe). */
+WEBP_EXTERN void* WebPBatchHostAlloc(size_t size);
+WEBP_EXTERN void WebPBatchHostFree(void* ptr);
+
+/* Number of CUDA devices visible to the library; 0 means WebPDecode*() will fail (there is no CPU path). */
+WEBP_EXTERN int WebPBatchDeviceCount(void);
+/* Human-readable text for the last CUDA/runtime error seen by the calling thread ("" if none). */
+WEBP_EXTERN const char* WebPBatchLastError(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WEBP_WEBP_DECODE_BATCH_H_ */

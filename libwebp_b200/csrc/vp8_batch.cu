@@ -1,0 +1,645 @@
+// vp8_batch.cu -- host driver of the batched decoder: per-item validation, device memory, uploads, kernel
+// sequencing per wave, status/pixel downloads. Public entry points: include/webp/decode_batch.h.
+//
+// Replaces the per-image control flow of DecodeInto (src/dec/webp_dec.c:447-523): WebPParseHeaders ->
+// VP8GetHeaders -> WebPAllocateDecBuffer -> VP8Decode, and the output-buffer contract of
+// src/dec/buffer_dec.c:41-228 (CheckDecBuffer / AllocateBuffer). There is no CPU decode path: without a
+// usable CUDA device every item fails and WebPBatchLastError() says why.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "vp8_container.h"
+#include "vp8_kernels.h"
+#include "webp/decode_batch.h"
+
+// ---------------------------------------------------------------------------------------------------------
+static thread_local char g_last_error[256] = "";
+
+static void set_error(const char* what, cudaError_t e) {
+  snprintf(g_last_error, sizeof(g_last_error), "%s: %s", what, e == cudaSuccess ? "failed" : cudaGetErrorString(e));
+}
+
+#define CU_TRY(call, what)            \
+  do {                                \
+    cudaError_t e_ = (call);          \
+    if (e_ != cudaSuccess) {          \
+      set_error((what), e_);          \
+      return false;                   \
+    }                                 \
+  } while (0)
+
+extern "C" const char* WebPBatchLastError(void) { return g_last_error; }
+
+extern "C" int WebPBatchDeviceCount(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" void* WebPBatchHostAlloc(size_t size) {
+  void* p = NULL;
+  if (cudaHostAlloc(&p, size, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return NULL; }
+  return p;
+}
+extern "C" void WebPBatchHostFree(void* ptr) { if (ptr != NULL) cudaFreeHost(ptr); }
+
+extern "C" int WebPBatchOptionsInitInternal(WebPBatchOptions* o, int version) {
+  if (o == NULL || WEBP_ABI_IS_INCOMPATIBLE(version, WEBP_BATCH_ABI_VERSION)) return 0;
+  memset(o, 0, sizeof(*o));
+  o->device = -1;
+  o->output = WEBP_BATCH_HOST;
+  return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-device state: two streams and a small cache of device allocations so that repeated WebPDecode() calls
+// do not pay cudaMalloc/cudaFree every time.
+struct CachedBlock { void* p; size_t cap; };
+
+struct DeviceCtx {
+  int device = -1;
+  bool ok = false;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;          // one batch at a time per device
+  std::vector<CachedBlock> cache;
+  size_t cached_bytes = 0;
+};
+
+static std::mutex g_ctx_mu;
+static DeviceCtx* g_ctx[64];
+
+static DeviceCtx* get_ctx(int device) {
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) { set_error("cudaGetDevice (no CUDA device; this library has no CPU path)", cudaGetLastError()); return nullptr; }
+  }
+  if (device >= 64) { set_error("device ordinal out of range", cudaSuccess); return nullptr; }
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  if (g_ctx[device] == nullptr) {
+    DeviceCtx* c = new DeviceCtx();
+    c->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_error("CUDA device init (no usable GPU; this library has no CPU path)", e); cudaGetLastError(); delete c; return nullptr; }
+    c->ok = true;
+    g_ctx[device] = c;
+  }
+  return g_ctx[device];
+}
+
+static void* dev_alloc(DeviceCtx* c, size_t bytes) {
+  if (bytes == 0) bytes = 256;
+  int best = -1;
+  for (size_t i = 0; i < c->cache.size(); ++i) {
+    if (c->cache[i].cap >= bytes && c->cache[i].cap <= 2 * bytes + (1 << 20) &&
+        (best < 0 || c->cache[i].cap < c->cache[best].cap)) best = (int)i;
+  }
+  if (best >= 0) {
+    void* p = c->cache[best].p;
+    c->cached_bytes -= c->cache[best].cap;
+    c->cache.erase(c->cache.begin() + best);
+    return p;
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {   // drop the cache and retry once
+    cudaGetLastError();
+    for (auto& b : c->cache) cudaFree(b.p);
+    c->cache.clear(); c->cached_bytes = 0;
+    e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) { set_error("cudaMalloc", e); cudaGetLastError(); return nullptr; }
+  }
+  return p;
+}
+
+struct Owned { void* p = nullptr; size_t cap = 0; };
+
+static bool own_alloc(DeviceCtx* c, Owned& o, size_t bytes) {
+  o.cap = bytes ? bytes : 256;
+  o.p = dev_alloc(c, o.cap);
+  return o.p != nullptr;
+}
+
+static void own_free(DeviceCtx* c, Owned& o) {
+  if (o.p == nullptr) return;
+  if (c->cached_bytes + o.cap <= ((size_t)8 << 30) && c->cache.size() < 64) {   // keep up to 8 GiB around
+    c->cache.push_back({ o.p, o.cap });
+    c->cached_bytes += o.cap;
+  } else {
+    cudaFree(o.p);
+  }
+  o.p = nullptr; o.cap = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+static const int kBpp[MODE_LAST] = { 3, 4, 3, 4, 4, 2, 2, 4, 4, 4, 2, 1, 1 };   // buffer_dec.c:24-27
+
+static bool csp_supported(int csp) {
+  return csp == MODE_RGB || csp == MODE_RGBA || csp == MODE_BGR || csp == MODE_BGRA || csp == MODE_ARGB ||
+         csp == MODE_rgbA || csp == MODE_bgrA || csp == MODE_Argb || csp == MODE_YUV;
+}
+
+// CheckDecBuffer (buffer_dec.c:41-84) for host output.
+static VP8StatusCode check_host_buffer(const WebPDecBuffer* b) {
+  const int w = b->width, h = b->height;
+  bool ok = true;
+  if (!WebPIsRGBMode(b->colorspace)) {
+    const WebPYUVABuffer* y = &b->u.YUVA;
+    const int uvw = (w + 1) / 2, uvh = (h + 1) / 2;
+    const uint64_t ys = (uint64_t)abs(y->y_stride), us = (uint64_t)abs(y->u_stride), vs = (uint64_t)abs(y->v_stride);
+    ok &= (ys * (h - 1) + w <= y->y_size) && (us * (uvh - 1) + uvw <= y->u_size) && (vs * (uvh - 1) + uvw <= y->v_size);
+    ok &= ((int)ys >= w) && ((int)us >= uvw) && ((int)vs >= uvw);
+    ok &= (y->y != NULL) && (y->u != NULL) && (y->v != NULL);
+  } else {
+    const WebPRGBABuffer* r = &b->u.RGBA;
+    const uint64_t st = (uint64_t)abs(r->stride);
+    const uint64_t row = (uint64_t)w * kBpp[b->colorspace];
+    ok &= (st * (h - 1) + row <= r->size) && (st >= row) && (r->rgba != NULL);
+  }
+  return ok ? VP8_STATUS_OK : VP8_STATUS_INVALID_PARAM;
+}
+
+// WebPAllocateDecBuffer / AllocateBuffer (buffer_dec.c:87-227) for host output, without crop/scale/flip.
+static VP8StatusCode prepare_host_buffer(int w, int h, WebPDecBuffer* b) {
+  if (b == NULL || w <= 0 || h <= 0) return VP8_STATUS_INVALID_PARAM;
+  b->width = w; b->height = h;
+  const int csp = b->colorspace;
+  if (csp < MODE_RGB || csp >= MODE_LAST) return VP8_STATUS_INVALID_PARAM;
+  if (b->is_external_memory <= 0 && b->private_memory == NULL) {
+    if ((uint64_t)w * kBpp[csp] >= (1ull << 31)) return VP8_STATUS_INVALID_PARAM;
+    const int stride = w * kBpp[csp];
+    const uint64_t size = (uint64_t)stride * h;
+    uint64_t uv_size = 0;
+    int uv_stride = 0;
+    if (!WebPIsRGBMode((WEBP_CSP_MODE)csp)) { uv_stride = (w + 1) / 2; uv_size = (uint64_t)uv_stride * ((h + 1) / 2); }
+    const uint64_t total = size + 2 * uv_size;
+    if (total >= (1ull << 34)) return VP8_STATUS_OUT_OF_MEMORY;   // WEBP_MAX_ALLOCABLE_MEMORY, utils.h:34-41
+    uint8_t* mem = (uint8_t*)malloc((size_t)total);
+    if (mem == NULL) return VP8_STATUS_OUT_OF_MEMORY;
+    b->private_memory = mem;
+    if (!WebPIsRGBMode((WEBP_CSP_MODE)csp)) {
+      WebPYUVABuffer* y = &b->u.YUVA;
+      y->y = mem; y->y_stride = stride; y->y_size = (size_t)size;
+      y->u = mem + size; y->u_stride = uv_stride; y->u_size = (size_t)uv_size;
+      y->v = mem + size + uv_size; y->v_stride = uv_stride; y->v_size = (size_t)uv_size;
+      y->a = NULL; y->a_size = 0; y->a_stride = 0;
+    } else {
+      b->u.RGBA.rgba = mem; b->u.RGBA.stride = stride; b->u.RGBA.size = (size_t)size;
+    }
+  }
+  return check_host_buffer(b);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+struct ItemPlan {
+  int img = -1;            // index among the device images, -1 when the item failed on the host
+  size_t frame_offset = 0; // VP8 frame tag inside the file
+  size_t out_bytes = 0;    // bytes of this image in the device output arena (tight strides)
+};
+
+struct Wave {
+  int first = 0, count = 0;
+  size_t mbs = 0;
+  int max_mb_w = 0, max_mb_h = 0, max_units = 0;
+  int ids_off[4] = { 0, 0, 0, 0 }, ids_cnt[4] = { 0, 0, 0, 0 };   // per log2(P) slice of the ids array
+};
+
+struct HostRange { const uint8_t* base; size_t size; size_t dev_off; };
+
+struct WebPBatch {
+  DeviceCtx* ctx = nullptr;
+  WebPBatchItem* items = nullptr;
+  int n = 0;
+  WebPBatchOptions opt;
+  std::vector<ItemPlan> plan;
+  std::vector<ImgDesc> imgs;       // device images, wave-major
+  std::vector<int> img_item;       // device image -> item
+  std::vector<Wave> waves;
+  std::vector<int> ids;            // token-parse launch lists
+  std::vector<int> statuses;       // host copy of FrameHdr::status
+  Owned d_in, d_imgs, d_hdrs, d_ids, d_mbinfo, d_coeffs, d_yuv, d_out;
+  size_t out_total = 0;
+  int max_mb_w = 1, max_mb_h = 1;
+  cudaEvent_t ev[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+  WebPBatchTimings timings;
+  bool decoded = false;
+};
+
+static void fail_all(WebPBatchItem* items, int n, VP8StatusCode st) {
+  for (int i = 0; i < n; ++i) if (items[i].status == VP8_STATUS_OK) items[i].status = st;
+}
+
+// Host-side part of one item: container walk, option/colourspace screening, output buffer.
+static VP8StatusCode plan_item(WebPBatchItem* it, const WebPBatchOptions& opt, Vp8Container* c) {
+  WebPDecoderConfig* cfg = it->config;
+  if (cfg == NULL) return VP8_STATUS_INVALID_PARAM;
+  VP8StatusCode st = vp8b_get_features(it->data, it->data_size, &cfg->input);
+  if (st != VP8_STATUS_OK) return st == VP8_STATUS_NOT_ENOUGH_DATA ? VP8_STATUS_BITSTREAM_ERROR : st;   // webp_dec.c:761-767
+  st = (VP8StatusCode)vp8b_parse_container(it->data, it->data_size, 1, c);
+  if (st != VP8_STATUS_OK) return st;
+  if (c->has_animation) return VP8_STATUS_UNSUPPORTED_FEATURE;             // webp_dec.c:427-429
+  if (c->is_lossless) return VP8_STATUS_UNSUPPORTED_FEATURE;               // lossless: not on this path
+  if (c->has_alph_chunk) return VP8_STATUS_UNSUPPORTED_FEATURE;            // ALPH plane: next
+  if (c->part0_size > c->frame_size - 10) return VP8_STATUS_NOT_ENOUGH_DATA;   // vp8_dec.c:345-348
+  const WebPDecoderOptions* o = &cfg->options;
+  if (o->use_cropping || o->use_scaling || o->flip) return VP8_STATUS_UNSUPPORTED_FEATURE;
+  const int csp = cfg->output.colorspace;
+  if (csp < MODE_RGB || csp >= MODE_LAST) return VP8_STATUS_INVALID_PARAM;
+  if (!csp_supported(csp)) return VP8_STATUS_UNSUPPORTED_FEATURE;
+  if (opt.output == WEBP_BATCH_HOST) return prepare_host_buffer(c->width, c->height, &cfg->output);
+  cfg->output.width = c->width; cfg->output.height = c->height;
+  return VP8_STATUS_OK;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Host pass: everything that can be decided without a GPU. Returns the number of items still alive.
+static int batch_plan(WebPBatch* b, std::vector<Vp8Container>& cont) {
+  const int n = b->n;
+  int alive = 0;
+  b->plan.resize(n);
+  cont.resize(n);
+  for (int i = 0; i < n; ++i) {
+    b->items[i].status = plan_item(&b->items[i], b->opt, &cont[i]);
+    if (b->items[i].status == VP8_STATUS_OK) ++alive;
+    else if (b->items[i].config != NULL && b->opt.output == WEBP_BATCH_HOST) {
+      WebPFreeDecBuffer(&b->items[i].config->output);   // webp_dec.c:513-515
+    }
+  }
+  return alive;
+}
+
+static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
+  DeviceCtx* ctx = b->ctx;
+  const int n = b->n;
+  // ---- input ranges: merge host buffers that sit (almost) next to each other into single H2D copies
+  std::vector<int> order;
+  for (int i = 0; i < n; ++i) if (b->items[i].status == VP8_STATUS_OK) order.push_back(i);
+  std::vector<int> by_addr(order);
+  std::sort(by_addr.begin(), by_addr.end(), [&](int a, int c2) { return b->items[a].data < b->items[c2].data; });
+  std::vector<HostRange> ranges;
+  std::vector<int> item_range(n, -1);
+  size_t in_total = 256;
+  for (int i : by_addr) {
+    const uint8_t* p = b->items[i].data;
+    const size_t sz = b->items[i].data_size;
+    if (!ranges.empty()) {
+      HostRange& r = ranges.back();
+      if (p >= r.base && p <= r.base + r.size + 4096) {
+        const size_t end = (size_t)(p - r.base) + sz;
+        if (end > r.size) r.size = end;
+        item_range[i] = (int)ranges.size() - 1;
+        continue;
+      }
+    }
+    ranges.push_back({ p, sz, 0 });
+    item_range[i] = (int)ranges.size() - 1;
+  }
+  for (auto& r : ranges) { r.dev_off = in_total; in_total += align_up(r.size, 256) + 256; }
+  // ---- device images, output offsets
+  size_t total_mbs = 0;
+  for (int i : order) {
+    const Vp8Container& c = cont[i];
+    const WebPDecoderConfig* cfg = b->items[i].config;
+    ImgDesc d;
+    memset(&d, 0, sizeof(d));
+    d.in_off = ranges[item_range[i]].dev_off + (size_t)(b->items[i].data - ranges[item_range[i]].base) + c.frame_offset;
+    d.vp8_size = (uint32_t)c.frame_size;
+    d.part0_size = c.part0_size;
+    d.width = (uint16_t)c.width; d.height = (uint16_t)c.height;
+    d.mb_w = (uint16_t)((c.width + 15) >> 4); d.mb_h = (uint16_t)((c.height + 15) >> 4);
+    d.csp = (uint8_t)cfg->output.colorspace;
+    d.flags = (uint8_t)((cfg->options.bypass_filtering ? VP8B_FLAG_BYPASS_FILTER : 0) |
+                        (cfg->options.no_fancy_upsampling ? VP8B_FLAG_NO_FANCY : 0));
+    const int ds = cfg->options.dithering_strength;
+    d.dither_f = (uint8_t)(ds < 0 ? 0 : ds > 100 ? 255 : ds * 255 / 100);
+    d.num_parts = (uint8_t)vp8b_prescan_partitions(b->items[i].data + c.frame_offset + 10, c.part0_size);
+    size_t bytes;
+    if (d.csp == MODE_YUV) {
+      d.out_stride = c.width;
+      bytes = (size_t)c.width * c.height + 2 * (size_t)((c.width + 1) / 2) * ((c.height + 1) / 2);
+    } else {
+      d.out_stride = c.width * kBpp[d.csp];
+      bytes = (size_t)d.out_stride * c.height;
+    }
+    d.out_off = b->out_total;
+    b->out_total += align_up(bytes, 256);
+    b->plan[i].img = (int)b->imgs.size();
+    b->plan[i].frame_offset = c.frame_offset;
+    b->plan[i].out_bytes = bytes;
+    b->imgs.push_back(d);
+    b->img_item.push_back(i);
+    total_mbs += (size_t)d.mb_w * d.mb_h;
+    b->max_mb_w = std::max(b->max_mb_w, (int)d.mb_w);
+    b->max_mb_h = std::max(b->max_mb_h, (int)d.mb_h);
+  }
+  const int m = (int)b->imgs.size();
+  b->statuses.assign(m, 0);
+  if (m == 0) return true;
+
+  CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+  // ---- resident allocations: input, descriptors, headers, output
+  if (!own_alloc(ctx, b->d_in, in_total + 256) || !own_alloc(ctx, b->d_imgs, sizeof(ImgDesc) * m) ||
+      !own_alloc(ctx, b->d_hdrs, sizeof(FrameHdr) * m) || !own_alloc(ctx, b->d_ids, sizeof(int) * m) ||
+      !own_alloc(ctx, b->d_out, b->out_total + 256)) return false;
+  // ---- waves: per-macroblock scratch = 16 (MbInfo) + 800 (coefficients) + 384 (planes) bytes
+  const size_t per_mb = 16 + 2 * VP8B_COEFFS_PER_MB + 384;
+  size_t budget = b->opt.scratch_bytes;
+  if (budget == 0) {
+    size_t free_b = 0, total_b = 0;
+    CU_TRY(cudaMemGetInfo(&free_b, &total_b), "cudaMemGetInfo");
+    budget = (size_t)((double)free_b * 0.85);
+  }
+  size_t wave_cap_mbs = std::max<size_t>(budget / per_mb, (size_t)b->max_mb_w * b->max_mb_h);
+  {
+    Wave w;
+    for (int k = 0; k < m; ++k) {
+      const size_t mbs = (size_t)b->imgs[k].mb_w * b->imgs[k].mb_h;
+      if (w.count > 0 && w.mbs + mbs > wave_cap_mbs) { b->waves.push_back(w); w = Wave(); w.first = k; }
+      b->imgs[k].mb_base = (uint32_t)w.mbs;
+      w.mbs += mbs; w.count++;
+      w.max_mb_w = std::max(w.max_mb_w, (int)b->imgs[k].mb_w);
+      w.max_mb_h = std::max(w.max_mb_h, (int)b->imgs[k].mb_h);
+      const ImgDesc& d = b->imgs[k];
+      const int units = (d.csp == MODE_YUV)
+                            ? ((d.width + 15) / 16) * d.height + 2 * ((((d.width + 1) / 2) + 15) / 16) * ((d.height + 1) / 2)
+                            : ((d.width + 3) / 4) * d.height;
+      w.max_units = std::max(w.max_units, units);
+    }
+    b->waves.push_back(w);
+  }
+  size_t max_wave_mbs = 0;
+  b->ids.resize(m);
+  for (auto& w : b->waves) {
+    max_wave_mbs = std::max(max_wave_mbs, w.mbs);
+    int pos = w.first;
+    for (int lg = 0; lg < 4; ++lg) {
+      w.ids_off[lg] = pos;
+      for (int k = w.first; k < w.first + w.count; ++k) if (b->imgs[k].num_parts == (1 << lg)) b->ids[pos++] = k;
+      w.ids_cnt[lg] = pos - w.ids_off[lg];
+    }
+  }
+  if (!own_alloc(ctx, b->d_mbinfo, max_wave_mbs * 16) || !own_alloc(ctx, b->d_coeffs, max_wave_mbs * 2 * VP8B_COEFFS_PER_MB) ||
+      !own_alloc(ctx, b->d_yuv, max_wave_mbs * 384)) return false;
+  // ---- uploads
+  cudaStream_t s = ctx->stream;
+  for (const auto& r : ranges) {
+    CU_TRY(cudaMemcpyAsync((uint8_t*)b->d_in.p + r.dev_off, r.base, r.size, cudaMemcpyHostToDevice, s), "H2D input");
+  }
+  CU_TRY(cudaMemcpyAsync(b->d_imgs.p, b->imgs.data(), sizeof(ImgDesc) * m, cudaMemcpyHostToDevice, s), "H2D descriptors");
+  CU_TRY(cudaMemcpyAsync(b->d_ids.p, b->ids.data(), sizeof(int) * m, cudaMemcpyHostToDevice, s), "H2D ids");
+  CU_TRY(vp8k_configure(b->max_mb_w, b->max_mb_h), "cudaFuncSetAttribute");
+  for (int k = 0; k < 8; ++k) CU_TRY(cudaEventCreate(&b->ev[k]), "cudaEventCreate");
+  CU_TRY(cudaStreamSynchronize(s), "upload sync");
+  return true;
+}
+
+static void batch_release(WebPBatch* b) {
+  if (b == nullptr) return;
+  if (b->ctx != nullptr) {
+    DeviceCtx* c = b->ctx;
+    own_free(c, b->d_in); own_free(c, b->d_imgs); own_free(c, b->d_hdrs); own_free(c, b->d_ids);
+    own_free(c, b->d_mbinfo); own_free(c, b->d_coeffs); own_free(c, b->d_yuv); own_free(c, b->d_out);
+    for (int k = 0; k < 8; ++k) if (b->ev[k]) cudaEventDestroy(b->ev[k]);
+  }
+  delete b;
+}
+
+extern "C" WebPBatch* WebPBatchCreate(WebPBatchItem* items, int num_items, const WebPBatchOptions* options,
+                                      VP8StatusCode* status) {
+  VP8StatusCode dummy;
+  if (status == NULL) status = &dummy;
+  *status = VP8_STATUS_INVALID_PARAM;
+  if (items == NULL || num_items <= 0) return NULL;
+  WebPBatchOptions opt;
+  if (options != NULL) opt = *options; else WebPBatchOptionsInit(&opt);
+  g_last_error[0] = 0;
+  WebPBatch* b = new WebPBatch();
+  b->items = items; b->n = num_items; b->opt = opt;
+  memset(&b->timings, 0, sizeof(b->timings));
+  std::vector<Vp8Container> cont;
+  if (batch_plan(b, cont) == 0) {   // nothing survived the host checks: no device work, no device needed
+    *status = VP8_STATUS_OK;
+    b->decoded = true;
+    return b;
+  }
+  DeviceCtx* ctx = get_ctx(opt.device);
+  if (ctx == nullptr) {
+    for (int i = 0; i < num_items; ++i) {
+      if (items[i].status != VP8_STATUS_OK) continue;
+      items[i].status = VP8_STATUS_USER_ABORT;
+      if (items[i].config != NULL && opt.output == WEBP_BATCH_HOST) WebPFreeDecBuffer(&items[i].config->output);
+    }
+    *status = VP8_STATUS_USER_ABORT;
+    fprintf(stderr, "libwebp_b200: %s\n", g_last_error);
+    delete b;
+    return NULL;
+  }
+  b->ctx = ctx;
+  ctx->mu.lock();
+  const bool ok = batch_build(b, cont);
+  ctx->mu.unlock();
+  if (!ok) {
+    const VP8StatusCode st = strstr(g_last_error, "cudaMalloc") ? VP8_STATUS_OUT_OF_MEMORY : VP8_STATUS_USER_ABORT;
+    for (int i = 0; i < num_items; ++i) {
+      if (items[i].status == VP8_STATUS_OK) {
+        items[i].status = st;
+        if (items[i].config != NULL && opt.output == WEBP_BATCH_HOST) WebPFreeDecBuffer(&items[i].config->output);
+      }
+    }
+    *status = st;
+    ctx->mu.lock(); batch_release(b); ctx->mu.unlock();
+    return NULL;
+  }
+  *status = VP8_STATUS_OK;
+  return b;
+}
+
+static bool batch_decode(WebPBatch* b) {
+  DeviceCtx* ctx = b->ctx;
+  const int m = (int)b->imgs.size();
+  memset(&b->timings, 0, sizeof(b->timings));
+  if (m == 0) return true;
+  CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+  cudaStream_t s = ctx->stream;
+  const uint8_t* arena = (const uint8_t*)b->d_in.p;
+  const ImgDesc* imgs = (const ImgDesc*)b->d_imgs.p;
+  FrameHdr* hdrs = (FrameHdr*)b->d_hdrs.p;
+  uint32_t* mbinfo = (uint32_t*)b->d_mbinfo.p;
+  int16_t* coeffs = (int16_t*)b->d_coeffs.p;
+  uint8_t* yuv = (uint8_t*)b->d_yuv.p;
+  float acc[5] = { 0, 0, 0, 0, 0 };
+  int launches = 0;
+  for (const Wave& w : b->waves) {
+    CU_TRY(cudaEventRecord(b->ev[0], s), "event");
+    vp8k_parse_modes(s, arena, imgs, hdrs, mbinfo, w.first, w.count, w.max_mb_w);
+    ++launches;
+    CU_TRY(cudaEventRecord(b->ev[1], s), "event");
+    CU_TRY(cudaMemsetAsync(coeffs, 0, w.mbs * 2 * VP8B_COEFFS_PER_MB, s), "memset coefficients");
+    for (int lg = 0; lg < 4; ++lg) {
+      if (w.ids_cnt[lg] == 0) continue;
+      vp8k_parse_tokens(s, arena, imgs, hdrs, mbinfo, coeffs, (const int*)b->d_ids.p + w.ids_off[lg], w.ids_cnt[lg], 1 << lg, w.max_mb_w);
+      ++launches;
+    }
+    CU_TRY(cudaEventRecord(b->ev[2], s), "event");
+    vp8k_reconstruct(s, imgs, hdrs, mbinfo, coeffs, yuv, w.first, w.count, w.max_mb_w, w.max_mb_h);
+    CU_TRY(cudaEventRecord(b->ev[3], s), "event");
+    vp8k_loop_filter(s, imgs, hdrs, mbinfo, yuv, w.first, w.count);
+    CU_TRY(cudaEventRecord(b->ev[4], s), "event");
+    vp8k_emit(s, imgs, hdrs, yuv, (uint8_t*)b->d_out.p, w.first, w.count, w.max_units);
+    CU_TRY(cudaEventRecord(b->ev[5], s), "event");
+    launches += 3;
+    CU_TRY(cudaStreamSynchronize(s), "kernel execution");
+    CU_TRY(cudaGetLastError(), "kernel launch");
+    for (int k = 0; k < 5; ++k) {
+      float ms = 0;
+      CU_TRY(cudaEventElapsedTime(&ms, b->ev[k], b->ev[k + 1]), "cudaEventElapsedTime");
+      acc[k] += ms;
+    }
+  }
+  b->timings.modes_ms = acc[0]; b->timings.tokens_ms = acc[1]; b->timings.recon_ms = acc[2];
+  b->timings.filter_ms = acc[3]; b->timings.emit_ms = acc[4];
+  b->timings.total_ms = acc[0] + acc[1] + acc[2] + acc[3] + acc[4];
+  b->timings.launches = launches;
+  // per-image status words: FrameHdr::status is the first field
+  CU_TRY(cudaMemcpy2DAsync(b->statuses.data(), sizeof(int), hdrs, sizeof(FrameHdr), sizeof(int), m, cudaMemcpyDeviceToHost, s),
+         "D2H status");
+  CU_TRY(cudaStreamSynchronize(s), "status sync");
+  for (int k = 0; k < m; ++k) {
+    WebPBatchItem* it = &b->items[b->img_item[k]];
+    it->status = (VP8StatusCode)b->statuses[k];
+    if (it->status != VP8_STATUS_OK && b->opt.output == WEBP_BATCH_HOST) WebPFreeDecBuffer(&it->config->output);
+  }
+  b->decoded = true;
+  return true;
+}
+
+extern "C" VP8StatusCode WebPBatchDecode(WebPBatch* b) {
+  if (b == NULL) return VP8_STATUS_INVALID_PARAM;
+  bool ok = true;
+  if (b->ctx != nullptr) {
+    b->ctx->mu.lock();
+    ok = batch_decode(b);
+    b->ctx->mu.unlock();
+  }
+  if (!ok) {
+    fprintf(stderr, "libwebp_b200: %s\n", g_last_error);
+    fail_all(b->items, b->n, VP8_STATUS_USER_ABORT);
+    return VP8_STATUS_USER_ABORT;
+  }
+  for (int i = 0; i < b->n; ++i) if (b->items[i].status != VP8_STATUS_OK) return b->items[i].status;
+  return VP8_STATUS_OK;
+}
+
+// Copies every decoded image into its host buffer. Consecutive images whose host buffers are contiguous and
+// tightly packed travel in one cudaMemcpyAsync.
+static bool batch_download(WebPBatch* b) {
+  DeviceCtx* ctx = b->ctx;
+  if (b->opt.output != WEBP_BATCH_HOST || b->imgs.empty()) return true;
+  CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+  cudaStream_t s = ctx->stream;
+  const uint8_t* dout = (const uint8_t*)b->d_out.p;
+  const int m = (int)b->imgs.size();
+  uint8_t* run_host = nullptr; const uint8_t* run_dev = nullptr; size_t run_bytes = 0;
+  auto flush = [&]() -> bool {
+    if (run_bytes > 0) CU_TRY(cudaMemcpyAsync(run_host, run_dev, run_bytes, cudaMemcpyDeviceToHost, s), "D2H pixels");
+    run_bytes = 0;
+    return true;
+  };
+  for (int k = 0; k < m; ++k) {
+    const WebPBatchItem* it = &b->items[b->img_item[k]];
+    if (it->status != VP8_STATUS_OK) continue;
+    const ImgDesc& d = b->imgs[k];
+    const WebPDecBuffer* o = &it->config->output;
+    const uint8_t* src = dout + d.out_off;
+    if (d.csp == MODE_YUV) {
+      if (!flush()) return false;
+      const int w = d.width, h = d.height, uvw = (w + 1) / 2, uvh = (h + 1) / 2;
+      const WebPYUVABuffer* y = &o->u.YUVA;
+      CU_TRY(cudaMemcpy2DAsync(y->y, y->y_stride, src, w, w, h, cudaMemcpyDeviceToHost, s), "D2H Y");
+      CU_TRY(cudaMemcpy2DAsync(y->u, y->u_stride, src + (size_t)w * h, uvw, uvw, uvh, cudaMemcpyDeviceToHost, s), "D2H U");
+      CU_TRY(cudaMemcpy2DAsync(y->v, y->v_stride, src + (size_t)w * h + (size_t)uvw * uvh, uvw, uvw, uvh, cudaMemcpyDeviceToHost, s), "D2H V");
+      continue;
+    }
+    const size_t row = (size_t)d.out_stride;
+    const size_t bytes = row * d.height;
+    if ((size_t)o->u.RGBA.stride == row) {
+      if (run_bytes > 0 && o->u.RGBA.rgba == run_host + run_bytes && src == run_dev + run_bytes) {
+        run_bytes += bytes;
+      } else {
+        if (!flush()) return false;
+        run_host = o->u.RGBA.rgba; run_dev = src; run_bytes = bytes;
+      }
+      if (run_bytes >= ((size_t)256 << 20)) { if (!flush()) return false; }
+    } else {
+      if (!flush()) return false;
+      CU_TRY(cudaMemcpy2DAsync(o->u.RGBA.rgba, (size_t)o->u.RGBA.stride, src, row, row, d.height, cudaMemcpyDeviceToHost, s), "D2H pixels 2D");
+    }
+  }
+  if (!flush()) return false;
+  CU_TRY(cudaStreamSynchronize(s), "download sync");
+  return true;
+}
+
+extern "C" VP8StatusCode WebPBatchDownload(WebPBatch* b) {
+  if (b == NULL || !b->decoded) return VP8_STATUS_INVALID_PARAM;
+  if (b->ctx == nullptr) return VP8_STATUS_OK;
+  b->ctx->mu.lock();
+  const bool ok = batch_download(b);
+  b->ctx->mu.unlock();
+  if (!ok) { fprintf(stderr, "libwebp_b200: %s\n", g_last_error); return VP8_STATUS_USER_ABORT; }
+  return VP8_STATUS_OK;
+}
+
+extern "C" void WebPBatchDestroy(WebPBatch* b) {
+  if (b == NULL) return;
+  DeviceCtx* c = b->ctx;
+  if (c == nullptr) { delete b; return; }
+  c->mu.lock();
+  batch_release(b);
+  c->mu.unlock();
+}
+
+extern "C" int WebPBatchOutput(const WebPBatch* b, int index, WebPBatchPlane* p) {
+  if (b == NULL || p == NULL || index < 0 || index >= b->n || b->plan[index].img < 0) return 0;
+  const ImgDesc& d = b->imgs[b->plan[index].img];
+  uint8_t* base = (uint8_t*)b->d_out.p + d.out_off;
+  memset(p, 0, sizeof(*p));
+  p->width = d.width; p->height = d.height;
+  p->y_or_rgba = base; p->stride = d.out_stride;
+  if (d.csp == MODE_YUV) {
+    const int uvw = (d.width + 1) / 2, uvh = (d.height + 1) / 2;
+    p->u = base + (size_t)d.width * d.height;
+    p->v = base + (size_t)d.width * d.height + (size_t)uvw * uvh;
+    p->uv_stride = uvw;
+  }
+  return 1;
+}
+
+extern "C" int WebPBatchGetTimings(const WebPBatch* b, WebPBatchTimings* t) {
+  if (b == NULL || t == NULL) return 0;
+  *t = b->timings;
+  return 1;
+}
+
+extern "C" VP8StatusCode WebPDecodeBatch(WebPBatchItem* items, int num_items, const WebPBatchOptions* options) {
+  VP8StatusCode st;
+  WebPBatch* b = WebPBatchCreate(items, num_items, options, &st);
+  if (b == NULL) {
+    if (st != VP8_STATUS_OK) return st;
+    return VP8_STATUS_INVALID_PARAM;
+  }
+  st = WebPBatchDecode(b);
+  if (st != VP8_STATUS_USER_ABORT) {
+    const VP8StatusCode dl = WebPBatchDownload(b);
+    if (dl != VP8_STATUS_OK) { fail_all(items, num_items, dl); st = dl; }
+  }
+  WebPBatchDestroy(b);
+  for (int i = 0; i < num_items; ++i) if (items[i].status != VP8_STATUS_OK) return items[i].status;
+  return st;
+}

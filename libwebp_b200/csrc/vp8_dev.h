@@ -1,0 +1,73 @@
+// vp8_dev.h -- device-side data layout of the batched VP8 decoder (shared by host driver and kernels).
+//
+// HBM layout of one wave of images (all arrays batch-wide, indexed through ImgDesc::mb_base):
+//   input arena   : the compressed files exactly as the caller laid them out (one or few H2D copies)
+//   ImgDesc[n]    : host-built geometry + where the VP8 frame of image i starts in the arena
+//   FrameHdr[n]   : written by the header/mode kernel: quantisers, probabilities, filter strengths, partitions
+//   MbInfo[M]     : 16 B per macroblock: 16 sub-block modes (4 bit each), nz codes, flags
+//   coeffs[M*400] : int16, dequantised, raster order inside each 4x4 block; blocks 0-15 Y, 16-19 U, 20-23 V,
+//                   24 = Y2 (the WHT input of i16 macroblocks)                         (800 B / macroblock)
+//   yuv[M*384]    : per image Y (16mb_w x 16mb_h) | U | V, macroblock-padded planes     (1.5 B / pixel)
+//   output arena  : RGBA/RGB/... or Y|U|V per image, tight strides
+#ifndef LIBWEBP_B200_VP8_DEV_H_
+#define LIBWEBP_B200_VP8_DEV_H_
+
+#include <stdint.h>
+
+#define VP8B_COEFFS_PER_MB 400
+#define VP8B_MAX_PARTS 8
+
+// VP8StatusCode values used on the device (include/webp/decode.h).
+#define VP8B_OK 0
+#define VP8B_BITSTREAM_ERROR 3
+#define VP8B_UNSUPPORTED 4
+#define VP8B_NOT_ENOUGH_DATA 7
+
+// ImgDesc::flags
+#define VP8B_FLAG_BYPASS_FILTER 1
+#define VP8B_FLAG_NO_FANCY 2
+
+typedef struct ImgDesc {
+  uint64_t in_off;     // byte offset of the VP8 frame tag inside the input arena
+  uint64_t out_off;    // byte offset of this image's pixels inside the output arena
+  uint32_t vp8_size;   // bytes from the frame tag to the end of the file (reference: io.data_size)
+  uint32_t part0_size; // first-partition length from the frame tag
+  uint32_t mb_base;    // first macroblock of this image in the per-macroblock arrays
+  int32_t out_stride;  // bytes per output row (RGB family) or Y stride (MODE_YUV; U/V stride = (w+1)/2)
+  uint16_t width, height, mb_w, mb_h;
+  uint8_t csp;         // WEBP_CSP_MODE
+  uint8_t flags;
+  uint8_t num_parts;   // host pre-scan of the partition count (launch geometry only; FrameHdr is authoritative)
+  uint8_t dither_f;    // options.dithering_strength mapped to 0..255 (0 = off), see parse_frame_header
+} ImgDesc;
+
+typedef struct FrameHdr {
+  int32_t status;               // VP8B_OK or the failure of the header / mode parse; token parse may overwrite
+  uint8_t filter_type;          // 0 none, 1 simple, 2 normal (after bypass_filtering)
+  uint8_t num_parts;
+  uint8_t use_skip, skip_p;
+  uint8_t update_map;
+  uint8_t seg_prob[3];
+  int16_t dq[4][6];             // per segment: y1 dc/ac, y2 dc/ac, uv dc/ac
+  uint8_t fstr[4][2][4];        // per segment, per is_i4x4: limit, ilevel, inner, hev_thresh
+  uint32_t part_off[VP8B_MAX_PARTS];   // token partitions, relative to the frame tag
+  uint32_t part_size[VP8B_MAX_PARTS];
+  uint8_t prob[4 * 8 * 3 * 11]; // [type][band][ctx][node]
+} FrameHdr;
+
+// MbInfo words (one uint4 per macroblock):
+//   x, y : sixteen 4-bit sub-block modes, mode n at bits 4*(n&7) of word n>>3 (i16: mode in the low nibble of x)
+//   z    : non_zero_y, 2 bits per luma block, block 0 in the top bits (reference: vp8i_dec.h:150-158)
+//   w    : bits 0-15 non_zero_uv | bit16 is_i4x4 | bits17-18 uvmode | bit19 skip | bits20-21 segment
+//          | bit22 has_y2 (i16 with a non-empty Y2 block) | bit23 filter-inner (set by the reconstruction)
+#define MBW_I4X4 (1u << 16)
+#define MBW_UVMODE_SHIFT 17
+#define MBW_SKIP (1u << 19)
+#define MBW_SEG_SHIFT 20
+#define MBW_HAS_Y2 (1u << 22)
+#define MBW_INNER (1u << 23)
+
+// intra modes (RFC 6386 numbering as used by the reference, src/dec/common_dec.h:18-40)
+enum { M_DC = 0, M_TM = 1, M_VE = 2, M_HE = 3, M_RD = 4, M_VR = 5, M_LD = 6, M_VL = 7, M_HD = 8, M_HU = 9 };
+
+#endif  // LIBWEBP_B200_VP8_DEV_H_

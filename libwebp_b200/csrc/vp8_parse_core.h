@@ -1,0 +1,463 @@
+// vp8_parse_core.h -- bitstream side of the batched VP8 decoder: boolean decoder, frame header, intra modes,
+// coefficient tokens. One lane walks one entropy-coded stream; everything it needs lives in registers and
+// in the shared-memory blocks handed in by the kernels of vp8_parse.cu.
+//
+// Replaces, for a whole batch at once:
+//   VP8GetHeaders / ParseSegmentHeader / ParseFilterHeader / ParsePartitions   src/dec/vp8_dec.c:162-395
+//   VP8ParseQuant src/dec/quant_dec.c:62-112, VP8ParseProba src/dec/tree_dec.c:515-538
+//   PrecomputeFilterStrengths src/dec/frame_dec.c:265-313
+//   VP8ParseIntraModeRow / ParseIntraMode src/dec/tree_dec.c:290-367
+//   VP8DecodeMB / ParseResiduals / GetCoeffs / GetLargeValue src/dec/vp8_dec.c:400-635
+//   VP8BitReader src/utils/bit_reader_inl_utils.h:107-157 (state kept as range-1, like the reference)
+//
+// The same source is compiled by nvcc (product) and by g++ with -DVP8_EMU (tests/emu: a host build used only
+// to unit-test this logic where no GPU exists; it is never part of the shipped library).
+#ifndef LIBWEBP_B200_VP8_PARSE_CORE_H_
+#define LIBWEBP_B200_VP8_PARSE_CORE_H_
+
+#include "vp8_dev.h"
+
+#if defined(__CUDACC__) && !defined(VP8_EMU)
+#define VP8_FN __device__ __forceinline__
+#define VP8_TABLE static __constant__ const
+#define VP8_CLZ(x) __clz((int)(x))
+#define VP8_BSWAP(x) __byte_perm((x), 0, 0x0123)
+#else
+#define VP8_FN static inline
+#define VP8_TABLE static const
+#define VP8_CLZ(x) __builtin_clz((unsigned)(x))
+#define VP8_BSWAP(x) __builtin_bswap32(x)
+#endif
+
+#include "vp8_tables.cuh"
+
+VP8_TABLE uint8_t kZigzagPos[16] = { 0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15 };
+// coefficient index -> probability band, as a byte offset (band * 33) into one type's [8][3][11] table
+VP8_TABLE uint16_t kBandOff[17] = { 0, 33, 66, 99, 198, 132, 165, 198, 198, 198, 198, 198, 198, 198, 198, 231, 0 };
+VP8_TABLE uint8_t kCatProb[4][12] = {
+  { 173, 148, 140, 0 }, { 176, 155, 140, 135, 0 }, { 180, 157, 141, 134, 130, 0 },
+  { 254, 254, 243, 230, 196, 177, 153, 140, 133, 130, 129, 0 }
+};
+// sub-block mode tree: node -> {next if bit 0, next if bit 1}; values <= 0 are leaves holding -mode
+VP8_TABLE int8_t kBModeTreeDev[9][2] = {
+  { -M_DC, 1 }, { -M_TM, 2 }, { -M_VE, 3 }, { 4, 6 }, { -M_HE, 5 }, { -M_RD, -M_VR }, { -M_LD, 7 },
+  { -M_VL, 8 }, { -M_HD, -M_HU }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Boolean decoder. `value` is a left-aligned 64-bit window refilled with aligned big-endian 32-bit words;
+// `range` is (true range - 1) in [127,254]. Bits past the end of the stream are whatever follows in the
+// arena (it is padded): any decode that looks at them is reported by bd_eof(), which reproduces the
+// reference's eof_ flag (bit_reader_utils.c:88-101) from the bit position alone.
+struct BoolDec {
+  const uint32_t* wp;   // next aligned word
+  const uint32_t* wend; // first word wholly past the stream: refills from there on shift in zeros
+  uint64_t value;
+  int nbits;            // valid bits in `value`
+  uint32_t range;
+  int last_shift;       // renormalisation shift of the most recent decode
+  int64_t loaded;       // stream bits moved into `value` so far
+  int64_t limit;        // 8*size - 8: a decode starting beyond this bit position reads past the end
+};
+
+VP8_FN uint32_t bd_load_word(BoolDec& d) {
+  const uint32_t* p = d.wp++;
+  return (p < d.wend) ? VP8_BSWAP(*p) : 0u;
+}
+
+VP8_FN void bd_init(BoolDec& d, const uint8_t* start, uint32_t size) {
+  const uintptr_t a = (uintptr_t)start;
+  const int off = (int)(a & 3);
+  d.wp = (const uint32_t*)(a - off);
+  d.wend = (const uint32_t*)((a + size + 3) & ~(uintptr_t)3);
+  d.value = (uint64_t)bd_load_word(d) << (32 + 8 * off);
+  d.nbits = 32 - 8 * off;
+  d.loaded = d.nbits;
+  d.range = 254;
+  d.last_shift = 0;
+  d.limit = 8 * (int64_t)size - 8;
+}
+
+// True when the reference's reader would have raised eof_: some decode started with fewer than 8 real bits
+// left. Positions are monotonic, so testing the most recent decode is enough (and size==0 trips at once).
+VP8_FN int bd_eof(const BoolDec& d) { return (d.loaded - d.nbits - d.last_shift) > d.limit; }
+
+VP8_FN int bd_bit(BoolDec& d, uint32_t prob) {
+  if (d.nbits <= 32) {
+    d.value |= (uint64_t)bd_load_word(d) << (32 - d.nbits);
+    d.nbits += 32;
+    d.loaded += 32;
+  }
+  const uint32_t split = (d.range * prob) >> 8;
+  const uint32_t top = (uint32_t)(d.value >> 56);
+  const int bit = top > split;
+  uint32_t r;   // new true range
+  if (bit) {
+    r = d.range - split;
+    d.value -= (uint64_t)(split + 1) << 56;
+  } else {
+    r = split + 1;
+  }
+  const int shift = VP8_CLZ(r) - 24;
+  d.range = (r << shift) - 1;
+  d.value <<= shift;
+  d.nbits -= shift;
+  d.last_shift = shift;
+  return bit;
+}
+
+VP8_FN uint32_t bd_value(BoolDec& d, int n) {
+  uint32_t v = 0;
+  while (n-- > 0) v |= (uint32_t)bd_bit(d, 0x80) << n;
+  return v;
+}
+
+VP8_FN int bd_signed(BoolDec& d, int n) {
+  const int v = (int)bd_value(d, n);
+  return bd_bit(d, 0x80) ? -v : v;
+}
+
+VP8_FN int clampi(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }
+
+// ---------------------------------------------------------------------------------------------------------
+// Frame header (partition 0 prefix). `frame` points at the 3-byte frame tag. Fills *h; returns the status.
+// The host already validated tag, signature, dimensions and part0_size <= available (vp8_container.c).
+VP8_FN int parse_frame_header(BoolDec& br, const uint8_t* frame, const ImgDesc& im, FrameHdr* h) {
+  const uint8_t* buf = frame + 10 + im.part0_size;         // first byte after partition 0
+  const uint32_t size = im.vp8_size - 10 - im.part0_size;  // bytes left for the token partitions
+  int seg_quant[4] = { 0, 0, 0, 0 }, seg_filter[4] = { 0, 0, 0, 0 };
+  int ref_lf0 = 0, mode_lf0 = 0;
+  int absolute_delta = 1;
+  bd_init(br, frame + 10, im.part0_size);
+  bd_bit(br, 0x80);   // colorspace
+  bd_bit(br, 0x80);   // clamp type
+  // segment header (reference: vp8_dec.c:162-196)
+  h->seg_prob[0] = h->seg_prob[1] = h->seg_prob[2] = 255;
+  h->update_map = 0;
+  const int use_segment = bd_bit(br, 0x80);
+  if (use_segment) {
+    h->update_map = (uint8_t)bd_bit(br, 0x80);
+    if (bd_bit(br, 0x80)) {
+      absolute_delta = bd_bit(br, 0x80);
+      for (int s = 0; s < 4; ++s) seg_quant[s] = bd_bit(br, 0x80) ? bd_signed(br, 7) : 0;
+      for (int s = 0; s < 4; ++s) seg_filter[s] = bd_bit(br, 0x80) ? bd_signed(br, 6) : 0;
+    }
+    if (h->update_map) {
+      for (int s = 0; s < 3; ++s) h->seg_prob[s] = bd_bit(br, 0x80) ? (uint8_t)bd_value(br, 8) : 255u;
+    }
+  }
+  if (bd_eof(br)) return VP8B_BITSTREAM_ERROR;
+  // filter header (vp8_dec.c:237-260)
+  const int simple = bd_bit(br, 0x80);
+  const int level = (int)bd_value(br, 6);
+  const int sharpness = (int)bd_value(br, 3);
+  const int use_lf_delta = bd_bit(br, 0x80);
+  if (use_lf_delta && bd_bit(br, 0x80)) {
+    for (int i = 0; i < 4; ++i) if (bd_bit(br, 0x80)) { const int v = bd_signed(br, 6); if (i == 0) ref_lf0 = v; }
+    for (int i = 0; i < 4; ++i) if (bd_bit(br, 0x80)) { const int v = bd_signed(br, 6); if (i == 0) mode_lf0 = v; }
+  }
+  int filter_type = (level == 0) ? 0 : simple ? 1 : 2;
+  if (bd_eof(br)) return VP8B_BITSTREAM_ERROR;
+  // token partitions (vp8_dec.c:203-234)
+  {
+    const int nparts = 1 << bd_value(br, 2);
+    const uint32_t last = (uint32_t)nparts - 1;
+    if (size < 3 * last) return VP8B_NOT_ENOUGH_DATA;
+    uint32_t off = (uint32_t)(buf - frame) + 3 * last;
+    uint32_t left = size - 3 * last;
+    for (uint32_t p = 0; p < last; ++p) {
+      uint32_t psize = buf[3 * p] | (buf[3 * p + 1] << 8) | (buf[3 * p + 2] << 16);
+      if (psize > left) psize = left;
+      h->part_off[p] = off; h->part_size[p] = psize;
+      off += psize; left -= psize;
+    }
+    h->part_off[last] = off; h->part_size[last] = left;
+    h->num_parts = (uint8_t)nparts;
+    if (!(off < im.vp8_size)) return VP8B_NOT_ENOUGH_DATA;
+  }
+  // quantisers (quant_dec.c:62-112)
+  {
+    const int base = (int)bd_value(br, 7);
+    const int dy1dc = bd_bit(br, 0x80) ? bd_signed(br, 4) : 0;
+    const int dy2dc = bd_bit(br, 0x80) ? bd_signed(br, 4) : 0;
+    const int dy2ac = bd_bit(br, 0x80) ? bd_signed(br, 4) : 0;
+    const int duvdc = bd_bit(br, 0x80) ? bd_signed(br, 4) : 0;
+    const int duvac = bd_bit(br, 0x80) ? bd_signed(br, 4) : 0;
+    int dither_amp = 0;
+    for (int s = 0; s < 4; ++s) {
+      int q = base;
+      if (use_segment) q = seg_quant[s] + (absolute_delta ? 0 : base);
+      else if (s > 0) { for (int k = 0; k < 6; ++k) h->dq[s][k] = h->dq[0][k]; continue; }
+      if (im.dither_f > 0 && q + duvac < 12) {   // VP8InitDithering, frame_dec.c:328-349
+        const int idx = (q + duvac < 0) ? 0 : q + duvac;
+        const int amp = (idx < 3) ? 8 - idx : (idx < 5) ? 4 : (idx < 8) ? 2 : 1;   // kQuantToDitherAmp
+        dither_amp |= (im.dither_f * amp) >> 3;
+      }
+      int y2ac = (kVp8AcQ[clampi(q + dy2ac, 0, 127)] * 101581) >> 16;
+      if (y2ac < 8) y2ac = 8;
+      h->dq[s][0] = kVp8DcQ[clampi(q + dy1dc, 0, 127)];
+      h->dq[s][1] = (int16_t)kVp8AcQ[clampi(q, 0, 127)];
+      h->dq[s][2] = (int16_t)(kVp8DcQ[clampi(q + dy2dc, 0, 127)] * 2);
+      h->dq[s][3] = (int16_t)y2ac;
+      h->dq[s][4] = kVp8DcQ[clampi(q + duvdc, 0, 117)];
+      h->dq[s][5] = (int16_t)kVp8AcQ[clampi(q + duvac, 0, 127)];
+    }
+    // Dithering that would change pixels is not implemented on the device: refuse rather than differ.
+    if (dither_amp != 0) return VP8B_UNSUPPORTED;
+  }
+  bd_bit(br, 0x80);   // update_proba: ignored on key frames
+  // coefficient probabilities (tree_dec.c:515-538)
+  for (int i = 0; i < 1056; ++i) {
+    h->prob[i] = bd_bit(br, kVp8CoeffUpdateProba[i]) ? (uint8_t)bd_value(br, 8) : kVp8CoeffProba0[i];
+  }
+  h->use_skip = (uint8_t)bd_bit(br, 0x80);
+  h->skip_p = h->use_skip ? (uint8_t)bd_value(br, 8) : 0;
+  // loop-filter strengths per segment and block type (frame_dec.c:265-313)
+  if (im.flags & VP8B_FLAG_BYPASS_FILTER) filter_type = 0;   // VP8EnterCritical, frame_dec.c:557-560
+  h->filter_type = (uint8_t)filter_type;
+  for (int s = 0; s < 4; ++s) {
+    int base_level = level;
+    if (use_segment) base_level = seg_filter[s] + (absolute_delta ? 0 : level);
+    for (int i4 = 0; i4 <= 1; ++i4) {
+      int lvl = base_level;
+      if (use_lf_delta) lvl += ref_lf0 + (i4 ? mode_lf0 : 0);
+      lvl = clampi(lvl, 0, 63);
+      int limit = 0, ilevel = 0, hev = 0;
+      if (lvl > 0) {
+        ilevel = lvl;
+        if (sharpness > 0) {
+          ilevel >>= (sharpness > 4) ? 2 : 1;
+          if (ilevel > 9 - sharpness) ilevel = 9 - sharpness;
+        }
+        if (ilevel < 1) ilevel = 1;
+        limit = 2 * lvl + ilevel;
+        hev = (lvl >= 40) ? 2 : (lvl >= 15) ? 1 : 0;
+      }
+      h->fstr[s][i4][0] = (uint8_t)limit; h->fstr[s][i4][1] = (uint8_t)ilevel;
+      h->fstr[s][i4][2] = (uint8_t)i4;    h->fstr[s][i4][3] = (uint8_t)hev;
+    }
+  }
+  return VP8B_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Intra modes of the whole frame (partition 0, strictly serial). `top` = mb_w words of scratch holding the
+// four bottom sub-block modes of the macroblock row above (one byte each). Writes MbInfo x,y,w.
+// Returns VP8B_OK or VP8B_NOT_ENOUGH_DATA (checked once per macroblock row, like vp8_dec.c:651-654).
+VP8_FN int parse_intra_modes(BoolDec& br, const ImgDesc& im, const FrameHdr* h, uint32_t* top, uint32_t* mbinfo /* 4 words per MB */) {
+  const int mb_w = im.mb_w, mb_h = im.mb_h;
+  const int update_map = h->update_map, use_skip = h->use_skip, skip_p = h->skip_p;
+  const uint32_t sp0 = h->seg_prob[0], sp1 = h->seg_prob[1], sp2 = h->seg_prob[2];
+  for (int mx = 0; mx < mb_w; ++mx) top[mx] = 0;   // M_DC == 0
+  for (int my = 0; my < mb_h; ++my) {
+    uint32_t left = 0;   // four left modes, byte y
+    for (int mx = 0; mx < mb_w; ++mx) {
+      uint32_t* out = mbinfo + 4 * ((size_t)my * mb_w + mx);
+      uint32_t w = 0, m0 = 0, m1 = 0;
+      if (update_map) {
+        const uint32_t seg = !bd_bit(br, sp0) ? (uint32_t)bd_bit(br, sp1) : (uint32_t)bd_bit(br, sp2) + 2u;
+        w |= seg << MBW_SEG_SHIFT;
+      }
+      if (use_skip && bd_bit(br, skip_p)) w |= MBW_SKIP;
+      if (bd_bit(br, 145)) {   // i16
+        const uint32_t ymode = bd_bit(br, 156) ? (bd_bit(br, 128) ? M_TM : M_HE) : (bd_bit(br, 163) ? M_VE : M_DC);
+        m0 = ymode;
+        top[mx] = ymode * 0x01010101u;
+        left = ymode * 0x01010101u;
+      } else {
+        uint32_t t = top[mx];
+        w |= MBW_I4X4;
+        for (int y = 0; y < 4; ++y) {
+          uint32_t ymode = (left >> (8 * y)) & 0xff;
+          for (int x = 0; x < 4; ++x) {
+            const uint32_t tm = (t >> (8 * x)) & 0xff;
+            const uint8_t* pr = &kVp8BModeProba[(tm * 10 + ymode) * 9];
+            int node = 0;
+            do { node = kBModeTreeDev[node][bd_bit(br, pr[node])]; } while (node > 0);
+            ymode = (uint32_t)(-node);
+            t = (t & ~(0xffu << (8 * x))) | (ymode << (8 * x));
+            const int n = y * 4 + x;
+            if (n < 8) m0 |= ymode << (4 * n); else m1 |= ymode << (4 * (n - 8));
+          }
+          left = (left & ~(0xffu << (8 * y))) | (ymode << (8 * y));
+        }
+        top[mx] = t;
+      }
+      const uint32_t uvmode = !bd_bit(br, 142) ? M_DC : !bd_bit(br, 114) ? M_VE : bd_bit(br, 183) ? M_TM : M_HE;
+      w |= uvmode << MBW_UVMODE_SHIFT;
+      out[0] = m0; out[1] = m1; out[2] = 0; out[3] = w;
+    }
+    if (bd_eof(br)) return VP8B_NOT_ENOUGH_DATA;
+  }
+  return VP8B_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Coefficient tokens.
+VP8_FN int large_value(BoolDec& d, const uint8_t* p) {
+  int v;
+  if (!bd_bit(d, p[3])) {
+    v = !bd_bit(d, p[4]) ? 2 : 3 + bd_bit(d, p[5]);
+  } else if (!bd_bit(d, p[6])) {
+    if (!bd_bit(d, p[7])) {
+      v = 5 + bd_bit(d, 159);
+    } else {
+      v = 7 + 2 * bd_bit(d, 165);
+      v += bd_bit(d, 145);
+    }
+  } else {
+    const int b1 = bd_bit(d, p[8]);
+    const int b0 = bd_bit(d, p[9 + b1]);
+    const int cat = 2 * b1 + b0;
+    v = 0;
+    for (const uint8_t* tab = kCatProb[cat]; *tab; ++tab) v += v + bd_bit(d, *tab);
+    v += 3 + (8 << cat);
+  }
+  return v;
+}
+
+// One 4x4 block. `probs` = this block type's [8 bands][3 ctx][11] table (shared memory), `out` = 16 int16 in
+// HBM (pre-zeroed). Returns nz = index of the last decoded coefficient + 1 (GetCoeffs, vp8_dec.c:443-469);
+// *dc_nz says whether the stored value at position 0 is non-zero after the int16 truncation.
+VP8_FN int parse_block(BoolDec& d, const uint8_t* probs, int ctx, int dq_dc, int dq_ac, int n, int16_t* out, int* dc_nz) {
+  const uint8_t* p = probs + kBandOff[n] + ctx * 11;
+  for (; n < 16; ++n) {
+    if (!bd_bit(d, p[0])) return n;
+    while (!bd_bit(d, p[1])) {
+      p = probs + kBandOff[++n];
+      if (n == 16) return 16;
+    }
+    int v;
+    const uint8_t* pn = probs + kBandOff[n + 1];
+    if (!bd_bit(d, p[2])) {
+      v = 1;
+      pn += 11;
+    } else {
+      v = large_value(d, p);
+      pn += 22;
+    }
+    p = pn;
+    if (bd_bit(d, 0x80)) v = -v;
+    const int16_t c = (int16_t)(v * (n > 0 ? dq_ac : dq_dc));
+    out[kZigzagPos[n]] = c;
+    if (n == 0) *dc_nz = (c != 0);
+  }
+  return 16;
+}
+
+// Progress hand-off between the token partitions of one image: partition p publishes how many macroblocks
+// it has finished (counted over all its rows); the partition owning the next row waits on it. No-ops for a
+// single partition. Defined by the including translation unit.
+#ifndef VP8_WAIT_PROGRESS
+#define VP8_WAIT_PROGRESS(ptr, need) ((void)0)
+#define VP8_PUBLISH_PROGRESS(ptr, val) ((void)0)
+#endif
+
+// Non-zero context of one macroblock column / row: bits 0-3 luma, 4-5 U, 6-7 V, bit 8 = Y2 (nz_dc).
+// State of one token partition of an image; it parses macroblock rows part, part+P, ... (vp8_dec.c:649-650).
+struct TokenPart {
+  BoolDec d;
+  int done;     // macroblocks finished by this partition (published to the partition owning the next row)
+  int status;   // VP8B_OK or VP8B_NOT_ENOUGH_DATA
+};
+
+VP8_FN void token_part_init(TokenPart& tp, const uint8_t* frame, const FrameHdr* h, int part) {
+  bd_init(tp.d, frame + h->part_off[part], h->part_size[part]);
+  tp.done = 0;
+  tp.status = VP8B_OK;
+}
+
+// One macroblock row `my` of partition `part` (= my % P).
+//   probs     : 1056 bytes, this frame's coefficient probabilities (shared memory)
+//   topctx    : (P+1) rows x mb_w uint16 ring of per-column contexts (shared by the image's partitions)
+//   progress  : P counters (shared); see above
+// Writes coefficients and MbInfo z / w.
+VP8_FN void parse_token_row(TokenPart& tp, const ImgDesc& im, const FrameHdr* h, int part, int my, const uint8_t* probs,
+                            uint16_t* topctx, volatile int* progress, uint32_t* mbinfo, int16_t* coeffs) {
+  const int P = h->num_parts, mb_w = im.mb_w;
+  const int use_skip = h->use_skip;
+  BoolDec& d = tp.d;
+  const uint16_t* trow = topctx + (size_t)((my + P) % (P + 1)) * mb_w;   // written by row my-1
+  uint16_t* orow = topctx + (size_t)(my % (P + 1)) * mb_w;
+  const int prev = (part + P - 1) % P;                // partition that owns row my-1
+  const int prev_rows = (my - 1 - prev) / P;          // rows it finished before row my-1 (meaningful if my>0)
+  uint32_t lctx = 0;
+  for (int mx = 0; mx < mb_w; ++mx) {
+    const size_t idx = (size_t)my * mb_w + mx;
+    uint32_t* info = mbinfo + 4 * idx;
+    uint32_t w = info[3];
+    uint32_t tctx = 0;
+    if (my > 0) {
+      if (P > 1) VP8_WAIT_PROGRESS(&progress[prev], prev_rows * mb_w + mx + 1);
+      tctx = trow[mx];
+    }
+    uint32_t nzy = 0, nzuv = 0;
+    const int is_i4 = (w & MBW_I4X4) != 0;
+    if (!(use_skip && (w & MBW_SKIP))) {
+      const int16_t* q = h->dq[(w >> MBW_SEG_SHIFT) & 3];
+      int16_t* dst = coeffs + idx * VP8B_COEFFS_PER_MB;
+      int first = 0;
+      const uint8_t* yprobs = probs + 3 * 264;
+      if (!is_i4) {
+        int dcnz = 0;
+        const int ctx = (int)((tctx >> 8) & 1) + (int)((lctx >> 8) & 1);
+        const int nz = parse_block(d, probs + 1 * 264, ctx, q[2], q[3], 0, dst + 24 * 16, &dcnz);
+        const uint32_t f = (nz > 0) ? 0x100u : 0u;
+        tctx = (tctx & 0xffu) | f;
+        lctx = (lctx & 0xffu) | f;
+        if (nz > 0) w |= MBW_HAS_Y2;
+        first = 1;
+        yprobs = probs;
+      }
+      uint32_t tnz = tctx & 0x0f, lnz = lctx & 0x0f;
+      for (int y = 0; y < 4; ++y) {
+        uint32_t l = lnz & 1;
+        for (int x = 0; x < 4; ++x) {
+          int dcnz = 0;
+          const int nz = parse_block(d, yprobs, (int)(l + (tnz & 1)), q[0], q[1], first, dst, &dcnz);
+          l = (nz > first);
+          tnz = (tnz >> 1) | (l << 7);
+          nzy = (nzy << 2) | (uint32_t)((nz > 3) ? 3 : (nz > 1) ? 2 : dcnz);
+          dst += 16;
+        }
+        tnz >>= 4;
+        lnz = (lnz >> 1) | (l << 7);
+      }
+      uint32_t out_t = tnz, out_l = lnz >> 4;
+      for (int ch = 0; ch < 4; ch += 2) {
+        uint32_t acc = 0;
+        tnz = (tctx >> (4 + ch)) & 0x0f;
+        lnz = (lctx >> (4 + ch)) & 0x0f;
+        for (int y = 0; y < 2; ++y) {
+          uint32_t l = lnz & 1;
+          for (int x = 0; x < 2; ++x) {
+            int dcnz = 0;
+            const int nz = parse_block(d, probs + 2 * 264, (int)(l + (tnz & 1)), q[4], q[5], 0, dst, &dcnz);
+            l = (nz > 0);
+            tnz = ((tnz >> 1) | (l << 3)) & 0xff;
+            acc = (acc << 2) | (uint32_t)((nz > 3) ? 3 : (nz > 1) ? 2 : dcnz);
+            dst += 16;
+          }
+          tnz >>= 2;
+          lnz = ((lnz >> 1) | (l << 5)) & 0xff;
+        }
+        nzuv |= acc << (4 * ch);
+        out_t |= ((tnz << 4) << ch) & 0xff;
+        out_l |= ((lnz & 0xf0) << ch) & 0xff;
+      }
+      tctx = (tctx & 0x100u) | (out_t & 0xff);
+      lctx = (lctx & 0x100u) | (out_l & 0xff);
+    } else {
+      tctx &= is_i4 ? 0x100u : 0u;
+      lctx &= is_i4 ? 0x100u : 0u;
+    }
+    info[2] = nzy;
+    info[3] = (w & 0xffff0000u) | nzuv;
+    orow[mx] = (uint16_t)tctx;
+    ++tp.done;
+    if (P > 1) VP8_PUBLISH_PROGRESS(&progress[part], tp.done);
+    if (bd_eof(d)) tp.status = VP8B_NOT_ENOUGH_DATA;   // keep going: later partitions wait on our progress
+  }
+}
+
+#endif  // LIBWEBP_B200_VP8_PARSE_CORE_H_

@@ -1,0 +1,576 @@
+// vp8_pixel_core.h -- pixel side of the batched VP8 decoder: inverse WHT/DCT + intra prediction (one warp per
+// macroblock inside a lag-2 macroblock wavefront), the in-loop deblocking filter (same wavefront shape), and
+// the output stage (fancy chroma upsampling + YUV->RGB, or plane copies).
+//
+// Replaces, for a whole batch at once:
+//   ReconstructRow src/dec/frame_dec.c:71-196; TransformOne/AC3/DC/UV/DCUV/WHT src/dsp/dec.c:44-162;
+//   VP8PredLuma4/16, VP8PredChroma8 src/dsp/dec.c:173-474
+//   DoFilter/FilterRow src/dec/frame_dec.c:203-260; Simple*/[VH]Filter* src/dsp/dec.c:484-693
+//   EmitFancyRGB/EmitSampledRGB/EmitYUV src/dec/io_dec.c:25-109; UPSAMPLE_FUNC src/dsp/upsampling.c:37-93;
+//   VP8YuvToRgb* src/dsp/yuv.h:59-144
+//
+// Lanes of a warp cooperate through a per-warp shared-memory workspace; every exchange point is a warp
+// barrier (WARP_PHASE ... WARP_PHASE_END). Under -DVP8_EMU (tests/emu) a phase becomes a loop over 32 lanes
+// so the same logic runs on a host without a GPU for unit tests; that build is never shipped.
+#ifndef LIBWEBP_B200_VP8_PIXEL_CORE_H_
+#define LIBWEBP_B200_VP8_PIXEL_CORE_H_
+
+#include "vp8_dev.h"
+
+#if defined(__CUDACC__) && !defined(VP8_EMU)
+#define VP8_PFN __device__ __forceinline__
+#define VP8_PTABLE static __constant__ const
+#define WARP_PHASE(lane) { const int lane = (int)(threadIdx.x & 31);
+#define WARP_PHASE_END } __syncwarp();
+#else
+#define VP8_PFN static inline
+#define VP8_PTABLE static const
+#define WARP_PHASE(lane) for (int lane = 0; lane < 32; ++lane) {
+#define WARP_PHASE_END }
+struct uint2 { uint32_t x, y; };
+struct uint4 { uint32_t x, y, z, w; };
+#endif
+
+VP8_PFN int clip8i(int v) { return v < 0 ? 0 : v > 255 ? 255 : v; }
+VP8_PFN int mul1(int a) { return ((a * 20091) >> 16) + a; }
+VP8_PFN int mul2(int a) { return (a * 35468) >> 16; }
+
+// ---------------------------------------------------------------------------------------------------------
+// Reconstruction workspace of one warp (shared memory). Tile coordinates: luma pixel (r, c) of the macroblock
+// lives at y[(r + 1) * 32 + c + 4]; row 0 is the row above, column 3 the column to the left, columns 20-23
+// the four pixels above-right (replicated at rows 4, 8, 12 for the right-most sub-blocks, frame_dec.c:131-141).
+// Chroma: u at uv[(r + 1) * 32 + c + 4], v at uv[(r + 1) * 32 + c + 20].
+struct ReconWs {
+  int16_t coef[VP8B_COEFFS_PER_MB];   // 800 B, 16-byte aligned
+  uint8_t y[17 * 32];
+  uint8_t uv[9 * 32];
+  int32_t tmp[2 * 16];                // first IDCT pass of the two blocks in flight
+  uint8_t edge[16];                   // 4x4 predictor edge: L L L K J I X A B C D E F G H H
+  uint32_t nzy;                       // running non_zero_y (DC codes of i16 blocks get filled in here)
+  uint32_t pad[3];
+};
+
+// Wavefront context of one image (shared memory of the block that owns the image): the unfiltered pixels each
+// macroblock needs from its neighbours. Lag 2 between rows keeps every entry valid exactly while it is read.
+struct ReconCtx {
+  uint8_t* top_y;    // 16 * mb_w : bottom row of the macroblock above, per column
+  uint8_t* top_u;    // 8 * mb_w
+  uint8_t* top_v;    // 8 * mb_w
+  uint8_t* left_y;   // 16 * mb_h : right column of the macroblock to the left, per row
+  uint8_t* left_u;   // 8 * mb_h
+  uint8_t* left_v;   // 8 * mb_h
+  uint8_t* corner;   // 4 * mb_h : y,u,v pixel above-left of the next macroblock of the row
+};
+
+#define recon_ctx_bytes(mb_w, mb_h) ((size_t)32 * (size_t)(mb_w) + (size_t)36 * (size_t)(mb_h))
+
+VP8_PFN void recon_ctx_bind(ReconCtx& c, uint8_t* mem, int mb_w, int mb_h) {
+  c.top_y = mem; c.top_u = c.top_y + 16 * mb_w; c.top_v = c.top_u + 8 * mb_w;
+  c.left_y = c.top_v + 8 * mb_w; c.left_u = c.left_y + 16 * mb_h; c.left_v = c.left_u + 8 * mb_h;
+  c.corner = c.left_v + 8 * mb_h;
+}
+
+// 4x4 predictors as (kind, first edge index) per pixel: 0x80 | a -> (E[a]+E[a+1]+1)>>1, else
+// (E[a]+2E[a+1]+E[a+2]+2)>>2, over the edge L L L K J I X A B C D E F G H H. Rows = modes VE..HU (2..9).
+VP8_PTABLE uint8_t kPred4[8][16] = {
+  /* VE */ { 6, 7, 8, 9, 6, 7, 8, 9, 6, 7, 8, 9, 6, 7, 8, 9 },
+  /* HE */ { 4, 4, 4, 4, 3, 3, 3, 3, 2, 2, 2, 2, 1, 1, 1, 1 },
+  /* RD */ { 5, 6, 7, 8, 4, 5, 6, 7, 3, 4, 5, 6, 2, 3, 4, 5 },
+  /* VR */ { 0x86, 0x87, 0x88, 0x89, 5, 6, 7, 8, 4, 0x86, 0x87, 0x88, 3, 5, 6, 7 },
+  /* LD */ { 7, 8, 9, 10, 8, 9, 10, 11, 9, 10, 11, 12, 10, 11, 12, 13 },
+  /* VL */ { 0x87, 0x88, 0x89, 0x8a, 7, 8, 9, 10, 0x88, 0x89, 0x8a, 11, 8, 9, 10, 12 },
+  /* HD */ { 0x85, 5, 6, 7, 0x84, 4, 0x85, 5, 0x83, 3, 0x84, 4, 0x82, 2, 0x83, 3 },
+  /* HU */ { 0x84, 3, 0x83, 2, 0x83, 2, 0x82, 1, 0x82, 1, 0, 0, 0, 0, 0, 0 }
+};
+
+// First IDCT pass of block `blk` by 16 lanes (l = 0..15): input column c = l >> 2, output k = l & 3
+// (TransformOne_C vertical pass, dsp/dec.c:48-59).
+VP8_PFN void idct_pass1(const int16_t* in, int l, int32_t* tmp) {
+  const int c = l >> 2, k = l & 3;
+  const int i0 = in[c], i1 = in[4 + c], i2 = in[8 + c], i3 = in[12 + c];
+  const int a = i0 + i2, b = i0 - i2;
+  const int cc = mul2(i1) - mul1(i3), d = mul1(i1) + mul2(i3);
+  tmp[4 * c + k] = (k == 0) ? a + d : (k == 1) ? b + cc : (k == 2) ? b - cc : a - d;
+}
+
+// Second pass for pixel (px, py): residual to add to the prediction, already >> 3 (dsp/dec.c:67-80).
+VP8_PFN int idct_pass2(const int32_t* tmp, int px, int py) {
+  const int t0 = tmp[py], t1 = tmp[4 + py], t2 = tmp[8 + py], t3 = tmp[12 + py];
+  const int dc = t0 + 4;
+  const int a = dc + t2, b = dc - t2;
+  const int c = mul2(t1) - mul1(t3), d = mul1(t1) + mul2(t3);
+  const int r = (px == 0) ? a + d : (px == 1) ? b + c : (px == 2) ? b - c : a - d;
+  return r >> 3;
+}
+
+// 16x16 / 8x8 prediction of one pixel. t = pointer to the block origin inside a 32-byte-stride tile.
+// `mode` after the border substitution of CheckMode (frame_dec.c:28-37): 0 DC, 1 TM, 2 V, 3 H, 4 DC without
+// top, 5 DC without left, 6 DC without both. `dc` = precomputed DC value for the DC modes.
+VP8_PFN int pred_big_pixel(const uint8_t* t, int mode, int dc, int x, int y) {
+  switch (mode) {
+    case 1: return clip8i((int)t[x - 32] + (int)t[y * 32 - 1] - (int)t[-33]);
+    case 2: return t[x - 32];
+    case 3: return t[y * 32 - 1];
+    default: return dc;
+  }
+}
+
+VP8_PFN int dc_big(const uint8_t* t, int mode, int size) {   // dsp/dec.c:215-244, 445-474
+  const int sh = (size == 16) ? 4 : 3;
+  int s = 0;
+  if (mode == 0) {
+    for (int i = 0; i < size; ++i) s += t[i - 32] + t[i * 32 - 1];
+    return (s + size) >> (sh + 1);
+  } else if (mode == 4) {
+    for (int i = 0; i < size; ++i) s += t[i * 32 - 1];
+    return (s + (size >> 1)) >> sh;
+  } else if (mode == 5) {
+    for (int i = 0; i < size; ++i) s += t[i - 32];
+    return (s + (size >> 1)) >> sh;
+  }
+  return 0x80;
+}
+
+VP8_PFN int check_mode(int mx, int my, int mode) {
+  if (mode == M_DC) return (mx == 0) ? ((my == 0) ? 6 : 5) : ((my == 0) ? 4 : 0);
+  return mode;
+}
+
+// Reconstructs macroblock (mx, my) of one image with one warp. `info` = this macroblock's MbInfo (4 words),
+// `coeffs` = its 400 coefficients in HBM, planes = the image's padded Y/U/V in HBM (write-only here).
+// Also finalises MbInfo: DC codes of i16 blocks and the filter-inner bit (vp8_dec.c:629-633).
+VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, int mb_w, uint32_t* info,
+                              const int16_t* coeffs, uint8_t* yplane, uint8_t* uplane, uint8_t* vplane) {
+  const uint32_t w = info[3];
+  const uint32_t m0 = info[0], m1 = info[1];
+  const uint32_t nzy_in = info[2];
+  const uint32_t nzuv = w & 0xffffu;
+  const int is_i4 = (w & MBW_I4X4) != 0;
+  const int has_y2 = (w & MBW_HAS_Y2) != 0;
+  const int any_coef = (nzy_in | nzuv) != 0 || has_y2;
+  const int ys = 16 * mb_w, uvs = 8 * mb_w;
+
+  // ---- phase 0: coefficients HBM -> shared, neighbour pixels -> tile
+  WARP_PHASE(lane)
+    if (any_coef) {
+      const uint4* src = (const uint4*)coeffs;
+      uint4* dst = (uint4*)ws.coef;
+      dst[lane] = src[lane];
+      if (lane < 18) dst[32 + lane] = src[32 + lane];
+    }
+    if (lane == 0) ws.nzy = nzy_in;
+    if (lane < 16) {
+      ws.y[4 + lane] = (my > 0) ? cx.top_y[16 * mx + lane] : 127;
+      ws.y[(lane + 1) * 32 + 3] = (mx > 0) ? cx.left_y[16 * my + lane] : 129;
+    } else if (lane < 20) {
+      const int k = lane - 16;
+      ws.y[20 + k] = (my > 0) ? ((mx < mb_w - 1) ? cx.top_y[16 * (mx + 1) + k] : cx.top_y[16 * mx + 15]) : 127;
+    } else if (lane == 20) {
+      ws.y[3] = (my > 0) ? ((mx > 0) ? cx.corner[4 * my + 0] : 129) : 127;
+      ws.uv[3] = (my > 0) ? ((mx > 0) ? cx.corner[4 * my + 1] : 129) : 127;
+      ws.uv[19] = (my > 0) ? ((mx > 0) ? cx.corner[4 * my + 2] : 129) : 127;
+    } else if (lane >= 24) {
+      const int k = lane - 24;
+      ws.uv[4 + k] = (my > 0) ? cx.top_u[8 * mx + k] : 127;
+      ws.uv[20 + k] = (my > 0) ? cx.top_v[8 * mx + k] : 127;
+      ws.uv[(k + 1) * 32 + 3] = (mx > 0) ? cx.left_u[8 * my + k] : 129;
+      ws.uv[(k + 1) * 32 + 19] = (mx > 0) ? cx.left_v[8 * my + k] : 129;
+    }
+  WARP_PHASE_END
+
+  // ---- phase 1: inverse WHT of the Y2 block into the 16 luma DCs (dsp/dec.c:137-162)
+  if (!is_i4 && has_y2) {
+    WARP_PHASE(lane)
+      if (lane < 4) {
+        const int16_t* in = ws.coef + 24 * 16;
+        const int i = lane;
+        const int a0 = in[0 + i] + in[12 + i], a1 = in[4 + i] + in[8 + i];
+        const int a2 = in[4 + i] - in[8 + i], a3 = in[0 + i] - in[12 + i];
+        ws.tmp[0 + i] = a0 + a1; ws.tmp[8 + i] = a0 - a1; ws.tmp[4 + i] = a3 + a2; ws.tmp[12 + i] = a3 - a2;
+      }
+    WARP_PHASE_END
+    WARP_PHASE(lane)
+      if (lane < 4) {
+        const int i = lane;
+        const int dc = ws.tmp[0 + i * 4] + 3;
+        const int a0 = dc + ws.tmp[3 + i * 4], a1 = ws.tmp[1 + i * 4] + ws.tmp[2 + i * 4];
+        const int a2 = ws.tmp[1 + i * 4] - ws.tmp[2 + i * 4], a3 = dc - ws.tmp[3 + i * 4];
+        ws.coef[(4 * i + 0) * 16] = (int16_t)((a0 + a1) >> 3);
+        ws.coef[(4 * i + 1) * 16] = (int16_t)((a3 + a2) >> 3);
+        ws.coef[(4 * i + 2) * 16] = (int16_t)((a0 - a1) >> 3);
+        ws.coef[(4 * i + 3) * 16] = (int16_t)((a3 - a2) >> 3);
+      }
+    WARP_PHASE_END
+    WARP_PHASE(lane)
+      if (lane == 0) {   // a block whose tokens held no AC gets code 1 iff its DC is non-zero (vp8_dec.c:511-515)
+        uint32_t nzy = ws.nzy;
+        for (int n = 0; n < 16; ++n) {
+          const int sh = 30 - 2 * n;
+          if (((nzy >> sh) & 3) == 0 && ws.coef[n * 16] != 0) nzy |= 1u << sh;
+        }
+        ws.nzy = nzy;
+      }
+    WARP_PHASE_END
+  }
+  const uint32_t nzy = ws.nzy;
+
+  // ---- phase 2: luma
+  if (is_i4) {
+    WARP_PHASE(lane)
+      if (lane < 12) ws.y[(4 + 4 * (lane >> 2)) * 32 + 20 + (lane & 3)] = ws.y[20 + (lane & 3)];
+    WARP_PHASE_END
+    for (int n = 0; n < 16; ++n) {
+      const int bx = n & 3, by = n >> 2;
+      const int mode = (int)(((n < 8) ? (m0 >> (4 * n)) : (m1 >> (4 * (n - 8)))) & 15);
+      const int coded = (int)((nzy >> (30 - 2 * n)) & 3);
+      uint8_t* const t = ws.y + (by * 4 + 1) * 32 + bx * 4 + 4;   // block origin in the tile
+      WARP_PHASE(lane)
+        if (lane < 16) {
+          const int i = lane;   // edge element: L L L K J I X A..H H
+          int off;
+          if (i < 6) off = ((i < 3) ? 3 : 5 - i) * 32 - 1;
+          else if (i == 6) off = -33;
+          else off = -32 + ((i - 7 < 7) ? i - 7 : 7);
+          ws.edge[i] = t[off];
+          if (coded) idct_pass1(ws.coef + n * 16, lane, ws.tmp);
+        }
+      WARP_PHASE_END
+      WARP_PHASE(lane)
+        if (lane < 16) {
+          const int px = lane & 3, py = lane >> 2;
+          const uint8_t* e = ws.edge;
+          int p;
+          if (mode == M_DC) {
+            p = (e[2] + e[3] + e[4] + e[5] + e[7] + e[8] + e[9] + e[10] + 4) >> 3;
+          } else if (mode == M_TM) {
+            p = clip8i((int)e[7 + px] + (int)e[5 - py] - (int)e[6]);
+          } else {
+            const int k = kPred4[mode - 2][lane];
+            const int a = k & 0x7f;
+            p = (k & 0x80) ? (e[a] + e[a + 1] + 1) >> 1 : (e[a] + 2 * e[a + 1] + e[a + 2] + 2) >> 2;
+          }
+          if (coded) p = clip8i(p + idct_pass2(ws.tmp, px, py));
+          t[py * 32 + px] = (uint8_t)p;
+        }
+      WARP_PHASE_END
+    }
+  } else {
+    const int mode = check_mode(mx, my, (int)(m0 & 15));
+    uint8_t* const t = ws.y + 32 + 4;
+    WARP_PHASE(lane)
+      const int dc = dc_big(t, mode, 16);
+      const int r = lane >> 1, c0 = (lane & 1) * 8;
+      uint8_t v[8];
+      for (int k = 0; k < 8; ++k) v[k] = (uint8_t)pred_big_pixel(t, mode, dc, c0 + k, r);
+      // reads above touch only the border row/column, writes only the block interior: no hazard in a phase
+      for (int k = 0; k < 8; ++k) t[r * 32 + c0 + k] = v[k];
+    WARP_PHASE_END
+    if (nzy != 0) {
+      for (int pair = 0; pair < 8; ++pair) {
+        WARP_PHASE(lane)
+          const int n = 2 * pair + (lane >> 4);
+          if ((nzy >> (30 - 2 * n)) & 3) idct_pass1(ws.coef + n * 16, lane & 15, ws.tmp + 16 * (lane >> 4));
+        WARP_PHASE_END
+        WARP_PHASE(lane)
+          const int n = 2 * pair + (lane >> 4);
+          if ((nzy >> (30 - 2 * n)) & 3) {
+            const int px = lane & 3, py = (lane >> 2) & 3;
+            uint8_t* const b = t + (n >> 2) * 4 * 32 + (n & 3) * 4;
+            b[py * 32 + px] = (uint8_t)clip8i(b[py * 32 + px] + idct_pass2(ws.tmp + 16 * (lane >> 4), px, py));
+          }
+        WARP_PHASE_END
+      }
+    }
+  }
+
+  // ---- phase 3: chroma (lanes 0-15 U, 16-31 V)
+  {
+    const int mode = check_mode(mx, my, (int)((w >> MBW_UVMODE_SHIFT) & 3));
+    WARP_PHASE(lane)
+      uint8_t* const t = ws.uv + 32 + 4 + 16 * (lane >> 4);
+      const int dc = dc_big(t, mode, 8);
+      const int r = (lane & 15) >> 1, c0 = (lane & 1) * 4;
+      uint8_t v[4];
+      for (int k = 0; k < 4; ++k) v[k] = (uint8_t)pred_big_pixel(t, mode, dc, c0 + k, r);
+      for (int k = 0; k < 4; ++k) t[r * 32 + c0 + k] = v[k];
+    WARP_PHASE_END
+    if (nzuv != 0) {
+      for (int k = 0; k < 4; ++k) {
+        WARP_PHASE(lane)
+          const int ch = lane >> 4;   // 0 U, 1 V
+          const int code = (int)((nzuv >> (8 * ch + 6 - 2 * k)) & 3);
+          if (code) idct_pass1(ws.coef + (16 + 4 * ch + k) * 16, lane & 15, ws.tmp + 16 * ch);
+        WARP_PHASE_END
+        WARP_PHASE(lane)
+          const int ch = lane >> 4;
+          const int code = (int)((nzuv >> (8 * ch + 6 - 2 * k)) & 3);
+          if (code) {
+            const int px = lane & 3, py = (lane >> 2) & 3;
+            uint8_t* const b = ws.uv + 32 + 4 + 16 * ch + (k >> 1) * 4 * 32 + (k & 1) * 4;
+            b[py * 32 + px] = (uint8_t)clip8i(b[py * 32 + px] + idct_pass2(ws.tmp + 16 * ch, px, py));
+          }
+        WARP_PHASE_END
+      }
+    }
+  }
+
+  // ---- phase 4: tile -> HBM planes, neighbour context for the macroblocks to the right and below, MbInfo
+  WARP_PHASE(lane)
+    if (lane < 16) {
+      const uint32_t* row = (const uint32_t*)(ws.y + (lane + 1) * 32 + 4);
+      uint4 v; v.x = row[0]; v.y = row[1]; v.z = row[2]; v.w = row[3];
+      *(uint4*)(yplane + (size_t)(16 * my + lane) * ys + 16 * mx) = v;
+      cx.top_y[16 * mx + lane] = ws.y[16 * 32 + 4 + lane];
+      cx.left_y[16 * my + lane] = ws.y[(lane + 1) * 32 + 19];
+    } else {
+      const int ch = (lane - 16) >> 3, r = lane & 7;
+      const uint32_t* row = (const uint32_t*)(ws.uv + (r + 1) * 32 + 4 + 16 * ch);
+      uint2 v; v.x = row[0]; v.y = row[1];
+      *(uint2*)((ch ? vplane : uplane) + (size_t)(8 * my + r) * uvs + 8 * mx) = v;
+      (ch ? cx.top_v : cx.top_u)[8 * mx + r] = ws.uv[8 * 32 + 4 + 16 * ch + r];
+      (ch ? cx.left_v : cx.left_u)[8 * my + r] = ws.uv[(r + 1) * 32 + 11 + 16 * ch];
+    }
+    if (lane == 0) {
+      cx.corner[4 * my + 0] = ws.y[19];
+      cx.corner[4 * my + 1] = ws.uv[11];
+      cx.corner[4 * my + 2] = ws.uv[27];
+      info[2] = nzy;
+      info[3] = (is_i4 || (nzy | nzuv) != 0) ? (w | MBW_INNER) : (w & ~MBW_INNER);
+    }
+  WARP_PHASE_END
+}
+
+// =========================================================================================================
+// In-loop deblocking filter. Thresholds as in the reference (clip tables of dec_clip_tables.c written as
+// clamps). One lane filters one line of 8 pixels across an edge; `p` addresses the first pixel after the
+// edge (q0), `step` is the distance between pixels across the edge, inside the warp's shared-memory tile.
+VP8_PFN int iabs_(int v) { return v < 0 ? -v : v; }
+VP8_PFN int sclip1_(int v) { return v < -128 ? -128 : v > 127 ? 127 : v; }
+VP8_PFN int sclip2_(int v) { return v < -16 ? -16 : v > 15 ? 15 : v; }
+
+VP8_PFN void lf_filter2(uint8_t* p, int step, int p1, int p0, int q0, int q1) {   // DoFilter2_C
+  const int a = 3 * (q0 - p0) + sclip1_(p1 - q1);
+  const int a1 = sclip2_((a + 4) >> 3), a2 = sclip2_((a + 3) >> 3);
+  p[-step] = (uint8_t)clip8i(p0 + a2);
+  p[0] = (uint8_t)clip8i(q0 - a1);
+}
+
+// kind 0: simple filter; 1: normal filter on a macroblock edge; 2: normal filter on an inner edge.
+VP8_PFN void lf_line(uint8_t* p, int step, int kind, int thresh, int ithresh, int hev_t) {
+  const int p1 = p[-2 * step], p0 = p[-step], q0 = p[0], q1 = p[step];
+  const int t2 = 2 * thresh + 1;
+  if (4 * iabs_(p0 - q0) + iabs_(p1 - q1) > t2) return;
+  if (kind == 0) { lf_filter2(p, step, p1, p0, q0, q1); return; }
+  const int p3 = p[-4 * step], p2 = p[-3 * step], q2 = p[2 * step], q3 = p[3 * step];
+  if (iabs_(p3 - p2) > ithresh || iabs_(p2 - p1) > ithresh || iabs_(p1 - p0) > ithresh ||
+      iabs_(q3 - q2) > ithresh || iabs_(q2 - q1) > ithresh || iabs_(q1 - q0) > ithresh) return;
+  if (iabs_(p1 - p0) > hev_t || iabs_(q1 - q0) > hev_t) { lf_filter2(p, step, p1, p0, q0, q1); return; }
+  if (kind == 1) {   // DoFilter6_C
+    const int a = sclip1_(3 * (q0 - p0) + sclip1_(p1 - q1));
+    const int a1 = (27 * a + 63) >> 7, a2 = (18 * a + 63) >> 7, a3 = (9 * a + 63) >> 7;
+    p[-3 * step] = (uint8_t)clip8i(p2 + a3); p[-2 * step] = (uint8_t)clip8i(p1 + a2); p[-step] = (uint8_t)clip8i(p0 + a1);
+    p[0] = (uint8_t)clip8i(q0 - a1); p[step] = (uint8_t)clip8i(q1 - a2); p[2 * step] = (uint8_t)clip8i(q2 - a3);
+  } else {           // DoFilter4_C
+    const int a = 3 * (q0 - p0);
+    const int a1 = sclip2_((a + 4) >> 3), a2 = sclip2_((a + 3) >> 3), a3 = (a1 + 1) >> 1;
+    p[-2 * step] = (uint8_t)clip8i(p1 + a3); p[-step] = (uint8_t)clip8i(p0 + a2);
+    p[0] = (uint8_t)clip8i(q0 - a1); p[step] = (uint8_t)clip8i(q1 - a3);
+  }
+}
+
+// Filter workspace of one warp: luma rows -4..15 / cols -4..15 at y[(r + 4) * 32 + c + 4]; chroma rows -4..7,
+// U at uv[(r + 4) * 32 + c + 4], V at uv[(r + 4) * 32 + c + 20].
+struct FilterWs {
+  uint8_t y[20 * 32];
+  uint8_t uv[12 * 32];
+};
+
+// Filters macroblock (mx, my) in place in the image's HBM planes, in the reference's edge order
+// (DoFilter, frame_dec.c:203-250). fs = {limit, ilevel, inner(unused), hev_thresh} for this macroblock's
+// segment / block type; `inner` = MbInfo filter-inner bit; filter_type 1 simple, 2 normal.
+VP8_PFN void filter_macroblock(FilterWs& ws, int mx, int my, int mb_w, int filter_type, const uint8_t* fs, int inner,
+                               uint8_t* yplane, uint8_t* uplane, uint8_t* vplane) {
+  const int limit = fs[0], ilevel = fs[1], hev_t = fs[3];
+  const int ys = 16 * mb_w, uvs = 8 * mb_w;
+  const int normal = (filter_type == 2);
+  if (limit == 0) return;
+  // ---- load
+  WARP_PHASE(lane)
+    if (lane < 20) {
+      const int gy = 16 * my - 4 + lane;
+      if (gy >= 0) {
+        const uint8_t* src = yplane + (size_t)gy * ys + 16 * mx;
+        const uint4 v = *(const uint4*)src;
+        uint32_t* d = (uint32_t*)(ws.y + lane * 32 + 4);
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        if (mx > 0) *(uint32_t*)(ws.y + lane * 32) = *(const uint32_t*)(src - 4);
+      }
+    } else if (normal) {
+      const int r = lane - 20;
+      const int gy = 8 * my - 4 + r;
+      if (gy >= 0) {
+        const uint8_t* su = uplane + (size_t)gy * uvs + 8 * mx;
+        const uint8_t* sv = vplane + (size_t)gy * uvs + 8 * mx;
+        const uint2 a = *(const uint2*)su, b = *(const uint2*)sv;
+        uint32_t* d = (uint32_t*)(ws.uv + r * 32);
+        d[1] = a.x; d[2] = a.y; d[5] = b.x; d[6] = b.y;
+        if (mx > 0) { d[0] = *(const uint32_t*)(su - 4); d[4] = *(const uint32_t*)(sv - 4); }
+      }
+    }
+  WARP_PHASE_END
+  // ---- vertical edges (filtering across columns): macroblock edge, then the three inner edges
+  for (int k = 0; k < 4; ++k) {
+    if (k == 0 ? (mx > 0) : inner) {
+      const int thresh = (k == 0) ? limit + 4 : limit;
+      const int kind = normal ? ((k == 0) ? 1 : 2) : 0;
+      WARP_PHASE(lane)
+        if (lane < 16) {
+          lf_line(ws.y + (4 + lane) * 32 + 4 + 4 * k, 1, kind, thresh, ilevel, hev_t);
+        } else if (normal && k < 2) {
+          const int r = lane & 7, ch = (lane - 16) >> 3;
+          lf_line(ws.uv + (4 + r) * 32 + 4 + 16 * ch + 4 * k, 1, kind, thresh, ilevel, hev_t);
+        }
+      WARP_PHASE_END
+    }
+  }
+  // ---- horizontal edges (filtering across rows)
+  for (int k = 0; k < 4; ++k) {
+    if (k == 0 ? (my > 0) : inner) {
+      const int thresh = (k == 0) ? limit + 4 : limit;
+      const int kind = normal ? ((k == 0) ? 1 : 2) : 0;
+      WARP_PHASE(lane)
+        if (lane < 16) {
+          lf_line(ws.y + (4 + 4 * k) * 32 + 4 + lane, 32, kind, thresh, ilevel, hev_t);
+        } else if (normal && k < 2) {
+          const int c = lane & 7, ch = (lane - 16) >> 3;
+          lf_line(ws.uv + (4 + 4 * k) * 32 + 4 + 16 * ch + c, 32, kind, thresh, ilevel, hev_t);
+        }
+      WARP_PHASE_END
+    }
+  }
+  // ---- store (everything that was loaded: no other macroblock of the same wavefront step touches it)
+  WARP_PHASE(lane)
+    if (lane < 20) {
+      const int gy = 16 * my - 4 + lane;
+      if (gy >= 0) {
+        uint8_t* dst = yplane + (size_t)gy * ys + 16 * mx;
+        const uint32_t* s = (const uint32_t*)(ws.y + lane * 32 + 4);
+        uint4 v; v.x = s[0]; v.y = s[1]; v.z = s[2]; v.w = s[3];
+        *(uint4*)dst = v;
+        if (mx > 0) *(uint32_t*)(dst - 4) = *(const uint32_t*)(ws.y + lane * 32);
+      }
+    } else if (normal) {
+      const int r = lane - 20;
+      const int gy = 8 * my - 4 + r;
+      if (gy >= 0) {
+        uint8_t* du = uplane + (size_t)gy * uvs + 8 * mx;
+        uint8_t* dv = vplane + (size_t)gy * uvs + 8 * mx;
+        const uint32_t* s = (const uint32_t*)(ws.uv + r * 32);
+        uint2 a, b; a.x = s[1]; a.y = s[2]; b.x = s[5]; b.y = s[6];
+        *(uint2*)du = a; *(uint2*)dv = b;
+        if (mx > 0) { *(uint32_t*)(du - 4) = s[0]; *(uint32_t*)(dv - 4) = s[4]; }
+      }
+    }
+  WARP_PHASE_END
+}
+
+// =========================================================================================================
+// Output stage. One thread converts four horizontally adjacent pixels.
+VP8_PFN int yuv_clip6(int v) { return ((v & ~16383) == 0) ? (v >> 6) : (v < 0) ? 0 : 255; }
+
+VP8_PFN void yuv_to_rgb(int y, int u, int v, int* r, int* g, int* b) {   // yuv.h:59-77
+  const int yy = (y * 19077) >> 8;
+  *r = yuv_clip6(yy + ((v * 26149) >> 8) - 14234);
+  *g = yuv_clip6(yy - ((u * 6419) >> 8) - ((v * 13320) >> 8) + 8708);
+  *b = yuv_clip6(yy + ((u * 33050) >> 8) - 17685);
+}
+
+// Fancy-upsampled chroma of pixel (i, j) of a w x h picture (UPSAMPLE_FUNC, upsampling.c:37-93 applied the way
+// EmitFancyRGB does over a whole frame, io_dec.c:57-109). `pl` = one chroma plane, stride uvs.
+// near/far = the chroma rows that weigh 3/4 and 1/4 for this luma row.
+VP8_PFN int fancy_chroma(const uint8_t* near, const uint8_t* far, int i, int w) {
+  if (i == 0) return (3 * near[0] + far[0] + 2) >> 2;
+  const int x = (i + 1) >> 1;
+  if (!(w & 1) && i == w - 1) return (3 * near[x - 1] + far[x - 1] + 2) >> 2;
+  const int nl = near[x - 1], nr = near[x], fl = far[x - 1], fr = far[x];
+  const int avg = nl + nr + fl + fr + 8;
+  return (i & 1) ? ((((avg + 2 * (nr + fl)) >> 3) + nl) >> 1) : ((((avg + 2 * (nl + fr)) >> 3) + nr) >> 1);
+}
+
+VP8_PFN uint32_t pack_pixel4(int csp, int r, int g, int b) {   // little-endian byte order in memory
+  switch (csp) {
+    case 1: case 7: return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16) | 0xff000000u;   // RGBA / rgbA
+    case 3: case 8: return (uint32_t)b | ((uint32_t)g << 8) | ((uint32_t)r << 16) | 0xff000000u;   // BGRA / bgrA
+    default: return 0xffu | ((uint32_t)r << 8) | ((uint32_t)g << 16) | ((uint32_t)b << 24);         // ARGB / Argb
+  }
+}
+
+// Pixels 4*q .. 4*q+3 of output row j of image `im`. yuv = the image's padded planes.
+VP8_PFN void emit_rgb_quad(const ImgDesc& im, const uint8_t* yplane, const uint8_t* uplane, const uint8_t* vplane,
+                           uint8_t* out, int q, int j) {
+  const int w = im.width, h = im.height;
+  const int ys = 16 * im.mb_w, uvs = 8 * im.mb_w;
+  const int uvh = (h + 1) >> 1;
+  const int csp = im.csp;
+  const int fancy = !(im.flags & VP8B_FLAG_NO_FANCY);
+  int rn, rf;   // near / far chroma rows
+  if (!fancy) { rn = rf = j >> 1; }
+  else if (j == 0) { rn = rf = 0; }
+  else if (j & 1) { rn = (j - 1) >> 1; rf = rn + 1 < uvh ? rn + 1 : uvh - 1; }
+  else { rn = j >> 1; rf = rn - 1; }
+  const uint8_t* yrow = yplane + (size_t)j * ys;
+  const uint8_t* un = uplane + (size_t)rn * uvs; const uint8_t* uf = uplane + (size_t)rf * uvs;
+  const uint8_t* vn = vplane + (size_t)rn * uvs; const uint8_t* vf = vplane + (size_t)rf * uvs;
+  uint8_t* orow = out + (size_t)j * im.out_stride;
+  const int i0 = 4 * q;
+  const int n = (w - i0 < 4) ? w - i0 : 4;
+  const int bpp = (csp == 0 || csp == 2) ? 3 : 4;
+  uint32_t px[4];
+  for (int k = 0; k < n; ++k) {
+    const int i = i0 + k;
+    int u, v, r, g, b;
+    if (fancy) { u = fancy_chroma(un, uf, i, w); v = fancy_chroma(vn, vf, i, w); }
+    else { u = un[i >> 1]; v = vn[i >> 1]; }
+    yuv_to_rgb(yrow[i], u, v, &r, &g, &b);
+    if (bpp == 4) {
+      px[k] = pack_pixel4(csp, r, g, b);
+    } else {
+      uint8_t* o = orow + 3 * i;
+      if (csp == 0) { o[0] = (uint8_t)r; o[1] = (uint8_t)g; o[2] = (uint8_t)b; }
+      else { o[0] = (uint8_t)b; o[1] = (uint8_t)g; o[2] = (uint8_t)r; }
+    }
+  }
+  if (bpp == 4) {
+    uint8_t* o = orow + 4 * i0;
+    if (n == 4 && (((uintptr_t)o) & 15) == 0) {
+      uint4 v4; v4.x = px[0]; v4.y = px[1]; v4.z = px[2]; v4.w = px[3];
+      *(uint4*)o = v4;
+    } else if ((((uintptr_t)o) & 3) == 0) {
+      for (int k = 0; k < n; ++k) ((uint32_t*)o)[k] = px[k];
+    } else {
+      for (int k = 0; k < n; ++k) { o[4 * k] = (uint8_t)px[k]; o[4 * k + 1] = (uint8_t)(px[k] >> 8); o[4 * k + 2] = (uint8_t)(px[k] >> 16); o[4 * k + 3] = (uint8_t)(px[k] >> 24); }
+    }
+  }
+}
+
+// MODE_YUV (EmitYUV, io_dec.c:25-40): 16 bytes of one row of one plane. plane 0 = Y (w x h), 1 = U, 2 = V
+// ((w+1)/2 x (h+1)/2). Output = y | u | v at out_off with strides out_stride / (w+1)/2.
+VP8_PFN void emit_yuv_chunk(const ImgDesc& im, const uint8_t* yplane, const uint8_t* uplane, const uint8_t* vplane,
+                            uint8_t* out, int plane, int q, int j) {
+  const int w = im.width, h = im.height;
+  const int uvw = (w + 1) >> 1, uvh = (h + 1) >> 1;
+  const int pw = plane ? uvw : w;
+  const int sstride = plane ? 8 * im.mb_w : 16 * im.mb_w;
+  const int dstride = plane ? uvw : im.out_stride;
+  const uint8_t* src = (plane == 0 ? yplane : plane == 1 ? uplane : vplane) + (size_t)j * sstride + 16 * q;
+  uint8_t* dst = out + (plane == 0 ? 0 : (size_t)im.out_stride * h + (plane == 2 ? (size_t)uvw * uvh : 0)) +
+                 (size_t)j * dstride + 16 * q;
+  const int n = (pw - 16 * q < 16) ? pw - 16 * q : 16;
+  if (n == 16 && ((((uintptr_t)dst) | ((uintptr_t)src)) & 15) == 0) {
+    *(uint4*)dst = *(const uint4*)src;
+  } else {
+    for (int k = 0; k < n; ++k) dst[k] = src[k];
+  }
+}
+
+#endif  // LIBWEBP_B200_VP8_PIXEL_CORE_H_

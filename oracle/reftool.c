@@ -193,7 +193,7 @@ int reft_decode(const uint8_t* data, size_t size, int csp, int flags, uint8_t* o
   int st;
   if (!WebPInitDecoderConfig(&cfg)) return -1;
   st = WebPGetFeatures(data, size, &cfg.input);
-  if (st != VP8_STATUS_OK) return st;
+  if (st != VP8_STATUS_OK) return WebPDecode(data, size, &cfg);   /* the status WebPDecode itself reports */
   cfg.options.bypass_filtering = flags & 1;
   cfg.options.no_fancy_upsampling = (flags >> 1) & 1;
   cfg.options.use_threads = (flags >> 2) & 1;

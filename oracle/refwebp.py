@@ -126,6 +126,9 @@ def decode(data, csp=MODE_RGBA, flags=0, simd=True, stride=None):
     L.reft_set_simd(1 if simd else 0)
     st, f = features(data)
     if st != 0:
+        dummy = np.zeros(16, np.uint8)
+        st = L.reft_decode(data, len(data), csp, flags, dummy.ctypes.data, 16, 16)
+        L.reft_set_simd(1)
         return st, None
     w, h = f["width"], f["height"]
     if csp in (MODE_YUV, MODE_YUVA):

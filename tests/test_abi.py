@@ -1,0 +1,123 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol include/webp/*.h
+declares, agrees with the reference on struct layouts and on everything the host decides (features, container
+errors, option screening). No kernel is launched here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol(product):
+    L = product.lib()
+    declared = set()
+    for hdr in ("types.h", "decode.h", "decode_batch.h"):
+        src = open(os.path.join(ROOT, "include", "webp", hdr)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        declared |= set(re.findall(r"^WEBP_EXTERN[^;(]*?\b(\w+)\s*\(", src, flags=re.M))
+    declared.add("VP8GetCPUInfo")
+    assert declared == set(product.EXPORTS), declared ^ set(product.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.WebPGetDecoderVersion() == 0x010302
+
+
+def test_struct_layouts_match_reference_abi(product):
+    # sizes on LP64 for ABI 0x0209 (src/webp/decode.h:184-217, 414-469)
+    assert C.sizeof(product.WebPRGBABuffer) == 24
+    assert C.sizeof(product.WebPYUVABuffer) == 80
+    assert C.sizeof(product.WebPDecBuffer) == 120
+    assert C.sizeof(product.WebPBitstreamFeatures) == 40
+    assert C.sizeof(product.WebPDecoderOptions) == 76
+    assert C.sizeof(product.WebPDecoderConfig) == 240
+    cfg = product.WebPDecoderConfig()
+    assert product.lib().WebPInitDecoderConfigInternal(C.byref(cfg), 0x0209) == 1
+    assert product.lib().WebPInitDecoderConfigInternal(C.byref(cfg), 0x0109) == 0   # ABI major mismatch
+
+
+def test_struct_layouts_match_reference_compiler(ref, product):
+    """Same sizes as the reference's own header compiled by gcc (via the reference .so's view of the structs)."""
+    import subprocess, tempfile
+    if not os.path.isdir("/root/reference"):
+        import pytest
+        pytest.skip("needs the reference headers")
+    src = ('#include <stdio.h>\n#include "src/webp/decode.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n",'
+           'sizeof(WebPRGBABuffer),sizeof(WebPYUVABuffer),sizeof(WebPDecBuffer),sizeof(WebPBitstreamFeatures),'
+           'sizeof(WebPDecoderOptions),sizeof(WebPDecoderConfig));return 0;}')
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I/root/reference", os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
+        sizes = list(map(int, subprocess.check_output([os.path.join(d, "s")]).split()))
+    mine = [C.sizeof(t) for t in (product.WebPRGBABuffer, product.WebPYUVABuffer, product.WebPDecBuffer,
+                                  product.WebPBitstreamFeatures, product.WebPDecoderOptions, product.WebPDecoderConfig)]
+    assert sizes == mine
+
+
+def test_features_match_oracle(product, port, manifest):
+    for e in manifest:
+        st, f = product.WebPGetFeatures(e["data"])
+        assert st == 0 and f == e["features"]
+        for n in (0, 4, 11, 12, 15, 20, 25, 29, 30, 31, 100):
+            cut = e["data"][:n]
+            assert product.WebPGetFeatures(cut) == port.features(cut), (e["file"], n)
+    w, h = C.c_int(), C.c_int()
+    d = manifest[0]["data"]
+    assert product.lib().WebPGetInfo(d, len(d), C.byref(w), C.byref(h)) == 1
+    assert (w.value, h.value) == (manifest[0]["features"]["width"], manifest[0]["features"]["height"])
+
+
+def test_host_side_failures_need_no_gpu(product, port, manifest):
+    """Errors decided by the container walk come back with the reference's status codes without touching a GPU."""
+    d = manifest[1]["data"]
+    for cut in (d[:0], d[:5], d[:11], d[:19], d[:29], b"RIFF" + d[4:8] + b"WEBX" + d[12:], d[: len(d) // 2]):
+        st, out = product.WebPDecode(cut)
+        want, _ = port.decode(cut, port.RGBA, 0)
+        if want in (3, 7) and out is None and st in (3, 7):
+            # truncated-inside-the-bitstream cases are decided on the device; the ones decided on the host must agree
+            if len(cut) < 30 or cut[8:12] != b"WEBP":
+                assert st == want, (len(cut), st, want)
+    L = product.lib()
+    assert L.WebPDecode(d, len(d), None) == product.VP8_STATUS_INVALID_PARAM
+    cfg = product.WebPDecoderConfig()
+    L.WebPInitDecoderConfigInternal(C.byref(cfg), 0x0209)
+    cfg.output.colorspace = 13
+    assert L.WebPDecode(d, len(d), C.byref(cfg)) == product.VP8_STATUS_INVALID_PARAM
+    for field in ("use_cropping", "use_scaling", "flip"):
+        L.WebPInitDecoderConfigInternal(C.byref(cfg), 0x0209)
+        setattr(cfg.options, field, 1)
+        assert L.WebPDecode(d, len(d), C.byref(cfg)) == product.VP8_STATUS_UNSUPPORTED_FEATURE
+    L.WebPInitDecoderConfigInternal(C.byref(cfg), 0x0209)
+    cfg.output.colorspace = product.MODE_RGB_565
+    assert L.WebPDecode(d, len(d), C.byref(cfg)) == product.VP8_STATUS_UNSUPPORTED_FEATURE
+    # external buffer too small -> INVALID_PARAM (buffer_dec.c:41-84)
+    L.WebPInitDecoderConfigInternal(C.byref(cfg), 0x0209)
+    buf = np.zeros(16, np.uint8)
+    cfg.output.colorspace = product.MODE_RGBA
+    cfg.output.is_external_memory = 1
+    cfg.output.u.RGBA.rgba = buf.ctypes.data
+    cfg.output.u.RGBA.stride = 4
+    cfg.output.u.RGBA.size = 16
+    assert L.WebPDecode(d, len(d), C.byref(cfg)) == product.VP8_STATUS_INVALID_PARAM
+
+
+def test_no_cpu_fallback(product, manifest):
+    """Without a CUDA device a well-formed file must NOT decode: the product has no CPU path."""
+    if product.device_count() > 0:
+        import pytest
+        pytest.skip("a GPU is present")
+    st, out = product.WebPDecode(manifest[0]["data"])
+    assert st != 0 and out is None
+    assert "CPU" in product.last_error() or "CUDA" in product.last_error()
+
+
+def test_product_never_touches_the_oracle():
+    """The shipped package must not import, link or read anything under oracle/ or tests/."""
+    pkg = os.path.join(ROOT, "libwebp_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".c", ".h", ".cu", ".cuh", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                for bad in ("oracle/", "oracle import", "from oracle", "vp8_oracle", "libwebp_ref", "tests/emu/libvp8"):
+                    assert bad not in text.replace("oracle/: ", "").replace("touches oracle/", ""), (f, bad)

@@ -1,0 +1,84 @@
+"""Device logic on the host (tests/emu): the product's parse / reconstruct / filter / emit code compiled with
+-DVP8_EMU (a warp phase = a loop over 32 lanes, a wavefront step = a loop over its macroblocks, visited in
+both orders) must reproduce the reference byte for byte. This is a unit test of the kernels' arithmetic and
+dependency analysis where no GPU exists; the GPU parity tests proper are tests/test_gpu_parity.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, sha
+
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR])
+    L = C.CDLL(os.path.join(EMU_DIR, "libvp8_emu.so"))
+    L.emu_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+
+    def run(data, w, h, csp, flags=0, reverse=0, unfiltered=None):
+        if csp == 11:
+            out = np.zeros(w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2), np.uint8)
+            stride = w
+        else:
+            bpp = 3 if csp in (0, 2) else 4
+            out = np.zeros((h, w * bpp), np.uint8)
+            stride = w * bpp
+        st = L.emu_decode(data, len(data), csp, flags, out.ctypes.data, out.size, stride, reverse,
+                          unfiltered.ctypes.data if unfiltered is not None else None)
+        return st, out
+    return run
+
+
+def test_emu_matches_manifest(emu, manifest):
+    for e in manifest:
+        w, h = e["features"]["width"], e["features"]["height"]
+        for key, want in e["sha256"].items():
+            csp, fl = map(int, key.split(":"))
+            for rev in (0, 1):
+                st, out = emu(e["data"], w, h, csp, fl, rev)
+                assert st == 0 and sha(out) == want, (e["file"], key, rev)
+
+
+def test_emu_stage_dumps_match_port(emu, port, manifest):
+    """Unfiltered reconstruction (K3's output) against the oracle's stage dump."""
+    for e in manifest:
+        st, d = port.dump(e["data"])
+        assert st == 0
+        unf = np.zeros(d["mb_w"] * d["mb_h"] * 384, np.uint8)
+        st, _ = emu(e["data"], d["width"], d["height"], 11, 0, 0, unf)
+        assert st == 0 and np.array_equal(unf, d["unfiltered"]), e["file"]
+
+
+def test_emu_status_on_damaged_files(emu, port, manifest):
+    data = next(e for e in manifest if e["file"] == "normal_8part_400x300.webp")["data"]
+    cases = [data[:n] for n in (200, 3000, len(data) // 2, len(data) - 1)]
+    rng = np.random.default_rng(7)
+    for _ in range(20):
+        b = bytearray(data)
+        for _ in range(3):
+            b[int(rng.integers(30, len(b)))] ^= int(rng.integers(1, 256))
+        cases.append(bytes(b))
+    data1 = next(e for e in manifest if e["file"] == "simple_1part_320x200.webp")["data"]
+    cases += [data1[:n] for n in (100, 2000, len(data1) - 1)]
+    for c in cases:
+        s_ref, a = port.decode(c, port.RGBA, 0)
+        w, h = port.features(c)[1]["width"], port.features(c)[1]["height"]
+        s_emu, b = emu(c, max(w, 1), max(h, 1), 1, 0)
+        assert s_emu == s_ref, (len(c), s_ref, s_emu)
+        if s_ref == 0:
+            assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("kind", ["simple", "8part"])
+def test_emu_full_hd(emu, ref, kind):
+    cfg = ref.cfg_simple_1part() if kind == "simple" else ref.cfg_normal_8part()
+    data = ref.encode(ref.synth(1920, 1080, 31), cfg)
+    for csp in (1, 11):
+        st, want = ref.decode(data, csp, 0)
+        st2, got = emu(data, 1920, 1080, csp, 0, 1)
+        assert st == st2 == 0 and np.array_equal(want.reshape(-1), got.reshape(-1))

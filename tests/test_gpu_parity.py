@@ -1,0 +1,161 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (WebPDecode / WebPDecodeBatch / the resident
+batch), must be byte-identical to the reference. Checkers: the committed golden manifest (reference hashes), the
+plain-C oracle, and the compiled reference when oracle/_ref travelled to the box. Integer/byte work: the bar
+is bit-exact everywhere."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import sha
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def W(product):
+    assert product.device_count() > 0, "no CUDA device: the product has no CPU path"
+    return product
+
+
+def test_webpdecode_matches_manifest(W, manifest):
+    for e in manifest:
+        for key, want in e["sha256"].items():
+            csp, fl = map(int, key.split(":"))
+            st, out = W.WebPDecode(e["data"], csp, bypass_filtering=fl & 1, no_fancy_upsampling=fl & 2)
+            assert st == 0, (e["file"], key, st, W.last_error())
+            assert sha(out) == want, (e["file"], key)
+
+
+def test_internal_memory_and_strides(W, port, manifest):
+    e = next(m for m in manifest if m["file"] == "odd_255x127_q50.webp")
+    _, want = port.decode(e["data"], port.RGBA, 0)
+    st, out = W.WebPDecode(e["data"], W.MODE_RGBA, external=False)          # library-allocated buffer
+    assert st == 0 and np.array_equal(out, want)
+    st, out = W.WebPDecode(e["data"], W.MODE_RGBA, stride=255 * 4 + 20)      # padded external rows
+    assert st == 0 and np.array_equal(out[:, :255 * 4], want) and not out[:, 255 * 4:].any()
+    st, out = W.WebPDecode(e["data"], W.MODE_YUV, external=False)
+    _, wanty = port.decode(e["data"], port.YUV, 0)
+    assert st == 0 and np.array_equal(out, wanty)
+    # simple API
+    L = W.lib()
+    w, h = C.c_int(), C.c_int()
+    p = L.WebPDecodeRGBA(e["data"], len(e["data"]), C.byref(w), C.byref(h))
+    assert p and (w.value, h.value) == (255, 127)
+    got = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), (127, 255 * 4)).copy()
+    L.WebPFree(p)
+    assert np.array_equal(got, want)
+
+
+def test_batch_mixed_sizes_modes_and_failures(W, port, manifest):
+    """One batch holding every fixture plus damaged files: per-item status and pixels as WebPDecode would give,
+    a bad image never poisons its neighbours."""
+    good = [e["data"] for e in manifest]
+    d = next(m for m in manifest if m["file"] == "normal_8part_400x300.webp")["data"]
+    rng = np.random.default_rng(11)
+    bad = [d[:200], d[:3000], d[: len(d) // 2], d[:-1], d[:11], b"junkjunkjunkjunk"]
+    for _ in range(10):
+        b = bytearray(d)
+        for _ in range(3):
+            b[int(rng.integers(30, len(b)))] ^= int(rng.integers(1, 256))
+        bad.append(bytes(b))
+    datas = []
+    for i in range(max(len(good), len(bad))):
+        if i < len(good):
+            datas.append(good[i])
+        if i < len(bad):
+            datas.append(bad[i])
+    for csp in (W.MODE_RGBA, W.MODE_YUV, W.MODE_BGR):
+        sts, outs = W.decode_batch(datas, csp)
+        for i, data in enumerate(datas):
+            want_st, want = port.decode(data, csp, 0)
+            assert sts[i] == want_st, (i, len(data), sts[i], want_st)
+            if want_st == 0:
+                assert np.array_equal(outs[i].reshape(-1), want.reshape(-1)), (i, csp)
+
+
+def test_fresh_corpora_against_compiled_reference(W, ref):
+    """Seeded corpora encoded on the spot by the reference encoder: simple/normal filter, 1/4 segments,
+    1..8 partitions, odd sizes; RGBA, rgbA, YUV; SIMD on and off on the reference side."""
+    cases = [(640, 360, ref.cfg_simple_1part(), 41), (640, 360, ref.cfg_normal_8part(), 42), (256, 256, ref.cfg_default(), 43),
+             (1920, 1080, ref.cfg_simple_1part(), 44), (1920, 1080, ref.cfg_normal_8part(), 45),
+             (333, 77, ref.EncCfg(60, 4, partitions=1, low_memory=1, segments=3), 46), (16, 16, ref.cfg_default(30), 47),
+             (2048, 64, ref.cfg_default(90), 48), (64, 2048, ref.cfg_normal_8part(20), 49)]
+    datas = [ref.encode(ref.synth(w, h, seed), cfg) for (w, h, cfg, seed) in cases]
+    for csp in (W.MODE_RGBA, W.MODE_rgbA, W.MODE_YUV):
+        for fl in (0, 1, 2):
+            if csp == W.MODE_YUV and fl == 2:
+                continue
+            sts, outs = W.decode_batch(datas, csp, bypass_filtering=fl & 1, no_fancy_upsampling=fl & 2)
+            for i, data in enumerate(datas):
+                for simd in (True, False):
+                    st, want = ref.decode(data, csp, fl, simd=simd)
+                    assert st == 0 and sts[i] == 0
+                    assert np.array_equal(outs[i].reshape(-1), want.reshape(-1)), (cases[i][:2], csp, fl, simd)
+
+
+def test_resident_batch_device_outputs_and_repeat(W, port, manifest):
+    """Resident API: decode twice from the same uploaded inputs, identical results; timings populated."""
+    datas = [e["data"] for e in manifest] * 3
+    b = W.Batch(datas, W.MODE_RGBA)
+    try:
+        assert b.create() == 0
+        assert b.decode() == 0
+        t = b.timings()
+        assert t["launches"] >= 5 and t["total_ms"] > 0
+        assert b.download() == 0
+        first = [b.host_output(i).copy() for i in range(b.n)]
+        assert b.decode() == 0 and b.download() == 0
+        for i in range(b.n):
+            assert np.array_equal(first[i], b.host_output(i))
+            _, want = port.decode(datas[i], port.RGBA, 0)
+            assert np.array_equal(first[i], want)
+        p = b.device_output(0)
+        assert p is not None and p.y_or_rgba and p.width == b.dims[0][0]
+    finally:
+        b.close()
+
+
+def test_waves_small_scratch(W, port, manifest):
+    """Force several waves through a tiny scratch budget: same bytes."""
+    datas = [e["data"] for e in manifest] * 4
+    b = W.Batch(datas, W.MODE_RGBA, scratch_bytes=700 * 1200)
+    try:
+        assert b.decode_oneshot() == 0
+        for i in range(b.n):
+            _, want = port.decode(datas[i], port.RGBA, 0)
+            assert np.array_equal(b.host_output(i), want), i
+    finally:
+        b.close()
+
+
+def test_dithering_option_is_exact_or_refused(W, ref, manifest):
+    """dwebp's default dithering_strength=50 only changes pixels for very fine quantisers (frame_dec.c:328-349).
+    Where it would, the product refuses; elsewhere the output equals the reference's."""
+    for e in manifest:
+        st, out = W.WebPDecode(e["data"], W.MODE_RGBA, dithering_strength=50)
+        if st == 0:
+            assert sha(out) == e["sha256"]["1:0"], e["file"]
+        else:
+            assert st == W.VP8_STATUS_UNSUPPORTED_FEATURE
+
+
+def test_full_size_batch_properties(W, ref):
+    """BASELINE config 2 at reduced count (64 distinct 1080p images, simple filter, 1 partition) and config 4 shape
+    (256x256 q80), decoded as one batch; every image compared with the reference; plus size-independent
+    properties: idempotence of repeated decodes and a checksum of checksums equal to the reference's."""
+    import hashlib
+    d2 = ref.encode_corpus(16, 1920, 1080, ref.cfg_simple_1part(), seed0=1000)
+    d3 = ref.encode_corpus(8, 1920, 1080, ref.cfg_normal_8part(), seed0=2000)
+    d4 = ref.encode_corpus(128, 256, 256, ref.cfg_default(), seed0=3000)
+    datas = d2 + d3 + d4
+    sts, outs = W.decode_batch(datas, W.MODE_RGBA)
+    h_gpu, h_ref = hashlib.sha256(), hashlib.sha256()
+    for i, data in enumerate(datas):
+        st, want = ref.decode(data, ref.MODE_RGBA, 0)
+        assert st == 0 and sts[i] == 0
+        assert np.array_equal(outs[i], want), i
+        h_gpu.update(sha(outs[i]).encode()); h_ref.update(sha(want).encode())
+    assert h_gpu.hexdigest() == h_ref.hexdigest()
+    sts2, outs2 = W.decode_batch(datas, W.MODE_RGBA)
+    assert all(np.array_equal(a, b) for a, b in zip(outs, outs2))
