@@ -343,8 +343,8 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
   if (m == 0) return true;
 
   CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
-  // ---- resident allocations: input, descriptors, headers, output
-  if (!own_alloc(ctx, b->d_in, in_total + 256) || !own_alloc(ctx, b->d_imgs, sizeof(ImgDesc) * m) ||
+  // ---- resident allocations: input (64 KB tail padding, see vp8_tokens_fsm.h:tk_lane_init), descriptors, headers, output
+  if (!own_alloc(ctx, b->d_in, in_total + 65536) || !own_alloc(ctx, b->d_imgs, sizeof(ImgDesc) * m) ||
       !own_alloc(ctx, b->d_hdrs, sizeof(FrameHdr) * m) || !own_alloc(ctx, b->d_ids, sizeof(int) * m) ||
       !own_alloc(ctx, b->d_out, b->out_total + 256)) return false;
   // ---- waves: per-macroblock scratch = 16 (MbInfo) + 800 (coefficients) + 384 (planes) bytes

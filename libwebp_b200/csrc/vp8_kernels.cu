@@ -12,6 +12,7 @@
 // carving and the inter-warp synchronisation.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #define VP8_WAIT_PROGRESS(ptr, need)                         \
   do {                                                       \
@@ -27,6 +28,7 @@
 #include "vp8_kernels.h"
 #include "vp8_parse_core.h"
 #include "vp8_pixel_core.h"
+#include "vp8_tokens_fsm.h"
 
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) k_parse_modes(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
@@ -71,6 +73,64 @@ __global__ void k_parse_tokens(const uint8_t* __restrict__ arena, const ImgDesc*
     parse_token_row(tp, im, h, part, my, probs, topctx, progress, mbi, cf);
   }
   if (tp.status != VP8B_OK) h->status = tp.status;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Lane-parallel token parser (vp8_tokens_fsm.h). A block owns IPB images x P partitions = IPB*P streams; stream j
+// sits in warp j / LPW, lane j % LPW (lanes >= LPW of a warp stay idle: fewer streams per warp means fewer
+// divergent block-end branches per iteration, more streams per warp means fewer issue slots per decode).
+#define TOK_IMG_BYTES 1152   // sizeof(TokImage) rounded up to 16
+#define TOK_TAB_BYTES 192    // sizeof(TokTables)
+
+template <int LPW>
+__global__ void __launch_bounds__(256) k_parse_tokens_fsm(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
+                                                          FrameHdr* hdrs, uint32_t* mbinfo, int16_t* coeffs,
+                                                          const int* __restrict__ ids, int count, int P, int ipb, int ctx_stride) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  TokTables* tables = reinterpret_cast<TokTables*>(smem);
+  uint8_t* img_mem = smem + TOK_TAB_BYTES;                                         // ipb * TOK_IMG_BYTES
+  int* progress = reinterpret_cast<int*>(img_mem + (size_t)ipb * TOK_IMG_BYTES);   // ipb * 8 ints
+  uint16_t* ctx_mem = reinterpret_cast<uint16_t*>(progress + ipb * VP8B_MAX_PARTS); // ipb * (P+1) * ctx_stride
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  tk_tables_fill(tables, tid, nthreads);
+  for (int k = tid; k < ipb * VP8B_MAX_PARTS; k += nthreads) progress[k] = 0;
+  for (int slot = 0; slot < ipb; ++slot) {
+    const int g = blockIdx.x * ipb + slot;
+    if (g < count) tk_image_fill(reinterpret_cast<TokImage*>(img_mem + (size_t)slot * TOK_IMG_BYTES), &hdrs[ids[g]], P, tid, nthreads);
+  }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5;
+  const int j = warp * LPW + lane;          // stream inside the block
+  if (lane >= LPW || j >= ipb * P) return;
+  const int slot = j / P, part = j % P;
+  const int g = blockIdx.x * ipb + slot;
+  if (g >= count) return;
+  const int img = ids[g];
+  const TokImage* timg = reinterpret_cast<const TokImage*>(img_mem + (size_t)slot * TOK_IMG_BYTES);
+  FrameHdr* h = &hdrs[img];
+  if (!timg->ok) {   // header failed (or, never expected, the host pre-scan disagreed with the device parse)
+    if (part == 0 && h->status == VP8B_OK) h->status = VP8B_BITSTREAM_ERROR;
+    return;
+  }
+  const ImgDesc im = imgs[img];
+  if (part >= im.mb_h) return;
+  TokShared sh;
+  sh.img = timg;
+  sh.img_s = tk_saddr_of(timg);
+  sh.tab_s = tk_saddr_of(tables);
+  asm volatile("" : "+r"(sh.img_s), "+r"(sh.tab_s));   // keep both as plain registers (no per-iteration cvta)
+  sh.topctx = ctx_mem + (size_t)slot * (P + 1) * ctx_stride;
+  sh.progress = progress + slot * VP8B_MAX_PARTS;
+  uint32_t* mbi = mbinfo + 4 * (size_t)im.mb_base;
+  int16_t* cf = coeffs + (size_t)im.mb_base * VP8B_COEFFS_PER_MB;
+  const uint32_t* arena32 = reinterpret_cast<const uint32_t*>(arena);
+  TokLane L;
+  tk_lane_init(L, arena32, im.in_off, h, part);
+  while (L.phase != 2) {
+    if (L.phase == 0) tk_mb_start(L, sh, im, P, mbi);
+    if (L.phase == 1) tk_step(L, sh, im, P, arena32, mbi, cf);
+  }
+  if (L.status != VP8B_OK) h->status = L.status;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -196,9 +256,59 @@ extern "C" void vp8k_parse_modes(cudaStream_t s, const uint8_t* arena, const Img
   k_parse_modes<<<count, 32, (size_t)max_mb_w * 4, s>>>(arena, imgs, hdrs, mbinfo, first, count);
 }
 
+static size_t tokens_fsm_smem_bytes(int P, int ipb, int max_mb_w) {
+  return TOK_TAB_BYTES + (size_t)ipb * TOK_IMG_BYTES + (size_t)ipb * VP8B_MAX_PARTS * 4 + (size_t)ipb * (P + 1) * max_mb_w * 2;
+}
+
+template <int LPW>
+static void launch_tokens_fsm(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,
+                              int16_t* coeffs, const int* ids, int count, int P, int max_mb_w, int warps) {
+  int ipb = (LPW * warps) / P;                 // images per block
+  if (ipb < 1) ipb = 1;
+  size_t smem = tokens_fsm_smem_bytes(P, ipb, max_mb_w);
+  while (ipb > 1 && smem > 200 * 1024) { ipb >>= 1; smem = tokens_fsm_smem_bytes(P, ipb, max_mb_w); }
+  const int streams = ipb * P;
+  const int threads = ((streams + LPW - 1) / LPW) * 32;
+  const int blocks = (count + ipb - 1) / ipb;
+  cudaFuncSetAttribute(k_parse_tokens_fsm<LPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_parse_tokens_fsm<LPW><<<blocks, threads, smem, s>>>(arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, ipb, max_mb_w);
+}
+
+// Streams per warp: enough warps to give every SM sub-partition one or two, as few lanes per warp as that allows.
+static int pick_lpw(int streams) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("WEBP_B200_TOKEN_LPW"); forced = e ? atoi(e) : 0; }
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
+  int lpw = 1;
+  while (lpw < 32 && streams / lpw > 148 * 4 * 2) lpw <<= 1;
+  return lpw;
+}
+
 extern "C" void vp8k_parse_tokens(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,
                                   int16_t* coeffs, const int* ids, int count, int P, int max_mb_w) {
-  k_parse_tokens<<<count, 32 * P, tokens_smem_bytes(P, max_mb_w), s>>>(arena, imgs, hdrs, mbinfo, coeffs, ids, P, max_mb_w);
+  // Two mappings of the same parse. Few streams (a few per SM sub-partition): one warp per partition, straight-line
+  // code on one lane, latency hidden by the other warps. Many streams: the lane-parallel state machine, which
+  // spends ~8x fewer issue slots per decode. WEBP_B200_TOKEN_MAP=warp|lanes forces one of them (A/B timing).
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("WEBP_B200_TOKEN_MAP");
+    forced = (e && e[0] == 'w') ? 1 : (e && e[0] == 'l') ? 2 : 0;
+  }
+  const int use_warp_map = forced ? (forced == 1) : (count * P < 16384);
+  if (use_warp_map) {
+    k_parse_tokens<<<count, 32 * P, tokens_smem_bytes(P, max_mb_w), s>>>(arena, imgs, hdrs, mbinfo, coeffs, ids, P, max_mb_w);
+    return;
+  }
+  const int lpw = pick_lpw(count * P);
+  const int warps = 2;
+  switch (lpw) {
+    case 1: launch_tokens_fsm<1>(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, max_mb_w, warps); break;
+    case 2: launch_tokens_fsm<2>(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, max_mb_w, warps); break;
+    case 4: launch_tokens_fsm<4>(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, max_mb_w, warps); break;
+    case 8: launch_tokens_fsm<8>(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, max_mb_w, warps); break;
+    case 16: launch_tokens_fsm<16>(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, max_mb_w, warps); break;
+    default: launch_tokens_fsm<32>(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, max_mb_w, warps); break;
+  }
 }
 
 extern "C" void vp8k_reconstruct(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, uint32_t* mbinfo, const int16_t* coeffs,

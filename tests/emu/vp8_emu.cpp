@@ -16,9 +16,13 @@
 #include "vp8_container.h"
 #include "vp8_parse_core.h"
 #include "vp8_pixel_core.h"
+#include "vp8_tokens_fsm.h"
 
+// variant bit 0: visit the macroblocks of a wavefront step in reverse order
+// variant bit 1: token parse with the row-at-a-time reference port (parse_token_row) instead of the lane FSM
 extern "C" int emu_decode(const uint8_t* data, size_t size, int csp, int flags, uint8_t* out, size_t out_size,
-                          int stride, int reverse_steps, uint8_t* unfiltered /* optional: y|u|v padded */) {
+                          int stride, int variant, uint8_t* unfiltered /* optional: y|u|v padded */) {
+  const int reverse_steps = variant & 1;
   Vp8Container c;
   int st = vp8b_parse_container(data, size, 1, &c);
   if (st != VP8_STATUS_OK) return st;
@@ -26,7 +30,7 @@ extern "C" int emu_decode(const uint8_t* data, size_t size, int csp, int flags, 
   if (c.part0_size > c.frame_size - 10) return VP8_STATUS_NOT_ENOUGH_DATA;
 
   // input arena with padding on both sides, like the device arena
-  std::vector<uint8_t> arena(size + 256, 0xA5);
+  std::vector<uint8_t> arena(size + 64 + 32768 + 64, 0xA5);
   memcpy(arena.data() + 64, data, size);
   ImgDesc im;
   memset(&im, 0, sizeof(im));
@@ -58,8 +62,35 @@ extern "C" int emu_decode(const uint8_t* data, size_t size, int csp, int flags, 
   if (hdr.status != VP8B_OK) return hdr.status;
   if (hdr.num_parts != im.num_parts) return -100;   // host pre-scan disagrees with the device parse
 
-  // K2: tokens, rows interleaved over the partitions in dependency order
-  {
+  // K2: tokens
+  if (!(variant & 2)) {   // lane FSM: one lane per partition, lanes advanced round-robin one iteration at a time
+    const int P = hdr.num_parts;
+    TokImage timg;
+    TokTables ttab;
+    tk_image_fill(&timg, &hdr, P, 0, 1);
+    tk_tables_fill(&ttab, 0, 1);
+    std::vector<uint16_t> topctx((size_t)(P + 1) * mb_w, 0);
+    std::vector<int> progress(P, 0);
+    TokShared sh; sh.img = &timg; sh.img_s = tk_saddr_of(&timg); sh.tab_s = tk_saddr_of(&ttab);
+    sh.topctx = topctx.data(); sh.progress = progress.data();
+    std::vector<TokLane> lanes(P);
+    // the arena buffer is only byte-aligned by the allocator's grace: use a word-aligned view
+    const uintptr_t abase = (uintptr_t)arena.data();
+    const uint32_t* arena32 = (const uint32_t*)(abase & ~(uintptr_t)3);
+    const uint64_t frame_off = (uint64_t)((const uint8_t*)frame - (const uint8_t*)arena32);
+    for (int p = 0; p < P; ++p) tk_lane_init(lanes[p], arena32, frame_off, &hdr, p);
+    for (bool any = true; any;) {
+      any = false;
+      for (int p = P - 1; p >= 0; --p) {   // reverse order: exercises the wait-for-progress path
+        TokLane& L = lanes[p];
+        if (L.phase == 2) continue;
+        any = true;
+        if (L.phase == 0) tk_mb_start(L, sh, im, P, mbinfo.data());
+        if (L.phase == 1) tk_step(L, sh, im, P, arena32, mbinfo.data(), coeffs.data());
+      }
+    }
+    for (int p = 0; p < P && p < mb_h; ++p) if (lanes[p].status != VP8B_OK) hdr.status = lanes[p].status;
+  } else {   // rows interleaved over the partitions in dependency order
     const int P = hdr.num_parts;
     std::vector<TokenPart> tp(P);
     std::vector<uint16_t> topctx((size_t)(P + 1) * mb_w, 0);
