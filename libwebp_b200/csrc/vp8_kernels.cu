@@ -76,32 +76,98 @@ __global__ void k_parse_tokens(const uint8_t* __restrict__ arena, const ImgDesc*
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Lane-parallel token parser (vp8_tokens_fsm.h). A block owns IPB images x P partitions = IPB*P streams; stream j
-// sits in warp j / LPW, lane j % LPW (lanes >= LPW of a warp stay idle: fewer streams per warp means fewer
-// divergent block-end branches per iteration, more streams per warp means fewer issue slots per decode).
-#define TOK_IMG_BYTES 1152   // sizeof(TokImage) rounded up to 16
-#define TOK_TAB_BYTES 192    // sizeof(TokTables)
+// Lane-parallel token parser (vp8_tokens_fsm.h). A block owns ipb images x P partitions = S streams. Stream j
+// sits in parsing warp j / lpw, lane j % lpw (lanes >= lpw of a warp stay idle: fewer streams per warp means
+// fewer divergent block-end branches per iteration, more streams per warp means fewer issue slots per decode).
+// The warp after the `cw` parsing warps is the producer: it keeps the streams' shared-memory rings topped up
+// with cp.async copies from the input arena.
+struct TokLayout {   // byte offsets inside the block's dynamic shared memory
+  uint32_t images, progress, ctl, rings, ctx, total;
+};
+__host__ __device__ static inline TokLayout tok_layout(int P, int ipb, int ctx_stride) {
+  TokLayout t;
+  const uint32_t S = (uint32_t)(ipb * P);
+  t.images = (TOK_TAB_BYTES + 15u) & ~15u;
+  t.progress = t.images + (uint32_t)ipb * TOK_IMG_BYTES;
+  t.ctl = t.progress + (uint32_t)ipb * VP8B_MAX_PARTS * 4u;
+  t.rings = (t.ctl + S * 8u + 15u) & ~15u;
+  t.ctx = t.rings + S * TK_RING_BYTES;
+  t.total = t.ctx + (uint32_t)ipb * (uint32_t)(P + 1) * (uint32_t)ctx_stride * 2u;
+  return t;
+}
 
-template <int LPW>
-__global__ void __launch_bounds__(256) k_parse_tokens_fsm(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
-                                                          FrameHdr* hdrs, uint32_t* mbinfo, int16_t* coeffs,
-                                                          const int* __restrict__ ids, int count, int P, int ipb, int ctx_stride) {
+__global__ void __launch_bounds__(32 * 9) k_parse_tokens_fsm(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
+                                                             FrameHdr* hdrs, uint32_t* mbinfo, int16_t* coeffs,
+                                                             const int* __restrict__ ids, int count, int P, int ipb, int lpw,
+                                                             int cw, int ctx_stride) {
   extern __shared__ __align__(16) uint8_t smem[];
+  const TokLayout lay = tok_layout(P, ipb, ctx_stride);
   TokTables* tables = reinterpret_cast<TokTables*>(smem);
-  uint8_t* img_mem = smem + TOK_TAB_BYTES;                                         // ipb * TOK_IMG_BYTES
-  int* progress = reinterpret_cast<int*>(img_mem + (size_t)ipb * TOK_IMG_BYTES);   // ipb * 8 ints
-  uint16_t* ctx_mem = reinterpret_cast<uint16_t*>(progress + ipb * VP8B_MAX_PARTS); // ipb * (P+1) * ctx_stride
+  uint8_t* img_mem = smem + lay.images;
+  int* progress = reinterpret_cast<int*>(smem + lay.progress);
+  TokStreamCtl* ctl = reinterpret_cast<TokStreamCtl*>(smem + lay.ctl);
+  uint16_t* ctx_mem = reinterpret_cast<uint16_t*>(smem + lay.ctx);
+  const tk_saddr smem_s = tk_saddr_of(smem);
   const int tid = threadIdx.x, nthreads = blockDim.x;
+  const int S = ipb * P;
+  // ---- prologue 1: tables, per-image blocks, progress counters
   tk_tables_fill(tables, tid, nthreads);
   for (int k = tid; k < ipb * VP8B_MAX_PARTS; k += nthreads) progress[k] = 0;
   for (int slot = 0; slot < ipb; ++slot) {
     const int g = blockIdx.x * ipb + slot;
-    if (g < count) tk_image_fill(reinterpret_cast<TokImage*>(img_mem + (size_t)slot * TOK_IMG_BYTES), &hdrs[ids[g]], P, tid, nthreads);
+    TokImage* ti = reinterpret_cast<TokImage*>(img_mem + (size_t)slot * TOK_IMG_BYTES);
+    if (g < count) tk_image_fill(ti, &hdrs[ids[g]], P, tid, nthreads);
+    else if (tid == 0) ti->ok = 0;
+  }
+  __syncthreads();
+  // ---- prologue 2: first fill of every live stream's ring
+  for (int k = tid; k < S * TK_RING_CHUNKS; k += nthreads) {
+    const int j = k / TK_RING_CHUNKS, slot = j / P, part = j % P;
+    const TokImage* ti = reinterpret_cast<const TokImage*>(img_mem + (size_t)slot * TOK_IMG_BYTES);
+    if (!ti->ok) continue;
+    const int img = ids[blockIdx.x * ipb + slot];
+    if (part >= imgs[img].mb_h) continue;
+    tk_stream_prefill(smem_s + lay.rings + (uint32_t)j * TK_RING_BYTES, arena, tk_stream_start(imgs[img].in_off, &hdrs[img], part),
+                      k % TK_RING_CHUNKS);
+  }
+  tk_copy_wait();
+  for (int j = tid; j < S; j += nthreads) {
+    const int slot = j / P, part = j % P;
+    const TokImage* ti = reinterpret_cast<const TokImage*>(img_mem + (size_t)slot * TOK_IMG_BYTES);
+    int live = ti->ok;
+    if (live) {
+      const int img = ids[blockIdx.x * ipb + slot];
+      live = part < imgs[img].mb_h;
+      if (live) tk_stream_open(&ctl[j], tk_stream_start(imgs[img].in_off, &hdrs[img], part));
+    }
+    if (!live) { ctl[j].rd_w = TK_STREAM_DONE; ctl[j].filled_c = 0; }
   }
   __syncthreads();
   const int lane = tid & 31, warp = tid >> 5;
-  const int j = warp * LPW + lane;          // stream inside the block
-  if (lane >= LPW || j >= ipb * P) return;
+  if (warp == cw) {
+    // ---- producer warp: lane l serves streams l, l + 32, ...
+    for (;;) {
+      int live = 0;
+      for (int j = lane; j < S; j += 32) {
+        const tk_saddr ctl_s = smem_s + lay.ctl + (uint32_t)j * 8u;
+        const uint32_t filled = tk_ldsv_u32(ctl_s + 4);
+        const uint32_t nf = tk_stream_topup(ctl_s, smem_s + lay.rings + (uint32_t)j * TK_RING_BYTES, arena, filled);
+        if (nf != 0) live = 1;
+        if (nf > filled) {
+          tk_copy_wait();
+          __threadfence_block();
+          tk_stsv_u32(ctl_s + 4, nf);
+        }
+      }
+      if (!__any_sync(0xffffffffu, live)) break;
+      __nanosleep(400);
+    }
+    return;
+  }
+  if (warp > cw) return;
+  // ---- parsing warps
+  const int j = warp * lpw + lane;          // stream inside the block
+  if (lane >= lpw || j >= S) return;
   const int slot = j / P, part = j % P;
   const int g = blockIdx.x * ipb + slot;
   if (g >= count) return;
@@ -123,12 +189,12 @@ __global__ void __launch_bounds__(256) k_parse_tokens_fsm(const uint8_t* __restr
   sh.progress = progress + slot * VP8B_MAX_PARTS;
   uint32_t* mbi = mbinfo + 4 * (size_t)im.mb_base;
   int16_t* cf = coeffs + (size_t)im.mb_base * VP8B_COEFFS_PER_MB;
-  const uint32_t* arena32 = reinterpret_cast<const uint32_t*>(arena);
   TokLane L;
-  tk_lane_init(L, arena32, im.in_off, h, part);
+  tk_lane_init(L, smem_s + lay.rings + (uint32_t)j * TK_RING_BYTES, smem_s + lay.ctl + (uint32_t)j * 8u, im.in_off, h, part,
+               mbi, im.mb_w, im.mb_h);
   while (L.phase != 2) {
     if (L.phase == 0) tk_mb_start(L, sh, im, P, mbi);
-    if (L.phase == 1) tk_step(L, sh, im, P, arena32, mbi, cf);
+    if (L.phase == 1) tk_step(L, sh, im, P, mbi, cf);
   }
   if (L.status != VP8B_OK) h->status = L.status;
 }
@@ -256,59 +322,51 @@ extern "C" void vp8k_parse_modes(cudaStream_t s, const uint8_t* arena, const Img
   k_parse_modes<<<count, 32, (size_t)max_mb_w * 4, s>>>(arena, imgs, hdrs, mbinfo, first, count);
 }
 
-static size_t tokens_fsm_smem_bytes(int P, int ipb, int max_mb_w) {
-  return TOK_TAB_BYTES + (size_t)ipb * TOK_IMG_BYTES + (size_t)ipb * VP8B_MAX_PARTS * 4 + (size_t)ipb * (P + 1) * max_mb_w * 2;
+static int env_int(const char* name) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : 0;
 }
 
-template <int LPW>
+// Launch geometry of the lane-parallel parser for `count` images of P partitions: cw parsing warps per block
+// (one per SM sub-partition by default), lpw streams per warp chosen so that the whole launch is resident at
+// once where it can be (148 SMs), and as many images per block as its streams hold.
 static void launch_tokens_fsm(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,
-                              int16_t* coeffs, const int* ids, int count, int P, int max_mb_w, int warps) {
-  int ipb = (LPW * warps) / P;                 // images per block
-  if (ipb < 1) ipb = 1;
-  size_t smem = tokens_fsm_smem_bytes(P, ipb, max_mb_w);
-  while (ipb > 1 && smem > 200 * 1024) { ipb >>= 1; smem = tokens_fsm_smem_bytes(P, ipb, max_mb_w); }
-  const int streams = ipb * P;
-  const int threads = ((streams + LPW - 1) / LPW) * 32;
+                              int16_t* coeffs, const int* ids, int count, int P, int max_mb_w) {
+  static int f_lpw = -1, f_cw = -1;
+  if (f_lpw < 0) { f_lpw = env_int("WEBP_B200_TOKEN_LPW"); f_cw = env_int("WEBP_B200_TOKEN_CW"); }
+  int cw = (f_cw >= 1 && f_cw <= 8) ? f_cw : 4;
+  const long streams = (long)count * P;
+  int lpw = (int)((streams + 148L * cw - 1) / (148L * cw));
+  if (f_lpw >= 1 && f_lpw <= 32) lpw = f_lpw;
+  if (lpw < 1) lpw = 1;
+  if (lpw > 32) lpw = 32;
+  while (cw * lpw < P) ++lpw;               // a block holds at least one image
+  int ipb = (cw * lpw) / P;                  // images per block
+  while (ipb > 1 && tok_layout(P, ipb, max_mb_w).total > 200u * 1024u) --ipb;
+  const TokLayout lay = tok_layout(P, ipb, max_mb_w);
   const int blocks = (count + ipb - 1) / ipb;
-  cudaFuncSetAttribute(k_parse_tokens_fsm<LPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_parse_tokens_fsm<LPW><<<blocks, threads, smem, s>>>(arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, ipb, max_mb_w);
-}
-
-// Streams per warp: enough warps to give every SM sub-partition one or two, as few lanes per warp as that allows.
-static int pick_lpw(int streams) {
-  static int forced = -1;
-  if (forced < 0) { const char* e = getenv("WEBP_B200_TOKEN_LPW"); forced = e ? atoi(e) : 0; }
-  if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
-  int lpw = 1;
-  while (lpw < 32 && streams / lpw > 148 * 4 * 2) lpw <<= 1;
-  return lpw;
+  static size_t configured = 0;
+  if (lay.total > configured) {
+    cudaFuncSetAttribute(k_parse_tokens_fsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
+    configured = lay.total;
+  }
+  k_parse_tokens_fsm<<<blocks, 32 * (cw + 1), lay.total, s>>>(arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, ipb, lpw, cw, max_mb_w);
 }
 
 extern "C" void vp8k_parse_tokens(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,
                                   int16_t* coeffs, const int* ids, int count, int P, int max_mb_w) {
-  // Two mappings of the same parse. Few streams (a few per SM sub-partition): one warp per partition, straight-line
-  // code on one lane, latency hidden by the other warps. Many streams: the lane-parallel state machine, which
-  // spends ~8x fewer issue slots per decode. WEBP_B200_TOKEN_MAP=warp|lanes forces one of them (A/B timing).
+  // Two mappings of the same parse: one warp per partition (straight-line code on one lane, latency hidden by
+  // the other warps of the SM) and the lane-parallel state machine. WEBP_B200_TOKEN_MAP=warp|lanes picks one.
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("WEBP_B200_TOKEN_MAP");
-    forced = (e && e[0] == 'w') ? 1 : (e && e[0] == 'l') ? 2 : 0;
+    forced = (e && e[0] == 'w') ? 1 : 2;
   }
-  const int use_warp_map = forced ? (forced == 1) : (count * P < 16384);
-  if (use_warp_map) {
+  if (forced == 1) {
     k_parse_tokens<<<count, 32 * P, tokens_smem_bytes(P, max_mb_w), s>>>(arena, imgs, hdrs, mbinfo, coeffs, ids, P, max_mb_w);
     return;
   }
-  const int lpw = pick_lpw(count * P);
-  const int warps = 2;
-  switch (lpw) {
-    case 1: launch_tokens_fsm<1>(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, max_mb_w, warps); break;
-    case 2: launch_tokens_fsm<2>(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, max_mb_w, warps); break;
-    case 4: launch_tokens_fsm<4>(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, max_mb_w, warps); break;
-    case 8: launch_tokens_fsm<8>(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, max_mb_w, warps); break;
-    case 16: launch_tokens_fsm<16>(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, max_mb_w, warps); break;
-    default: launch_tokens_fsm<32>(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, max_mb_w, warps); break;
-  }
+  launch_tokens_fsm(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, max_mb_w);
 }
 
 extern "C" void vp8k_reconstruct(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, uint32_t* mbinfo, const int16_t* coeffs,

@@ -7,6 +7,12 @@
 // (GetCoeffs' nested loops and GetLargeValue's branches, src/dec/vp8_dec.c:411-469, become table rows).
 // Only block ends (every ~18 decodes), the rare large-value categories and macroblock starts branch.
 //
+// The parsing warps never touch the compressed bytes in HBM: a PRODUCER warp of the same thread block streams
+// every partition through a 256-byte shared-memory ring with 16-byte cp.async copies, far ahead of the reader,
+// so no parsing warp ever waits on a global load (a warp-wide scoreboard stall would hold back all its lanes).
+// Ring protocol per stream: the reader publishes the next word it will read (rd_w), the producer the first
+// 16-byte chunk that is not in the ring yet (filled_c); chunk c lives in slot c & 15.
+//
 // Everything on the per-decode path is 32-bit: shared-window addresses for the probabilities and tables,
 // a word index into the input arena, an element index into the coefficient plane.
 //
@@ -26,10 +32,21 @@ typedef uint32_t tk_saddr;   // address inside the shared-memory window
 TK_FN tk_saddr tk_saddr_of(const void* p) { return (tk_saddr)__cvta_generic_to_shared(p); }
 TK_FN uint32_t tk_lds_u8(tk_saddr a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 TK_FN uint32_t tk_lds_u16(tk_saddr a) { uint32_t v; asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+TK_FN uint32_t tk_lds_u32(tk_saddr a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 TK_FN void tk_lds_v2(tk_saddr a, uint32_t& x, uint32_t& y) { asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(a)); }
+// ring words and the ring protocol words change under the reader's feet: volatile accesses
+TK_FN uint32_t tk_ldsv_u32(tk_saddr a) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+TK_FN void tk_stsv_u32(tk_saddr a, uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 TK_FN uint32_t tk_shr_clamp(uint32_t w, int n) { return __funnelshift_rc(w, 0u, (uint32_t)n); }   // w >> n, 0 when n >= 32
+TK_FN uint32_t tk_shl_clamp(uint32_t w, int n) { return __funnelshift_lc(0u, w, (uint32_t)n); }   // w << n, 0 when n >= 32
 TK_FN uint32_t tk_shl_pair(uint32_t hi, uint32_t lo, int n) { return __funnelshift_l(lo, hi, (uint32_t)n); }
+TK_FN void tk_copy16(tk_saddr dst, const uint8_t* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+TK_FN void tk_copy_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+TK_FN uint32_t tk_ldg_u32(const uint32_t* p) { return __ldg(p); }
 #else
+#include <string.h>
 #define TK_FN static inline
 #define TK_CLZ(x) __builtin_clz((unsigned)(x))
 #define TK_BSWAP(x) __builtin_bswap32(x)
@@ -38,9 +55,16 @@ typedef uintptr_t tk_saddr;
 TK_FN tk_saddr tk_saddr_of(const void* p) { return (tk_saddr)p; }
 TK_FN uint32_t tk_lds_u8(tk_saddr a) { return *(const uint8_t*)a; }
 TK_FN uint32_t tk_lds_u16(tk_saddr a) { return *(const uint16_t*)a; }
+TK_FN uint32_t tk_lds_u32(tk_saddr a) { return *(const uint32_t*)a; }
 TK_FN void tk_lds_v2(tk_saddr a, uint32_t& x, uint32_t& y) { x = ((const uint32_t*)a)[0]; y = ((const uint32_t*)a)[1]; }
+TK_FN uint32_t tk_ldsv_u32(tk_saddr a) { return *(volatile const uint32_t*)a; }
+TK_FN void tk_stsv_u32(tk_saddr a, uint32_t v) { *(volatile uint32_t*)a = v; }
 TK_FN uint32_t tk_shr_clamp(uint32_t w, int n) { return n >= 32 ? 0u : (w >> n); }
+TK_FN uint32_t tk_shl_clamp(uint32_t w, int n) { return n >= 32 ? 0u : (w << n); }
 TK_FN uint32_t tk_shl_pair(uint32_t hi, uint32_t lo, int n) { return n == 0 ? hi : ((hi << n) | (lo >> (32 - n))); }
+TK_FN void tk_copy16(tk_saddr dst, const uint8_t* src) { memcpy((void*)dst, src, 16); }
+TK_FN void tk_copy_wait() {}
+TK_FN uint32_t tk_ldg_u32(const uint32_t* p) { return *p; }
 #endif
 
 // ---- token-tree states
@@ -102,24 +126,52 @@ enum { S_P0 = 0, S_P1, S_P2, S_P3, S_P4, S_P5, S_P6, S_P7, S_P8, S_P9, S_P10, S_
   /* EXTRA*/ { TE_(S_EXTRA, 1, 2, 0, TE_EXTRA),                      TE_(S_EXTRA, 1, 2, 1, TE_EXTRA) },          \
   /* SIGN */ { TE_(S_P0, 0, 1, 0, TE_EMIT | TE_NEWCOEF),             TE_(S_P0, 0, 1, 0, TE_EMIT | TE_NEG | TE_NEWCOEF) } }
 
+// ---- block sequence word, one per block of a macroblock in parse order (seq 0 = Y2, 1..16 luma, 17..24 chroma)
+//  [3:0] bit of the top context  [7:4] bit of the left context  [12:8] shift of the 2-bit nz code
+//  13 chroma  14 luma  [16:15] block type when the macroblock is i16 (luma of i4x4 macroblocks: type 3)
+//  [18:17] dequantiser pair  [23:19] block index inside the macroblock's coefficients
+#define TQ_TB(q) ((q) & 15u)
+#define TQ_LB(q) (((q) >> 4) & 15u)
+#define TQ_NZSH(q) (((q) >> 8) & 31u)
+#define TQ_CHROMA (1u << 13)
+#define TQ_LUMA (1u << 14)
+#define TQ_TYPE(q) (((q) >> 15) & 3u)
+#define TQ_QPAIR(q) (((q) >> 17) & 3u)
+#define TQ_BLK(q) (((q) >> 19) & 31u)
+
 // Block-wide constant tables in shared memory (filled by tk_tables_fill).
 struct TokTables {
   uint32_t trans[16][2];   // 128 B
   uint16_t band_off[18];   // band(n) * 33 for n = 0..16 (+ one spare), at byte offset 128
   uint8_t zigzag[16];      // at byte offset 164
   uint8_t pad[12];
+  uint32_t seq[28];        // at byte offset 192
 };
 #define TKT_BAND 128
 #define TKT_ZIGZAG 164
+#define TKT_SEQ 192
+#define TOK_TAB_BYTES 304    // sizeof(TokTables)
 
 // Shared-memory block of one image: probabilities, token constants, dequantisers, flags.
 struct TokImage {
   uint8_t prob[1056];          // [type][band][ctx][node]
   uint8_t consts[TKC_BYTES];   // at offset 1056
-  int16_t dq[4][6];            // per segment: y1 dc/ac, y2 dc/ac, uv dc/ac
+  int16_t dq[4][6];            // per segment: y1 dc/ac, y2 dc/ac, uv dc/ac; at offset 1084
   int32_t ok;                  // header parsed and the partition count matches the launch
   int32_t use_skip;
-  int32_t pad[2];
+  int32_t pad[3];
+};
+#define TKI_CONSTS 1056
+#define TKI_DQ 1084
+#define TOK_IMG_BYTES 1152   // sizeof(TokImage)
+
+// Shared-memory ring of one stream and its protocol words.
+#define TK_RING_BYTES 256
+#define TK_RING_CHUNKS 16
+#define TK_STREAM_DONE 0xffffffffu
+struct TokStreamCtl {
+  uint32_t rd_w;       // reader -> producer: next arena word the reader will fetch; TK_STREAM_DONE when finished
+  uint32_t filled_c;   // producer -> reader: first 16-byte chunk (absolute arena chunk index) not yet in the ring
 };
 
 // Per-lane state (registers). phase: 0 = needs a macroblock, 1 = decoding, 2 = finished.
@@ -129,7 +181,10 @@ struct TokLane {
   int nbits;
   uint32_t range;
   uint32_t wi;        // next word of the stream, as an index into the arena viewed as uint32[]
+  uint32_t avail_w;   // words below this index are known to be in the ring
   int shift;          // renormalisation shift of the most recent decode
+  tk_saddr ring_s;    // this stream's ring
+  tk_saddr ctl_s;     // this stream's TokStreamCtl
   // token tree
   uint32_t state8;    // state * 8
   tk_saddr pp;        // shared address of the next probability
@@ -140,6 +195,7 @@ struct TokLane {
   int extra_left, cat;
   // block
   int seq;            // 0 = Y2, 1..16 luma, 17..24 chroma; 25 = macroblock done
+  uint32_t sq;        // block sequence word of `seq`
   int first, dcnz;
   uint32_t tnz, lnz;  // bit 0-3 luma, 4-5 U, 6-7 V, 8 Y2
   uint32_t nzy, nzuv;
@@ -147,7 +203,8 @@ struct TokLane {
   uint32_t outi;      // index of the current block's first coefficient inside the image's coefficient plane
   // macroblock / partition
   int mx, my, part, done_mbs, phase, status;
-  uint32_t w;
+  uint32_t w;         // MbInfo word 3 of the current macroblock
+  uint32_t w_next;    // ... of this partition's next macroblock (fetched one macroblock ahead)
   int seg;
   // stream geometry for the end-of-data test (bits)
   int64_t pos_bias;   // stream bits loaded = 32 * wi - pos_bias
@@ -170,6 +227,20 @@ TK_FN void tk_tables_fill(TokTables* t, int tid, int nthreads) {
   for (int k = tid; k < 32; k += nthreads) t->trans[k >> 1][k & 1] = trans[k >> 1][k & 1];
   for (int k = tid; k < 18; k += nthreads) t->band_off[k] = (uint16_t)((k < 17 ? bands[k] : 0) * 33);
   for (int k = tid; k < 16; k += nthreads) t->zigzag[k] = zz[k];
+  for (int k = tid; k < 28; k += nthreads) {
+    uint32_t q = 0;
+    if (k == 0) {                      // Y2: context bit 8 on both sides, type 1, y2 dequantisers, block 24
+      q = 8u | (8u << 4) | (1u << 15) | (1u << 17) | (24u << 19);
+    } else if (k <= 16) {              // luma block k-1
+      const uint32_t blk = (uint32_t)k - 1;
+      q = (blk & 3) | ((blk >> 2) << 4) | ((30 - 2 * blk) << 8) | TQ_LUMA | (0u << 15) | (0u << 17) | (blk << 19);
+    } else if (k <= 24) {              // chroma block c: U 0-3, V 4-7
+      const uint32_t c = (uint32_t)k - 17, blk = 16 + c;
+      const uint32_t tb = 4 + (c & 1) + 2 * (c >> 2), lb = 4 + ((c >> 1) & 1) + 2 * (c >> 2);
+      q = tb | (lb << 4) | ((8 * (c >> 2) + 6 - 2 * (c & 3)) << 8) | TQ_CHROMA | (2u << 15) | (2u << 17) | (blk << 19);
+    }
+    t->seq[k] = q;
+  }
 }
 
 // Fills the shared per-image block from the parsed frame header (any thread subset may call with its slice).
@@ -181,16 +252,46 @@ TK_FN void tk_image_fill(TokImage* im, const FrameHdr* h, int P, int tid, int nt
   if (tid == 0) { im->ok = (h->status == VP8B_OK && h->num_parts == P) ? 1 : 0; im->use_skip = h->use_skip; }
 }
 
-// Lane for token partition `part` of an image. `arena32` = the input arena as words, frame_off = byte offset
-// of the frame tag inside it. The arena is padded by >= 32 KB so that a lane that ran past the end of its
-// stream (detected at the next macroblock boundary) never leaves the allocation.
-TK_FN void tk_lane_init(TokLane& L, const uint32_t* arena32, uint64_t frame_off, const FrameHdr* h, int part) {
-  const uint64_t a = frame_off + h->part_off[part];
+// ---- producer side of the ring -------------------------------------------------------------------------
+// First fill of one chunk slot (k = 0..15) of a stream starting at arena byte `a`; every thread of the block
+// takes some (stream, k) pairs, then tk_copy_wait() + a block barrier, then tk_stream_open() by one thread.
+TK_FN void tk_stream_prefill(tk_saddr ring_s, const uint8_t* arena, uint64_t a, int k) {
+  const uint64_t c = (a >> 4) + (uint64_t)k;
+  tk_copy16(ring_s + (uint32_t)((c & (TK_RING_CHUNKS - 1)) * 16), arena + 16 * c);
+}
+TK_FN void tk_stream_open(TokStreamCtl* ctl, uint64_t a) {
+  ctl->rd_w = (uint32_t)(a >> 2);
+  ctl->filled_c = (uint32_t)(a >> 4) + TK_RING_CHUNKS;
+}
+// One top-up of one stream by its producer lane: issues the copies of every chunk whose slot the reader has
+// left, returns the new filled_c (to be published with tk_stsv_u32 after tk_copy_wait() and a fence), or 0
+// when the reader has finished. *filled = the value published last time.
+TK_FN uint32_t tk_stream_topup(tk_saddr ctl_s, tk_saddr ring_s, const uint8_t* arena, uint32_t filled) {
+  const uint32_t rd_w = tk_ldsv_u32(ctl_s);
+  if (rd_w == TK_STREAM_DONE) return 0;
+  const uint32_t lim = (rd_w >> 2) + TK_RING_CHUNKS;   // chunk c overwrites chunk c-16, which must lie behind the reader
+  uint32_t c = filled;
+  for (; c < lim; ++c) tk_copy16(ring_s + (c & (TK_RING_CHUNKS - 1)) * 16, arena + 16 * (uint64_t)c);
+  return c;
+}
+
+// ---- reader side -----------------------------------------------------------------------------------------
+// Lane for token partition `part` of an image. frame_off = byte offset of the frame tag inside the arena.
+// The arena is padded by >= 32 KB so that neither a lane that ran past the end of its stream (detected at the
+// next macroblock boundary) nor the producer's read-ahead ever leaves the allocation.
+TK_FN uint64_t tk_stream_start(uint64_t frame_off, const FrameHdr* h, int part) { return frame_off + h->part_off[part]; }
+
+TK_FN void tk_lane_init(TokLane& L, tk_saddr ring_s, tk_saddr ctl_s, uint64_t frame_off, const FrameHdr* h, int part,
+                        const uint32_t* mbinfo, int mb_w, int mb_h) {
+  const uint64_t a = tk_stream_start(frame_off, h, part);
   const uint32_t size = h->part_size[part];
   const int off = (int)(a & 3);
+  L.ring_s = ring_s; L.ctl_s = ctl_s;
   L.wi = (uint32_t)(a >> 2);
-  const uint32_t w0 = TK_BSWAP(arena32[L.wi]);
+  L.avail_w = ((uint32_t)(a >> 4) + TK_RING_CHUNKS) * 4;
+  const uint32_t w0 = TK_BSWAP(tk_ldsv_u32(ring_s + ((L.wi & (TK_RING_BYTES / 4 - 1)) << 2)));
   L.wi++;
+  tk_stsv_u32(ctl_s, L.wi);
   L.vhi = (off == 0) ? w0 : (w0 << (8 * off));
   L.vlo = 0;
   L.nbits = 32 - 8 * off;
@@ -200,8 +301,9 @@ TK_FN void tk_lane_init(TokLane& L, const uint32_t* arena32, uint64_t frame_off,
   L.limit = 8 * (int64_t)size - 8;
   L.state8 = 0; L.pp = 0; L.pnb = 0; L.pbase = 0;
   L.v = 0; L.n = 0; L.nc11 = 0; L.extra_left = 0; L.cat = 0;
-  L.seq = 0; L.first = 0; L.dcnz = 0; L.tnz = 0; L.lnz = 0; L.nzy = 0; L.nzuv = 0; L.dq = 0; L.outi = 0;
+  L.seq = 0; L.sq = 0; L.first = 0; L.dcnz = 0; L.tnz = 0; L.lnz = 0; L.nzy = 0; L.nzuv = 0; L.dq = 0; L.outi = 0;
   L.mx = 0; L.my = part; L.part = part; L.done_mbs = 0; L.phase = 0; L.status = VP8B_OK; L.w = 0; L.seg = 0;
+  L.w_next = (part < mb_h) ? tk_ldg_u32(mbinfo + 4 * ((size_t)part * mb_w) + 3) : 0;
 }
 
 // The reference's eof_ flag from bit positions (see vp8_parse_core.h:bd_eof).
@@ -210,55 +312,42 @@ TK_FN int tk_eof(const TokLane& L) {
   return (loaded - L.nbits - L.shift) > L.limit;
 }
 
-// Sets up block `seq` of the current macroblock (context, probabilities, dequantisers, output index).
-TK_FN void tk_block_setup(TokLane& L, const TokShared& sh, uint32_t mb_coef_index) {
-  const int seq = L.seq;
-  const int is_i4 = (L.w & MBW_I4X4) != 0;
-  int blk, tb, lb, type, qi;
-  if (seq == 0) { blk = 24; tb = 8; lb = 8; type = 1; qi = 2; }
-  else {
-    blk = seq - 1;
-    if (blk < 16) { tb = blk & 3; lb = blk >> 2; type = is_i4 ? 3 : 0; qi = 0; }
-    else { const int c = blk - 16; tb = 4 + (c & 1) + 2 * (c >> 2); lb = 4 + ((c >> 1) & 1) + 2 * (c >> 2); type = 2; qi = 4; }
-  }
-  const uint32_t ctx = ((L.tnz >> tb) & 1) + ((L.lnz >> lb) & 1);
-  const int16_t* q = sh.img->dq[L.seg];
-  L.dq = (uint32_t)(uint16_t)q[qi] | ((uint32_t)(uint16_t)q[qi + 1] << 16);
-  L.first = (blk < 16 && !is_i4) ? 1 : 0;
-  L.n = L.first;
-  L.pbase = sh.img_s + (uint32_t)type * 264u;
-  L.pp = L.pbase + (uint32_t)L.first * 33u + ctx * 11u;
-  L.pnb = L.pbase + tk_lds_u16(sh.tab_s + TKT_BAND + 2 * (L.n + 1));
-  L.state8 = S_P0 * 8;
-  L.dcnz = 0;
-  L.outi = mb_coef_index + (uint32_t)blk * 16u;
+TK_FN void tk_lane_finish(TokLane& L) {
+  L.phase = 2;
+  tk_stsv_u32(L.ctl_s, TK_STREAM_DONE);
 }
 
-// Finishes block `seq` with return value nz (GetCoeffs), updates contexts and nz codes (vp8_dec.c:517-609).
+// Sets up block L.seq of the current macroblock (context, probabilities, dequantisers, output index).
+TK_FN void tk_block_setup(TokLane& L, const TokShared& sh, uint32_t mb_coef_index) {
+  const uint32_t q = tk_lds_u32(sh.tab_s + TKT_SEQ + 4u * (uint32_t)L.seq);
+  const uint32_t i4_luma = ((q & TQ_LUMA) && (L.w & MBW_I4X4)) ? 1u : 0u;
+  const uint32_t i16_luma = (q & TQ_LUMA) ? 1u - i4_luma : 0u;
+  const uint32_t type = i4_luma ? 3u : TQ_TYPE(q);
+  const uint32_t ctx = ((L.tnz >> TQ_TB(q)) & 1u) + ((L.lnz >> TQ_LB(q)) & 1u);
+  L.sq = q;
+  L.dq = tk_lds_u32(sh.img_s + TKI_DQ + 12u * (uint32_t)L.seg + 4u * TQ_QPAIR(q));
+  L.first = (int)i16_luma;
+  L.n = (int)i16_luma;
+  L.pbase = sh.img_s + type * 264u;
+  L.pp = L.pbase + i16_luma * 33u + ctx * 11u;
+  L.pnb = L.pbase + (i16_luma ? 66u : 33u);   // band(n + 1) * 33 for n = 1 / n = 0
+  L.state8 = S_P0 * 8;
+  L.dcnz = 0;
+  L.outi = mb_coef_index + TQ_BLK(q) * 16u;
+}
+
+// Finishes block L.seq with return value nz (GetCoeffs), updates contexts and nz codes (vp8_dec.c:517-609).
 TK_FN void tk_block_end(TokLane& L, int nz) {
-  const int seq = L.seq;
-  if (seq == 0) {
-    const uint32_t f = (nz > 0) ? 0x100u : 0u;
-    L.tnz = (L.tnz & 0xffu) | f;
-    L.lnz = (L.lnz & 0xffu) | f;
-    if (nz > 0) L.w |= MBW_HAS_Y2;
-  } else {
-    const int blk = seq - 1;
-    const uint32_t code = (nz > 3) ? 3u : (nz > 1) ? 2u : (uint32_t)L.dcnz;
-    const uint32_t l = (nz > L.first) ? 1u : 0u;
-    int tb, lb;
-    if (blk < 16) {
-      tb = blk & 3; lb = blk >> 2;
-      L.nzy |= code << (30 - 2 * blk);
-    } else {
-      const int c = blk - 16;
-      tb = 4 + (c & 1) + 2 * (c >> 2); lb = 4 + ((c >> 1) & 1) + 2 * (c >> 2);
-      L.nzuv |= code << (8 * (c >> 2) + 6 - 2 * (c & 3));
-    }
-    L.tnz = (L.tnz & ~(1u << tb)) | (l << tb);
-    L.lnz = (L.lnz & ~(1u << lb)) | (l << lb);
-  }
-  L.seq = seq + 1;
+  const uint32_t q = L.sq;
+  const uint32_t tb = TQ_TB(q), lb = TQ_LB(q);
+  const uint32_t l = (nz > L.first) ? 1u : 0u;
+  const uint32_t code = ((nz > 3) ? 3u : (nz > 1) ? 2u : (uint32_t)L.dcnz) << TQ_NZSH(q);
+  if (q & TQ_LUMA) L.nzy |= code;
+  if (q & TQ_CHROMA) L.nzuv |= code;
+  if (!(q & (TQ_LUMA | TQ_CHROMA)) && nz > 0) L.w |= MBW_HAS_Y2;
+  L.tnz = (L.tnz & ~(1u << tb)) | (l << tb);
+  L.lnz = (L.lnz & ~(1u << lb)) | (l << lb);
+  L.seq++;
 }
 
 // Writes the macroblock's results and advances to the next one.
@@ -275,7 +364,7 @@ TK_FN void tk_mb_finish(TokLane& L, const TokShared& sh, const ImgDesc& im, int 
     // Ran past the end of the partition: the image is lost (vp8_dec.c:651-659). Stop reading the bitstream and
     // release every partition that waits on this one.
     L.status = VP8B_NOT_ENOUGH_DATA;
-    L.phase = 2;
+    tk_lane_finish(L);
     if (P > 1) { TK_FENCE(); sh.progress[L.part] = 0x7fffffff; }
     return;
   }
@@ -286,7 +375,7 @@ TK_FN void tk_mb_finish(TokLane& L, const TokShared& sh, const ImgDesc& im, int 
 // when the partition owning the row above has not got far enough yet (the caller simply retries).
 TK_FN void tk_mb_start(TokLane& L, const TokShared& sh, const ImgDesc& im, int P, uint32_t* mbinfo) {
   const int mb_w = im.mb_w;
-  if (L.my >= im.mb_h) { L.phase = 2; return; }
+  if (L.my >= im.mb_h) { tk_lane_finish(L); return; }
   uint32_t tctx = 0;
   if (L.my > 0) {
     if (P > 1) {
@@ -298,7 +387,12 @@ TK_FN void tk_mb_start(TokLane& L, const TokShared& sh, const ImgDesc& im, int P
     tctx = sh.topctx[(size_t)((L.my + P) % (P + 1)) * mb_w + L.mx];
   }
   const size_t idx = (size_t)L.my * mb_w + L.mx;
-  L.w = mbinfo[4 * idx + 3];
+  L.w = L.w_next;
+  {   // fetch the flags of this partition's next macroblock now; they are needed one macroblock from here
+    int nx = L.mx + 1, ny = L.my;
+    if (nx == mb_w) { nx = 0; ny += P; }
+    if (ny < im.mb_h) L.w_next = tk_ldg_u32(mbinfo + 4 * ((size_t)ny * mb_w + nx) + 3);
+  }
   L.seg = (int)((L.w >> MBW_SEG_SHIFT) & 3);
   L.tnz = tctx;
   if (L.mx == 0) L.lnz = 0;
@@ -316,18 +410,23 @@ TK_FN void tk_mb_start(TokLane& L, const TokShared& sh, const ImgDesc& im, int P
 }
 
 // One iteration of a lane in phase 1: one boolean decode and its consequences.
-//   arena32 : input arena as words          coeffs : this image's coefficient plane (int16, pre-zeroed)
-TK_FN void tk_step(TokLane& L, const TokShared& sh, const ImgDesc& im, int P, const uint32_t* arena32,
-                   uint32_t* mbinfo, int16_t* coeffs) {
+//   coeffs : this image's coefficient plane (int16, pre-zeroed)
+TK_FN void tk_step(TokLane& L, const TokShared& sh, const ImgDesc& im, int P, uint32_t* mbinfo, int16_t* coeffs) {
   const uint32_t prob = tk_lds_u8(L.pp);
   uint32_t e0, e1;
   tk_lds_v2(sh.tab_s + L.state8, e0, e1);
   // ---- boolean decode (bit_reader_inl_utils.h:107-136, range kept minus one)
   if (L.nbits <= 32) {   // vlo is empty: append one big-endian word behind the valid bits
-    const uint32_t w = TK_BSWAP(arena32[L.wi]);
+    if (L.wi >= L.avail_w) {   // first look at what the producer has published since
+      L.avail_w = tk_ldsv_u32(L.ctl_s + 4) * 4u;
+      if (L.wi >= L.avail_w) return;   // the ring has run dry (start-up only): try again next iteration
+      TK_FENCE();
+    }
+    const uint32_t w = TK_BSWAP(tk_ldsv_u32(L.ring_s + ((L.wi & (TK_RING_BYTES / 4 - 1)) << 2)));
     L.wi++;
+    tk_stsv_u32(L.ctl_s, L.wi);
     L.vhi |= tk_shr_clamp(w, L.nbits);
-    L.vlo = w << (32 - L.nbits);
+    L.vlo = tk_shl_clamp(w, 32 - L.nbits);
     L.nbits += 32;
   }
   const uint32_t split = (L.range * prob) >> 8;
@@ -344,7 +443,7 @@ TK_FN void tk_step(TokLane& L, const TokShared& sh, const ImgDesc& im, int P, co
   const uint32_t e = bit ? e1 : e0;
   L.v = L.v * (int)TE_VMUL(e) + (int)TE_VADD(e);
   L.state8 = TE_STATE8(e);
-  tk_saddr pp = ((e & TE_ABS) ? (sh.img_s + 1056u) : L.pp) + TE_OFF(e);
+  tk_saddr pp = ((e & TE_ABS) ? (sh.img_s + TKI_CONSTS) : L.pp) + TE_OFF(e);
   const uint32_t cs = TE_CTX(e);
   L.nc11 = cs ? cs * 11u : L.nc11;
   if (e & (TE_CAT | TE_EXTRA)) {   // DCT_CAT3..6: rare
@@ -354,7 +453,7 @@ TK_FN void tk_step(TokLane& L, const TokShared& sh, const ImgDesc& im, int P, co
     } else if (--L.extra_left == 0) {
       L.v += 3 + (8 << L.cat);
       L.state8 = S_SIGN * 8;
-      pp = sh.img_s + 1056u + TKC_SIGN;
+      pp = sh.img_s + TKI_CONSTS + TKC_SIGN;
     }
   }
   int done = -1;

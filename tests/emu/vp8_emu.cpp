@@ -20,6 +20,7 @@
 
 // variant bit 0: visit the macroblocks of a wavefront step in reverse order
 // variant bit 1: token parse with the row-at-a-time reference port (parse_token_row) instead of the lane FSM
+// variant bit 2: lane FSM with a lazy ring producer
 extern "C" int emu_decode(const uint8_t* data, size_t size, int csp, int flags, uint8_t* out, size_t out_size,
                           int stride, int variant, uint8_t* unfiltered /* optional: y|u|v padded */) {
   const int reverse_steps = variant & 1;
@@ -74,19 +75,39 @@ extern "C" int emu_decode(const uint8_t* data, size_t size, int csp, int flags, 
     TokShared sh; sh.img = &timg; sh.img_s = tk_saddr_of(&timg); sh.tab_s = tk_saddr_of(&ttab);
     sh.topctx = topctx.data(); sh.progress = progress.data();
     std::vector<TokLane> lanes(P);
-    // the arena buffer is only byte-aligned by the allocator's grace: use a word-aligned view
+    // the arena buffer is only byte-aligned by the allocator's grace: use a 16-byte aligned view
     const uintptr_t abase = (uintptr_t)arena.data();
-    const uint32_t* arena32 = (const uint32_t*)(abase & ~(uintptr_t)3);
-    const uint64_t frame_off = (uint64_t)((const uint8_t*)frame - (const uint8_t*)arena32);
-    for (int p = 0; p < P; ++p) tk_lane_init(lanes[p], arena32, frame_off, &hdr, p);
+    const uint8_t* arena16 = (const uint8_t*)(abase & ~(uintptr_t)15);
+    const uint64_t frame_off = (uint64_t)((const uint8_t*)frame - arena16);
+    // one shared-memory ring + protocol block per stream, topped up by an emulated producer
+    std::vector<uint8_t> ringmem((size_t)P * TK_RING_BYTES + 16);
+    uint8_t* rings = (uint8_t*)(((uintptr_t)ringmem.data() + 15) & ~(uintptr_t)15);
+    std::vector<TokStreamCtl> ctl(P);
+    for (int p = 0; p < P; ++p) {
+      if (p >= mb_h) { ctl[p].rd_w = TK_STREAM_DONE; ctl[p].filled_c = 0; continue; }
+      const uint64_t a = tk_stream_start(frame_off, &hdr, p);
+      for (int k = 0; k < TK_RING_CHUNKS; ++k) tk_stream_prefill(tk_saddr_of(rings + (size_t)p * TK_RING_BYTES), arena16, a, k);
+      tk_stream_open(&ctl[p], a);
+      tk_lane_init(lanes[p], tk_saddr_of(rings + (size_t)p * TK_RING_BYTES), tk_saddr_of(&ctl[p]), frame_off, &hdr, p,
+                   mbinfo.data(), mb_w, mb_h);
+    }
+    for (int p = mb_h; p < P; ++p) lanes[p].phase = 2;
+    const long topup_every = (variant & 4) ? 3000 : 40;   // variant bit 2: a lazy producer (readers find the ring dry)
+    long iter = 0;
     for (bool any = true; any;) {
       any = false;
+      if (iter++ % topup_every == 0) {
+        for (int p = 0; p < P; ++p) {
+          const uint32_t nf = tk_stream_topup(tk_saddr_of(&ctl[p]), tk_saddr_of(rings + (size_t)p * TK_RING_BYTES), arena16, ctl[p].filled_c);
+          if (nf > ctl[p].filled_c) ctl[p].filled_c = nf;
+        }
+      }
       for (int p = P - 1; p >= 0; --p) {   // reverse order: exercises the wait-for-progress path
         TokLane& L = lanes[p];
         if (L.phase == 2) continue;
         any = true;
         if (L.phase == 0) tk_mb_start(L, sh, im, P, mbinfo.data());
-        if (L.phase == 1) tk_step(L, sh, im, P, arena32, mbinfo.data(), coeffs.data());
+        if (L.phase == 1) tk_step(L, sh, im, P, mbinfo.data(), coeffs.data());
       }
     }
     for (int p = 0; p < P && p < mb_h; ++p) if (lanes[p].status != VP8B_OK) hdr.status = lanes[p].status;

@@ -1,3 +1,5 @@
+#!/bin/bash
+# GPU box: A/B timing of the token-parse mappings (not a bench line: numbers go to gpurun_out/ only).
 mkdir -p gpurun_out
 show() { python - "$1" <<'PY'
 import json,sys
@@ -6,14 +8,20 @@ d=json.loads(l[-1]) if l else None
 print(sys.argv[1], d and (d["value"], d["ms_per_step"], {k:v["ms"] for k,v in d["kernels"].items()}))
 PY
 }
-timeout 300 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
-B="python bench.py --distinct 64 --steps 3 --e2e-steps 0 --no-cpu-baseline"
-WEBP_B200_TOKEN_MAP=lanes WEBP_B200_TOKEN_LPW=4 $B > gpurun_out/h_l4.log 2>&1; show gpurun_out/h_l4.log
-WEBP_B200_TOKEN_MAP=lanes WEBP_B200_TOKEN_LPW=8 $B > gpurun_out/h_l8.log 2>&1; show gpurun_out/h_l8.log
-T="$B --workload vp8_256x256_q80_rgbA --distinct 512"
-WEBP_B200_TOKEN_MAP=warp $T > gpurun_out/t_warp.log 2>&1; show gpurun_out/t_warp.log
-for l in 8 16 32; do WEBP_B200_TOKEN_MAP=lanes WEBP_B200_TOKEN_LPW=$l $T > gpurun_out/t_l$l.log 2>&1; show gpurun_out/t_l$l.log; done
-W="$B --workload vp8_1080p_q75_m4_8part_normal_rgba"
-WEBP_B200_TOKEN_MAP=warp $W > gpurun_out/p8_warp.log 2>&1; show gpurun_out/p8_warp.log
-for l in 8 32; do WEBP_B200_TOKEN_MAP=lanes WEBP_B200_TOKEN_LPW=$l $W > gpurun_out/p8_l$l.log 2>&1; show gpurun_out/p8_l$l.log; done
-tail -3 gpurun_out/t_l32.log | cut -c1-300
+timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+B="python bench.py --distinct 64 --steps 2 --e2e-steps 0 --no-cpu-baseline"
+run() { name=$1; shift; env "$@" $B $EXTRA > gpurun_out/$name.log 2>&1; show gpurun_out/$name.log; }
+EXTRA=""
+run h_default WEBP_B200_TOKEN_MAP=lanes
+run h_cw8_l4 WEBP_B200_TOKEN_CW=8 WEBP_B200_TOKEN_LPW=4
+run h_cw8_l7 WEBP_B200_TOKEN_CW=8 WEBP_B200_TOKEN_LPW=7
+run h_cw4_l14 WEBP_B200_TOKEN_CW=4 WEBP_B200_TOKEN_LPW=14
+run h_cw2_l14 WEBP_B200_TOKEN_CW=2 WEBP_B200_TOKEN_LPW=14
+EXTRA="--workload vp8_256x256_q80_rgbA --distinct 512"
+run t_default WEBP_B200_TOKEN_MAP=lanes
+run t_cw8 WEBP_B200_TOKEN_CW=8
+run t_cw4_l16 WEBP_B200_TOKEN_CW=4 WEBP_B200_TOKEN_LPW=16
+EXTRA="--workload vp8_1080p_q75_m4_8part_normal_rgba"
+run p8_default WEBP_B200_TOKEN_MAP=lanes
+run p8_cw8 WEBP_B200_TOKEN_CW=8
+run p8_cw4_l16 WEBP_B200_TOKEN_CW=4 WEBP_B200_TOKEN_LPW=16
