@@ -35,8 +35,10 @@ typedef enum WebPBatchMemory {
 typedef struct WebPBatchOptions {
   int device;                /* CUDA device ordinal, -1 = the calling thread's current device */
   WebPBatchMemory output;    /* where decoded pixels end up */
-  size_t scratch_bytes;      /* cap on device scratch per wave (0 = default: 40% of free memory) */
-  uint32_t pad[8];
+  size_t scratch_bytes;      /* cap on device scratch per wave (0 = default: 85% of free memory) */
+  int pipeline_waves;        /* split the batch into this many waves (0 = default: one wave unless scratch memory
+                                forces more; downloads overlap the pixel stages chunk by chunk either way) */
+  uint32_t pad[7];
 } WebPBatchOptions;
 
 WEBP_EXTERN int WebPBatchOptionsInitInternal(WebPBatchOptions*, int);

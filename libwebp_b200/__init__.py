@@ -73,7 +73,8 @@ class WebPBatchItem(C.Structure):
 
 
 class WebPBatchOptions(C.Structure):
-    _fields_ = [("device", C.c_int), ("output", C.c_int), ("scratch_bytes", C.c_size_t), ("pad", C.c_uint32 * 8)]
+    _fields_ = [("device", C.c_int), ("output", C.c_int), ("scratch_bytes", C.c_size_t),
+                ("pipeline_waves", C.c_int), ("pad", C.c_uint32 * 7)]
 
 
 class WebPBatchPlane(C.Structure):

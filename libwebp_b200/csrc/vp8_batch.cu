@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <vector>
 
@@ -65,10 +66,12 @@ struct CachedBlock { void* p; size_t cap; };
 struct DeviceCtx {
   int device = -1;
   bool ok = false;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;        // kernels, uploads
+  cudaStream_t copy_stream = nullptr;   // pixel downloads, overlapped with the kernels of the next wave
   std::mutex mu;          // one batch at a time per device
   std::vector<CachedBlock> cache;
   size_t cached_bytes = 0;
+  size_t cache_limit = 0;   // released blocks are kept for the next batch up to this many bytes
 };
 
 static std::mutex g_ctx_mu;
@@ -85,7 +88,15 @@ static DeviceCtx* get_ctx(int device) {
     c->device = device;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { set_error("CUDA device init (no usable GPU; this library has no CPU path)", e); cudaGetLastError(); delete c; return nullptr; }
+    {
+      size_t free_b = 0, total_b = 0;
+      const char* env = getenv("WEBP_B200_CACHE_GB");
+      if (env != NULL) c->cache_limit = (size_t)atof(env) << 30;
+      else if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) c->cache_limit = (size_t)((double)free_b * 0.80);
+      cudaGetLastError();
+    }
     c->ok = true;
     g_ctx[device] = c;
   }
@@ -127,7 +138,7 @@ static bool own_alloc(DeviceCtx* c, Owned& o, size_t bytes) {
 
 static void own_free(DeviceCtx* c, Owned& o) {
   if (o.p == nullptr) return;
-  if (c->cached_bytes + o.cap <= ((size_t)8 << 30) && c->cache.size() < 64) {   // keep up to 8 GiB around
+  if (c->cached_bytes + o.cap <= c->cache_limit && c->cache.size() < 64) {   // cudaFree/cudaMalloc of tens of GB cost 0.1-1 s
     c->cache.push_back({ o.p, o.cap });
     c->cached_bytes += o.cap;
   } else {
@@ -225,7 +236,10 @@ struct WebPBatch {
   Owned d_in, d_imgs, d_hdrs, d_ids, d_mbinfo, d_coeffs, d_yuv, d_out;
   size_t out_total = 0;
   int max_mb_w = 1, max_mb_h = 1;
-  cudaEvent_t ev[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+  std::vector<cudaEvent_t> ev;     // pool of timing / hand-off events, grown on demand
+  size_t ev_used = 0;
+  struct Span { int stage, a, b; };
+  std::vector<Span> spans;         // (stage, first event, second event) of every timed launch of the last decode
   WebPBatchTimings timings;
   bool decoded = false;
 };
@@ -353,9 +367,21 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
   if (budget == 0) {
     size_t free_b = 0, total_b = 0;
     CU_TRY(cudaMemGetInfo(&free_b, &total_b), "cudaMemGetInfo");
-    budget = (size_t)((double)free_b * 0.85);
+    budget = (size_t)((double)(free_b + ctx->cached_bytes) * 0.85);
   }
   size_t wave_cap_mbs = std::max<size_t>(budget / per_mb, (size_t)b->max_mb_w * b->max_mb_h);
+  {
+    // More than one wave only on request (or when scratch memory forces it): the token parse wants every stream
+    // it can get in flight, and measured end to end one wave + chunked pixel stages beats two waves whose
+    // downloads overlap the second parse (profiles/r01*_e2e_sweep.log).
+    int waves = b->opt.pipeline_waves;
+    if (waves <= 0) {
+      static int env_waves = -1;
+      if (env_waves < 0) { const char* e = getenv("WEBP_B200_HOST_WAVES"); env_waves = e ? atoi(e) : 0; }
+      waves = env_waves > 0 ? env_waves : 1;
+    }
+    if (waves > 1) wave_cap_mbs = std::min(wave_cap_mbs, std::max<size_t>((total_mbs + waves - 1) / waves, (size_t)b->max_mb_w * b->max_mb_h));
+  }
   {
     Wave w;
     for (int k = 0; k < m; ++k) {
@@ -394,7 +420,6 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
   CU_TRY(cudaMemcpyAsync(b->d_imgs.p, b->imgs.data(), sizeof(ImgDesc) * m, cudaMemcpyHostToDevice, s), "H2D descriptors");
   CU_TRY(cudaMemcpyAsync(b->d_ids.p, b->ids.data(), sizeof(int) * m, cudaMemcpyHostToDevice, s), "H2D ids");
   CU_TRY(vp8k_configure(b->max_mb_w, b->max_mb_h), "cudaFuncSetAttribute");
-  for (int k = 0; k < 8; ++k) CU_TRY(cudaEventCreate(&b->ev[k]), "cudaEventCreate");
   CU_TRY(cudaStreamSynchronize(s), "upload sync");
   return true;
 }
@@ -405,7 +430,7 @@ static void batch_release(WebPBatch* b) {
     DeviceCtx* c = b->ctx;
     own_free(c, b->d_in); own_free(c, b->d_imgs); own_free(c, b->d_hdrs); own_free(c, b->d_ids);
     own_free(c, b->d_mbinfo); own_free(c, b->d_coeffs); own_free(c, b->d_yuv); own_free(c, b->d_out);
-    for (int k = 0; k < 8; ++k) if (b->ev[k]) cudaEventDestroy(b->ev[k]);
+    for (auto e : b->ev) if (e) cudaEventDestroy(e);
   }
   delete b;
 }
@@ -460,100 +485,21 @@ extern "C" WebPBatch* WebPBatchCreate(WebPBatchItem* items, int num_items, const
   return b;
 }
 
-static bool batch_decode(WebPBatch* b) {
-  DeviceCtx* ctx = b->ctx;
-  const int m = (int)b->imgs.size();
-  memset(&b->timings, 0, sizeof(b->timings));
-  if (m == 0) return true;
-  CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
-  cudaStream_t s = ctx->stream;
-  const uint8_t* arena = (const uint8_t*)b->d_in.p;
-  const ImgDesc* imgs = (const ImgDesc*)b->d_imgs.p;
-  FrameHdr* hdrs = (FrameHdr*)b->d_hdrs.p;
-  uint32_t* mbinfo = (uint32_t*)b->d_mbinfo.p;
-  int16_t* coeffs = (int16_t*)b->d_coeffs.p;
-  uint8_t* yuv = (uint8_t*)b->d_yuv.p;
-  float acc[5] = { 0, 0, 0, 0, 0 };
-  int launches = 0;
-  for (const Wave& w : b->waves) {
-    CU_TRY(cudaEventRecord(b->ev[0], s), "event");
-    vp8k_parse_modes(s, arena, imgs, hdrs, mbinfo, w.first, w.count, w.max_mb_w);
-    ++launches;
-    CU_TRY(cudaEventRecord(b->ev[1], s), "event");
-    CU_TRY(cudaMemsetAsync(coeffs, 0, w.mbs * 2 * VP8B_COEFFS_PER_MB, s), "memset coefficients");
-    for (int lg = 0; lg < 4; ++lg) {
-      if (w.ids_cnt[lg] == 0) continue;
-      vp8k_parse_tokens(s, arena, imgs, hdrs, mbinfo, coeffs, (const int*)b->d_ids.p + w.ids_off[lg], w.ids_cnt[lg], 1 << lg, w.max_mb_w);
-      ++launches;
-    }
-    CU_TRY(cudaEventRecord(b->ev[2], s), "event");
-    vp8k_reconstruct(s, imgs, hdrs, mbinfo, coeffs, yuv, w.first, w.count, w.max_mb_w, w.max_mb_h);
-    CU_TRY(cudaEventRecord(b->ev[3], s), "event");
-    vp8k_loop_filter(s, imgs, hdrs, mbinfo, yuv, w.first, w.count);
-    CU_TRY(cudaEventRecord(b->ev[4], s), "event");
-    vp8k_emit(s, imgs, hdrs, yuv, (uint8_t*)b->d_out.p, w.first, w.count, w.max_units);
-    CU_TRY(cudaEventRecord(b->ev[5], s), "event");
-    launches += 3;
-    CU_TRY(cudaStreamSynchronize(s), "kernel execution");
-    CU_TRY(cudaGetLastError(), "kernel launch");
-    for (int k = 0; k < 5; ++k) {
-      float ms = 0;
-      CU_TRY(cudaEventElapsedTime(&ms, b->ev[k], b->ev[k + 1]), "cudaEventElapsedTime");
-      acc[k] += ms;
-    }
-  }
-  b->timings.modes_ms = acc[0]; b->timings.tokens_ms = acc[1]; b->timings.recon_ms = acc[2];
-  b->timings.filter_ms = acc[3]; b->timings.emit_ms = acc[4];
-  b->timings.total_ms = acc[0] + acc[1] + acc[2] + acc[3] + acc[4];
-  b->timings.launches = launches;
-  // per-image status words: FrameHdr::status is the first field
-  CU_TRY(cudaMemcpy2DAsync(b->statuses.data(), sizeof(int), hdrs, sizeof(FrameHdr), sizeof(int), m, cudaMemcpyDeviceToHost, s),
-         "D2H status");
-  CU_TRY(cudaStreamSynchronize(s), "status sync");
-  for (int k = 0; k < m; ++k) {
-    WebPBatchItem* it = &b->items[b->img_item[k]];
-    it->status = (VP8StatusCode)b->statuses[k];
-    if (it->status != VP8_STATUS_OK && b->opt.output == WEBP_BATCH_HOST) WebPFreeDecBuffer(&it->config->output);
-  }
-  b->decoded = true;
-  return true;
-}
-
-extern "C" VP8StatusCode WebPBatchDecode(WebPBatch* b) {
-  if (b == NULL) return VP8_STATUS_INVALID_PARAM;
-  bool ok = true;
-  if (b->ctx != nullptr) {
-    b->ctx->mu.lock();
-    ok = batch_decode(b);
-    b->ctx->mu.unlock();
-  }
-  if (!ok) {
-    fprintf(stderr, "libwebp_b200: %s\n", g_last_error);
-    fail_all(b->items, b->n, VP8_STATUS_USER_ABORT);
-    return VP8_STATUS_USER_ABORT;
-  }
-  for (int i = 0; i < b->n; ++i) if (b->items[i].status != VP8_STATUS_OK) return b->items[i].status;
-  return VP8_STATUS_OK;
-}
-
-// Copies every decoded image into its host buffer. Consecutive images whose host buffers are contiguous and
-// tightly packed travel in one cudaMemcpyAsync.
-static bool batch_download(WebPBatch* b) {
-  DeviceCtx* ctx = b->ctx;
-  if (b->opt.output != WEBP_BATCH_HOST || b->imgs.empty()) return true;
-  CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
-  cudaStream_t s = ctx->stream;
+// Queues the device->host copies of images [first, first + count) on stream `s`. Consecutive images whose
+// host buffers are contiguous and tightly packed travel in one cudaMemcpyAsync. With check_status the images
+// that failed are skipped (their buffers are already released); without it the statuses are not known yet and
+// every image still owns a valid destination.
+static bool enqueue_download(WebPBatch* b, int first, int count, cudaStream_t s, bool check_status) {
   const uint8_t* dout = (const uint8_t*)b->d_out.p;
-  const int m = (int)b->imgs.size();
   uint8_t* run_host = nullptr; const uint8_t* run_dev = nullptr; size_t run_bytes = 0;
   auto flush = [&]() -> bool {
     if (run_bytes > 0) CU_TRY(cudaMemcpyAsync(run_host, run_dev, run_bytes, cudaMemcpyDeviceToHost, s), "D2H pixels");
     run_bytes = 0;
     return true;
   };
-  for (int k = 0; k < m; ++k) {
+  for (int k = first; k < first + count; ++k) {
     const WebPBatchItem* it = &b->items[b->img_item[k]];
-    if (it->status != VP8_STATUS_OK) continue;
+    if (check_status && it->status != VP8_STATUS_OK) continue;
     const ImgDesc& d = b->imgs[k];
     const WebPDecBuffer* o = &it->config->output;
     const uint8_t* src = dout + d.out_off;
@@ -581,8 +527,140 @@ static bool batch_download(WebPBatch* b) {
       CU_TRY(cudaMemcpy2DAsync(o->u.RGBA.rgba, (size_t)o->u.RGBA.stride, src, row, row, d.height, cudaMemcpyDeviceToHost, s), "D2H pixels 2D");
     }
   }
-  if (!flush()) return false;
-  CU_TRY(cudaStreamSynchronize(s), "download sync");
+  return flush();
+}
+
+enum { ST_MODES = 0, ST_TOKENS, ST_RECON, ST_FILTER, ST_EMIT, ST_COUNT };
+
+static int ev_mark(WebPBatch* b, cudaStream_t s) {   // records the next pooled event on `s`; -1 on failure
+  if (b->ev_used == b->ev.size()) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) { set_error("cudaEventCreate", cudaGetLastError()); return -1; }
+    b->ev.push_back(e);
+  }
+  if (cudaEventRecord(b->ev[b->ev_used], s) != cudaSuccess) { set_error("cudaEventRecord", cudaGetLastError()); return -1; }
+  return (int)b->ev_used++;
+}
+
+// Runs the kernels on the device's compute stream. The two parse kernels take a whole wave at a time (the
+// serial entropy decode needs every stream it can get in flight); the pixel stages then walk the wave in
+// chunks, and with `download` (one-shot host-output path) each chunk's pixels start their way back on the copy
+// stream as soon as its emit kernel has finished, while the next chunk is reconstructed / the next wave parsed.
+static bool batch_decode(WebPBatch* b, bool download) {
+  DeviceCtx* ctx = b->ctx;
+  const int m = (int)b->imgs.size();
+  memset(&b->timings, 0, sizeof(b->timings));
+  if (m == 0) return true;
+  CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+  cudaStream_t s = ctx->stream;
+  const uint8_t* arena = (const uint8_t*)b->d_in.p;
+  const ImgDesc* imgs = (const ImgDesc*)b->d_imgs.p;
+  FrameHdr* hdrs = (FrameHdr*)b->d_hdrs.p;
+  uint32_t* mbinfo = (uint32_t*)b->d_mbinfo.p;
+  int16_t* coeffs = (int16_t*)b->d_coeffs.p;
+  uint8_t* yuv = (uint8_t*)b->d_yuv.p;
+  int launches = 0;
+  b->ev_used = 0;
+  b->spans.clear();
+  // chunk of the pixel stages when downloads ride along: ~2 GiB of output (256 full-HD images) per chunk
+  size_t chunk_bytes = (size_t)2 << 30;
+  { const char* e = getenv("WEBP_B200_CHUNK_MB"); if (e != NULL && atoi(e) > 0) chunk_bytes = (size_t)atoi(e) << 20; }
+#define MARK(var) const int var = ev_mark(b, s); if (var < 0) return false
+  for (const Wave& w : b->waves) {
+    MARK(e0);
+    vp8k_parse_modes(s, arena, imgs, hdrs, mbinfo, w.first, w.count, w.max_mb_w);
+    ++launches;
+    MARK(e1);
+    CU_TRY(cudaMemsetAsync(coeffs, 0, w.mbs * 2 * VP8B_COEFFS_PER_MB, s), "memset coefficients");
+    for (int lg = 0; lg < 4; ++lg) {
+      if (w.ids_cnt[lg] == 0) continue;
+      vp8k_parse_tokens(s, arena, imgs, hdrs, mbinfo, coeffs, (const int*)b->d_ids.p + w.ids_off[lg], w.ids_cnt[lg], 1 << lg, w.max_mb_w);
+      ++launches;
+    }
+    MARK(e2);
+    b->spans.push_back({ ST_MODES, e0, e1 });
+    b->spans.push_back({ ST_TOKENS, e1, e2 });
+    int prev = e2;
+    for (int c0 = w.first; c0 < w.first + w.count;) {
+      int c1 = w.first + w.count;
+      if (download) {
+        size_t acc = 0;
+        for (c1 = c0; c1 < w.first + w.count && (c1 == c0 || acc + b->plan[b->img_item[c1]].out_bytes <= chunk_bytes); ++c1)
+          acc += b->plan[b->img_item[c1]].out_bytes;
+      }
+      const int cnt = c1 - c0;
+      vp8k_reconstruct(s, imgs, hdrs, mbinfo, coeffs, yuv, c0, cnt, w.max_mb_w, w.max_mb_h);
+      MARK(e3);
+      vp8k_loop_filter(s, imgs, hdrs, mbinfo, yuv, c0, cnt);
+      MARK(e4);
+      vp8k_emit(s, imgs, hdrs, yuv, (uint8_t*)b->d_out.p, c0, cnt, w.max_units);
+      MARK(e5);
+      launches += 3;
+      b->spans.push_back({ ST_RECON, prev, e3 });
+      b->spans.push_back({ ST_FILTER, e3, e4 });
+      b->spans.push_back({ ST_EMIT, e4, e5 });
+      prev = e5;
+      if (download) {
+        CU_TRY(cudaStreamWaitEvent(ctx->copy_stream, b->ev[e5], 0), "cudaStreamWaitEvent");
+        if (!enqueue_download(b, c0, cnt, ctx->copy_stream, false)) return false;
+      }
+      c0 = c1;
+    }
+  }
+#undef MARK
+  // per-image status words: FrameHdr::status is the first field
+  CU_TRY(cudaMemcpy2DAsync(b->statuses.data(), sizeof(int), hdrs, sizeof(FrameHdr), sizeof(int), m, cudaMemcpyDeviceToHost, s),
+         "D2H status");
+  CU_TRY(cudaStreamSynchronize(s), "kernel execution");
+  CU_TRY(cudaGetLastError(), "kernel launch");
+  if (download) CU_TRY(cudaStreamSynchronize(ctx->copy_stream), "download sync");
+  float acc[ST_COUNT] = { 0, 0, 0, 0, 0 };
+  for (const auto& sp : b->spans) {
+    float ms = 0;
+    CU_TRY(cudaEventElapsedTime(&ms, b->ev[sp.a], b->ev[sp.b]), "cudaEventElapsedTime");
+    acc[sp.stage] += ms;
+  }
+  b->timings.modes_ms = acc[ST_MODES]; b->timings.tokens_ms = acc[ST_TOKENS]; b->timings.recon_ms = acc[ST_RECON];
+  b->timings.filter_ms = acc[ST_FILTER]; b->timings.emit_ms = acc[ST_EMIT];
+  b->timings.total_ms = acc[0] + acc[1] + acc[2] + acc[3] + acc[4];
+  b->timings.launches = launches;
+  for (int k = 0; k < m; ++k) {
+    WebPBatchItem* it = &b->items[b->img_item[k]];
+    it->status = (VP8StatusCode)b->statuses[k];
+    if (it->status != VP8_STATUS_OK && b->opt.output == WEBP_BATCH_HOST) WebPFreeDecBuffer(&it->config->output);
+  }
+  b->decoded = true;
+  return true;
+}
+
+static VP8StatusCode batch_decode_locked(WebPBatch* b, bool download) {
+  bool ok = true;
+  if (b->ctx != nullptr) {
+    b->ctx->mu.lock();
+    ok = batch_decode(b, download);
+    if (!ok) { cudaStreamSynchronize(b->ctx->stream); cudaStreamSynchronize(b->ctx->copy_stream); cudaGetLastError(); }
+    b->ctx->mu.unlock();
+  }
+  if (!ok) {
+    fprintf(stderr, "libwebp_b200: %s\n", g_last_error);
+    fail_all(b->items, b->n, VP8_STATUS_USER_ABORT);
+    return VP8_STATUS_USER_ABORT;
+  }
+  for (int i = 0; i < b->n; ++i) if (b->items[i].status != VP8_STATUS_OK) return b->items[i].status;
+  return VP8_STATUS_OK;
+}
+
+extern "C" VP8StatusCode WebPBatchDecode(WebPBatch* b) {
+  if (b == NULL) return VP8_STATUS_INVALID_PARAM;
+  return batch_decode_locked(b, false);
+}
+
+static bool batch_download(WebPBatch* b) {
+  DeviceCtx* ctx = b->ctx;
+  if (b->opt.output != WEBP_BATCH_HOST || b->imgs.empty()) return true;
+  CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+  if (!enqueue_download(b, 0, (int)b->imgs.size(), ctx->copy_stream, true)) return false;
+  CU_TRY(cudaStreamSynchronize(ctx->copy_stream), "download sync");
   return true;
 }
 
@@ -591,6 +669,7 @@ extern "C" VP8StatusCode WebPBatchDownload(WebPBatch* b) {
   if (b->ctx == nullptr) return VP8_STATUS_OK;
   b->ctx->mu.lock();
   const bool ok = batch_download(b);
+  if (!ok) { cudaStreamSynchronize(b->ctx->copy_stream); cudaGetLastError(); }
   b->ctx->mu.unlock();
   if (!ok) { fprintf(stderr, "libwebp_b200: %s\n", g_last_error); return VP8_STATUS_USER_ABORT; }
   return VP8_STATUS_OK;
@@ -628,18 +707,31 @@ extern "C" int WebPBatchGetTimings(const WebPBatch* b, WebPBatchTimings* t) {
 }
 
 extern "C" VP8StatusCode WebPDecodeBatch(WebPBatchItem* items, int num_items, const WebPBatchOptions* options) {
+  static int trace = -1;
+  if (trace < 0) trace = getenv("WEBP_B200_TRACE") != NULL;
+  const auto t0 = std::chrono::steady_clock::now();
   VP8StatusCode st;
   WebPBatch* b = WebPBatchCreate(items, num_items, options, &st);
   if (b == NULL) {
     if (st != VP8_STATUS_OK) return st;
     return VP8_STATUS_INVALID_PARAM;
   }
-  st = WebPBatchDecode(b);
-  if (st != VP8_STATUS_USER_ABORT) {
-    const VP8StatusCode dl = WebPBatchDownload(b);
-    if (dl != VP8_STATUS_OK) { fail_all(items, num_items, dl); st = dl; }
-  }
+  const auto t1 = std::chrono::steady_clock::now();
+  st = batch_decode_locked(b, b->opt.output == WEBP_BATCH_HOST);   // downloads ride along, wave by wave
+  const auto t2 = std::chrono::steady_clock::now();
+  const WebPBatchTimings tm = b->timings;
+  const size_t nwaves = b->waves.size();
   WebPBatchDestroy(b);
+  if (trace) {
+    const auto t3 = std::chrono::steady_clock::now();
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point c) {
+      return std::chrono::duration<double, std::milli>(c - a).count();
+    };
+    fprintf(stderr, "libwebp_b200 trace: %d items, %zu waves: create(plan+alloc+H2D) %.1f ms, decode+download %.1f ms "
+            "(kernels %.1f = modes %.1f tokens %.1f recon %.1f filter %.1f emit %.1f), destroy %.1f ms\n",
+            num_items, nwaves, ms(t0, t1), ms(t1, t2), tm.total_ms, tm.modes_ms, tm.tokens_ms, tm.recon_ms, tm.filter_ms,
+            tm.emit_ms, ms(t2, t3));
+  }
   for (int i = 0; i < num_items; ++i) if (items[i].status != VP8_STATUS_OK) return items[i].status;
   return st;
 }

@@ -45,17 +45,23 @@ __global__ void __launch_bounds__(32) k_parse_modes(const uint8_t* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-__global__ void k_parse_tokens(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs, FrameHdr* hdrs,
-                               uint32_t* mbinfo, int16_t* coeffs, const int* __restrict__ ids, int P, int ctx_stride) {
+// Shared memory: probabilities 1056 B | dequantiser words 48 B | progress P+1 ints (padded to 48 B) | top contexts.
+#define TOKW_PROGRESS (1056 + 48)
+#define TOKW_CTX (TOKW_PROGRESS + 48)
+__global__ void __launch_bounds__(32 * VP8B_MAX_PARTS) k_parse_tokens(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
+                                                                      FrameHdr* hdrs, uint32_t* mbinfo, int16_t* coeffs,
+                                                                      const int* __restrict__ ids, int P) {
   extern __shared__ __align__(16) uint8_t smem[];
-  uint8_t* probs = smem;                                   // 1056 B
-  volatile int* progress = (volatile int*)(smem + 1056);   // P ints (+ status word)
-  uint16_t* topctx = (uint16_t*)(smem + 1056 + 4 * (VP8B_MAX_PARTS + 1) + 12);   // (P+1) * ctx_stride
+  uint8_t* probs = smem;
+  uint32_t* dqs = (uint32_t*)(smem + 1056);
+  volatile int* progress = (volatile int*)(smem + TOKW_PROGRESS);   // P ints (+ status word)
+  uint16_t* topctx = (uint16_t*)(smem + TOKW_CTX);                  // (P+1) * mb_w
   const int img = ids[blockIdx.x];
   const ImgDesc im = imgs[img];
   FrameHdr* h = &hdrs[img];
   const int tid = threadIdx.x, lane = tid & 31, part = tid >> 5;
   for (int k = tid; k < 264; k += blockDim.x) ((uint32_t*)probs)[k] = ((const uint32_t*)h->prob)[k];
+  if (tid < 12) dqs[tid] = ((const uint32_t*)h->dq)[tid];
   if (tid < P) progress[tid] = 0;
   if (tid == 0) progress[VP8B_MAX_PARTS] = (h->status == VP8B_OK && h->num_parts == P) ? 1 : 0;
   __syncthreads();
@@ -64,13 +70,12 @@ __global__ void k_parse_tokens(const uint8_t* __restrict__ arena, const ImgDesc*
     return;
   }
   if (lane != 0 || part >= im.mb_h) return;
-  (void)ctx_stride;
   TokenPart tp;
   token_part_init(tp, arena + im.in_off, h, part);
   uint32_t* mbi = mbinfo + 4 * (size_t)im.mb_base;
   int16_t* cf = coeffs + (size_t)im.mb_base * VP8B_COEFFS_PER_MB;
   for (int my = part; my < im.mb_h; my += P) {
-    parse_token_row(tp, im, h, part, my, probs, topctx, progress, mbi, cf);
+    parse_token_row(tp, im, h, part, my, probs, dqs, topctx, progress, mbi, cf);
   }
   if (tp.status != VP8B_OK) h->status = tp.status;
 }
@@ -306,7 +311,7 @@ static size_t recon_smem_bytes(int max_mb_w, int max_mb_h) {
 }
 
 static size_t tokens_smem_bytes(int P, int max_mb_w) {
-  return 1056 + 4 * (VP8B_MAX_PARTS + 1) + 12 + (size_t)(P + 1) * max_mb_w * 2;
+  return TOKW_CTX + (size_t)(P + 1) * max_mb_w * 2;
 }
 
 extern "C" cudaError_t vp8k_configure(int max_mb_w, int max_mb_h) {
@@ -360,10 +365,13 @@ extern "C" void vp8k_parse_tokens(cudaStream_t s, const uint8_t* arena, const Im
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("WEBP_B200_TOKEN_MAP");
-    forced = (e && e[0] == 'w') ? 1 : 2;
+    forced = (e && e[0] == 'w') ? 1 : (e && e[0] == 'l') ? 2 : 0;
   }
-  if (forced == 1) {
-    k_parse_tokens<<<count, 32 * P, tokens_smem_bytes(P, max_mb_w), s>>>(arena, imgs, hdrs, mbinfo, coeffs, ids, P, max_mb_w);
+  // Up to ~16 streams per SM sub-partition the straight-line parser keeps the issue slots busy on its own; beyond
+  // that the state machine's shared instruction stream wins (measured: profiles/r01*_token_map_sweep.log).
+  const int use_warp_map = forced ? (forced == 1) : ((long)count * P <= 148L * 4 * 16);
+  if (use_warp_map) {
+    k_parse_tokens<<<count, 32 * P, tokens_smem_bytes(P, max_mb_w), s>>>(arena, imgs, hdrs, mbinfo, coeffs, ids, P);
     return;
   }
   launch_tokens_fsm(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, max_mb_w);

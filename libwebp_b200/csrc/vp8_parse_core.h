@@ -45,24 +45,49 @@ VP8_TABLE int8_t kBModeTreeDev[9][2] = {
 };
 
 // ---------------------------------------------------------------------------------------------------------
-// Boolean decoder. `value` is a left-aligned 64-bit window refilled with aligned big-endian 32-bit words;
-// `range` is (true range - 1) in [127,254]. Bits past the end of the stream are whatever follows in the
-// arena (it is padded): any decode that looks at them is reported by bd_eof(), which reproduces the
-// reference's eof_ flag (bit_reader_utils.c:88-101) from the bit position alone.
+// Boolean decoder (VP8GetBit, bit_reader_inl_utils.h:107-136) shaped for few instructions per decode.
+//   V:vlo   64-bit left-aligned window on the stream, `nbits` of it valid; the decode only looks at V's top byte
+//   R24     (range - 1) << 24, range - 1 in [127, 254] as in the reference, so that
+//             split            = umulhi(R24, prob)              one IMAD.HI
+//             (split + 1)<<24  = split * 2^24 + 2^24            one IMAD
+//             bit              = V >= (split + 1) << 24         one compare, no shift of V
+//           and the new true range, still << 24, normalises with one count-leading-zeros.
+//   nxt     the next aligned word of the stream, fetched one refill ahead of its use (a warp never waits on HBM)
+// bd_fill() tops the window up to > 32 valid bits; every decode consumes at most 7, so callers place one
+// bd_fill() per four decodes instead of testing before each (see parse_block).
+// Words wholly past the stream read as zero; any decode that starts in them is reported by bd_eof(), which
+// reproduces the reference's eof_ flag (bit_reader_utils.c:88-101) from the bit position alone.
+#if defined(__CUDACC__) && !defined(VP8_EMU)
+#define VP8_UMULHI(a, b) __umulhi((a), (b))
+#define VP8_LDG(p) __ldg(p)
+VP8_FN uint32_t vp8_shr_clamp(uint32_t w, int n) { return __funnelshift_rc(w, 0u, (uint32_t)n); }   // 0 when n >= 32
+VP8_FN uint32_t vp8_shl_clamp(uint32_t w, int n) { return __funnelshift_lc(0u, w, (uint32_t)n); }
+VP8_FN uint32_t vp8_shl_pair(uint32_t hi, uint32_t lo, int n) { return __funnelshift_l(lo, hi, (uint32_t)n); }
+VP8_FN int vp8_shiftamt(uint32_t x) { int r; asm("bfind.shiftamt.u32 %0, %1;" : "=r"(r) : "r"(x)); return r; }   // clz, x != 0
+#else
+#define VP8_UMULHI(a, b) ((uint32_t)(((uint64_t)(a) * (uint64_t)(b)) >> 32))
+#define VP8_LDG(p) (*(p))
+VP8_FN uint32_t vp8_shr_clamp(uint32_t w, int n) { return n >= 32 ? 0u : (w >> n); }
+VP8_FN uint32_t vp8_shl_clamp(uint32_t w, int n) { return n >= 32 ? 0u : (w << n); }
+VP8_FN uint32_t vp8_shl_pair(uint32_t hi, uint32_t lo, int n) { return n == 0 ? hi : ((hi << n) | (lo >> (32 - n))); }
+VP8_FN int vp8_shiftamt(uint32_t x) { return __builtin_clz(x); }
+#endif
+
 struct BoolDec {
-  const uint32_t* wp;   // next aligned word
-  const uint32_t* wend; // first word wholly past the stream: refills from there on shift in zeros
-  uint64_t value;
-  int nbits;            // valid bits in `value`
-  uint32_t range;
-  int last_shift;       // renormalisation shift of the most recent decode
-  int64_t loaded;       // stream bits moved into `value` so far
-  int64_t limit;        // 8*size - 8: a decode starting beyond this bit position reads past the end
+  const uint32_t* wp;    // word after `nxt`
+  const uint32_t* wend;  // first word wholly past the stream: from there on zeros are shifted in
+  const uint32_t* wbase; // stream bits moved into the window so far = 32 * (wp - wbase) - bias8
+  uint32_t V, vlo, nxt;  // nxt holds the raw (little-endian) word
+  int nbits;             // valid bits in V:vlo
+  uint32_t R24;
+  int last_shift;        // renormalisation shift of the most recent decode
+  int bias8;
+  int64_t limit;         // 8*size - 8: a decode starting beyond this bit position reads past the end
 };
 
-VP8_FN uint32_t bd_load_word(BoolDec& d) {
+VP8_FN uint32_t bd_fetch(BoolDec& d) {
   const uint32_t* p = d.wp++;
-  return (p < d.wend) ? VP8_BSWAP(*p) : 0u;
+  return (p < d.wend) ? VP8_LDG(p) : 0u;
 }
 
 VP8_FN void bd_init(BoolDec& d, const uint8_t* start, uint32_t size) {
@@ -70,40 +95,58 @@ VP8_FN void bd_init(BoolDec& d, const uint8_t* start, uint32_t size) {
   const int off = (int)(a & 3);
   d.wp = (const uint32_t*)(a - off);
   d.wend = (const uint32_t*)((a + size + 3) & ~(uintptr_t)3);
-  d.value = (uint64_t)bd_load_word(d) << (32 + 8 * off);
+  d.wbase = d.wp + 1;
+  d.V = VP8_BSWAP(bd_fetch(d)) << (8 * off);
+  d.vlo = 0;
   d.nbits = 32 - 8 * off;
-  d.loaded = d.nbits;
-  d.range = 254;
+  d.nxt = bd_fetch(d);
+  d.bias8 = 8 * off;
+  d.R24 = 254u << 24;
   d.last_shift = 0;
   d.limit = 8 * (int64_t)size - 8;
 }
 
 // True when the reference's reader would have raised eof_: some decode started with fewer than 8 real bits
 // left. Positions are monotonic, so testing the most recent decode is enough (and size==0 trips at once).
-VP8_FN int bd_eof(const BoolDec& d) { return (d.loaded - d.nbits - d.last_shift) > d.limit; }
+VP8_FN int bd_eof(const BoolDec& d) {
+  const int64_t loaded = 32 * (int64_t)(d.wp - d.wbase) - d.bias8;
+  return (loaded - d.nbits - d.last_shift) > d.limit;
+}
 
-VP8_FN int bd_bit(BoolDec& d, uint32_t prob) {
+// Window -> more than 32 valid bits. vlo is empty whenever nbits <= 32.
+VP8_FN void bd_fill(BoolDec& d) {
   if (d.nbits <= 32) {
-    d.value |= (uint64_t)bd_load_word(d) << (32 - d.nbits);
+    const uint32_t w = VP8_BSWAP(d.nxt);
+    d.nxt = bd_fetch(d);
+    d.V |= vp8_shr_clamp(w, d.nbits);
+    d.vlo = vp8_shl_clamp(w, 32 - d.nbits);
     d.nbits += 32;
-    d.loaded += 32;
   }
-  const uint32_t split = (d.range * prob) >> 8;
-  const uint32_t top = (uint32_t)(d.value >> 56);
-  const int bit = top > split;
-  uint32_t r;   // new true range
-  if (bit) {
-    r = d.range - split;
-    d.value -= (uint64_t)(split + 1) << 56;
-  } else {
-    r = split + 1;
-  }
-  const int shift = VP8_CLZ(r) - 24;
-  d.range = (r << shift) - 1;
-  d.value <<= shift;
+}
+
+// One decode given (split + 1) << 24; needs >= 8 valid bits.
+VP8_FN int bd_decode(BoolDec& d, uint32_t s1) {
+  const int bit = d.V >= s1;
+  uint32_t r24 = s1;                       // true range << 24
+  if (bit) { r24 = d.R24 + (1u << 24) - s1; d.V -= s1; }
+  const int shift = vp8_shiftamt(r24);
+  d.R24 = (r24 << shift) - (1u << 24);
+  d.V = vp8_shl_pair(d.V, d.vlo, shift);
+  d.vlo <<= shift;
   d.nbits -= shift;
   d.last_shift = shift;
   return bit;
+}
+
+VP8_FN int bd_bit_nofill(BoolDec& d, uint32_t prob) {
+  return bd_decode(d, (VP8_UMULHI(d.R24, prob) << 24) + (1u << 24));
+}
+// prob = 128 (VP8GetSigned / VP8GetValue bits): split = range >> 1
+VP8_FN int bd_half_nofill(BoolDec& d) { return bd_decode(d, ((d.R24 >> 25) << 24) + (1u << 24)); }
+
+VP8_FN int bd_bit(BoolDec& d, uint32_t prob) {
+  bd_fill(d);
+  return bd_bit_nofill(d, prob);
 }
 
 VP8_FN uint32_t bd_value(BoolDec& d, int n) {
@@ -293,56 +336,63 @@ VP8_FN int parse_intra_modes(BoolDec& br, const ImgDesc& im, const FrameHdr* h, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Coefficient tokens.
-VP8_FN int large_value(BoolDec& d, const uint8_t* p) {
+// Coefficient tokens. Window discipline: bd_fill() leaves > 32 valid bits and a decode uses at most 7, so up
+// to four bd_*_nofill() calls may follow one bd_fill().
+VP8_FN int large_value(BoolDec& d, const uint8_t* p) {   // GetLargeValue, vp8_dec.c:411-440; sign decoded by the caller
   int v;
-  if (!bd_bit(d, p[3])) {
-    v = !bd_bit(d, p[4]) ? 2 : 3 + bd_bit(d, p[5]);
-  } else if (!bd_bit(d, p[6])) {
-    if (!bd_bit(d, p[7])) {
-      v = 5 + bd_bit(d, 159);
+  bd_fill(d);
+  if (!bd_bit_nofill(d, p[3])) {
+    v = !bd_bit_nofill(d, p[4]) ? 2 : 3 + bd_bit_nofill(d, p[5]);
+  } else if (!bd_bit_nofill(d, p[6])) {
+    bd_fill(d);
+    if (!bd_bit_nofill(d, p[7])) {
+      v = 5 + bd_bit_nofill(d, 159);
     } else {
-      v = 7 + 2 * bd_bit(d, 165);
-      v += bd_bit(d, 145);
+      v = 7 + 2 * bd_bit_nofill(d, 165);
+      v += bd_bit_nofill(d, 145);
     }
   } else {
-    const int b1 = bd_bit(d, p[8]);
-    const int b0 = bd_bit(d, p[9 + b1]);
+    bd_fill(d);
+    const int b1 = bd_bit_nofill(d, p[8]);
+    const int b0 = bd_bit_nofill(d, p[9 + b1]);
     const int cat = 2 * b1 + b0;
     v = 0;
     for (const uint8_t* tab = kCatProb[cat]; *tab; ++tab) v += v + bd_bit(d, *tab);
     v += 3 + (8 << cat);
+    bd_fill(d);
   }
   return v;
 }
 
-// One 4x4 block. `probs` = this block type's [8 bands][3 ctx][11] table (shared memory), `out` = 16 int16 in
-// HBM (pre-zeroed). Returns nz = index of the last decoded coefficient + 1 (GetCoeffs, vp8_dec.c:443-469);
-// *dc_nz says whether the stored value at position 0 is non-zero after the int16 truncation.
-VP8_FN int parse_block(BoolDec& d, const uint8_t* probs, int ctx, int dq_dc, int dq_ac, int n, int16_t* out, int* dc_nz) {
-  const uint8_t* p = probs + kBandOff[n] + ctx * 11;
-  for (; n < 16; ++n) {
-    if (!bd_bit(d, p[0])) return n;
-    while (!bd_bit(d, p[1])) {
-      p = probs + kBandOff[++n];
-      if (n == 16) return 16;
+// One 4x4 block. `tp` = this block type's [8 bands][3 ctx][11] table (shared memory), `out` = 16 int16 in
+// HBM (pre-zeroed), dq = dc | ac << 16. Returns nz = index of the last decoded coefficient + 1 (GetCoeffs,
+// vp8_dec.c:443-469); *dc_nz says whether the stored value at position 0 is non-zero after the int16 truncation.
+VP8_FN int parse_block(BoolDec& d, const uint8_t* tp, int ctx, uint32_t dq, int n, int16_t* out, int* dc_nz) {
+  const uint8_t* p = tp + kBandOff[n] + ctx * 11;
+  for (;;) {
+    bd_fill(d);
+    if (!bd_bit_nofill(d, p[0])) return n;
+    while (!bd_bit_nofill(d, p[1])) {
+      if (++n == 16) return 16;
+      p = tp + kBandOff[n];
+      bd_fill(d);
     }
+    const uint8_t* pn = tp + kBandOff[n + 1];
     int v;
-    const uint8_t* pn = probs + kBandOff[n + 1];
-    if (!bd_bit(d, p[2])) {
+    if (!bd_bit_nofill(d, p[2])) {
       v = 1;
       pn += 11;
     } else {
       v = large_value(d, p);
       pn += 22;
     }
-    p = pn;
-    if (bd_bit(d, 0x80)) v = -v;
-    const int16_t c = (int16_t)(v * (n > 0 ? dq_ac : dq_dc));
+    if (bd_half_nofill(d)) v = -v;
+    const int16_t c = (int16_t)(v * (int)(n > 0 ? (dq >> 16) : (dq & 0xffffu)));
     out[kZigzagPos[n]] = c;
     if (n == 0) *dc_nz = (c != 0);
+    if (++n == 16) return 16;
+    p = pn;
   }
-  return 16;
 }
 
 // Progress hand-off between the token partitions of one image: partition p publishes how many macroblocks
@@ -352,6 +402,22 @@ VP8_FN int parse_block(BoolDec& d, const uint8_t* probs, int ctx, int dq_dc, int
 #define VP8_WAIT_PROGRESS(ptr, need) ((void)0)
 #define VP8_PUBLISH_PROGRESS(ptr, val) ((void)0)
 #endif
+
+// Blocks of a macroblock in parse order (seq 0 = Y2, 1..16 luma, 17..24 chroma), one word each:
+//  [3:0] bit of the top context  [7:4] bit of the left context  [12:8] shift of the 2-bit nz code
+//  13 chroma  14 luma  [16:15] block type when the macroblock is i16 (luma of i4x4 macroblocks: type 3)
+//  [18:17] dequantiser pair  [23:19] block index inside the macroblock's coefficients
+#define SQ_(tb, lb, sh, fl, type, qp, blk) ((uint32_t)(tb) | ((uint32_t)(lb) << 4) | ((uint32_t)(sh) << 8) | (fl) | ((uint32_t)(type) << 15) | ((uint32_t)(qp) << 17) | ((uint32_t)(blk) << 19))
+#define SQ_CHROMA (1u << 13)
+#define SQ_LUMA (1u << 14)
+#define SQ_Y(b) SQ_((b) & 3, (b) >> 2, 30 - 2 * (b), SQ_LUMA, 0, 0, (b))
+#define SQ_C(c) SQ_(4 + ((c) & 1) + 2 * ((c) >> 2), 4 + (((c) >> 1) & 1) + 2 * ((c) >> 2), 8 * ((c) >> 2) + 6 - 2 * ((c) & 3), SQ_CHROMA, 2, 2, 16 + (c))
+VP8_TABLE uint32_t kBlockSeq[25] = {
+  SQ_(8, 8, 0, 0, 1, 1, 24),
+  SQ_Y(0), SQ_Y(1), SQ_Y(2), SQ_Y(3), SQ_Y(4), SQ_Y(5), SQ_Y(6), SQ_Y(7),
+  SQ_Y(8), SQ_Y(9), SQ_Y(10), SQ_Y(11), SQ_Y(12), SQ_Y(13), SQ_Y(14), SQ_Y(15),
+  SQ_C(0), SQ_C(1), SQ_C(2), SQ_C(3), SQ_C(4), SQ_C(5), SQ_C(6), SQ_C(7)
+};
 
 // Non-zero context of one macroblock column / row: bits 0-3 luma, 4-5 U, 6-7 V, bit 8 = Y2 (nz_dc).
 // State of one token partition of an image; it parses macroblock rows part, part+P, ... (vp8_dec.c:649-650).
@@ -369,11 +435,12 @@ VP8_FN void token_part_init(TokenPart& tp, const uint8_t* frame, const FrameHdr*
 
 // One macroblock row `my` of partition `part` (= my % P).
 //   probs     : 1056 bytes, this frame's coefficient probabilities (shared memory)
+//   dqs       : the frame's dequantisers as dc | ac << 16 words, [segment][y1, y2, uv] (shared memory)
 //   topctx    : (P+1) rows x mb_w uint16 ring of per-column contexts (shared by the image's partitions)
 //   progress  : P counters (shared); see above
 // Writes coefficients and MbInfo z / w.
 VP8_FN void parse_token_row(TokenPart& tp, const ImgDesc& im, const FrameHdr* h, int part, int my, const uint8_t* probs,
-                            uint16_t* topctx, volatile int* progress, uint32_t* mbinfo, int16_t* coeffs) {
+                            const uint32_t* dqs, uint16_t* topctx, volatile int* progress, uint32_t* mbinfo, int16_t* coeffs) {
   const int P = h->num_parts, mb_w = im.mb_w;
   const int use_skip = h->use_skip;
   BoolDec& d = tp.d;
@@ -382,71 +449,38 @@ VP8_FN void parse_token_row(TokenPart& tp, const ImgDesc& im, const FrameHdr* h,
   const int prev = (part + P - 1) % P;                // partition that owns row my-1
   const int prev_rows = (my - 1 - prev) / P;          // rows it finished before row my-1 (meaningful if my>0)
   uint32_t lctx = 0;
-  for (int mx = 0; mx < mb_w; ++mx) {
-    const size_t idx = (size_t)my * mb_w + mx;
-    uint32_t* info = mbinfo + 4 * idx;
-    uint32_t w = info[3];
+  uint32_t* info = mbinfo + 4 * ((size_t)my * mb_w);
+  int16_t* dst = coeffs + (size_t)my * mb_w * VP8B_COEFFS_PER_MB;
+  uint32_t w_next = info[3];
+  for (int mx = 0; mx < mb_w; ++mx, info += 4, dst += VP8B_COEFFS_PER_MB) {
+    uint32_t w = w_next;
+    if (mx + 1 < mb_w) w_next = info[7];   // next macroblock's flags: fetched a whole macroblock ahead of their use
     uint32_t tctx = 0;
     if (my > 0) {
       if (P > 1) VP8_WAIT_PROGRESS(&progress[prev], prev_rows * mb_w + mx + 1);
       tctx = trow[mx];
     }
     uint32_t nzy = 0, nzuv = 0;
-    const int is_i4 = (w & MBW_I4X4) != 0;
+    const uint32_t is_i4 = (w >> 16) & 1u;   // MBW_I4X4
     if (!(use_skip && (w & MBW_SKIP))) {
-      const int16_t* q = h->dq[(w >> MBW_SEG_SHIFT) & 3];
-      int16_t* dst = coeffs + idx * VP8B_COEFFS_PER_MB;
-      int first = 0;
-      const uint8_t* yprobs = probs + 3 * 264;
-      if (!is_i4) {
+      const uint32_t* q3 = dqs + 3 * ((w >> MBW_SEG_SHIFT) & 3);
+      for (int seq = (int)is_i4; seq < 25; ++seq) {
+        const uint32_t sq = kBlockSeq[seq];
+        const uint32_t tb = sq & 15u, lb = (sq >> 4) & 15u;
+        const uint32_t i4_luma = (sq >> 14) & is_i4;          // luma block of an i4x4 macroblock
+        const uint32_t first = ((sq >> 14) & 1u) ^ i4_luma;   // luma block of an i16 macroblock: starts at coefficient 1
+        const uint32_t type = i4_luma ? 3u : ((sq >> 15) & 3u);
+        const int ctx = (int)(((tctx >> tb) & 1u) + ((lctx >> lb) & 1u));
         int dcnz = 0;
-        const int ctx = (int)((tctx >> 8) & 1) + (int)((lctx >> 8) & 1);
-        const int nz = parse_block(d, probs + 1 * 264, ctx, q[2], q[3], 0, dst + 24 * 16, &dcnz);
-        const uint32_t f = (nz > 0) ? 0x100u : 0u;
-        tctx = (tctx & 0xffu) | f;
-        lctx = (lctx & 0xffu) | f;
-        if (nz > 0) w |= MBW_HAS_Y2;
-        first = 1;
-        yprobs = probs;
+        const int nz = parse_block(d, probs + type * 264u, ctx, q3[(sq >> 17) & 3u], (int)first, dst + 16 * ((sq >> 19) & 31u), &dcnz);
+        const uint32_t l = (nz > (int)first) ? 1u : 0u;
+        const uint32_t code = ((nz > 3) ? 3u : (nz > 1) ? 2u : (uint32_t)dcnz) << ((sq >> 8) & 31u);
+        if (sq & SQ_LUMA) nzy |= code;
+        if (sq & SQ_CHROMA) nzuv |= code;
+        if (seq == 0 && nz > 0) w |= MBW_HAS_Y2;
+        tctx = (tctx & ~(1u << tb)) | (l << tb);
+        lctx = (lctx & ~(1u << lb)) | (l << lb);
       }
-      uint32_t tnz = tctx & 0x0f, lnz = lctx & 0x0f;
-      for (int y = 0; y < 4; ++y) {
-        uint32_t l = lnz & 1;
-        for (int x = 0; x < 4; ++x) {
-          int dcnz = 0;
-          const int nz = parse_block(d, yprobs, (int)(l + (tnz & 1)), q[0], q[1], first, dst, &dcnz);
-          l = (nz > first);
-          tnz = (tnz >> 1) | (l << 7);
-          nzy = (nzy << 2) | (uint32_t)((nz > 3) ? 3 : (nz > 1) ? 2 : dcnz);
-          dst += 16;
-        }
-        tnz >>= 4;
-        lnz = (lnz >> 1) | (l << 7);
-      }
-      uint32_t out_t = tnz, out_l = lnz >> 4;
-      for (int ch = 0; ch < 4; ch += 2) {
-        uint32_t acc = 0;
-        tnz = (tctx >> (4 + ch)) & 0x0f;
-        lnz = (lctx >> (4 + ch)) & 0x0f;
-        for (int y = 0; y < 2; ++y) {
-          uint32_t l = lnz & 1;
-          for (int x = 0; x < 2; ++x) {
-            int dcnz = 0;
-            const int nz = parse_block(d, probs + 2 * 264, (int)(l + (tnz & 1)), q[4], q[5], 0, dst, &dcnz);
-            l = (nz > 0);
-            tnz = ((tnz >> 1) | (l << 3)) & 0xff;
-            acc = (acc << 2) | (uint32_t)((nz > 3) ? 3 : (nz > 1) ? 2 : dcnz);
-            dst += 16;
-          }
-          tnz >>= 2;
-          lnz = ((lnz >> 1) | (l << 5)) & 0xff;
-        }
-        nzuv |= acc << (4 * ch);
-        out_t |= ((tnz << 4) << ch) & 0xff;
-        out_l |= ((lnz & 0xf0) << ch) & 0xff;
-      }
-      tctx = (tctx & 0x100u) | (out_t & 0xff);
-      lctx = (lctx & 0x100u) | (out_l & 0xff);
     } else {
       tctx &= is_i4 ? 0x100u : 0u;
       lctx &= is_i4 ? 0x100u : 0u;

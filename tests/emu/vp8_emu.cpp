@@ -118,7 +118,7 @@ extern "C" int emu_decode(const uint8_t* data, size_t size, int csp, int flags, 
     std::vector<int> progress(P, 0);
     for (int p = 0; p < P; ++p) token_part_init(tp[p], frame, &hdr, p);
     for (int my = 0; my < mb_h; ++my) {
-      parse_token_row(tp[my % P], im, &hdr, my % P, my, hdr.prob, topctx.data(), progress.data(), mbinfo.data(), coeffs.data());
+      parse_token_row(tp[my % P], im, &hdr, my % P, my, hdr.prob, (const uint32_t*)hdr.dq, topctx.data(), progress.data(), mbinfo.data(), coeffs.data());
     }
     for (int p = 0; p < P && p < mb_h; ++p) if (tp[p].status != VP8B_OK) hdr.status = tp[p].status;
   }

@@ -12,16 +12,10 @@ timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 B="python bench.py --distinct 64 --steps 2 --e2e-steps 0 --no-cpu-baseline"
 run() { name=$1; shift; env "$@" $B $EXTRA > gpurun_out/$name.log 2>&1; show gpurun_out/$name.log; }
 EXTRA=""
-run h_default WEBP_B200_TOKEN_MAP=lanes
-run h_cw8_l4 WEBP_B200_TOKEN_CW=8 WEBP_B200_TOKEN_LPW=4
-run h_cw8_l7 WEBP_B200_TOKEN_CW=8 WEBP_B200_TOKEN_LPW=7
-run h_cw4_l14 WEBP_B200_TOKEN_CW=4 WEBP_B200_TOKEN_LPW=14
-run h_cw2_l14 WEBP_B200_TOKEN_CW=2 WEBP_B200_TOKEN_LPW=14
+run h_warp WEBP_B200_TOKEN_MAP=warp
 EXTRA="--workload vp8_256x256_q80_rgbA --distinct 512"
-run t_default WEBP_B200_TOKEN_MAP=lanes
-run t_cw8 WEBP_B200_TOKEN_CW=8
-run t_cw4_l16 WEBP_B200_TOKEN_CW=4 WEBP_B200_TOKEN_LPW=16
+run t_warp WEBP_B200_TOKEN_MAP=warp
+run t_lanes WEBP_B200_TOKEN_MAP=lanes WEBP_B200_TOKEN_CW=4 WEBP_B200_TOKEN_LPW=16
 EXTRA="--workload vp8_1080p_q75_m4_8part_normal_rgba"
-run p8_default WEBP_B200_TOKEN_MAP=lanes
-run p8_cw8 WEBP_B200_TOKEN_CW=8
-run p8_cw4_l16 WEBP_B200_TOKEN_CW=4 WEBP_B200_TOKEN_LPW=16
+run p8_warp WEBP_B200_TOKEN_MAP=warp
+run p8_lanes WEBP_B200_TOKEN_MAP=lanes WEBP_B200_TOKEN_CW=8
