@@ -5,8 +5,9 @@
 //   ImgDesc[n]    : host-built geometry + where the VP8 frame of image i starts in the arena
 //   FrameHdr[n]   : written by the header/mode kernel: quantisers, probabilities, filter strengths, partitions
 //   MbInfo[M]     : 16 B per macroblock: 16 sub-block modes (4 bit each), nz codes, flags
-//   coeffs[M*400] : int16, dequantised, raster order inside each 4x4 block; blocks 0-15 Y, 16-19 U, 20-23 V,
-//                   24 = Y2 (the WHT input of i16 macroblocks)                         (800 B / macroblock)
+//   coeffs[M*400] : int16 coefficient LEVELS exactly as parsed (not yet dequantised), in parse (zigzag) order inside
+//                   each 4x4 block; blocks 0-15 Y, 16-19 U, 20-23 V, 24 = Y2 (the WHT input of i16 macroblocks);
+//                   dequantisation + zigzag scatter happen in the reconstruction kernel      (800 B / macroblock)
 //   yuv[M*384]    : per image Y (16mb_w x 16mb_h) | U | V, macroblock-padded planes     (1.5 B / pixel)
 //   output arena  : RGBA/RGB/... or Y|U|V per image, tight strides
 #ifndef LIBWEBP_B200_VP8_DEV_H_

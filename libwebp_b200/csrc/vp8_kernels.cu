@@ -45,23 +45,21 @@ __global__ void __launch_bounds__(32) k_parse_modes(const uint8_t* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Shared memory: probabilities 1056 B | dequantiser words 48 B | progress P+1 ints (padded to 48 B) | top contexts.
-#define TOKW_PROGRESS (1056 + 48)
+// Shared memory: probabilities by position 2244 B (padded to 2256) | progress P+1 ints (padded to 48 B) | top contexts.
+#define TOKW_PROGRESS 2256
 #define TOKW_CTX (TOKW_PROGRESS + 48)
 __global__ void __launch_bounds__(32 * VP8B_MAX_PARTS) k_parse_tokens(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
                                                                       FrameHdr* hdrs, uint32_t* mbinfo, int16_t* coeffs,
                                                                       const int* __restrict__ ids, int P) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint8_t* probs = smem;
-  uint32_t* dqs = (uint32_t*)(smem + 1056);
   volatile int* progress = (volatile int*)(smem + TOKW_PROGRESS);   // P ints (+ status word)
   uint16_t* topctx = (uint16_t*)(smem + TOKW_CTX);                  // (P+1) * mb_w
   const int img = ids[blockIdx.x];
   const ImgDesc im = imgs[img];
   FrameHdr* h = &hdrs[img];
   const int tid = threadIdx.x, lane = tid & 31, part = tid >> 5;
-  for (int k = tid; k < 264; k += blockDim.x) ((uint32_t*)probs)[k] = ((const uint32_t*)h->prob)[k];
-  if (tid < 12) dqs[tid] = ((const uint32_t*)h->dq)[tid];
+  for (int k = tid; k < VP8B_POSPROB_BYTES; k += blockDim.x) probs[k] = posprob_byte(h->prob, k);
   if (tid < P) progress[tid] = 0;
   if (tid == 0) progress[VP8B_MAX_PARTS] = (h->status == VP8B_OK && h->num_parts == P) ? 1 : 0;
   __syncthreads();
@@ -75,7 +73,7 @@ __global__ void __launch_bounds__(32 * VP8B_MAX_PARTS) k_parse_tokens(const uint
   uint32_t* mbi = mbinfo + 4 * (size_t)im.mb_base;
   int16_t* cf = coeffs + (size_t)im.mb_base * VP8B_COEFFS_PER_MB;
   for (int my = part; my < im.mb_h; my += P) {
-    parse_token_row(tp, im, h, part, my, probs, dqs, topctx, progress, mbi, cf);
+    parse_token_row(tp, im, h, part, my, probs, topctx, progress, mbi, cf);
   }
   if (tp.status != VP8B_OK) h->status = tp.status;
 }
@@ -233,7 +231,8 @@ __global__ void __launch_bounds__(32 * RECON_WARPS) k_reconstruct(const ImgDesc*
     for (int my = my_lo + warp; my <= my_hi; my += RECON_WARPS) {
       const int mx = d - 2 * my;
       const size_t idx = (size_t)my * mb_w + mx;
-      recon_macroblock(ws, cx, mx, my, mb_w, mbi + 4 * idx, cf + idx * VP8B_COEFFS_PER_MB, yp, up, vp);
+      const int16_t* dq6 = hdrs[img].dq[(mbi[4 * idx + 3] >> MBW_SEG_SHIFT) & 3];
+      recon_macroblock(ws, cx, mx, my, mb_w, mbi + 4 * idx, cf + idx * VP8B_COEFFS_PER_MB, dq6, yp, up, vp);
     }
     __syncthreads();
   }

@@ -364,35 +364,47 @@ VP8_FN int large_value(BoolDec& d, const uint8_t* p) {   // GetLargeValue, vp8_d
   return v;
 }
 
-// One 4x4 block. `tp` = this block type's [8 bands][3 ctx][11] table (shared memory), `out` = 16 int16 in
-// HBM (pre-zeroed), dq = dc | ac << 16. Returns nz = index of the last decoded coefficient + 1 (GetCoeffs,
-// vp8_dec.c:443-469); *dc_nz says whether the stored value at position 0 is non-zero after the int16 truncation.
-VP8_FN int parse_block(BoolDec& d, const uint8_t* tp, int ctx, uint32_t dq, int n, int16_t* out, int* dc_nz) {
-  const uint8_t* p = tp + kBandOff[n] + ctx * 11;
+// Probabilities laid out by coefficient position instead of band, so that walking a block is pure pointer
+// arithmetic: [type 4][position 17][ctx 3][11] = 4 x 561 bytes (position 16 is only ever addressed, never read).
+#define VP8B_POSPROB_TYPE 561
+#define VP8B_POSPROB_BYTES (4 * VP8B_POSPROB_TYPE)
+VP8_TABLE uint8_t kBandOfPos[17] = { 0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7, 0 };
+// byte k of the expanded table (any thread subset may fill its slice)
+VP8_FN uint8_t posprob_byte(const uint8_t* prob /* [4][8][3][11] */, int k) {
+  const int t = k / VP8B_POSPROB_TYPE, r = k % VP8B_POSPROB_TYPE;
+  return prob[t * 264 + kBandOfPos[r / 33] * 33 + r % 33];
+}
+
+// One 4x4 block. `tp` = this block type's [17 positions][3 ctx][11] table (shared memory), `out` = 16 int16 in
+// HBM (pre-zeroed): the decoded LEVELS in parse (zigzag) order; dequantisation and the zigzag scatter happen
+// where the coefficients are consumed (recon_macroblock). Returns nz = index of the last decoded coefficient
+// + 1 (GetCoeffs, vp8_dec.c:443-469).
+VP8_FN int parse_block(BoolDec& d, const uint8_t* tp, int ctx, int n, int16_t* out) {
+  const uint8_t* pz = tp + n * 33;       // position n, ctx 0
+  const uint8_t* p = pz + ctx * 11;
   for (;;) {
     bd_fill(d);
-    if (!bd_bit_nofill(d, p[0])) return n;
+    if (!bd_bit_nofill(d, p[0])) break;
     while (!bd_bit_nofill(d, p[1])) {
+      pz += 33;
+      p = pz;
       if (++n == 16) return 16;
-      p = tp + kBandOff[n];
       bd_fill(d);
     }
-    const uint8_t* pn = tp + kBandOff[n + 1];
     int v;
     if (!bd_bit_nofill(d, p[2])) {
       v = 1;
-      pn += 11;
+      p = pz + (33 + 11);
     } else {
       v = large_value(d, p);
-      pn += 22;
+      p = pz + (33 + 22);
     }
     if (bd_half_nofill(d)) v = -v;
-    const int16_t c = (int16_t)(v * (int)(n > 0 ? (dq >> 16) : (dq & 0xffffu)));
-    out[kZigzagPos[n]] = c;
-    if (n == 0) *dc_nz = (c != 0);
-    if (++n == 16) return 16;
-    p = pn;
+    out[n] = (int16_t)v;
+    pz += 33;
+    if (++n == 16) break;
   }
+  return n;
 }
 
 // Progress hand-off between the token partitions of one image: partition p publishes how many macroblocks
@@ -434,13 +446,12 @@ VP8_FN void token_part_init(TokenPart& tp, const uint8_t* frame, const FrameHdr*
 }
 
 // One macroblock row `my` of partition `part` (= my % P).
-//   probs     : 1056 bytes, this frame's coefficient probabilities (shared memory)
-//   dqs       : the frame's dequantisers as dc | ac << 16 words, [segment][y1, y2, uv] (shared memory)
+//   probs     : VP8B_POSPROB_BYTES, this frame's coefficient probabilities by position (shared memory)
 //   topctx    : (P+1) rows x mb_w uint16 ring of per-column contexts (shared by the image's partitions)
 //   progress  : P counters (shared); see above
 // Writes coefficients and MbInfo z / w.
 VP8_FN void parse_token_row(TokenPart& tp, const ImgDesc& im, const FrameHdr* h, int part, int my, const uint8_t* probs,
-                            const uint32_t* dqs, uint16_t* topctx, volatile int* progress, uint32_t* mbinfo, int16_t* coeffs) {
+                            uint16_t* topctx, volatile int* progress, uint32_t* mbinfo, int16_t* coeffs) {
   const int P = h->num_parts, mb_w = im.mb_w;
   const int use_skip = h->use_skip;
   BoolDec& d = tp.d;
@@ -463,7 +474,6 @@ VP8_FN void parse_token_row(TokenPart& tp, const ImgDesc& im, const FrameHdr* h,
     uint32_t nzy = 0, nzuv = 0;
     const uint32_t is_i4 = (w >> 16) & 1u;   // MBW_I4X4
     if (!(use_skip && (w & MBW_SKIP))) {
-      const uint32_t* q3 = dqs + 3 * ((w >> MBW_SEG_SHIFT) & 3);
       for (int seq = (int)is_i4; seq < 25; ++seq) {
         const uint32_t sq = kBlockSeq[seq];
         const uint32_t tb = sq & 15u, lb = (sq >> 4) & 15u;
@@ -471,10 +481,10 @@ VP8_FN void parse_token_row(TokenPart& tp, const ImgDesc& im, const FrameHdr* h,
         const uint32_t first = ((sq >> 14) & 1u) ^ i4_luma;   // luma block of an i16 macroblock: starts at coefficient 1
         const uint32_t type = i4_luma ? 3u : ((sq >> 15) & 3u);
         const int ctx = (int)(((tctx >> tb) & 1u) + ((lctx >> lb) & 1u));
-        int dcnz = 0;
-        const int nz = parse_block(d, probs + type * 264u, ctx, q3[(sq >> 17) & 3u], (int)first, dst + 16 * ((sq >> 19) & 31u), &dcnz);
+        const int nz = parse_block(d, probs + type * (uint32_t)VP8B_POSPROB_TYPE, ctx, (int)first, dst + 16 * ((sq >> 19) & 31u));
         const uint32_t l = (nz > (int)first) ? 1u : 0u;
-        const uint32_t code = ((nz > 3) ? 3u : (nz > 1) ? 2u : (uint32_t)dcnz) << ((sq >> 8) & 31u);
+        // nz code; a lone DC level counts as "DC only" here and is re-examined after dequantisation (recon_macroblock)
+        const uint32_t code = ((nz > 3) ? 3u : (nz > 1) ? 2u : l) << ((sq >> 8) & 31u);
         if (sq & SQ_LUMA) nzy |= code;
         if (sq & SQ_CHROMA) nzuv |= code;
         if (seq == 0 && nz > 0) w |= MBW_HAS_Y2;

@@ -22,11 +22,13 @@
 #define VP8_PTABLE static __constant__ const
 #define WARP_PHASE(lane) { const int lane = (int)(threadIdx.x & 31);
 #define WARP_PHASE_END } __syncwarp();
+#define VP8_PCLZ(x) __clz((int)(x))
 #else
 #define VP8_PFN static inline
 #define VP8_PTABLE static const
 #define WARP_PHASE(lane) for (int lane = 0; lane < 32; ++lane) {
 #define WARP_PHASE_END }
+#define VP8_PCLZ(x) __builtin_clz((unsigned)(x))
 struct uint2 { uint32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
 #endif
@@ -47,7 +49,8 @@ struct ReconWs {
   int32_t tmp[2 * 16];                // first IDCT pass of the two blocks in flight
   uint8_t edge[16];                   // 4x4 predictor edge: L L L K J I X A B C D E F G H H
   uint32_t nzy;                       // running non_zero_y (DC codes of i16 blocks get filled in here)
-  uint32_t pad[3];
+  uint32_t nzuv;                      // non_zero_uv after the lone-DC check
+  uint32_t pad[2];
 };
 
 // Wavefront context of one image (shared memory of the block that owns the image): the unfiltered pixels each
@@ -136,29 +139,34 @@ VP8_PFN int check_mode(int mx, int my, int mode) {
   return mode;
 }
 
+VP8_PTABLE uint8_t kZigzagOfPos[16] = { 0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15 };
+
 // Reconstructs macroblock (mx, my) of one image with one warp. `info` = this macroblock's MbInfo (4 words),
-// `coeffs` = its 400 coefficients in HBM, planes = the image's padded Y/U/V in HBM (write-only here).
-// Also finalises MbInfo: DC codes of i16 blocks and the filter-inner bit (vp8_dec.c:629-633).
+// `coeffs` = its 400 coefficient LEVELS in HBM (parse order inside each block, as the token parser left them),
+// dq6 = the dequantisers of the macroblock's segment {y1 dc, ac, y2 dc, ac, uv dc, ac} (VP8ParseQuant,
+// quant_dec.c:62-112; the multiply and the int16 store are GetCoeffs', vp8_dec.c:463-466), planes = the image's
+// padded Y/U/V in HBM (write-only here).
+// Also finalises MbInfo: nz codes of lone-DC blocks and of i16 blocks, and the filter-inner bit (vp8_dec.c:629-633).
 VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, int mb_w, uint32_t* info,
-                              const int16_t* coeffs, uint8_t* yplane, uint8_t* uplane, uint8_t* vplane) {
+                              const int16_t* coeffs, const int16_t* dq6, uint8_t* yplane, uint8_t* uplane, uint8_t* vplane) {
   const uint32_t w = info[3];
   const uint32_t m0 = info[0], m1 = info[1];
   const uint32_t nzy_in = info[2];
-  const uint32_t nzuv = w & 0xffffu;
+  const uint32_t nzuv_in = w & 0xffffu;
   const int is_i4 = (w & MBW_I4X4) != 0;
   const int has_y2 = (w & MBW_HAS_Y2) != 0;
-  const int any_coef = (nzy_in | nzuv) != 0 || has_y2;
+  const int any_coef = (nzy_in | nzuv_in) != 0 || has_y2;
   const int ys = 16 * mb_w, uvs = 8 * mb_w;
 
-  // ---- phase 0: coefficients HBM -> shared, neighbour pixels -> tile
+  // ---- phase 0: levels HBM -> dequantised coefficients in raster order in shared; neighbour pixels -> tile
   WARP_PHASE(lane)
     if (any_coef) {
-      const uint4* src = (const uint4*)coeffs;
-      uint4* dst = (uint4*)ws.coef;
-      dst[lane] = src[lane];
-      if (lane < 18) dst[32 + lane] = src[32 + lane];
+      for (int i = lane; i < VP8B_COEFFS_PER_MB; i += 32) {
+        const int blk = i >> 4, n = i & 15;
+        const int qi = ((blk < 16) ? 0 : (blk < 24) ? 4 : 2) + (n > 0);
+        ws.coef[blk * 16 + kZigzagOfPos[n]] = (int16_t)((int)coeffs[i] * (int)dq6[qi]);
+      }
     }
-    if (lane == 0) ws.nzy = nzy_in;
     if (lane < 16) {
       ws.y[4 + lane] = (my > 0) ? cx.top_y[16 * mx + lane] : 127;
       ws.y[(lane + 1) * 32 + 3] = (mx > 0) ? cx.left_y[16 * my + lane] : 129;
@@ -177,6 +185,25 @@ VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, i
       ws.uv[(k + 1) * 32 + 19] = (mx > 0) ? cx.left_v[8 * my + k] : 129;
     }
   WARP_PHASE_END
+  // A block whose only token was the DC counts as coded only if the dequantised int16 is non-zero
+  // (NzCodeBits(nz, dst[0] != 0), vp8_dec.c:511-515): the parser could not know, so look now.
+  WARP_PHASE(lane)
+    if (lane == 0) {
+      uint32_t ny = nzy_in, nuv = nzuv_in;
+      for (uint32_t m = ny & ~(ny >> 1) & 0x55555555u; m != 0; m &= m - 1) {
+        const int sh = 31 - VP8_PCLZ(m & (0u - m));   // bit position of the lowest lone-DC code
+        if (ws.coef[((30 - sh) >> 1) * 16] == 0) ny &= ~(1u << sh);
+      }
+      for (uint32_t m = nuv & ~(nuv >> 1) & 0x5555u; m != 0; m &= m - 1) {
+        const int sh = 31 - VP8_PCLZ(m & (0u - m));
+        const int c = 4 * (sh >> 3) + ((6 - (sh & 7)) >> 1);   // inverse of sh = 8 * (c >> 2) + 6 - 2 * (c & 3)
+        if (ws.coef[(16 + c) * 16] == 0) nuv &= ~(1u << sh);
+      }
+      ws.nzy = ny; ws.nzuv = nuv;
+    }
+  WARP_PHASE_END
+  const uint32_t nzuv = ws.nzuv;
+
 
   // ---- phase 1: inverse WHT of the Y2 block into the 16 luma DCs (dsp/dec.c:137-162)
   if (!is_i4 && has_y2) {
@@ -335,7 +362,8 @@ VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, i
       cx.corner[4 * my + 1] = ws.uv[11];
       cx.corner[4 * my + 2] = ws.uv[27];
       info[2] = nzy;
-      info[3] = (is_i4 || (nzy | nzuv) != 0) ? (w | MBW_INNER) : (w & ~MBW_INNER);
+      const uint32_t w2 = (w & 0xffff0000u) | nzuv;
+      info[3] = (is_i4 || (nzy | nzuv) != 0) ? (w2 | MBW_INNER) : (w2 & ~MBW_INNER);
     }
   WARP_PHASE_END
 }

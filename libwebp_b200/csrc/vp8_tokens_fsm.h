@@ -196,10 +196,9 @@ struct TokLane {
   // block
   int seq;            // 0 = Y2, 1..16 luma, 17..24 chroma; 25 = macroblock done
   uint32_t sq;        // block sequence word of `seq`
-  int first, dcnz;
+  int first;
   uint32_t tnz, lnz;  // bit 0-3 luma, 4-5 U, 6-7 V, 8 Y2
   uint32_t nzy, nzuv;
-  uint32_t dq;        // dc | ac << 16
   uint32_t outi;      // index of the current block's first coefficient inside the image's coefficient plane
   // macroblock / partition
   int mx, my, part, done_mbs, phase, status;
@@ -301,7 +300,7 @@ TK_FN void tk_lane_init(TokLane& L, tk_saddr ring_s, tk_saddr ctl_s, uint64_t fr
   L.limit = 8 * (int64_t)size - 8;
   L.state8 = 0; L.pp = 0; L.pnb = 0; L.pbase = 0;
   L.v = 0; L.n = 0; L.nc11 = 0; L.extra_left = 0; L.cat = 0;
-  L.seq = 0; L.sq = 0; L.first = 0; L.dcnz = 0; L.tnz = 0; L.lnz = 0; L.nzy = 0; L.nzuv = 0; L.dq = 0; L.outi = 0;
+  L.seq = 0; L.sq = 0; L.first = 0; L.tnz = 0; L.lnz = 0; L.nzy = 0; L.nzuv = 0; L.outi = 0;
   L.mx = 0; L.my = part; L.part = part; L.done_mbs = 0; L.phase = 0; L.status = VP8B_OK; L.w = 0; L.seg = 0;
   L.w_next = (part < mb_h) ? tk_ldg_u32(mbinfo + 4 * ((size_t)part * mb_w) + 3) : 0;
 }
@@ -325,14 +324,12 @@ TK_FN void tk_block_setup(TokLane& L, const TokShared& sh, uint32_t mb_coef_inde
   const uint32_t type = i4_luma ? 3u : TQ_TYPE(q);
   const uint32_t ctx = ((L.tnz >> TQ_TB(q)) & 1u) + ((L.lnz >> TQ_LB(q)) & 1u);
   L.sq = q;
-  L.dq = tk_lds_u32(sh.img_s + TKI_DQ + 12u * (uint32_t)L.seg + 4u * TQ_QPAIR(q));
   L.first = (int)i16_luma;
   L.n = (int)i16_luma;
   L.pbase = sh.img_s + type * 264u;
   L.pp = L.pbase + i16_luma * 33u + ctx * 11u;
   L.pnb = L.pbase + (i16_luma ? 66u : 33u);   // band(n + 1) * 33 for n = 1 / n = 0
   L.state8 = S_P0 * 8;
-  L.dcnz = 0;
   L.outi = mb_coef_index + TQ_BLK(q) * 16u;
 }
 
@@ -341,7 +338,7 @@ TK_FN void tk_block_end(TokLane& L, int nz) {
   const uint32_t q = L.sq;
   const uint32_t tb = TQ_TB(q), lb = TQ_LB(q);
   const uint32_t l = (nz > L.first) ? 1u : 0u;
-  const uint32_t code = ((nz > 3) ? 3u : (nz > 1) ? 2u : (uint32_t)L.dcnz) << TQ_NZSH(q);
+  const uint32_t code = ((nz > 3) ? 3u : (nz > 1) ? 2u : l) << TQ_NZSH(q);   // lone DC: re-examined by recon_macroblock
   if (q & TQ_LUMA) L.nzy |= code;
   if (q & TQ_CHROMA) L.nzuv |= code;
   if (!(q & (TQ_LUMA | TQ_CHROMA)) && nz > 0) L.w |= MBW_HAS_Y2;
@@ -410,7 +407,7 @@ TK_FN void tk_mb_start(TokLane& L, const TokShared& sh, const ImgDesc& im, int P
 }
 
 // One iteration of a lane in phase 1: one boolean decode and its consequences.
-//   coeffs : this image's coefficient plane (int16, pre-zeroed)
+//   coeffs : this image's coefficient plane (int16 levels in parse order, pre-zeroed)
 TK_FN void tk_step(TokLane& L, const TokShared& sh, const ImgDesc& im, int P, uint32_t* mbinfo, int16_t* coeffs) {
   const uint32_t prob = tk_lds_u8(L.pp);
   uint32_t e0, e1;
@@ -457,13 +454,7 @@ TK_FN void tk_step(TokLane& L, const TokShared& sh, const ImgDesc& im, int P, ui
     }
   }
   int done = -1;
-  if (e & TE_EMIT) {
-    const int val = (e & TE_NEG) ? -L.v : L.v;
-    const int q = (int)((L.n > 0) ? (L.dq >> 16) : (L.dq & 0xffffu));
-    const int16_t c = (int16_t)(val * q);
-    coeffs[L.outi + tk_lds_u8(sh.tab_s + TKT_ZIGZAG + L.n)] = c;
-    L.dcnz |= (L.n == 0 && c != 0) ? 1 : 0;
-  }
+  if (e & TE_EMIT) coeffs[L.outi + (uint32_t)L.n] = (int16_t)((e & TE_NEG) ? -L.v : L.v);   // level, parse order
   if (e & TE_NEWCOEF) {   // a zero (row ctx 0, node 1) or a finished coefficient (row nextctx, node 0)
     pp = L.pnb + ((e & TE_ZERO) ? 1u : L.nc11);
     L.n++;

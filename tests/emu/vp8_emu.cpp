@@ -114,11 +114,13 @@ extern "C" int emu_decode(const uint8_t* data, size_t size, int csp, int flags, 
   } else {   // rows interleaved over the partitions in dependency order
     const int P = hdr.num_parts;
     std::vector<TokenPart> tp(P);
+    std::vector<uint8_t> posprob(VP8B_POSPROB_BYTES);
+    for (int k = 0; k < VP8B_POSPROB_BYTES; ++k) posprob[k] = posprob_byte(hdr.prob, k);
     std::vector<uint16_t> topctx((size_t)(P + 1) * mb_w, 0);
     std::vector<int> progress(P, 0);
     for (int p = 0; p < P; ++p) token_part_init(tp[p], frame, &hdr, p);
     for (int my = 0; my < mb_h; ++my) {
-      parse_token_row(tp[my % P], im, &hdr, my % P, my, hdr.prob, (const uint32_t*)hdr.dq, topctx.data(), progress.data(), mbinfo.data(), coeffs.data());
+      parse_token_row(tp[my % P], im, &hdr, my % P, my, posprob.data(), topctx.data(), progress.data(), mbinfo.data(), coeffs.data());
     }
     for (int p = 0; p < P && p < mb_h; ++p) if (tp[p].status != VP8B_OK) hdr.status = tp[p].status;
   }
@@ -137,7 +139,8 @@ extern "C" int emu_decode(const uint8_t* data, size_t size, int csp, int flags, 
         const int mx = d - 2 * my;
         if (mx < 0 || mx >= mb_w) continue;
         const size_t idx = (size_t)my * mb_w + mx;
-        recon_macroblock(ws, cx, mx, my, mb_w, mbinfo.data() + 4 * idx, coeffs.data() + idx * VP8B_COEFFS_PER_MB, yp, up, vp);
+        const int16_t* dq6 = hdr.dq[(mbinfo[4 * idx + 3] >> MBW_SEG_SHIFT) & 3];
+        recon_macroblock(ws, cx, mx, my, mb_w, mbinfo.data() + 4 * idx, coeffs.data() + idx * VP8B_COEFFS_PER_MB, dq6, yp, up, vp);
       }
     }
   }
