@@ -392,9 +392,12 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
       w.max_mb_w = std::max(w.max_mb_w, (int)b->imgs[k].mb_w);
       w.max_mb_h = std::max(w.max_mb_h, (int)b->imgs[k].mb_h);
       const ImgDesc& d = b->imgs[k];
+      // work items of the output kernel (must match k_emit / emit_uses_pairs in vp8_pixel_core.h)
+      const bool pairs = !(d.flags & VP8B_FLAG_NO_FANCY) && kBpp[d.csp] == 4;
       const int units = (d.csp == MODE_YUV)
                             ? ((d.width + 15) / 16) * d.height + 2 * ((((d.width + 1) / 2) + 15) / 16) * ((d.height + 1) / 2)
-                            : ((d.width + 3) / 4) * d.height;
+                            : pairs ? ((d.width + 7) / 8) * (d.height / 2 + 1)
+                                    : ((d.width + 3) / 4) * d.height;
       w.max_units = std::max(w.max_units, units);
     }
     b->waves.push_back(w);

@@ -297,6 +297,9 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(const ImgDesc* __restrict
     if (t < ny) emit_yuv_chunk(im, yp, up, vp, o, 0, t % qy, t / qy);
     else if (t < ny + nuv) emit_yuv_chunk(im, yp, up, vp, o, 1, (t - ny) % quv, (t - ny) / quv);
     else if (t < ny + 2 * nuv) emit_yuv_chunk(im, yp, up, vp, o, 2, (t - ny - nuv) % quv, (t - ny - nuv) / quv);
+  } else if (emit_uses_pairs(im.csp, im.flags)) {   // 8 pixels x 2 rows per thread
+    const int qw = (im.width + 7) >> 3;
+    if (t < qw * ((im.height >> 1) + 1)) emit_rgba_pair8(im, yp, up, vp, o, t % qw, t / qw);
   } else {
     const int qw = (im.width + 3) >> 2;
     if (t < qw * im.height) emit_rgb_quad(im, yp, up, vp, o, t % qw, t / qw);

@@ -23,12 +23,14 @@
 #define WARP_PHASE(lane) { const int lane = (int)(threadIdx.x & 31);
 #define WARP_PHASE_END } __syncwarp();
 #define VP8_PCLZ(x) __clz((int)(x))
+#define VP8_UNROLL _Pragma("unroll")
 #else
 #define VP8_PFN static inline
 #define VP8_PTABLE static const
 #define WARP_PHASE(lane) for (int lane = 0; lane < 32; ++lane) {
 #define WARP_PHASE_END }
 #define VP8_PCLZ(x) __builtin_clz((unsigned)(x))
+#define VP8_UNROLL
 struct uint2 { uint32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
 #endif
@@ -577,6 +579,102 @@ VP8_PFN void emit_rgb_quad(const ImgDesc& im, const uint8_t* yplane, const uint8
       for (int k = 0; k < n; ++k) ((uint32_t*)o)[k] = px[k];
     } else {
       for (int k = 0; k < n; ++k) { o[4 * k] = (uint8_t)px[k]; o[4 * k + 1] = (uint8_t)(px[k] >> 8); o[4 * k + 2] = (uint8_t)(px[k] >> 16); o[4 * k + 3] = (uint8_t)(px[k] >> 24); }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fast path of the output stage for the 4-byte RGB family with fancy upsampling: one thread converts 8 pixels
+// of the two output rows 2t-1 and 2t, which share the chroma rows t-1 and t (UPSAMPLE_FUNC processes exactly
+// these row pairs, upsampling.c:37-93; the first and, for even heights, the last row stand alone,
+// io_dec.c:72-109). Edge replication = clamping the chroma column / row (verified against the closed form in
+// fancy_chroma()). Loads are 8-byte (Y) and 4-byte (chroma) words, stores 16-byte.
+#if defined(__CUDACC__) && !defined(VP8_EMU)
+VP8_PFN int sat_u8(int v) { int r; asm("cvt.sat.u8.s32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
+#else
+VP8_PFN int sat_u8(int v) { return v < 0 ? 0 : v > 255 ? 255 : v; }
+#endif
+
+VP8_PFN uint32_t yuv_to_px4(int csp, int y, int u, int v) {
+  const int yy = (y * 19077) >> 8;
+  const int r = sat_u8((yy + ((v * 26149) >> 8) - 14234) >> 6);
+  const int g = sat_u8((yy - ((u * 6419) >> 8) - ((v * 13320) >> 8) + 8708) >> 6);
+  const int b = sat_u8((yy + ((u * 33050) >> 8) - 17685) >> 6);
+  return pack_pixel4(csp, r, g, b);
+}
+
+// Six chroma samples of plane row `row` for output pixels 8q..8q+7: columns 4q-1 .. 4q+4, clamped to [0, uvw).
+VP8_PFN void load_chroma6(const uint8_t* row, int q, int uvw, int c[6]) {
+  const int x0 = 4 * q;
+  if (x0 + 4 < uvw) {   // interior: one aligned word + two neighbours
+    const uint32_t wd = *(const uint32_t*)(row + x0);
+    c[0] = row[x0 > 0 ? x0 - 1 : 0];
+    c[1] = wd & 0xff; c[2] = (wd >> 8) & 0xff; c[3] = (wd >> 16) & 0xff; c[4] = wd >> 24;
+    c[5] = row[x0 + 4];
+  } else {
+    for (int k = 0; k < 6; ++k) { int x = x0 - 1 + k; x = x < 0 ? 0 : x >= uvw ? uvw - 1 : x; c[k] = row[x]; }
+  }
+}
+
+// Upsampled chroma of the 8 pixels for the row whose nearer chroma row is `n` (the other is `f`).
+VP8_PFN void upsample8(const int n[6], const int f[6], int out[8]) {
+VP8_UNROLL
+  for (int k = 0; k < 5; ++k) {   // column pair (k, k+1) of the six: pixels 2k-1 (odd member) and 2k (even member)
+    const int nl = n[k], nr = n[k + 1], fl = f[k], fr = f[k + 1];
+    const int s = nl + nr + fl + fr + 8;
+    if (k > 0) out[2 * k - 1] = (((s + 2 * (nr + fl)) >> 3) + nl) >> 1;
+    if (k < 4) out[2 * k] = (((s + 2 * (nl + fr)) >> 3) + nr) >> 1;
+  }
+}
+
+// Which images take the fast path (host driver and kernel must agree on the work-item count).
+VP8_PFN int emit_uses_pairs(int csp, int flags) {
+  return !(flags & VP8B_FLAG_NO_FANCY) && (csp == 1 || csp == 3 || csp == 4 || csp == 7 || csp == 8 || csp == 9);
+}
+
+// Pixels 8q..8q+7 of output rows 2t-1 and 2t.
+VP8_PFN void emit_rgba_pair8(const ImgDesc& im, const uint8_t* yplane, const uint8_t* uplane, const uint8_t* vplane,
+                             uint8_t* out, int q, int t) {
+  const int w = im.width, h = im.height;
+  const int ys = 16 * im.mb_w, uvs = 8 * im.mb_w;
+  const int uvw = (w + 1) >> 1, uvh = (h + 1) >> 1;
+  const int csp = im.csp;
+  const int ra = t > 0 ? t - 1 : 0, rb = t < uvh ? t : uvh - 1;
+  int ua[6], ub[6], va[6], vb[6];
+  load_chroma6(uplane + (size_t)ra * uvs, q, uvw, ua);
+  load_chroma6(uplane + (size_t)rb * uvs, q, uvw, ub);
+  load_chroma6(vplane + (size_t)ra * uvs, q, uvw, va);
+  load_chroma6(vplane + (size_t)rb * uvs, q, uvw, vb);
+  const int i0 = 8 * q;
+  const int n = (w - i0 < 8) ? w - i0 : 8;
+VP8_UNROLL
+  for (int half = 0; half < 2; ++half) {
+    const int j = 2 * t - 1 + half;
+    if (j < 0 || j >= h) continue;
+    int u8[8], v8[8];
+    if (half == 0) { upsample8(ua, ub, u8); upsample8(va, vb, v8); }
+    else { upsample8(ub, ua, u8); upsample8(vb, va, v8); }
+    const uint2 yw = *(const uint2*)(yplane + (size_t)j * ys + i0);
+    uint32_t px[8];
+VP8_UNROLL
+    for (int k = 0; k < 8; ++k) {
+      const int y = (int)(((k < 4 ? yw.x : yw.y) >> (8 * (k & 3))) & 0xff);
+      px[k] = yuv_to_px4(csp, y, u8[k], v8[k]);
+    }
+    uint8_t* o = out + (size_t)j * im.out_stride + 4 * (size_t)i0;
+    if (n == 8 && (((uintptr_t)o) & 15) == 0) {
+      uint4 a, b;
+      a.x = px[0]; a.y = px[1]; a.z = px[2]; a.w = px[3];
+      b.x = px[4]; b.y = px[5]; b.z = px[6]; b.w = px[7];
+      ((uint4*)o)[0] = a; ((uint4*)o)[1] = b;
+    } else if ((((uintptr_t)o) & 3) == 0) {
+VP8_UNROLL
+      for (int k = 0; k < 8; ++k) if (k < n) ((uint32_t*)o)[k] = px[k];
+    } else {
+VP8_UNROLL
+      for (int k = 0; k < 8; ++k) if (k < n) {
+        o[4 * k] = (uint8_t)px[k]; o[4 * k + 1] = (uint8_t)(px[k] >> 8); o[4 * k + 2] = (uint8_t)(px[k] >> 16); o[4 * k + 3] = (uint8_t)(px[k] >> 24);
+      }
     }
   }
 }

@@ -172,6 +172,8 @@ extern "C" int emu_decode(const uint8_t* data, size_t size, int csp, int flags, 
       const int pw = plane ? uvw : w, ph = plane ? uvh : h;
       for (int j = 0; j < ph; ++j) for (int q = 0; q < (pw + 15) / 16; ++q) emit_yuv_chunk(im, yp, up, vp, out, plane, q, j);
     }
+  } else if (emit_uses_pairs(csp, flags)) {
+    for (int t = 0; t <= h / 2; ++t) for (int q = 0; q < (w + 7) / 8; ++q) emit_rgba_pair8(im, yp, up, vp, out, q, t);
   } else {
     for (int j = 0; j < h; ++j) for (int q = 0; q < (w + 3) / 4; ++q) emit_rgb_quad(im, yp, up, vp, out, q, j);
   }
