@@ -217,6 +217,9 @@ __global__ void __launch_bounds__(32 * RECON_WARPS) k_reconstruct(const ImgDesc*
   ReconWs& ws = *reinterpret_cast<ReconWs*>(smem + sizeof(ReconWs) * warp);
   ReconCtx cx;
   recon_ctx_bind(cx, smem + sizeof(ReconWs) * RECON_WARPS, mb_w, mb_h);
+  __shared__ int16_t dqs[24];   // the frame's dequantisers, [segment][y1 dc/ac, y2 dc/ac, uv dc/ac]
+  if (threadIdx.x < 24) dqs[threadIdx.x] = (&hdrs[img].dq[0][0])[threadIdx.x];
+  __syncthreads();
   const size_t nmb = (size_t)mb_w * mb_h;
   uint8_t* yp = yuv + (size_t)im.mb_base * 384;
   uint8_t* up = yp + nmb * 256;
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(32 * RECON_WARPS) k_reconstruct(const ImgDesc*
     for (int my = my_lo + warp; my <= my_hi; my += RECON_WARPS) {
       const int mx = d - 2 * my;
       const size_t idx = (size_t)my * mb_w + mx;
-      const int16_t* dq6 = hdrs[img].dq[(mbi[4 * idx + 3] >> MBW_SEG_SHIFT) & 3];
+      const int16_t* dq6 = dqs + 6 * ((mbi[4 * idx + 3] >> MBW_SEG_SHIFT) & 3);
       recon_macroblock(ws, cx, mx, my, mb_w, mbi + 4 * idx, cf + idx * VP8B_COEFFS_PER_MB, dq6, yp, up, vp);
     }
     __syncthreads();

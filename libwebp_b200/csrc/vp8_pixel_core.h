@@ -45,14 +45,13 @@ VP8_PFN int mul2(int a) { return (a * 35468) >> 16; }
 // the four pixels above-right (replicated at rows 4, 8, 12 for the right-most sub-blocks, frame_dec.c:131-141).
 // Chroma: u at uv[(r + 1) * 32 + c + 4], v at uv[(r + 1) * 32 + c + 20].
 struct ReconWs {
-  int16_t coef[VP8B_COEFFS_PER_MB];   // 800 B, 16-byte aligned
+  int16_t res[24 * 16];               // residual (IDCT output, already >> 3) of blocks 0-23, raster order inside a block
   uint8_t y[17 * 32];
   uint8_t uv[9 * 32];
-  int32_t tmp[2 * 16];                // first IDCT pass of the two blocks in flight
-  uint8_t edge[16];                   // 4x4 predictor edge: L L L K J I X A B C D E F G H H
-  uint32_t nzy;                       // running non_zero_y (DC codes of i16 blocks get filled in here)
-  uint32_t nzuv;                      // non_zero_uv after the lone-DC check
-  uint32_t pad[2];
+  int16_t dc[16];                     // inverse WHT of the Y2 block: DC coefficient of the 16 luma blocks (i16 only)
+  uint8_t edge[2][16];                // 4x4 predictor edges of the two sub-blocks in flight: L L L K J I X A B C D E F G H H
+  uint32_t nz;                        // some block of the macroblock has a non-zero coefficient
+  uint32_t pad[3];
 };
 
 // Wavefront context of one image (shared memory of the block that owns the image): the unfiltered pixels each
@@ -88,24 +87,55 @@ VP8_PTABLE uint8_t kPred4[8][16] = {
   /* HU */ { 0x84, 3, 0x83, 2, 0x83, 2, 0x82, 1, 0x82, 1, 0, 0, 0, 0, 0, 0 }
 };
 
-// First IDCT pass of block `blk` by 16 lanes (l = 0..15): input column c = l >> 2, output k = l & 3
-// (TransformOne_C vertical pass, dsp/dec.c:48-59).
-VP8_PFN void idct_pass1(const int16_t* in, int l, int32_t* tmp) {
-  const int c = l >> 2, k = l & 3;
-  const int i0 = in[c], i1 = in[4 + c], i2 = in[8 + c], i3 = in[12 + c];
-  const int a = i0 + i2, b = i0 - i2;
-  const int cc = mul2(i1) - mul1(i3), d = mul1(i1) + mul2(i3);
-  tmp[4 * c + k] = (k == 0) ? a + d : (k == 1) ? b + cc : (k == 2) ? b - cc : a - d;
+// 16 coefficient levels of one block (parse order, two 16-byte words of HBM) -> dequantised int16 values in raster
+// order (GetCoeffs' `out[kZigzag[n]] = level * dq[n > 0]` with the int16 store, vp8_dec.c:463-466).
+VP8_PFN void load_block_coeffs(const int16_t* levels, int q_dc, int q_ac, int in[16]) {
+  const uint4 a = ((const uint4*)levels)[0], b = ((const uint4*)levels)[1];
+  const uint32_t wd[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+  // raster position of parse position n (kZigzag, vp8_dec.c:406)
+  const int zz[16] = { 0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15 };
+  VP8_UNROLL
+  for (int n = 0; n < 16; ++n) {
+    const int lvl = (n & 1) ? ((int)wd[n >> 1] >> 16) : (int)(int16_t)(wd[n >> 1] & 0xffffu);
+    in[zz[n]] = (int)(int16_t)(lvl * (n == 0 ? q_dc : q_ac));
+  }
 }
 
-// Second pass for pixel (px, py): residual to add to the prediction, already >> 3 (dsp/dec.c:67-80).
-VP8_PFN int idct_pass2(const int32_t* tmp, int px, int py) {
-  const int t0 = tmp[py], t1 = tmp[4 + py], t2 = tmp[8 + py], t3 = tmp[12 + py];
-  const int dc = t0 + 4;
-  const int a = dc + t2, b = dc - t2;
-  const int c = mul2(t1) - mul1(t3), d = mul1(t1) + mul2(t3);
-  const int r = (px == 0) ? a + d : (px == 1) ? b + c : (px == 2) ? b - c : a - d;
-  return r >> 3;
+// TransformOne_C (dsp/dec.c:44-82) without the prediction: out = the 16 residuals to add, raster order.
+VP8_PFN void idct_block(const int in[16], int out[16]) {
+  int tmp[16];
+  VP8_UNROLL
+  for (int i = 0; i < 4; ++i) {   // vertical pass
+    const int a = in[i] + in[8 + i], b = in[i] - in[8 + i];
+    const int c = mul2(in[4 + i]) - mul1(in[12 + i]), d = mul1(in[4 + i]) + mul2(in[12 + i]);
+    tmp[4 * i + 0] = a + d; tmp[4 * i + 1] = b + c; tmp[4 * i + 2] = b - c; tmp[4 * i + 3] = a - d;
+  }
+  VP8_UNROLL
+  for (int i = 0; i < 4; ++i) {   // horizontal pass: output row i
+    const int dc = tmp[i] + 4;
+    const int a = dc + tmp[8 + i], b = dc - tmp[8 + i];
+    const int c = mul2(tmp[4 + i]) - mul1(tmp[12 + i]), d = mul1(tmp[4 + i]) + mul2(tmp[12 + i]);
+    out[4 * i + 0] = (a + d) >> 3; out[4 * i + 1] = (b + c) >> 3; out[4 * i + 2] = (b - c) >> 3; out[4 * i + 3] = (a - d) >> 3;
+  }
+}
+
+// TransformWHT_C (dsp/dec.c:137-162): 16 dequantised Y2 coefficients (raster order) -> DC of luma block k in dc[k].
+VP8_PFN void wht_block(const int in[16], int16_t dc[16]) {
+  int tmp[16];
+  VP8_UNROLL
+  for (int i = 0; i < 4; ++i) {
+    const int a0 = in[0 + i] + in[12 + i], a1 = in[4 + i] + in[8 + i];
+    const int a2 = in[4 + i] - in[8 + i], a3 = in[0 + i] - in[12 + i];
+    tmp[0 + i] = a0 + a1; tmp[8 + i] = a0 - a1; tmp[4 + i] = a3 + a2; tmp[12 + i] = a3 - a2;
+  }
+  VP8_UNROLL
+  for (int i = 0; i < 4; ++i) {
+    const int d0 = tmp[0 + i * 4] + 3;
+    const int a0 = d0 + tmp[3 + i * 4], a1 = tmp[1 + i * 4] + tmp[2 + i * 4];
+    const int a2 = tmp[1 + i * 4] - tmp[2 + i * 4], a3 = d0 - tmp[3 + i * 4];
+    dc[4 * i + 0] = (int16_t)((a0 + a1) >> 3); dc[4 * i + 1] = (int16_t)((a3 + a2) >> 3);
+    dc[4 * i + 2] = (int16_t)((a0 - a1) >> 3); dc[4 * i + 3] = (int16_t)((a3 - a2) >> 3);
+  }
 }
 
 // 16x16 / 8x8 prediction of one pixel. t = pointer to the block origin inside a 32-byte-stride tile.
@@ -141,44 +171,47 @@ VP8_PFN int check_mode(int mx, int my, int mode) {
   return mode;
 }
 
-VP8_PTABLE uint8_t kZigzagOfPos[16] = { 0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15 };
-
 // Reconstructs macroblock (mx, my) of one image with one warp. `info` = this macroblock's MbInfo (4 words),
 // `coeffs` = its 400 coefficient LEVELS in HBM (parse order inside each block, as the token parser left them),
 // dq6 = the dequantisers of the macroblock's segment {y1 dc, ac, y2 dc, ac, uv dc, ac} (VP8ParseQuant,
-// quant_dec.c:62-112; the multiply and the int16 store are GetCoeffs', vp8_dec.c:463-466), planes = the image's
-// padded Y/U/V in HBM (write-only here).
-// Also finalises MbInfo: nz codes of lone-DC blocks and of i16 blocks, and the filter-inner bit (vp8_dec.c:629-633).
+// quant_dec.c:62-112), planes = the image's padded Y/U/V in HBM (write-only here).
+// Order of work: (0) neighbour pixels into the tile, inverse WHT by one lane; (1) one lane per 4x4 block:
+// dequantise + inverse DCT in registers, residuals to shared; (2) luma prediction + residual: all 256 pixels at
+// once for i16, a 10-step sub-block wavefront (two sub-blocks per step) for i4x4; (3) chroma; (4) tile -> planes.
+// Also finalises MbInfo: the filter-inner bit (vp8_dec.c:629-633), which needs the lone-DC rule
+// NzCodeBits(nz, dst[0] != 0) (vp8_dec.c:511-515) evaluated on the dequantised int16.
 VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, int mb_w, uint32_t* info,
                               const int16_t* coeffs, const int16_t* dq6, uint8_t* yplane, uint8_t* uplane, uint8_t* vplane) {
   const uint32_t w = info[3];
   const uint32_t m0 = info[0], m1 = info[1];
-  const uint32_t nzy_in = info[2];
-  const uint32_t nzuv_in = w & 0xffffu;
+  const uint32_t nzy = info[2];
+  const uint32_t nzuv = w & 0xffffu;
   const int is_i4 = (w & MBW_I4X4) != 0;
   const int has_y2 = (w & MBW_HAS_Y2) != 0;
-  const int any_coef = (nzy_in | nzuv_in) != 0 || has_y2;
+  const int any_coef = (nzy | nzuv) != 0 || has_y2;
   const int ys = 16 * mb_w, uvs = 8 * mb_w;
 
-  // ---- phase 0: levels HBM -> dequantised coefficients in raster order in shared; neighbour pixels -> tile
+  // ---- phase 0: neighbour pixels -> tile; inverse WHT of the Y2 block (lane 21)
   WARP_PHASE(lane)
-    if (any_coef) {
-      for (int i = lane; i < VP8B_COEFFS_PER_MB; i += 32) {
-        const int blk = i >> 4, n = i & 15;
-        const int qi = ((blk < 16) ? 0 : (blk < 24) ? 4 : 2) + (n > 0);
-        ws.coef[blk * 16 + kZigzagOfPos[n]] = (int16_t)((int)coeffs[i] * (int)dq6[qi]);
-      }
-    }
+    if (lane == 0) ws.nz = 0;
     if (lane < 16) {
       ws.y[4 + lane] = (my > 0) ? cx.top_y[16 * mx + lane] : 127;
       ws.y[(lane + 1) * 32 + 3] = (mx > 0) ? cx.left_y[16 * my + lane] : 129;
     } else if (lane < 20) {
       const int k = lane - 16;
-      ws.y[20 + k] = (my > 0) ? ((mx < mb_w - 1) ? cx.top_y[16 * (mx + 1) + k] : cx.top_y[16 * mx + 15]) : 127;
+      const uint8_t tr = (my > 0) ? ((mx < mb_w - 1) ? cx.top_y[16 * (mx + 1) + k] : cx.top_y[16 * mx + 15]) : 127;
+      ws.y[20 + k] = tr;
+      if (is_i4) { ws.y[4 * 32 + 20 + k] = tr; ws.y[8 * 32 + 20 + k] = tr; ws.y[12 * 32 + 20 + k] = tr; }
     } else if (lane == 20) {
       ws.y[3] = (my > 0) ? ((mx > 0) ? cx.corner[4 * my + 0] : 129) : 127;
       ws.uv[3] = (my > 0) ? ((mx > 0) ? cx.corner[4 * my + 1] : 129) : 127;
       ws.uv[19] = (my > 0) ? ((mx > 0) ? cx.corner[4 * my + 2] : 129) : 127;
+    } else if (lane == 21) {
+      if (!is_i4 && has_y2) {
+        int in[16];
+        load_block_coeffs(coeffs + 24 * 16, dq6[2], dq6[3], in);
+        wht_block(in, ws.dc);
+      }
     } else if (lane >= 24) {
       const int k = lane - 24;
       ws.uv[4 + k] = (my > 0) ? cx.top_u[8 * mx + k] : 127;
@@ -187,98 +220,81 @@ VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, i
       ws.uv[(k + 1) * 32 + 19] = (mx > 0) ? cx.left_v[8 * my + k] : 129;
     }
   WARP_PHASE_END
-  // A block whose only token was the DC counts as coded only if the dequantised int16 is non-zero
-  // (NzCodeBits(nz, dst[0] != 0), vp8_dec.c:511-515): the parser could not know, so look now.
-  WARP_PHASE(lane)
-    if (lane == 0) {
-      uint32_t ny = nzy_in, nuv = nzuv_in;
-      for (uint32_t m = ny & ~(ny >> 1) & 0x55555555u; m != 0; m &= m - 1) {
-        const int sh = 31 - VP8_PCLZ(m & (0u - m));   // bit position of the lowest lone-DC code
-        if (ws.coef[((30 - sh) >> 1) * 16] == 0) ny &= ~(1u << sh);
-      }
-      for (uint32_t m = nuv & ~(nuv >> 1) & 0x5555u; m != 0; m &= m - 1) {
-        const int sh = 31 - VP8_PCLZ(m & (0u - m));
-        const int c = 4 * (sh >> 3) + ((6 - (sh & 7)) >> 1);   // inverse of sh = 8 * (c >> 2) + 6 - 2 * (c & 3)
-        if (ws.coef[(16 + c) * 16] == 0) nuv &= ~(1u << sh);
-      }
-      ws.nzy = ny; ws.nzuv = nuv;
-    }
-  WARP_PHASE_END
-  const uint32_t nzuv = ws.nzuv;
 
-
-  // ---- phase 1: inverse WHT of the Y2 block into the 16 luma DCs (dsp/dec.c:137-162)
-  if (!is_i4 && has_y2) {
+  // ---- phase 1: residuals of all 24 blocks, one lane per block
+  if (any_coef) {
     WARP_PHASE(lane)
-      if (lane < 4) {
-        const int16_t* in = ws.coef + 24 * 16;
-        const int i = lane;
-        const int a0 = in[0 + i] + in[12 + i], a1 = in[4 + i] + in[8 + i];
-        const int a2 = in[4 + i] - in[8 + i], a3 = in[0 + i] - in[12 + i];
-        ws.tmp[0 + i] = a0 + a1; ws.tmp[8 + i] = a0 - a1; ws.tmp[4 + i] = a3 + a2; ws.tmp[12 + i] = a3 - a2;
-      }
-    WARP_PHASE_END
-    WARP_PHASE(lane)
-      if (lane < 4) {
-        const int i = lane;
-        const int dc = ws.tmp[0 + i * 4] + 3;
-        const int a0 = dc + ws.tmp[3 + i * 4], a1 = ws.tmp[1 + i * 4] + ws.tmp[2 + i * 4];
-        const int a2 = ws.tmp[1 + i * 4] - ws.tmp[2 + i * 4], a3 = dc - ws.tmp[3 + i * 4];
-        ws.coef[(4 * i + 0) * 16] = (int16_t)((a0 + a1) >> 3);
-        ws.coef[(4 * i + 1) * 16] = (int16_t)((a3 + a2) >> 3);
-        ws.coef[(4 * i + 2) * 16] = (int16_t)((a0 - a1) >> 3);
-        ws.coef[(4 * i + 3) * 16] = (int16_t)((a3 - a2) >> 3);
-      }
-    WARP_PHASE_END
-    WARP_PHASE(lane)
-      if (lane == 0) {   // a block whose tokens held no AC gets code 1 iff its DC is non-zero (vp8_dec.c:511-515)
-        uint32_t nzy = ws.nzy;
-        for (int n = 0; n < 16; ++n) {
-          const int sh = 30 - 2 * n;
-          if (((nzy >> sh) & 3) == 0 && ws.coef[n * 16] != 0) nzy |= 1u << sh;
+      if (lane < 24) {
+        const int blk = lane;
+        const int luma = blk < 16;
+        const uint32_t code = luma ? ((nzy >> (30 - 2 * blk)) & 3u)
+                                   : ((nzuv >> (8 * ((blk - 16) >> 2) + 6 - 2 * ((blk - 16) & 3))) & 3u);
+        const int i16_luma = luma && !is_i4;
+        const int wht_dc = (i16_luma && has_y2) ? (int)ws.dc[blk] : 0;
+        int out[16];
+        int coded = 0;
+        if (code != 0 || wht_dc != 0) {
+          int in[16];
+          if (code != 0) {
+            load_block_coeffs(coeffs + blk * 16, luma ? dq6[0] : dq6[4], luma ? dq6[1] : dq6[5], in);
+          } else {
+            VP8_UNROLL
+            for (int k = 0; k < 16; ++k) in[k] = 0;
+          }
+          if (i16_luma) in[0] = wht_dc;
+          coded = (code >= 2) || in[0] != 0;   // a lone DC level whose int16 product is 0 leaves the block uncoded
+          idct_block(in, out);
+        } else {
+          VP8_UNROLL
+          for (int k = 0; k < 16; ++k) out[k] = 0;
         }
-        ws.nzy = nzy;
+        uint4 lo, hi;
+        lo.x = (uint32_t)(uint16_t)out[0] | ((uint32_t)out[1] << 16); lo.y = (uint32_t)(uint16_t)out[2] | ((uint32_t)out[3] << 16);
+        lo.z = (uint32_t)(uint16_t)out[4] | ((uint32_t)out[5] << 16); lo.w = (uint32_t)(uint16_t)out[6] | ((uint32_t)out[7] << 16);
+        hi.x = (uint32_t)(uint16_t)out[8] | ((uint32_t)out[9] << 16); hi.y = (uint32_t)(uint16_t)out[10] | ((uint32_t)out[11] << 16);
+        hi.z = (uint32_t)(uint16_t)out[12] | ((uint32_t)out[13] << 16); hi.w = (uint32_t)(uint16_t)out[14] | ((uint32_t)out[15] << 16);
+        uint4* dst = (uint4*)(ws.res + blk * 16);
+        dst[0] = lo; dst[1] = hi;
+        if (coded) ws.nz = 1;
       }
     WARP_PHASE_END
   }
-  const uint32_t nzy = ws.nzy;
 
   // ---- phase 2: luma
   if (is_i4) {
-    WARP_PHASE(lane)
-      if (lane < 12) ws.y[(4 + 4 * (lane >> 2)) * 32 + 20 + (lane & 3)] = ws.y[20 + (lane & 3)];
-    WARP_PHASE_END
-    for (int n = 0; n < 16; ++n) {
-      const int bx = n & 3, by = n >> 2;
-      const int mode = (int)(((n < 8) ? (m0 >> (4 * n)) : (m1 >> (4 * (n - 8)))) & 15);
-      const int coded = (int)((nzy >> (30 - 2 * n)) & 3);
-      uint8_t* const t = ws.y + (by * 4 + 1) * 32 + bx * 4 + 4;   // block origin in the tile
+    for (int step = 0; step < 10; ++step) {
+      const int by0 = (step > 2) ? (step - 2) >> 1 : 0;   // first sub-block row on this anti-diagonal bx + 2*by = step
       WARP_PHASE(lane)
-        if (lane < 16) {
-          const int i = lane;   // edge element: L L L K J I X A..H H
+        const int by = by0 + (lane >> 4), bx = step - 2 * by;
+        if (by < 4 && bx >= 0 && bx < 4 && lane < 32) {
+          const uint8_t* const t = ws.y + (by * 4 + 1) * 32 + bx * 4 + 4;   // block origin in the tile
+          const int i = lane & 15;   // edge element: L L L K J I X A..H H
           int off;
           if (i < 6) off = ((i < 3) ? 3 : 5 - i) * 32 - 1;
           else if (i == 6) off = -33;
           else off = -32 + ((i - 7 < 7) ? i - 7 : 7);
-          ws.edge[i] = t[off];
-          if (coded) idct_pass1(ws.coef + n * 16, lane, ws.tmp);
+          ws.edge[lane >> 4][i] = t[off];
         }
       WARP_PHASE_END
       WARP_PHASE(lane)
-        if (lane < 16) {
-          const int px = lane & 3, py = lane >> 2;
-          const uint8_t* e = ws.edge;
+        const int by = by0 + (lane >> 4), bx = step - 2 * by;
+        if (by < 4 && bx >= 0 && bx < 4) {
+          const int n = by * 4 + bx;
+          const int mode = (int)(((n < 8) ? (m0 >> (4 * n)) : (m1 >> (4 * (n - 8)))) & 15);
+          uint8_t* const t = ws.y + (by * 4 + 1) * 32 + bx * 4 + 4;
+          const int l = lane & 15, px = l & 3, py = l >> 2;
+          const uint8_t* e = ws.edge[lane >> 4];
           int p;
           if (mode == M_DC) {
             p = (e[2] + e[3] + e[4] + e[5] + e[7] + e[8] + e[9] + e[10] + 4) >> 3;
           } else if (mode == M_TM) {
             p = clip8i((int)e[7 + px] + (int)e[5 - py] - (int)e[6]);
           } else {
-            const int k = kPred4[mode - 2][lane];
+            const int k = kPred4[mode - 2][l];
             const int a = k & 0x7f;
             p = (k & 0x80) ? (e[a] + e[a + 1] + 1) >> 1 : (e[a] + 2 * e[a + 1] + e[a + 2] + 2) >> 2;
           }
-          if (coded) p = clip8i(p + idct_pass2(ws.tmp, px, py));
+          if (any_coef) p = clip8i(p + (int)ws.res[n * 16 + l]);
           t[py * 32 + px] = (uint8_t)p;
         }
       WARP_PHASE_END
@@ -289,58 +305,33 @@ VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, i
     WARP_PHASE(lane)
       const int dc = dc_big(t, mode, 16);
       const int r = lane >> 1, c0 = (lane & 1) * 8;
-      uint8_t v[8];
-      for (int k = 0; k < 8; ++k) v[k] = (uint8_t)pred_big_pixel(t, mode, dc, c0 + k, r);
-      // reads above touch only the border row/column, writes only the block interior: no hazard in a phase
-      for (int k = 0; k < 8; ++k) t[r * 32 + c0 + k] = v[k];
-    WARP_PHASE_END
-    if (nzy != 0) {
-      for (int pair = 0; pair < 8; ++pair) {
-        WARP_PHASE(lane)
-          const int n = 2 * pair + (lane >> 4);
-          if ((nzy >> (30 - 2 * n)) & 3) idct_pass1(ws.coef + n * 16, lane & 15, ws.tmp + 16 * (lane >> 4));
-        WARP_PHASE_END
-        WARP_PHASE(lane)
-          const int n = 2 * pair + (lane >> 4);
-          if ((nzy >> (30 - 2 * n)) & 3) {
-            const int px = lane & 3, py = (lane >> 2) & 3;
-            uint8_t* const b = t + (n >> 2) * 4 * 32 + (n & 3) * 4;
-            b[py * 32 + px] = (uint8_t)clip8i(b[py * 32 + px] + idct_pass2(ws.tmp + 16 * (lane >> 4), px, py));
-          }
-        WARP_PHASE_END
+      int v[8];
+      for (int k = 0; k < 8; ++k) v[k] = pred_big_pixel(t, mode, dc, c0 + k, r);
+      if (any_coef) {
+        const int16_t* ra = ws.res + ((r >> 2) * 4 + (c0 >> 2)) * 16 + (r & 3) * 4;   // blocks (c0>>2) and (c0>>2)+1 of block row r>>2
+        for (int k = 0; k < 4; ++k) { v[k] = clip8i(v[k] + ra[k]); v[4 + k] = clip8i(v[4 + k] + ra[16 + k]); }
       }
-    }
+      // reads above touch only the border row/column, writes only the block interior: no hazard in a phase
+      for (int k = 0; k < 8; ++k) t[r * 32 + c0 + k] = (uint8_t)v[k];
+    WARP_PHASE_END
   }
 
   // ---- phase 3: chroma (lanes 0-15 U, 16-31 V)
   {
     const int mode = check_mode(mx, my, (int)((w >> MBW_UVMODE_SHIFT) & 3));
     WARP_PHASE(lane)
-      uint8_t* const t = ws.uv + 32 + 4 + 16 * (lane >> 4);
+      const int ch = lane >> 4;
+      uint8_t* const t = ws.uv + 32 + 4 + 16 * ch;
       const int dc = dc_big(t, mode, 8);
       const int r = (lane & 15) >> 1, c0 = (lane & 1) * 4;
-      uint8_t v[4];
-      for (int k = 0; k < 4; ++k) v[k] = (uint8_t)pred_big_pixel(t, mode, dc, c0 + k, r);
-      for (int k = 0; k < 4; ++k) t[r * 32 + c0 + k] = v[k];
-    WARP_PHASE_END
-    if (nzuv != 0) {
-      for (int k = 0; k < 4; ++k) {
-        WARP_PHASE(lane)
-          const int ch = lane >> 4;   // 0 U, 1 V
-          const int code = (int)((nzuv >> (8 * ch + 6 - 2 * k)) & 3);
-          if (code) idct_pass1(ws.coef + (16 + 4 * ch + k) * 16, lane & 15, ws.tmp + 16 * ch);
-        WARP_PHASE_END
-        WARP_PHASE(lane)
-          const int ch = lane >> 4;
-          const int code = (int)((nzuv >> (8 * ch + 6 - 2 * k)) & 3);
-          if (code) {
-            const int px = lane & 3, py = (lane >> 2) & 3;
-            uint8_t* const b = ws.uv + 32 + 4 + 16 * ch + (k >> 1) * 4 * 32 + (k & 1) * 4;
-            b[py * 32 + px] = (uint8_t)clip8i(b[py * 32 + px] + idct_pass2(ws.tmp + 16 * ch, px, py));
-          }
-        WARP_PHASE_END
+      int v[4];
+      for (int k = 0; k < 4; ++k) v[k] = pred_big_pixel(t, mode, dc, c0 + k, r);
+      if (any_coef) {
+        const int16_t* ra = ws.res + (16 + 4 * ch + (r >> 2) * 2 + (c0 >> 2)) * 16 + (r & 3) * 4;
+        for (int k = 0; k < 4; ++k) v[k] = clip8i(v[k] + ra[k]);
       }
-    }
+      for (int k = 0; k < 4; ++k) t[r * 32 + c0 + k] = (uint8_t)v[k];
+    WARP_PHASE_END
   }
 
   // ---- phase 4: tile -> HBM planes, neighbour context for the macroblocks to the right and below, MbInfo
@@ -363,9 +354,7 @@ VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, i
       cx.corner[4 * my + 0] = ws.y[19];
       cx.corner[4 * my + 1] = ws.uv[11];
       cx.corner[4 * my + 2] = ws.uv[27];
-      info[2] = nzy;
-      const uint32_t w2 = (w & 0xffff0000u) | nzuv;
-      info[3] = (is_i4 || (nzy | nzuv) != 0) ? (w2 | MBW_INNER) : (w2 & ~MBW_INNER);
+      info[3] = (is_i4 || ws.nz != 0) ? (w | MBW_INNER) : (w & ~MBW_INNER);
     }
   WARP_PHASE_END
 }
