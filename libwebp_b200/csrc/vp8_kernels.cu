@@ -34,13 +34,16 @@
 __global__ void __launch_bounds__(32) k_parse_modes(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
                                                     FrameHdr* hdrs, uint32_t* mbinfo, int first, int count) {
   extern __shared__ uint32_t top_modes[];   // mb_w words
+  __shared__ uint8_t bprob[900];            // kVp8BModeProba, out of the constant bank (indexed per decode)
   const int i = blockIdx.x;
+  for (int k = threadIdx.x; k < 900; k += 32) bprob[k] = kVp8BModeProba[k];
+  __syncthreads();
   if (i >= count || threadIdx.x != 0) return;
   const ImgDesc im = imgs[first + i];
   FrameHdr* h = &hdrs[first + i];
   BoolDec br;
   int st = parse_frame_header(br, arena + im.in_off, im, h);
-  if (st == VP8B_OK) st = parse_intra_modes(br, im, h, top_modes, mbinfo + 4 * (size_t)im.mb_base);
+  if (st == VP8B_OK) st = parse_intra_modes(br, im, h, top_modes, bprob, mbinfo + 4 * (size_t)im.mb_base);
   h->status = st;
 }
 

@@ -25,6 +25,11 @@
 #else
 #define VP8_FN static inline
 #define VP8_TABLE static const
+#ifndef VP8_EMU_VECTORS
+#define VP8_EMU_VECTORS
+struct uint2 { uint32_t x, y; };
+struct uint4 { uint32_t x, y, z, w; };
+#endif
 #define VP8_CLZ(x) __builtin_clz((unsigned)(x))
 #define VP8_BSWAP(x) __builtin_bswap32(x)
 #endif
@@ -37,11 +42,6 @@ VP8_TABLE uint16_t kBandOff[17] = { 0, 33, 66, 99, 198, 132, 165, 198, 198, 198,
 VP8_TABLE uint8_t kCatProb[4][12] = {
   { 173, 148, 140, 0 }, { 176, 155, 140, 135, 0 }, { 180, 157, 141, 134, 130, 0 },
   { 254, 254, 243, 230, 196, 177, 153, 140, 133, 130, 129, 0 }
-};
-// sub-block mode tree: node -> {next if bit 0, next if bit 1}; values <= 0 are leaves holding -mode
-VP8_TABLE int8_t kBModeTreeDev[9][2] = {
-  { -M_DC, 1 }, { -M_TM, 2 }, { -M_VE, 3 }, { 4, 6 }, { -M_HE, 5 }, { -M_RD, -M_VR }, { -M_LD, 7 },
-  { -M_VL, 8 }, { -M_HD, -M_HU }
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -285,9 +285,28 @@ VP8_FN int parse_frame_header(BoolDec& br, const uint8_t* frame, const ImgDesc& 
 
 // ---------------------------------------------------------------------------------------------------------
 // Intra modes of the whole frame (partition 0, strictly serial). `top` = mb_w words of scratch holding the
-// four bottom sub-block modes of the macroblock row above (one byte each). Writes MbInfo x,y,w.
-// Returns VP8B_OK or VP8B_NOT_ENOUGH_DATA (checked once per macroblock row, like vp8_dec.c:651-654).
-VP8_FN int parse_intra_modes(BoolDec& br, const ImgDesc& im, const FrameHdr* h, uint32_t* top, uint32_t* mbinfo /* 4 words per MB */) {
+// four bottom sub-block modes of the macroblock row above (one byte each); `bprob` = kVp8BModeProba
+// ([top mode][left mode][9]) staged in shared memory by the kernel (a pointer to the table itself elsewhere).
+// Writes MbInfo x,y,w. Returns VP8B_OK or VP8B_NOT_ENOUGH_DATA (checked once per macroblock row, like
+// vp8_dec.c:651-654). Sub-block mode tree of tree_dec.c:28-36 written out as straight-line decisions.
+VP8_FN uint32_t parse_bmode(BoolDec& d, const uint8_t* p) {
+  bd_fill(d);
+  if (!bd_bit_nofill(d, p[0])) return M_DC;
+  if (!bd_bit_nofill(d, p[1])) return M_TM;
+  if (!bd_bit_nofill(d, p[2])) return M_VE;
+  if (!bd_bit_nofill(d, p[3])) {
+    bd_fill(d);
+    if (!bd_bit_nofill(d, p[4])) return M_HE;
+    return bd_bit_nofill(d, p[5]) ? M_VR : M_RD;
+  }
+  bd_fill(d);
+  if (!bd_bit_nofill(d, p[6])) return M_LD;
+  if (!bd_bit_nofill(d, p[7])) return M_VL;
+  return bd_bit_nofill(d, p[8]) ? M_HU : M_HD;
+}
+
+VP8_FN int parse_intra_modes(BoolDec& br, const ImgDesc& im, const FrameHdr* h, uint32_t* top, const uint8_t* bprob,
+                             uint32_t* mbinfo /* 4 words per MB */) {
   const int mb_w = im.mb_w, mb_h = im.mb_h;
   const int update_map = h->update_map, use_skip = h->use_skip, skip_p = h->skip_p;
   const uint32_t sp0 = h->seg_prob[0], sp1 = h->seg_prob[1], sp2 = h->seg_prob[2];
@@ -297,13 +316,16 @@ VP8_FN int parse_intra_modes(BoolDec& br, const ImgDesc& im, const FrameHdr* h, 
     for (int mx = 0; mx < mb_w; ++mx) {
       uint32_t* out = mbinfo + 4 * ((size_t)my * mb_w + mx);
       uint32_t w = 0, m0 = 0, m1 = 0;
+      bd_fill(br);   // segment (<= 2) + skip + block size: at most 4 decodes
       if (update_map) {
-        const uint32_t seg = !bd_bit(br, sp0) ? (uint32_t)bd_bit(br, sp1) : (uint32_t)bd_bit(br, sp2) + 2u;
+        const uint32_t seg = !bd_bit_nofill(br, sp0) ? (uint32_t)bd_bit_nofill(br, sp1) : (uint32_t)bd_bit_nofill(br, sp2) + 2u;
         w |= seg << MBW_SEG_SHIFT;
       }
-      if (use_skip && bd_bit(br, skip_p)) w |= MBW_SKIP;
-      if (bd_bit(br, 145)) {   // i16
-        const uint32_t ymode = bd_bit(br, 156) ? (bd_bit(br, 128) ? M_TM : M_HE) : (bd_bit(br, 163) ? M_VE : M_DC);
+      if (use_skip && bd_bit_nofill(br, skip_p)) w |= MBW_SKIP;
+      if (bd_bit_nofill(br, 145)) {   // i16
+        bd_fill(br);
+        const uint32_t ymode = bd_bit_nofill(br, 156) ? (bd_bit_nofill(br, 128) ? M_TM : M_HE)
+                                                      : (bd_bit_nofill(br, 163) ? M_VE : M_DC);
         m0 = ymode;
         top[mx] = ymode * 0x01010101u;
         left = ymode * 0x01010101u;
@@ -314,10 +336,7 @@ VP8_FN int parse_intra_modes(BoolDec& br, const ImgDesc& im, const FrameHdr* h, 
           uint32_t ymode = (left >> (8 * y)) & 0xff;
           for (int x = 0; x < 4; ++x) {
             const uint32_t tm = (t >> (8 * x)) & 0xff;
-            const uint8_t* pr = &kVp8BModeProba[(tm * 10 + ymode) * 9];
-            int node = 0;
-            do { node = kBModeTreeDev[node][bd_bit(br, pr[node])]; } while (node > 0);
-            ymode = (uint32_t)(-node);
+            ymode = parse_bmode(br, bprob + (tm * 10 + ymode) * 9);
             t = (t & ~(0xffu << (8 * x))) | (ymode << (8 * x));
             const int n = y * 4 + x;
             if (n < 8) m0 |= ymode << (4 * n); else m1 |= ymode << (4 * (n - 8));
@@ -326,9 +345,11 @@ VP8_FN int parse_intra_modes(BoolDec& br, const ImgDesc& im, const FrameHdr* h, 
         }
         top[mx] = t;
       }
-      const uint32_t uvmode = !bd_bit(br, 142) ? M_DC : !bd_bit(br, 114) ? M_VE : bd_bit(br, 183) ? M_TM : M_HE;
+      bd_fill(br);
+      const uint32_t uvmode = !bd_bit_nofill(br, 142) ? M_DC : !bd_bit_nofill(br, 114) ? M_VE : bd_bit_nofill(br, 183) ? M_TM : M_HE;
       w |= uvmode << MBW_UVMODE_SHIFT;
-      out[0] = m0; out[1] = m1; out[2] = 0; out[3] = w;
+      uint4 o4; o4.x = m0; o4.y = m1; o4.z = 0; o4.w = w;
+      *(uint4*)out = o4;
     }
     if (bd_eof(br)) return VP8B_NOT_ENOUGH_DATA;
   }

@@ -31,8 +31,11 @@
 #define WARP_PHASE_END }
 #define VP8_PCLZ(x) __builtin_clz((unsigned)(x))
 #define VP8_UNROLL
+#ifndef VP8_EMU_VECTORS
+#define VP8_EMU_VECTORS
 struct uint2 { uint32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
+#endif
 #endif
 
 VP8_PFN int clip8i(int v) { return v < 0 ? 0 : v > 255 ? 255 : v; }

@@ -58,7 +58,7 @@ extern "C" int emu_decode(const uint8_t* data, size_t size, int csp, int flags, 
     BoolDec br;
     std::vector<uint32_t> top(mb_w);
     hdr.status = parse_frame_header(br, frame, im, &hdr);
-    if (hdr.status == VP8B_OK) hdr.status = parse_intra_modes(br, im, &hdr, top.data(), mbinfo.data());
+    if (hdr.status == VP8B_OK) hdr.status = parse_intra_modes(br, im, &hdr, top.data(), kVp8BModeProba, mbinfo.data());
   }
   if (hdr.status != VP8B_OK) return hdr.status;
   if (hdr.num_parts != im.num_parts) return -100;   // host pre-scan disagrees with the device parse
