@@ -103,6 +103,27 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def host_memory_budget():
+    """Bytes of host memory this job may still take: min(MemAvailable, cgroup limit - usage)."""
+    avail = None
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                avail = int(ln.split()[1]) * 1024
+    except OSError:
+        pass
+    for lim_f, use_f in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                         ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            lim = open(lim_f).read().strip()
+            if lim != "max":
+                room = int(lim) - int(open(use_f).read().strip())
+                avail = room if avail is None else min(avail, room)
+        except (OSError, ValueError):
+            pass
+    return avail
+
+
 def cpu_baseline(datas, csp_ref, seconds, threads):
     """Reference WebPDecode, one image per thread on `threads` host threads, bounded sample (oracle/_ref)."""
     from oracle import refwebp as R
@@ -227,7 +248,17 @@ def main():
     e2e_steps = args.steps if args.e2e_steps < 0 else args.e2e_steps
     e2e = None
     if e2e_steps > 0:
-        hb = W.Batch(datas, csp, device=device, output=W.WEBP_BATCH_HOST, pinned=True)
+        # page-locked input + output buffers of every rank must fit the host: shrink the e2e batch if they would not
+        e2e_n = batch_n
+        per_img = 4 * w * h + file_bytes // batch_n + 1024
+        room = host_memory_budget()
+        if room is not None:
+            fit = int(0.5 * room / world / per_img)
+            if fit < e2e_n:
+                e2e_n = max(distinct, fit // distinct * distinct)
+        e2e_datas = datas[:e2e_n]
+        e2e_mpix = e2e_n * w * h * 1e-6
+        hb = W.Batch(e2e_datas, csp, device=device, output=W.WEBP_BATCH_HOST, pinned=True)
         if hb.decode_oneshot() != 0:     # warm-up (also faults the pinned pages in)
             raise SystemExit(f"WebPDecodeBatch failed: {W.last_error()}")
         barrier()
@@ -239,12 +270,13 @@ def main():
         e2e_ms_step = reduce_max((time.perf_counter() - t1) * 1e3 / e2e_steps)
         # spot-check the bytes that came back against the reference (not timed)
         ok = True
-        for i in (0, batch_n // 2, batch_n - 1):
-            s_ref, want = R.decode(datas[i], getattr(R, "MODE_" + cspname), 0)
+        for i in (0, e2e_n // 2, e2e_n - 1):
+            s_ref, want = R.decode(e2e_datas[i], getattr(R, "MODE_" + cspname), 0)
             ok &= bool(s_ref == 0 and np.array_equal(hb.host_output(i), want))
-        e2e = {"value": round(mpix * world / (e2e_ms_step * 1e-3), 1), "unit": UNIT, "h2d_bytes_per_step": hb.h2d_bytes,
+        e2e = {"value": round(e2e_mpix * world / (e2e_ms_step * 1e-3), 1), "unit": UNIT, "h2d_bytes_per_step": hb.h2d_bytes,
                "d2h_bytes_per_step": hb.d2h_bytes, "ms_per_step": round(e2e_ms_step, 3), "steps": e2e_steps,
-               "bit_exact_spot_check": ok}
+               "batch_per_gpu": e2e_n, "bit_exact_spot_check": ok,
+               "api": "WebPDecodeBatch(host buffers in, host buffers out), pinned memory"}
         hb.close()
 
     if rank != 0:
@@ -273,6 +305,14 @@ def main():
                         "share": round(per[k] / max(sum(per.values()), 1e-9), 3)} for k in per}
     dom = max(per, key=per.get)
     achieved = alg[dom] / (per[dom] * 1e-3) / 1e9
+    # DRAM traffic of the dominant kernel from the committed ncu capture of this workload (per launch), if one exists
+    traffic, traffic_src = None, None
+    try:
+        for t in json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))):
+            if t["kernel"] == "k_" + dom[:-3] and t["workload"] == args.workload and t["batch"] == batch_n:
+                traffic, traffic_src = t["dram_bytes"], t["source"]
+    except (OSError, ValueError, KeyError):
+        pass
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     bits_per_cycle_sm = (file_bytes * 8) / (per["tokens_ms"] * 1e-3 * sm_mhz * 1e6 * 148) if per["tokens_ms"] > 0 else None
     step_bytes = file_bytes + 4.0 * px
@@ -287,7 +327,8 @@ def main():
                    "corpus_seconds": round(t_corpus, 1)},
         "e2e": e2e, "gpu_launches": launches,
         "roofline": {"kernel": "k_" + dom[:-3], "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
-                     "frac": round(achieved / hbm_peak, 5), "traffic": None, "peak_source": peak_src,
+                     "frac": round(achieved / hbm_peak, 5), "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_bytes": int(alg[dom]), "peak_source": peak_src,
                      "note": "serial boolean decoding: latency/issue-bound, not HBM-bound; see parse_bits_per_cycle_per_sm"},
         "roofline_step": {"bound": "hbm", "achieved": round(step_bytes / (dev_ms_step * 1e-3) / 1e9, 1), "peak": hbm_peak,
                           "unit": "GB/s", "frac": round(step_bytes / (dev_ms_step * 1e-3) / 1e9 / hbm_peak, 4),

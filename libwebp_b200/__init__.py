@@ -339,6 +339,21 @@ class Batch:
         self.in_buf = self.out_buf = None
 
 
+def shard_indices(n_items, rank, world):
+    """Items of a batch that rank `rank` of `world` decodes: i % world == rank (images are independent, so the
+    batch shards by index with no exchange). Every index belongs to exactly one rank."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    return list(range(rank, n_items, world))
+
+
+def decode_batch_sharded(datas, rank, world, csp=MODE_RGBA, device=-1, **kw):
+    """This rank's share of `datas` through WebPDecodeBatch -> (indices, statuses, outputs)."""
+    idx = shard_indices(len(datas), rank, world)
+    sts, outs = decode_batch([datas[i] for i in idx], csp, device=device, **kw) if idx else ([], [])
+    return idx, sts, outs
+
+
 def decode_batch(datas, csp=MODE_RGBA, bypass_filtering=False, no_fancy_upsampling=False, device=-1, pinned=True):
     """WebPDecodeBatch over a list of files -> (statuses, [ndarray or None])."""
     b = Batch(datas, csp, bypass_filtering, no_fancy_upsampling, device, WEBP_BATCH_HOST, pinned)
