@@ -17,6 +17,7 @@
 
 #include "vp8_container.h"
 #include "vp8_kernels.h"
+#include "vp8l_alpha_core.h"   // AlphaHdr, AlGroup and the sizing macros only: nothing of it runs on the host
 #include "webp/decode_batch.h"
 
 // ---------------------------------------------------------------------------------------------------------
@@ -234,6 +235,12 @@ struct WebPBatch {
   std::vector<int> ids;            // token-parse launch lists
   std::vector<int> statuses;       // host copy of FrameHdr::status
   Owned d_in, d_imgs, d_hdrs, d_ids, d_mbinfo, d_coeffs, d_yuv, d_out;
+  // images with an ALPH chunk
+  std::vector<int> aimgs;              // their image indices
+  std::vector<AlphaPlan> aplans;
+  std::vector<AlphaHdr> ahdrs;         // host copy after the header pass / after the decode
+  Owned d_aimgs, d_aplans, d_ahdrs, d_awork, d_awork2, d_alpha;
+  bool alpha_planned = false;          // work areas sized from the headers (kept across repeated decodes)
   size_t out_total = 0;
   int max_mb_w = 1, max_mb_h = 1;
   std::vector<cudaEvent_t> ev;     // pool of timing / hand-off events, grown on demand
@@ -258,7 +265,7 @@ static VP8StatusCode plan_item(WebPBatchItem* it, const WebPBatchOptions& opt, V
   if (st != VP8_STATUS_OK) return st;
   if (c->has_animation) return VP8_STATUS_UNSUPPORTED_FEATURE;             // webp_dec.c:427-429
   if (c->is_lossless) return VP8_STATUS_UNSUPPORTED_FEATURE;               // lossless: not on this path
-  if (c->has_alph_chunk) return VP8_STATUS_UNSUPPORTED_FEATURE;            // ALPH plane: next
+  if (c->has_alph_chunk && cfg->options.alpha_dithering_strength > 0) return VP8_STATUS_UNSUPPORTED_FEATURE;   // alpha de-banding
   if (c->part0_size > c->frame_size - 10) return VP8_STATUS_NOT_ENOUGH_DATA;   // vp8_dec.c:345-348
   const WebPDecoderOptions* o = &cfg->options;
   if (o->use_cropping || o->use_scaling || o->flip) return VP8_STATUS_UNSUPPORTED_FEATURE;
@@ -333,6 +340,13 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
     const int ds = cfg->options.dithering_strength;
     d.dither_f = (uint8_t)(ds < 0 ? 0 : ds > 100 ? 255 : ds * 255 / 100);
     d.num_parts = (uint8_t)vp8b_prescan_partitions(b->items[i].data + c.frame_offset + 10, c.part0_size);
+    d.alpha_plane = VP8B_NO_ALPHA;
+    if (c.has_alph_chunk) {
+      d.alpha_in = ranges[item_range[i]].dev_off + (size_t)(b->items[i].data - ranges[item_range[i]].base) + c.alpha_offset;
+      d.alpha_size = (uint32_t)c.alpha_size;
+      d.alpha_index = (uint32_t)b->aimgs.size();
+      b->aimgs.push_back((int)b->imgs.size());
+    }
     size_t bytes;
     if (d.csp == MODE_YUV) {
       d.out_stride = c.width;
@@ -433,6 +447,7 @@ static void batch_release(WebPBatch* b) {
     DeviceCtx* c = b->ctx;
     own_free(c, b->d_in); own_free(c, b->d_imgs); own_free(c, b->d_hdrs); own_free(c, b->d_ids);
     own_free(c, b->d_mbinfo); own_free(c, b->d_coeffs); own_free(c, b->d_yuv); own_free(c, b->d_out);
+    own_free(c, b->d_aimgs); own_free(c, b->d_aplans); own_free(c, b->d_ahdrs); own_free(c, b->d_awork); own_free(c, b->d_awork2); own_free(c, b->d_alpha);
     for (auto e : b->ev) if (e) cudaEventDestroy(e);
   }
   delete b;
@@ -545,6 +560,71 @@ static int ev_mark(WebPBatch* b, cudaStream_t s) {   // records the next pooled 
   return (int)b->ev_used++;
 }
 
+// ALPH chunks of the batch: header pass, host-side sizing of the work areas (first decode only), then the pixel
+// pass + unfilter, all queued on the compute stream ahead of the VP8 kernels. Leaves every image's w x h alpha
+// plane in d_alpha; k_emit picks it up through ImgDesc::alpha_plane.
+static bool batch_alpha(WebPBatch* b) {
+  DeviceCtx* ctx = b->ctx;
+  const int na = (int)b->aimgs.size();
+  if (na == 0) return true;
+  cudaStream_t s = ctx->stream;
+  const uint8_t* arena = (const uint8_t*)b->d_in.p;
+  if (!b->alpha_planned) {
+    b->aplans.assign(na, AlphaPlan());
+    b->ahdrs.resize(na);
+    size_t work1 = 0;
+    for (int a = 0; a < na; ++a) {
+      const ImgDesc& d = b->imgs[b->aimgs[a]];
+      b->aplans[a].scratch = work1; work1 += align_up(AL_SCRATCH_BYTES, 256);
+      b->aplans[a].meta = work1; work1 += align_up(4 * (size_t)AL_META_PIXELS_BOUND(d.width, d.height) + 16, 256);
+      b->aplans[a].tdata = work1; work1 += align_up(8 * (size_t)AL_META_PIXELS_BOUND(d.width, d.height) + 16, 256);
+    }
+    if (!own_alloc(ctx, b->d_aimgs, sizeof(int) * na) || !own_alloc(ctx, b->d_aplans, sizeof(AlphaPlan) * na) ||
+        !own_alloc(ctx, b->d_ahdrs, sizeof(AlphaHdr) * na) || !own_alloc(ctx, b->d_awork, work1)) return false;
+    for (int a = 0; a < na; ++a) {
+      b->aplans[a].scratch += (uint64_t)(uintptr_t)b->d_awork.p;
+      b->aplans[a].meta += (uint64_t)(uintptr_t)b->d_awork.p;
+      b->aplans[a].tdata += (uint64_t)(uintptr_t)b->d_awork.p;
+    }
+    CU_TRY(cudaMemcpyAsync(b->d_aimgs.p, b->aimgs.data(), sizeof(int) * na, cudaMemcpyHostToDevice, s), "H2D alpha image list");
+    CU_TRY(cudaMemcpyAsync(b->d_aplans.p, b->aplans.data(), sizeof(AlphaPlan) * na, cudaMemcpyHostToDevice, s), "H2D alpha plans");
+  }
+  vp8k_alpha_header(s, arena, (const ImgDesc*)b->d_imgs.p, (const int*)b->d_aimgs.p, (const AlphaPlan*)b->d_aplans.p,
+                    (AlphaHdr*)b->d_ahdrs.p, na);
+  if (!b->alpha_planned) {
+    CU_TRY(cudaMemcpyAsync(b->ahdrs.data(), b->d_ahdrs.p, sizeof(AlphaHdr) * na, cudaMemcpyDeviceToHost, s), "D2H alpha headers");
+    CU_TRY(cudaStreamSynchronize(s), "alpha header pass");
+    size_t work2 = 0, planes = 0;
+    std::vector<size_t> tab(na, 0), grp(na, 0), cod(na, 0);
+    for (int a = 0; a < na; ++a) {
+      const AlphaHdr& h = b->ahdrs[a];
+      ImgDesc& d = b->imgs[b->aimgs[a]];
+      if (h.status != AL_OK) continue;
+      if (h.method == 1) {
+        tab[a] = work2; work2 += align_up((size_t)h.num_groups * (size_t)h.group_entries * 4, 256);
+        grp[a] = work2; work2 += align_up((size_t)h.num_groups * sizeof(AlGroup), 256);
+        cod[a] = work2; work2 += align_up(4 * ((size_t)h.xsize * d.height + 4), 256);
+      }
+      d.alpha_plane = planes;
+      planes += align_up((size_t)d.width * d.height, 256);
+    }
+    Owned w2;
+    if (!own_alloc(ctx, w2, work2 + 256) || !own_alloc(ctx, b->d_alpha, planes + 256)) { own_free(ctx, w2); return false; }
+    b->d_awork2 = w2;   // lives as long as the batch
+    for (int a = 0; a < na; ++a) {
+      const uint64_t base = (uint64_t)(uintptr_t)b->d_awork2.p;
+      b->aplans[a].tables = base + tab[a]; b->aplans[a].groups = base + grp[a]; b->aplans[a].coded = base + cod[a];
+    }
+    CU_TRY(cudaMemcpyAsync(b->d_aplans.p, b->aplans.data(), sizeof(AlphaPlan) * na, cudaMemcpyHostToDevice, s), "H2D alpha plans");
+    CU_TRY(cudaMemcpyAsync(b->d_imgs.p, b->imgs.data(), sizeof(ImgDesc) * b->imgs.size(), cudaMemcpyHostToDevice, s), "H2D descriptors");
+    b->alpha_planned = true;
+  }
+  vp8k_alpha_decode(s, arena, (const ImgDesc*)b->d_imgs.p, (const int*)b->d_aimgs.p, (const AlphaPlan*)b->d_aplans.p,
+                    (AlphaHdr*)b->d_ahdrs.p, (uint8_t*)b->d_alpha.p, na);
+  CU_TRY(cudaMemcpyAsync(b->ahdrs.data(), b->d_ahdrs.p, sizeof(AlphaHdr) * na, cudaMemcpyDeviceToHost, s), "D2H alpha status");
+  return true;
+}
+
 // Runs the kernels on the device's compute stream. The two parse kernels take a whole wave at a time (the
 // serial entropy decode needs every stream it can get in flight); the pixel stages then walk the wave in
 // chunks, and with `download` (one-shot host-output path) each chunk's pixels start their way back on the copy
@@ -569,6 +649,7 @@ static bool batch_decode(WebPBatch* b, bool download) {
   size_t chunk_bytes = (size_t)2 << 30;
   { const char* e = getenv("WEBP_B200_CHUNK_MB"); if (e != NULL && atoi(e) > 0) chunk_bytes = (size_t)atoi(e) << 20; }
 #define MARK(var) const int var = ev_mark(b, s); if (var < 0) return false
+  if (!batch_alpha(b)) return false;
   for (const Wave& w : b->waves) {
     MARK(e0);
     vp8k_parse_modes(s, arena, imgs, hdrs, mbinfo, w.first, w.count, w.max_mb_w);
@@ -596,7 +677,7 @@ static bool batch_decode(WebPBatch* b, bool download) {
       MARK(e3);
       vp8k_loop_filter(s, imgs, hdrs, mbinfo, yuv, c0, cnt);
       MARK(e4);
-      vp8k_emit(s, imgs, hdrs, yuv, (uint8_t*)b->d_out.p, c0, cnt, w.max_units);
+      vp8k_emit(s, imgs, hdrs, yuv, (const uint8_t*)b->d_alpha.p, (uint8_t*)b->d_out.p, c0, cnt, w.max_units);
       MARK(e5);
       launches += 3;
       b->spans.push_back({ ST_RECON, prev, e3 });
@@ -630,6 +711,8 @@ static bool batch_decode(WebPBatch* b, bool download) {
   for (int k = 0; k < m; ++k) {
     WebPBatchItem* it = &b->items[b->img_item[k]];
     it->status = (VP8StatusCode)b->statuses[k];
+    // a lost alpha plane loses the image (frame_dec.c:452-460), unless the VP8 stream had already failed
+    if (it->status == VP8_STATUS_OK && b->imgs[k].alpha_size != 0) it->status = (VP8StatusCode)b->ahdrs[b->imgs[k].alpha_index].status;
     if (it->status != VP8_STATUS_OK && b->opt.output == WEBP_BATCH_HOST) WebPFreeDecBuffer(&it->config->output);
   }
   b->decoded = true;

@@ -10,6 +10,8 @@
 //                   dequantisation + zigzag scatter happen in the reconstruction kernel      (800 B / macroblock)
 //   yuv[M*384]    : per image Y (16mb_w x 16mb_h) | U | V, macroblock-padded planes     (1.5 B / pixel)
 //   output arena  : RGBA/RGB/... or Y|U|V per image, tight strides
+//   alpha arena   : images with an ALPH chunk only: AlphaHdr, lookup tables, coded bytes, w x h alpha plane
+//                   (vp8l_alpha_core.h)
 #ifndef LIBWEBP_B200_VP8_DEV_H_
 #define LIBWEBP_B200_VP8_DEV_H_
 
@@ -40,7 +42,13 @@ typedef struct ImgDesc {
   uint8_t flags;
   uint8_t num_parts;   // host pre-scan of the partition count (launch geometry only; FrameHdr is authoritative)
   uint8_t dither_f;    // options.dithering_strength mapped to 0..255 (0 = off), see parse_frame_header
+  uint64_t alpha_in;   // byte offset of the ALPH chunk payload inside the input arena (alpha_size == 0: no alpha)
+  uint64_t alpha_plane;// byte offset of this image's decoded w x h alpha plane inside the alpha arena (host fills it
+                       // after the alpha header pass); VP8B_NO_ALPHA when the image has none
+  uint32_t alpha_size; // ALPH payload bytes
+  uint32_t alpha_index;// index among the batch's alpha images
 } ImgDesc;
+#define VP8B_NO_ALPHA 0xffffffffffffffffull
 
 typedef struct FrameHdr {
   int32_t status;               // VP8B_OK or the failure of the header / mode parse; token parse may overwrite

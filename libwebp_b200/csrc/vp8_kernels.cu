@@ -29,6 +29,8 @@
 #include "vp8_parse_core.h"
 #include "vp8_pixel_core.h"
 #include "vp8_tokens_fsm.h"
+#define AL_BLOCK_SYNC() __syncthreads()
+#include "vp8l_alpha_core.h"
 
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) k_parse_modes(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
@@ -284,8 +286,8 @@ __global__ void __launch_bounds__(32 * FILTER_WARPS) k_loop_filter(const ImgDesc
 #define EMIT_THREADS 256
 
 __global__ void __launch_bounds__(EMIT_THREADS) k_emit(const ImgDesc* __restrict__ imgs, const FrameHdr* __restrict__ hdrs,
-                                                       const uint8_t* __restrict__ yuv, uint8_t* out, int first,
-                                                       int blocks_per_image) {
+                                                       const uint8_t* __restrict__ yuv, const uint8_t* __restrict__ alpha_arena,
+                                                       uint8_t* out, int first, int blocks_per_image) {
   const int img = first + blockIdx.x / blocks_per_image;
   const int chunk = blockIdx.x % blocks_per_image;
   if (hdrs[img].status != VP8B_OK) return;
@@ -295,6 +297,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(const ImgDesc* __restrict
   const uint8_t* up = yp + nmb * 256;
   const uint8_t* vp = up + nmb * 64;
   uint8_t* o = out + im.out_off;
+  const uint8_t* alpha = (im.alpha_plane != VP8B_NO_ALPHA) ? alpha_arena + im.alpha_plane : nullptr;
   const int t = chunk * EMIT_THREADS + threadIdx.x;
   if (im.csp == 11) {   // MODE_YUV: 16-byte chunks of Y rows, then U rows, then V rows
     const int w = im.width, h = im.height, uvw = (w + 1) >> 1, uvh = (h + 1) >> 1;
@@ -305,10 +308,10 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(const ImgDesc* __restrict
     else if (t < ny + 2 * nuv) emit_yuv_chunk(im, yp, up, vp, o, 2, (t - ny - nuv) % quv, (t - ny - nuv) / quv);
   } else if (emit_uses_pairs(im.csp, im.flags)) {   // 8 pixels x 2 rows per thread
     const int qw = (im.width + 7) >> 3;
-    if (t < qw * ((im.height >> 1) + 1)) emit_rgba_pair8(im, yp, up, vp, o, t % qw, t / qw);
+    if (t < qw * ((im.height >> 1) + 1)) emit_rgba_pair8(im, yp, up, vp, alpha, o, t % qw, t / qw);
   } else {
     const int qw = (im.width + 3) >> 2;
-    if (t < qw * im.height) emit_rgb_quad(im, yp, up, vp, o, t % qw, t / qw);
+    if (t < qw * im.height) emit_rgb_quad(im, yp, up, vp, alpha, o, t % qw, t / qw);
   }
 }
 
@@ -395,8 +398,59 @@ extern "C" void vp8k_loop_filter(cudaStream_t s, const ImgDesc* imgs, const Fram
   k_loop_filter<<<count, 32 * FILTER_WARPS, 0, s>>>(imgs, hdrs, mbinfo, yuv, first);
 }
 
-extern "C" void vp8k_emit(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint8_t* yuv, uint8_t* out, int first,
-                          int count, int max_units) {
+extern "C" void vp8k_emit(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint8_t* yuv, const uint8_t* alpha_arena,
+                          uint8_t* out, int first, int count, int max_units) {
   const int bpi = (max_units + EMIT_THREADS - 1) / EMIT_THREADS;
-  k_emit<<<(unsigned)count * (unsigned)bpi, EMIT_THREADS, 0, s>>>(imgs, hdrs, yuv, out, first, bpi);
+  k_emit<<<(unsigned)count * (unsigned)bpi, EMIT_THREADS, 0, s>>>(imgs, hdrs, yuv, alpha_arena, out, first, bpi);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ALPH chunks (vp8l_alpha_core.h). `aimgs` = indices of the images that carry one. Work areas are byte offsets
+// into `work` (host-planned, AlphaPlan).
+__global__ void __launch_bounds__(32) k_alpha_header(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
+                                                     const int* __restrict__ aimgs, const AlphaPlan* __restrict__ plans,
+                                                     AlphaHdr* ahdrs) {
+  if (threadIdx.x != 0) return;
+  const int a = blockIdx.x;
+  const ImgDesc im = imgs[aimgs[a]];
+  const AlphaPlan pl = plans[a];
+  alph_parse_header(arena + im.alpha_in, im.alpha_size, im.width, im.height, (uint8_t*)pl.scratch, (uint16_t*)pl.meta,
+                    (uint32_t*)pl.tdata, &ahdrs[a]);
+}
+
+__global__ void __launch_bounds__(32) k_alpha_pixels(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
+                                                     const int* __restrict__ aimgs, const AlphaPlan* __restrict__ plans,
+                                                     AlphaHdr* ahdrs) {
+  if (threadIdx.x != 0) return;
+  const int a = blockIdx.x;
+  AlphaHdr* hd = &ahdrs[a];
+  if (hd->status != AL_OK || hd->method == 0) return;
+  const ImgDesc im = imgs[aimgs[a]];
+  const AlphaPlan pl = plans[a];
+  hd->status = alph_decode_pixels(arena + im.alpha_in, im.alpha_size, im.height, hd, (const uint16_t*)pl.meta,
+                                  (uint32_t*)pl.tables, (AlGroup*)pl.groups, (uint8_t*)pl.scratch, (uint32_t*)pl.coded);
+}
+
+#define ALPHA_FINISH_THREADS 1024
+__global__ void __launch_bounds__(ALPHA_FINISH_THREADS) k_alpha_finish(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
+                                                                       const int* __restrict__ aimgs, const AlphaPlan* __restrict__ plans,
+                                                                       const AlphaHdr* __restrict__ ahdrs, uint8_t* alpha_arena) {
+  const int a = blockIdx.x;
+  const AlphaHdr* hd = &ahdrs[a];
+  if (hd->status != AL_OK) return;
+  const ImgDesc im = imgs[aimgs[a]];
+  const AlphaPlan pl = plans[a];
+  if (im.alpha_plane == VP8B_NO_ALPHA) return;
+  alph_finish(hd, arena + im.alpha_in + 1, (uint32_t*)pl.coded, (const uint32_t*)pl.tdata, im.width, im.height,
+              alpha_arena + im.alpha_plane, (int)threadIdx.x, (int)blockDim.x);
+}
+
+extern "C" void vp8k_alpha_header(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, const int* aimgs, const AlphaPlan* plans,
+                                  AlphaHdr* ahdrs, int count) {
+  k_alpha_header<<<count, 32, 0, s>>>(arena, imgs, aimgs, plans, ahdrs);
+}
+extern "C" void vp8k_alpha_decode(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, const int* aimgs, const AlphaPlan* plans,
+                                  AlphaHdr* ahdrs, uint8_t* alpha_arena, int count) {
+  k_alpha_pixels<<<count, 32, 0, s>>>(arena, imgs, aimgs, plans, ahdrs);
+  k_alpha_finish<<<count, ALPHA_FINISH_THREADS, 0, s>>>(arena, imgs, aimgs, plans, ahdrs, alpha_arena);
 }

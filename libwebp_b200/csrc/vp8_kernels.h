@@ -24,8 +24,26 @@ void vp8k_reconstruct(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs,
 void vp8k_loop_filter(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint32_t* mbinfo, uint8_t* yuv,
                       int first, int count);
 // max_units = largest per-image work-item count (RGB: ceil(w/4)*h; YUV: 16-byte chunks of the three planes).
-void vp8k_emit(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint8_t* yuv, uint8_t* out, int first,
-               int count, int max_units);
+void vp8k_emit(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint8_t* yuv, const uint8_t* alpha_arena,
+               uint8_t* out, int first, int count, int max_units);
+
+// ALPH chunks (vp8l_alpha_core.h): `aimgs` = the `count` image indices that carry one, `plans` = where each of them
+// works (device addresses). Header pass first; the host then sizes tables / planes from the AlphaHdr it
+// reads back, fills the rest of the plans and ImgDesc::alpha_plane, and runs the decode (pixels + unfilter).
+struct AlphaHdr;
+typedef struct AlphaPlan {
+  uint64_t scratch;   // AL_SCRATCH_BYTES: sub-image tables, colour cache, palette, AlScratch
+  uint64_t meta;      // 4 bytes per meta-Huffman pixel (upper bound)
+  uint64_t tdata;     // tile images of the predictor / cross-colour transforms (upper bound)
+  uint64_t tables;    // num_groups * group_entries words                 (after the header pass)
+  uint64_t groups;    // num_groups AlGroup                               (after the header pass)
+  uint64_t coded;     // xsize * height ARGB words                        (after the header pass)
+} AlphaPlan;
+void vp8k_alpha_header(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, const int* aimgs, const AlphaPlan* plans,
+                       struct AlphaHdr* ahdrs, int count);
+void vp8k_alpha_decode(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, const int* aimgs, const AlphaPlan* plans,
+                       struct AlphaHdr* ahdrs, uint8_t* alpha_arena, int count);
+
 
 #ifdef __cplusplus
 }

@@ -519,17 +519,23 @@ VP8_PFN int fancy_chroma(const uint8_t* near, const uint8_t* far, int i, int w) 
   return (i & 1) ? ((((avg + 2 * (nr + fl)) >> 3) + nl) >> 1) : ((((avg + 2 * (nl + fr)) >> 3) + nr) >> 1);
 }
 
-VP8_PFN uint32_t pack_pixel4(int csp, int r, int g, int b) {   // little-endian byte order in memory
+// a = the pixel's alpha (0xff for opaque images). Premultiplied modes scale the colour by alpha exactly like
+// ApplyAlphaMultiply_C (alpha_processing.c:214-241): untouched when a == 0xff, else (c * a * 32897) >> 23.
+VP8_PFN uint32_t pack_pixel4(int csp, int r, int g, int b, int a) {   // little-endian byte order in memory
+  if (csp >= 7 && a != 0xff) {
+    const uint32_t m = (uint32_t)a * 32897u;
+    r = (int)(((uint32_t)r * m) >> 23); g = (int)(((uint32_t)g * m) >> 23); b = (int)(((uint32_t)b * m) >> 23);
+  }
   switch (csp) {
-    case 1: case 7: return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16) | 0xff000000u;   // RGBA / rgbA
-    case 3: case 8: return (uint32_t)b | ((uint32_t)g << 8) | ((uint32_t)r << 16) | 0xff000000u;   // BGRA / bgrA
-    default: return 0xffu | ((uint32_t)r << 8) | ((uint32_t)g << 16) | ((uint32_t)b << 24);         // ARGB / Argb
+    case 1: case 7: return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16) | ((uint32_t)a << 24);   // RGBA / rgbA
+    case 3: case 8: return (uint32_t)b | ((uint32_t)g << 8) | ((uint32_t)r << 16) | ((uint32_t)a << 24);   // BGRA / bgrA
+    default: return (uint32_t)a | ((uint32_t)r << 8) | ((uint32_t)g << 16) | ((uint32_t)b << 24);           // ARGB / Argb
   }
 }
 
 // Pixels 4*q .. 4*q+3 of output row j of image `im`. yuv = the image's padded planes.
 VP8_PFN void emit_rgb_quad(const ImgDesc& im, const uint8_t* yplane, const uint8_t* uplane, const uint8_t* vplane,
-                           uint8_t* out, int q, int j) {
+                           const uint8_t* alpha /* w x h plane or NULL */, uint8_t* out, int q, int j) {
   const int w = im.width, h = im.height;
   const int ys = 16 * im.mb_w, uvs = 8 * im.mb_w;
   const int uvh = (h + 1) >> 1;
@@ -555,7 +561,7 @@ VP8_PFN void emit_rgb_quad(const ImgDesc& im, const uint8_t* yplane, const uint8
     else { u = un[i >> 1]; v = vn[i >> 1]; }
     yuv_to_rgb(yrow[i], u, v, &r, &g, &b);
     if (bpp == 4) {
-      px[k] = pack_pixel4(csp, r, g, b);
+      px[k] = pack_pixel4(csp, r, g, b, alpha ? (int)alpha[(size_t)j * w + i] : 0xff);
     } else {
       uint8_t* o = orow + 3 * i;
       if (csp == 0) { o[0] = (uint8_t)r; o[1] = (uint8_t)g; o[2] = (uint8_t)b; }
@@ -587,12 +593,12 @@ VP8_PFN int sat_u8(int v) { int r; asm("cvt.sat.u8.s32 %0, %1;" : "=r"(r) : "r"(
 VP8_PFN int sat_u8(int v) { return v < 0 ? 0 : v > 255 ? 255 : v; }
 #endif
 
-VP8_PFN uint32_t yuv_to_px4(int csp, int y, int u, int v) {
+VP8_PFN uint32_t yuv_to_px4(int csp, int y, int u, int v, int a) {
   const int yy = (y * 19077) >> 8;
   const int r = sat_u8((yy + ((v * 26149) >> 8) - 14234) >> 6);
   const int g = sat_u8((yy - ((u * 6419) >> 8) - ((v * 13320) >> 8) + 8708) >> 6);
   const int b = sat_u8((yy + ((u * 33050) >> 8) - 17685) >> 6);
-  return pack_pixel4(csp, r, g, b);
+  return pack_pixel4(csp, r, g, b, a);
 }
 
 // Six chroma samples of plane row `row` for output pixels 8q..8q+7: columns 4q-1 .. 4q+4, clamped to [0, uvw).
@@ -626,7 +632,7 @@ VP8_PFN int emit_uses_pairs(int csp, int flags) {
 
 // Pixels 8q..8q+7 of output rows 2t-1 and 2t.
 VP8_PFN void emit_rgba_pair8(const ImgDesc& im, const uint8_t* yplane, const uint8_t* uplane, const uint8_t* vplane,
-                             uint8_t* out, int q, int t) {
+                             const uint8_t* alpha /* w x h plane or NULL */, uint8_t* out, int q, int t) {
   const int w = im.width, h = im.height;
   const int ys = 16 * im.mb_w, uvs = 8 * im.mb_w;
   const int uvw = (w + 1) >> 1, uvh = (h + 1) >> 1;
@@ -651,7 +657,8 @@ VP8_UNROLL
 VP8_UNROLL
     for (int k = 0; k < 8; ++k) {
       const int y = (int)(((k < 4 ? yw.x : yw.y) >> (8 * (k & 3))) & 0xff);
-      px[k] = yuv_to_px4(csp, y, u8[k], v8[k]);
+      const int a = (alpha != 0 && k < n) ? (int)alpha[(size_t)j * w + i0 + k] : 0xff;
+      px[k] = yuv_to_px4(csp, y, u8[k], v8[k], a);
     }
     uint8_t* o = out + (size_t)j * im.out_stride + 4 * (size_t)i0;
     if (n == 8 && (((uintptr_t)o) & 15) == 0) {

@@ -33,6 +33,17 @@ def manifest():
 
 
 @pytest.fixture(scope="session")
+def amanifest():
+    """Fixtures with an ALPH chunk (reference-produced hashes, tests/golden/make_golden.py)."""
+    with open(os.path.join(GOLDEN, "manifest_alpha.json")) as f:
+        m = json.load(f)
+    for e in m:
+        with open(os.path.join(GOLDEN, e["file"]), "rb") as f:
+            e["data"] = f.read()
+    return m
+
+
+@pytest.fixture(scope="session")
 def port():
     """The plain-C oracle (oracle/vp8_oracle.c); compiled on demand with gcc."""
     from oracle import portwebp

@@ -17,6 +17,7 @@
 #include "vp8_parse_core.h"
 #include "vp8_pixel_core.h"
 #include "vp8_tokens_fsm.h"
+#include "vp8l_alpha_core.h"
 
 // variant bit 0: visit the macroblocks of a wavefront step in reverse order
 // variant bit 1: token parse with the row-at-a-time reference port (parse_token_row) instead of the lane FSM
@@ -27,7 +28,7 @@ extern "C" int emu_decode(const uint8_t* data, size_t size, int csp, int flags, 
   Vp8Container c;
   int st = vp8b_parse_container(data, size, 1, &c);
   if (st != VP8_STATUS_OK) return st;
-  if (c.has_animation || c.is_lossless || c.has_alph_chunk) return VP8_STATUS_UNSUPPORTED_FEATURE;
+  if (c.has_animation || c.is_lossless) return VP8_STATUS_UNSUPPORTED_FEATURE;
   if (c.part0_size > c.frame_size - 10) return VP8_STATUS_NOT_ENOUGH_DATA;
 
   // input arena with padding on both sides, like the device arena
@@ -162,6 +163,32 @@ extern "C" int emu_decode(const uint8_t* data, size_t size, int csp, int flags, 
     }
   }
 
+  // K6: ALPH chunk (header pass, pixel pass, inverse transforms + unfilter on one emulated thread)
+  std::vector<uint8_t> alpha_plane;
+  const uint8_t* alpha = nullptr;
+  if (c.has_alph_chunk) {
+    const uint8_t* alph = data + c.alpha_offset;
+    const uint32_t alph_size = (uint32_t)c.alpha_size;
+    std::vector<uint8_t> scratch(AL_SCRATCH_BYTES + 64);
+    uint8_t* sc16 = (uint8_t*)(((uintptr_t)scratch.data() + 15) & ~(uintptr_t)15);
+    std::vector<uint32_t> meta(AL_META_PIXELS_BOUND(im.width, im.height) + 8);
+    std::vector<uint32_t> tdata(2 * (size_t)AL_META_PIXELS_BOUND(im.width, im.height) + 8);
+    AlphaHdr ah;
+    alph_parse_header(alph, alph_size, im.width, im.height, sc16, (uint16_t*)meta.data(), tdata.data(), &ah);
+    std::vector<uint32_t> coded;
+    if (ah.status == AL_OK && ah.method == 1) {
+      std::vector<uint32_t> tables((size_t)ah.num_groups * ah.group_entries);
+      std::vector<AlGroup> groups(ah.num_groups);
+      coded.assign((size_t)ah.xsize * im.height + 4, 0);
+      ah.status = alph_decode_pixels(alph, alph_size, im.height, &ah, (const uint16_t*)meta.data(), tables.data(), groups.data(),
+                                     sc16, coded.data());
+    }
+    if (ah.status != AL_OK) return ah.status;
+    alpha_plane.assign((size_t)im.width * im.height, 0);
+    alph_finish(&ah, alph + 1, coded.data(), tdata.data(), im.width, im.height, alpha_plane.data(), 0, 1);
+    alpha = alpha_plane.data();
+  }
+
   // K5: output
   const int w = im.width, h = im.height;
   if (csp == MODE_YUV) {
@@ -173,9 +200,9 @@ extern "C" int emu_decode(const uint8_t* data, size_t size, int csp, int flags, 
       for (int j = 0; j < ph; ++j) for (int q = 0; q < (pw + 15) / 16; ++q) emit_yuv_chunk(im, yp, up, vp, out, plane, q, j);
     }
   } else if (emit_uses_pairs(csp, flags)) {
-    for (int t = 0; t <= h / 2; ++t) for (int q = 0; q < (w + 7) / 8; ++q) emit_rgba_pair8(im, yp, up, vp, out, q, t);
+    for (int t = 0; t <= h / 2; ++t) for (int q = 0; q < (w + 7) / 8; ++q) emit_rgba_pair8(im, yp, up, vp, alpha, out, q, t);
   } else {
-    for (int j = 0; j < h; ++j) for (int q = 0; q < (w + 3) / 4; ++q) emit_rgb_quad(im, yp, up, vp, out, q, j);
+    for (int j = 0; j < h; ++j) for (int q = 0; q < (w + 3) / 4; ++q) emit_rgb_quad(im, yp, up, vp, alpha, out, q, j);
   }
   return VP8_STATUS_OK;
 }

@@ -83,3 +83,34 @@ def test_emu_full_hd(emu, ref, kind):
         st, want = ref.decode(data, csp, 0)
         st2, got = emu(data, 1920, 1080, csp, 0, 1 if csp == 1 else 2)
         assert st == st2 == 0 and np.array_equal(want.reshape(-1), got.reshape(-1))
+
+
+def test_emu_alpha_matches_manifest(emu, amanifest):
+    """ALPH chunks (raw, palette + every row filter, VP8L predictor transform) through the device code's host build:
+    alpha byte, premultiplied modes, alpha-first modes, and alpha ignored where the output has no alpha channel."""
+    for e in amanifest:
+        w, h = e["features"]["width"], e["features"]["height"]
+        for key, want in e["sha256"].items():
+            csp, fl = map(int, key.split(":"))
+            st, out = emu(e["data"], w, h, csp, fl, 0)
+            assert st == 0 and sha(out) == want, (e["file"], key)
+
+
+def test_emu_alpha_status_on_damaged_chunks(emu, ref, amanifest):
+    """A damaged ALPH payload must end exactly like the reference: same status (header failures surface as
+    VP8_STATUS_OUT_OF_MEMORY there, pixel-loop failures as VP8_STATUS_BITSTREAM_ERROR), same pixels when it decodes."""
+    rng = np.random.default_rng(3)
+    for e in amanifest:
+        data = e["data"]
+        i = data.find(b"ALPH")
+        size = int.from_bytes(data[i + 4:i + 8], "little")
+        w, h = e["features"]["width"], e["features"]["height"]
+        for _ in range(8):
+            b = bytearray(data)
+            b[i + 8 + int(rng.integers(0, size))] ^= int(rng.integers(1, 256))
+            b = bytes(b)
+            s_ref, want = ref.decode(b, ref.MODE_RGBA, 0)
+            s_emu, got = emu(b, w, h, 1, 0, 0)
+            assert s_emu == s_ref, (e["file"], s_ref, s_emu)
+            if s_ref == 0:
+                assert np.array_equal(want.reshape(-1), got.reshape(-1)), e["file"]

@@ -159,3 +159,45 @@ def test_full_size_batch_properties(W, ref):
     assert h_gpu.hexdigest() == h_ref.hexdigest()
     sts2, outs2 = W.decode_batch(datas, W.MODE_RGBA)
     assert all(np.array_equal(a, b) for a, b in zip(outs, outs2))
+
+
+def test_alpha_matches_manifest(W, amanifest):
+    """ALPH chunks decoded on the device (VP8L subset + row unfilters), alpha merged by the output kernel."""
+    for e in amanifest:
+        for key, want in e["sha256"].items():
+            csp, fl = map(int, key.split(":"))
+            st, out = W.WebPDecode(e["data"], csp, bypass_filtering=fl & 1, no_fancy_upsampling=fl & 2)
+            assert st == 0, (e["file"], key, st, W.last_error())
+            assert sha(out) == want, (e["file"], key)
+
+
+def test_alpha_batch_with_opaque_and_damaged(W, ref, manifest, amanifest):
+    """One batch mixing opaque images, images with alpha and damaged ALPH payloads; decoded twice on the resident path
+    (the alpha work areas are planned once and reused)."""
+    rng = np.random.default_rng(17)
+    datas = [e["data"] for e in manifest[:4]] + [e["data"] for e in amanifest]
+    for e in amanifest[:4]:
+        d = e["data"]
+        i = d.find(b"ALPH")
+        size = int.from_bytes(d[i + 4:i + 8], "little")
+        for _ in range(3):
+            b = bytearray(d)
+            b[i + 8 + int(rng.integers(0, size))] ^= int(rng.integers(1, 256))
+            datas.append(bytes(b))
+    for csp in (W.MODE_RGBA, W.MODE_rgbA, W.MODE_Argb):
+        sts, outs = W.decode_batch(datas, csp, device=0)
+        for d, st, out in zip(datas, sts, outs):
+            s_ref, want = ref.decode(d, csp, 0)
+            assert st == s_ref, (len(d), st, s_ref)
+            if s_ref == 0:
+                assert np.array_equal(out.reshape(-1), want.reshape(-1))
+
+
+def test_alpha_large_gradient(W, ref):
+    """Config-5 shape at a size the CPU checker finishes quickly: 1024x1024 q90 with a gradient-filtered ALPH chunk."""
+    cfg = ref.EncCfg(90.0, 4, alpha_filtering=2)
+    data = ref.encode(ref.synth(1024, 1024, 77, alpha=True), cfg)
+    for csp in (W.MODE_RGBA, W.MODE_rgbA):
+        s_ref, want = ref.decode(data, csp, 0)
+        st, out = W.WebPDecode(data, csp)
+        assert st == s_ref == 0 and np.array_equal(out.reshape(-1), want.reshape(-1))
