@@ -31,6 +31,7 @@ WORKLOADS = {
     "vp8_1080p_q75_m4_1part_simple_rgba": (1920, 1080, 4096, "cfg_simple_1part", "RGBA"),
     "vp8_1080p_q75_m4_8part_normal_rgba": (1920, 1080, 4096, "cfg_normal_8part", "RGBA"),
     "vp8_256x256_q80_rgbA": (256, 256, 65536, "cfg_default", "rgbA"),
+    "vp8_4096x4096_q90_alpha_rgba": (4096, 4096, 256, "cfg_alpha_q90", "RGBA"),
 }
 METRIC = "webp_lossy_decode_mpix_per_s_rgba"
 UNIT = "Mpix/s"
@@ -60,7 +61,7 @@ def make_corpus(workload, distinct, rank, threads):
     from oracle import refwebp as R
     w, h, _, cfgname, _ = WORKLOADS[workload]
     cfg = getattr(R, cfgname)()
-    return R.encode_corpus(distinct, w, h, cfg, seed0=1 + 100000 * rank, nthreads=threads)
+    return R.encode_corpus(distinct, w, h, cfg, seed0=1 + 100000 * rank, alpha=("alpha" in workload), nthreads=threads)
 
 
 class ClockSampler:
@@ -235,7 +236,7 @@ def main():
         t = res.timings()
         dev_ms += t["total_ms"]
         launches += t["launches"]
-        for k in ("modes_ms", "tokens_ms", "recon_ms", "filter_ms", "emit_ms"):
+        for k in ("modes_ms", "tokens_ms", "recon_ms", "filter_ms", "emit_ms", "alpha_ms"):
             stage[k] = stage.get(k, 0.0) + t[k]
     barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
@@ -300,6 +301,7 @@ def main():
         "recon_ms": 1.5 * px + 16 * n_mb,                             # planes out (+ the non-zero coefficients in)
         "filter_ms": 3.0 * px,                                        # planes read + written
         "emit_ms": 5.5 * px,                                          # 1.5 B/px in, 4 B/px out
+        "alpha_ms": 1.0 * px if "alpha" in args.workload else 0.0,    # one alpha byte per pixel out (the chunk itself is tiny)
     }
     kernels = {k[:-3]: {"ms": round(per[k], 3), "alg_GBps": round(alg[k] / (per[k] * 1e-3) / 1e9, 1) if per[k] > 0 else None,
                         "share": round(per[k] / max(sum(per.values()), 1e-9), 3)} for k in per}

@@ -85,7 +85,8 @@ typedef struct WebPBatchTimings {
   float filter_ms;   /* in-loop deblocking wavefront */
   float emit_ms;     /* upsample + YUV->RGB (or plane copy) */
   int launches;
-  uint32_t pad[5];
+  float alpha_ms;    /* ALPH chunks: VP8L header + pixel passes, inverse transforms, unfilter (0 without alpha) */
+  uint32_t pad[4];
 } WebPBatchTimings;
 WEBP_EXTERN int WebPBatchGetTimings(const WebPBatch* batch, WebPBatchTimings* t);
 

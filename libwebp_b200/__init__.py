@@ -84,7 +84,8 @@ class WebPBatchPlane(C.Structure):
 
 class WebPBatchTimings(C.Structure):
     _fields_ = [("total_ms", C.c_float), ("modes_ms", C.c_float), ("tokens_ms", C.c_float), ("recon_ms", C.c_float),
-                ("filter_ms", C.c_float), ("emit_ms", C.c_float), ("launches", C.c_int), ("pad", C.c_uint32 * 5)]
+                ("filter_ms", C.c_float), ("emit_ms", C.c_float), ("launches", C.c_int), ("alpha_ms", C.c_float),
+                ("pad", C.c_uint32 * 4)]
 
 
 EXPORTS = [  # every symbol include/webp/*.h declares

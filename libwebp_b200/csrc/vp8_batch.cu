@@ -548,7 +548,7 @@ static bool enqueue_download(WebPBatch* b, int first, int count, cudaStream_t s,
   return flush();
 }
 
-enum { ST_MODES = 0, ST_TOKENS, ST_RECON, ST_FILTER, ST_EMIT, ST_COUNT };
+enum { ST_MODES = 0, ST_TOKENS, ST_RECON, ST_FILTER, ST_EMIT, ST_ALPHA, ST_COUNT };
 
 static int ev_mark(WebPBatch* b, cudaStream_t s) {   // records the next pooled event on `s`; -1 on failure
   if (b->ev_used == b->ev.size()) {
@@ -649,7 +649,13 @@ static bool batch_decode(WebPBatch* b, bool download) {
   size_t chunk_bytes = (size_t)2 << 30;
   { const char* e = getenv("WEBP_B200_CHUNK_MB"); if (e != NULL && atoi(e) > 0) chunk_bytes = (size_t)atoi(e) << 20; }
 #define MARK(var) const int var = ev_mark(b, s); if (var < 0) return false
-  if (!batch_alpha(b)) return false;
+  if (!b->aimgs.empty()) {
+    MARK(ea0);
+    if (!batch_alpha(b)) return false;
+    MARK(ea1);
+    b->spans.push_back({ ST_ALPHA, ea0, ea1 });
+    launches += 3;
+  }
   for (const Wave& w : b->waves) {
     MARK(e0);
     vp8k_parse_modes(s, arena, imgs, hdrs, mbinfo, w.first, w.count, w.max_mb_w);
@@ -698,7 +704,7 @@ static bool batch_decode(WebPBatch* b, bool download) {
   CU_TRY(cudaStreamSynchronize(s), "kernel execution");
   CU_TRY(cudaGetLastError(), "kernel launch");
   if (download) CU_TRY(cudaStreamSynchronize(ctx->copy_stream), "download sync");
-  float acc[ST_COUNT] = { 0, 0, 0, 0, 0 };
+  float acc[ST_COUNT] = { 0, 0, 0, 0, 0, 0 };
   for (const auto& sp : b->spans) {
     float ms = 0;
     CU_TRY(cudaEventElapsedTime(&ms, b->ev[sp.a], b->ev[sp.b]), "cudaEventElapsedTime");
@@ -706,7 +712,8 @@ static bool batch_decode(WebPBatch* b, bool download) {
   }
   b->timings.modes_ms = acc[ST_MODES]; b->timings.tokens_ms = acc[ST_TOKENS]; b->timings.recon_ms = acc[ST_RECON];
   b->timings.filter_ms = acc[ST_FILTER]; b->timings.emit_ms = acc[ST_EMIT];
-  b->timings.total_ms = acc[0] + acc[1] + acc[2] + acc[3] + acc[4];
+  b->timings.alpha_ms = acc[ST_ALPHA];
+  b->timings.total_ms = acc[0] + acc[1] + acc[2] + acc[3] + acc[4] + acc[ST_ALPHA];
   b->timings.launches = launches;
   for (int k = 0; k < m; ++k) {
     WebPBatchItem* it = &b->items[b->img_item[k]];

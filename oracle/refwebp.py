@@ -49,6 +49,10 @@ def cfg_default(quality=80.0):           # config 4: cwebp defaults at q80 (4 se
     return EncCfg(quality, 4)
 
 
+def cfg_alpha_q90():                     # config 5: q90 with an ALPH chunk, gradient-filtered (alpha_filter best)
+    return EncCfg(90.0, 4, alpha_filtering=2)
+
+
 _lib = None
 
 
