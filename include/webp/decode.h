@@ -121,9 +121,8 @@ typedef enum VP8StatusCode { /* decode.h:235-244 */
   VP8_STATUS_NOT_ENOUGH_DATA
 } VP8StatusCode;
 
-/* Incremental API (decode.h:281-372). Exported so existing callers link; a streaming front end makes no
- * sense for a batch device decoder, so the constructors return NULL (the reference's out-of-memory path)
- * and the methods report VP8_STATUS_INVALID_PARAM on a NULL decoder, exactly as the reference does. */
+/* Incremental API (decode.h:281-372), as a buffering shim: same calls, same status protocol
+ * (VP8_STATUS_SUSPENDED until the file is complete), one device decode when the last byte has arrived. */
 WEBP_EXTERN WebPIDecoder* WebPINewDecoder(WebPDecBuffer* output_buffer);
 WEBP_EXTERN WebPIDecoder* WebPIDecode(const uint8_t* data, size_t data_size, WebPDecoderConfig* config);
 WEBP_EXTERN void WebPIDelete(WebPIDecoder* idec);

@@ -130,18 +130,108 @@ uint8_t* WebPDecodeYUVInto(const uint8_t* data, size_t size, uint8_t* luma, size
   return (WebPDecode(data, size, &config) == VP8_STATUS_OK) ? luma : NULL;
 }
 
-/* ---- incremental API: link-compatible, intentionally inert (see include/webp/decode.h) ----------------- */
-WebPIDecoder* WebPINewDecoder(WebPDecBuffer* output_buffer) { (void)output_buffer; return NULL; }
+/* ---- incremental API (src/dec/idec_dec.c:604-909) as a buffering shim ------------------------------------
+ * A batch device decoder has nothing to gain from decoding row by row as bytes arrive, so the shim keeps the
+ * reference's interface and status protocol and does the work in one go: WebPIAppend() accumulates, WebPIUpdate()
+ * looks at the caller's growing buffer, both answer VP8_STATUS_SUSPENDED until the whole file is there (the RIFF
+ * size says when; a bare VP8 stream is tried on every call and "not enough data" reads as suspended), then the
+ * image is decoded once on the device and the status is VP8_STATUS_OK or the decode error, which sticks. */
+struct WebPIDecoder {
+  WebPDecoderConfig* config;     /* caller's config (WebPIDecode) or NULL */
+  WebPDecoderConfig own_config;  /* used when the caller gave only an output buffer, or nothing */
+  WebPDecBuffer* final_output;   /* WebPINewDecoder(output_buffer): receives the result */
+  uint8_t* buf; size_t size, cap; int mode;   /* 0 unset, 1 append, 2 update */
+  VP8StatusCode status;          /* SUSPENDED until decoded, then final */
+};
+
+static WebPIDecoder* NewIDecoder(WebPDecBuffer* output_buffer, WebPDecoderConfig* config) {
+  WebPIDecoder* const idec = (WebPIDecoder*)calloc(1, sizeof(*idec));
+  if (idec == NULL) return NULL;
+  WebPInitDecoderConfig(&idec->own_config);
+  idec->own_config.output.colorspace = MODE_RGB;   /* idec_dec.c: default output when none is given */
+  idec->config = config;
+  idec->final_output = output_buffer;
+  idec->status = VP8_STATUS_SUSPENDED;
+  return idec;
+}
+
+WebPIDecoder* WebPINewDecoder(WebPDecBuffer* output_buffer) { return NewIDecoder(output_buffer, NULL); }
+
 WebPIDecoder* WebPIDecode(const uint8_t* data, size_t data_size, WebPDecoderConfig* config) {
-  (void)data; (void)data_size; (void)config;
-  return NULL;
+  WebPBitstreamFeatures tmp;
+  WebPBitstreamFeatures* const features = (config == NULL) ? &tmp : &config->input;
+  memset(&tmp, 0, sizeof(tmp));
+  if (data != NULL && data_size > 0) {
+    if (WebPGetFeatures(data, data_size, features) != VP8_STATUS_OK) return NULL;
+  }
+  return NewIDecoder(NULL, config);
 }
-void WebPIDelete(WebPIDecoder* idec) { (void)idec; }
+
+void WebPIDelete(WebPIDecoder* idec) {
+  if (idec == NULL) return;
+  free(idec->buf);
+  WebPFreeDecBuffer(&idec->own_config.output);
+  free(idec);
+}
+
+/* Bytes the container announces for the whole file, 0 when it does not say (bare bitstream / header incomplete). */
+static size_t AnnouncedSize(const uint8_t* data, size_t size) {
+  if (size >= 12 && !memcmp(data, "RIFF", 4) && !memcmp(data + 8, "WEBP", 4)) {
+    const uint32_t riff = (uint32_t)data[4] | ((uint32_t)data[5] << 8) | ((uint32_t)data[6] << 16) | ((uint32_t)data[7] << 24);
+    return (size_t)riff + 8;
+  }
+  return 0;
+}
+
+static VP8StatusCode IDecodeNow(WebPIDecoder* idec, const uint8_t* data, size_t size) {
+  WebPDecoderConfig* cfg = (idec->config != NULL) ? idec->config : &idec->own_config;
+  VP8StatusCode st;
+  size_t total;
+  if (idec->status != VP8_STATUS_SUSPENDED) return idec->status;
+  if (size < 12) return VP8_STATUS_SUSPENDED;
+  total = AnnouncedSize(data, size);
+  if (total != 0 && size < total) {
+    /* still arriving; a header that is already wrong is reported at once, like the reference does */
+    WebPBitstreamFeatures f;
+    st = WebPGetFeatures(data, size, &f);
+    if (st != VP8_STATUS_OK && st != VP8_STATUS_NOT_ENOUGH_DATA) { idec->status = st; return st; }
+    return VP8_STATUS_SUSPENDED;
+  }
+  if (idec->config == NULL && idec->final_output != NULL) {   /* decode straight into the caller's buffer */
+    cfg->output = *idec->final_output;
+  }
+  st = WebPDecode(data, size, cfg);
+  if (st == VP8_STATUS_NOT_ENOUGH_DATA && total == 0) return VP8_STATUS_SUSPENDED;   /* bare stream, more may come */
+  if (st == VP8_STATUS_OK && idec->config == NULL && idec->final_output != NULL) {
+    *idec->final_output = cfg->output;
+    memset(&cfg->output, 0, sizeof(cfg->output));   /* ownership moved */
+  }
+  idec->status = st;
+  return st;
+}
+
 VP8StatusCode WebPIAppend(WebPIDecoder* idec, const uint8_t* data, size_t data_size) {
-  (void)idec; (void)data; (void)data_size;
-  return VP8_STATUS_INVALID_PARAM;
+  if (idec == NULL || data == NULL) return VP8_STATUS_INVALID_PARAM;
+  if (idec->status != VP8_STATUS_SUSPENDED) return idec->status;
+  if (idec->mode == 2) return VP8_STATUS_INVALID_PARAM;   /* no mixing of append and update (idec_dec.c:94) */
+  idec->mode = 1;
+  if (idec->size + data_size > idec->cap) {
+    size_t ncap = idec->cap ? idec->cap : 4096;
+    uint8_t* nb;
+    while (ncap < idec->size + data_size) ncap *= 2;
+    nb = (uint8_t*)realloc(idec->buf, ncap);
+    if (nb == NULL) return VP8_STATUS_OUT_OF_MEMORY;
+    idec->buf = nb; idec->cap = ncap;
+  }
+  memcpy(idec->buf + idec->size, data, data_size);
+  idec->size += data_size;
+  return IDecodeNow(idec, idec->buf, idec->size);
 }
+
 VP8StatusCode WebPIUpdate(WebPIDecoder* idec, const uint8_t* data, size_t data_size) {
-  (void)idec; (void)data; (void)data_size;
-  return VP8_STATUS_INVALID_PARAM;
+  if (idec == NULL || data == NULL) return VP8_STATUS_INVALID_PARAM;
+  if (idec->status != VP8_STATUS_SUSPENDED) return idec->status;
+  if (idec->mode == 1) return VP8_STATUS_INVALID_PARAM;
+  idec->mode = 2;
+  return IDecodeNow(idec, data, data_size);
 }

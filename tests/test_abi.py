@@ -121,3 +121,31 @@ def test_product_never_touches_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 for bad in ("oracle/", "oracle import", "from oracle", "vp8_oracle", "libwebp_ref", "tests/emu/libvp8"):
                     assert bad not in text.replace("oracle/: ", "").replace("touches oracle/", ""), (f, bad)
+
+
+def test_incremental_protocol_without_device(product, manifest):
+    """WebPIAppend / WebPIUpdate up to (not including) the last byte: VP8_STATUS_SUSPENDED, no device needed; bad
+    headers are refused at once; append and update do not mix (src/dec/idec_dec.c:700-760)."""
+    import ctypes as C
+    L = product.lib()
+    L.WebPINewDecoder.restype = C.c_void_p
+    L.WebPINewDecoder.argtypes = [C.c_void_p]
+    L.WebPIAppend.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    L.WebPIUpdate.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    L.WebPIDelete.argtypes = [C.c_void_p]
+    L.WebPIDecode.restype = C.c_void_p
+    L.WebPIDecode.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p]
+    data = manifest[1]["data"]
+    idec = L.WebPINewDecoder(None)
+    assert idec
+    for lo, hi in ((0, 10), (10, 500), (500, len(data) - 1)):
+        assert L.WebPIAppend(idec, data[lo:hi], hi - lo) == product.VP8_STATUS_SUSPENDED
+    assert L.WebPIUpdate(idec, data, len(data) - 1) == product.VP8_STATUS_INVALID_PARAM      # no mixing
+    L.WebPIDelete(idec)
+    idec = L.WebPINewDecoder(None)
+    bad = b"RIFF" + (100).to_bytes(4, "little") + b"WEBPjunkjunkjunkjunkjunkjunk"
+    assert L.WebPIUpdate(idec, bad, len(bad)) == product.VP8_STATUS_BITSTREAM_ERROR
+    assert L.WebPIUpdate(idec, bad, len(bad)) == product.VP8_STATUS_BITSTREAM_ERROR               # the error sticks
+    L.WebPIDelete(idec)
+    assert not L.WebPIDecode(b"junkjunkjunkjunkjunk", 20, None)                                  # features must parse
+    assert L.WebPIAppend(None, data, 10) == product.VP8_STATUS_INVALID_PARAM

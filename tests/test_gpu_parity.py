@@ -201,3 +201,46 @@ def test_alpha_large_gradient(W, ref):
         s_ref, want = ref.decode(data, csp, 0)
         st, out = W.WebPDecode(data, csp)
         assert st == s_ref == 0 and np.array_equal(out.reshape(-1), want.reshape(-1))
+
+
+def test_incremental_api(W, port, manifest, amanifest):
+    """dwebp -incremental's call sequence: WebPIDecode(config) + WebPIUpdate with a growing prefix, and
+    WebPINewDecoder + WebPIAppend in chunks; SUSPENDED until the last byte, then the same pixels as WebPDecode."""
+    L = W.lib()
+    L.WebPINewDecoder.restype = C.c_void_p
+    L.WebPINewDecoder.argtypes = [C.c_void_p]
+    L.WebPIDecode.restype = C.c_void_p
+    L.WebPIDecode.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p]
+    L.WebPIAppend.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    L.WebPIUpdate.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    L.WebPIDelete.argtypes = [C.c_void_p]
+    for e in (manifest[2], amanifest[0]):
+        data = e["data"]
+        _, want = W.WebPDecode(data, W.MODE_RGBA)
+        w, h = e["features"]["width"], e["features"]["height"]
+        # update mode with a caller config
+        cfg = W._new_config(W.MODE_RGBA, 0, 0)
+        idec = L.WebPIDecode(data, len(data), C.byref(cfg))
+        assert idec
+        for n in (30, len(data) // 3, len(data) - 1):
+            assert L.WebPIUpdate(idec, data, n) == W.VP8_STATUS_SUSPENDED
+        assert L.WebPIUpdate(idec, data, len(data)) == W.VP8_STATUS_OK
+        got = np.ctypeslib.as_array(C.cast(cfg.output.u.RGBA.rgba, C.POINTER(C.c_uint8)), (h, cfg.output.u.RGBA.stride)).copy()
+        L.WebPIDelete(idec)
+        L.WebPFreeDecBuffer(C.byref(cfg.output))
+        assert np.array_equal(got[:, :w * 4], want[:, :w * 4])
+        # append mode into a caller buffer object
+        buf = W.WebPDecBuffer()
+        L.WebPInitDecBufferInternal(C.byref(buf), W.WEBP_DECODER_ABI_VERSION)
+        buf.colorspace = W.MODE_RGBA
+        idec = L.WebPINewDecoder(C.byref(buf))
+        st, pos = W.VP8_STATUS_SUSPENDED, 0
+        for chunk in (100, 1000, len(data)):
+            nxt = min(len(data), pos + chunk)
+            st = L.WebPIAppend(idec, data[pos:nxt], nxt - pos)
+            pos = nxt
+            assert st == (W.VP8_STATUS_OK if pos == len(data) else W.VP8_STATUS_SUSPENDED)
+        got = np.ctypeslib.as_array(C.cast(buf.u.RGBA.rgba, C.POINTER(C.c_uint8)), (h, buf.u.RGBA.stride)).copy()
+        L.WebPIDelete(idec)
+        L.WebPFreeDecBuffer(C.byref(buf))
+        assert np.array_equal(got[:, :w * 4], want[:, :w * 4])
