@@ -153,7 +153,7 @@ def WebPGetFeatures(data):
     return st, dict(width=f.width, height=f.height, has_alpha=f.has_alpha, has_animation=f.has_animation, format=f.format)
 
 
-def _new_config(csp, bypass_filtering, no_fancy_upsampling, dithering_strength=0):
+def _new_config(csp, bypass_filtering, no_fancy_upsampling, dithering_strength=0, crop=None, flip=False):
     cfg = WebPDecoderConfig()
     if not lib().WebPInitDecoderConfigInternal(C.byref(cfg), WEBP_DECODER_ABI_VERSION):
         raise RuntimeError("WebPInitDecoderConfig failed (ABI mismatch)")
@@ -161,6 +161,10 @@ def _new_config(csp, bypass_filtering, no_fancy_upsampling, dithering_strength=0
     cfg.options.bypass_filtering = int(bool(bypass_filtering))
     cfg.options.no_fancy_upsampling = int(bool(no_fancy_upsampling))
     cfg.options.dithering_strength = dithering_strength
+    cfg.options.flip = int(bool(flip))
+    if crop is not None:
+        cfg.options.use_cropping = 1
+        (cfg.options.crop_left, cfg.options.crop_top, cfg.options.crop_width, cfg.options.crop_height) = crop
     return cfg
 
 
@@ -186,15 +190,17 @@ def out_bytes(csp, w, h, stride=None):
 
 
 def WebPDecode(data, csp=MODE_RGBA, bypass_filtering=False, no_fancy_upsampling=False, stride=None, external=True,
-               dithering_strength=0):
+               dithering_strength=0, crop=None, flip=False):
     """One image through the C-ABI WebPDecode (a GPU batch of one). Returns (status, ndarray or None):
-    (h, stride) bytes for RGB-family modes, flat y|u|v for MODE_YUV."""
+    (h, stride) bytes for RGB-family modes, flat y|u|v for MODE_YUV. crop = (left, top, width, height)."""
     L = lib()
-    cfg = _new_config(csp, bypass_filtering, no_fancy_upsampling, dithering_strength)
+    cfg = _new_config(csp, bypass_filtering, no_fancy_upsampling, dithering_strength, crop, flip)
     st, f = WebPGetFeatures(data)
     if st != VP8_STATUS_OK:
         return L.WebPDecode(data, len(data), C.byref(cfg)), None
     w, h = f["width"], f["height"]
+    if crop is not None and crop[2] > 0 and crop[3] > 0:
+        w, h = crop[2], crop[3]
     if external:
         if csp == MODE_YUV:
             out = np.zeros(out_bytes(csp, w, h), np.uint8)

@@ -268,12 +268,20 @@ static VP8StatusCode plan_item(WebPBatchItem* it, const WebPBatchOptions& opt, V
   if (c->has_alph_chunk && cfg->options.alpha_dithering_strength > 0) return VP8_STATUS_UNSUPPORTED_FEATURE;   // alpha de-banding
   if (c->part0_size > c->frame_size - 10) return VP8_STATUS_NOT_ENOUGH_DATA;   // vp8_dec.c:345-348
   const WebPDecoderOptions* o = &cfg->options;
-  if (o->use_cropping || o->use_scaling || o->flip) return VP8_STATUS_UNSUPPORTED_FEATURE;
+  if (o->use_scaling) return VP8_STATUS_UNSUPPORTED_FEATURE;   // the rescaler is not on the device
   const int csp = cfg->output.colorspace;
   if (csp < MODE_RGB || csp >= MODE_LAST) return VP8_STATUS_INVALID_PARAM;
   if (!csp_supported(csp)) return VP8_STATUS_UNSUPPORTED_FEATURE;
-  if (opt.output == WEBP_BATCH_HOST) return prepare_host_buffer(c->width, c->height, &cfg->output);
-  cfg->output.width = c->width; cfg->output.height = c->height;
+  int ow = c->width, oh = c->height;
+  if (o->use_cropping) {   // WebPAllocateDecBuffer, buffer_dec.c:184-195 (x, y snapped to even like the decoder's own io)
+    const int x = o->crop_left & ~1, y = o->crop_top & ~1;
+    const int cw = o->crop_width, ch = o->crop_height;
+    if (x < 0 || y < 0 || cw <= 0 || ch <= 0 || x >= ow || cw > ow || cw > ow - x || y >= oh || ch > oh || ch > oh - y)
+      return VP8_STATUS_INVALID_PARAM;
+    ow = cw; oh = ch;
+  }
+  if (opt.output == WEBP_BATCH_HOST) return prepare_host_buffer(ow, oh, &cfg->output);
+  cfg->output.width = ow; cfg->output.height = oh;
   return VP8_STATUS_OK;
 }
 
@@ -336,7 +344,13 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
     d.mb_w = (uint16_t)((c.width + 15) >> 4); d.mb_h = (uint16_t)((c.height + 15) >> 4);
     d.csp = (uint8_t)cfg->output.colorspace;
     d.flags = (uint8_t)((cfg->options.bypass_filtering ? VP8B_FLAG_BYPASS_FILTER : 0) |
-                        (cfg->options.no_fancy_upsampling ? VP8B_FLAG_NO_FANCY : 0));
+                        (cfg->options.no_fancy_upsampling ? VP8B_FLAG_NO_FANCY : 0) |
+                        (cfg->options.flip ? VP8B_FLAG_FLIP : 0));
+    d.out_w = d.width; d.out_h = d.height;
+    if (cfg->options.use_cropping) {
+      d.crop_x = (uint16_t)(cfg->options.crop_left & ~1); d.crop_y = (uint16_t)(cfg->options.crop_top & ~1);
+      d.out_w = (uint16_t)cfg->options.crop_width; d.out_h = (uint16_t)cfg->options.crop_height;
+    }
     const int ds = cfg->options.dithering_strength;
     d.dither_f = (uint8_t)(ds < 0 ? 0 : ds > 100 ? 255 : ds * 255 / 100);
     d.num_parts = (uint8_t)vp8b_prescan_partitions(b->items[i].data + c.frame_offset + 10, c.part0_size);
@@ -349,11 +363,11 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
     }
     size_t bytes;
     if (d.csp == MODE_YUV) {
-      d.out_stride = c.width;
-      bytes = (size_t)c.width * c.height + 2 * (size_t)((c.width + 1) / 2) * ((c.height + 1) / 2);
+      d.out_stride = d.out_w;
+      bytes = (size_t)d.out_w * d.out_h + 2 * (size_t)((d.out_w + 1) / 2) * ((d.out_h + 1) / 2);
     } else {
-      d.out_stride = c.width * kBpp[d.csp];
-      bytes = (size_t)d.out_stride * c.height;
+      d.out_stride = d.out_w * kBpp[d.csp];
+      bytes = (size_t)d.out_stride * d.out_h;
     }
     d.out_off = b->out_total;
     b->out_total += align_up(bytes, 256);
@@ -407,11 +421,11 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
       w.max_mb_h = std::max(w.max_mb_h, (int)b->imgs[k].mb_h);
       const ImgDesc& d = b->imgs[k];
       // work items of the output kernel (must match k_emit / emit_uses_pairs in vp8_pixel_core.h)
-      const bool pairs = !(d.flags & VP8B_FLAG_NO_FANCY) && kBpp[d.csp] == 4;
+      const bool pairs = !(d.flags & VP8B_FLAG_NO_FANCY) && (d.crop_x & 7) == 0 && kBpp[d.csp] == 4;
       const int units = (d.csp == MODE_YUV)
-                            ? ((d.width + 15) / 16) * d.height + 2 * ((((d.width + 1) / 2) + 15) / 16) * ((d.height + 1) / 2)
-                            : pairs ? ((d.width + 7) / 8) * (d.height / 2 + 1)
-                                    : ((d.width + 3) / 4) * d.height;
+                            ? ((d.out_w + 15) / 16) * d.out_h + 2 * ((((d.out_w + 1) / 2) + 15) / 16) * ((d.out_h + 1) / 2)
+                            : pairs ? ((d.out_w + 7) / 8) * (d.out_h / 2 + 1)
+                                    : ((d.out_w + 3) / 4) * d.out_h;
       w.max_units = std::max(w.max_units, units);
     }
     b->waves.push_back(w);
@@ -523,7 +537,7 @@ static bool enqueue_download(WebPBatch* b, int first, int count, cudaStream_t s,
     const uint8_t* src = dout + d.out_off;
     if (d.csp == MODE_YUV) {
       if (!flush()) return false;
-      const int w = d.width, h = d.height, uvw = (w + 1) / 2, uvh = (h + 1) / 2;
+      const int w = d.out_w, h = d.out_h, uvw = (w + 1) / 2, uvh = (h + 1) / 2;
       const WebPYUVABuffer* y = &o->u.YUVA;
       CU_TRY(cudaMemcpy2DAsync(y->y, y->y_stride, src, w, w, h, cudaMemcpyDeviceToHost, s), "D2H Y");
       CU_TRY(cudaMemcpy2DAsync(y->u, y->u_stride, src + (size_t)w * h, uvw, uvw, uvh, cudaMemcpyDeviceToHost, s), "D2H U");
@@ -531,7 +545,7 @@ static bool enqueue_download(WebPBatch* b, int first, int count, cudaStream_t s,
       continue;
     }
     const size_t row = (size_t)d.out_stride;
-    const size_t bytes = row * d.height;
+    const size_t bytes = row * d.out_h;
     if ((size_t)o->u.RGBA.stride == row) {
       if (run_bytes > 0 && o->u.RGBA.rgba == run_host + run_bytes && src == run_dev + run_bytes) {
         run_bytes += bytes;
@@ -542,7 +556,7 @@ static bool enqueue_download(WebPBatch* b, int first, int count, cudaStream_t s,
       if (run_bytes >= ((size_t)256 << 20)) { if (!flush()) return false; }
     } else {
       if (!flush()) return false;
-      CU_TRY(cudaMemcpy2DAsync(o->u.RGBA.rgba, (size_t)o->u.RGBA.stride, src, row, row, d.height, cudaMemcpyDeviceToHost, s), "D2H pixels 2D");
+      CU_TRY(cudaMemcpy2DAsync(o->u.RGBA.rgba, (size_t)o->u.RGBA.stride, src, row, row, d.out_h, cudaMemcpyDeviceToHost, s), "D2H pixels 2D");
     }
   }
   return flush();
@@ -782,12 +796,12 @@ extern "C" int WebPBatchOutput(const WebPBatch* b, int index, WebPBatchPlane* p)
   const ImgDesc& d = b->imgs[b->plan[index].img];
   uint8_t* base = (uint8_t*)b->d_out.p + d.out_off;
   memset(p, 0, sizeof(*p));
-  p->width = d.width; p->height = d.height;
+  p->width = d.out_w; p->height = d.out_h;
   p->y_or_rgba = base; p->stride = d.out_stride;
   if (d.csp == MODE_YUV) {
-    const int uvw = (d.width + 1) / 2, uvh = (d.height + 1) / 2;
-    p->u = base + (size_t)d.width * d.height;
-    p->v = base + (size_t)d.width * d.height + (size_t)uvw * uvh;
+    const int uvw = (d.out_w + 1) / 2, uvh = (d.out_h + 1) / 2;
+    p->u = base + (size_t)d.out_w * d.out_h;
+    p->v = base + (size_t)d.out_w * d.out_h + (size_t)uvw * uvh;
     p->uv_stride = uvw;
   }
   return 1;

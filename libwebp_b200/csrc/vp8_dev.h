@@ -29,6 +29,7 @@
 // ImgDesc::flags
 #define VP8B_FLAG_BYPASS_FILTER 1
 #define VP8B_FLAG_NO_FANCY 2
+#define VP8B_FLAG_FLIP 4     // options.flip: output rows bottom-up (WebPFlipBuffer, buffer_dec.c:152-175)
 
 typedef struct ImgDesc {
   uint64_t in_off;     // byte offset of the VP8 frame tag inside the input arena
@@ -47,6 +48,9 @@ typedef struct ImgDesc {
                        // after the alpha header pass); VP8B_NO_ALPHA when the image has none
   uint32_t alpha_size; // ALPH payload bytes
   uint32_t alpha_index;// index among the batch's alpha images
+  // output window (options.use_cropping, webp_dec.c:802-829; the whole picture otherwise). crop_x / crop_y are even.
+  // The window is upsampled and emitted as if it were the picture (edges replicate at the window, io_dec.c:57-109).
+  uint16_t crop_x, crop_y, out_w, out_h;
 } ImgDesc;
 #define VP8B_NO_ALPHA 0xffffffffffffffffull
 
@@ -62,6 +66,8 @@ typedef struct FrameHdr {
   uint32_t part_off[VP8B_MAX_PARTS];   // token partitions, relative to the frame tag
   uint32_t part_size[VP8B_MAX_PARTS];
   uint8_t prob[4 * 8 * 3 * 11]; // [type][band][ctx][node]
+  int32_t rows;                 // macroblock rows that get decoded: all of them, or down to the bottom of the crop
+                                // window plus the filter's reach (VP8EnterCritical, frame_dec.c:571-596)
 } FrameHdr;
 
 // MbInfo words (one uint4 per macroblock):

@@ -72,12 +72,13 @@ __global__ void __launch_bounds__(32 * VP8B_MAX_PARTS) k_parse_tokens(const uint
     if (tid == 0 && h->status == VP8B_OK) h->status = VP8B_BITSTREAM_ERROR;
     return;
   }
-  if (lane != 0 || part >= im.mb_h) return;
+  const int rows = h->rows;
+  if (lane != 0 || part >= rows) return;
   TokenPart tp;
   token_part_init(tp, arena + im.in_off, h, part);
   uint32_t* mbi = mbinfo + 4 * (size_t)im.mb_base;
   int16_t* cf = coeffs + (size_t)im.mb_base * VP8B_COEFFS_PER_MB;
-  for (int my = part; my < im.mb_h; my += P) {
+  for (int my = part; my < rows; my += P) {
     parse_token_row(tp, im, h, part, my, probs, topctx, progress, mbi, cf);
   }
   if (tp.status != VP8B_OK) h->status = tp.status;
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(32 * 9) k_parse_tokens_fsm(const uint8_t* __re
     const TokImage* ti = reinterpret_cast<const TokImage*>(img_mem + (size_t)slot * TOK_IMG_BYTES);
     if (!ti->ok) continue;
     const int img = ids[blockIdx.x * ipb + slot];
-    if (part >= imgs[img].mb_h) continue;
+    if (part >= hdrs[img].rows) continue;
     tk_stream_prefill(smem_s + lay.rings + (uint32_t)j * TK_RING_BYTES, arena, tk_stream_start(imgs[img].in_off, &hdrs[img], part),
                       k % TK_RING_CHUNKS);
   }
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(32 * 9) k_parse_tokens_fsm(const uint8_t* __re
     int live = ti->ok;
     if (live) {
       const int img = ids[blockIdx.x * ipb + slot];
-      live = part < imgs[img].mb_h;
+      live = part < hdrs[img].rows;
       if (live) tk_stream_open(&ctl[j], tk_stream_start(imgs[img].in_off, &hdrs[img], part));
     }
     if (!live) { ctl[j].rd_w = TK_STREAM_DONE; ctl[j].filled_c = 0; }
@@ -187,7 +188,8 @@ __global__ void __launch_bounds__(32 * 9) k_parse_tokens_fsm(const uint8_t* __re
     return;
   }
   const ImgDesc im = imgs[img];
-  if (part >= im.mb_h) return;
+  const int rows = h->rows;
+  if (part >= rows) return;
   TokShared sh;
   sh.img = timg;
   sh.img_s = tk_saddr_of(timg);
@@ -199,9 +201,9 @@ __global__ void __launch_bounds__(32 * 9) k_parse_tokens_fsm(const uint8_t* __re
   int16_t* cf = coeffs + (size_t)im.mb_base * VP8B_COEFFS_PER_MB;
   TokLane L;
   tk_lane_init(L, smem_s + lay.rings + (uint32_t)j * TK_RING_BYTES, smem_s + lay.ctl + (uint32_t)j * 8u, im.in_off, h, part,
-               mbi, im.mb_w, im.mb_h);
+               mbi, im.mb_w, rows);
   while (L.phase != 2) {
-    if (L.phase == 0) tk_mb_start(L, sh, im, P, mbi);
+    if (L.phase == 0) tk_mb_start(L, sh, im, rows, P, mbi);
     if (L.phase == 1) tk_step(L, sh, im, P, mbi, cf);
   }
   if (L.status != VP8B_OK) h->status = L.status;
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(32 * RECON_WARPS) k_reconstruct(const ImgDesc*
   const int img = first + blockIdx.x;
   if (hdrs[img].status != VP8B_OK) return;
   const ImgDesc im = imgs[img];
-  const int mb_w = im.mb_w, mb_h = im.mb_h;
+  const int mb_w = im.mb_w, mb_h = hdrs[img].rows;
   const int warp = threadIdx.x >> 5;
   ReconWs& ws = *reinterpret_cast<ReconWs*>(smem + sizeof(ReconWs) * warp);
   ReconCtx cx;
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(32 * RECON_WARPS) k_reconstruct(const ImgDesc*
   __shared__ int16_t dqs[24];   // the frame's dequantisers, [segment][y1 dc/ac, y2 dc/ac, uv dc/ac]
   if (threadIdx.x < 24) dqs[threadIdx.x] = (&hdrs[img].dq[0][0])[threadIdx.x];
   __syncthreads();
-  const size_t nmb = (size_t)mb_w * mb_h;
+  const size_t nmb = (size_t)mb_w * im.mb_h;
   uint8_t* yp = yuv + (size_t)im.mb_base * 384;
   uint8_t* up = yp + nmb * 256;
   uint8_t* vp = up + nmb * 64;
@@ -257,13 +259,13 @@ __global__ void __launch_bounds__(32 * FILTER_WARPS) k_loop_filter(const ImgDesc
   const FrameHdr* h = &hdrs[img];
   if (h->status != VP8B_OK || h->filter_type == 0) return;
   const ImgDesc im = imgs[img];
-  const int mb_w = im.mb_w, mb_h = im.mb_h;
+  const int mb_w = im.mb_w, mb_h = h->rows;
   const int filter_type = h->filter_type;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x < 32) fstr[threadIdx.x] = ((const uint8_t*)h->fstr)[threadIdx.x];
   __syncthreads();
   FilterWs& ws = wss[warp];
-  const size_t nmb = (size_t)mb_w * mb_h;
+  const size_t nmb = (size_t)mb_w * im.mb_h;
   uint8_t* yp = yuv + (size_t)im.mb_base * 384;
   uint8_t* up = yp + nmb * 256;
   uint8_t* vp = up + nmb * 64;
@@ -293,25 +295,28 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(const ImgDesc* __restrict
   if (hdrs[img].status != VP8B_OK) return;
   const ImgDesc im = imgs[img];
   const size_t nmb = (size_t)im.mb_w * im.mb_h;
+  // planes and alpha re-based at the output window (crop_x, crop_y are even)
   const uint8_t* yp = yuv + (size_t)im.mb_base * 384;
-  const uint8_t* up = yp + nmb * 256;
-  const uint8_t* vp = up + nmb * 64;
+  const uint8_t* up = yp + nmb * 256 + (size_t)(im.crop_y >> 1) * (8 * im.mb_w) + (im.crop_x >> 1);
+  const uint8_t* vp = yp + nmb * 256 + nmb * 64 + (size_t)(im.crop_y >> 1) * (8 * im.mb_w) + (im.crop_x >> 1);
+  yp += (size_t)im.crop_y * (16 * im.mb_w) + im.crop_x;
   uint8_t* o = out + im.out_off;
-  const uint8_t* alpha = (im.alpha_plane != VP8B_NO_ALPHA) ? alpha_arena + im.alpha_plane : nullptr;
+  const uint8_t* alpha = (im.alpha_plane != VP8B_NO_ALPHA) ? alpha_arena + im.alpha_plane + (size_t)im.crop_y * im.width + im.crop_x : nullptr;
   const int t = chunk * EMIT_THREADS + threadIdx.x;
+  const int w = im.out_w, h = im.out_h;
   if (im.csp == 11) {   // MODE_YUV: 16-byte chunks of Y rows, then U rows, then V rows
-    const int w = im.width, h = im.height, uvw = (w + 1) >> 1, uvh = (h + 1) >> 1;
+    const int uvw = (w + 1) >> 1, uvh = (h + 1) >> 1;
     const int qy = (w + 15) >> 4, quv = (uvw + 15) >> 4;
     const int ny = qy * h, nuv = quv * uvh;
     if (t < ny) emit_yuv_chunk(im, yp, up, vp, o, 0, t % qy, t / qy);
     else if (t < ny + nuv) emit_yuv_chunk(im, yp, up, vp, o, 1, (t - ny) % quv, (t - ny) / quv);
     else if (t < ny + 2 * nuv) emit_yuv_chunk(im, yp, up, vp, o, 2, (t - ny - nuv) % quv, (t - ny - nuv) / quv);
-  } else if (emit_uses_pairs(im.csp, im.flags)) {   // 8 pixels x 2 rows per thread
-    const int qw = (im.width + 7) >> 3;
-    if (t < qw * ((im.height >> 1) + 1)) emit_rgba_pair8(im, yp, up, vp, alpha, o, t % qw, t / qw);
+  } else if (emit_uses_pairs(im.csp, im.flags, im.crop_x)) {   // 8 pixels x 2 rows per thread
+    const int qw = (w + 7) >> 3;
+    if (t < qw * ((h >> 1) + 1)) emit_rgba_pair8(im, yp, up, vp, alpha, o, t % qw, t / qw);
   } else {
-    const int qw = (im.width + 3) >> 2;
-    if (t < qw * im.height) emit_rgb_quad(im, yp, up, vp, alpha, o, t % qw, t / qw);
+    const int qw = (w + 3) >> 2;
+    if (t < qw * h) emit_rgb_quad(im, yp, up, vp, alpha, o, t % qw, t / qw);
   }
 }
 
@@ -427,7 +432,7 @@ __global__ void __launch_bounds__(32) k_alpha_pixels(const uint8_t* __restrict__
   if (hd->status != AL_OK || hd->method == 0) return;
   const ImgDesc im = imgs[aimgs[a]];
   const AlphaPlan pl = plans[a];
-  hd->status = alph_decode_pixels(arena + im.alpha_in, im.alpha_size, im.height, hd, (const uint16_t*)pl.meta,
+  hd->status = alph_decode_pixels(arena + im.alpha_in, im.alpha_size, im.height, (int)im.crop_y + (int)im.out_h, hd, (const uint16_t*)pl.meta,
                                   (uint32_t*)pl.tables, (AlGroup*)pl.groups, (uint8_t*)pl.scratch, (uint32_t*)pl.coded);
 }
 
@@ -441,7 +446,7 @@ __global__ void __launch_bounds__(ALPHA_FINISH_THREADS) k_alpha_finish(const uin
   const ImgDesc im = imgs[aimgs[a]];
   const AlphaPlan pl = plans[a];
   if (im.alpha_plane == VP8B_NO_ALPHA) return;
-  alph_finish(hd, arena + im.alpha_in + 1, (uint32_t*)pl.coded, (const uint32_t*)pl.tdata, im.width, im.height,
+  alph_finish(hd, arena + im.alpha_in + 1, (uint32_t*)pl.coded, (const uint32_t*)pl.tdata, im.width, im.height, im.crop_y,
               alpha_arena + im.alpha_plane, (int)threadIdx.x, (int)blockDim.x);
 }
 

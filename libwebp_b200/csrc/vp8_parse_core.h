@@ -258,6 +258,11 @@ VP8_FN int parse_frame_header(BoolDec& br, const uint8_t* frame, const ImgDesc& 
   // loop-filter strengths per segment and block type (frame_dec.c:265-313)
   if (im.flags & VP8B_FLAG_BYPASS_FILTER) filter_type = 0;   // VP8EnterCritical, frame_dec.c:557-560
   h->filter_type = (uint8_t)filter_type;
+  {   // rows below the crop window (plus what the loop filter reads past it) are never decoded, nor checked for eof
+    const int extra = (filter_type == 2) ? 8 : (filter_type == 1) ? 2 : 0;   // kFilterExtraRows, frame_dec.c:201
+    const int rows = ((int)im.crop_y + (int)im.out_h + 15 + extra) >> 4;
+    h->rows = rows < (int)im.mb_h ? rows : (int)im.mb_h;
+  }
   for (int s = 0; s < 4; ++s) {
     int base_level = level;
     if (use_segment) base_level = seg_filter[s] + (absolute_delta ? 0 : level);
@@ -307,7 +312,7 @@ VP8_FN uint32_t parse_bmode(BoolDec& d, const uint8_t* p) {
 
 VP8_FN int parse_intra_modes(BoolDec& br, const ImgDesc& im, const FrameHdr* h, uint32_t* top, const uint8_t* bprob,
                              uint32_t* mbinfo /* 4 words per MB */) {
-  const int mb_w = im.mb_w, mb_h = im.mb_h;
+  const int mb_w = im.mb_w, mb_h = h->rows;
   const int update_map = h->update_map, use_skip = h->use_skip, skip_p = h->skip_p;
   const uint32_t sp0 = h->seg_prob[0], sp1 = h->seg_prob[1], sp2 = h->seg_prob[2];
   for (int mx = 0; mx < mb_w; ++mx) top[mx] = 0;   // M_DC == 0

@@ -535,8 +535,8 @@ VP8_PFN uint32_t pack_pixel4(int csp, int r, int g, int b, int a) {   // little-
 
 // Pixels 4*q .. 4*q+3 of output row j of image `im`. yuv = the image's padded planes.
 VP8_PFN void emit_rgb_quad(const ImgDesc& im, const uint8_t* yplane, const uint8_t* uplane, const uint8_t* vplane,
-                           const uint8_t* alpha /* w x h plane or NULL */, uint8_t* out, int q, int j) {
-  const int w = im.width, h = im.height;
+                           const uint8_t* alpha /* window origin inside the frame-wide plane, or NULL */, uint8_t* out, int q, int j) {
+  const int w = im.out_w, h = im.out_h;
   const int ys = 16 * im.mb_w, uvs = 8 * im.mb_w;
   const int uvh = (h + 1) >> 1;
   const int csp = im.csp;
@@ -549,7 +549,7 @@ VP8_PFN void emit_rgb_quad(const ImgDesc& im, const uint8_t* yplane, const uint8
   const uint8_t* yrow = yplane + (size_t)j * ys;
   const uint8_t* un = uplane + (size_t)rn * uvs; const uint8_t* uf = uplane + (size_t)rf * uvs;
   const uint8_t* vn = vplane + (size_t)rn * uvs; const uint8_t* vf = vplane + (size_t)rf * uvs;
-  uint8_t* orow = out + (size_t)j * im.out_stride;
+  uint8_t* orow = out + (size_t)((im.flags & VP8B_FLAG_FLIP) ? h - 1 - j : j) * im.out_stride;
   const int i0 = 4 * q;
   const int n = (w - i0 < 4) ? w - i0 : 4;
   const int bpp = (csp == 0 || csp == 2) ? 3 : 4;
@@ -561,7 +561,7 @@ VP8_PFN void emit_rgb_quad(const ImgDesc& im, const uint8_t* yplane, const uint8
     else { u = un[i >> 1]; v = vn[i >> 1]; }
     yuv_to_rgb(yrow[i], u, v, &r, &g, &b);
     if (bpp == 4) {
-      px[k] = pack_pixel4(csp, r, g, b, alpha ? (int)alpha[(size_t)j * w + i] : 0xff);
+      px[k] = pack_pixel4(csp, r, g, b, alpha ? (int)alpha[(size_t)j * im.width + i] : 0xff);
     } else {
       uint8_t* o = orow + 3 * i;
       if (csp == 0) { o[0] = (uint8_t)r; o[1] = (uint8_t)g; o[2] = (uint8_t)b; }
@@ -626,14 +626,14 @@ VP8_UNROLL
 }
 
 // Which images take the fast path (host driver and kernel must agree on the work-item count).
-VP8_PFN int emit_uses_pairs(int csp, int flags) {
-  return !(flags & VP8B_FLAG_NO_FANCY) && (csp == 1 || csp == 3 || csp == 4 || csp == 7 || csp == 8 || csp == 9);
+VP8_PFN int emit_uses_pairs(int csp, int flags, int crop_x) {   // crop_x: the word loads need the window 8-pixel aligned
+  return !(flags & VP8B_FLAG_NO_FANCY) && (crop_x & 7) == 0 && (csp == 1 || csp == 3 || csp == 4 || csp == 7 || csp == 8 || csp == 9);
 }
 
 // Pixels 8q..8q+7 of output rows 2t-1 and 2t.
 VP8_PFN void emit_rgba_pair8(const ImgDesc& im, const uint8_t* yplane, const uint8_t* uplane, const uint8_t* vplane,
-                             const uint8_t* alpha /* w x h plane or NULL */, uint8_t* out, int q, int t) {
-  const int w = im.width, h = im.height;
+                             const uint8_t* alpha /* window origin inside the frame-wide plane, or NULL */, uint8_t* out, int q, int t) {
+  const int w = im.out_w, h = im.out_h;
   const int ys = 16 * im.mb_w, uvs = 8 * im.mb_w;
   const int uvw = (w + 1) >> 1, uvh = (h + 1) >> 1;
   const int csp = im.csp;
@@ -657,10 +657,10 @@ VP8_UNROLL
 VP8_UNROLL
     for (int k = 0; k < 8; ++k) {
       const int y = (int)(((k < 4 ? yw.x : yw.y) >> (8 * (k & 3))) & 0xff);
-      const int a = (alpha != 0 && k < n) ? (int)alpha[(size_t)j * w + i0 + k] : 0xff;
+      const int a = (alpha != 0 && k < n) ? (int)alpha[(size_t)j * im.width + i0 + k] : 0xff;
       px[k] = yuv_to_px4(csp, y, u8[k], v8[k], a);
     }
-    uint8_t* o = out + (size_t)j * im.out_stride + 4 * (size_t)i0;
+    uint8_t* o = out + (size_t)((im.flags & VP8B_FLAG_FLIP) ? h - 1 - j : j) * im.out_stride + 4 * (size_t)i0;
     if (n == 8 && (((uintptr_t)o) & 15) == 0) {
       uint4 a, b;
       a.x = px[0]; a.y = px[1]; a.z = px[2]; a.w = px[3];
@@ -682,14 +682,15 @@ VP8_UNROLL
 // ((w+1)/2 x (h+1)/2). Output = y | u | v at out_off with strides out_stride / (w+1)/2.
 VP8_PFN void emit_yuv_chunk(const ImgDesc& im, const uint8_t* yplane, const uint8_t* uplane, const uint8_t* vplane,
                             uint8_t* out, int plane, int q, int j) {
-  const int w = im.width, h = im.height;
+  const int w = im.out_w, h = im.out_h;
   const int uvw = (w + 1) >> 1, uvh = (h + 1) >> 1;
   const int pw = plane ? uvw : w;
+  const int jd = (im.flags & VP8B_FLAG_FLIP) ? (plane ? uvh : h) - 1 - j : j;   // destination row
   const int sstride = plane ? 8 * im.mb_w : 16 * im.mb_w;
   const int dstride = plane ? uvw : im.out_stride;
   const uint8_t* src = (plane == 0 ? yplane : plane == 1 ? uplane : vplane) + (size_t)j * sstride + 16 * q;
   uint8_t* dst = out + (plane == 0 ? 0 : (size_t)im.out_stride * h + (plane == 2 ? (size_t)uvw * uvh : 0)) +
-                 (size_t)j * dstride + 16 * q;
+                 (size_t)jd * dstride + 16 * q;
   const int n = (pw - 16 * q < 16) ? pw - 16 * q : 16;
   if (n == 16 && ((((uintptr_t)dst) | ((uintptr_t)src)) & 15) == 0) {
     *(uint4*)dst = *(const uint4*)src;

@@ -370,9 +370,9 @@ TK_FN void tk_mb_finish(TokLane& L, const TokShared& sh, const ImgDesc& im, int 
 
 // Starts the next macroblock of this lane's partition, or finishes the lane. Returns without doing anything
 // when the partition owning the row above has not got far enough yet (the caller simply retries).
-TK_FN void tk_mb_start(TokLane& L, const TokShared& sh, const ImgDesc& im, int P, uint32_t* mbinfo) {
+TK_FN void tk_mb_start(TokLane& L, const TokShared& sh, const ImgDesc& im, int rows, int P, uint32_t* mbinfo) {
   const int mb_w = im.mb_w;
-  if (L.my >= im.mb_h) { tk_lane_finish(L); return; }
+  if (L.my >= rows) { tk_lane_finish(L); return; }
   uint32_t tctx = 0;
   if (L.my > 0) {
     if (P > 1) {
@@ -388,7 +388,7 @@ TK_FN void tk_mb_start(TokLane& L, const TokShared& sh, const ImgDesc& im, int P
   {   // fetch the flags of this partition's next macroblock now; they are needed one macroblock from here
     int nx = L.mx + 1, ny = L.my;
     if (nx == mb_w) { nx = 0; ny += P; }
-    if (ny < im.mb_h) L.w_next = tk_ldg_u32(mbinfo + 4 * ((size_t)ny * mb_w + nx) + 3);
+    if (ny < rows) L.w_next = tk_ldg_u32(mbinfo + 4 * ((size_t)ny * mb_w + nx) + 3);
   }
   L.seg = (int)((L.w >> MBW_SEG_SHIFT) & 3);
   L.tnz = tctx;

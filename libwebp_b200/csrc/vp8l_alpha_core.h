@@ -414,7 +414,8 @@ struct AlphaHdr {
   uint8_t huff_bits;        // meta-Huffman precision, 0 = one group
   uint8_t ttype[4];         // transform types
   uint8_t tbits[4];         // tile bits (predictor, cross colour) or bundling bits (colour indexing)
-  uint8_t pad[3];
+  uint8_t use_8b;           // set by the pixel pass: the reference would have taken its 8-bit path (DecodeAlphaData)
+  uint8_t pad[2];
   int32_t txsize[4];        // image width the transform applies to
   uint32_t tdata[4];        // word offset of the transform's tile image inside the transform-data area
   int32_t xsize;            // width of the coded image (after bundling)
@@ -442,7 +443,7 @@ struct AlphaHdr {
 AL_NOINLINE void alph_parse_header(const uint8_t* alph, uint32_t alph_size, int w, int h, uint8_t* scratch, uint16_t* meta,
                                    uint32_t* tdata, AlphaHdr* hd) {
   hd->status = AL_OUT_OF_MEMORY;   // every failure in here is a header failure (see the top of this file)
-  hd->method = 0; hd->filter = 0; hd->ntrans = 0; hd->cache_bits = 0; hd->huff_bits = 0;
+  hd->method = 0; hd->filter = 0; hd->ntrans = 0; hd->cache_bits = 0; hd->huff_bits = 0; hd->use_8b = 0;
   hd->xsize = w; hd->huff_xsize = 0; hd->num_groups = 1; hd->group_entries = AL_GROUP_ENTRIES(0);
   hd->br_val = 0; hd->br_pos = 0; hd->br_bit_pos = 0;
   if (alph_size <= 1) return;
@@ -524,8 +525,10 @@ AL_NOINLINE void alph_parse_header(const uint8_t* alph, uint32_t alph_size, int 
 }
 
 // Pass B. tables = num_groups * group_entries words, groups = num_groups AlGroup, scratch as in pass A (its
-// colour-cache area and AlScratch are reused), out = xsize * h ARGB words. Returns the image status.
-AL_NOINLINE int alph_decode_pixels(const uint8_t* alph, uint32_t alph_size, int h, const AlphaHdr* hd, const uint16_t* meta,
+// colour-cache area and AlScratch are reused), out = xsize * h ARGB words. last_row = rows the caller needs (the
+// bottom of the crop window, h without cropping): like the reference, decoding stops there, so data missing further
+// down is never noticed. Returns the image status.
+AL_NOINLINE int alph_decode_pixels(const uint8_t* alph, uint32_t alph_size, int h, int last_row, AlphaHdr* hd, const uint16_t* meta,
                                    uint32_t* tables, AlGroup* groups, uint8_t* scratch, uint32_t* out) {
   uint32_t* cache = (uint32_t*)scratch + AL_SUB_TABLE_ENTRIES;
   AlScratch* sc = (AlScratch*)(cache + (1 << AL_MAX_CACHE_BITS) + 256);
@@ -542,10 +545,11 @@ AL_NOINLINE int alph_decode_pixels(const uint8_t* alph, uint32_t alph_size, int 
   // so keep both shapes.
   int use_8b = (hd->ntrans == 1 && hd->ttype[0] == AL_T_COLOR_INDEXING && cache_bits == 0);
   for (int g = 0; g < num_groups && use_8b; ++g) use_8b = groups[g].trivial_literal;
+  hd->use_8b = (uint8_t)use_8b;
   const int cache_size = cache_bits ? (1 << cache_bits) : 0, cache_shift = 32 - cache_bits;
   for (int i = 0; i < cache_size; ++i) cache[i] = 0;
   const int width = hd->xsize;
-  const int end = width * h;
+  const int end = width * h, last = width * (last_row < h ? last_row : h);
   const int mask = hd->huff_bits ? (1 << hd->huff_bits) - 1 : -1;
   const int hbits = hd->huff_bits, hxs = hd->huff_xsize;
   const int len_code_limit = AL_NUM_LITERAL + AL_NUM_LENGTH;
@@ -553,7 +557,7 @@ AL_NOINLINE int alph_decode_pixels(const uint8_t* alph, uint32_t alph_size, int 
   int ok = 1;
   const AlGroup* grp = &groups[hbits ? meta[0] : 0];
   const uint32_t* gt = tables + (size_t)(grp - groups) * stride;
-  while (pos < end && !(use_8b && b.eos)) {
+  while (pos < last && !(use_8b && b.eos)) {
     if ((col & mask) == 0) {
       grp = &groups[hbits ? meta[hxs * (row >> hbits) + (col >> hbits)] : 0];
       gt = tables + (size_t)(grp - groups) * stride;
@@ -603,7 +607,7 @@ AL_NOINLINE int alph_decode_pixels(const uint8_t* alph, uint32_t alph_size, int 
       pos += length;
       col += length;
       while (col >= width) { col -= width; ++row; }
-      if (pos < end && (col & mask)) {
+      if (pos < last && (col & mask)) {
         grp = &groups[hbits ? meta[hxs * (row >> hbits) + (col >> hbits)] : 0];
         gt = tables + (size_t)(grp - groups) * stride;
       }
@@ -720,8 +724,11 @@ AL_FN int al_color_delta(int8_t pred, int8_t color) { return ((int)pred * (int)c
 //   vertical   : out[y][x] = in[y][x] + out[y-1][x], row 0 as horizontal                 -> row 0 first, then columns in parallel
 //   gradient   : out[y][x] = in[y][x] + clip(left + top - topleft), row 0 as horizontal  -> skewed wavefront, one row per
 //                thread, row y one column behind row y-1
+// crop_top: first row of the output window. The reference's 8-bit path only unfilters from there when the filter
+// is horizontal (ExtractPalettedAlphaRows, vp8l_dec.c:887-912), i.e. the window's first row is predicted from
+// nothing instead of from the row above; reproduce that.
 AL_FN void alph_finish(const AlphaHdr* hd, const uint8_t* raw /* method 0 */, uint32_t* px /* method 1 */, const uint32_t* tdata,
-                       int w, int h, uint8_t* plane, int tid, int nt) {
+                       int w, int h, int crop_top, uint8_t* plane, int tid, int nt) {
   const size_t total = (size_t)w * (size_t)h;
   if (hd->method == 0) {
     for (size_t i = (size_t)tid; i < total; i += (size_t)nt) plane[i] = raw[i];
@@ -772,7 +779,8 @@ AL_FN void alph_finish(const AlphaHdr* hd, const uint8_t* raw /* method 0 */, ui
   const int filter = hd->filter;
   if (filter == 0) return;
   if (filter == 1) {
-    if (tid == 0) for (int y = 1; y < h; ++y) plane[(size_t)y * w] = (uint8_t)(plane[(size_t)y * w] + plane[(size_t)(y - 1) * w]);
+    const int y_first = (hd->method == 1 && hd->use_8b) ? crop_top : 0;
+    if (tid == 0) for (int y = y_first + 1; y < h; ++y) plane[(size_t)y * w] = (uint8_t)(plane[(size_t)y * w] + plane[(size_t)(y - 1) * w]);
     AL_BLOCK_SYNC();
     for (int y = tid; y < h; y += nt) {
       uint8_t* row = plane + (size_t)y * w;

@@ -74,6 +74,8 @@ def lib():
                                          C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.reft_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
         L.reft_features.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int)]
+        if hasattr(L, "reft_decode_window"):
+            L.reft_decode_window.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_size_t]
         L.reft_decode_bench.restype = C.c_double
         L.reft_decode_bench.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
@@ -145,6 +147,21 @@ def decode(data, csp=MODE_RGBA, flags=0, simd=True, stride=None):
         st = L.reft_decode(data, len(data), csp, flags, out.ctypes.data, out.size, stride)
     L.reft_set_simd(1)
     return st, (out if st == 0 else None)
+
+
+def decode_window(data, csp=MODE_RGBA, flags=0, crop=None):
+    """Reference WebPDecode with options.use_cropping (crop = (left, top, width, height)) and/or FLAG_FLIP, into a
+    tight buffer of the output size. Returns (status, flat ndarray or None)."""
+    L = lib()
+    st, f = features(data)
+    w, h = (crop[2], crop[3]) if crop else (f["width"], f["height"])
+    if st != 0 or w <= 0 or h <= 0:
+        w = h = 4
+    n = (w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2)) if csp == MODE_YUV else w * h * BPP[csp]
+    out = np.zeros(max(n, 16), np.uint8)
+    c4 = (C.c_int * 4)(*(crop if crop else (0, 0, 0, 0)))
+    st = L.reft_decode_window(data, len(data), csp, flags, c4, out.ctypes.data, out.size)
+    return st, (out[:n] if st == 0 else None)
 
 
 def decode_bench(datas, nthreads, csp=MODE_RGBA, passes=1, simd=True):

@@ -22,8 +22,22 @@
 // variant bit 0: visit the macroblocks of a wavefront step in reverse order
 // variant bit 1: token parse with the row-at-a-time reference port (parse_token_row) instead of the lane FSM
 // variant bit 2: lane FSM with a lazy ring producer
+static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags, uint8_t* out, size_t out_size,
+                           int stride, int variant, uint8_t* unfiltered, int crop_x, int crop_y, int crop_w, int crop_h);
+
 extern "C" int emu_decode(const uint8_t* data, size_t size, int csp, int flags, uint8_t* out, size_t out_size,
                           int stride, int variant, uint8_t* unfiltered /* optional: y|u|v padded */) {
+  return emu_decode_crop(data, size, csp, flags, out, out_size, stride, variant, unfiltered, 0, 0, 0, 0);
+}
+
+// crop_w == 0: no cropping. flags bit 2 = flip. `stride` and `out` describe the (cropped) output.
+extern "C" int emu_decode_window(const uint8_t* data, size_t size, int csp, int flags, uint8_t* out, size_t out_size,
+                                 int stride, int crop_x, int crop_y, int crop_w, int crop_h) {
+  return emu_decode_crop(data, size, csp, flags, out, out_size, stride, 0, nullptr, crop_x, crop_y, crop_w, crop_h);
+}
+
+static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags, uint8_t* out, size_t out_size,
+                           int stride, int variant, uint8_t* unfiltered, int crop_x, int crop_y, int crop_w, int crop_h) {
   const int reverse_steps = variant & 1;
   Vp8Container c;
   int st = vp8b_parse_container(data, size, 1, &c);
@@ -42,6 +56,8 @@ extern "C" int emu_decode(const uint8_t* data, size_t size, int csp, int flags, 
   im.width = (uint16_t)c.width; im.height = (uint16_t)c.height;
   im.mb_w = (uint16_t)((c.width + 15) >> 4); im.mb_h = (uint16_t)((c.height + 15) >> 4);
   im.csp = (uint8_t)csp; im.flags = (uint8_t)flags; im.out_stride = stride;
+  im.out_w = im.width; im.out_h = im.height;
+  if (crop_w > 0) { im.crop_x = (uint16_t)(crop_x & ~1); im.crop_y = (uint16_t)(crop_y & ~1); im.out_w = (uint16_t)crop_w; im.out_h = (uint16_t)crop_h; }
   im.num_parts = (uint8_t)vp8b_prescan_partitions(data + c.frame_offset + 10, c.part0_size);
   const int mb_w = im.mb_w, mb_h = im.mb_h;
   const size_t nmb = (size_t)mb_w * mb_h;
@@ -63,6 +79,7 @@ extern "C" int emu_decode(const uint8_t* data, size_t size, int csp, int flags, 
   }
   if (hdr.status != VP8B_OK) return hdr.status;
   if (hdr.num_parts != im.num_parts) return -100;   // host pre-scan disagrees with the device parse
+  const int rows = hdr.rows;   // macroblock rows that get decoded (all of them unless cropping)
 
   // K2: tokens
   if (!(variant & 2)) {   // lane FSM: one lane per partition, lanes advanced round-robin one iteration at a time
@@ -85,14 +102,14 @@ extern "C" int emu_decode(const uint8_t* data, size_t size, int csp, int flags, 
     uint8_t* rings = (uint8_t*)(((uintptr_t)ringmem.data() + 15) & ~(uintptr_t)15);
     std::vector<TokStreamCtl> ctl(P);
     for (int p = 0; p < P; ++p) {
-      if (p >= mb_h) { ctl[p].rd_w = TK_STREAM_DONE; ctl[p].filled_c = 0; continue; }
+      if (p >= rows) { ctl[p].rd_w = TK_STREAM_DONE; ctl[p].filled_c = 0; continue; }
       const uint64_t a = tk_stream_start(frame_off, &hdr, p);
       for (int k = 0; k < TK_RING_CHUNKS; ++k) tk_stream_prefill(tk_saddr_of(rings + (size_t)p * TK_RING_BYTES), arena16, a, k);
       tk_stream_open(&ctl[p], a);
       tk_lane_init(lanes[p], tk_saddr_of(rings + (size_t)p * TK_RING_BYTES), tk_saddr_of(&ctl[p]), frame_off, &hdr, p,
-                   mbinfo.data(), mb_w, mb_h);
+                   mbinfo.data(), mb_w, rows);
     }
-    for (int p = mb_h; p < P; ++p) lanes[p].phase = 2;
+    for (int p = rows; p < P; ++p) lanes[p].phase = 2;
     const long topup_every = (variant & 4) ? 3000 : 40;   // variant bit 2: a lazy producer (readers find the ring dry)
     long iter = 0;
     for (bool any = true; any;) {
@@ -107,11 +124,11 @@ extern "C" int emu_decode(const uint8_t* data, size_t size, int csp, int flags, 
         TokLane& L = lanes[p];
         if (L.phase == 2) continue;
         any = true;
-        if (L.phase == 0) tk_mb_start(L, sh, im, P, mbinfo.data());
+        if (L.phase == 0) tk_mb_start(L, sh, im, rows, P, mbinfo.data());
         if (L.phase == 1) tk_step(L, sh, im, P, mbinfo.data(), coeffs.data());
       }
     }
-    for (int p = 0; p < P && p < mb_h; ++p) if (lanes[p].status != VP8B_OK) hdr.status = lanes[p].status;
+    for (int p = 0; p < P && p < rows; ++p) if (lanes[p].status != VP8B_OK) hdr.status = lanes[p].status;
   } else {   // rows interleaved over the partitions in dependency order
     const int P = hdr.num_parts;
     std::vector<TokenPart> tp(P);
@@ -120,10 +137,10 @@ extern "C" int emu_decode(const uint8_t* data, size_t size, int csp, int flags, 
     std::vector<uint16_t> topctx((size_t)(P + 1) * mb_w, 0);
     std::vector<int> progress(P, 0);
     for (int p = 0; p < P; ++p) token_part_init(tp[p], frame, &hdr, p);
-    for (int my = 0; my < mb_h; ++my) {
+    for (int my = 0; my < rows; ++my) {
       parse_token_row(tp[my % P], im, &hdr, my % P, my, posprob.data(), topctx.data(), progress.data(), mbinfo.data(), coeffs.data());
     }
-    for (int p = 0; p < P && p < mb_h; ++p) if (tp[p].status != VP8B_OK) hdr.status = tp[p].status;
+    for (int p = 0; p < P && p < rows; ++p) if (tp[p].status != VP8B_OK) hdr.status = tp[p].status;
   }
   if (hdr.status != VP8B_OK) return hdr.status;
 
@@ -133,10 +150,10 @@ extern "C" int emu_decode(const uint8_t* data, size_t size, int csp, int flags, 
     std::vector<uint8_t> ctxmem(recon_ctx_bytes(mb_w, mb_h) + 64, 0);
     ReconCtx cx;
     recon_ctx_bind(cx, ctxmem.data(), mb_w, mb_h);
-    const int steps = mb_w + 2 * (mb_h - 1);
+    const int steps = mb_w + 2 * (rows - 1);
     for (int d = 0; d < steps; ++d) {
-      for (int k = 0; k < mb_h; ++k) {
-        const int my = reverse_steps ? mb_h - 1 - k : k;
+      for (int k = 0; k < rows; ++k) {
+        const int my = reverse_steps ? rows - 1 - k : k;
         const int mx = d - 2 * my;
         if (mx < 0 || mx >= mb_w) continue;
         const size_t idx = (size_t)my * mb_w + mx;
@@ -150,10 +167,10 @@ extern "C" int emu_decode(const uint8_t* data, size_t size, int csp, int flags, 
   // K4: loop-filter wavefront
   if (hdr.filter_type > 0) {
     FilterWs ws;
-    const int steps = mb_w + 2 * (mb_h - 1);
+    const int steps = mb_w + 2 * (rows - 1);
     for (int d = 0; d < steps; ++d) {
-      for (int k = 0; k < mb_h; ++k) {
-        const int my = reverse_steps ? mb_h - 1 - k : k;
+      for (int k = 0; k < rows; ++k) {
+        const int my = reverse_steps ? rows - 1 - k : k;
         const int mx = d - 2 * my;
         if (mx < 0 || mx >= mb_w) continue;
         const uint32_t w = mbinfo[4 * ((size_t)my * mb_w + mx) + 3];
@@ -180,29 +197,33 @@ extern "C" int emu_decode(const uint8_t* data, size_t size, int csp, int flags, 
       std::vector<uint32_t> tables((size_t)ah.num_groups * ah.group_entries);
       std::vector<AlGroup> groups(ah.num_groups);
       coded.assign((size_t)ah.xsize * im.height + 4, 0);
-      ah.status = alph_decode_pixels(alph, alph_size, im.height, &ah, (const uint16_t*)meta.data(), tables.data(), groups.data(),
+      ah.status = alph_decode_pixels(alph, alph_size, im.height, (int)im.crop_y + (int)im.out_h, &ah, (const uint16_t*)meta.data(), tables.data(), groups.data(),
                                      sc16, coded.data());
     }
     if (ah.status != AL_OK) return ah.status;
     alpha_plane.assign((size_t)im.width * im.height, 0);
-    alph_finish(&ah, alph + 1, coded.data(), tdata.data(), im.width, im.height, alpha_plane.data(), 0, 1);
+    alph_finish(&ah, alph + 1, coded.data(), tdata.data(), im.width, im.height, im.crop_y, alpha_plane.data(), 0, 1);
     alpha = alpha_plane.data();
   }
 
-  // K5: output
-  const int w = im.width, h = im.height;
+  // K5: output (window re-based like k_emit)
+  const int w = im.out_w, h = im.out_h;
+  const uint8_t* wy = yp + (size_t)im.crop_y * (16 * mb_w) + im.crop_x;
+  const uint8_t* wu = up + (size_t)(im.crop_y >> 1) * (8 * mb_w) + (im.crop_x >> 1);
+  const uint8_t* wv = vp + (size_t)(im.crop_y >> 1) * (8 * mb_w) + (im.crop_x >> 1);
+  if (alpha) alpha += (size_t)im.crop_y * im.width + im.crop_x;
   if (csp == MODE_YUV) {
     const int uvw = (w + 1) / 2, uvh = (h + 1) / 2;
     if (out_size < (size_t)w * h + 2 * (size_t)uvw * uvh) return VP8_STATUS_INVALID_PARAM;
     im.out_stride = w;
     for (int plane = 0; plane < 3; ++plane) {
       const int pw = plane ? uvw : w, ph = plane ? uvh : h;
-      for (int j = 0; j < ph; ++j) for (int q = 0; q < (pw + 15) / 16; ++q) emit_yuv_chunk(im, yp, up, vp, out, plane, q, j);
+      for (int j = 0; j < ph; ++j) for (int q = 0; q < (pw + 15) / 16; ++q) emit_yuv_chunk(im, wy, wu, wv, out, plane, q, j);
     }
-  } else if (emit_uses_pairs(csp, flags)) {
-    for (int t = 0; t <= h / 2; ++t) for (int q = 0; q < (w + 7) / 8; ++q) emit_rgba_pair8(im, yp, up, vp, alpha, out, q, t);
+  } else if (emit_uses_pairs(csp, flags, im.crop_x)) {
+    for (int t = 0; t <= h / 2; ++t) for (int q = 0; q < (w + 7) / 8; ++q) emit_rgba_pair8(im, wy, wu, wv, alpha, out, q, t);
   } else {
-    for (int j = 0; j < h; ++j) for (int q = 0; q < (w + 3) / 4; ++q) emit_rgb_quad(im, yp, up, vp, alpha, out, q, j);
+    for (int j = 0; j < h; ++j) for (int q = 0; q < (w + 3) / 4; ++q) emit_rgb_quad(im, wy, wu, wv, alpha, out, q, j);
   }
   return VP8_STATUS_OK;
 }

@@ -84,10 +84,12 @@ def test_host_side_failures_need_no_gpu(product, port, manifest):
     L.WebPInitDecoderConfigInternal(C.byref(cfg), 0x0209)
     cfg.output.colorspace = 13
     assert L.WebPDecode(d, len(d), C.byref(cfg)) == product.VP8_STATUS_INVALID_PARAM
-    for field in ("use_cropping", "use_scaling", "flip"):
-        L.WebPInitDecoderConfigInternal(C.byref(cfg), 0x0209)
-        setattr(cfg.options, field, 1)
-        assert L.WebPDecode(d, len(d), C.byref(cfg)) == product.VP8_STATUS_UNSUPPORTED_FEATURE
+    L.WebPInitDecoderConfigInternal(C.byref(cfg), 0x0209)
+    cfg.options.use_scaling = 1            # the rescaler is not on the device: refused, never decoded on the host
+    assert L.WebPDecode(d, len(d), C.byref(cfg)) == product.VP8_STATUS_UNSUPPORTED_FEATURE
+    L.WebPInitDecoderConfigInternal(C.byref(cfg), 0x0209)
+    cfg.options.use_cropping = 1           # an empty crop window is an invalid parameter (buffer_dec.c:184-195)
+    assert L.WebPDecode(d, len(d), C.byref(cfg)) == product.VP8_STATUS_INVALID_PARAM
     L.WebPInitDecoderConfigInternal(C.byref(cfg), 0x0209)
     cfg.output.colorspace = product.MODE_RGB_565
     assert L.WebPDecode(d, len(d), C.byref(cfg)) == product.VP8_STATUS_UNSUPPORTED_FEATURE

@@ -244,3 +244,33 @@ def test_incremental_api(W, port, manifest, amanifest):
         L.WebPIDelete(idec)
         L.WebPFreeDecBuffer(C.byref(buf))
         assert np.array_equal(got[:, :w * 4], want[:, :w * 4])
+
+
+def test_crop_and_flip(W, ref, manifest, amanifest):
+    """options.use_cropping / options.flip through the C ABI against the reference (see tests/test_emu.py for the rules)."""
+    rng = np.random.default_rng(21)
+    for e in list(manifest) + list(amanifest):
+        Wd, Hd = e["features"]["width"], e["features"]["height"]
+        for it in range(3):
+            crop = None
+            if it > 0:
+                cw, ch = int(rng.integers(1, Wd + 1)), int(rng.integers(1, Hd + 1))
+                crop = (int(rng.integers(0, Wd - cw + 1)), int(rng.integers(0, Hd - ch + 1)), cw, ch)
+            flip = bool(rng.integers(0, 2))
+            for csp in (W.MODE_RGBA, W.MODE_rgbA, W.MODE_BGR, W.MODE_YUV):
+                s_ref, want = ref.decode_window(e["data"], csp, 8 if flip else 0, crop)
+                st, got = W.WebPDecode(e["data"], csp, crop=crop, flip=flip)
+                assert st == s_ref, (e["file"], crop, flip, csp, st, s_ref)
+                if s_ref == 0:
+                    assert np.array_equal(want, got.reshape(-1)), (e["file"], crop, flip, csp)
+    data = manifest[1]["data"]
+    for crop in ((300, 0, 40, 10), (0, 0, 0, 10), (0, 199, 10, 3)):
+        st, _ = W.WebPDecode(data, W.MODE_RGBA, crop=crop)
+        assert st == W.VP8_STATUS_INVALID_PARAM
+    cut = data[: len(data) * 2 // 3]
+    for crop in ((0, 0, 320, 32), (0, 120, 320, 80)):
+        s_ref, want = ref.decode_window(cut, W.MODE_RGBA, 0, crop)
+        st, got = W.WebPDecode(cut, W.MODE_RGBA, crop=crop)
+        assert st == s_ref
+        if s_ref == 0:
+            assert np.array_equal(want, got.reshape(-1))
