@@ -500,23 +500,57 @@ VP8_FN void parse_token_row(TokenPart& tp, const ImgDesc& im, const FrameHdr* h,
     uint32_t nzy = 0, nzuv = 0;
     const uint32_t is_i4 = (w >> 16) & 1u;   // MBW_I4X4
     if (!(use_skip && (w & MBW_SKIP))) {
-      for (int seq = (int)is_i4; seq < 25; ++seq) {
-        const uint32_t sq = kBlockSeq[seq];
-        const uint32_t tb = sq & 15u, lb = (sq >> 4) & 15u;
-        const uint32_t i4_luma = (sq >> 14) & is_i4;          // luma block of an i4x4 macroblock
-        const uint32_t first = ((sq >> 14) & 1u) ^ i4_luma;   // luma block of an i16 macroblock: starts at coefficient 1
-        const uint32_t type = i4_luma ? 3u : ((sq >> 15) & 3u);
-        const int ctx = (int)(((tctx >> tb) & 1u) + ((lctx >> lb) & 1u));
-        const int nz = parse_block(d, probs + type * (uint32_t)VP8B_POSPROB_TYPE, ctx, (int)first, dst + 16 * ((sq >> 19) & 31u));
-        const uint32_t l = (nz > (int)first) ? 1u : 0u;
-        // nz code; a lone DC level counts as "DC only" here and is re-examined after dequantisation (recon_macroblock)
-        const uint32_t code = ((nz > 3) ? 3u : (nz > 1) ? 2u : l) << ((sq >> 8) & 31u);
-        if (sq & SQ_LUMA) nzy |= code;
-        if (sq & SQ_CHROMA) nzuv |= code;
-        if (seq == 0 && nz > 0) w |= MBW_HAS_Y2;
-        tctx = (tctx & ~(1u << tb)) | (l << tb);
-        lctx = (lctx & ~(1u << lb)) | (l << lb);
+      // Contexts as shift registers, like ParseResiduals (vp8_dec.c:517-609): the bit of the next block sits in bit 0.
+      const uint8_t* yprobs = probs + 3 * VP8B_POSPROB_TYPE;   // luma with DC (i4x4 macroblocks)
+      int first = 0;
+      if (!is_i4) {   // Y2 block: the 16 luma DCs; the luma blocks then start at coefficient 1 with the type-0 tables
+        const int ctx = (int)(((tctx >> 8) & 1u) + ((lctx >> 8) & 1u));
+        const int nz = parse_block(d, probs + 1 * VP8B_POSPROB_TYPE, ctx, 0, dst + 24 * 16);
+        const uint32_t f = (nz > 0) ? 0x100u : 0u;
+        tctx = (tctx & 0xffu) | f;
+        lctx = (lctx & 0xffu) | f;
+        if (nz > 0) w |= MBW_HAS_Y2;
+        first = 1;
+        yprobs = probs;
       }
+      int16_t* out = dst;
+      uint32_t tnz = tctx & 0x0f, lnz = lctx & 0x0f;
+      for (int y = 0; y < 4; ++y) {
+        uint32_t l = lnz & 1;
+        for (int x = 0; x < 4; ++x) {
+          const int nz = parse_block(d, yprobs, (int)(l + (tnz & 1)), first, out);
+          l = (nz > first);
+          tnz = (tnz >> 1) | (l << 7);
+          // nz code; a lone DC level counts as "DC only" here and is re-examined after dequantisation (recon_macroblock)
+          nzy = (nzy << 2) | (uint32_t)((nz > 3) ? 3 : (nz > 1) ? 2 : (int)l);
+          out += 16;
+        }
+        tnz >>= 4;
+        lnz = (lnz >> 1) | (l << 7);
+      }
+      uint32_t out_t = tnz, out_l = lnz >> 4;
+      for (int ch = 0; ch < 4; ch += 2) {   // U then V: 2x2 blocks each
+        uint32_t acc = 0;
+        tnz = (tctx >> (4 + ch)) & 0x0f;
+        lnz = (lctx >> (4 + ch)) & 0x0f;
+        for (int y = 0; y < 2; ++y) {
+          uint32_t l = lnz & 1;
+          for (int x = 0; x < 2; ++x) {
+            const int nz = parse_block(d, probs + 2 * VP8B_POSPROB_TYPE, (int)(l + (tnz & 1)), 0, out);
+            l = (nz > 0);
+            tnz = ((tnz >> 1) | (l << 3)) & 0xff;
+            acc = (acc << 2) | (uint32_t)((nz > 3) ? 3 : (nz > 1) ? 2 : (int)l);
+            out += 16;
+          }
+          tnz >>= 2;
+          lnz = ((lnz >> 1) | (l << 5)) & 0xff;
+        }
+        nzuv |= acc << (4 * ch);
+        out_t |= ((tnz << 4) << ch) & 0xff;
+        out_l |= ((lnz & 0xf0) << ch) & 0xff;
+      }
+      tctx = (tctx & 0x100u) | (out_t & 0xff);
+      lctx = (lctx & 0x100u) | (out_l & 0xff);
     } else {
       tctx &= is_i4 ? 0x100u : 0u;
       lctx &= is_i4 ? 0x100u : 0u;
