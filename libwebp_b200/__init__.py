@@ -20,7 +20,8 @@ LIB_PATH = os.path.join(_HERE, "libwebpdecoder_b200.so")
 # WEBP_CSP_MODE (include/webp/decode.h)
 MODE_RGB, MODE_RGBA, MODE_BGR, MODE_BGRA, MODE_ARGB, MODE_RGBA_4444, MODE_RGB_565 = 0, 1, 2, 3, 4, 5, 6
 MODE_rgbA, MODE_bgrA, MODE_Argb, MODE_rgbA_4444, MODE_YUV, MODE_YUVA = 7, 8, 9, 10, 11, 12
-BPP = {MODE_RGB: 3, MODE_RGBA: 4, MODE_BGR: 3, MODE_BGRA: 4, MODE_ARGB: 4, MODE_rgbA: 4, MODE_bgrA: 4, MODE_Argb: 4}
+BPP = {MODE_RGB: 3, MODE_RGBA: 4, MODE_BGR: 3, MODE_BGRA: 4, MODE_ARGB: 4, MODE_RGBA_4444: 2, MODE_RGB_565: 2,
+       MODE_rgbA: 4, MODE_bgrA: 4, MODE_Argb: 4, MODE_rgbA_4444: 2}
 
 # VP8StatusCode
 (VP8_STATUS_OK, VP8_STATUS_OUT_OF_MEMORY, VP8_STATUS_INVALID_PARAM, VP8_STATUS_BITSTREAM_ERROR,
@@ -171,12 +172,15 @@ def _new_config(csp, bypass_filtering, no_fancy_upsampling, dithering_strength=0
 def _attach_external(cfg, csp, w, h, buf_addr, stride):
     """Point cfg.output at caller memory starting at buf_addr; returns the number of bytes it spans."""
     cfg.output.is_external_memory = 1
-    if csp == MODE_YUV:
+    if csp in (MODE_YUV, MODE_YUVA):
         uvw, uvh = (w + 1) // 2, (h + 1) // 2
         y = cfg.output.u.YUVA
         y.y, y.y_stride, y.y_size = buf_addr, w, w * h
         y.u, y.u_stride, y.u_size = buf_addr + w * h, uvw, uvw * uvh
         y.v, y.v_stride, y.v_size = buf_addr + w * h + uvw * uvh, uvw, uvw * uvh
+        if csp == MODE_YUVA:
+            y.a, y.a_stride, y.a_size = buf_addr + w * h + 2 * uvw * uvh, w, w * h
+            return 2 * w * h + 2 * uvw * uvh
         return w * h + 2 * uvw * uvh
     r = cfg.output.u.RGBA
     r.rgba, r.stride, r.size = buf_addr, stride, stride * h
@@ -184,8 +188,8 @@ def _attach_external(cfg, csp, w, h, buf_addr, stride):
 
 
 def out_bytes(csp, w, h, stride=None):
-    if csp == MODE_YUV:
-        return w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2)
+    if csp in (MODE_YUV, MODE_YUVA):
+        return w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2) + (w * h if csp == MODE_YUVA else 0)
     return (stride or w * BPP[csp]) * h
 
 
@@ -202,7 +206,7 @@ def WebPDecode(data, csp=MODE_RGBA, bypass_filtering=False, no_fancy_upsampling=
     if crop is not None and crop[2] > 0 and crop[3] > 0:
         w, h = crop[2], crop[3]
     if external:
-        if csp == MODE_YUV:
+        if csp in (MODE_YUV, MODE_YUVA):
             out = np.zeros(out_bytes(csp, w, h), np.uint8)
         else:
             stride = stride or w * BPP.get(csp, 4)
@@ -213,7 +217,7 @@ def WebPDecode(data, csp=MODE_RGBA, bypass_filtering=False, no_fancy_upsampling=
     st = L.WebPDecode(data, len(data), C.byref(cfg))       # library-allocated output
     if st != VP8_STATUS_OK:
         return st, None
-    if csp == MODE_YUV:
+    if csp in (MODE_YUV, MODE_YUVA):
         out = np.ctypeslib.as_array(C.cast(cfg.output.u.YUVA.y, C.POINTER(C.c_uint8)), (out_bytes(csp, w, h),)).copy()
     else:
         s = cfg.output.u.RGBA.stride
@@ -264,7 +268,7 @@ class Batch:
             st, f = WebPGetFeatures(d)
             w, h = (f["width"], f["height"]) if st == VP8_STATUS_OK else (1, 1)
             self.dims.append((w, h))
-            nb = out_bytes(csp, w, h) if csp in BPP or csp == MODE_YUV else 4 * w * h
+            nb = out_bytes(csp, w, h) if csp in BPP or csp in (MODE_YUV, MODE_YUVA) else 4 * w * h
             out_off.append(out_off[-1] + ((nb + 255) & ~255))
         self.out_off = out_off
         self.output_mode = output
@@ -331,7 +335,7 @@ class Batch:
         """numpy view of image i in the packed host output buffer."""
         w, h = self.dims[i]
         a = self._out_arr[self.out_off[i]:self.out_off[i] + out_bytes(self.csp, w, h)]
-        return a if self.csp == MODE_YUV else a.reshape(h, w * BPP[self.csp])
+        return a if self.csp in (MODE_YUV, MODE_YUVA) else a.reshape(h, w * BPP[self.csp])
 
     def destroy(self):
         if self.handle:

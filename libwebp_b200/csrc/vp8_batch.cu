@@ -151,10 +151,7 @@ static void own_free(DeviceCtx* c, Owned& o) {
 // ---------------------------------------------------------------------------------------------------------
 static const int kBpp[MODE_LAST] = { 3, 4, 3, 4, 4, 2, 2, 4, 4, 4, 2, 1, 1 };   // buffer_dec.c:24-27
 
-static bool csp_supported(int csp) {
-  return csp == MODE_RGB || csp == MODE_RGBA || csp == MODE_BGR || csp == MODE_BGRA || csp == MODE_ARGB ||
-         csp == MODE_rgbA || csp == MODE_bgrA || csp == MODE_Argb || csp == MODE_YUV;
-}
+static bool csp_supported(int csp) { return csp >= MODE_RGB && csp < MODE_LAST; }   // all thirteen of decode.h:150-163
 
 // CheckDecBuffer (buffer_dec.c:41-84) for host output.
 static VP8StatusCode check_host_buffer(const WebPDecBuffer* b) {
@@ -167,6 +164,10 @@ static VP8StatusCode check_host_buffer(const WebPDecBuffer* b) {
     ok &= (ys * (h - 1) + w <= y->y_size) && (us * (uvh - 1) + uvw <= y->u_size) && (vs * (uvh - 1) + uvw <= y->v_size);
     ok &= ((int)ys >= w) && ((int)us >= uvw) && ((int)vs >= uvw);
     ok &= (y->y != NULL) && (y->u != NULL) && (y->v != NULL);
+    if (b->colorspace == MODE_YUVA) {
+      const uint64_t as = (uint64_t)abs(y->a_stride);
+      ok &= (as * (h - 1) + w <= y->a_size) && ((int)as >= w) && (y->a != NULL);
+    }
   } else {
     const WebPRGBABuffer* r = &b->u.RGBA;
     const uint64_t st = (uint64_t)abs(r->stride);
@@ -186,10 +187,11 @@ static VP8StatusCode prepare_host_buffer(int w, int h, WebPDecBuffer* b) {
     if ((uint64_t)w * kBpp[csp] >= (1ull << 31)) return VP8_STATUS_INVALID_PARAM;
     const int stride = w * kBpp[csp];
     const uint64_t size = (uint64_t)stride * h;
-    uint64_t uv_size = 0;
+    uint64_t uv_size = 0, a_size = 0;
     int uv_stride = 0;
     if (!WebPIsRGBMode((WEBP_CSP_MODE)csp)) { uv_stride = (w + 1) / 2; uv_size = (uint64_t)uv_stride * ((h + 1) / 2); }
-    const uint64_t total = size + 2 * uv_size;
+    if (csp == MODE_YUVA) a_size = (uint64_t)w * h;
+    const uint64_t total = size + 2 * uv_size + a_size;
     if (total >= (1ull << 34)) return VP8_STATUS_OUT_OF_MEMORY;   // WEBP_MAX_ALLOCABLE_MEMORY, utils.h:34-41
     uint8_t* mem = (uint8_t*)malloc((size_t)total);
     if (mem == NULL) return VP8_STATUS_OUT_OF_MEMORY;
@@ -199,7 +201,7 @@ static VP8StatusCode prepare_host_buffer(int w, int h, WebPDecBuffer* b) {
       y->y = mem; y->y_stride = stride; y->y_size = (size_t)size;
       y->u = mem + size; y->u_stride = uv_stride; y->u_size = (size_t)uv_size;
       y->v = mem + size + uv_size; y->v_stride = uv_stride; y->v_size = (size_t)uv_size;
-      y->a = NULL; y->a_size = 0; y->a_stride = 0;
+      y->a = (csp == MODE_YUVA) ? mem + size + 2 * uv_size : NULL; y->a_size = (size_t)a_size; y->a_stride = (csp == MODE_YUVA) ? w : 0;
     } else {
       b->u.RGBA.rgba = mem; b->u.RGBA.stride = stride; b->u.RGBA.size = (size_t)size;
     }
@@ -362,9 +364,10 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
       b->aimgs.push_back((int)b->imgs.size());
     }
     size_t bytes;
-    if (d.csp == MODE_YUV) {
+    if (d.csp == MODE_YUV || d.csp == MODE_YUVA) {
       d.out_stride = d.out_w;
-      bytes = (size_t)d.out_w * d.out_h + 2 * (size_t)((d.out_w + 1) / 2) * ((d.out_h + 1) / 2);
+      bytes = (size_t)d.out_w * d.out_h + 2 * (size_t)((d.out_w + 1) / 2) * ((d.out_h + 1) / 2) +
+              (d.csp == MODE_YUVA ? (size_t)d.out_w * d.out_h : 0);
     } else {
       d.out_stride = d.out_w * kBpp[d.csp];
       bytes = (size_t)d.out_stride * d.out_h;
@@ -422,8 +425,8 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
       const ImgDesc& d = b->imgs[k];
       // work items of the output kernel (must match k_emit / emit_uses_pairs in vp8_pixel_core.h)
       const bool pairs = !(d.flags & VP8B_FLAG_NO_FANCY) && (d.crop_x & 7) == 0 && kBpp[d.csp] == 4;
-      const int units = (d.csp == MODE_YUV)
-                            ? ((d.out_w + 15) / 16) * d.out_h + 2 * ((((d.out_w + 1) / 2) + 15) / 16) * ((d.out_h + 1) / 2)
+      const int units = (d.csp == MODE_YUV || d.csp == MODE_YUVA)
+                            ? (d.csp == MODE_YUVA ? 2 : 1) * ((d.out_w + 15) / 16) * d.out_h + 2 * ((((d.out_w + 1) / 2) + 15) / 16) * ((d.out_h + 1) / 2)
                             : pairs ? ((d.out_w + 7) / 8) * (d.out_h / 2 + 1)
                                     : ((d.out_w + 3) / 4) * d.out_h;
       w.max_units = std::max(w.max_units, units);
@@ -535,13 +538,16 @@ static bool enqueue_download(WebPBatch* b, int first, int count, cudaStream_t s,
     const ImgDesc& d = b->imgs[k];
     const WebPDecBuffer* o = &it->config->output;
     const uint8_t* src = dout + d.out_off;
-    if (d.csp == MODE_YUV) {
+    if (d.csp == MODE_YUV || d.csp == MODE_YUVA) {
       if (!flush()) return false;
       const int w = d.out_w, h = d.out_h, uvw = (w + 1) / 2, uvh = (h + 1) / 2;
       const WebPYUVABuffer* y = &o->u.YUVA;
       CU_TRY(cudaMemcpy2DAsync(y->y, y->y_stride, src, w, w, h, cudaMemcpyDeviceToHost, s), "D2H Y");
       CU_TRY(cudaMemcpy2DAsync(y->u, y->u_stride, src + (size_t)w * h, uvw, uvw, uvh, cudaMemcpyDeviceToHost, s), "D2H U");
       CU_TRY(cudaMemcpy2DAsync(y->v, y->v_stride, src + (size_t)w * h + (size_t)uvw * uvh, uvw, uvw, uvh, cudaMemcpyDeviceToHost, s), "D2H V");
+      if (d.csp == MODE_YUVA) {
+        CU_TRY(cudaMemcpy2DAsync(y->a, y->a_stride, src + (size_t)w * h + 2 * (size_t)uvw * uvh, w, w, h, cudaMemcpyDeviceToHost, s), "D2H A");
+      }
       continue;
     }
     const size_t row = (size_t)d.out_stride;
@@ -798,7 +804,7 @@ extern "C" int WebPBatchOutput(const WebPBatch* b, int index, WebPBatchPlane* p)
   memset(p, 0, sizeof(*p));
   p->width = d.out_w; p->height = d.out_h;
   p->y_or_rgba = base; p->stride = d.out_stride;
-  if (d.csp == MODE_YUV) {
+  if (d.csp == MODE_YUV || d.csp == MODE_YUVA) {
     const int uvw = (d.out_w + 1) / 2, uvh = (d.out_h + 1) / 2;
     p->u = base + (size_t)d.out_w * d.out_h;
     p->v = base + (size_t)d.out_w * d.out_h + (size_t)uvw * uvh;

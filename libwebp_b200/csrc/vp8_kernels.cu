@@ -304,13 +304,14 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(const ImgDesc* __restrict
   const uint8_t* alpha = (im.alpha_plane != VP8B_NO_ALPHA) ? alpha_arena + im.alpha_plane + (size_t)im.crop_y * im.width + im.crop_x : nullptr;
   const int t = chunk * EMIT_THREADS + threadIdx.x;
   const int w = im.out_w, h = im.out_h;
-  if (im.csp == 11) {   // MODE_YUV: 16-byte chunks of Y rows, then U rows, then V rows
+  if (im.csp == 11 || im.csp == 12) {   // MODE_YUV / MODE_YUVA: 16-byte chunks of Y rows, then U, V (and alpha) rows
     const int uvw = (w + 1) >> 1, uvh = (h + 1) >> 1;
     const int qy = (w + 15) >> 4, quv = (uvw + 15) >> 4;
     const int ny = qy * h, nuv = quv * uvh;
-    if (t < ny) emit_yuv_chunk(im, yp, up, vp, o, 0, t % qy, t / qy);
-    else if (t < ny + nuv) emit_yuv_chunk(im, yp, up, vp, o, 1, (t - ny) % quv, (t - ny) / quv);
-    else if (t < ny + 2 * nuv) emit_yuv_chunk(im, yp, up, vp, o, 2, (t - ny - nuv) % quv, (t - ny - nuv) / quv);
+    if (t < ny) emit_yuv_chunk(im, yp, up, vp, alpha, o, 0, t % qy, t / qy);
+    else if (t < ny + nuv) emit_yuv_chunk(im, yp, up, vp, alpha, o, 1, (t - ny) % quv, (t - ny) / quv);
+    else if (t < ny + 2 * nuv) emit_yuv_chunk(im, yp, up, vp, alpha, o, 2, (t - ny - nuv) % quv, (t - ny - nuv) / quv);
+    else if (im.csp == 12 && t < 2 * ny + 2 * nuv) emit_yuv_chunk(im, yp, up, vp, alpha, o, 3, (t - ny - 2 * nuv) % qy, (t - ny - 2 * nuv) / qy);
   } else if (emit_uses_pairs(im.csp, im.flags, im.crop_x)) {   // 8 pixels x 2 rows per thread
     const int qw = (w + 7) >> 3;
     if (t < qw * ((h >> 1) + 1)) emit_rgba_pair8(im, yp, up, vp, alpha, o, t % qw, t / qw);

@@ -533,6 +533,24 @@ VP8_PFN uint32_t pack_pixel4(int csp, int r, int g, int b, int a) {   // little-
   }
 }
 
+// 16-bit colourspaces (yuv.h:93-123, bytes in memory order rg | gb resp. rg | ba; WEBP_SWAP_16BIT_CSP is off in the
+// reference build). a = 8-bit alpha or 0xff. rgbA_4444 scales by the 4-bit alpha like ApplyAlphaMultiply4444_C
+// (alpha_processing.c:244-283): nibbles replicated to bytes, times a * 0x1111, >> 16; alpha 15 leaves the pixel alone.
+VP8_PFN uint32_t pack_pixel2(int csp, int r, int g, int b, int a) {
+  if (csp == 6) return (uint32_t)((r & 0xf8) | (g >> 5)) | ((uint32_t)(((g << 3) & 0xe0) | (b >> 3)) << 8);   // RGB_565
+  const uint32_t a4 = (uint32_t)a >> 4;
+  uint32_t rg = (uint32_t)((r & 0xf0) | (g >> 4)), ba = (uint32_t)(b & 0xf0) | a4;
+  if (csp == 10 && a4 != 15) {
+    const uint32_t m = a4 * 0x1111u;
+    const uint32_t r2 = ((((rg & 0xf0) | (rg >> 4)) * m) >> 16) & 0xff;
+    const uint32_t g2 = ((((rg & 0x0f) | ((rg << 4) & 0xf0)) * m) >> 16) & 0xff;
+    const uint32_t b2 = ((((ba & 0xf0) | (ba >> 4)) * m) >> 16) & 0xff;
+    rg = (r2 & 0xf0) | ((g2 >> 4) & 0x0f);
+    ba = (b2 & 0xf0) | a4;
+  }
+  return rg | (ba << 8);
+}
+
 // Pixels 4*q .. 4*q+3 of output row j of image `im`. yuv = the image's padded planes.
 VP8_PFN void emit_rgb_quad(const ImgDesc& im, const uint8_t* yplane, const uint8_t* uplane, const uint8_t* vplane,
                            const uint8_t* alpha /* window origin inside the frame-wide plane, or NULL */, uint8_t* out, int q, int j) {
@@ -552,7 +570,7 @@ VP8_PFN void emit_rgb_quad(const ImgDesc& im, const uint8_t* yplane, const uint8
   uint8_t* orow = out + (size_t)((im.flags & VP8B_FLAG_FLIP) ? h - 1 - j : j) * im.out_stride;
   const int i0 = 4 * q;
   const int n = (w - i0 < 4) ? w - i0 : 4;
-  const int bpp = (csp == 0 || csp == 2) ? 3 : 4;
+  const int bpp = (csp == 0 || csp == 2) ? 3 : (csp == 5 || csp == 6 || csp == 10) ? 2 : 4;
   uint32_t px[4];
   for (int k = 0; k < n; ++k) {
     const int i = i0 + k;
@@ -562,6 +580,9 @@ VP8_PFN void emit_rgb_quad(const ImgDesc& im, const uint8_t* yplane, const uint8
     yuv_to_rgb(yrow[i], u, v, &r, &g, &b);
     if (bpp == 4) {
       px[k] = pack_pixel4(csp, r, g, b, alpha ? (int)alpha[(size_t)j * im.width + i] : 0xff);
+    } else if (bpp == 2) {
+      const uint32_t p2 = pack_pixel2(csp, r, g, b, alpha ? (int)alpha[(size_t)j * im.width + i] : 0xff);
+      orow[2 * i] = (uint8_t)p2; orow[2 * i + 1] = (uint8_t)(p2 >> 8);
     } else {
       uint8_t* o = orow + 3 * i;
       if (csp == 0) { o[0] = (uint8_t)r; o[1] = (uint8_t)g; o[2] = (uint8_t)b; }
@@ -680,10 +701,18 @@ VP8_UNROLL
 
 // MODE_YUV (EmitYUV, io_dec.c:25-40): 16 bytes of one row of one plane. plane 0 = Y (w x h), 1 = U, 2 = V
 // ((w+1)/2 x (h+1)/2). Output = y | u | v at out_off with strides out_stride / (w+1)/2.
+// plane 3 (MODE_YUVA only, EmitAlphaYUV io_dec.c:131-152) = the alpha plane, 0xff where the file has none.
 VP8_PFN void emit_yuv_chunk(const ImgDesc& im, const uint8_t* yplane, const uint8_t* uplane, const uint8_t* vplane,
-                            uint8_t* out, int plane, int q, int j) {
+                            const uint8_t* alpha, uint8_t* out, int plane, int q, int j) {
   const int w = im.out_w, h = im.out_h;
   const int uvw = (w + 1) >> 1, uvh = (h + 1) >> 1;
+  if (plane == 3) {
+    const int jd = (im.flags & VP8B_FLAG_FLIP) ? h - 1 - j : j;
+    uint8_t* dst = out + (size_t)im.out_stride * h + 2 * (size_t)uvw * uvh + (size_t)jd * w + 16 * q;
+    const int n = (w - 16 * q < 16) ? w - 16 * q : 16;
+    for (int k = 0; k < n; ++k) dst[k] = alpha ? alpha[(size_t)j * im.width + 16 * q + k] : 0xff;
+    return;
+  }
   const int pw = plane ? uvw : w;
   const int jd = (im.flags & VP8B_FLAG_FLIP) ? (plane ? uvh : h) - 1 - j : j;   // destination row
   const int sstride = plane ? 8 * im.mb_w : 16 * im.mb_w;

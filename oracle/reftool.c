@@ -237,14 +237,18 @@ int reft_decode_window(const uint8_t* data, size_t size, int csp, int flags, con
   }
   cfg.output.colorspace = (WEBP_CSP_MODE)csp;
   cfg.output.is_external_memory = 1;
-  if (csp == MODE_YUV) {
+  if (csp == MODE_YUV || csp == MODE_YUVA) {
     const int uvw = (w + 1) / 2, uvh = (h + 1) / 2;
-    if (out_size < (size_t)w * h + 2 * (size_t)uvw * uvh) return -2;
+    if (out_size < (size_t)w * h + 2 * (size_t)uvw * uvh + (csp == MODE_YUVA ? (size_t)w * h : 0)) return -2;
     cfg.output.u.YUVA.y = out; cfg.output.u.YUVA.y_stride = w; cfg.output.u.YUVA.y_size = (size_t)w * h;
     cfg.output.u.YUVA.u = out + (size_t)w * h; cfg.output.u.YUVA.u_stride = uvw; cfg.output.u.YUVA.u_size = (size_t)uvw * uvh;
     cfg.output.u.YUVA.v = cfg.output.u.YUVA.u + (size_t)uvw * uvh; cfg.output.u.YUVA.v_stride = uvw; cfg.output.u.YUVA.v_size = (size_t)uvw * uvh;
+    if (csp == MODE_YUVA) {
+      cfg.output.u.YUVA.a = cfg.output.u.YUVA.v + (size_t)uvw * uvh; cfg.output.u.YUVA.a_stride = w; cfg.output.u.YUVA.a_size = (size_t)w * h;
+    }
   } else {
-    const int bpp = (csp == MODE_RGB || csp == MODE_BGR) ? 3 : 4;
+    const int bpp = (csp == MODE_RGB || csp == MODE_BGR) ? 3
+                  : (csp == MODE_RGBA_4444 || csp == MODE_RGB_565 || csp == MODE_rgbA_4444) ? 2 : 4;
     if (out_size < (size_t)w * h * bpp) return -2;
     cfg.output.u.RGBA.rgba = out; cfg.output.u.RGBA.stride = w * bpp; cfg.output.u.RGBA.size = out_size;
   }

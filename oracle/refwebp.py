@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(_HERE, "_ref", "libwebp_ref.so")
 MODE_RGB, MODE_RGBA, MODE_BGR, MODE_BGRA, MODE_ARGB = 0, 1, 2, 3, 4
 MODE_rgbA, MODE_bgrA, MODE_Argb = 7, 8, 9
 MODE_YUV, MODE_YUVA = 11, 12
-BPP = {0: 3, 1: 4, 2: 3, 3: 4, 4: 4, 7: 4, 8: 4, 9: 4}
+BPP = {0: 3, 1: 4, 2: 3, 3: 4, 4: 4, 5: 2, 6: 2, 7: 4, 8: 4, 9: 4, 10: 2}
+MODE_RGBA_4444, MODE_RGB_565, MODE_rgbA_4444 = 5, 6, 10
 
 FLAG_BYPASS_FILTER, FLAG_NO_FANCY, FLAG_THREADS, FLAG_FLIP = 1, 2, 4, 8
 
@@ -157,7 +158,8 @@ def decode_window(data, csp=MODE_RGBA, flags=0, crop=None):
     w, h = (crop[2], crop[3]) if crop else (f["width"], f["height"])
     if st != 0 or w <= 0 or h <= 0:
         w = h = 4
-    n = (w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2)) if csp == MODE_YUV else w * h * BPP[csp]
+    n = (w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2) + (w * h if csp == MODE_YUVA else 0)) if csp in (MODE_YUV, MODE_YUVA) \
+        else w * h * BPP[csp]
     out = np.zeros(max(n, 16), np.uint8)
     c4 = (C.c_int * 4)(*(crop if crop else (0, 0, 0, 0)))
     st = L.reft_decode_window(data, len(data), csp, flags, c4, out.ctypes.data, out.size)

@@ -212,13 +212,13 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
   const uint8_t* wu = up + (size_t)(im.crop_y >> 1) * (8 * mb_w) + (im.crop_x >> 1);
   const uint8_t* wv = vp + (size_t)(im.crop_y >> 1) * (8 * mb_w) + (im.crop_x >> 1);
   if (alpha) alpha += (size_t)im.crop_y * im.width + im.crop_x;
-  if (csp == MODE_YUV) {
+  if (csp == MODE_YUV || csp == MODE_YUVA) {
     const int uvw = (w + 1) / 2, uvh = (h + 1) / 2;
-    if (out_size < (size_t)w * h + 2 * (size_t)uvw * uvh) return VP8_STATUS_INVALID_PARAM;
+    if (out_size < (size_t)w * h + 2 * (size_t)uvw * uvh + (csp == MODE_YUVA ? (size_t)w * h : 0)) return VP8_STATUS_INVALID_PARAM;
     im.out_stride = w;
-    for (int plane = 0; plane < 3; ++plane) {
-      const int pw = plane ? uvw : w, ph = plane ? uvh : h;
-      for (int j = 0; j < ph; ++j) for (int q = 0; q < (pw + 15) / 16; ++q) emit_yuv_chunk(im, wy, wu, wv, out, plane, q, j);
+    for (int plane = 0; plane < (csp == MODE_YUVA ? 4 : 3); ++plane) {
+      const int pw = (plane == 1 || plane == 2) ? uvw : w, ph = (plane == 1 || plane == 2) ? uvh : h;
+      for (int j = 0; j < ph; ++j) for (int q = 0; q < (pw + 15) / 16; ++q) emit_yuv_chunk(im, wy, wu, wv, alpha, out, plane, q, j);
     }
   } else if (emit_uses_pairs(csp, flags, im.crop_x)) {
     for (int t = 0; t <= h / 2; ++t) for (int q = 0; q < (w + 7) / 8; ++q) emit_rgba_pair8(im, wy, wu, wv, alpha, out, q, t);

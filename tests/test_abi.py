@@ -90,9 +90,6 @@ def test_host_side_failures_need_no_gpu(product, port, manifest):
     L.WebPInitDecoderConfigInternal(C.byref(cfg), 0x0209)
     cfg.options.use_cropping = 1           # an empty crop window is an invalid parameter (buffer_dec.c:184-195)
     assert L.WebPDecode(d, len(d), C.byref(cfg)) == product.VP8_STATUS_INVALID_PARAM
-    L.WebPInitDecoderConfigInternal(C.byref(cfg), 0x0209)
-    cfg.output.colorspace = product.MODE_RGB_565
-    assert L.WebPDecode(d, len(d), C.byref(cfg)) == product.VP8_STATUS_UNSUPPORTED_FEATURE
     # external buffer too small -> INVALID_PARAM (buffer_dec.c:41-84)
     L.WebPInitDecoderConfigInternal(C.byref(cfg), 0x0209)
     buf = np.zeros(16, np.uint8)

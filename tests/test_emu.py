@@ -127,10 +127,10 @@ def test_emu_crop_and_flip_match_reference(ref, manifest, amanifest):
 
     def emu_window(data, csp, dev_flags, crop, W, H):
         w, h = (crop[2], crop[3]) if crop else (W, H)
-        n = (w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2)) if csp == 11 else w * h * ref.BPP[csp]
+        n = (w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2) + (w * h if csp == 12 else 0)) if csp in (11, 12) else w * h * ref.BPP[csp]
         out = np.zeros(max(n, 16), np.uint8)
         c = crop or (0, 0, 0, 0)
-        st = L.emu_decode_window(data, len(data), csp, dev_flags, out.ctypes.data, out.size, w if csp == 11 else w * ref.BPP[csp],
+        st = L.emu_decode_window(data, len(data), csp, dev_flags, out.ctypes.data, out.size, w if csp in (11, 12) else w * ref.BPP[csp],
                                  c[0], c[1], c[2], c[3])
         return st, out[:n]
 
@@ -143,7 +143,7 @@ def test_emu_crop_and_flip_match_reference(ref, manifest, amanifest):
                 cw, ch = int(rng.integers(1, W + 1)), int(rng.integers(1, H + 1))
                 crop = (int(rng.integers(0, W - cw + 1)), int(rng.integers(0, H - ch + 1)), cw, ch)
             flip, nofancy = int(rng.integers(0, 2)), int(rng.integers(0, 2)) if it % 2 else 0
-            for csp in (1, 7, 0, 11):
+            for csp in (1, 7, 0, 11, 5, 6, 10, 12):   # incl. the 16-bit colourspaces and MODE_YUVA
                 s_ref, want = ref.decode_window(e["data"], csp, (8 if flip else 0) | (2 if nofancy else 0), crop)
                 s_emu, got = emu_window(e["data"], csp, (4 if flip else 0) | (2 if nofancy else 0), crop, W, H)
                 assert s_emu == s_ref, (e["file"], crop, flip, csp, s_ref, s_emu)

@@ -257,7 +257,8 @@ def test_crop_and_flip(W, ref, manifest, amanifest):
                 cw, ch = int(rng.integers(1, Wd + 1)), int(rng.integers(1, Hd + 1))
                 crop = (int(rng.integers(0, Wd - cw + 1)), int(rng.integers(0, Hd - ch + 1)), cw, ch)
             flip = bool(rng.integers(0, 2))
-            for csp in (W.MODE_RGBA, W.MODE_rgbA, W.MODE_BGR, W.MODE_YUV):
+            for csp in (W.MODE_RGBA, W.MODE_rgbA, W.MODE_BGR, W.MODE_YUV, W.MODE_RGB_565, W.MODE_RGBA_4444, W.MODE_rgbA_4444,
+                        W.MODE_YUVA, W.MODE_Argb, W.MODE_bgrA):
                 s_ref, want = ref.decode_window(e["data"], csp, 8 if flip else 0, crop)
                 st, got = W.WebPDecode(e["data"], csp, crop=crop, flip=flip)
                 assert st == s_ref, (e["file"], crop, flip, csp, st, s_ref)
