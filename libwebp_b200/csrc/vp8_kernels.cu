@@ -29,6 +29,7 @@
 #include "vp8_parse_core.h"
 #include "vp8_pixel_core.h"
 #include "vp8_tokens_fsm.h"
+#include "vp8_tokens_lockstep.h"
 #define AL_BLOCK_SYNC() __syncthreads()
 #include "vp8l_alpha_core.h"
 
@@ -210,6 +211,87 @@ __global__ void __launch_bounds__(32 * 9) k_parse_tokens_fsm(const uint8_t* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Lockstep token parser (vp8_tokens_lockstep.h). A block owns ipb images x P partitions = S streams; stream j
+// sits in warp j % cw, lane j / cw (so the partitions of one image sit in different warps), lanes >= lpw idle.
+// With one stream per lane and ~7 lanes per warp, ONE warp per SM sub-partition carries the whole of BASELINE
+// config 2 (4096 streams over 592 sub-partitions) and the loop runs at its dependency latency, not at the issue
+// rate shared with six other warps.
+struct TlLayout {   // byte offsets inside the block's dynamic shared memory
+  uint32_t images, progress, ctx, total;
+};
+__host__ __device__ static inline TlLayout tl_layout(int P, int ipb, int ctx_stride) {
+  TlLayout t;
+  t.images = (TL_TAB_BYTES + 15u) & ~15u;
+  t.progress = t.images + (uint32_t)ipb * TL_IMG_STRIDE;
+  t.ctx = t.progress + (uint32_t)ipb * VP8B_MAX_PARTS * 4u;
+  t.total = t.ctx + (uint32_t)ipb * (uint32_t)(P + 1) * (uint32_t)ctx_stride * 2u;
+  return t;
+}
+
+__global__ void __launch_bounds__(32 * 8, 1) k_parse_tokens_lockstep(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
+                                                                  FrameHdr* hdrs, uint32_t* mbinfo, int16_t* coeffs,
+                                                                  const int* __restrict__ ids, int count, int P, int ipb, int lpw,
+                                                                  int cw, int ctx_stride) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const TlLayout lay = tl_layout(P, ipb, ctx_stride);
+  TlTables* tables = reinterpret_cast<TlTables*>(smem);
+  int* progress = reinterpret_cast<int*>(smem + lay.progress);
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  tl_tables_fill(tables, tid, nthreads);
+  for (int k = tid; k < ipb * VP8B_MAX_PARTS; k += nthreads) progress[k] = 0;
+  for (int slot = 0; slot < ipb; ++slot) {
+    const int g = blockIdx.x * ipb + slot;
+    if (g < count) tl_image_fill(smem + lay.images + (size_t)slot * TL_IMG_STRIDE, &hdrs[ids[g]], tid, nthreads);
+  }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5;
+  const int j = lane * cw + warp;           // stream inside the block
+  const int slot = j / P, part = j % P;
+  const int g = blockIdx.x * ipb + slot;
+  int have = lane < lpw && j < ipb * P && g < count;
+  const int img = have ? ids[g] : 0;
+  FrameHdr* h = &hdrs[img];
+  if (have && !(h->status == VP8B_OK && h->num_parts == P)) {   // header failed (or, never expected, the host pre-scan disagreed)
+    if (part == 0 && h->status == VP8B_OK) h->status = VP8B_BITSTREAM_ERROR;
+    have = 0;
+  }
+  const ImgDesc im = imgs[img];
+  TlCtx c;
+  c.img_s = tk_saddr_of(smem + lay.images + (size_t)(have ? slot : 0) * TL_IMG_STRIDE);
+  c.tab_s = tk_saddr_of(tables);
+  asm volatile("" : "+r"(c.img_s), "+r"(c.tab_s));   // keep both as plain registers (no per-iteration cvta)
+  c.topctx = reinterpret_cast<uint16_t*>(smem + lay.ctx) + (size_t)(have ? slot : 0) * (P + 1) * ctx_stride;
+  c.progress = progress + (have ? slot : 0) * VP8B_MAX_PARTS;
+  c.mbinfo = mbinfo + 4 * (size_t)im.mb_base;
+  c.coeffs = coeffs + (size_t)im.mb_base * VP8B_COEFFS_PER_MB;
+  c.mb_w = im.mb_w; c.rows = have ? h->rows : 0; c.P = P; c.part = part; c.use_skip = h->use_skip; c.ctx_stride = ctx_stride;
+  if (part >= c.rows) have = 0;
+  TlLane L;
+  if (have) {
+    tl_lane_init(L, c, arena + im.in_off, h);
+  } else {
+    tl_lane_idle(L, c, arena);
+  }
+  // One decode per lane per step, four steps per window top-up, and the whole warp (parked lanes included) meets at
+  // the vote: the lanes never run apart by more than the block-end branches inside one step. (Left to itself the
+  // compiler turns "decode until the block ends" into an inner loop, and a lane whose block has ended would wait
+  // at that loop's exit for the longest block in the warp.)
+  if (P > 1) {
+    while (__any_sync(0xffffffffu, L.alive)) {
+      bd_fill(L.d);
+      tl_step<1>(L, c); tl_step<1>(L, c); tl_step<1>(L, c); tl_step<1>(L, c);
+    }
+  } else {
+    if (have && !tl_mb_next(L, c)) tl_lane_park(L, c);
+    while (__any_sync(0xffffffffu, L.alive)) {
+      bd_fill(L.d);
+      tl_step<0>(L, c); tl_step<0>(L, c); tl_step<0>(L, c); tl_step<0>(L, c);
+    }
+  }
+  if (have && L.status != VP8B_OK) h->status = L.status;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 #define RECON_WARPS 8
 
 __global__ void __launch_bounds__(32 * RECON_WARPS) k_reconstruct(const ImgDesc* __restrict__ imgs, const FrameHdr* __restrict__ hdrs,
@@ -375,6 +457,31 @@ static void launch_tokens_fsm(cudaStream_t s, const uint8_t* arena, const ImgDes
   k_parse_tokens_fsm<<<blocks, 32 * (cw + 1), lay.total, s>>>(arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, ipb, lpw, cw, max_mb_w);
 }
 
+// Launch geometry of the lockstep parser: cw warps per block (one per SM sub-partition), lpw streams per warp so
+// that one block per SM holds the whole launch where shared memory allows it.
+static void launch_tokens_lockstep(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,
+                                   int16_t* coeffs, const int* ids, int count, int P, int max_mb_w) {
+  static int f_lpw = -1, f_cw = -1;
+  if (f_lpw < 0) { f_lpw = env_int("WEBP_B200_TOKEN_LPW"); f_cw = env_int("WEBP_B200_TOKEN_CW"); }
+  int cw = (f_cw == 2 || f_cw == 4 || f_cw == 8) ? f_cw : 4;
+  const long streams = (long)count * P;
+  int lpw = (int)((streams + 148L * cw - 1) / (148L * cw));
+  if (f_lpw >= 1 && f_lpw <= 32) lpw = f_lpw;
+  if (lpw < 1) lpw = 1;
+  if (lpw > 32) lpw = 32;
+  while (cw * lpw < P) ++lpw;               // a block holds at least one image
+  int ipb = (cw * lpw) / P;                  // images per block
+  while (ipb > 1 && tl_layout(P, ipb, max_mb_w).total > 200u * 1024u) --ipb;
+  const TlLayout lay = tl_layout(P, ipb, max_mb_w);
+  const int blocks = (count + ipb - 1) / ipb;
+  static size_t configured = 0;
+  if (lay.total > configured) {
+    cudaFuncSetAttribute(k_parse_tokens_lockstep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
+    configured = lay.total;
+  }
+  k_parse_tokens_lockstep<<<blocks, 32 * cw, lay.total, s>>>(arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, ipb, lpw, cw, max_mb_w);
+}
+
 extern "C" void vp8k_parse_tokens(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,
                                   int16_t* coeffs, const int* ids, int count, int P, int max_mb_w) {
   // Two mappings of the same parse: one warp per partition (straight-line code on one lane, latency hidden by
@@ -382,8 +489,9 @@ extern "C" void vp8k_parse_tokens(cudaStream_t s, const uint8_t* arena, const Im
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("WEBP_B200_TOKEN_MAP");
-    forced = (e && e[0] == 'w') ? 1 : (e && e[0] == 'l') ? 2 : 0;
+    forced = (e && e[0] == 'w') ? 1 : (e && e[0] == 'l') ? 2 : (e && e[0] == 'k') ? 3 : 0;
   }
+  if (forced == 3) { launch_tokens_lockstep(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, max_mb_w); return; }
   // Up to ~16 streams per SM sub-partition the straight-line parser keeps the issue slots busy on its own; beyond
   // that the state machine's shared instruction stream wins (measured: profiles/r01*_token_map_sweep.log).
   const int use_warp_map = forced ? (forced == 1) : ((long)count * P <= 148L * 4 * 16);

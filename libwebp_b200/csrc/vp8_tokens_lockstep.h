@@ -1,0 +1,333 @@
+// vp8_tokens_lockstep.h -- coefficient-token parser, third mapping: few lanes per warp in strict lockstep.
+//
+// One LANE owns one token partition. Every loop iteration is exactly one boolean decode per lane, and the whole
+// token syntax of GetCoeffs / GetLargeValue (src/dec/vp8_dec.c:411-469) is a 61-state x {0,1} transition table.
+// What makes the iteration short (about 40 SASS instructions, against ~25 per decode for a warp that serves one
+// stream only) is that the probability address IS the state:
+//
+//   row   shared address of a 64-byte row, one per (block type, coefficient position n); walking a block is
+//         `row += 64`, and n == 16 is `row == rowend`
+//   s     index inside the row: 0..32 = [ctx 3][node 11] of that position's band, 33..60 = the fixed
+//         probabilities (sign, 159/165/145, the DCT_CAT3..6 extra bits), replicated in every row so that
+//         `prob = row[s]` holds in every state
+//
+// and a transition entry is only {next s, advance row?, emit?, end of block?, addend of the value}: the context
+// of the next coefficient, the category and the extra-bit weights are all folded into which state comes next.
+// Block ends (every ~17 decodes per lane) and macroblock ends branch; finished lanes leave the loop.
+//
+// The compressed bytes are read straight from HBM through the read-only path, one aligned word per refill,
+// fetched one refill (>= 32 payload bits, ~40 iterations) ahead of its use.
+//
+// Replaces VP8DecodeMB / ParseResiduals / GetCoeffs / GetLargeValue (src/dec/vp8_dec.c:400-635) for a batch.
+// Dual build like the other cores: nvcc for the product, g++ -DVP8_EMU for tests/emu.
+#ifndef LIBWEBP_B200_VP8_TOKENS_LOCKSTEP_H_
+#define LIBWEBP_B200_VP8_TOKENS_LOCKSTEP_H_
+
+#include "vp8_dev.h"
+#include "vp8_parse_core.h"
+#include "vp8_tokens_fsm.h"   // TK_FN, tk_saddr and the shared-memory access helpers
+
+// ---- states
+#define TL_SIGN1 33    // sign of a coefficient of magnitude 1 (next context 1)
+#define TL_SIGN2 34    // sign of a larger one (next context 2)
+#define TL_C159 35
+#define TL_C165 36
+#define TL_C145 37
+#define TL_CAT3 38     // 3 extra bits
+#define TL_CAT4 41     // 4
+#define TL_CAT5 45     // 5
+#define TL_CAT6 50     // 11
+#define TL_STATES 61
+#define TL_ROW_BYTES 64
+#define TL_TYPE_BYTES (16 * TL_ROW_BYTES)
+#define TL_IMG_BYTES (4 * TL_TYPE_BYTES)
+#define TL_IMG_STRIDE (TL_IMG_BYTES + 20)   // odd multiple of 4 banks: the lanes of a warp spread over the banks
+
+// ---- transition entry:  [5:0] next s   6 advance the row (n++)   7 emit +-v at n   8 end of block   [26:16] addend of v
+#define TL_ADV 64u
+#define TL_EMIT 128u
+#define TL_EOB 256u
+#define TL_E(next, flags, add) ((uint32_t)(next) | (uint32_t)(flags) | ((uint32_t)(add) << 16))
+
+TK_FN uint32_t tl_trans_entry(int s, int b) {
+  if (s < 33) {
+    const int base = (s / 11) * 11, k = s % 11;
+    switch (k) {
+      case 0: return b ? TL_E(s + 1, 0, 0) : TL_E(s, TL_EOB, 0);
+      case 1: return b ? TL_E(s + 1, 0, 0) : TL_E(1, TL_ADV, 0);            // a zero: next position, ctx 0, node 1
+      case 2: return b ? TL_E(s + 1, 0, 0) : TL_E(TL_SIGN1, 0, 1);
+      case 3: return b ? TL_E(base + 6, 0, 0) : TL_E(base + 4, 0, 0);
+      case 4: return b ? TL_E(base + 5, 0, 0) : TL_E(TL_SIGN2, 0, 2);
+      case 5: return b ? TL_E(TL_SIGN2, 0, 4) : TL_E(TL_SIGN2, 0, 3);
+      case 6: return b ? TL_E(base + 8, 0, 0) : TL_E(base + 7, 0, 0);
+      case 7: return b ? TL_E(TL_C165, 0, 7) : TL_E(TL_C159, 0, 5);
+      case 8: return b ? TL_E(base + 10, 0, 0) : TL_E(base + 9, 0, 0);
+      case 9: return b ? TL_E(TL_CAT4, 0, 3 + 16) : TL_E(TL_CAT3, 0, 3 + 8);
+      default: return b ? TL_E(TL_CAT6, 0, 3 + 64) : TL_E(TL_CAT5, 0, 3 + 32);
+    }
+  }
+  if (s == TL_SIGN1) return TL_E(11, TL_ADV | TL_EMIT, 0);
+  if (s == TL_SIGN2) return TL_E(22, TL_ADV | TL_EMIT, 0);
+  if (s == TL_C159) return TL_E(TL_SIGN2, 0, b);
+  if (s == TL_C165) return TL_E(TL_C145, 0, 2 * b);
+  if (s == TL_C145) return TL_E(TL_SIGN2, 0, b);
+  int first, nb;
+  if (s < TL_CAT4) { first = TL_CAT3; nb = 3; }
+  else if (s < TL_CAT5) { first = TL_CAT4; nb = 4; }
+  else if (s < TL_CAT6) { first = TL_CAT5; nb = 5; }
+  else { first = TL_CAT6; nb = 11; }
+  const int i = s - first;
+  return TL_E(i == nb - 1 ? TL_SIGN2 : s + 1, 0, b << (nb - 1 - i));
+}
+
+// byte s of the row of (type t, position n)
+TK_FN uint8_t tl_row_byte(const uint8_t* prob /* [4][8][3][11] */, int t, int n, int s) {
+  const uint8_t fixed[28] = { 128, 128, 159, 165, 145, 173, 148, 140, 176, 155, 140, 135, 180, 157, 141, 134, 130,
+                              254, 254, 243, 230, 196, 177, 153, 140, 133, 130, 129 };
+  const uint8_t bands[16] = { 0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7 };
+  if (s < 33) return prob[t * 264 + bands[n] * 33 + s];
+  if (s < TL_STATES) return fixed[s - 33];
+  return 0;
+}
+
+// Block-wide tables in shared memory.
+struct TlTables {
+  uint32_t trans[64][2];   // [s][bit]
+  uint32_t seqmask[28];    // block seq (0 = Y2, 1..16 luma, 17..24 chroma): its two context bits inside TlLane::cx
+};
+#define TLT_SEQMASK 512
+#define TL_TAB_BYTES 624    // sizeof(TlTables)
+
+TK_FN uint32_t tl_seqmask(int k) {
+  if (k == 0) return (1u << 8) | (1u << 24);
+  if (k <= 16) { const uint32_t blk = (uint32_t)k - 1; return (1u << (blk & 3)) | (1u << (16 + (blk >> 2))); }
+  if (k <= 24) {
+    const uint32_t c = (uint32_t)k - 17;
+    return (1u << (4 + (c & 1) + 2 * (c >> 2))) | (1u << (16 + 4 + ((c >> 1) & 1) + 2 * (c >> 2)));
+  }
+  return 0;
+}
+
+TK_FN void tl_tables_fill(TlTables* t, int tid, int nthreads) {
+  for (int k = tid; k < 128; k += nthreads) t->trans[k >> 1][k & 1] = (k >> 1) < TL_STATES ? tl_trans_entry(k >> 1, k & 1) : TL_E(63, 0, 0);   // 63 = TL_DEAD
+  for (int k = tid; k < 28; k += nthreads) t->seqmask[k] = tl_seqmask(k);
+}
+
+// One image's rows (TL_IMG_BYTES at `dst`, 4-byte aligned) from the parsed header; any thread subset.
+TK_FN void tl_image_fill(uint8_t* dst, const FrameHdr* h, int tid, int nthreads) {
+  for (int k = tid; k < TL_IMG_BYTES / 4; k += nthreads) {
+    const int t = k >> 8, n = (k >> 4) & 15, s0 = (k & 15) * 4;
+    uint32_t w = 0;
+    for (int j = 0; j < 4; ++j) w |= (uint32_t)tl_row_byte(h->prob, t, n, s0 + j) << (8 * j);
+    ((uint32_t*)dst)[k] = w;
+  }
+}
+
+// ---- per-lane state (registers)
+struct TlLane {
+  BoolDec d;
+  tk_saddr row, rowend;   // current row, row of position 16 of the current block type
+  uint32_t s;
+  uint32_t v;             // magnitude under construction
+  int16_t* blkcoef;       // the current block's 16 coefficients
+  uint32_t ofs;           // - (row of position 0 of the current block type) / 32, see the store in tl_step
+  uint32_t cx;            // non-zero contexts: top in bits 0-8 (0-3 luma, 4-5 U, 6-7 V, 8 Y2), left in bits 16-24
+  uint32_t acc_lo, acc_hi;// 2-bit nz codes of the macroblock's blocks shifted in, in parse order
+  uint32_t m;             // context bits of the current block (seqmask)
+  int seq;                // 0 = Y2, 1..16 luma, 17..24 chroma
+  uint32_t first;         // first coefficient of the current block (1 for the luma blocks of i16 macroblocks)
+  // macroblock
+  tk_saddr ystart, yend;  // luma rows of this macroblock: start, end
+  int16_t* mbcoef;
+  uint32_t w, w_next;     // MbInfo word 3 of this / the partition's next macroblock
+  int mx, my;
+  int done_mbs;
+  int waiting;            // P > 1: the partition owning the row above has not got far enough yet
+  int alive;              // 0 once parked
+  int status;
+};
+
+// Per-lane constants.
+struct TlCtx {
+  tk_saddr img_s;         // this image's rows
+  tk_saddr tab_s;         // TlTables
+  uint16_t* topctx;       // (P + 1) x ctx_stride ring
+  volatile int* progress; // P counters
+  uint32_t* mbinfo;       // this image's MbInfo
+  int16_t* coeffs;        // this image's coefficient plane
+  int mb_w, rows, P, part, use_skip, ctx_stride;
+};
+
+TK_FN void tl_lane_reset(TlLane& L, const TlCtx& c) {
+  L.row = 0; L.rowend = 0; L.s = 0; L.v = 0; L.blkcoef = c.coeffs; L.ofs = 0; L.cx = 0; L.acc_lo = 0; L.acc_hi = 0; L.m = 0; L.seq = 0; L.first = 0;
+  L.ystart = 0; L.yend = 0; L.mbcoef = c.coeffs;
+  L.mx = 0; L.my = c.part; L.done_mbs = 0; L.waiting = 1; L.alive = 1; L.status = VP8B_OK;
+  L.w = 0; L.w_next = 0;
+}
+
+TK_FN void tl_lane_init(TlLane& L, const TlCtx& c, const uint8_t* frame, const FrameHdr* h) {
+  bd_init(L.d, frame + h->part_off[c.part], h->part_size[c.part]);
+  tl_lane_reset(L, c);
+  L.w_next = (c.part < c.rows) ? VP8_LDG(c.mbinfo + 4 * ((size_t)c.part * c.mb_w) + 3) : 0;
+}
+
+// Sets up block L.seq (contexts in L.cx are final for it).
+TK_FN void tl_block_setup(TlLane& L, const TlCtx& c) {
+  const int chroma = L.seq >= 17;
+  L.m = tk_lds_u32(c.tab_s + TLT_SEQMASK + 4u * (uint32_t)L.seq);
+#if defined(__CUDACC__) && !defined(VP8_EMU)
+  const uint32_t ctx = (uint32_t)__popc(L.cx & L.m);
+#else
+  const uint32_t ctx = (uint32_t)__builtin_popcount(L.cx & L.m);
+#endif
+  if (L.seq == 0) {            // Y2: type 1, block 24
+    L.row = c.img_s + 1 * TL_TYPE_BYTES; L.rowend = L.row + TL_TYPE_BYTES; L.first = 0;
+    L.blkcoef = L.mbcoef + 24 * 16;
+  } else {
+    L.rowend = chroma ? c.img_s + 3 * TL_TYPE_BYTES : L.yend;
+    L.row = chroma ? c.img_s + 2 * TL_TYPE_BYTES : L.ystart;
+    L.first = chroma ? 0u : (uint32_t)((L.yend - L.ystart) != TL_TYPE_BYTES);
+    L.blkcoef = L.mbcoef + (L.seq - 1) * 16;
+  }
+  L.ofs = 0u - (uint32_t)((L.rowend - TL_TYPE_BYTES) >> 5);
+  L.s = ctx * 11u;
+}
+
+// Leaves the lane either with a block set up (returns 1), waiting for the row above (returns 0, L.waiting = 1) or
+// finished (returns 0, L.waiting = 0, L.my >= rows or L.status != OK). Skipped macroblocks are consumed here.
+TK_FN int tl_mb_next(TlLane& L, const TlCtx& c) {
+  const int P = c.P, mb_w = c.mb_w;
+  for (;;) {
+    if (L.my >= c.rows || L.status != VP8B_OK) { L.waiting = 0; return 0; }
+    uint32_t tctx = 0;
+    if (L.my > 0) {
+      if (P > 1) {
+        const int prev = (c.part + P - 1) % P;
+        const int need = ((L.my - 1 - prev) / P) * mb_w + L.mx + 1;
+        if (c.progress[prev] < need) { L.waiting = 1; return 0; }
+        TK_FENCE();
+      }
+      tctx = c.topctx[(size_t)((L.my + P) % (P + 1)) * c.ctx_stride + L.mx];
+    }
+    L.waiting = 0;
+    const size_t idx = (size_t)L.my * mb_w + L.mx;
+    L.w = L.w_next;
+    {   // flags of this partition's next macroblock: needed one macroblock from here
+      int nx = L.mx + 1, ny = L.my;
+      if (nx == mb_w) { nx = 0; ny += P; }
+      if (ny < c.rows) L.w_next = VP8_LDG(c.mbinfo + 4 * ((size_t)ny * mb_w + nx) + 3);
+    }
+    if (L.mx == 0) L.cx = 0;
+    L.cx = (L.cx & 0xffff0000u) | tctx;
+    const int is_i4 = (L.w & MBW_I4X4) != 0;
+    uint32_t nzy = 0, nzuv = 0;
+    const int skipped = c.use_skip && (L.w & MBW_SKIP);
+    if (!skipped) {
+      L.acc_lo = 0; L.acc_hi = 0;
+      L.mbcoef = c.coeffs + idx * VP8B_COEFFS_PER_MB;
+      L.yend = c.img_s + (is_i4 ? 4u : 1u) * TL_TYPE_BYTES;                 // type 3 (with DC) or type 0 (from n = 1)
+      L.ystart = L.yend - TL_TYPE_BYTES + (is_i4 ? 0u : (uint32_t)TL_ROW_BYTES);
+      L.seq = is_i4 ? 1 : 0;
+      tl_block_setup(L, c);
+      return 1;
+    }
+    L.cx &= is_i4 ? 0x01000100u : 0u;
+    // finish the skipped macroblock (same stores as tl_mb_finish with empty codes)
+    c.mbinfo[4 * idx + 2] = nzy;
+    c.mbinfo[4 * idx + 3] = (L.w & 0xffff0000u) | nzuv;
+    c.topctx[(size_t)(L.my % (P + 1)) * c.ctx_stride + L.mx] = (uint16_t)(L.cx & 0x1ffu);
+    L.done_mbs++;
+    if (++L.mx == mb_w) { L.mx = 0; L.my += P; }
+    if (bd_eof(L.d)) {
+      L.status = VP8B_NOT_ENOUGH_DATA;
+      if (P > 1) { TK_FENCE(); c.progress[c.part] = 0x7fffffff; }
+    } else if (P > 1) { TK_FENCE(); c.progress[c.part] = L.done_mbs; }
+  }
+}
+
+// The macroblock's last block has ended: store its results, move on.
+TK_FN void tl_mb_finish(TlLane& L, const TlCtx& c) {
+  const int P = c.P, mb_w = c.mb_w;
+  const size_t idx = (size_t)L.my * mb_w + L.mx;
+  const uint32_t nzy = (L.acc_hi << 16) | (L.acc_lo >> 16);
+  const uint32_t uv = L.acc_lo & 0xffffu;                      // U codes in bits 15-8, V in 7-0
+  const uint32_t nzuv = (uv >> 8) | ((uv & 0xffu) << 8);       // reference order: U bits 0-7, V bits 8-15
+  uint32_t w = L.w;
+  if ((L.acc_hi >> 16) & 3u) w |= MBW_HAS_Y2;                  // the Y2 block's code, shifted in first
+  c.mbinfo[4 * idx + 2] = nzy;
+  c.mbinfo[4 * idx + 3] = (w & 0xffff0000u) | nzuv;
+  c.topctx[(size_t)(L.my % (P + 1)) * c.ctx_stride + L.mx] = (uint16_t)(L.cx & 0x1ffu);
+  L.done_mbs++;
+  if (++L.mx == mb_w) { L.mx = 0; L.my += P; }
+  if (bd_eof(L.d)) {
+    // Ran past the end of the partition: the image is lost (vp8_dec.c:651-659); release whoever waits on us.
+    L.status = VP8B_NOT_ENOUGH_DATA;
+    if (P > 1) { TK_FENCE(); c.progress[c.part] = 0x7fffffff; }
+  } else if (P > 1) { TK_FENCE(); c.progress[c.part] = L.done_mbs; }
+}
+
+// Parks a lane that has nothing (more) to do: state 63 decodes a zero probability for ever, never emits, never
+// ends a block, and its reader only shifts in zeros. Dead lanes keep executing the loop in step with the others.
+#define TL_DEAD 63u
+TK_FN void tl_lane_park(TlLane& L, const TlCtx& c) {
+  L.s = TL_DEAD; L.row = c.img_s; L.rowend = 0; L.alive = 0; L.waiting = 0;
+}
+
+// A lane without a stream: a reader over zero bytes at `any` (a valid address), parked from the start.
+TK_FN void tl_lane_idle(TlLane& L, const TlCtx& c, const uint8_t* any) {
+  bd_init(L.d, any, 0);
+  tl_lane_reset(L, c);
+  tl_lane_park(L, c);
+}
+
+// One iteration: one boolean decode and its consequences; the caller has topped the window up (bd_fill) within
+// the last three decodes. Returns 0 when the lane has finished (it is parked then).
+// MULTI = the image has several token partitions (lanes may have to wait for the row above).
+template <int MULTI>
+TK_FN int tl_step(TlLane& L, const TlCtx& c) {
+  if (MULTI) {
+    if (L.waiting) {
+      if (!tl_mb_next(L, c)) {
+        if (!L.waiting) tl_lane_park(L, c);
+        return L.alive;
+      }
+    }
+  }
+  // ---- boolean decode (bit_reader_inl_utils.h:107-136)
+  const uint32_t prob = tk_lds_u8(L.row + L.s);
+  uint32_t e0, e1;
+  tk_lds_v2(c.tab_s + L.s * 8u, e0, e1);
+  const int bit = bd_bit_nofill(L.d, prob);
+  // ---- transition
+  const uint32_t e = bit ? e1 : e0;
+  const uint32_t adv = e & TL_ADV;
+  L.s = e & 63u;
+  L.v += e >> 16;
+  if (e & TL_EMIT) {   // level, parse order: coefficient n of the block sits at byte 2n = (row - row of n = 0) / 32
+    *(int16_t*)((uint8_t*)L.blkcoef + (uint32_t)((L.row >> 5) + L.ofs)) = (int16_t)(bit ? -(int)L.v : (int)L.v);
+    L.v = 0;
+  }
+  L.row += adv;
+  if ((e & TL_EOB) || L.row == L.rowend) {
+    // ---- end of block (GetCoeffs' return value nz; ParseResiduals' bookkeeping, vp8_dec.c:517-609)
+    const uint32_t nz = 16u - (uint32_t)((L.rowend - L.row) >> 6);
+    const uint32_t l = nz > L.first ? 1u : 0u;
+    const uint32_t code = nz > 3 ? 3u : nz > 1 ? 2u : l;   // a lone DC level is re-examined after dequantisation (recon_macroblock)
+    L.acc_hi = (L.acc_hi << 2) | (L.acc_lo >> 30);
+    L.acc_lo = (L.acc_lo << 2) | code;
+    L.cx = (L.cx & ~L.m) | (l ? L.m : 0u);
+    L.seq++;
+    if (L.seq == 25) {
+      tl_mb_finish(L, c);
+      if (!tl_mb_next(L, c)) {
+        if (!(MULTI && L.waiting)) tl_lane_park(L, c);
+        return L.alive;
+      }
+    } else {
+      tl_block_setup(L, c);
+    }
+  }
+  return 1;
+}
+
+#endif  // LIBWEBP_B200_VP8_TOKENS_LOCKSTEP_H_

@@ -17,11 +17,13 @@
 #include "vp8_parse_core.h"
 #include "vp8_pixel_core.h"
 #include "vp8_tokens_fsm.h"
+#include "vp8_tokens_lockstep.h"
 #include "vp8l_alpha_core.h"
 
 // variant bit 0: visit the macroblocks of a wavefront step in reverse order
 // variant bit 1: token parse with the row-at-a-time reference port (parse_token_row) instead of the lane FSM
 // variant bit 2: lane FSM with a lazy ring producer
+// variant bit 3: lockstep lane parser (vp8_tokens_lockstep.h), lanes advanced round-robin one decode at a time
 static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags, uint8_t* out, size_t out_size,
                            int stride, int variant, uint8_t* unfiltered, int crop_x, int crop_y, int crop_w, int crop_h);
 
@@ -82,7 +84,43 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
   const int rows = hdr.rows;   // macroblock rows that get decoded (all of them unless cropping)
 
   // K2: tokens
-  if (!(variant & 2)) {   // lane FSM: one lane per partition, lanes advanced round-robin one iteration at a time
+  if (variant & 8) {   // lockstep parser: one lane per partition, one decode per lane per round
+    const int P = hdr.num_parts;
+    std::vector<uint8_t> imgmem(TL_IMG_BYTES + 16);
+    uint8_t* img16 = (uint8_t*)(((uintptr_t)imgmem.data() + 15) & ~(uintptr_t)15);
+    std::vector<uint64_t> tabmem((sizeof(TlTables) + 7) / 8);
+    TlTables* ttab = (TlTables*)tabmem.data();
+    tl_image_fill(img16, &hdr, 0, 1);
+    tl_tables_fill(ttab, 0, 1);
+    std::vector<uint16_t> topctx((size_t)(P + 1) * mb_w, 0);
+    std::vector<int> progress(VP8B_MAX_PARTS, 0);
+    std::vector<TlLane> lanes(P);
+    std::vector<TlCtx> ctxs(P);
+    std::vector<int> live(P, 0);
+    for (int p = 0; p < P && p < rows; ++p) {
+      TlCtx& cc = ctxs[p];
+      cc.img_s = tk_saddr_of(img16); cc.tab_s = tk_saddr_of(ttab);
+      cc.topctx = topctx.data(); cc.progress = progress.data();
+      cc.mbinfo = mbinfo.data(); cc.coeffs = coeffs.data();
+      cc.mb_w = mb_w; cc.rows = rows; cc.P = P; cc.part = p; cc.use_skip = hdr.use_skip; cc.ctx_stride = mb_w;
+      tl_lane_init(lanes[p], cc, frame, &hdr);
+      live[p] = (P > 1) ? 1 : tl_mb_next(lanes[p], cc);
+      if (!live[p]) tl_lane_park(lanes[p], cc);
+    }
+    for (bool any = true; any;) {
+      any = false;
+      for (int p = P - 1; p >= 0; --p) {   // reverse order: exercises the wait-for-progress path
+        if (!live[p]) continue;
+        any = true;
+        bd_fill(lanes[p].d);
+        for (int k = 0; k < 4; ++k) {   // parked lanes keep stepping, harmlessly, like on the device
+          if (P > 1) tl_step<1>(lanes[p], ctxs[p]); else tl_step<0>(lanes[p], ctxs[p]);
+        }
+        live[p] = lanes[p].alive;
+      }
+    }
+    for (int p = 0; p < P && p < rows; ++p) if (lanes[p].status != VP8B_OK) hdr.status = lanes[p].status;
+  } else if (!(variant & 2)) {   // lane FSM: one lane per partition, lanes advanced round-robin one iteration at a time
     const int P = hdr.num_parts;
     TokImage timg;
     TokTables ttab;
