@@ -34,19 +34,22 @@
 #include "vp8l_alpha_core.h"
 
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_parse_modes(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
-                                                    FrameHdr* hdrs, uint32_t* mbinfo, int first, int count) {
-  extern __shared__ uint32_t top_modes[];   // mb_w words
-  __shared__ uint8_t bprob[900];            // kVp8BModeProba, out of the constant bank (indexed per decode)
-  const int i = blockIdx.x;
-  for (int k = threadIdx.x; k < 900; k += 32) bprob[k] = kVp8BModeProba[k];
+#define MODES_WARPS 28   // one image per warp, seven per SM sub-partition (see k_parse_tokens)
+__global__ void __launch_bounds__(32 * MODES_WARPS, 1) k_parse_modes(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
+                                                                     FrameHdr* hdrs, uint32_t* mbinfo, int first, int count, int ipb,
+                                                                     int max_mb_w) {
+  extern __shared__ uint32_t top_modes_all[];   // ipb x max_mb_w words
+  __shared__ uint8_t bprob[900];                // kVp8BModeProba, out of the constant bank (indexed per decode)
+  const int warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * ipb + warp;
+  for (int k = threadIdx.x; k < 900; k += blockDim.x) bprob[k] = kVp8BModeProba[k];
   __syncthreads();
-  if (i >= count || threadIdx.x != 0) return;
+  if (i >= count || (threadIdx.x & 31) != 0) return;
   const ImgDesc im = imgs[first + i];
   FrameHdr* h = &hdrs[first + i];
   BoolDec br;
   int st = parse_frame_header(br, arena + im.in_off, im, h);
-  if (st == VP8B_OK) st = parse_intra_modes(br, im, h, top_modes, bprob, mbinfo + 4 * (size_t)im.mb_base);
+  if (st == VP8B_OK) st = parse_intra_modes(br, im, h, top_modes_all + (size_t)warp * max_mb_w, bprob, mbinfo + 4 * (size_t)im.mb_base);
   h->status = st;
 }
 
@@ -54,23 +57,35 @@ __global__ void __launch_bounds__(32) k_parse_modes(const uint8_t* __restrict__ 
 // Shared memory: probabilities by position 2244 B (padded to 2256) | progress P+1 ints (padded to 48 B) | top contexts.
 #define TOKW_PROGRESS 2256
 #define TOKW_CTX (TOKW_PROGRESS + 48)
-__global__ void __launch_bounds__(32 * VP8B_MAX_PARTS) k_parse_tokens(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
+#define TOKW_MAX_WARPS 28   // 7 per SM sub-partition: what the register file holds at 64 registers per thread
+// A block owns ipb images x P partitions; warp w parses partition w % P of the block's image w / P. Packing 28
+// warps into one block per SM puts exactly seven streams on every sub-partition (single-warp blocks are spread by
+// the hardware as it sees fit, and the sub-partition that gets an eighth stream finishes last).
+__global__ void __launch_bounds__(32 * TOKW_MAX_WARPS, 1) k_parse_tokens(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
                                                                       FrameHdr* hdrs, uint32_t* mbinfo, int16_t* coeffs,
-                                                                      const int* __restrict__ ids, int P) {
-  extern __shared__ __align__(16) uint8_t smem[];
+                                                                      const int* __restrict__ ids, int count, int P, int ipb, int slot_bytes) {
+  extern __shared__ __align__(16) uint8_t smem_all[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slot = warp / P, part = warp % P;
+  const int g = blockIdx.x * ipb + slot;
+  const int live = slot < ipb && g < count;
+  uint8_t* smem = smem_all + (size_t)(live ? slot : 0) * slot_bytes;
   uint8_t* probs = smem;
   volatile int* progress = (volatile int*)(smem + TOKW_PROGRESS);   // P ints (+ status word)
   uint16_t* topctx = (uint16_t*)(smem + TOKW_CTX);                  // (P+1) * mb_w
-  const int img = ids[blockIdx.x];
+  const int img = live ? ids[g] : 0;
   const ImgDesc im = imgs[img];
   FrameHdr* h = &hdrs[img];
-  const int tid = threadIdx.x, lane = tid & 31, part = tid >> 5;
-  for (int k = tid; k < VP8B_POSPROB_BYTES; k += blockDim.x) probs[k] = posprob_byte(h->prob, k);
-  if (tid < P) progress[tid] = 0;
-  if (tid == 0) progress[VP8B_MAX_PARTS] = (h->status == VP8B_OK && h->num_parts == P) ? 1 : 0;
+  if (live) {
+    const int t = part * 32 + lane;   // this image's threads
+    for (int k = t; k < VP8B_POSPROB_BYTES; k += 32 * P) probs[k] = posprob_byte(h->prob, k);
+    if (t < P) progress[t] = 0;
+    if (t == 0) progress[VP8B_MAX_PARTS] = (h->status == VP8B_OK && h->num_parts == P) ? 1 : 0;
+  }
   __syncthreads();
+  if (!live) return;
   if (!progress[VP8B_MAX_PARTS]) {   // header failed (or, never expected, the host pre-scan disagreed)
-    if (tid == 0 && h->status == VP8B_OK) h->status = VP8B_BITSTREAM_ERROR;
+    if (part == 0 && lane == 0 && h->status == VP8B_OK) h->status = VP8B_BITSTREAM_ERROR;
     return;
   }
   const int rows = h->rows;
@@ -228,7 +243,7 @@ __host__ __device__ static inline TlLayout tl_layout(int P, int ipb, int ctx_str
   return t;
 }
 
-__global__ void __launch_bounds__(32 * 8, 1) k_parse_tokens_lockstep(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
+__global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_lockstep(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
                                                                   FrameHdr* hdrs, uint32_t* mbinfo, int16_t* coeffs,
                                                                   const int* __restrict__ ids, int count, int P, int ipb, int lpw,
                                                                   int cw, int ctx_stride) {
@@ -409,21 +424,35 @@ static size_t recon_smem_bytes(int max_mb_w, int max_mb_h) {
   return sizeof(ReconWs) * RECON_WARPS + ((recon_ctx_bytes(max_mb_w, max_mb_h) + 15) & ~(size_t)15);
 }
 
-static size_t tokens_smem_bytes(int P, int max_mb_w) {
-  return TOKW_CTX + (size_t)(P + 1) * max_mb_w * 2;
+static size_t tokens_slot_bytes(int P, int max_mb_w) {
+  return (TOKW_CTX + (size_t)(P + 1) * max_mb_w * 2 + 15) & ~(size_t)15;
 }
 
 extern "C" cudaError_t vp8k_configure(int max_mb_w, int max_mb_h) {
   cudaError_t e = cudaFuncSetAttribute(k_reconstruct, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)recon_smem_bytes(max_mb_w, max_mb_h));
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_parse_tokens, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)tokens_smem_bytes(VP8B_MAX_PARTS, max_mb_w));
+  return cudaSuccess;
+}
+
+static int pack_per_block(int count, int max_per_block) {   // as many as fit, but no fewer than 148 blocks where the launch allows
+  int ipb = max_per_block;
+  while (ipb > 1 && (count + ipb - 2) / (ipb - 1) <= 148) --ipb;
+  return ipb;
 }
 
 extern "C" void vp8k_parse_modes(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,
                                  int first, int count, int max_mb_w) {
-  k_parse_modes<<<count, 32, (size_t)max_mb_w * 4, s>>>(arena, imgs, hdrs, mbinfo, first, count);
+  int ipb = MODES_WARPS;
+  while (ipb > 1 && (size_t)ipb * max_mb_w * 4 > 200u * 1024u) --ipb;
+  ipb = pack_per_block(count, ipb);
+  static size_t configured = 0;
+  const size_t smem = (size_t)ipb * max_mb_w * 4;
+  if (smem > configured) {
+    cudaFuncSetAttribute(k_parse_modes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  k_parse_modes<<<(count + ipb - 1) / ipb, 32 * ipb, smem, s>>>(arena, imgs, hdrs, mbinfo, first, count, ipb, max_mb_w);
 }
 
 static int env_int(const char* name) {
@@ -463,7 +492,7 @@ static void launch_tokens_lockstep(cudaStream_t s, const uint8_t* arena, const I
                                    int16_t* coeffs, const int* ids, int count, int P, int max_mb_w) {
   static int f_lpw = -1, f_cw = -1;
   if (f_lpw < 0) { f_lpw = env_int("WEBP_B200_TOKEN_LPW"); f_cw = env_int("WEBP_B200_TOKEN_CW"); }
-  int cw = (f_cw == 2 || f_cw == 4 || f_cw == 8) ? f_cw : 4;
+  int cw = (f_cw >= 1 && f_cw <= 16) ? f_cw : (P > 1 ? 16 : 8);
   const long streams = (long)count * P;
   int lpw = (int)((streams + 148L * cw - 1) / (148L * cw));
   if (f_lpw >= 1 && f_lpw <= 32) lpw = f_lpw;
@@ -484,19 +513,35 @@ static void launch_tokens_lockstep(cudaStream_t s, const uint8_t* arena, const I
 
 extern "C" void vp8k_parse_tokens(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,
                                   int16_t* coeffs, const int* ids, int count, int P, int max_mb_w) {
-  // Two mappings of the same parse: one warp per partition (straight-line code on one lane, latency hidden by
-  // the other warps of the SM) and the lane-parallel state machine. WEBP_B200_TOKEN_MAP=warp|lanes picks one.
+  // Three mappings of the same parse: one warp per partition (straight-line code on one lane; seven warps per SM
+  // sub-partition keep its issue port busy), the lockstep lanes (vp8_tokens_lockstep.h: a third of the issue slots
+  // per decode, but one iteration costs a whole dependent chain, so it needs several warps per sub-partition to
+  // pay), and the older table-driven state machine (vp8_tokens_fsm.h). WEBP_B200_TOKEN_MAP=warp|k|lanes forces one.
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("WEBP_B200_TOKEN_MAP");
     forced = (e && e[0] == 'w') ? 1 : (e && e[0] == 'l') ? 2 : (e && e[0] == 'k') ? 3 : 0;
   }
-  if (forced == 3) { launch_tokens_lockstep(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, max_mb_w); return; }
-  // Up to ~16 streams per SM sub-partition the straight-line parser keeps the issue slots busy on its own; beyond
-  // that the state machine's shared instruction stream wins (measured: profiles/r01*_token_map_sweep.log).
-  const int use_warp_map = forced ? (forced == 1) : ((long)count * P <= 148L * 4 * 16);
+  // Measured (profiles/r01i_token_map_sweep.log): 4096 streams: warp 377 ms, lockstep 418; 32768 streams (8 partitions):
+  // warp 420, state machine 247, lockstep 168; 65536 thumbnails: warp 274, lockstep 208.
+  const int many = (long)count * P > 148L * 4 * 16;
+  if (forced == 3 || (forced == 0 && many)) { launch_tokens_lockstep(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, max_mb_w); return; }
+  const int use_warp_map = forced ? (forced == 1) : 1;
   if (use_warp_map) {
-    k_parse_tokens<<<count, 32 * P, tokens_smem_bytes(P, max_mb_w), s>>>(arena, imgs, hdrs, mbinfo, coeffs, ids, P);
+    // one block per SM where the launch fits in one wave, else as many images per block as the block may hold
+    static int f_ipb = -1;
+    if (f_ipb < 0) f_ipb = env_int("WEBP_B200_TOKEN_IPB");
+    const int slot = (int)tokens_slot_bytes(P, max_mb_w);
+    int ipb = TOKW_MAX_WARPS / P;
+    if (f_ipb >= 1 && f_ipb <= ipb) ipb = f_ipb;
+    while (ipb > 1 && (size_t)ipb * slot > 200u * 1024u) --ipb;
+    ipb = pack_per_block(count, ipb);
+    static size_t configured = 0;
+    if ((size_t)ipb * slot > configured) {
+      cudaFuncSetAttribute(k_parse_tokens, cudaFuncAttributeMaxDynamicSharedMemorySize, ipb * slot);
+      configured = (size_t)ipb * slot;
+    }
+    k_parse_tokens<<<(count + ipb - 1) / ipb, 32 * ipb * P, (size_t)ipb * slot, s>>>(arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, ipb, slot);
     return;
   }
   launch_tokens_fsm(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, max_mb_w);
