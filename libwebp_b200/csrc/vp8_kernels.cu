@@ -293,17 +293,18 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_lockstep(const uint
   // at that loop's exit for the longest block in the warp.)
   if (P > 1) {
     while (__any_sync(0xffffffffu, L.alive)) {
-      bd_fill(L.d);
+      bd_fill_lookahead(L.d);
       tl_step<1>(L, c); tl_step<1>(L, c); tl_step<1>(L, c); tl_step<1>(L, c);
     }
   } else {
     if (have && !tl_mb_next(L, c)) tl_lane_park(L, c);
     while (__any_sync(0xffffffffu, L.alive)) {
-      bd_fill(L.d);
+      bd_fill_lookahead(L.d);
       tl_step<0>(L, c); tl_step<0>(L, c); tl_step<0>(L, c); tl_step<0>(L, c);
     }
   }
   if (have && L.status != VP8B_OK) h->status = L.status;
+  if (L.sink == 0xffffffffu) h->status = VP8B_BITSTREAM_ERROR;   // never true (an XOR of bytes): keeps TlLane::sink alive
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -124,6 +124,22 @@ VP8_FN void bd_fill(BoolDec& d) {
   }
 }
 
+// bd_fill() for a warp whose lanes all wait when one waits (vp8_tokens_lockstep.h): the word fetched here is not
+// looked at before the NEXT fill -- not even to replace it by zero past the end of the stream, which bd_fetch()
+// does with a select that has to wait for the load. The load address is clamped instead and the zero is chosen
+// when the word is consumed.
+VP8_FN void bd_fill_lookahead(BoolDec& d) {
+  if (d.nbits <= 32) {
+    const uint32_t* p = d.wp;   // d.nxt came from p - 1
+    const uint32_t w = (p - 1 < d.wend) ? VP8_BSWAP(d.nxt) : 0u;
+    d.nxt = VP8_LDG(p < d.wend ? p : d.wend);   // wend itself lies inside the arena's tail padding
+    d.wp = p + 1;
+    d.V |= vp8_shr_clamp(w, d.nbits);
+    d.vlo = vp8_shl_clamp(w, 32 - d.nbits);
+    d.nbits += 32;
+  }
+}
+
 // One decode given (split + 1) << 24; needs >= 8 valid bits.
 VP8_FN int bd_decode(BoolDec& d, uint32_t s1) {
   const int bit = d.V >= s1;

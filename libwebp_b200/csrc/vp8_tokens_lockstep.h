@@ -92,11 +92,11 @@ TK_FN uint8_t tl_row_byte(const uint8_t* prob /* [4][8][3][11] */, int t, int n,
 
 // Block-wide tables in shared memory.
 struct TlTables {
-  uint32_t trans[64][2];   // [s][bit]
+  uint32_t trans[128][2];  // [s + 64 * adv][bit]: indexed by the low 7 bits of the entry that led here (both halves alike)
   uint32_t seqmask[28];    // block seq (0 = Y2, 1..16 luma, 17..24 chroma): its two context bits inside TlLane::cx
 };
-#define TLT_SEQMASK 512
-#define TL_TAB_BYTES 624    // sizeof(TlTables)
+#define TLT_SEQMASK 1024
+#define TL_TAB_BYTES 1136    // sizeof(TlTables)
 
 TK_FN uint32_t tl_seqmask(int k) {
   if (k == 0) return (1u << 8) | (1u << 24);
@@ -109,7 +109,10 @@ TK_FN uint32_t tl_seqmask(int k) {
 }
 
 TK_FN void tl_tables_fill(TlTables* t, int tid, int nthreads) {
-  for (int k = tid; k < 128; k += nthreads) t->trans[k >> 1][k & 1] = (k >> 1) < TL_STATES ? tl_trans_entry(k >> 1, k & 1) : TL_E(63, 0, 0);   // 63 = TL_DEAD
+  for (int k = tid; k < 256; k += nthreads) {
+    const int st = (k >> 1) & 63;
+    t->trans[k >> 1][k & 1] = st < TL_STATES ? tl_trans_entry(st, k & 1) : TL_E(63, 0, 0);   // 63 = TL_DEAD
+  }
   for (int k = tid; k < 28; k += nthreads) t->seqmask[k] = tl_seqmask(k);
 }
 
@@ -127,7 +130,9 @@ TK_FN void tl_image_fill(uint8_t* dst, const FrameHdr* h, int tid, int nthreads)
 struct TlLane {
   BoolDec d;
   tk_saddr row, rowend;   // current row, row of position 16 of the current block type
-  uint32_t s;
+  uint32_t s;             // state the current block started in (tl_block_setup -> tl_prime); the walk itself lives in e0/e1
+  uint32_t sink;          // see tl_step (never meaningful)
+  uint32_t prob, e0, e1;  // the pending decode: its probability and the transition entries of its two outcomes
   uint32_t v;             // magnitude under construction
   int16_t* blkcoef;       // the current block's 16 coefficients
   uint32_t ofs;           // - (row of position 0 of the current block type) / 32, see the store in tl_step
@@ -159,7 +164,7 @@ struct TlCtx {
 };
 
 TK_FN void tl_lane_reset(TlLane& L, const TlCtx& c) {
-  L.row = 0; L.rowend = 0; L.s = 0; L.v = 0; L.blkcoef = c.coeffs; L.ofs = 0; L.cx = 0; L.acc_lo = 0; L.acc_hi = 0; L.m = 0; L.seq = 0; L.first = 0;
+  L.row = 0; L.rowend = 0; L.s = 0; L.sink = 0; L.prob = 0; L.e0 = 0; L.e1 = 0; L.v = 0; L.blkcoef = c.coeffs; L.ofs = 0; L.cx = 0; L.acc_lo = 0; L.acc_hi = 0; L.m = 0; L.seq = 0; L.first = 0;
   L.ystart = 0; L.yend = 0; L.mbcoef = c.coeffs;
   L.mx = 0; L.my = c.part; L.done_mbs = 0; L.waiting = 1; L.alive = 1; L.status = VP8B_OK;
   L.w = 0; L.w_next = 0;
@@ -169,6 +174,12 @@ TK_FN void tl_lane_init(TlLane& L, const TlCtx& c, const uint8_t* frame, const F
   bd_init(L.d, frame + h->part_off[c.part], h->part_size[c.part]);
   tl_lane_reset(L, c);
   L.w_next = (c.part < c.rows) ? VP8_LDG(c.mbinfo + 4 * ((size_t)c.part * c.mb_w) + 3) : 0;
+}
+
+// Loads the pending decode (probability, both transition entries) of state L.s in row L.row.
+TK_FN void tl_prime(TlLane& L, const TlCtx& c) {
+  L.prob = tk_lds_u8(L.row + L.s);
+  tk_lds_v2(c.tab_s + L.s * 8u, L.e0, L.e1);
 }
 
 // Sets up block L.seq (contexts in L.cx are final for it).
@@ -191,6 +202,7 @@ TK_FN void tl_block_setup(TlLane& L, const TlCtx& c) {
   }
   L.ofs = 0u - (uint32_t)((L.rowend - TL_TYPE_BYTES) >> 5);
   L.s = ctx * 11u;
+  tl_prime(L, c);
 }
 
 // Leaves the lane either with a block set up (returns 1), waiting for the row above (returns 0, L.waiting = 1) or
@@ -271,6 +283,7 @@ TK_FN void tl_mb_finish(TlLane& L, const TlCtx& c) {
 #define TL_DEAD 63u
 TK_FN void tl_lane_park(TlLane& L, const TlCtx& c) {
   L.s = TL_DEAD; L.row = c.img_s; L.rowend = 0; L.alive = 0; L.waiting = 0;
+  tl_prime(L, c);
 }
 
 // A lane without a stream: a reader over zero bytes at `any` (a valid address), parked from the start.
@@ -293,15 +306,24 @@ TK_FN int tl_step(TlLane& L, const TlCtx& c) {
       }
     }
   }
+  // ---- what the NEXT decode needs, fetched for both outcomes of this one before its bit is known: the dependent
+  // chain of an iteration is then select -> multiply -> compare, and the shared-memory latency runs beside it.
+  // (ADV is bit 6 = the row stride, so `row + (e & 127)` is the next probability's address as it stands.)
+  const uint32_t o0 = L.e0 & 127u, o1 = L.e1 & 127u;
+  uint32_t e00, e01, e10, e11;
+  tk_lds_v2_pinned(c.tab_s + o0 * 8u, e00, e01);
+  tk_lds_v2_pinned(c.tab_s + o1 * 8u, e10, e11);
+  const uint32_t p0 = tk_lds_u8_pinned(L.row + o0), p1 = tk_lds_u8_pinned(L.row + o1);
   // ---- boolean decode (bit_reader_inl_utils.h:107-136)
-  const uint32_t prob = tk_lds_u8(L.row + L.s);
-  uint32_t e0, e1;
-  tk_lds_v2(c.tab_s + L.s * 8u, e0, e1);
-  const int bit = bd_bit_nofill(L.d, prob);
+  const int bit = bd_bit_nofill(L.d, L.prob);
   // ---- transition
-  const uint32_t e = bit ? e1 : e0;
+  const uint32_t e = bit ? L.e1 : L.e0;
+  L.prob = bit ? p1 : p0;
+  L.sink ^= p1;   // an unconditional use: without it the assembler folds the select into a load of p1 predicated on the
+                  // bit, which puts the shared-memory latency straight back on the dependent chain
+  L.e0 = bit ? e10 : e00;
+  L.e1 = bit ? e11 : e01;
   const uint32_t adv = e & TL_ADV;
-  L.s = e & 63u;
   L.v += e >> 16;
   if (e & TL_EMIT) {   // level, parse order: coefficient n of the block sits at byte 2n = (row - row of n = 0) / 32
     *(int16_t*)((uint8_t*)L.blkcoef + (uint32_t)((L.row >> 5) + L.ofs)) = (int16_t)(bit ? -(int)L.v : (int)L.v);

@@ -86,7 +86,7 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
   // K2: tokens
   if (variant & 8) {   // lockstep parser: one lane per partition, one decode per lane per round
     const int P = hdr.num_parts;
-    std::vector<uint8_t> imgmem(TL_IMG_BYTES + 16);
+    std::vector<uint8_t> imgmem(TL_IMG_BYTES + 16 + 128);   // the look-ahead loads run up to 63 bytes past the rows
     uint8_t* img16 = (uint8_t*)(((uintptr_t)imgmem.data() + 15) & ~(uintptr_t)15);
     std::vector<uint64_t> tabmem((sizeof(TlTables) + 7) / 8);
     TlTables* ttab = (TlTables*)tabmem.data();
@@ -112,7 +112,7 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
       for (int p = P - 1; p >= 0; --p) {   // reverse order: exercises the wait-for-progress path
         if (!live[p]) continue;
         any = true;
-        bd_fill(lanes[p].d);
+        bd_fill_lookahead(lanes[p].d);
         for (int k = 0; k < 4; ++k) {   // parked lanes keep stepping, harmlessly, like on the device
           if (P > 1) tl_step<1>(lanes[p], ctxs[p]); else tl_step<0>(lanes[p], ctxs[p]);
         }
