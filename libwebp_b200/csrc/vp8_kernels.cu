@@ -281,6 +281,9 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_lockstep(const uint
   c.coeffs = coeffs + (size_t)im.mb_base * VP8B_COEFFS_PER_MB;
   c.mb_w = im.mb_w; c.rows = have ? h->rows : 0; c.P = P; c.part = part; c.use_skip = h->use_skip; c.ctx_stride = ctx_stride;
   if (part >= c.rows) have = 0;
+  // per-lane copies of what the rare paths need: left as kernel parameters they are re-read from the constant bank
+  // in every iteration (the loads get hoisted above the branches that need them)
+  asm volatile("" : "+r"(c.P), "+r"(c.ctx_stride), "+r"(c.mb_w), "+l"(c.mbinfo), "+l"(c.coeffs));
   TlLane L;
   if (have) {
     tl_lane_init(L, c, arena + im.in_off, h);
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_lockstep(const uint
       tl_step<1>(L, c); tl_step<1>(L, c); tl_step<1>(L, c); tl_step<1>(L, c);
     }
   } else {
-    if (have && !tl_mb_next(L, c)) tl_lane_park(L, c);
+    if (have && !tl_mb_next<0>(L, c)) tl_lane_park(L, c);
     while (__any_sync(0xffffffffu, L.alive)) {
       bd_fill_lookahead(L.d);
       tl_step<0>(L, c); tl_step<0>(L, c); tl_step<0>(L, c); tl_step<0>(L, c);

@@ -130,19 +130,19 @@ TK_FN void tl_image_fill(uint8_t* dst, const FrameHdr* h, int tid, int nthreads)
 struct TlLane {
   BoolDec d;
   tk_saddr row, rowend;   // current row, row of position 16 of the current block type
-  uint32_t s;             // state the current block started in (tl_block_setup -> tl_prime); the walk itself lives in e0/e1
+  uint32_t s;             // state the current block started in (tl_prime); the walk itself lives in e0/e1
   uint32_t sink;          // see tl_step (never meaningful)
   uint32_t prob, e0, e1;  // the pending decode: its probability and the transition entries of its two outcomes
   uint32_t v;             // magnitude under construction
-  int16_t* blkcoef;       // the current block's 16 coefficients
-  uint32_t ofs;           // - (row of position 0 of the current block type) / 32, see the store in tl_step
+  uint32_t ofs;           // coefficient n of the current block goes to byte (row >> 5) + ofs of the macroblock's 800
   uint32_t cx;            // non-zero contexts: top in bits 0-8 (0-3 luma, 4-5 U, 6-7 V, 8 Y2), left in bits 16-24
   uint32_t acc_lo, acc_hi;// 2-bit nz codes of the macroblock's blocks shifted in, in parse order
   uint32_t m;             // context bits of the current block (seqmask)
+  uint32_t lut;           // nz -> 2-bit code of the current block: 2-bit fields indexed by min(nz, 4)
   int seq;                // 0 = Y2, 1..16 luma, 17..24 chroma
-  uint32_t first;         // first coefficient of the current block (1 for the luma blocks of i16 macroblocks)
   // macroblock
-  tk_saddr ystart, yend;  // luma rows of this macroblock: start, end
+  tk_saddr yrow, yend;    // luma rows of this macroblock: first one parsed, end
+  uint32_t yofs, ylut;    // luma blocks: ofs - 32 * seq, lut
   int16_t* mbcoef;
   uint32_t w, w_next;     // MbInfo word 3 of this / the partition's next macroblock
   int mx, my;
@@ -151,6 +151,8 @@ struct TlLane {
   int alive;              // 0 once parked
   int status;
 };
+#define TL_LUT_FROM0 0x3a4u   // nz 0 -> 0, 1 -> 1 (a lone DC level: re-examined after dequantisation, recon_macroblock), 2,3 -> 2, >= 4 -> 3
+#define TL_LUT_FROM1 0x3a0u   // luma blocks of i16 macroblocks start at coefficient 1: nz = 1 means empty
 
 // Per-lane constants.
 struct TlCtx {
@@ -164,8 +166,9 @@ struct TlCtx {
 };
 
 TK_FN void tl_lane_reset(TlLane& L, const TlCtx& c) {
-  L.row = 0; L.rowend = 0; L.s = 0; L.sink = 0; L.prob = 0; L.e0 = 0; L.e1 = 0; L.v = 0; L.blkcoef = c.coeffs; L.ofs = 0; L.cx = 0; L.acc_lo = 0; L.acc_hi = 0; L.m = 0; L.seq = 0; L.first = 0;
-  L.ystart = 0; L.yend = 0; L.mbcoef = c.coeffs;
+  L.row = 0; L.rowend = 0; L.s = 0; L.sink = 0; L.prob = 0; L.e0 = 0; L.e1 = 0; L.v = 0; L.ofs = 0; L.cx = 0;
+  L.acc_lo = 0; L.acc_hi = 0; L.m = 0; L.lut = 0; L.seq = 0;
+  L.yrow = 0; L.yend = 0; L.yofs = 0; L.ylut = 0; L.mbcoef = c.coeffs;
   L.mx = 0; L.my = c.part; L.done_mbs = 0; L.waiting = 1; L.alive = 1; L.status = VP8B_OK;
   L.w = 0; L.w_next = 0;
 }
@@ -182,47 +185,76 @@ TK_FN void tl_prime(TlLane& L, const TlCtx& c) {
   tk_lds_v2(c.tab_s + L.s * 8u, L.e0, L.e1);
 }
 
-// Sets up block L.seq (contexts in L.cx are final for it).
+TK_FN uint32_t tl_popc(uint32_t x) {
+#if defined(__CUDACC__) && !defined(VP8_EMU)
+  return (uint32_t)__popc(x);
+#else
+  return (uint32_t)__builtin_popcount(x);
+#endif
+}
+
+// Sets up block L.seq >= 1 (contexts in L.cx are final for it). Luma blocks sit at 32 * (seq - 1) bytes of the
+// macroblock's coefficients, chroma blocks follow them (blocks 16..23 = seq 17..24).
 TK_FN void tl_block_setup(TlLane& L, const TlCtx& c) {
   const int chroma = L.seq >= 17;
+  const tk_saddr crow = c.img_s + 2 * TL_TYPE_BYTES;
   L.m = tk_lds_u32(c.tab_s + TLT_SEQMASK + 4u * (uint32_t)L.seq);
-#if defined(__CUDACC__) && !defined(VP8_EMU)
-  const uint32_t ctx = (uint32_t)__popc(L.cx & L.m);
-#else
-  const uint32_t ctx = (uint32_t)__builtin_popcount(L.cx & L.m);
-#endif
-  if (L.seq == 0) {            // Y2: type 1, block 24
-    L.row = c.img_s + 1 * TL_TYPE_BYTES; L.rowend = L.row + TL_TYPE_BYTES; L.first = 0;
-    L.blkcoef = L.mbcoef + 24 * 16;
-  } else {
-    L.rowend = chroma ? c.img_s + 3 * TL_TYPE_BYTES : L.yend;
-    L.row = chroma ? c.img_s + 2 * TL_TYPE_BYTES : L.ystart;
-    L.first = chroma ? 0u : (uint32_t)((L.yend - L.ystart) != TL_TYPE_BYTES);
-    L.blkcoef = L.mbcoef + (L.seq - 1) * 16;
-  }
-  L.ofs = 0u - (uint32_t)((L.rowend - TL_TYPE_BYTES) >> 5);
-  L.s = ctx * 11u;
+  L.rowend = chroma ? crow + TL_TYPE_BYTES : L.yend;
+  L.row = chroma ? crow : L.yrow;
+  L.lut = chroma ? TL_LUT_FROM0 : L.ylut;
+  L.ofs = (uint32_t)L.seq * 32u + (chroma ? 0u - 32u - (uint32_t)(crow >> 5) : L.yofs);
+  L.s = tl_popc(L.cx & L.m) * 11u;
   tl_prime(L, c);
+}
+
+// The Y2 block of an i16 macroblock (seq 0): type 1, block 24.
+TK_FN void tl_y2_setup(TlLane& L, const TlCtx& c) {
+  L.m = (1u << 8) | (1u << 24);
+  L.row = c.img_s + 1 * TL_TYPE_BYTES;
+  L.rowend = L.row + TL_TYPE_BYTES;
+  L.lut = TL_LUT_FROM0;
+  L.ofs = 24u * 32u - (uint32_t)(L.row >> 5);
+  L.s = tl_popc(L.cx & L.m) * 11u;
+  tl_prime(L, c);
+}
+
+// Stores a finished (or skipped) macroblock's results and steps to the partition's next macroblock.
+template <int MULTI>
+TK_FN void tl_mb_store(TlLane& L, const TlCtx& c, uint32_t nzy, uint32_t w3) {
+  const int P = MULTI ? c.P : 1, mb_w = c.mb_w;
+  const size_t idx = (size_t)L.my * mb_w + L.mx;
+  c.mbinfo[4 * idx + 2] = nzy;
+  c.mbinfo[4 * idx + 3] = w3;
+  const int ring_row = MULTI ? L.my % (P + 1) : (L.my & 1);
+  c.topctx[(size_t)ring_row * c.ctx_stride + L.mx] = (uint16_t)(L.cx & 0x1ffu);
+  L.done_mbs++;
+  if (++L.mx == mb_w) { L.mx = 0; L.my += P; }
+  if (bd_eof(L.d)) {
+    // Ran past the end of the partition: the image is lost (vp8_dec.c:651-659); release whoever waits on us.
+    L.status = VP8B_NOT_ENOUGH_DATA;
+    if (MULTI) { TK_FENCE(); c.progress[c.part] = 0x7fffffff; }
+  } else if (MULTI) { TK_FENCE(); c.progress[c.part] = L.done_mbs; }
 }
 
 // Leaves the lane either with a block set up (returns 1), waiting for the row above (returns 0, L.waiting = 1) or
 // finished (returns 0, L.waiting = 0, L.my >= rows or L.status != OK). Skipped macroblocks are consumed here.
+template <int MULTI>
 TK_FN int tl_mb_next(TlLane& L, const TlCtx& c) {
-  const int P = c.P, mb_w = c.mb_w;
+  const int P = MULTI ? c.P : 1, mb_w = c.mb_w;
   for (;;) {
     if (L.my >= c.rows || L.status != VP8B_OK) { L.waiting = 0; return 0; }
     uint32_t tctx = 0;
     if (L.my > 0) {
-      if (P > 1) {
+      if (MULTI) {
         const int prev = (c.part + P - 1) % P;
         const int need = ((L.my - 1 - prev) / P) * mb_w + L.mx + 1;
         if (c.progress[prev] < need) { L.waiting = 1; return 0; }
         TK_FENCE();
       }
-      tctx = c.topctx[(size_t)((L.my + P) % (P + 1)) * c.ctx_stride + L.mx];
+      const int ring_row = MULTI ? (L.my + P) % (P + 1) : ((L.my + 1) & 1);
+      tctx = c.topctx[(size_t)ring_row * c.ctx_stride + L.mx];
     }
     L.waiting = 0;
-    const size_t idx = (size_t)L.my * mb_w + L.mx;
     L.w = L.w_next;
     {   // flags of this partition's next macroblock: needed one macroblock from here
       int nx = L.mx + 1, ny = L.my;
@@ -232,50 +264,32 @@ TK_FN int tl_mb_next(TlLane& L, const TlCtx& c) {
     if (L.mx == 0) L.cx = 0;
     L.cx = (L.cx & 0xffff0000u) | tctx;
     const int is_i4 = (L.w & MBW_I4X4) != 0;
-    uint32_t nzy = 0, nzuv = 0;
-    const int skipped = c.use_skip && (L.w & MBW_SKIP);
-    if (!skipped) {
+    if (!(c.use_skip && (L.w & MBW_SKIP))) {
       L.acc_lo = 0; L.acc_hi = 0;
-      L.mbcoef = c.coeffs + idx * VP8B_COEFFS_PER_MB;
-      L.yend = c.img_s + (is_i4 ? 4u : 1u) * TL_TYPE_BYTES;                 // type 3 (with DC) or type 0 (from n = 1)
-      L.ystart = L.yend - TL_TYPE_BYTES + (is_i4 ? 0u : (uint32_t)TL_ROW_BYTES);
-      L.seq = is_i4 ? 1 : 0;
-      tl_block_setup(L, c);
+      L.mbcoef = c.coeffs + ((size_t)L.my * mb_w + L.mx) * VP8B_COEFFS_PER_MB;
+      // luma: type 3 from coefficient 0 (i4x4) or type 0 from coefficient 1 (after the Y2 block)
+      const tk_saddr ybase = c.img_s + (is_i4 ? 3u : 0u) * TL_TYPE_BYTES;
+      L.yend = ybase + TL_TYPE_BYTES;
+      L.yrow = ybase + (is_i4 ? 0u : (uint32_t)TL_ROW_BYTES);
+      L.ylut = is_i4 ? TL_LUT_FROM0 : TL_LUT_FROM1;
+      L.yofs = 0u - 32u - (uint32_t)(ybase >> 5);
+      if (is_i4) { L.seq = 1; tl_block_setup(L, c); } else { L.seq = 0; tl_y2_setup(L, c); }
       return 1;
     }
     L.cx &= is_i4 ? 0x01000100u : 0u;
-    // finish the skipped macroblock (same stores as tl_mb_finish with empty codes)
-    c.mbinfo[4 * idx + 2] = nzy;
-    c.mbinfo[4 * idx + 3] = (L.w & 0xffff0000u) | nzuv;
-    c.topctx[(size_t)(L.my % (P + 1)) * c.ctx_stride + L.mx] = (uint16_t)(L.cx & 0x1ffu);
-    L.done_mbs++;
-    if (++L.mx == mb_w) { L.mx = 0; L.my += P; }
-    if (bd_eof(L.d)) {
-      L.status = VP8B_NOT_ENOUGH_DATA;
-      if (P > 1) { TK_FENCE(); c.progress[c.part] = 0x7fffffff; }
-    } else if (P > 1) { TK_FENCE(); c.progress[c.part] = L.done_mbs; }
+    tl_mb_store<MULTI>(L, c, 0u, L.w & 0xffff0000u);
   }
 }
 
 // The macroblock's last block has ended: store its results, move on.
+template <int MULTI>
 TK_FN void tl_mb_finish(TlLane& L, const TlCtx& c) {
-  const int P = c.P, mb_w = c.mb_w;
-  const size_t idx = (size_t)L.my * mb_w + L.mx;
   const uint32_t nzy = (L.acc_hi << 16) | (L.acc_lo >> 16);
   const uint32_t uv = L.acc_lo & 0xffffu;                      // U codes in bits 15-8, V in 7-0
   const uint32_t nzuv = (uv >> 8) | ((uv & 0xffu) << 8);       // reference order: U bits 0-7, V bits 8-15
   uint32_t w = L.w;
   if ((L.acc_hi >> 16) & 3u) w |= MBW_HAS_Y2;                  // the Y2 block's code, shifted in first
-  c.mbinfo[4 * idx + 2] = nzy;
-  c.mbinfo[4 * idx + 3] = (w & 0xffff0000u) | nzuv;
-  c.topctx[(size_t)(L.my % (P + 1)) * c.ctx_stride + L.mx] = (uint16_t)(L.cx & 0x1ffu);
-  L.done_mbs++;
-  if (++L.mx == mb_w) { L.mx = 0; L.my += P; }
-  if (bd_eof(L.d)) {
-    // Ran past the end of the partition: the image is lost (vp8_dec.c:651-659); release whoever waits on us.
-    L.status = VP8B_NOT_ENOUGH_DATA;
-    if (P > 1) { TK_FENCE(); c.progress[c.part] = 0x7fffffff; }
-  } else if (P > 1) { TK_FENCE(); c.progress[c.part] = L.done_mbs; }
+  tl_mb_store<MULTI>(L, c, nzy, (w & 0xffff0000u) | nzuv);
 }
 
 // Parks a lane that has nothing (more) to do: state 63 decodes a zero probability for ever, never emits, never
@@ -293,14 +307,20 @@ TK_FN void tl_lane_idle(TlLane& L, const TlCtx& c, const uint8_t* any) {
   tl_lane_park(L, c);
 }
 
-// One iteration: one boolean decode and its consequences; the caller has topped the window up (bd_fill) within
-// the last three decodes. Returns 0 when the lane has finished (it is parked then).
+#if defined(__GNUC__) || defined(__CUDACC__)
+#define TL_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#else
+#define TL_UNLIKELY(x) (x)
+#endif
+
+// One iteration: one boolean decode and its consequences; the caller has topped the window up (bd_fill_lookahead)
+// within the last three decodes. Returns 0 when the lane has finished (it is parked then).
 // MULTI = the image has several token partitions (lanes may have to wait for the row above).
 template <int MULTI>
 TK_FN int tl_step(TlLane& L, const TlCtx& c) {
   if (MULTI) {
     if (L.waiting) {
-      if (!tl_mb_next(L, c)) {
+      if (!tl_mb_next<MULTI>(L, c)) {
         if (!L.waiting) tl_lane_park(L, c);
         return L.alive;
       }
@@ -323,25 +343,23 @@ TK_FN int tl_step(TlLane& L, const TlCtx& c) {
                   // bit, which puts the shared-memory latency straight back on the dependent chain
   L.e0 = bit ? e10 : e00;
   L.e1 = bit ? e11 : e01;
-  const uint32_t adv = e & TL_ADV;
   L.v += e >> 16;
-  if (e & TL_EMIT) {   // level, parse order: coefficient n of the block sits at byte 2n = (row - row of n = 0) / 32
-    *(int16_t*)((uint8_t*)L.blkcoef + (uint32_t)((L.row >> 5) + L.ofs)) = (int16_t)(bit ? -(int)L.v : (int)L.v);
+  if (e & TL_EMIT) {   // level, parse order
+    *(int16_t*)((uint8_t*)L.mbcoef + (uint32_t)((L.row >> 5) + L.ofs)) = (int16_t)(bit ? -(int)L.v : (int)L.v);
     L.v = 0;
   }
-  L.row += adv;
-  if ((e & TL_EOB) || L.row == L.rowend) {
+  L.row += e & TL_ADV;
+  if (TL_UNLIKELY((e & TL_EOB) || L.row == L.rowend)) {
     // ---- end of block (GetCoeffs' return value nz; ParseResiduals' bookkeeping, vp8_dec.c:517-609)
-    const uint32_t nz = 16u - (uint32_t)((L.rowend - L.row) >> 6);
-    const uint32_t l = nz > L.first ? 1u : 0u;
-    const uint32_t code = nz > 3 ? 3u : nz > 1 ? 2u : l;   // a lone DC level is re-examined after dequantisation (recon_macroblock)
+    const uint32_t nz2 = 32u - (uint32_t)((L.rowend - L.row) >> 5);   // 2 * nz
+    const uint32_t code = (L.lut >> (nz2 < 8u ? nz2 : 8u)) & 3u;       // non-zero exactly when the block counts as non-empty
     L.acc_hi = (L.acc_hi << 2) | (L.acc_lo >> 30);
     L.acc_lo = (L.acc_lo << 2) | code;
-    L.cx = (L.cx & ~L.m) | (l ? L.m : 0u);
+    L.cx = (L.cx & ~L.m) | (code ? L.m : 0u);
     L.seq++;
-    if (L.seq == 25) {
-      tl_mb_finish(L, c);
-      if (!tl_mb_next(L, c)) {
+    if (TL_UNLIKELY(L.seq == 25)) {
+      tl_mb_finish<MULTI>(L, c);
+      if (!tl_mb_next<MULTI>(L, c)) {
         if (!(MULTI && L.waiting)) tl_lane_park(L, c);
         return L.alive;
       }

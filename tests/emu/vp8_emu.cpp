@@ -104,7 +104,7 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
       cc.mbinfo = mbinfo.data(); cc.coeffs = coeffs.data();
       cc.mb_w = mb_w; cc.rows = rows; cc.P = P; cc.part = p; cc.use_skip = hdr.use_skip; cc.ctx_stride = mb_w;
       tl_lane_init(lanes[p], cc, frame, &hdr);
-      live[p] = (P > 1) ? 1 : tl_mb_next(lanes[p], cc);
+      live[p] = (P > 1) ? 1 : tl_mb_next<0>(lanes[p], cc);
       if (!live[p]) tl_lane_park(lanes[p], cc);
     }
     for (bool any = true; any;) {
