@@ -284,6 +284,8 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_lockstep(const uint
   // per-lane copies of what the rare paths need: left as kernel parameters they are re-read from the constant bank
   // in every iteration (the loads get hoisted above the branches that need them)
   asm volatile("" : "+r"(c.P), "+r"(c.ctx_stride), "+r"(c.mb_w), "+l"(c.mbinfo), "+l"(c.coeffs));
+  __builtin_assume(__isGlobal(c.mbinfo));
+  __builtin_assume(__isGlobal(c.coeffs));
   TlLane L;
   if (have) {
     tl_lane_init(L, c, arena + im.in_off, h);
@@ -296,14 +298,20 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_lockstep(const uint
   // at that loop's exit for the longest block in the warp.)
   if (P > 1) {
     while (__any_sync(0xffffffffu, L.alive)) {
-      bd_fill_lookahead(L.d);
-      tl_step<1>(L, c); tl_step<1>(L, c); tl_step<1>(L, c); tl_step<1>(L, c);
+#pragma unroll 1
+      for (int r = 0; r < 8; ++r) {
+        bd_fill_lookahead(L.d);
+        tl_step<1>(L, c); tl_step<1>(L, c); tl_step<1>(L, c); tl_step<1>(L, c);
+      }
     }
   } else {
     if (have && !tl_mb_next<0>(L, c)) tl_lane_park(L, c);
     while (__any_sync(0xffffffffu, L.alive)) {
-      bd_fill_lookahead(L.d);
-      tl_step<0>(L, c); tl_step<0>(L, c); tl_step<0>(L, c); tl_step<0>(L, c);
+#pragma unroll 1
+      for (int r = 0; r < 8; ++r) {   // the vote costs as much as half a step: take it every 32 steps
+        bd_fill_lookahead(L.d);
+        tl_step<0>(L, c); tl_step<0>(L, c); tl_step<0>(L, c); tl_step<0>(L, c);
+      }
     }
   }
   if (have && L.status != VP8B_OK) h->status = L.status;
@@ -496,8 +504,10 @@ static void launch_tokens_lockstep(cudaStream_t s, const uint8_t* arena, const I
                                    int16_t* coeffs, const int* ids, int count, int P, int max_mb_w) {
   static int f_lpw = -1, f_cw = -1;
   if (f_lpw < 0) { f_lpw = env_int("WEBP_B200_TOKEN_LPW"); f_cw = env_int("WEBP_B200_TOKEN_CW"); }
-  int cw = (f_cw >= 1 && f_cw <= 16) ? f_cw : (P > 1 ? 16 : 8);
   const long streams = (long)count * P;
+  // one warp per SM sub-partition while the streams fit seven to a warp, then more warps (shared memory caps a block at
+  // ~43 images' probability rows, so many small images want their lanes spread over more warps)
+  int cw = (f_cw >= 1 && f_cw <= 16) ? f_cw : (streams <= 148L * 4 * 8 ? 4 : P > 1 ? 16 : 8);
   int lpw = (int)((streams + 148L * cw - 1) / (148L * cw));
   if (f_lpw >= 1 && f_lpw <= 32) lpw = f_lpw;
   if (lpw < 1) lpw = 1;
@@ -526,9 +536,10 @@ extern "C" void vp8k_parse_tokens(cudaStream_t s, const uint8_t* arena, const Im
     const char* e = getenv("WEBP_B200_TOKEN_MAP");
     forced = (e && e[0] == 'w') ? 1 : (e && e[0] == 'l') ? 2 : (e && e[0] == 'k') ? 3 : 0;
   }
-  // Measured (profiles/r01i_token_map_sweep.log): 4096 streams: warp 377 ms, lockstep 418; 32768 streams (8 partitions):
-  // warp 420, state machine 247, lockstep 168; 65536 thumbnails: warp 274, lockstep 208.
-  const int many = (long)count * P > 148L * 4 * 16;
+  // Measured per 4096 full-HD images (profiles/r01*_token_map_sweep.log): 4096 streams: warp 377 ms, lockstep 331;
+  // 32768 streams (8 partitions): warp 420, state machine 247, lockstep 162; 65536 thumbnails: warp 274, lockstep 178.
+  // Below two streams per SM sub-partition a lane-per-stream warp has nothing to share its instructions with.
+  const int many = (long)count * P >= 148L * 4 * 2;
   if (forced == 3 || (forced == 0 && many)) { launch_tokens_lockstep(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, max_mb_w); return; }
   const int use_warp_map = forced ? (forced == 1) : 1;
   if (use_warp_map) {

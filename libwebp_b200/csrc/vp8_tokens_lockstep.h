@@ -137,7 +137,7 @@ struct TlLane {
   uint32_t ofs;           // coefficient n of the current block goes to byte (row >> 5) + ofs of the macroblock's 800
   uint32_t cx;            // non-zero contexts: top in bits 0-8 (0-3 luma, 4-5 U, 6-7 V, 8 Y2), left in bits 16-24
   uint32_t acc_lo, acc_hi;// 2-bit nz codes of the macroblock's blocks shifted in, in parse order
-  uint32_t m;             // context bits of the current block (seqmask)
+  uint32_t m, m_next;     // context bits of the current / the next block (seqmask)
   uint32_t lut;           // nz -> 2-bit code of the current block: 2-bit fields indexed by min(nz, 4)
   int seq;                // 0 = Y2, 1..16 luma, 17..24 chroma
   // macroblock
@@ -167,7 +167,7 @@ struct TlCtx {
 
 TK_FN void tl_lane_reset(TlLane& L, const TlCtx& c) {
   L.row = 0; L.rowend = 0; L.s = 0; L.sink = 0; L.prob = 0; L.e0 = 0; L.e1 = 0; L.v = 0; L.ofs = 0; L.cx = 0;
-  L.acc_lo = 0; L.acc_hi = 0; L.m = 0; L.lut = 0; L.seq = 0;
+  L.acc_lo = 0; L.acc_hi = 0; L.m = 0; L.m_next = 0; L.lut = 0; L.seq = 0;
   L.yrow = 0; L.yend = 0; L.yofs = 0; L.ylut = 0; L.mbcoef = c.coeffs;
   L.mx = 0; L.my = c.part; L.done_mbs = 0; L.waiting = 1; L.alive = 1; L.status = VP8B_OK;
   L.w = 0; L.w_next = 0;
@@ -198,7 +198,8 @@ TK_FN uint32_t tl_popc(uint32_t x) {
 TK_FN void tl_block_setup(TlLane& L, const TlCtx& c) {
   const int chroma = L.seq >= 17;
   const tk_saddr crow = c.img_s + 2 * TL_TYPE_BYTES;
-  L.m = tk_lds_u32(c.tab_s + TLT_SEQMASK + 4u * (uint32_t)L.seq);
+  L.m = L.m_next;   // fetched while the previous block was parsed: one shared-memory round trip less at the block end
+  L.m_next = tk_lds_u32(c.tab_s + TLT_SEQMASK + 4u * (uint32_t)L.seq + 4u);
   L.rowend = chroma ? crow + TL_TYPE_BYTES : L.yend;
   L.row = chroma ? crow : L.yrow;
   L.lut = chroma ? TL_LUT_FROM0 : L.ylut;
@@ -210,6 +211,7 @@ TK_FN void tl_block_setup(TlLane& L, const TlCtx& c) {
 // The Y2 block of an i16 macroblock (seq 0): type 1, block 24.
 TK_FN void tl_y2_setup(TlLane& L, const TlCtx& c) {
   L.m = (1u << 8) | (1u << 24);
+  L.m_next = (1u << 0) | (1u << 16);   // seq 1
   L.row = c.img_s + 1 * TL_TYPE_BYTES;
   L.rowend = L.row + TL_TYPE_BYTES;
   L.lut = TL_LUT_FROM0;
@@ -273,7 +275,7 @@ TK_FN int tl_mb_next(TlLane& L, const TlCtx& c) {
       L.yrow = ybase + (is_i4 ? 0u : (uint32_t)TL_ROW_BYTES);
       L.ylut = is_i4 ? TL_LUT_FROM0 : TL_LUT_FROM1;
       L.yofs = 0u - 32u - (uint32_t)(ybase >> 5);
-      if (is_i4) { L.seq = 1; tl_block_setup(L, c); } else { L.seq = 0; tl_y2_setup(L, c); }
+      if (is_i4) { L.seq = 1; L.m_next = (1u << 0) | (1u << 16); tl_block_setup(L, c); } else { L.seq = 0; tl_y2_setup(L, c); }
       return 1;
     }
     L.cx &= is_i4 ? 0x01000100u : 0u;
