@@ -275,3 +275,36 @@ def test_crop_and_flip(W, ref, manifest, amanifest):
         assert st == s_ref
         if s_ref == 0:
             assert np.array_equal(want, got.reshape(-1))
+
+
+@pytest.mark.parametrize("mapping", ["warp", "k", "lanes"])
+def test_every_token_mapping(mapping):
+    """The three mappings of the token parse (one warp per partition, lockstep lanes, lane state machine) are picked by
+    stream count; here each is forced in turn (WEBP_B200_TOKEN_MAP is read once per process, hence the subprocess) and
+    must pass the manifest, mixed-batch and fresh-corpus parity tests above."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("WEBP_B200_TOKEN_MAP_INNER"):
+        pytest.skip("inner run")
+    env = dict(os.environ, WEBP_B200_TOKEN_MAP=mapping, WEBP_B200_TOKEN_MAP_INNER="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
+                        "manifest or mixed_sizes or fresh_corpora or full_size or damaged"], env=env, capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_many_streams_take_the_lockstep_parser(W, ref):
+    """Enough streams per partition count for the default choice to be the lockstep parser (>= two per SM sub-partition):
+    1300 one-partition and 300 eight-partition images of mixed small sizes, every one compared with the reference."""
+    d1 = [ref.encode(ref.synth(48 + 16 * (k % 3), 40 + 8 * (k % 5), 7000 + k), ref.cfg_simple_1part(40 + k)) for k in range(40)]
+    d8 = [ref.encode(ref.synth(64 + 16 * (k % 4), 144 + 16 * (k % 2), 7100 + k), ref.cfg_normal_8part(50 + 2 * k)) for k in range(20)]
+    distinct = d1 + d8
+    order = [i % 40 for i in range(1300)] + [40 + i % 20 for i in range(300)]
+    datas = [distinct[j] for j in order]
+    sts, outs = W.decode_batch(datas, W.MODE_RGBA)
+    wants = [ref.decode(d, ref.MODE_RGBA, 0) for d in distinct]
+    for i, j in enumerate(order):
+        st, want = wants[j]
+        assert st == 0 and sts[i] == 0, i
+        assert np.array_equal(outs[i], want), i
