@@ -292,26 +292,18 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_lockstep(const uint
   } else {
     tl_lane_idle(L, c, arena);
   }
-  // One decode per lane per step, four steps per window top-up, and the whole warp (parked lanes included) meets at
-  // the vote: the lanes never run apart by more than the block-end branches inside one step. (Left to itself the
-  // compiler turns "decode until the block ends" into an inner loop, and a lane whose block has ended would wait
-  // at that loop's exit for the longest block in the warp.)
+  // Groups of four decodes per lane between event points (vp8_tokens_lockstep.h:tl_group); a step is branch-free, so
+  // the running lanes of the warp execute it as one instruction stream. A lane starts as "needs a macroblock", which
+  // the first event point resolves.
   if (P > 1) {
     while (__any_sync(0xffffffffu, L.alive)) {
 #pragma unroll 1
-      for (int r = 0; r < 8; ++r) {
-        bd_fill_lookahead(L.d);
-        tl_step<1>(L, c); tl_step<1>(L, c); tl_step<1>(L, c); tl_step<1>(L, c);
-      }
+      for (int r = 0; r < 8; ++r) tl_group<1>(L, c);   // the vote costs as much as half a step: take it every 32 steps
     }
   } else {
-    if (have && !tl_mb_next<0>(L, c)) tl_lane_park(L, c);
     while (__any_sync(0xffffffffu, L.alive)) {
 #pragma unroll 1
-      for (int r = 0; r < 8; ++r) {   // the vote costs as much as half a step: take it every 32 steps
-        bd_fill_lookahead(L.d);
-        tl_step<0>(L, c); tl_step<0>(L, c); tl_step<0>(L, c); tl_step<0>(L, c);
-      }
+      for (int r = 0; r < 8; ++r) tl_group<0>(L, c);
     }
   }
   if (have && L.status != VP8B_OK) h->status = L.status;

@@ -111,7 +111,7 @@ TK_FN uint32_t tl_seqmask(int k) {
 TK_FN void tl_tables_fill(TlTables* t, int tid, int nthreads) {
   for (int k = tid; k < 256; k += nthreads) {
     const int st = (k >> 1) & 63;
-    t->trans[k >> 1][k & 1] = st < TL_STATES ? tl_trans_entry(st, k & 1) : TL_E(63, 0, 0);   // 63 = TL_DEAD
+    t->trans[k >> 1][k & 1] = st < TL_STATES ? tl_trans_entry(st, k & 1) : 0u;
   }
   for (int k = tid; k < 28; k += nthreads) t->seqmask[k] = tl_seqmask(k);
 }
@@ -125,6 +125,13 @@ TK_FN void tl_image_fill(uint8_t* dst, const FrameHdr* h, int tid, int nthreads)
     ((uint32_t*)dst)[k] = w;
   }
 }
+
+// Lane phases (TlLane::pend). Only running lanes execute a step; the others sit out the rest of their group and
+// are looked after at the warp's next event point.
+#define TL_RUN 0        // a block is set up, the pending decode is loaded
+#define TL_BLOCK_END 1  // the block has ended: bookkeeping and the next block / macroblock are due
+#define TL_NEED_MB 2    // the next macroblock has to be started (first one, or the row above is not ready yet)
+#define TL_FINISHED 3
 
 // ---- per-lane state (registers)
 struct TlLane {
@@ -147,6 +154,7 @@ struct TlLane {
   uint32_t w, w_next;     // MbInfo word 3 of this / the partition's next macroblock
   int mx, my;
   int done_mbs;
+  int pend;               // TL_RUN / TL_BLOCK_END / TL_NEED_MB / TL_FINISHED
   int waiting;            // P > 1: the partition owning the row above has not got far enough yet
   int alive;              // 0 once parked
   int status;
@@ -166,10 +174,11 @@ struct TlCtx {
 };
 
 TK_FN void tl_lane_reset(TlLane& L, const TlCtx& c) {
-  L.row = 0; L.rowend = 0; L.s = 0; L.sink = 0; L.prob = 0; L.e0 = 0; L.e1 = 0; L.v = 0; L.ofs = 0; L.cx = 0;
+  L.row = c.img_s; L.rowend = 0; L.s = 0; L.sink = 0; L.prob = 0; L.e0 = 0; L.e1 = 0; L.v = 0; L.ofs = 0; L.cx = 0;
   L.acc_lo = 0; L.acc_hi = 0; L.m = 0; L.m_next = 0; L.lut = 0; L.seq = 0;
   L.yrow = 0; L.yend = 0; L.yofs = 0; L.ylut = 0; L.mbcoef = c.coeffs;
   L.mx = 0; L.my = c.part; L.done_mbs = 0; L.waiting = 1; L.alive = 1; L.status = VP8B_OK;
+  L.pend = TL_NEED_MB;
   L.w = 0; L.w_next = 0;
 }
 
@@ -294,15 +303,12 @@ TK_FN void tl_mb_finish(TlLane& L, const TlCtx& c) {
   tl_mb_store<MULTI>(L, c, nzy, (w & 0xffff0000u) | nzuv);
 }
 
-// Parks a lane that has nothing (more) to do: state 63 decodes a zero probability for ever, never emits, never
-// ends a block, and its reader only shifts in zeros. Dead lanes keep executing the loop in step with the others.
-#define TL_DEAD 63u
 TK_FN void tl_lane_park(TlLane& L, const TlCtx& c) {
-  L.s = TL_DEAD; L.row = c.img_s; L.rowend = 0; L.alive = 0; L.waiting = 0;
-  tl_prime(L, c);
+  L.pend = TL_FINISHED; L.alive = 0; L.waiting = 0;
+  (void)c;
 }
 
-// A lane without a stream: a reader over zero bytes at `any` (a valid address), parked from the start.
+// A lane without a stream: finished from the start (`any` = some valid address for its reader).
 TK_FN void tl_lane_idle(TlLane& L, const TlCtx& c, const uint8_t* any) {
   bd_init(L.d, any, 0);
   tl_lane_reset(L, c);
@@ -315,19 +321,9 @@ TK_FN void tl_lane_idle(TlLane& L, const TlCtx& c, const uint8_t* any) {
 #define TL_UNLIKELY(x) (x)
 #endif
 
-// One iteration: one boolean decode and its consequences; the caller has topped the window up (bd_fill_lookahead)
-// within the last three decodes. Returns 0 when the lane has finished (it is parked then).
-// MULTI = the image has several token partitions (lanes may have to wait for the row above).
-template <int MULTI>
-TK_FN int tl_step(TlLane& L, const TlCtx& c) {
-  if (MULTI) {
-    if (L.waiting) {
-      if (!tl_mb_next<MULTI>(L, c)) {
-        if (!L.waiting) tl_lane_park(L, c);
-        return L.alive;
-      }
-    }
-  }
+// One decode and its consequences, branch-free: a block end only marks the lane. The caller has topped the window up
+// (bd_fill_lookahead) within the last three decodes.
+TK_FN void tl_step(TlLane& L, const TlCtx& c) {
   // ---- what the NEXT decode needs, fetched for both outcomes of this one before its bit is known: the dependent
   // chain of an iteration is then select -> multiply -> compare, and the shared-memory latency runs beside it.
   // (ADV is bit 6 = the row stride, so `row + (e & 127)` is the next probability's address as it stands.)
@@ -351,25 +347,48 @@ TK_FN int tl_step(TlLane& L, const TlCtx& c) {
     L.v = 0;
   }
   L.row += e & TL_ADV;
-  if (TL_UNLIKELY((e & TL_EOB) || L.row == L.rowend)) {
-    // ---- end of block (GetCoeffs' return value nz; ParseResiduals' bookkeeping, vp8_dec.c:517-609)
-    const uint32_t nz2 = 32u - (uint32_t)((L.rowend - L.row) >> 5);   // 2 * nz
-    const uint32_t code = (L.lut >> (nz2 < 8u ? nz2 : 8u)) & 3u;       // non-zero exactly when the block counts as non-empty
-    L.acc_hi = (L.acc_hi << 2) | (L.acc_lo >> 30);
-    L.acc_lo = (L.acc_lo << 2) | code;
-    L.cx = (L.cx & ~L.m) | (code ? L.m : 0u);
-    L.seq++;
-    if (TL_UNLIKELY(L.seq == 25)) {
-      tl_mb_finish<MULTI>(L, c);
-      if (!tl_mb_next<MULTI>(L, c)) {
-        if (!(MULTI && L.waiting)) tl_lane_park(L, c);
-        return L.alive;
+  if ((e & TL_EOB) || L.row == L.rowend) L.pend = TL_BLOCK_END;
+}
+
+// The warp's event point, once per group of steps: lanes whose block has ended do ParseResiduals' bookkeeping
+// (vp8_dec.c:517-609) with GetCoeffs' return value nz and start their next block or macroblock; lanes that need a
+// macroblock (MULTI = several token partitions: the row above may not be ready) try again.
+template <int MULTI>
+TK_FN void tl_events(TlLane& L, const TlCtx& c) {
+  if (L.pend == TL_BLOCK_END || L.pend == TL_NEED_MB) {
+    int need_mb = (L.pend == TL_NEED_MB);
+    L.pend = TL_RUN;
+    if (!need_mb) {
+      const uint32_t nz2 = 32u - (uint32_t)((L.rowend - L.row) >> 5);   // 2 * nz
+      const uint32_t code = (L.lut >> (nz2 < 8u ? nz2 : 8u)) & 3u;       // non-zero exactly when the block counts as non-empty
+      L.acc_hi = (L.acc_hi << 2) | (L.acc_lo >> 30);
+      L.acc_lo = (L.acc_lo << 2) | code;
+      L.cx = (L.cx & ~L.m) | (code ? L.m : 0u);
+      L.seq++;
+      if (TL_UNLIKELY(L.seq == 25)) {
+        tl_mb_finish<MULTI>(L, c);
+        need_mb = 1;
+      } else {
+        tl_block_setup(L, c);
       }
-    } else {
-      tl_block_setup(L, c);
+    }
+    if (TL_UNLIKELY(need_mb)) {
+      if (!tl_mb_next<MULTI>(L, c)) {
+        if (MULTI && L.waiting) L.pend = TL_NEED_MB; else tl_lane_park(L, c);
+      }
     }
   }
-  return 1;
+}
+
+// One group: the event point, a top-up of the window, four decodes.
+template <int MULTI>
+TK_FN void tl_group(TlLane& L, const TlCtx& c) {
+  tl_events<MULTI>(L, c);
+  if (L.pend == TL_RUN) bd_fill_lookahead(L.d);
+  if (L.pend == TL_RUN) tl_step(L, c);
+  if (L.pend == TL_RUN) tl_step(L, c);
+  if (L.pend == TL_RUN) tl_step(L, c);
+  if (L.pend == TL_RUN) tl_step(L, c);
 }
 
 #endif  // LIBWEBP_B200_VP8_TOKENS_LOCKSTEP_H_

@@ -104,18 +104,14 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
       cc.mbinfo = mbinfo.data(); cc.coeffs = coeffs.data();
       cc.mb_w = mb_w; cc.rows = rows; cc.P = P; cc.part = p; cc.use_skip = hdr.use_skip; cc.ctx_stride = mb_w;
       tl_lane_init(lanes[p], cc, frame, &hdr);
-      live[p] = (P > 1) ? 1 : tl_mb_next<0>(lanes[p], cc);
-      if (!live[p]) tl_lane_park(lanes[p], cc);
+      live[p] = 1;
     }
     for (bool any = true; any;) {
       any = false;
       for (int p = P - 1; p >= 0; --p) {   // reverse order: exercises the wait-for-progress path
         if (!live[p]) continue;
         any = true;
-        bd_fill_lookahead(lanes[p].d);
-        for (int k = 0; k < 4; ++k) {   // parked lanes keep stepping, harmlessly, like on the device
-          if (P > 1) tl_step<1>(lanes[p], ctxs[p]); else tl_step<0>(lanes[p], ctxs[p]);
-        }
+        if (P > 1) tl_group<1>(lanes[p], ctxs[p]); else tl_group<0>(lanes[p], ctxs[p]);
         live[p] = lanes[p].alive;
       }
     }
