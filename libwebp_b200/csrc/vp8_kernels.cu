@@ -246,7 +246,7 @@ __host__ __device__ static inline TlLayout tl_layout(int P, int ipb, int ctx_str
 __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_lockstep(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
                                                                   FrameHdr* hdrs, uint32_t* mbinfo, int16_t* coeffs,
                                                                   const int* __restrict__ ids, int count, int P, int ipb, int lpw,
-                                                                  int cw, int ctx_stride) {
+                                                                  int cw, int ctx_stride, int grouped) {
   extern __shared__ __align__(16) uint8_t smem[];
   const TlLayout lay = tl_layout(P, ipb, ctx_stride);
   TlTables* tables = reinterpret_cast<TlTables*>(smem);
@@ -292,18 +292,37 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_lockstep(const uint
   } else {
     tl_lane_idle(L, c, arena);
   }
-  // Groups of four decodes per lane between event points (vp8_tokens_lockstep.h:tl_group); a step is branch-free, so
-  // the running lanes of the warp execute it as one instruction stream. A lane starts as "needs a macroblock", which
-  // the first event point resolves.
-  if (P > 1) {
-    while (__any_sync(0xffffffffu, L.alive)) {
-#pragma unroll 1
-      for (int r = 0; r < 8; ++r) tl_group<1>(L, c);   // the vote costs as much as half a step: take it every 32 steps
+  // The counters of the loops below start from a per-thread value (always 0: sink is an XOR of bytes), for a
+  // warp-uniform one makes the compiler fence the loop body with WARPSYNC.ALL; the vote costs as much as half a step
+  // and is taken every 32 steps.
+  const int r0 = (int)(L.sink >> 31);
+  if (grouped) {
+    // Groups of four decodes per lane between event points (vp8_tokens_lockstep.h:tl_group). A lane starts as "needs a
+    // macroblock", which the first event point resolves.
+    if (P > 1) {
+      while (__any_sync(0xffffffffu, L.alive)) { for (int r = r0; r < 8; ++r) tl_group<1>(L, c); }
+    } else {
+      while (__any_sync(0xffffffffu, L.alive)) { for (int r = r0; r < 8; ++r) tl_group<0>(L, c); }
     }
   } else {
-    while (__any_sync(0xffffffffu, L.alive)) {
-#pragma unroll 1
-      for (int r = 0; r < 8; ++r) tl_group<0>(L, c);
+    // One decode per lane per step with the block ends handled on the spot; the whole warp (parked lanes included)
+    // meets again at the end of every step. (Left to itself the compiler turns "decode until the block ends" into an
+    // inner loop, and a lane whose block has ended would wait at that loop's exit for the longest block in the warp.)
+    if (P > 1) {
+      while (__any_sync(0xffffffffu, L.alive)) {
+        for (int r = r0; r < 8; ++r) {
+          bd_fill_lookahead(L.d);
+          tl_step_inline<1>(L, c); tl_step_inline<1>(L, c); tl_step_inline<1>(L, c); tl_step_inline<1>(L, c);
+        }
+      }
+    } else {
+      if (have && !tl_mb_next<0>(L, c)) tl_lane_park(L, c);
+      while (__any_sync(0xffffffffu, L.alive)) {
+        for (int r = r0; r < 8; ++r) {
+          bd_fill_lookahead(L.d);
+          tl_step_inline<0>(L, c); tl_step_inline<0>(L, c); tl_step_inline<0>(L, c); tl_step_inline<0>(L, c);
+        }
+      }
     }
   }
   if (have && L.status != VP8B_OK) h->status = L.status;
@@ -499,7 +518,7 @@ static void launch_tokens_lockstep(cudaStream_t s, const uint8_t* arena, const I
   const long streams = (long)count * P;
   // one warp per SM sub-partition while the streams fit seven to a warp, then more warps (shared memory caps a block at
   // ~43 images' probability rows, so many small images want their lanes spread over more warps)
-  int cw = (f_cw >= 1 && f_cw <= 16) ? f_cw : (streams <= 148L * 4 * 8 ? 4 : P > 1 ? 16 : 8);
+  int cw = (f_cw >= 1 && f_cw <= 16) ? f_cw : (streams <= 148L * 4 * 8 ? 4 : 8);
   int lpw = (int)((streams + 148L * cw - 1) / (148L * cw));
   if (f_lpw >= 1 && f_lpw <= 32) lpw = f_lpw;
   if (lpw < 1) lpw = 1;
@@ -514,7 +533,15 @@ static void launch_tokens_lockstep(cudaStream_t s, const uint8_t* arena, const I
     cudaFuncSetAttribute(k_parse_tokens_lockstep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
     configured = lay.total;
   }
-  k_parse_tokens_lockstep<<<blocks, 32 * cw, lay.total, s>>>(arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, ipb, lpw, cw, max_mb_w);
+  // How the lanes are run (vp8_tokens_lockstep.h): block ends on the spot while a warp has few lanes, grouped event
+  // points when it has many (their cost is shared by all the lanes that have a block end pending). Measured per 4096
+  // full-HD images: 1 partition (7 lanes per warp) 305 vs 385 ms, 8 partitions (28 lanes) 160 vs 91 ms; 65536
+  // thumbnails (shared memory holds 43 images per block: 5 lanes) 170 vs 201 ms.
+  static int f_grouped = -2;
+  if (f_grouped == -2) { const char* e = getenv("WEBP_B200_TOKEN_GROUPED"); f_grouped = e ? atoi(e) : -1; }
+  const int lanes_per_warp = (ipb * P + cw - 1) / cw;
+  const int grouped = f_grouped >= 0 ? f_grouped : (lanes_per_warp >= 16);
+  k_parse_tokens_lockstep<<<blocks, 32 * cw, lay.total, s>>>(arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, ipb, lpw, cw, max_mb_w, grouped);
 }
 
 extern "C" void vp8k_parse_tokens(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,

@@ -27,6 +27,12 @@
 #include "vp8_parse_core.h"
 #include "vp8_tokens_fsm.h"   // TK_FN, tk_saddr and the shared-memory access helpers
 
+#if defined(__GNUC__) || defined(__CUDACC__)
+#define TL_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#else
+#define TL_UNLIKELY(x) (x)
+#endif
+
 // ---- states
 #define TL_SIGN1 33    // sign of a coefficient of magnitude 1 (next context 1)
 #define TL_SIGN2 34    // sign of a larger one (next context 2)
@@ -111,7 +117,7 @@ TK_FN uint32_t tl_seqmask(int k) {
 TK_FN void tl_tables_fill(TlTables* t, int tid, int nthreads) {
   for (int k = tid; k < 256; k += nthreads) {
     const int st = (k >> 1) & 63;
-    t->trans[k >> 1][k & 1] = st < TL_STATES ? tl_trans_entry(st, k & 1) : 0u;
+    t->trans[k >> 1][k & 1] = st < TL_STATES ? tl_trans_entry(st, k & 1) : TL_E(63, 0, 0);   // 63 = TL_DEAD
   }
   for (int k = tid; k < 28; k += nthreads) t->seqmask[k] = tl_seqmask(k);
 }
@@ -303,9 +309,14 @@ TK_FN void tl_mb_finish(TlLane& L, const TlCtx& c) {
   tl_mb_store<MULTI>(L, c, nzy, (w & 0xffff0000u) | nzuv);
 }
 
+// Parks a lane that has nothing (more) to do. Where every lane of the warp executes every step (tl_step_inline) a
+// parked lane keeps decoding in state 63: a zero probability for ever, never emits, never ends a block, and its
+// reader only shifts in zeros.
+#define TL_DEAD 63u
 TK_FN void tl_lane_park(TlLane& L, const TlCtx& c) {
   L.pend = TL_FINISHED; L.alive = 0; L.waiting = 0;
-  (void)c;
+  L.s = TL_DEAD; L.row = c.img_s; L.rowend = 0;
+  tl_prime(L, c);
 }
 
 // A lane without a stream: finished from the start (`any` = some valid address for its reader).
@@ -315,15 +326,9 @@ TK_FN void tl_lane_idle(TlLane& L, const TlCtx& c, const uint8_t* any) {
   tl_lane_park(L, c);
 }
 
-#if defined(__GNUC__) || defined(__CUDACC__)
-#define TL_UNLIKELY(x) __builtin_expect(!!(x), 0)
-#else
-#define TL_UNLIKELY(x) (x)
-#endif
-
-// One decode and its consequences, branch-free: a block end only marks the lane. The caller has topped the window up
+// One boolean decode and the transition it selects; returns the transition entry. The caller has topped the window up
 // (bd_fill_lookahead) within the last three decodes.
-TK_FN void tl_step(TlLane& L, const TlCtx& c) {
+TK_FN uint32_t tl_decode(TlLane& L, const TlCtx& c) {
   // ---- what the NEXT decode needs, fetched for both outcomes of this one before its bit is known: the dependent
   // chain of an iteration is then select -> multiply -> compare, and the shared-memory latency runs beside it.
   // (ADV is bit 6 = the row stride, so `row + (e & 127)` is the next probability's address as it stands.)
@@ -347,6 +352,54 @@ TK_FN void tl_step(TlLane& L, const TlCtx& c) {
     L.v = 0;
   }
   L.row += e & TL_ADV;
+  return e;
+}
+
+// ParseResiduals' bookkeeping at the end of a block (vp8_dec.c:517-609) with GetCoeffs' return value nz, then the next
+// block. Returns 1 when the macroblock's last block has ended instead (tl_mb_finish + tl_mb_next are due).
+TK_FN int tl_block_end(TlLane& L, const TlCtx& c) {
+  const uint32_t nz2 = 32u - (uint32_t)((L.rowend - L.row) >> 5);   // 2 * nz
+  const uint32_t code = (L.lut >> (nz2 < 8u ? nz2 : 8u)) & 3u;       // non-zero exactly when the block counts as non-empty
+  L.acc_hi = (L.acc_hi << 2) | (L.acc_lo >> 30);
+  L.acc_lo = (L.acc_lo << 2) | code;
+  L.cx = (L.cx & ~L.m) | (code ? L.m : 0u);
+  L.seq++;
+  if (TL_UNLIKELY(L.seq == 25)) return 1;
+  tl_block_setup(L, c);
+  return 0;
+}
+
+// ---- first way of running the lanes: every lane executes every step, and a lane whose block has ended does its
+// bookkeeping on the spot while the others wait. Best when a warp is alone on its SM sub-partition (one dependent
+// chain to follow, nothing to overlap the bookkeeping with). Returns 0 once the lane has finished (parked).
+template <int MULTI>
+TK_FN int tl_step_inline(TlLane& L, const TlCtx& c) {
+  if (MULTI) {
+    if (L.waiting) {
+      if (!tl_mb_next<MULTI>(L, c)) {
+        if (!L.waiting) tl_lane_park(L, c);
+        return L.alive;
+      }
+    }
+  }
+  const uint32_t e = tl_decode(L, c);
+  if (TL_UNLIKELY((e & TL_EOB) || L.row == L.rowend)) {
+    if (tl_block_end(L, c)) {
+      tl_mb_finish<MULTI>(L, c);
+      if (!tl_mb_next<MULTI>(L, c)) {
+        if (!(MULTI && L.waiting)) tl_lane_park(L, c);
+        return L.alive;
+      }
+    }
+  }
+  return 1;
+}
+
+// ---- second way: a step is branch-free and a block end only marks the lane, which then sits out the rest of its
+// group of four steps; the bookkeeping of all marked lanes happens together at the group's event point. Fewer
+// instructions per decode; best when several warps share the sub-partition.
+TK_FN void tl_step(TlLane& L, const TlCtx& c) {
+  const uint32_t e = tl_decode(L, c);
   if ((e & TL_EOB) || L.row == L.rowend) L.pend = TL_BLOCK_END;
 }
 
@@ -358,19 +411,9 @@ TK_FN void tl_events(TlLane& L, const TlCtx& c) {
   if (L.pend == TL_BLOCK_END || L.pend == TL_NEED_MB) {
     int need_mb = (L.pend == TL_NEED_MB);
     L.pend = TL_RUN;
-    if (!need_mb) {
-      const uint32_t nz2 = 32u - (uint32_t)((L.rowend - L.row) >> 5);   // 2 * nz
-      const uint32_t code = (L.lut >> (nz2 < 8u ? nz2 : 8u)) & 3u;       // non-zero exactly when the block counts as non-empty
-      L.acc_hi = (L.acc_hi << 2) | (L.acc_lo >> 30);
-      L.acc_lo = (L.acc_lo << 2) | code;
-      L.cx = (L.cx & ~L.m) | (code ? L.m : 0u);
-      L.seq++;
-      if (TL_UNLIKELY(L.seq == 25)) {
-        tl_mb_finish<MULTI>(L, c);
-        need_mb = 1;
-      } else {
-        tl_block_setup(L, c);
-      }
+    if (!need_mb && tl_block_end(L, c)) {
+      tl_mb_finish<MULTI>(L, c);
+      need_mb = 1;
     }
     if (TL_UNLIKELY(need_mb)) {
       if (!tl_mb_next<MULTI>(L, c)) {

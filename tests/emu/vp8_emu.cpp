@@ -23,7 +23,7 @@
 // variant bit 0: visit the macroblocks of a wavefront step in reverse order
 // variant bit 1: token parse with the row-at-a-time reference port (parse_token_row) instead of the lane FSM
 // variant bit 2: lane FSM with a lazy ring producer
-// variant bit 3: lockstep lane parser (vp8_tokens_lockstep.h), lanes advanced round-robin one decode at a time
+// variant bit 3: lockstep lane parser (vp8_tokens_lockstep.h), lanes advanced round-robin; with bit 4 its grouped event points
 static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags, uint8_t* out, size_t out_size,
                            int stride, int variant, uint8_t* unfiltered, int crop_x, int crop_y, int crop_w, int crop_h);
 
@@ -106,12 +106,21 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
       tl_lane_init(lanes[p], cc, frame, &hdr);
       live[p] = 1;
     }
+    const bool grouped = (variant & 16) != 0;   // variant bit 4: grouped event points instead of block ends on the spot
+    if (!grouped && P == 1 && live[0] && !tl_mb_next<0>(lanes[0], ctxs[0])) { tl_lane_park(lanes[0], ctxs[0]); live[0] = 0; }
     for (bool any = true; any;) {
       any = false;
       for (int p = P - 1; p >= 0; --p) {   // reverse order: exercises the wait-for-progress path
         if (!live[p]) continue;
         any = true;
-        if (P > 1) tl_group<1>(lanes[p], ctxs[p]); else tl_group<0>(lanes[p], ctxs[p]);
+        if (grouped) {
+          if (P > 1) tl_group<1>(lanes[p], ctxs[p]); else tl_group<0>(lanes[p], ctxs[p]);
+        } else {
+          bd_fill_lookahead(lanes[p].d);
+          for (int k = 0; k < 4; ++k) {   // parked lanes keep stepping, harmlessly, like on the device
+            if (P > 1) tl_step_inline<1>(lanes[p], ctxs[p]); else tl_step_inline<0>(lanes[p], ctxs[p]);
+          }
+        }
         live[p] = lanes[p].alive;
       }
     }
