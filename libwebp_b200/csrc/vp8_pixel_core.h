@@ -646,6 +646,68 @@ VP8_UNROLL
   }
 }
 
+// Opaque pixel of the 4-byte family from y << 16 (as extracted from the packed word) and 8-bit u, v; the same
+// arithmetic as yuv_to_rgb() with the products taken as high halves where the operand arrives pre-shifted, and the
+// three clips + the byte packing done by two saturating pack conversions. ORDER: 0 = R,G,B,A  1 = B,G,R,A  2 = A,R,G,B.
+#if defined(__CUDACC__) && !defined(VP8_EMU)
+VP8_PFN uint32_t pack_sat2(int hi, int lo, uint32_t upper) {   // sat_u8(hi) << 8 | sat_u8(lo) | upper << 16
+  uint32_t d; asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(lo), "r"(upper)); return d;
+}
+VP8_PFN int mulhi_s(int a, int b) { return __mulhi(a, b); }
+#else
+VP8_PFN uint32_t pack_sat2(int hi, int lo, uint32_t upper) { return ((uint32_t)sat_u8(hi) << 8) | (uint32_t)sat_u8(lo) | (upper << 16); }
+VP8_PFN int mulhi_s(int a, int b) { return (int)(((int64_t)a * (int64_t)b) >> 32); }
+#endif
+
+template <int ORDER>
+VP8_PFN uint32_t yuv_to_px4_opaque(int y16, int u, int v) {
+  const int yy = mulhi_s(y16, 19077 << 8);                       // (y * 19077) >> 8
+  const int r = (yy + ((v * 26149) >> 8) - 14234) >> 6;
+  const int g = (yy + (8708 - ((u * 6419) >> 8)) - ((v * 13320) >> 8)) >> 6;
+  const int b = (yy + ((u * 33050) >> 8) - 17685) >> 6;
+  if (ORDER == 0) return pack_sat2(g, r, pack_sat2(255, b, 0));
+  if (ORDER == 1) return pack_sat2(g, b, pack_sat2(255, r, 0));
+  return pack_sat2(r, 255, pack_sat2(b, g, 0));
+}
+
+// emit_rgba_pair8() for images without an alpha plane (premultiplied modes equal the plain ones there), aligned rows.
+template <int ORDER>
+VP8_PFN void emit_opaque_pair8(const ImgDesc& im, const uint8_t* yplane, const uint8_t* uplane, const uint8_t* vplane,
+                               uint8_t* out, int q, int t) {
+  const int w = im.out_w, h = im.out_h;
+  const int ys = 16 * im.mb_w, uvs = 8 * im.mb_w;
+  const int uvw = (w + 1) >> 1, uvh = (h + 1) >> 1;
+  const int ra = t > 0 ? t - 1 : 0, rb = t < uvh ? t : uvh - 1;
+  int ua[6], ub[6], va[6], vb[6];
+  load_chroma6(uplane + (size_t)ra * uvs, q, uvw, ua);
+  load_chroma6(uplane + (size_t)rb * uvs, q, uvw, ub);
+  load_chroma6(vplane + (size_t)ra * uvs, q, uvw, va);
+  load_chroma6(vplane + (size_t)rb * uvs, q, uvw, vb);
+  const int i0 = 8 * q;
+VP8_UNROLL
+  for (int half = 0; half < 2; ++half) {
+    const int j = 2 * t - 1 + half;
+    if (j < 0 || j >= h) continue;
+    int u8[8], v8[8];
+    if (half == 0) { upsample8(ua, ub, u8); upsample8(va, vb, v8); }
+    else { upsample8(ub, ua, u8); upsample8(vb, va, v8); }
+    const uint2 yw = *(const uint2*)(yplane + (size_t)j * ys + i0);
+    uint32_t px[8];
+VP8_UNROLL
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t wd = k < 4 ? yw.x : yw.y;
+      const int sh = 8 * (k & 3);
+      const int y16 = (int)(sh <= 16 ? (wd << (16 - sh)) & 0xff0000u : (wd >> 8) & 0xff0000u);
+      px[k] = yuv_to_px4_opaque<ORDER>(y16, u8[k], v8[k]);
+    }
+    uint4* o = (uint4*)(out + (size_t)((im.flags & VP8B_FLAG_FLIP) ? h - 1 - j : j) * im.out_stride + 4 * (size_t)i0);
+    uint4 a, b;
+    a.x = px[0]; a.y = px[1]; a.z = px[2]; a.w = px[3];
+    b.x = px[4]; b.y = px[5]; b.z = px[6]; b.w = px[7];
+    o[0] = a; o[1] = b;
+  }
+}
+
 // Which images take the fast path (host driver and kernel must agree on the work-item count).
 VP8_PFN int emit_uses_pairs(int csp, int flags, int crop_x) {   // crop_x: the word loads need the window 8-pixel aligned
   return !(flags & VP8B_FLAG_NO_FANCY) && (crop_x & 7) == 0 && (csp == 1 || csp == 3 || csp == 4 || csp == 7 || csp == 8 || csp == 9);
@@ -658,6 +720,12 @@ VP8_PFN void emit_rgba_pair8(const ImgDesc& im, const uint8_t* yplane, const uin
   const int ys = 16 * im.mb_w, uvs = 8 * im.mb_w;
   const int uvw = (w + 1) >> 1, uvh = (h + 1) >> 1;
   const int csp = im.csp;
+  if (alpha == 0 && w - 8 * q >= 8 && ((((uintptr_t)out) | (uintptr_t)im.out_stride) & 15) == 0) {   // opaque, whole, 16-byte aligned
+    if (csp == 1 || csp == 7) emit_opaque_pair8<0>(im, yplane, uplane, vplane, out, q, t);
+    else if (csp == 3 || csp == 8) emit_opaque_pair8<1>(im, yplane, uplane, vplane, out, q, t);
+    else emit_opaque_pair8<2>(im, yplane, uplane, vplane, out, q, t);
+    return;
+  }
   const int ra = t > 0 ? t - 1 : 0, rb = t < uvh ? t : uvh - 1;
   int ua[6], ub[6], va[6], vb[6];
   load_chroma6(uplane + (size_t)ra * uvs, q, uvw, ua);
