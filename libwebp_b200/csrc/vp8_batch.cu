@@ -69,6 +69,7 @@ struct DeviceCtx {
   bool ok = false;
   cudaStream_t stream = nullptr;        // kernels, uploads
   cudaStream_t copy_stream = nullptr;   // pixel downloads, overlapped with the kernels of the next wave
+  cudaStream_t pixel_stream = nullptr;  // row bands: reconstruction / filter / output of one band while the next is parsed
   std::mutex mu;          // one batch at a time per device
   std::vector<CachedBlock> cache;
   size_t cached_bytes = 0;
@@ -90,6 +91,7 @@ static DeviceCtx* get_ctx(int device) {
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->pixel_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { set_error("CUDA device init (no usable GPU; this library has no CPU path)", e); cudaGetLastError(); delete c; return nullptr; }
     {
       size_t free_b = 0, total_b = 0;
@@ -237,6 +239,7 @@ struct WebPBatch {
   std::vector<int> ids;            // token-parse launch lists
   std::vector<int> statuses;       // host copy of FrameHdr::status
   Owned d_in, d_imgs, d_hdrs, d_ids, d_mbinfo, d_coeffs, d_yuv, d_out;
+  Owned d_band;   // row bands: TokResume[m] | uint16 top contexts [m][max_mb_w] | unfiltered top pixels [m][32 * max_mb_w]
   // images with an ALPH chunk
   std::vector<int> aimgs;              // their image indices
   std::vector<AlphaPlan> aplans;
@@ -446,6 +449,8 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
   }
   if (!own_alloc(ctx, b->d_mbinfo, max_wave_mbs * 16) || !own_alloc(ctx, b->d_coeffs, max_wave_mbs * 2 * VP8B_COEFFS_PER_MB) ||
       !own_alloc(ctx, b->d_yuv, max_wave_mbs * 384)) return false;
+  if (!own_alloc(ctx, b->d_band, align_up((size_t)m * sizeof(TokResume), 256) + align_up((size_t)m * 2 * b->max_mb_w, 256) +
+                                     (size_t)m * 32 * b->max_mb_w + 256)) return false;
   // ---- uploads
   cudaStream_t s = ctx->stream;
   for (const auto& r : ranges) {
@@ -463,7 +468,7 @@ static void batch_release(WebPBatch* b) {
   if (b->ctx != nullptr) {
     DeviceCtx* c = b->ctx;
     own_free(c, b->d_in); own_free(c, b->d_imgs); own_free(c, b->d_hdrs); own_free(c, b->d_ids);
-    own_free(c, b->d_mbinfo); own_free(c, b->d_coeffs); own_free(c, b->d_yuv); own_free(c, b->d_out);
+    own_free(c, b->d_mbinfo); own_free(c, b->d_coeffs); own_free(c, b->d_yuv); own_free(c, b->d_out); own_free(c, b->d_band);
     own_free(c, b->d_aimgs); own_free(c, b->d_aplans); own_free(c, b->d_ahdrs); own_free(c, b->d_awork); own_free(c, b->d_awork2); own_free(c, b->d_alpha);
     for (auto e : b->ev) if (e) cudaEventDestroy(e);
   }
@@ -568,6 +573,46 @@ static bool enqueue_download(WebPBatch* b, int first, int count, cudaStream_t s,
   return flush();
 }
 
+// Output rows [row_lo(k), row_hi(k)) of images [first, first + count) (4-byte RGB family, not flipped): one 2-D copy
+// when the images are equally sized and equally spaced on both sides, else one copy per image.
+static bool enqueue_download_rows(WebPBatch* b, int first, int count, int pair_begin, int pair_end, cudaStream_t s) {
+  const uint8_t* dout = (const uint8_t*)b->d_out.p;
+  auto rows_of = [&](const ImgDesc& d, int* lo, int* hi) {
+    const long l = pair_begin > 0 ? 2L * pair_begin - 1 : 0, h = 2L * pair_end - 1;
+    *lo = (int)std::min<long>(l, d.out_h); *hi = (int)std::min<long>(h, d.out_h);
+  };
+  bool uniform = count > 1;
+  const ImgDesc& d0 = b->imgs[first];
+  const WebPDecBuffer* o0 = &b->items[b->img_item[first]].config->output;
+  ptrdiff_t hpitch = 0, dpitch = 0;
+  for (int k = first; k < first + count && uniform; ++k) {
+    const ImgDesc& d = b->imgs[k];
+    const WebPDecBuffer* o = &b->items[b->img_item[k]].config->output;
+    if (d.out_h != d0.out_h || d.out_stride != d0.out_stride || o->u.RGBA.stride != d.out_stride) uniform = false;
+    if (k == first + 1) { hpitch = o->u.RGBA.rgba - o0->u.RGBA.rgba; dpitch = (ptrdiff_t)(d.out_off - d0.out_off); }
+    if (k > first && (o->u.RGBA.rgba - o0->u.RGBA.rgba != hpitch * (k - first) || (ptrdiff_t)(d.out_off - d0.out_off) != dpitch * (k - first)))
+      uniform = false;
+  }
+  if (uniform && hpitch > 0 && dpitch > 0 && (size_t)hpitch < ((size_t)1 << 31) && (size_t)dpitch < ((size_t)1 << 31)) {
+    int lo, hi; rows_of(d0, &lo, &hi);
+    if (hi <= lo) return true;
+    const size_t row = (size_t)d0.out_stride;
+    CU_TRY(cudaMemcpy2DAsync(o0->u.RGBA.rgba + lo * row, (size_t)hpitch, dout + d0.out_off + lo * row, (size_t)dpitch, (hi - lo) * row,
+                             (size_t)count, cudaMemcpyDeviceToHost, s), "D2H pixel band 2D");
+    return true;
+  }
+  for (int k = first; k < first + count; ++k) {
+    const ImgDesc& d = b->imgs[k];
+    const WebPDecBuffer* o = &b->items[b->img_item[k]].config->output;
+    int lo, hi; rows_of(d, &lo, &hi);
+    if (hi <= lo) continue;
+    const size_t row = (size_t)d.out_stride;
+    CU_TRY(cudaMemcpy2DAsync(o->u.RGBA.rgba + (size_t)lo * o->u.RGBA.stride, (size_t)o->u.RGBA.stride, dout + d.out_off + lo * row, row, row,
+                             (size_t)(hi - lo), cudaMemcpyDeviceToHost, s), "D2H pixel band");
+  }
+  return true;
+}
+
 enum { ST_MODES = 0, ST_TOKENS, ST_RECON, ST_FILTER, ST_EMIT, ST_ALPHA, ST_COUNT };
 
 static int ev_mark(WebPBatch* b, cudaStream_t s) {   // records the next pooled event on `s`; -1 on failure
@@ -669,6 +714,7 @@ static bool batch_decode(WebPBatch* b, bool download) {
   size_t chunk_bytes = (size_t)2 << 30;
   { const char* e = getenv("WEBP_B200_CHUNK_MB"); if (e != NULL && atoi(e) > 0) chunk_bytes = (size_t)atoi(e) << 20; }
 #define MARK(var) const int var = ev_mark(b, s); if (var < 0) return false
+  MARK(e_begin);
   if (!b->aimgs.empty()) {
     MARK(ea0);
     if (!batch_alpha(b)) return false;
@@ -687,6 +733,68 @@ static bool batch_decode(WebPBatch* b, bool download) {
       vp8k_parse_tokens(s, arena, imgs, hdrs, mbinfo, coeffs, (const int*)b->d_ids.p + w.ids_off[lg], w.ids_cnt[lg], 1 << lg, w.max_mb_w);
       ++launches;
     }
+    // ---- row bands: see vp8_kernels.h. The wave qualifies when every image has one token partition, the lockstep
+    // parser takes the launch, and every image goes through the row-pair output path unflipped and uncropped.
+    int bands = 1;
+    {
+      static int env_bands = -1;
+      if (env_bands < 0) { const char* e = getenv("WEBP_B200_BANDS"); env_bands = e ? atoi(e) : 1; }
+      bool ok = env_bands > 1 && b->aimgs.empty() && w.ids_cnt[0] == w.count && vp8k_tokens_take_bands(w.count, 1) && w.max_mb_h >= 16;
+      for (int k = w.first; ok && k < w.first + w.count; ++k) {
+        const ImgDesc& d = b->imgs[k];
+        const bool pairs = !(d.flags & VP8B_FLAG_NO_FANCY) && kBpp[d.csp] == 4 && d.csp != MODE_YUVA;
+        if (!pairs || (d.flags & VP8B_FLAG_FLIP) || d.crop_x != 0 || d.crop_y != 0 || d.out_w != d.width || d.out_h != d.height) ok = false;
+      }
+      // Off unless asked for (WEBP_B200_BANDS=n). Measured on 4096 full-HD images (profiles/r01m_row_bands.log): the
+      // download of one band during the parse of the next slows the parse as much as it hides (a kernel running beside a
+      // 55 GB/s device-to-host copy takes 2-3x as long on this box: tokens 312 -> 632 ms, end to end 1003 -> 1013 ms), and
+      // running the pixel KERNELS beside the parse (WEBP_B200_BAND_OVERLAP=1) is worse still: the lockstep parser follows
+      // one dependent chain per warp and loses more from sharing its issue port than the overlap gains (tokens 653 ms).
+      if (ok) bands = std::min(env_bands, w.max_mb_h / 8);
+    }
+    if (bands > 1) {
+      static int overlap = -1;
+      if (overlap < 0) { const char* e = getenv("WEBP_B200_BAND_OVERLAP"); overlap = (e != NULL && atoi(e) > 0) ? 1 : 0; }
+      cudaStream_t ps = overlap ? ctx->pixel_stream : s;
+      TokResume* resume = (TokResume*)b->d_band.p;
+      uint16_t* resume_ctx = (uint16_t*)((uint8_t*)b->d_band.p + align_up((size_t)m * sizeof(TokResume), 256));
+      uint8_t* band_ctx = (uint8_t*)resume_ctx + align_up((size_t)m * 2 * b->max_mb_w, 256);
+      b->spans.push_back({ ST_MODES, e0, e1 });
+      int prev_tok = e1, last_px = -1;
+      for (int k = 0; k < bands; ++k) {
+        const int r0 = (int)((long)w.max_mb_h * k / bands), r1 = (k == bands - 1) ? 0x7fffffff : (int)((long)w.max_mb_h * (k + 1) / bands);
+        // the loop filter of the next band still touches the last 3 luma / 6 chroma-covered rows of this one, and the
+        // upsampler looks one chroma row ahead: hold back the last 8 + 2 pixel rows (kFilterExtraRows, frame_dec.c:201)
+        const int p0 = (k == 0) ? 0 : 8 * r0 - 4, p1 = (k == bands - 1) ? 0x7fffffff : 8 * r1 - 4;
+        vp8k_parse_tokens_band(s, arena, imgs, hdrs, mbinfo, coeffs, (const int*)b->d_ids.p + w.ids_off[0], w.count, w.max_mb_w, r0, r1,
+                               resume, resume_ctx);
+        ++launches;
+        MARK(et);
+        b->spans.push_back({ ST_TOKENS, prev_tok, et });
+        if (ps != s) CU_TRY(cudaStreamWaitEvent(ps, b->ev[et], 0), "cudaStreamWaitEvent");
+        const int q0 = ev_mark(b, ps); if (q0 < 0) return false;
+        vp8k_reconstruct(ps, imgs, hdrs, mbinfo, coeffs, yuv, w.first, w.count, w.max_mb_w, w.max_mb_h, r0, r1, band_ctx);
+        const int q1 = ev_mark(b, ps); if (q1 < 0) return false;
+        vp8k_loop_filter(ps, imgs, hdrs, mbinfo, yuv, w.first, w.count, r0, r1);
+        const int q2 = ev_mark(b, ps); if (q2 < 0) return false;
+        const int band_pairs = (p1 == 0x7fffffff ? (16 * w.max_mb_h) / 2 + 1 : p1) - p0;
+        vp8k_emit(ps, imgs, hdrs, yuv, (const uint8_t*)b->d_alpha.p, (uint8_t*)b->d_out.p, w.first, w.count,
+                  ((16 * w.max_mb_w + 7) / 8) * band_pairs, p0, p1);
+        const int q3 = ev_mark(b, ps); if (q3 < 0) return false;
+        launches += 3;
+        b->spans.push_back({ ST_RECON, q0, q1 });
+        b->spans.push_back({ ST_FILTER, q1, q2 });
+        b->spans.push_back({ ST_EMIT, q2, q3 });
+        last_px = q3;
+        prev_tok = (ps == s) ? q3 : et;
+        if (download) {
+          CU_TRY(cudaStreamWaitEvent(ctx->copy_stream, b->ev[q3], 0), "cudaStreamWaitEvent");
+          if (!enqueue_download_rows(b, w.first, w.count, p0, p1, ctx->copy_stream)) return false;
+        }
+      }
+      if (ps != s) CU_TRY(cudaStreamWaitEvent(s, b->ev[last_px], 0), "cudaStreamWaitEvent");   // the scratch arrays are free again
+      continue;
+    }
     MARK(e2);
     b->spans.push_back({ ST_MODES, e0, e1 });
     b->spans.push_back({ ST_TOKENS, e1, e2 });
@@ -699,11 +807,11 @@ static bool batch_decode(WebPBatch* b, bool download) {
           acc += b->plan[b->img_item[c1]].out_bytes;
       }
       const int cnt = c1 - c0;
-      vp8k_reconstruct(s, imgs, hdrs, mbinfo, coeffs, yuv, c0, cnt, w.max_mb_w, w.max_mb_h);
+      vp8k_reconstruct(s, imgs, hdrs, mbinfo, coeffs, yuv, c0, cnt, w.max_mb_w, w.max_mb_h, 0, 0x7fffffff, (uint8_t*)b->d_band.p);
       MARK(e3);
-      vp8k_loop_filter(s, imgs, hdrs, mbinfo, yuv, c0, cnt);
+      vp8k_loop_filter(s, imgs, hdrs, mbinfo, yuv, c0, cnt, 0, 0x7fffffff);
       MARK(e4);
-      vp8k_emit(s, imgs, hdrs, yuv, (const uint8_t*)b->d_alpha.p, (uint8_t*)b->d_out.p, c0, cnt, w.max_units);
+      vp8k_emit(s, imgs, hdrs, yuv, (const uint8_t*)b->d_alpha.p, (uint8_t*)b->d_out.p, c0, cnt, w.max_units, 0, 0x7fffffff);
       MARK(e5);
       launches += 3;
       b->spans.push_back({ ST_RECON, prev, e3 });
@@ -718,6 +826,7 @@ static bool batch_decode(WebPBatch* b, bool download) {
     }
   }
 #undef MARK
+  const int e_end = ev_mark(b, s); if (e_end < 0) return false;
   // per-image status words: FrameHdr::status is the first field
   CU_TRY(cudaMemcpy2DAsync(b->statuses.data(), sizeof(int), hdrs, sizeof(FrameHdr), sizeof(int), m, cudaMemcpyDeviceToHost, s),
          "D2H status");
@@ -733,7 +842,8 @@ static bool batch_decode(WebPBatch* b, bool download) {
   b->timings.modes_ms = acc[ST_MODES]; b->timings.tokens_ms = acc[ST_TOKENS]; b->timings.recon_ms = acc[ST_RECON];
   b->timings.filter_ms = acc[ST_FILTER]; b->timings.emit_ms = acc[ST_EMIT];
   b->timings.alpha_ms = acc[ST_ALPHA];
-  b->timings.total_ms = acc[0] + acc[1] + acc[2] + acc[3] + acc[4] + acc[ST_ALPHA];
+  // with row bands the pixel stages of one band overlap the parse of the next: the step is what the stream saw end to end
+  { float ms = 0; CU_TRY(cudaEventElapsedTime(&ms, b->ev[e_begin], b->ev[e_end]), "cudaEventElapsedTime"); b->timings.total_ms = ms; }
   b->timings.launches = launches;
   for (int k = 0; k < m; ++k) {
     WebPBatchItem* it = &b->items[b->img_item[k]];
@@ -751,7 +861,7 @@ static VP8StatusCode batch_decode_locked(WebPBatch* b, bool download) {
   if (b->ctx != nullptr) {
     b->ctx->mu.lock();
     ok = batch_decode(b, download);
-    if (!ok) { cudaStreamSynchronize(b->ctx->stream); cudaStreamSynchronize(b->ctx->copy_stream); cudaGetLastError(); }
+    if (!ok) { cudaStreamSynchronize(b->ctx->stream); cudaStreamSynchronize(b->ctx->pixel_stream); cudaStreamSynchronize(b->ctx->copy_stream); cudaGetLastError(); }
     b->ctx->mu.unlock();
   }
   if (!ok) {

@@ -246,7 +246,8 @@ __host__ __device__ static inline TlLayout tl_layout(int P, int ipb, int ctx_str
 __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_lockstep(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
                                                                   FrameHdr* hdrs, uint32_t* mbinfo, int16_t* coeffs,
                                                                   const int* __restrict__ ids, int count, int P, int ipb, int lpw,
-                                                                  int cw, int ctx_stride, int grouped) {
+                                                                  int cw, int ctx_stride, int grouped, int row_begin, int row_end,
+                                                                  TokResume* resume, uint16_t* resume_ctx) {
   extern __shared__ __align__(16) uint8_t smem[];
   const TlLayout lay = tl_layout(P, ipb, ctx_stride);
   TlTables* tables = reinterpret_cast<TlTables*>(smem);
@@ -279,8 +280,12 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_lockstep(const uint
   c.progress = progress + (have ? slot : 0) * VP8B_MAX_PARTS;
   c.mbinfo = mbinfo + 4 * (size_t)im.mb_base;
   c.coeffs = coeffs + (size_t)im.mb_base * VP8B_COEFFS_PER_MB;
-  c.mb_w = im.mb_w; c.rows = have ? h->rows : 0; c.P = P; c.part = part; c.use_skip = h->use_skip; c.ctx_stride = ctx_stride;
-  if (part >= c.rows) have = 0;
+  // Row bands (single-partition images only): this launch parses macroblock rows [row_begin, row_end) and leaves the
+  // reader and the top contexts of each stream in `resume` / `resume_ctx` for the launch that takes the next band.
+  const int rows_total = have ? h->rows : 0;
+  c.mb_w = im.mb_w; c.rows = rows_total < row_end ? rows_total : row_end; c.P = P; c.part = part; c.use_skip = h->use_skip;
+  c.ctx_stride = ctx_stride;
+  if (part >= c.rows || row_begin >= c.rows) have = 0;
   // per-lane copies of what the rare paths need: left as kernel parameters they are re-read from the constant bank
   // in every iteration (the loads get hoisted above the branches that need them)
   asm volatile("" : "+r"(c.P), "+r"(c.ctx_stride), "+r"(c.mb_w), "+l"(c.mbinfo), "+l"(c.coeffs));
@@ -289,6 +294,16 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_lockstep(const uint
   TlLane L;
   if (have) {
     tl_lane_init(L, c, arena + im.in_off, h);
+    if (row_begin > 0) {
+      const TokResume rs = resume[img];
+      L.d.wp = L.d.wbase + rs.wp_off; L.d.V = rs.V; L.d.vlo = rs.vlo; L.d.nxt = rs.nxt; L.d.R24 = rs.R24;
+      L.d.nbits = rs.nbits; L.d.last_shift = rs.last_shift;
+      L.my = row_begin;
+      L.w_next = __ldg(c.mbinfo + 4 * ((size_t)row_begin * c.mb_w) + 3);
+      uint16_t* ring = c.topctx + (size_t)((row_begin - 1) & 1) * ctx_stride;
+      const uint16_t* saved = resume_ctx + (size_t)img * ctx_stride;
+      for (int x = 0; x < c.mb_w; ++x) ring[x] = saved[x];
+    }
   } else {
     tl_lane_idle(L, c, arena);
   }
@@ -326,6 +341,16 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_lockstep(const uint
     }
   }
   if (have && L.status != VP8B_OK) h->status = L.status;
+  if (have && L.status == VP8B_OK && row_end < rows_total) {   // more bands to come
+    TokResume rs;
+    const BoolDec& d = L.parked;
+    rs.wp_off = (int32_t)(d.wp - d.wbase); rs.V = d.V; rs.vlo = d.vlo; rs.nxt = d.nxt; rs.R24 = d.R24;
+    rs.nbits = d.nbits; rs.last_shift = d.last_shift; rs.pad = 0;
+    resume[img] = rs;
+    const uint16_t* ring = c.topctx + (size_t)((row_end - 1) & 1) * ctx_stride;
+    uint16_t* saved = resume_ctx + (size_t)img * ctx_stride;
+    for (int x = 0; x < c.mb_w; ++x) saved[x] = ring[x];
+  }
   if (L.sink == 0xffffffffu) h->status = VP8B_BITSTREAM_ERROR;   // never true (an XOR of bytes): keeps TlLane::sink alive
 }
 
@@ -334,18 +359,25 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_lockstep(const uint
 
 __global__ void __launch_bounds__(32 * RECON_WARPS) k_reconstruct(const ImgDesc* __restrict__ imgs, const FrameHdr* __restrict__ hdrs,
                                                                   uint32_t* mbinfo, const int16_t* __restrict__ coeffs,
-                                                                  uint8_t* yuv, int first) {
+                                                                  uint8_t* yuv, int first, int row_begin, int row_end,
+                                                                  uint8_t* band_ctx, int band_ctx_stride) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int img = first + blockIdx.x;
   if (hdrs[img].status != VP8B_OK) return;
   const ImgDesc im = imgs[img];
   const int mb_w = im.mb_w, mb_h = hdrs[img].rows;
+  // macroblock rows [r0, r1) of this launch (row bands: the top-neighbour pixels of row r0 come from band_ctx, where the
+  // launch that reconstructed row r0 - 1 left them; they must be the UNFILTERED ones, and the planes get filtered in between)
+  const int r0 = row_begin, r1 = mb_h < row_end ? mb_h : row_end;
+  if (r0 >= r1) return;
   const int warp = threadIdx.x >> 5;
   ReconWs& ws = *reinterpret_cast<ReconWs*>(smem + sizeof(ReconWs) * warp);
   ReconCtx cx;
   recon_ctx_bind(cx, smem + sizeof(ReconWs) * RECON_WARPS, mb_w, mb_h);
   __shared__ int16_t dqs[24];   // the frame's dequantisers, [segment][y1 dc/ac, y2 dc/ac, uv dc/ac]
   if (threadIdx.x < 24) dqs[threadIdx.x] = (&hdrs[img].dq[0][0])[threadIdx.x];
+  uint8_t* saved = band_ctx + (size_t)img * band_ctx_stride;
+  if (r0 > 0) for (int k = threadIdx.x; k < 8 * mb_w; k += blockDim.x) ((uint32_t*)cx.top_y)[k] = ((const uint32_t*)saved)[k];
   __syncthreads();
   const size_t nmb = (size_t)mb_w * im.mb_h;
   uint8_t* yp = yuv + (size_t)im.mb_base * 384;
@@ -353,26 +385,29 @@ __global__ void __launch_bounds__(32 * RECON_WARPS) k_reconstruct(const ImgDesc*
   uint8_t* vp = up + nmb * 64;
   uint32_t* mbi = mbinfo + 4 * (size_t)im.mb_base;
   const int16_t* cf = coeffs + (size_t)im.mb_base * VP8B_COEFFS_PER_MB;
-  const int steps = mb_w + 2 * (mb_h - 1);
+  const int nrows = r1 - r0;
+  const int steps = mb_w + 2 * (nrows - 1);
   for (int d = 0; d < steps; ++d) {
-    // rows with a macroblock on this anti-diagonal: mx = d - 2*my in [0, mb_w)
-    const int my_lo = (d - mb_w + 2 > 0) ? (d - mb_w + 2) >> 1 : 0;
-    const int my_hi = (d >> 1) < mb_h - 1 ? (d >> 1) : mb_h - 1;
-    for (int my = my_lo + warp; my <= my_hi; my += RECON_WARPS) {
-      const int mx = d - 2 * my;
+    // rows with a macroblock on this anti-diagonal: mx = d - 2*(my - r0) in [0, mb_w)
+    const int ly_lo = (d - mb_w + 2 > 0) ? (d - mb_w + 2) >> 1 : 0;
+    const int ly_hi = (d >> 1) < nrows - 1 ? (d >> 1) : nrows - 1;
+    for (int ly = ly_lo + warp; ly <= ly_hi; ly += RECON_WARPS) {
+      const int mx = d - 2 * ly, my = r0 + ly;
       const size_t idx = (size_t)my * mb_w + mx;
       const int16_t* dq6 = dqs + 6 * ((mbi[4 * idx + 3] >> MBW_SEG_SHIFT) & 3);
       recon_macroblock(ws, cx, mx, my, mb_w, mbi + 4 * idx, cf + idx * VP8B_COEFFS_PER_MB, dq6, yp, up, vp);
     }
     __syncthreads();
   }
+  if (r1 < mb_h) for (int k = threadIdx.x; k < 8 * mb_w; k += blockDim.x) ((uint32_t*)saved)[k] = ((const uint32_t*)cx.top_y)[k];
 }
 
 // ---------------------------------------------------------------------------------------------------------
 #define FILTER_WARPS 8
 
 __global__ void __launch_bounds__(32 * FILTER_WARPS) k_loop_filter(const ImgDesc* __restrict__ imgs, const FrameHdr* __restrict__ hdrs,
-                                                                   const uint32_t* __restrict__ mbinfo, uint8_t* yuv, int first) {
+                                                                   const uint32_t* __restrict__ mbinfo, uint8_t* yuv, int first,
+                                                                   int row_begin, int row_end) {
   __shared__ __align__(16) FilterWs wss[FILTER_WARPS];
   __shared__ uint8_t fstr[32];
   const int img = first + blockIdx.x;
@@ -390,12 +425,14 @@ __global__ void __launch_bounds__(32 * FILTER_WARPS) k_loop_filter(const ImgDesc
   uint8_t* up = yp + nmb * 256;
   uint8_t* vp = up + nmb * 64;
   const uint32_t* mbi = mbinfo + 4 * (size_t)im.mb_base;
-  const int steps = mb_w + 2 * (mb_h - 1);
+  const int r0 = row_begin, r1 = mb_h < row_end ? mb_h : row_end;   // macroblock rows of this launch (row bands)
+  const int nrows = r1 - r0;
+  const int steps = nrows > 0 ? mb_w + 2 * (nrows - 1) : 0;
   for (int d = 0; d < steps; ++d) {
-    const int my_lo = (d - mb_w + 2 > 0) ? (d - mb_w + 2) >> 1 : 0;
-    const int my_hi = (d >> 1) < mb_h - 1 ? (d >> 1) : mb_h - 1;
-    for (int my = my_lo + warp; my <= my_hi; my += FILTER_WARPS) {
-      const int mx = d - 2 * my;
+    const int ly_lo = (d - mb_w + 2 > 0) ? (d - mb_w + 2) >> 1 : 0;
+    const int ly_hi = (d >> 1) < nrows - 1 ? (d >> 1) : nrows - 1;
+    for (int ly = ly_lo + warp; ly <= ly_hi; ly += FILTER_WARPS) {
+      const int mx = d - 2 * ly, my = r0 + ly;
       const uint32_t w = mbi[4 * ((size_t)my * mb_w + mx) + 3];
       const uint8_t* fs = fstr + 8 * ((w >> MBW_SEG_SHIFT) & 3) + ((w & MBW_I4X4) ? 4 : 0);
       filter_macroblock(ws, mx, my, mb_w, filter_type, fs, (w & MBW_INNER) != 0, yp, up, vp);
@@ -409,7 +446,7 @@ __global__ void __launch_bounds__(32 * FILTER_WARPS) k_loop_filter(const ImgDesc
 
 __global__ void __launch_bounds__(EMIT_THREADS) k_emit(const ImgDesc* __restrict__ imgs, const FrameHdr* __restrict__ hdrs,
                                                        const uint8_t* __restrict__ yuv, const uint8_t* __restrict__ alpha_arena,
-                                                       uint8_t* out, int first, int blocks_per_image) {
+                                                       uint8_t* out, int first, int blocks_per_image, int pair_begin, int pair_end) {
   const int img = first + blockIdx.x / blocks_per_image;
   const int chunk = blockIdx.x % blocks_per_image;
   if (hdrs[img].status != VP8B_OK) return;
@@ -433,8 +470,9 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(const ImgDesc* __restrict
     else if (t < ny + 2 * nuv) emit_yuv_chunk(im, yp, up, vp, alpha, o, 2, (t - ny - nuv) % quv, (t - ny - nuv) / quv);
     else if (im.csp == 12 && t < 2 * ny + 2 * nuv) emit_yuv_chunk(im, yp, up, vp, alpha, o, 3, (t - ny - 2 * nuv) % qy, (t - ny - 2 * nuv) / qy);
   } else if (emit_uses_pairs(im.csp, im.flags, im.crop_x)) {   // 8 pixels x 2 rows per thread
-    const int qw = (w + 7) >> 3;
-    if (t < qw * ((h >> 1) + 1)) emit_rgba_pair8(im, yp, up, vp, alpha, o, t % qw, t / qw);
+    const int qw = (w + 7) >> 3;   // row pairs [pair_begin, pair_end) of this launch (row bands; everything otherwise)
+    const int pairs = (h >> 1) + 1, pt = t / qw + pair_begin;
+    if (pt < pairs && pt < pair_end) emit_rgba_pair8(im, yp, up, vp, alpha, o, t % qw, pt);
   } else {
     const int qw = (w + 3) >> 2;
     if (t < qw * h) emit_rgb_quad(im, yp, up, vp, alpha, o, t % qw, t / qw);
@@ -512,7 +550,8 @@ static void launch_tokens_fsm(cudaStream_t s, const uint8_t* arena, const ImgDes
 // Launch geometry of the lockstep parser: cw warps per block (one per SM sub-partition), lpw streams per warp so
 // that one block per SM holds the whole launch where shared memory allows it.
 static void launch_tokens_lockstep(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,
-                                   int16_t* coeffs, const int* ids, int count, int P, int max_mb_w) {
+                                   int16_t* coeffs, const int* ids, int count, int P, int max_mb_w, int row_begin, int row_end,
+                                   TokResume* resume, uint16_t* resume_ctx) {
   static int f_lpw = -1, f_cw = -1;
   if (f_lpw < 0) { f_lpw = env_int("WEBP_B200_TOKEN_LPW"); f_cw = env_int("WEBP_B200_TOKEN_CW"); }
   const long streams = (long)count * P;
@@ -541,7 +580,20 @@ static void launch_tokens_lockstep(cudaStream_t s, const uint8_t* arena, const I
   if (f_grouped == -2) { const char* e = getenv("WEBP_B200_TOKEN_GROUPED"); f_grouped = e ? atoi(e) : -1; }
   const int lanes_per_warp = (ipb * P + cw - 1) / cw;
   const int grouped = f_grouped >= 0 ? f_grouped : (lanes_per_warp >= 16);
-  k_parse_tokens_lockstep<<<blocks, 32 * cw, lay.total, s>>>(arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, ipb, lpw, cw, max_mb_w, grouped);
+  k_parse_tokens_lockstep<<<blocks, 32 * cw, lay.total, s>>>(arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, ipb, lpw, cw, max_mb_w, grouped,
+                                                             row_begin, row_end, resume, resume_ctx);
+}
+
+extern "C" int vp8k_tokens_take_bands(int count, int P) {   // does vp8k_parse_tokens pick the mapping that can parse by row bands?
+  const char* e = getenv("WEBP_B200_TOKEN_MAP");
+  if (e != NULL && e[0] != 'k') return 0;
+  return P == 1 && ((e != NULL && e[0] == 'k') || (long)count * P >= 148L * 4 * 2);
+}
+
+extern "C" void vp8k_parse_tokens_band(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,
+                                       int16_t* coeffs, const int* ids, int count, int max_mb_w, int row_begin, int row_end,
+                                       TokResume* resume, uint16_t* resume_ctx) {
+  launch_tokens_lockstep(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, 1, max_mb_w, row_begin, row_end, resume, resume_ctx);
 }
 
 extern "C" void vp8k_parse_tokens(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,
@@ -559,7 +611,10 @@ extern "C" void vp8k_parse_tokens(cudaStream_t s, const uint8_t* arena, const Im
   // 32768 streams (8 partitions): warp 420, state machine 247, lockstep 162; 65536 thumbnails: warp 274, lockstep 178.
   // Below two streams per SM sub-partition a lane-per-stream warp has nothing to share its instructions with.
   const int many = (long)count * P >= 148L * 4 * 2;
-  if (forced == 3 || (forced == 0 && many)) { launch_tokens_lockstep(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, max_mb_w); return; }
+  if (forced == 3 || (forced == 0 && many)) {
+    launch_tokens_lockstep(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, max_mb_w, 0, 0x7fffffff, nullptr, nullptr);
+    return;
+  }
   const int use_warp_map = forced ? (forced == 1) : 1;
   if (use_warp_map) {
     // one block per SM where the launch fits in one wave, else as many images per block as the block may hold
@@ -582,19 +637,21 @@ extern "C" void vp8k_parse_tokens(cudaStream_t s, const uint8_t* arena, const Im
 }
 
 extern "C" void vp8k_reconstruct(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, uint32_t* mbinfo, const int16_t* coeffs,
-                                 uint8_t* yuv, int first, int count, int max_mb_w, int max_mb_h) {
-  k_reconstruct<<<count, 32 * RECON_WARPS, recon_smem_bytes(max_mb_w, max_mb_h), s>>>(imgs, hdrs, mbinfo, coeffs, yuv, first);
+                                 uint8_t* yuv, int first, int count, int max_mb_w, int max_mb_h, int row_begin, int row_end,
+                                 uint8_t* band_ctx) {
+  k_reconstruct<<<count, 32 * RECON_WARPS, recon_smem_bytes(max_mb_w, max_mb_h), s>>>(imgs, hdrs, mbinfo, coeffs, yuv, first, row_begin,
+                                                                                      row_end, band_ctx, 32 * max_mb_w);
 }
 
 extern "C" void vp8k_loop_filter(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint32_t* mbinfo, uint8_t* yuv,
-                                 int first, int count) {
-  k_loop_filter<<<count, 32 * FILTER_WARPS, 0, s>>>(imgs, hdrs, mbinfo, yuv, first);
+                                 int first, int count, int row_begin, int row_end) {
+  k_loop_filter<<<count, 32 * FILTER_WARPS, 0, s>>>(imgs, hdrs, mbinfo, yuv, first, row_begin, row_end);
 }
 
 extern "C" void vp8k_emit(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint8_t* yuv, const uint8_t* alpha_arena,
-                          uint8_t* out, int first, int count, int max_units) {
+                          uint8_t* out, int first, int count, int max_units, int pair_begin, int pair_end) {
   const int bpi = (max_units + EMIT_THREADS - 1) / EMIT_THREADS;
-  k_emit<<<(unsigned)count * (unsigned)bpi, EMIT_THREADS, 0, s>>>(imgs, hdrs, yuv, alpha_arena, out, first, bpi);
+  k_emit<<<(unsigned)count * (unsigned)bpi, EMIT_THREADS, 0, s>>>(imgs, hdrs, yuv, alpha_arena, out, first, bpi, pair_begin, pair_end);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -19,13 +19,23 @@ void vp8k_parse_modes(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs,
 // `ids` = device array of `count` image indices that all have P token partitions.
 void vp8k_parse_tokens(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,
                        int16_t* coeffs, const int* ids, int count, int P, int max_mb_w);
+// Row bands: the token parse, the reconstruction, the loop filter and (for the 4-byte RGB family with fancy upsampling)
+// the output stage can each take a range of macroblock rows / output row pairs of every image, so that the pixel stages
+// and the download of one band run while the next band is parsed. `resume` (one TokResume per image), `resume_ctx`
+// (max_mb_w uint16 per image) and `band_ctx` (32 * max_mb_w bytes per image) carry the state across the band launches.
+// Whole images: rows [0, INT_MAX), pairs [0, INT_MAX).
+typedef struct TokResume { int32_t wp_off; uint32_t V, vlo, nxt, R24; int32_t nbits, last_shift, pad; } TokResume;
+int vp8k_tokens_take_bands(int count, int P);
+void vp8k_parse_tokens_band(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,
+                            int16_t* coeffs, const int* ids, int count, int max_mb_w, int row_begin, int row_end,
+                            TokResume* resume, uint16_t* resume_ctx);
 void vp8k_reconstruct(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, uint32_t* mbinfo, const int16_t* coeffs,
-                      uint8_t* yuv, int first, int count, int max_mb_w, int max_mb_h);
+                      uint8_t* yuv, int first, int count, int max_mb_w, int max_mb_h, int row_begin, int row_end, uint8_t* band_ctx);
 void vp8k_loop_filter(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint32_t* mbinfo, uint8_t* yuv,
-                      int first, int count);
+                      int first, int count, int row_begin, int row_end);
 // max_units = largest per-image work-item count (RGB: ceil(w/4)*h; YUV: 16-byte chunks of the three planes).
 void vp8k_emit(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint8_t* yuv, const uint8_t* alpha_arena,
-               uint8_t* out, int first, int count, int max_units);
+               uint8_t* out, int first, int count, int max_units, int pair_begin, int pair_end);
 
 // ALPH chunks (vp8l_alpha_core.h): `aimgs` = the `count` image indices that carry one, `plans` = where each of them
 // works (device addresses). Header pass first; the host then sizes tables / planes from the AlphaHdr it

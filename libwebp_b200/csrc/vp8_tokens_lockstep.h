@@ -161,6 +161,7 @@ struct TlLane {
   int mx, my;
   int done_mbs;
   int pend;               // TL_RUN / TL_BLOCK_END / TL_NEED_MB / TL_FINISHED
+  BoolDec parked;         // see tl_lane_park
   int waiting;            // P > 1: the partition owning the row above has not got far enough yet
   int alive;              // 0 once parked
   int status;
@@ -183,7 +184,7 @@ TK_FN void tl_lane_reset(TlLane& L, const TlCtx& c) {
   L.row = c.img_s; L.rowend = 0; L.s = 0; L.sink = 0; L.prob = 0; L.e0 = 0; L.e1 = 0; L.v = 0; L.ofs = 0; L.cx = 0;
   L.acc_lo = 0; L.acc_hi = 0; L.m = 0; L.m_next = 0; L.lut = 0; L.seq = 0;
   L.yrow = 0; L.yend = 0; L.yofs = 0; L.ylut = 0; L.mbcoef = c.coeffs;
-  L.mx = 0; L.my = c.part; L.done_mbs = 0; L.waiting = 1; L.alive = 1; L.status = VP8B_OK;
+  L.mx = 0; L.my = c.part; L.done_mbs = 0; L.waiting = 1; L.alive = 1; L.status = VP8B_OK; L.parked = L.d;
   L.pend = TL_NEED_MB;
   L.w = 0; L.w_next = 0;
 }
@@ -315,6 +316,7 @@ TK_FN void tl_mb_finish(TlLane& L, const TlCtx& c) {
 #define TL_DEAD 63u
 TK_FN void tl_lane_park(TlLane& L, const TlCtx& c) {
   L.pend = TL_FINISHED; L.alive = 0; L.waiting = 0;
+  L.parked = L.d;   // the reader as the lane left it (a launch that parses a band of rows hands it to the next one)
   L.s = TL_DEAD; L.row = c.img_s; L.rowend = 0;
   tl_prime(L, c);
 }

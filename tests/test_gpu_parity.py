@@ -308,3 +308,37 @@ def test_many_streams_take_the_lockstep_parser(W, ref):
         st, want = wants[j]
         assert st == 0 and sts[i] == 0, i
         assert np.array_equal(outs[i], want), i
+
+
+def test_row_bands(ref):
+    """WEBP_B200_BANDS=4 (read once per process, hence the subprocess): a wave of single-partition images large enough for
+    the lockstep parser is decoded in row bands -- token parse, reconstruction, loop filter, output and download of band
+    k before band k+1, the parser's and the reconstruction's state handed from launch to launch. Images taller and
+    shorter than a band, simple and normal loop filter, several 4-byte colourspaces; every image against the reference."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "import libwebp_b200 as W\n"
+        "from oracle import refwebp as ref\n"
+        "cfg_n = ref.EncCfg(70, 4, partitions=0, low_memory=0, segments=4)\n"
+        "distinct = []\n"
+        "for k in range(24):\n"
+        "    w, h = 48 + 16 * (k %% 3), (40, 130, 272, 300, 415, 512)[k %% 6]\n"
+        "    distinct.append(ref.encode(ref.synth(w, h, 9000 + k), ref.cfg_simple_1part(50 + k) if k %% 2 else cfg_n))\n"
+        "datas = [distinct[i %% 24] for i in range(1300)]\n"
+        "for csp in (W.MODE_RGBA, W.MODE_BGRA, W.MODE_ARGB):\n"
+        "    sts, outs = W.decode_batch(datas, csp)\n"
+        "    wants = [ref.decode(d, csp, 0) for d in distinct]\n"
+        "    for i in range(1300):\n"
+        "        st, want = wants[i %% 24]\n"
+        "        assert st == 0 and sts[i] == 0, (csp, i, sts[i])\n"
+        "        assert np.array_equal(outs[i].reshape(-1), want.reshape(-1)), (csp, i)\n"
+        "print('bands ok')\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for overlap in ("0", "1"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, WEBP_B200_BANDS="4", WEBP_B200_BAND_OVERLAP=overlap),
+                           capture_output=True, text=True)
+        assert r.returncode == 0 and "bands ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
