@@ -49,11 +49,22 @@
 #define TL_IMG_BYTES (4 * TL_TYPE_BYTES)
 #define TL_IMG_STRIDE (TL_IMG_BYTES + 20)   // odd multiple of 4 banks: the lanes of a warp spread over the banks
 
-// ---- transition entry:  [5:0] next s   6 advance the row (n++)   7 emit +-v at n   8 end of block   [26:16] addend of v
-#define TL_ADV 64u
-#define TL_EMIT 128u
-#define TL_EOB 256u
-#define TL_E(next, flags, add) ((uint32_t)(next) | (uint32_t)(flags) | ((uint32_t)(add) << 16))
+// ---- transition entry. o = next s + 64 * (advance the row, i.e. n++): the offset of the next probability from the current
+// row, and the index of the next state's entries in the table (whose two halves are alike).
+//   [31:25] o          so that the probability's address is row + (e >> 25): one shift-and-add
+//   [24:14] addend of v
+//   [9:3]   o again    so that the entries' address is table + (e & 0x3f8): one AND, the table base rides in the load
+//   1       end of block      0  emit +-v at n
+#define TL_ADV 64u     // flag arguments of TL_E only
+#define TL_EMIT 1u
+#define TL_EOB 2u
+#define TL_E(next, flags, add) \
+  (((((uint32_t)(next)) | ((uint32_t)(flags) & TL_ADV)) << 25) | ((uint32_t)(add) << 14) | \
+   ((((uint32_t)(next)) | ((uint32_t)(flags) & TL_ADV)) << 3) | ((uint32_t)(flags) & 3u))
+#define TL_E_OFS(e) ((e) >> 25)
+#define TL_E_TAB(e) ((e) & 0x3f8u)
+#define TL_E_ADD(e) (((e) >> 14) & 0x7ffu)
+#define TL_E_ROWSTEP(e) (((e) >> 31) << 6)
 
 TK_FN uint32_t tl_trans_entry(int s, int b) {
   if (s < 33) {
@@ -333,12 +344,11 @@ TK_FN void tl_lane_idle(TlLane& L, const TlCtx& c, const uint8_t* any) {
 TK_FN uint32_t tl_decode(TlLane& L, const TlCtx& c) {
   // ---- what the NEXT decode needs, fetched for both outcomes of this one before its bit is known: the dependent
   // chain of an iteration is then select -> multiply -> compare, and the shared-memory latency runs beside it.
-  // (ADV is bit 6 = the row stride, so `row + (e & 127)` is the next probability's address as it stands.)
-  const uint32_t o0 = L.e0 & 127u, o1 = L.e1 & 127u;
+  // (ADV is bit 6 of o = the row stride, so `row + o` is the next probability's address as it stands.)
   uint32_t e00, e01, e10, e11;
-  tk_lds_v2_pinned(c.tab_s + o0 * 8u, e00, e01);
-  tk_lds_v2_pinned(c.tab_s + o1 * 8u, e10, e11);
-  const uint32_t p0 = tk_lds_u8_pinned(L.row + o0), p1 = tk_lds_u8_pinned(L.row + o1);
+  tk_lds_v2_pinned(c.tab_s + TL_E_TAB(L.e0), e00, e01);
+  tk_lds_v2_pinned(c.tab_s + TL_E_TAB(L.e1), e10, e11);
+  const uint32_t p0 = tk_lds_u8_pinned(L.row + TL_E_OFS(L.e0)), p1 = tk_lds_u8_pinned(L.row + TL_E_OFS(L.e1));
   // ---- boolean decode (bit_reader_inl_utils.h:107-136)
   const int bit = bd_bit_nofill(L.d, L.prob);
   // ---- transition
@@ -348,12 +358,12 @@ TK_FN uint32_t tl_decode(TlLane& L, const TlCtx& c) {
                   // bit, which puts the shared-memory latency straight back on the dependent chain
   L.e0 = bit ? e10 : e00;
   L.e1 = bit ? e11 : e01;
-  L.v += e >> 16;
+  L.v += TL_E_ADD(e);
   if (e & TL_EMIT) {   // level, parse order
     *(int16_t*)((uint8_t*)L.mbcoef + (uint32_t)((L.row >> 5) + L.ofs)) = (int16_t)(bit ? -(int)L.v : (int)L.v);
     L.v = 0;
   }
-  L.row += e & TL_ADV;
+  L.row += TL_E_ROWSTEP(e);
   return e;
 }
 
