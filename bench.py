@@ -331,7 +331,7 @@ def main():
         "roofline": {"kernel": "k_" + dom[:-3], "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
                      "frac": round(achieved / hbm_peak, 5), "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes": int(alg[dom]), "peak_source": peak_src,
-                     "note": "serial boolean decoding: latency/issue-bound, not HBM-bound; see parse_bits_per_cycle_per_sm"},
+                     "note": "serial boolean decoding: bound by the latency of one dependent chain per stream, not by HBM; see parse_bits_per_cycle_per_sm"},
         "roofline_step": {"bound": "hbm", "achieved": round(step_bytes / (dev_ms_step * 1e-3) / 1e9, 1), "peak": hbm_peak,
                           "unit": "GB/s", "frac": round(step_bytes / (dev_ms_step * 1e-3) / 1e9 / hbm_peak, 4),
                           "bytes": "compressed file + RGBA output per image"},
