@@ -311,7 +311,15 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_lockstep(const uint
   // warp-uniform one makes the compiler fence the loop body with WARPSYNC.ALL; the vote costs as much as half a step
   // and is taken every 32 steps.
   const int r0 = (int)(L.sink >> 31);
-  if (grouped) {
+  if (grouped == 2) {
+    // Straight-line groups (vp8_tokens_lockstep.h:tl_group_flat): lanes that are not running execute a stand-in.
+    if (have) tl_set_aside(L);   // "needs a macroblock": the first event point takes the reader back
+    if (P > 1) {
+      while (__any_sync(0xffffffffu, L.alive)) { for (int r = r0; r < 8; ++r) tl_group_flat<1>(L, c); }
+    } else {
+      while (__any_sync(0xffffffffu, L.alive)) { for (int r = r0; r < 8; ++r) tl_group_flat<0>(L, c); }
+    }
+  } else if (grouped) {
     // Groups of four decodes per lane between event points (vp8_tokens_lockstep.h:tl_group). A lane starts as "needs a
     // macroblock", which the first event point resolves.
     if (P > 1) {
@@ -572,14 +580,15 @@ static void launch_tokens_lockstep(cudaStream_t s, const uint8_t* arena, const I
     cudaFuncSetAttribute(k_parse_tokens_lockstep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
     configured = lay.total;
   }
-  // How the lanes are run (vp8_tokens_lockstep.h): block ends on the spot while a warp has few lanes, grouped event
-  // points when it has many (their cost is shared by all the lanes that have a block end pending). Measured per 4096
-  // full-HD images: 1 partition (7 lanes per warp) 305 vs 385 ms, 8 partitions (28 lanes) 160 vs 91 ms; 65536
-  // thumbnails (shared memory holds 43 images per block: 5 lanes) 170 vs 201 ms.
+  // How the lanes are run (vp8_tokens_lockstep.h): 0 = block ends on the spot, while a warp has few lanes; 2 = groups of four
+  // straight-line steps with one event point, when it has many (the event point's cost is shared by all the lanes that have
+  // a block end pending); 1 = the same with branches around the steps of lanes that are not running. Measured per 4096
+  // full-HD images, styles 0 / 1 / 2: 1 partition (7 lanes per warp) 300 / 385 / 303 ms, 8 partitions (28 lanes) 160 / 91 /
+  // 83 ms; 65536 thumbnails (shared memory holds 43 images per block: 5 lanes) 170 / 201 / 205 ms.
   static int f_grouped = -2;
   if (f_grouped == -2) { const char* e = getenv("WEBP_B200_TOKEN_GROUPED"); f_grouped = e ? atoi(e) : -1; }
   const int lanes_per_warp = (ipb * P + cw - 1) / cw;
-  const int grouped = f_grouped >= 0 ? f_grouped : (lanes_per_warp >= 16);
+  const int grouped = f_grouped >= 0 ? f_grouped : (lanes_per_warp >= 16 ? 2 : 0);
   k_parse_tokens_lockstep<<<blocks, 32 * cw, lay.total, s>>>(arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, ipb, lpw, cw, max_mb_w, grouped,
                                                              row_begin, row_end, resume, resume_ctx);
 }

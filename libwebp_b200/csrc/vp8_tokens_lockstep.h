@@ -173,6 +173,7 @@ struct TlLane {
   int done_mbs;
   int pend;               // TL_RUN / TL_BLOCK_END / TL_NEED_MB / TL_FINISHED
   BoolDec parked;         // see tl_lane_park
+  uint32_t sv_V, sv_vlo, sv_R24; int sv_nbits, sv_shift;   // see tl_set_aside
   int waiting;            // P > 1: the partition owning the row above has not got far enough yet
   int alive;              // 0 once parked
   int status;
@@ -196,6 +197,7 @@ TK_FN void tl_lane_reset(TlLane& L, const TlCtx& c) {
   L.acc_lo = 0; L.acc_hi = 0; L.m = 0; L.m_next = 0; L.lut = 0; L.seq = 0;
   L.yrow = 0; L.yend = 0; L.yofs = 0; L.ylut = 0; L.mbcoef = c.coeffs;
   L.mx = 0; L.my = c.part; L.done_mbs = 0; L.waiting = 1; L.alive = 1; L.status = VP8B_OK; L.parked = L.d;
+  L.sv_V = L.d.V; L.sv_vlo = L.d.vlo; L.sv_R24 = L.d.R24; L.sv_nbits = L.d.nbits; L.sv_shift = L.d.last_shift;
   L.pend = TL_NEED_MB;
   L.w = 0; L.w_next = 0;
 }
@@ -433,6 +435,39 @@ TK_FN void tl_events(TlLane& L, const TlCtx& c) {
       }
     }
   }
+}
+
+// ---- third way: like the second, but a lane that is not running keeps executing the steps on a stand-in state
+// instead of branching around them, so that the four steps of a group are straight-line code the scheduler can
+// overlap. The stand-in: dead-state entries (no emit, no advance, no block end) and a reader whose real registers
+// are set aside in TlLane::sv (the words it has fetched stay put: the top-up is skipped for such lanes).
+TK_FN void tl_set_aside(TlLane& L) {
+  L.sv_V = L.d.V; L.sv_vlo = L.d.vlo; L.sv_R24 = L.d.R24; L.sv_nbits = L.d.nbits; L.sv_shift = L.d.last_shift;
+  L.prob = 0; L.e0 = TL_E(TL_DEAD, 0, 0); L.e1 = TL_E(TL_DEAD, 0, 0);
+}
+TK_FN void tl_take_back(TlLane& L) {
+  L.d.V = L.sv_V; L.d.vlo = L.sv_vlo; L.d.R24 = L.sv_R24; L.d.nbits = L.sv_nbits; L.d.last_shift = L.sv_shift;
+}
+
+TK_FN void tl_step_flat(TlLane& L, const TlCtx& c) {
+  const uint32_t e = tl_decode(L, c);
+  // tl_set_aside() on a block end, written as selects: a branch here would cut the group into four basic blocks
+  const bool done = (L.pend == TL_RUN) & (((e & TL_EOB) != 0u) | (L.row == L.rowend));
+  L.pend = done ? TL_BLOCK_END : L.pend;
+  L.sv_V = done ? L.d.V : L.sv_V; L.sv_vlo = done ? L.d.vlo : L.sv_vlo; L.sv_R24 = done ? L.d.R24 : L.sv_R24;
+  L.sv_nbits = done ? L.d.nbits : L.sv_nbits; L.sv_shift = done ? L.d.last_shift : L.sv_shift;
+  L.prob = done ? 0u : L.prob; L.e0 = done ? TL_E(TL_DEAD, 0, 0) : L.e0; L.e1 = done ? TL_E(TL_DEAD, 0, 0) : L.e1;
+}
+
+template <int MULTI>
+TK_FN void tl_group_flat(TlLane& L, const TlCtx& c) {
+  if (L.pend == TL_BLOCK_END || L.pend == TL_NEED_MB) {
+    tl_take_back(L);
+    tl_events<MULTI>(L, c);
+    if (L.pend != TL_RUN) tl_set_aside(L);   // still waiting for the row above, or finished
+  }
+  if (L.pend == TL_RUN) bd_fill_lookahead(L.d);
+  tl_step_flat(L, c); tl_step_flat(L, c); tl_step_flat(L, c); tl_step_flat(L, c);
 }
 
 // One group: the event point, a top-up of the window, four decodes.

@@ -113,7 +113,9 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
       for (int p = P - 1; p >= 0; --p) {   // reverse order: exercises the wait-for-progress path
         if (!live[p]) continue;
         any = true;
-        if (grouped) {
+        if (grouped && (variant & 32)) {   // variant bit 5: straight-line groups
+          if (P > 1) tl_group_flat<1>(lanes[p], ctxs[p]); else tl_group_flat<0>(lanes[p], ctxs[p]);
+        } else if (grouped) {
           if (P > 1) tl_group<1>(lanes[p], ctxs[p]); else tl_group<0>(lanes[p], ctxs[p]);
         } else {
           bd_fill_lookahead(lanes[p].d);
