@@ -775,7 +775,7 @@ static bool batch_decode(WebPBatch* b, bool download) {
         const int q0 = ev_mark(b, ps); if (q0 < 0) return false;
         vp8k_reconstruct(ps, imgs, hdrs, mbinfo, coeffs, yuv, w.first, w.count, w.max_mb_w, w.max_mb_h, r0, r1, band_ctx);
         const int q1 = ev_mark(b, ps); if (q1 < 0) return false;
-        vp8k_loop_filter(ps, imgs, hdrs, mbinfo, yuv, w.first, w.count, r0, r1);
+        vp8k_loop_filter(ps, imgs, hdrs, mbinfo, yuv, w.first, w.count, w.max_mb_h, r0, r1);
         const int q2 = ev_mark(b, ps); if (q2 < 0) return false;
         const int band_pairs = (p1 == 0x7fffffff ? (16 * w.max_mb_h) / 2 + 1 : p1) - p0;
         vp8k_emit(ps, imgs, hdrs, yuv, (const uint8_t*)b->d_alpha.p, (uint8_t*)b->d_out.p, w.first, w.count,
@@ -809,7 +809,7 @@ static bool batch_decode(WebPBatch* b, bool download) {
       const int cnt = c1 - c0;
       vp8k_reconstruct(s, imgs, hdrs, mbinfo, coeffs, yuv, c0, cnt, w.max_mb_w, w.max_mb_h, 0, 0x7fffffff, (uint8_t*)b->d_band.p);
       MARK(e3);
-      vp8k_loop_filter(s, imgs, hdrs, mbinfo, yuv, c0, cnt, 0, 0x7fffffff);
+      vp8k_loop_filter(s, imgs, hdrs, mbinfo, yuv, c0, cnt, w.max_mb_h, 0, 0x7fffffff);
       MARK(e4);
       vp8k_emit(s, imgs, hdrs, yuv, (const uint8_t*)b->d_alpha.p, (uint8_t*)b->d_out.p, c0, cnt, w.max_units, 0, 0x7fffffff);
       MARK(e5);

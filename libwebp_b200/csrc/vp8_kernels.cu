@@ -393,6 +393,9 @@ __global__ void __launch_bounds__(32 * RECON_WARPS) k_reconstruct(const ImgDesc*
   uint8_t* vp = up + nmb * 64;
   uint32_t* mbi = mbinfo + 4 * (size_t)im.mb_base;
   const int16_t* cf = coeffs + (size_t)im.mb_base * VP8B_COEFFS_PER_MB;
+  // Lag-2 anti-diagonal wavefront with a block-wide barrier per step. (A barrier-free variant -- one warp per row,
+  // progress counters in shared memory, as k_loop_filter does now -- measured 52 -> 72 ms here: this kernel is issue-bound
+  // and the warps that spin on a counter take issue slots from the ones that work; at a barrier they sleep.)
   const int nrows = r1 - r0;
   const int steps = mb_w + 2 * (nrows - 1);
   for (int d = 0; d < steps; ++d) {
@@ -435,17 +438,29 @@ __global__ void __launch_bounds__(32 * FILTER_WARPS) k_loop_filter(const ImgDesc
   const uint32_t* mbi = mbinfo + 4 * (size_t)im.mb_base;
   const int r0 = row_begin, r1 = mb_h < row_end ? mb_h : row_end;   // macroblock rows of this launch (row bands)
   const int nrows = r1 - r0;
-  const int steps = nrows > 0 ? mb_w + 2 * (nrows - 1) : 0;
-  for (int d = 0; d < steps; ++d) {
-    const int ly_lo = (d - mb_w + 2 > 0) ? (d - mb_w + 2) >> 1 : 0;
-    const int ly_hi = (d >> 1) < nrows - 1 ? (d >> 1) : nrows - 1;
-    for (int ly = ly_lo + warp; ly <= ly_hi; ly += FILTER_WARPS) {
-      const int mx = d - 2 * ly, my = r0 + ly;
+  // Wavefront without block-wide barriers: warp w owns rows r0 + w, r0 + w + 8, ... and walks each left to right; macroblock
+  // (mx, my) follows (mx - 1, my) (same warp) and (mx + 1, my - 1), whose owner publishes the count of macroblocks it has
+  // finished (frame_dec.c:203-262 filters in raster order and reaches 3 pixels up and left, 4 with the ones it only reads).
+  // Measured against a barrier per anti-diagonal: simple filter 27.4 -> 26.0 ms, normal filter 64 -> 50 ms per 4096 full-HD images.
+  extern __shared__ __align__(16) uint8_t fsmem[];
+  volatile int* row_done = reinterpret_cast<volatile int*>(fsmem);
+  for (int k = threadIdx.x; k < nrows; k += blockDim.x) row_done[k] = 0;
+  __syncthreads();
+  for (int ly = warp; ly < nrows; ly += FILTER_WARPS) {
+    const int my = r0 + ly;
+    for (int mx = 0; mx < mb_w; ++mx) {
+      if (ly > 0) {
+        const int need = mx + 2 < mb_w ? mx + 2 : mb_w;
+        while (row_done[ly - 1] < need) __nanosleep(20);
+        __threadfence_block();
+      }
       const uint32_t w = mbi[4 * ((size_t)my * mb_w + mx) + 3];
       const uint8_t* fs = fstr + 8 * ((w >> MBW_SEG_SHIFT) & 3) + ((w & MBW_I4X4) ? 4 : 0);
       filter_macroblock(ws, mx, my, mb_w, filter_type, fs, (w & MBW_INNER) != 0, yp, up, vp);
+      __syncwarp();
+      __threadfence_block();
+      if ((threadIdx.x & 31) == 0) row_done[ly] = mx + 1;
     }
-    __syncthreads();
   }
 }
 
@@ -653,8 +668,8 @@ extern "C" void vp8k_reconstruct(cudaStream_t s, const ImgDesc* imgs, const Fram
 }
 
 extern "C" void vp8k_loop_filter(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint32_t* mbinfo, uint8_t* yuv,
-                                 int first, int count, int row_begin, int row_end) {
-  k_loop_filter<<<count, 32 * FILTER_WARPS, 0, s>>>(imgs, hdrs, mbinfo, yuv, first, row_begin, row_end);
+                                 int first, int count, int max_mb_h, int row_begin, int row_end) {
+  k_loop_filter<<<count, 32 * FILTER_WARPS, (size_t)max_mb_h * 4 + 16, s>>>(imgs, hdrs, mbinfo, yuv, first, row_begin, row_end);
 }
 
 extern "C" void vp8k_emit(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint8_t* yuv, const uint8_t* alpha_arena,
