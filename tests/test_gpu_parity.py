@@ -277,7 +277,7 @@ def test_crop_and_flip(W, ref, manifest, amanifest):
             assert np.array_equal(want, got.reshape(-1))
 
 
-@pytest.mark.parametrize("mapping", ["warp", "k", "lanes"])
+@pytest.mark.parametrize("mapping", ["warp", "k", "k:1", "k:2", "lanes"])
 def test_every_token_mapping(mapping):
     """The three mappings of the token parse (one warp per partition, lockstep lanes, lane state machine) are picked by
     stream count; here each is forced in turn (WEBP_B200_TOKEN_MAP is read once per process, hence the subprocess) and
@@ -287,9 +287,11 @@ def test_every_token_mapping(mapping):
     import sys
     if os.environ.get("WEBP_B200_TOKEN_MAP_INNER"):
         pytest.skip("inner run")
-    env = dict(os.environ, WEBP_B200_TOKEN_MAP=mapping, WEBP_B200_TOKEN_MAP_INNER="1")
+    env = dict(os.environ, WEBP_B200_TOKEN_MAP=mapping.split(":")[0], WEBP_B200_TOKEN_MAP_INNER="1")
+    if ":" in mapping:   # the lockstep parser's other two ways of running its lanes (grouped event points, straight-line groups)
+        env["WEBP_B200_TOKEN_GROUPED"] = mapping.split(":")[1]
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
-                        "manifest or mixed_sizes or fresh_corpora or full_size or damaged"], env=env, capture_output=True, text=True,
+                        "manifest or mixed_sizes or fresh_corpora or full_size or damaged or many_streams"], env=env, capture_output=True, text=True,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
