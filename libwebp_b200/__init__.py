@@ -154,7 +154,17 @@ def WebPGetFeatures(data):
     return st, dict(width=f.width, height=f.height, has_alpha=f.has_alpha, has_animation=f.has_animation, format=f.format)
 
 
-def _new_config(csp, bypass_filtering, no_fancy_upsampling, dithering_strength=0, crop=None, flip=False):
+def scaled_dims(w, h, scaled):
+    """WebPRescalerGetScaledDimensions (src/utils/rescaler_utils.c:86-118): 0 = keep the ratio."""
+    sw, sh = scaled
+    if sw == 0 and h > 0:
+        sw = (w * sh + h - 1) // h
+    if sh == 0 and w > 0:
+        sh = (h * sw + w - 1) // w
+    return sw, sh
+
+
+def _new_config(csp, bypass_filtering, no_fancy_upsampling, dithering_strength=0, crop=None, flip=False, scaled=None):
     cfg = WebPDecoderConfig()
     if not lib().WebPInitDecoderConfigInternal(C.byref(cfg), WEBP_DECODER_ABI_VERSION):
         raise RuntimeError("WebPInitDecoderConfig failed (ABI mismatch)")
@@ -166,6 +176,9 @@ def _new_config(csp, bypass_filtering, no_fancy_upsampling, dithering_strength=0
     if crop is not None:
         cfg.options.use_cropping = 1
         (cfg.options.crop_left, cfg.options.crop_top, cfg.options.crop_width, cfg.options.crop_height) = crop
+    if scaled is not None:
+        cfg.options.use_scaling = 1
+        cfg.options.scaled_width, cfg.options.scaled_height = scaled
     return cfg
 
 
@@ -194,17 +207,22 @@ def out_bytes(csp, w, h, stride=None):
 
 
 def WebPDecode(data, csp=MODE_RGBA, bypass_filtering=False, no_fancy_upsampling=False, stride=None, external=True,
-               dithering_strength=0, crop=None, flip=False):
+               dithering_strength=0, crop=None, flip=False, scaled=None):
     """One image through the C-ABI WebPDecode (a GPU batch of one). Returns (status, ndarray or None):
-    (h, stride) bytes for RGB-family modes, flat y|u|v for MODE_YUV. crop = (left, top, width, height)."""
+    (h, stride) bytes for RGB-family modes, flat y|u|v for MODE_YUV. crop = (left, top, width, height);
+    scaled = (width, height) turns options.use_scaling on (0 = keep the ratio)."""
     L = lib()
-    cfg = _new_config(csp, bypass_filtering, no_fancy_upsampling, dithering_strength, crop, flip)
+    cfg = _new_config(csp, bypass_filtering, no_fancy_upsampling, dithering_strength, crop, flip, scaled)
     st, f = WebPGetFeatures(data)
     if st != VP8_STATUS_OK:
         return L.WebPDecode(data, len(data), C.byref(cfg)), None
     w, h = f["width"], f["height"]
     if crop is not None and crop[2] > 0 and crop[3] > 0:
         w, h = crop[2], crop[3]
+    if scaled is not None:
+        w, h = scaled_dims(w, h, scaled)
+        if w <= 0 or h <= 0:
+            return L.WebPDecode(data, len(data), C.byref(cfg)), None
     if external:
         if csp in (MODE_YUV, MODE_YUVA):
             out = np.zeros(out_bytes(csp, w, h), np.uint8)

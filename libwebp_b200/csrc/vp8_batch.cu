@@ -222,6 +222,7 @@ struct Wave {
   int first = 0, count = 0;
   size_t mbs = 0;
   int max_mb_w = 0, max_mb_h = 0, max_units = 0;
+  int max_scaled_items = 0;   // images with options.use_scaling: work items of vp8k_emit_scaled (0 = none in this wave)
   int ids_off[4] = { 0, 0, 0, 0 }, ids_cnt[4] = { 0, 0, 0, 0 };   // per log2(P) slice of the ids array
 };
 
@@ -273,7 +274,7 @@ static VP8StatusCode plan_item(WebPBatchItem* it, const WebPBatchOptions& opt, V
   if (c->has_alph_chunk && cfg->options.alpha_dithering_strength > 0) return VP8_STATUS_UNSUPPORTED_FEATURE;   // alpha de-banding
   if (c->part0_size > c->frame_size - 10) return VP8_STATUS_NOT_ENOUGH_DATA;   // vp8_dec.c:345-348
   const WebPDecoderOptions* o = &cfg->options;
-  if (o->use_scaling) return VP8_STATUS_UNSUPPORTED_FEATURE;   // the rescaler is not on the device
+  if (o->use_scaling && c->has_alph_chunk) return VP8_STATUS_UNSUPPORTED_FEATURE;   // rescaled alpha (io_dec.c:272-300,414-470) is not on the device
   const int csp = cfg->output.colorspace;
   if (csp < MODE_RGB || csp >= MODE_LAST) return VP8_STATUS_INVALID_PARAM;
   if (!csp_supported(csp)) return VP8_STATUS_UNSUPPORTED_FEATURE;
@@ -285,12 +286,22 @@ static VP8StatusCode plan_item(WebPBatchItem* it, const WebPBatchOptions& opt, V
       return VP8_STATUS_INVALID_PARAM;
     ow = cw; oh = ch;
   }
+  if (o->use_scaling) {   // WebPAllocateDecBuffer, buffer_dec.c:197-205; WebPRescalerGetScaledDimensions, rescaler_utils.c:86-118
+    int sw = o->scaled_width, sh = o->scaled_height;
+    if (sw == 0 && oh > 0) sw = (int)(((uint64_t)ow * sh + oh - 1) / oh);
+    if (sh == 0 && ow > 0) sh = (int)(((uint64_t)oh * sw + ow - 1) / ow);
+    if (sw <= 0 || sh <= 0 || sw > 0x3fffffff || sh > 0x3fffffff) return VP8_STATUS_INVALID_PARAM;
+    if (sw > 16383 || sh > 16383) return VP8_STATUS_UNSUPPORTED_FEATURE;   // ImgDesc keeps 16-bit dimensions
+    ow = sw; oh = sh;
+  }
   if (opt.output == WEBP_BATCH_HOST) return prepare_host_buffer(ow, oh, &cfg->output);
   cfg->output.width = ow; cfg->output.height = oh;
   return VP8_STATUS_OK;
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int final_w(const ImgDesc& d) { return d.dst_w ? d.dst_w : d.out_w; }   // the picture that leaves the device
+static inline int final_h(const ImgDesc& d) { return d.dst_h ? d.dst_h : d.out_h; }
 
 // Host pass: everything that can be decided without a GPU. Returns the number of items still alive.
 static int batch_plan(WebPBatch* b, std::vector<Vp8Container>& cont) {
@@ -356,6 +367,13 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
       d.crop_x = (uint16_t)(cfg->options.crop_left & ~1); d.crop_y = (uint16_t)(cfg->options.crop_top & ~1);
       d.out_w = (uint16_t)cfg->options.crop_width; d.out_h = (uint16_t)cfg->options.crop_height;
     }
+    int fw = d.out_w, fh = d.out_h;   // the picture that leaves the device
+    if (cfg->options.use_scaling) {
+      fw = cfg->output.width; fh = cfg->output.height;   // set by plan_item
+      d.dst_w = (uint16_t)fw; d.dst_h = (uint16_t)fh;
+      // WebPIoInitFromOptions, webp_dec.c:851-856: no loop filter for large downscaling ratios (against the whole picture)
+      if (fw < c.width * 3 / 4 && fh < c.height * 3 / 4) d.flags |= VP8B_FLAG_BYPASS_FILTER;
+    }
     const int ds = cfg->options.dithering_strength;
     d.dither_f = (uint8_t)(ds < 0 ? 0 : ds > 100 ? 255 : ds * 255 / 100);
     d.num_parts = (uint8_t)vp8b_prescan_partitions(b->items[i].data + c.frame_offset + 10, c.part0_size);
@@ -368,12 +386,11 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
     }
     size_t bytes;
     if (d.csp == MODE_YUV || d.csp == MODE_YUVA) {
-      d.out_stride = d.out_w;
-      bytes = (size_t)d.out_w * d.out_h + 2 * (size_t)((d.out_w + 1) / 2) * ((d.out_h + 1) / 2) +
-              (d.csp == MODE_YUVA ? (size_t)d.out_w * d.out_h : 0);
+      d.out_stride = fw;
+      bytes = (size_t)fw * fh + 2 * (size_t)((fw + 1) / 2) * ((fh + 1) / 2) + (d.csp == MODE_YUVA ? (size_t)fw * fh : 0);
     } else {
-      d.out_stride = d.out_w * kBpp[d.csp];
-      bytes = (size_t)d.out_stride * d.out_h;
+      d.out_stride = fw * kBpp[d.csp];
+      bytes = (size_t)d.out_stride * fh;
     }
     d.out_off = b->out_total;
     b->out_total += align_up(bytes, 256);
@@ -433,6 +450,10 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
                             : pairs ? ((d.out_w + 7) / 8) * (d.out_h / 2 + 1)
                                     : ((d.out_w + 3) / 4) * d.out_h;
       w.max_units = std::max(w.max_units, units);
+      if (d.dst_w != 0) {
+        const int uvdw = (d.dst_w + 1) / 2;
+        w.max_scaled_items = std::max(w.max_scaled_items, (d.csp == MODE_YUV || d.csp == MODE_YUVA) ? d.dst_w + 2 * uvdw + (d.csp == MODE_YUVA ? d.dst_w : 0) : (int)d.dst_w);
+      }
     }
     b->waves.push_back(w);
   }
@@ -545,7 +566,7 @@ static bool enqueue_download(WebPBatch* b, int first, int count, cudaStream_t s,
     const uint8_t* src = dout + d.out_off;
     if (d.csp == MODE_YUV || d.csp == MODE_YUVA) {
       if (!flush()) return false;
-      const int w = d.out_w, h = d.out_h, uvw = (w + 1) / 2, uvh = (h + 1) / 2;
+      const int w = final_w(d), h = final_h(d), uvw = (w + 1) / 2, uvh = (h + 1) / 2;
       const WebPYUVABuffer* y = &o->u.YUVA;
       CU_TRY(cudaMemcpy2DAsync(y->y, y->y_stride, src, w, w, h, cudaMemcpyDeviceToHost, s), "D2H Y");
       CU_TRY(cudaMemcpy2DAsync(y->u, y->u_stride, src + (size_t)w * h, uvw, uvw, uvh, cudaMemcpyDeviceToHost, s), "D2H U");
@@ -556,7 +577,7 @@ static bool enqueue_download(WebPBatch* b, int first, int count, cudaStream_t s,
       continue;
     }
     const size_t row = (size_t)d.out_stride;
-    const size_t bytes = row * d.out_h;
+    const size_t bytes = row * final_h(d);
     if ((size_t)o->u.RGBA.stride == row) {
       if (run_bytes > 0 && o->u.RGBA.rgba == run_host + run_bytes && src == run_dev + run_bytes) {
         run_bytes += bytes;
@@ -567,7 +588,7 @@ static bool enqueue_download(WebPBatch* b, int first, int count, cudaStream_t s,
       if (run_bytes >= ((size_t)256 << 20)) { if (!flush()) return false; }
     } else {
       if (!flush()) return false;
-      CU_TRY(cudaMemcpy2DAsync(o->u.RGBA.rgba, (size_t)o->u.RGBA.stride, src, row, row, d.out_h, cudaMemcpyDeviceToHost, s), "D2H pixels 2D");
+      CU_TRY(cudaMemcpy2DAsync(o->u.RGBA.rgba, (size_t)o->u.RGBA.stride, src, row, row, final_h(d), cudaMemcpyDeviceToHost, s), "D2H pixels 2D");
     }
   }
   return flush();
@@ -743,7 +764,7 @@ static bool batch_decode(WebPBatch* b, bool download) {
       for (int k = w.first; ok && k < w.first + w.count; ++k) {
         const ImgDesc& d = b->imgs[k];
         const bool pairs = !(d.flags & VP8B_FLAG_NO_FANCY) && kBpp[d.csp] == 4 && d.csp != MODE_YUVA;
-        if (!pairs || (d.flags & VP8B_FLAG_FLIP) || d.crop_x != 0 || d.crop_y != 0 || d.out_w != d.width || d.out_h != d.height) ok = false;
+        if (!pairs || d.dst_w != 0 || (d.flags & VP8B_FLAG_FLIP) || d.crop_x != 0 || d.crop_y != 0 || d.out_w != d.width || d.out_h != d.height) ok = false;
       }
       // Off unless asked for (WEBP_B200_BANDS=n). Measured on 4096 full-HD images (profiles/r01m_row_bands.log): the
       // download of one band during the parse of the next slows the parse as much as it hides (a kernel running beside a
@@ -812,6 +833,7 @@ static bool batch_decode(WebPBatch* b, bool download) {
       vp8k_loop_filter(s, imgs, hdrs, mbinfo, yuv, c0, cnt, w.max_mb_h, 0, 0x7fffffff);
       MARK(e4);
       vp8k_emit(s, imgs, hdrs, yuv, (const uint8_t*)b->d_alpha.p, (uint8_t*)b->d_out.p, c0, cnt, w.max_units, 0, 0x7fffffff);
+      if (w.max_scaled_items > 0) { vp8k_emit_scaled(s, imgs, hdrs, yuv, (uint8_t*)b->d_out.p, c0, cnt, w.max_scaled_items); ++launches; }
       MARK(e5);
       launches += 3;
       b->spans.push_back({ ST_RECON, prev, e3 });
@@ -912,12 +934,13 @@ extern "C" int WebPBatchOutput(const WebPBatch* b, int index, WebPBatchPlane* p)
   const ImgDesc& d = b->imgs[b->plan[index].img];
   uint8_t* base = (uint8_t*)b->d_out.p + d.out_off;
   memset(p, 0, sizeof(*p));
-  p->width = d.out_w; p->height = d.out_h;
+  const int fw = final_w(d), fh = final_h(d);
+  p->width = fw; p->height = fh;
   p->y_or_rgba = base; p->stride = d.out_stride;
   if (d.csp == MODE_YUV || d.csp == MODE_YUVA) {
-    const int uvw = (d.out_w + 1) / 2, uvh = (d.out_h + 1) / 2;
-    p->u = base + (size_t)d.out_w * d.out_h;
-    p->v = base + (size_t)d.out_w * d.out_h + (size_t)uvw * uvh;
+    const int uvw = (fw + 1) / 2, uvh = (fh + 1) / 2;
+    p->u = base + (size_t)fw * fh;
+    p->v = base + (size_t)fw * fh + (size_t)uvw * uvh;
     p->uv_stride = uvw;
   }
   return 1;

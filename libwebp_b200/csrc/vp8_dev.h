@@ -51,6 +51,10 @@ typedef struct ImgDesc {
   // output window (options.use_cropping, webp_dec.c:802-829; the whole picture otherwise). crop_x / crop_y are even.
   // The window is upsampled and emitted as if it were the picture (edges replicate at the window, io_dec.c:57-109).
   uint16_t crop_x, crop_y, out_w, out_h;
+  // options.use_scaling: the window above is rescaled to dst_w x dst_h (io_dec.c:239-556, src/dsp/rescaler.c); 0 = no scaling.
+  // out_stride / out_off then describe the scaled picture.
+  uint16_t dst_w, dst_h;
+  uint32_t pad_;
 } ImgDesc;
 #define VP8B_NO_ALPHA 0xffffffffffffffffull
 

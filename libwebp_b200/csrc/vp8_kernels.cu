@@ -474,6 +474,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(const ImgDesc* __restrict
   const int chunk = blockIdx.x % blocks_per_image;
   if (hdrs[img].status != VP8B_OK) return;
   const ImgDesc im = imgs[img];
+  if (im.dst_w != 0) return;   // options.use_scaling: k_emit_scaled
   const size_t nmb = (size_t)im.mb_w * im.mb_h;
   // planes and alpha re-based at the output window (crop_x, crop_y are even)
   const uint8_t* yp = yuv + (size_t)im.mb_base * 384;
@@ -500,6 +501,22 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(const ImgDesc* __restrict
     const int qw = (w + 3) >> 2;
     if (t < qw * h) emit_rgb_quad(im, yp, up, vp, alpha, o, t % qw, t / qw);
   }
+}
+
+// options.use_scaling: one thread per output column of a plane (vp8_pixel_core.h:emit_scaled_column).
+__global__ void __launch_bounds__(EMIT_THREADS) k_emit_scaled(const ImgDesc* __restrict__ imgs, const FrameHdr* __restrict__ hdrs,
+                                                              const uint8_t* __restrict__ yuv, uint8_t* out, int first, int blocks_per_image) {
+  const int img = first + blockIdx.x / blocks_per_image;
+  const int chunk = blockIdx.x % blocks_per_image;
+  if (hdrs[img].status != VP8B_OK) return;
+  const ImgDesc im = imgs[img];
+  if (im.dst_w == 0) return;
+  const size_t nmb = (size_t)im.mb_w * im.mb_h;
+  const uint8_t* yp = yuv + (size_t)im.mb_base * 384;
+  const uint8_t* up = yp + nmb * 256 + (size_t)(im.crop_y >> 1) * (8 * im.mb_w) + (im.crop_x >> 1);
+  const uint8_t* vp = yp + nmb * 256 + nmb * 64 + (size_t)(im.crop_y >> 1) * (8 * im.mb_w) + (im.crop_x >> 1);
+  yp += (size_t)im.crop_y * (16 * im.mb_w) + im.crop_x;
+  emit_scaled_column(im, yp, up, vp, out + im.out_off, chunk * EMIT_THREADS + threadIdx.x);
 }
 
 // =========================================================================================================
@@ -676,6 +693,12 @@ extern "C" void vp8k_emit(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* h
                           uint8_t* out, int first, int count, int max_units, int pair_begin, int pair_end) {
   const int bpi = (max_units + EMIT_THREADS - 1) / EMIT_THREADS;
   k_emit<<<(unsigned)count * (unsigned)bpi, EMIT_THREADS, 0, s>>>(imgs, hdrs, yuv, alpha_arena, out, first, bpi, pair_begin, pair_end);
+}
+
+extern "C" void vp8k_emit_scaled(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint8_t* yuv, uint8_t* out,
+                                 int first, int count, int max_items) {
+  const int bpi = (max_items + EMIT_THREADS - 1) / EMIT_THREADS;
+  k_emit_scaled<<<(unsigned)count * (unsigned)bpi, EMIT_THREADS, 0, s>>>(imgs, hdrs, yuv, out, first, bpi);
 }
 
 // ---------------------------------------------------------------------------------------------------------

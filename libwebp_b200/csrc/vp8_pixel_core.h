@@ -767,6 +767,176 @@ VP8_UNROLL
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// options.use_scaling. The reference rescales Y, U and V with one WebPRescaler each (src/utils/rescaler_utils.c,
+// src/dsp/rescaler.c: fixed point, 32 fractional bits) as the rows arrive and converts YUV444 -> RGB row by row
+// (EmitRescaledRGB / ExportRGB, io_dec.c:357-412), or stores the planes (EmitRescaledYUV, io_dec.c:252-270).
+// Here one thread owns one OUTPUT COLUMN of one plane: the horizontal pass of a source row is a closed form of
+// the column index (import_row_*), the vertical pass is the reference's state machine with the column's two
+// accumulators in registers. Everything is uint32 / uint64 arithmetic exactly as in the reference.
+#define RS_ONE (1ull << 32)
+#define RS_FRAC(x, y) ((uint32_t)((((uint64_t)(x)) << 32) / (uint64_t)(y)))
+#define RS_MULT_FIX(x, y) ((((uint64_t)(x)) * (uint64_t)(y) + (RS_ONE >> 1)) >> 32)
+#define RS_MULT_FIX_FLOOR(x, y) ((((uint64_t)(x)) * (uint64_t)(y)) >> 32)
+
+struct Rescaler {   // one plane of one image, as seen by one output column (WebPRescalerInit, rescaler_utils.c:24-84)
+  const uint8_t* src; int src_stride;
+  int src_w, src_h, dst_w, dst_h;
+  int x_expand, y_expand;
+  int x_add, x_sub, y_add, y_sub, y_accum;
+  uint32_t fx_scale, fy_scale, fxy_scale;
+  int src_y, dst_y;
+  uint32_t irow, frow;   // this column's entries of the two work rows
+};
+
+VP8_PFN void rescaler_init(Rescaler& r, const uint8_t* src, int src_stride, int src_w, int src_h, int dst_w, int dst_h) {
+  r.src = src; r.src_stride = src_stride;
+  r.src_w = src_w; r.src_h = src_h; r.dst_w = dst_w; r.dst_h = dst_h;
+  r.x_expand = src_w < dst_w; r.y_expand = src_h < dst_h;
+  r.x_add = r.x_expand ? dst_w - 1 : src_w;
+  r.x_sub = r.x_expand ? src_w - 1 : dst_w;
+  r.fx_scale = r.x_expand ? 0u : RS_FRAC(1, r.x_sub);
+  r.y_add = r.y_expand ? src_h - 1 : src_h;
+  r.y_sub = r.y_expand ? dst_h - 1 : dst_h;
+  r.y_accum = r.y_expand ? r.y_sub : r.y_add;
+  r.fxy_scale = 0;
+  if (!r.y_expand) {
+    const uint64_t ratio = ((uint64_t)dst_h * RS_ONE) / ((uint64_t)r.x_add * (uint64_t)r.y_add);
+    r.fxy_scale = (ratio != (uint32_t)ratio) ? 0u : (uint32_t)ratio;
+    r.fy_scale = RS_FRAC(1, r.y_sub);
+  } else {
+    r.fy_scale = RS_FRAC(1, r.x_add);
+  }
+  r.src_y = 0; r.dst_y = 0; r.irow = 0; r.frow = 0;
+}
+
+// frow[x] of WebPRescalerImportRowShrink_C (rescaler.c:62-95) for one source row: output k consumes the inputs
+// n(k-1) .. n(k)-1 with n(k) = ceil((k+1) * x_add / x_sub), starting from the fraction the previous output left over.
+VP8_PFN uint32_t import_row_shrink(const Rescaler& r, const uint8_t* row, int x) {
+  const int64_t t1 = (int64_t)(x + 1) * r.x_add;
+  const int n1 = (int)((t1 + r.x_sub - 1) / r.x_sub);
+  const int acc1 = (int)(t1 - (int64_t)n1 * r.x_sub);          // accum after this output (<= 0)
+  int n0 = 0;
+  uint32_t sum = 0;
+  if (x > 0) {
+    const int64_t t0 = (int64_t)x * r.x_add;
+    n0 = (int)((t0 + r.x_sub - 1) / r.x_sub);
+    const int acc0 = (int)(t0 - (int64_t)n0 * r.x_sub);
+    const uint32_t frac0 = (uint32_t)row[n0 - 1] * (uint32_t)(-acc0);
+    sum = (uint32_t)(int)RS_MULT_FIX(frac0, r.fx_scale);
+  }
+  for (int i = n0; i < n1; ++i) sum += row[i];
+  const uint32_t frac = (uint32_t)row[n1 - 1] * (uint32_t)(-acc1);
+  return sum * (uint32_t)r.x_sub - frac;
+}
+
+// frow[x] of WebPRescalerImportRowExpand_C (rescaler.c:29-60): bilinear, the input position advanced a(k) times before
+// output k, a(k) the smallest a >= 0 with x_add - k * x_sub + a * x_add >= 0.
+VP8_PFN uint32_t import_row_expand(const Rescaler& r, const uint8_t* row, int x) {
+  const int64_t d = (int64_t)x * r.x_sub - r.x_add;
+  const int a = (d > 0) ? (int)((d + r.x_add - 1) / r.x_add) : 0;
+  const int accum = (int)((int64_t)r.x_add - (int64_t)x * r.x_sub + (int64_t)a * r.x_add);
+  const uint32_t left = row[a];
+  const uint32_t right = (r.src_w > 1) ? row[a + 1 < r.src_w ? a + 1 : r.src_w - 1] : left;
+  return right * (uint32_t)r.x_add + (left - right) * (uint32_t)accum;
+}
+
+// The next output sample of this column: import source rows until one is due (WebPRescalerImport, rescaler_utils.c:
+// 132-155), then export it (WebPRescalerExportRow + ExportRowExpand_C / ExportRowShrink_C, rescaler.c:100-196).
+VP8_PFN int rescaler_next(Rescaler& r, int x) {
+  while (r.y_accum > 0 && r.src_y < r.src_h) {
+    const uint8_t* row = r.src + (size_t)r.src_y * r.src_stride;
+    if (r.y_expand) r.irow = r.frow;   // the two work rows swap roles
+    r.frow = r.x_expand ? import_row_expand(r, row, x) : import_row_shrink(r, row, x);
+    if (!r.y_expand) r.irow += r.frow;
+    ++r.src_y;
+    r.y_accum -= r.y_sub;
+  }
+  int v;
+  if (r.y_expand) {
+    if (r.y_accum == 0) {
+      v = (int)RS_MULT_FIX(r.frow, r.fy_scale);
+    } else {
+      const uint32_t B = RS_FRAC(-r.y_accum, r.y_sub);
+      const uint32_t A = (uint32_t)(RS_ONE - B);
+      const uint64_t I = (uint64_t)A * r.frow + (uint64_t)B * r.irow;
+      const uint32_t J = (uint32_t)((I + (RS_ONE >> 1)) >> 32);
+      v = (int)RS_MULT_FIX(J, r.fy_scale);
+    }
+  } else if (r.fxy_scale) {
+    const uint32_t yscale = r.fy_scale * (uint32_t)(-r.y_accum);
+    if (yscale) {
+      const uint32_t frac = (uint32_t)RS_MULT_FIX_FLOOR(r.frow, yscale);
+      v = (int)RS_MULT_FIX(r.irow - frac, r.fxy_scale);
+      r.irow = frac;
+    } else {
+      v = (int)RS_MULT_FIX(r.irow, r.fxy_scale);
+      r.irow = 0;
+    }
+  } else {   // src_width == 1, same height: the accumulated row as it stands (rescaler.c:208-216)
+    v = (int)(r.irow & 0xffu);
+    r.irow = 0;
+    r.y_accum += r.y_add; ++r.dst_y;
+    return v;
+  }
+  r.y_accum += r.y_add;
+  ++r.dst_y;
+  return v > 255 ? 255 : v;
+}
+
+// One pixel of any RGB-family colourspace at column x of output row `orow` (a = 0xff: scaling is only offered for
+// opaque images).
+VP8_PFN void store_rgb_pixel(int csp, int y, int u, int v, uint8_t* orow, int x) {
+  int r, g, b;
+  yuv_to_rgb(y, u, v, &r, &g, &b);
+  if (csp == 0 || csp == 2) {
+    uint8_t* o = orow + 3 * x;
+    if (csp == 0) { o[0] = (uint8_t)r; o[1] = (uint8_t)g; o[2] = (uint8_t)b; } else { o[0] = (uint8_t)b; o[1] = (uint8_t)g; o[2] = (uint8_t)r; }
+  } else if (csp == 5 || csp == 6 || csp == 10) {
+    const uint32_t p2 = pack_pixel2(csp, r, g, b, 0xff);
+    orow[2 * x] = (uint8_t)p2; orow[2 * x + 1] = (uint8_t)(p2 >> 8);
+  } else {
+    const uint32_t p4 = pack_pixel4(csp, r, g, b, 0xff);
+    uint8_t* o = orow + 4 * x;
+    o[0] = (uint8_t)p4; o[1] = (uint8_t)(p4 >> 8); o[2] = (uint8_t)(p4 >> 16); o[3] = (uint8_t)(p4 >> 24);
+  }
+}
+
+// Work item `t` of a scaled image. RGB family: t = output column, all rows (Y, U, V each rescaled to dst_w x dst_h,
+// then converted). MODE_YUV / MODE_YUVA: t in [0, dst_w) = a Y column, then (dst_w+1)/2 U columns, as many V columns,
+// and for MODE_YUVA dst_w columns of the (opaque) alpha plane. yplane/uplane/vplane = the window's origin.
+VP8_PFN void emit_scaled_column(const ImgDesc& im, const uint8_t* yplane, const uint8_t* uplane, const uint8_t* vplane,
+                                uint8_t* out, int t) {
+  const int sw = im.out_w, sh = im.out_h, dw = im.dst_w, dh = im.dst_h;
+  const int ys = 16 * im.mb_w, uvs = 8 * im.mb_w;
+  const int uv_sw = (sw + 1) >> 1, uv_sh = (sh + 1) >> 1;
+  const int flip = (im.flags & VP8B_FLAG_FLIP) != 0;
+  if (im.csp == 11 || im.csp == 12) {
+    const int uv_dw = (dw + 1) >> 1, uv_dh = (dh + 1) >> 1;
+    Rescaler r;
+    uint8_t* dst; int stride, rows, x;
+    if (t < dw) { rescaler_init(r, yplane, ys, sw, sh, dw, dh); dst = out; stride = im.out_stride; rows = dh; x = t; }
+    else if (t < dw + uv_dw) { rescaler_init(r, uplane, uvs, uv_sw, uv_sh, uv_dw, uv_dh); dst = out + (size_t)im.out_stride * dh; stride = uv_dw; rows = uv_dh; x = t - dw; }
+    else if (t < dw + 2 * uv_dw) { rescaler_init(r, vplane, uvs, uv_sw, uv_sh, uv_dw, uv_dh); dst = out + (size_t)im.out_stride * dh + (size_t)uv_dw * uv_dh; stride = uv_dw; rows = uv_dh; x = t - dw - uv_dw; }
+    else if (im.csp == 12 && t < 2 * dw + 2 * uv_dw) {
+      uint8_t* a = out + (size_t)im.out_stride * dh + 2 * (size_t)uv_dw * uv_dh;
+      for (int k = 0; k < dh; ++k) a[(size_t)k * dw + (t - dw - 2 * uv_dw)] = 0xff;   // FillAlphaPlane, io_dec.c:283-288
+      return;
+    } else return;
+    for (int k = 0; k < rows; ++k) dst[(size_t)(flip ? rows - 1 - k : k) * stride + x] = (uint8_t)rescaler_next(r, x);
+    return;
+  }
+  if (t >= dw) return;
+  Rescaler ry, ru, rv;
+  rescaler_init(ry, yplane, ys, sw, sh, dw, dh);
+  rescaler_init(ru, uplane, uvs, uv_sw, uv_sh, dw, dh);
+  rescaler_init(rv, vplane, uvs, uv_sw, uv_sh, dw, dh);
+  for (int k = 0; k < dh; ++k) {
+    const int y = rescaler_next(ry, t), u = rescaler_next(ru, t), v = rescaler_next(rv, t);
+    store_rgb_pixel(im.csp, y, u, v, out + (size_t)(flip ? dh - 1 - k : k) * im.out_stride, t);
+  }
+}
+
 // MODE_YUV (EmitYUV, io_dec.c:25-40): 16 bytes of one row of one plane. plane 0 = Y (w x h), 1 = U, 2 = V
 // ((w+1)/2 x (h+1)/2). Output = y | u | v at out_off with strides out_stride / (w+1)/2.
 // plane 3 (MODE_YUVA only, EmitAlphaYUV io_dec.c:131-152) = the alpha plane, 0xff where the file has none.

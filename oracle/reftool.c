@@ -255,6 +255,52 @@ int reft_decode_window(const uint8_t* data, size_t size, int csp, int flags, con
   return WebPDecode(data, size, &cfg);
 }
 
+/* WebPDecode with options.use_scaling (scaled2 = requested width, height; 0 = keep the ratio), optionally on a crop
+ * window, into a tight external buffer; dims2 receives the scaled dimensions the decoder settled on. */
+int reft_decode_scaled(const uint8_t* data, size_t size, int csp, int flags, const int* crop4, const int* scaled2, int* dims2,
+                       uint8_t* out, size_t out_size) {
+  WebPDecoderConfig cfg;
+  int st, w, h, sw, sh;
+  if (!WebPInitDecoderConfig(&cfg)) return -1;
+  st = WebPGetFeatures(data, size, &cfg.input);
+  if (st != VP8_STATUS_OK) return WebPDecode(data, size, &cfg);
+  cfg.options.bypass_filtering = flags & 1;
+  cfg.options.no_fancy_upsampling = (flags >> 1) & 1;
+  cfg.options.flip = (flags >> 3) & 1;
+  w = cfg.input.width; h = cfg.input.height;
+  if (crop4 != NULL && crop4[2] > 0) {
+    cfg.options.use_cropping = 1;
+    cfg.options.crop_left = crop4[0]; cfg.options.crop_top = crop4[1];
+    cfg.options.crop_width = crop4[2]; cfg.options.crop_height = crop4[3];
+    w = crop4[2]; h = crop4[3];
+  }
+  cfg.options.use_scaling = 1;
+  cfg.options.scaled_width = scaled2[0]; cfg.options.scaled_height = scaled2[1];
+  sw = scaled2[0]; sh = scaled2[1];
+  if (sw == 0 && h > 0) sw = (int)(((uint64_t)w * sh + h - 1) / h);
+  if (sh == 0 && w > 0) sh = (int)(((uint64_t)h * sw + w - 1) / w);
+  dims2[0] = sw; dims2[1] = sh;
+  cfg.output.colorspace = (WEBP_CSP_MODE)csp;
+  if (sw <= 0 || sh <= 0) return WebPDecode(data, size, &cfg);   /* the status the decoder reports for this request */
+  cfg.output.is_external_memory = 1;
+  if (csp == MODE_YUV || csp == MODE_YUVA) {
+    const int uvw = (sw + 1) / 2, uvh = (sh + 1) / 2;
+    if (out_size < (size_t)sw * sh + 2 * (size_t)uvw * uvh + (csp == MODE_YUVA ? (size_t)sw * sh : 0)) return -2;
+    cfg.output.u.YUVA.y = out; cfg.output.u.YUVA.y_stride = sw; cfg.output.u.YUVA.y_size = (size_t)sw * sh;
+    cfg.output.u.YUVA.u = out + (size_t)sw * sh; cfg.output.u.YUVA.u_stride = uvw; cfg.output.u.YUVA.u_size = (size_t)uvw * uvh;
+    cfg.output.u.YUVA.v = cfg.output.u.YUVA.u + (size_t)uvw * uvh; cfg.output.u.YUVA.v_stride = uvw; cfg.output.u.YUVA.v_size = (size_t)uvw * uvh;
+    if (csp == MODE_YUVA) {
+      cfg.output.u.YUVA.a = cfg.output.u.YUVA.v + (size_t)uvw * uvh; cfg.output.u.YUVA.a_stride = sw; cfg.output.u.YUVA.a_size = (size_t)sw * sh;
+    }
+  } else {
+    const int bpp = (csp == MODE_RGB || csp == MODE_BGR) ? 3
+                  : (csp == MODE_RGBA_4444 || csp == MODE_RGB_565 || csp == MODE_rgbA_4444) ? 2 : 4;
+    if (out_size < (size_t)sw * sh * bpp) return -2;
+    cfg.output.u.RGBA.rgba = out; cfg.output.u.RGBA.stride = sw * bpp; cfg.output.u.RGBA.size = out_size;
+  }
+  return WebPDecode(data, size, &cfg);
+}
+
 int reft_features(const uint8_t* data, size_t size, int* feat5) {
   WebPBitstreamFeatures f;
   const int st = WebPGetFeatures(data, size, &f);

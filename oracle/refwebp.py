@@ -77,6 +77,9 @@ def lib():
         L.reft_features.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int)]
         if hasattr(L, "reft_decode_window"):
             L.reft_decode_window.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_size_t]
+        if hasattr(L, "reft_decode_scaled"):
+            L.reft_decode_scaled.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                             C.POINTER(C.c_int), C.c_void_p, C.c_size_t]
         L.reft_decode_bench.restype = C.c_double
         L.reft_decode_bench.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
@@ -164,6 +167,28 @@ def decode_window(data, csp=MODE_RGBA, flags=0, crop=None):
     c4 = (C.c_int * 4)(*(crop if crop else (0, 0, 0, 0)))
     st = L.reft_decode_window(data, len(data), csp, flags, c4, out.ctypes.data, out.size)
     return st, (out[:n] if st == 0 else None)
+
+
+def decode_scaled(data, csp=MODE_RGBA, flags=0, crop=None, scaled=(0, 0)):
+    """Reference WebPDecode with options.use_scaling (scaled = (width, height), 0 = keep the ratio), optionally on a crop
+    window. Returns (status, (scaled_w, scaled_h), flat ndarray or None)."""
+    L = lib()
+    c4 = (C.c_int * 4)(*(crop if crop else (0, 0, 0, 0)))
+    s2 = (C.c_int * 2)(*scaled)
+    d2 = (C.c_int * 2)(0, 0)
+    st0, f = features(data)
+    w, h = (crop[2], crop[3]) if crop else (f["width"], f["height"])
+    sw, sh = scaled
+    if sw == 0 and h > 0:
+        sw = (w * sh + h - 1) // h
+    if sh == 0 and w > 0:
+        sh = (h * sw + w - 1) // w
+    sw, sh = max(sw, 1), max(sh, 1)
+    n = (sw * sh + 2 * ((sw + 1) // 2) * ((sh + 1) // 2) + (sw * sh if csp == MODE_YUVA else 0)) if csp in (MODE_YUV, MODE_YUVA) \
+        else sw * sh * BPP[csp]
+    out = np.zeros(max(n, 16), np.uint8)
+    st = L.reft_decode_scaled(data, len(data), csp, flags, c4, s2, d2, out.ctypes.data, out.size)
+    return st, (d2[0], d2[1]), (out[:n] if st == 0 else None)
 
 
 def decode_bench(datas, nthreads, csp=MODE_RGBA, passes=1, simd=True):

@@ -25,7 +25,8 @@
 // variant bit 2: lane FSM with a lazy ring producer
 // variant bit 3: lockstep lane parser (vp8_tokens_lockstep.h), lanes advanced round-robin; with bit 4 its grouped event points
 static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags, uint8_t* out, size_t out_size,
-                           int stride, int variant, uint8_t* unfiltered, int crop_x, int crop_y, int crop_w, int crop_h);
+                           int stride, int variant, uint8_t* unfiltered, int crop_x, int crop_y, int crop_w, int crop_h,
+                           int scaled_w = 0, int scaled_h = 0);
 
 extern "C" int emu_decode(const uint8_t* data, size_t size, int csp, int flags, uint8_t* out, size_t out_size,
                           int stride, int variant, uint8_t* unfiltered /* optional: y|u|v padded */) {
@@ -38,8 +39,16 @@ extern "C" int emu_decode_window(const uint8_t* data, size_t size, int csp, int 
   return emu_decode_crop(data, size, csp, flags, out, out_size, stride, 0, nullptr, crop_x, crop_y, crop_w, crop_h);
 }
 
+// options.use_scaling: the (cropped) picture rescaled to scaled_w x scaled_h (both given); `stride` and `out` describe
+// the scaled picture.
+extern "C" int emu_decode_scaled(const uint8_t* data, size_t size, int csp, int flags, uint8_t* out, size_t out_size,
+                                 int stride, int crop_x, int crop_y, int crop_w, int crop_h, int scaled_w, int scaled_h) {
+  return emu_decode_crop(data, size, csp, flags, out, out_size, stride, 0, nullptr, crop_x, crop_y, crop_w, crop_h, scaled_w, scaled_h);
+}
+
 static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags, uint8_t* out, size_t out_size,
-                           int stride, int variant, uint8_t* unfiltered, int crop_x, int crop_y, int crop_w, int crop_h) {
+                           int stride, int variant, uint8_t* unfiltered, int crop_x, int crop_y, int crop_w, int crop_h,
+                           int scaled_w, int scaled_h) {
   const int reverse_steps = variant & 1;
   Vp8Container c;
   int st = vp8b_parse_container(data, size, 1, &c);
@@ -60,6 +69,10 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
   im.csp = (uint8_t)csp; im.flags = (uint8_t)flags; im.out_stride = stride;
   im.out_w = im.width; im.out_h = im.height;
   if (crop_w > 0) { im.crop_x = (uint16_t)(crop_x & ~1); im.crop_y = (uint16_t)(crop_y & ~1); im.out_w = (uint16_t)crop_w; im.out_h = (uint16_t)crop_h; }
+  if (scaled_w > 0) {   // like batch_build (vp8_batch.cu): scaled dimensions, and no loop filter for large downscaling ratios
+    im.dst_w = (uint16_t)scaled_w; im.dst_h = (uint16_t)scaled_h;
+    if (scaled_w < c.width * 3 / 4 && scaled_h < c.height * 3 / 4) im.flags |= VP8B_FLAG_BYPASS_FILTER;
+  }
   im.num_parts = (uint8_t)vp8b_prescan_partitions(data + c.frame_offset + 10, c.part0_size);
   const int mb_w = im.mb_w, mb_h = im.mb_h;
   const size_t nmb = (size_t)mb_w * mb_h;
@@ -257,6 +270,14 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
   const uint8_t* wu = up + (size_t)(im.crop_y >> 1) * (8 * mb_w) + (im.crop_x >> 1);
   const uint8_t* wv = vp + (size_t)(im.crop_y >> 1) * (8 * mb_w) + (im.crop_x >> 1);
   if (alpha) alpha += (size_t)im.crop_y * im.width + im.crop_x;
+  if (im.dst_w != 0) {
+    if (alpha) return VP8_STATUS_UNSUPPORTED_FEATURE;
+    const int dw = im.dst_w, uvdw = (dw + 1) / 2;
+    const int items = (csp == MODE_YUV || csp == MODE_YUVA) ? dw + 2 * uvdw + (csp == MODE_YUVA ? dw : 0) : dw;
+    if (csp == MODE_YUV || csp == MODE_YUVA) im.out_stride = dw;
+    for (int t = 0; t < items; ++t) emit_scaled_column(im, wy, wu, wv, out, t);
+    return VP8_STATUS_OK;
+  }
   if (csp == MODE_YUV || csp == MODE_YUVA) {
     const int uvw = (w + 1) / 2, uvh = (h + 1) / 2;
     if (out_size < (size_t)w * h + 2 * (size_t)uvw * uvh + (csp == MODE_YUVA ? (size_t)w * h : 0)) return VP8_STATUS_INVALID_PARAM;

@@ -164,3 +164,35 @@ def test_emu_crop_and_flip_match_reference(ref, manifest, amanifest):
         s_emu, _ = emu_window(data, 1, 0, crop, 320, 200)
         assert s_ref == 2   # the product refuses these on the host (plan_item), the emulation harness never sees them
         del s_emu
+
+
+def test_emu_scaling_matches_reference(ref, manifest):
+    """options.use_scaling (io_dec.c:239-556, src/dsp/rescaler.c): up and down, one axis each way, ratio-preserving
+    requests, crop + scale, planar and packed colourspaces, flip; the loop filter is dropped for large downscaling ratios
+    exactly like WebPIoInitFromOptions does. The device code's host build against the reference, byte for byte."""
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR])
+    L = C.CDLL(os.path.join(EMU_DIR, "libvp8_emu.so"))
+    L.emu_decode_scaled.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_int, C.c_int, C.c_int]
+    rng = np.random.default_rng(21)
+    for e in manifest:
+        W, H = e["features"]["width"], e["features"]["height"]
+        for it in range(6):
+            crop = None
+            if it >= 4:
+                cw, ch = int(rng.integers(1, W + 1)), int(rng.integers(1, H + 1))
+                crop = (int(rng.integers(0, W - cw + 1)), int(rng.integers(0, H - ch + 1)), cw, ch)
+            w, h = (crop[2], crop[3]) if crop else (W, H)
+            req = [(max(1, w // 2), max(1, h // 3)), (w * 2 + 1, h + 7), (max(1, w - 1), h * 3), (0, max(1, h // 2)), (w + 5, 0),
+                   (int(rng.integers(1, 2 * w + 2)), int(rng.integers(1, 2 * h + 2)))][it]
+            flip = int(rng.integers(0, 2))
+            for csp in (1, 0, 11, 6, 12, 4):
+                s_ref, (sw, sh), want = ref.decode_scaled(e["data"], csp, 8 if flip else 0, crop, req)
+                assert s_ref == 0, (e["file"], req, crop, s_ref)
+                n = (sw * sh + 2 * ((sw + 1) // 2) * ((sh + 1) // 2) + (sw * sh if csp == 12 else 0)) if csp in (11, 12) else sw * sh * ref.BPP[csp]
+                out = np.zeros(max(n, 16), np.uint8)
+                c = crop or (0, 0, 0, 0)
+                st = L.emu_decode_scaled(e["data"], len(e["data"]), csp, 4 if flip else 0, out.ctypes.data, out.size,
+                                         sw if csp in (11, 12) else sw * ref.BPP[csp], c[0], c[1], c[2], c[3], sw, sh)
+                assert st == 0, (e["file"], req, crop, csp, st)
+                assert np.array_equal(out[:n], want), (e["file"], req, crop, flip, csp, (sw, sh))

@@ -344,3 +344,33 @@ def test_row_bands(ref):
         r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, WEBP_B200_BANDS="4", WEBP_B200_BAND_OVERLAP=overlap),
                            capture_output=True, text=True)
         assert r.returncode == 0 and "bands ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_scaling(W, ref, manifest, amanifest):
+    """options.use_scaling through the C ABI: the rescaler runs on the device (one thread per output column), output
+    identical to the reference's for up- and downscaling, ratio-preserving requests, crop + scale, flip, packed and
+    planar colourspaces; impossible requests are refused with the reference's status, scaled alpha is not offered."""
+    rng = np.random.default_rng(22)
+    for e in manifest:
+        Wd, Hd = e["features"]["width"], e["features"]["height"]
+        for it in range(5):
+            crop = None
+            if it >= 3:
+                cw, ch = int(rng.integers(1, Wd + 1)), int(rng.integers(1, Hd + 1))
+                crop = (int(rng.integers(0, Wd - cw + 1)), int(rng.integers(0, Hd - ch + 1)), cw, ch)
+            w, h = (crop[2], crop[3]) if crop else (Wd, Hd)
+            req = [(max(1, w // 2), max(1, h // 3)), (w * 2 + 1, h + 7), (0, max(1, h // 2)),
+                   (int(rng.integers(1, 2 * w + 2)), int(rng.integers(1, 2 * h + 2))), (max(1, w - 1), h * 2)][it]
+            flip = bool(rng.integers(0, 2))
+            for csp in (W.MODE_RGBA, W.MODE_RGB, W.MODE_YUV, W.MODE_RGB_565):
+                s_ref, (sw, sh), want = ref.decode_scaled(e["data"], csp, 8 if flip else 0, crop, req)
+                st, out = W.WebPDecode(e["data"], csp, crop=crop, flip=flip, scaled=req)
+                assert st == s_ref == 0, (e["file"], req, crop, csp, st, s_ref, W.last_error())
+                assert np.array_equal(out.reshape(-1)[:want.size], want), (e["file"], req, crop, flip, csp, (sw, sh))
+    data = manifest[0]["data"]
+    for req in ((0, 0), (-3, 10)):
+        s_ref, _, _ = ref.decode_scaled(data, W.MODE_RGBA, 0, None, req)
+        st, _ = W.WebPDecode(data, W.MODE_RGBA, scaled=req)
+        assert st == s_ref != 0, (req, st, s_ref)
+    st, _ = W.WebPDecode(amanifest[0]["data"], W.MODE_RGBA, scaled=(10, 10))
+    assert st == 4   # VP8_STATUS_UNSUPPORTED_FEATURE: refused, never decoded differently
