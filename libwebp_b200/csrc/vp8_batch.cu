@@ -274,7 +274,6 @@ static VP8StatusCode plan_item(WebPBatchItem* it, const WebPBatchOptions& opt, V
   if (c->has_alph_chunk && cfg->options.alpha_dithering_strength > 0) return VP8_STATUS_UNSUPPORTED_FEATURE;   // alpha de-banding
   if (c->part0_size > c->frame_size - 10) return VP8_STATUS_NOT_ENOUGH_DATA;   // vp8_dec.c:345-348
   const WebPDecoderOptions* o = &cfg->options;
-  if (o->use_scaling && c->has_alph_chunk) return VP8_STATUS_UNSUPPORTED_FEATURE;   // rescaled alpha (io_dec.c:272-300,414-470) is not on the device
   const int csp = cfg->output.colorspace;
   if (csp < MODE_RGB || csp >= MODE_LAST) return VP8_STATUS_INVALID_PARAM;
   if (!csp_supported(csp)) return VP8_STATUS_UNSUPPORTED_FEATURE;
@@ -833,7 +832,7 @@ static bool batch_decode(WebPBatch* b, bool download) {
       vp8k_loop_filter(s, imgs, hdrs, mbinfo, yuv, c0, cnt, w.max_mb_h, 0, 0x7fffffff);
       MARK(e4);
       vp8k_emit(s, imgs, hdrs, yuv, (const uint8_t*)b->d_alpha.p, (uint8_t*)b->d_out.p, c0, cnt, w.max_units, 0, 0x7fffffff);
-      if (w.max_scaled_items > 0) { vp8k_emit_scaled(s, imgs, hdrs, yuv, (uint8_t*)b->d_out.p, c0, cnt, w.max_scaled_items); ++launches; }
+      if (w.max_scaled_items > 0) { vp8k_emit_scaled(s, imgs, hdrs, yuv, (const uint8_t*)b->d_alpha.p, (uint8_t*)b->d_out.p, c0, cnt, w.max_scaled_items); ++launches; }
       MARK(e5);
       launches += 3;
       b->spans.push_back({ ST_RECON, prev, e3 });

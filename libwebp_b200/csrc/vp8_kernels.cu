@@ -505,7 +505,8 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(const ImgDesc* __restrict
 
 // options.use_scaling: one thread per output column of a plane (vp8_pixel_core.h:emit_scaled_column).
 __global__ void __launch_bounds__(EMIT_THREADS) k_emit_scaled(const ImgDesc* __restrict__ imgs, const FrameHdr* __restrict__ hdrs,
-                                                              const uint8_t* __restrict__ yuv, uint8_t* out, int first, int blocks_per_image) {
+                                                              const uint8_t* __restrict__ yuv, const uint8_t* __restrict__ alpha_arena,
+                                                              uint8_t* out, int first, int blocks_per_image) {
   const int img = first + blockIdx.x / blocks_per_image;
   const int chunk = blockIdx.x % blocks_per_image;
   if (hdrs[img].status != VP8B_OK) return;
@@ -516,7 +517,8 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit_scaled(const ImgDesc* __r
   const uint8_t* up = yp + nmb * 256 + (size_t)(im.crop_y >> 1) * (8 * im.mb_w) + (im.crop_x >> 1);
   const uint8_t* vp = yp + nmb * 256 + nmb * 64 + (size_t)(im.crop_y >> 1) * (8 * im.mb_w) + (im.crop_x >> 1);
   yp += (size_t)im.crop_y * (16 * im.mb_w) + im.crop_x;
-  emit_scaled_column(im, yp, up, vp, out + im.out_off, chunk * EMIT_THREADS + threadIdx.x);
+  const uint8_t* alpha = (im.alpha_plane != VP8B_NO_ALPHA) ? alpha_arena + im.alpha_plane + (size_t)im.crop_y * im.width + im.crop_x : nullptr;
+  emit_scaled_column(im, yp, up, vp, alpha, out + im.out_off, chunk * EMIT_THREADS + threadIdx.x);
 }
 
 // =========================================================================================================
@@ -695,10 +697,10 @@ extern "C" void vp8k_emit(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* h
   k_emit<<<(unsigned)count * (unsigned)bpi, EMIT_THREADS, 0, s>>>(imgs, hdrs, yuv, alpha_arena, out, first, bpi, pair_begin, pair_end);
 }
 
-extern "C" void vp8k_emit_scaled(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint8_t* yuv, uint8_t* out,
-                                 int first, int count, int max_items) {
+extern "C" void vp8k_emit_scaled(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint8_t* yuv, const uint8_t* alpha_arena,
+                                 uint8_t* out, int first, int count, int max_items) {
   const int bpi = (max_items + EMIT_THREADS - 1) / EMIT_THREADS;
-  k_emit_scaled<<<(unsigned)count * (unsigned)bpi, EMIT_THREADS, 0, s>>>(imgs, hdrs, yuv, out, first, bpi);
+  k_emit_scaled<<<(unsigned)count * (unsigned)bpi, EMIT_THREADS, 0, s>>>(imgs, hdrs, yuv, alpha_arena, out, first, bpi);
 }
 
 // ---------------------------------------------------------------------------------------------------------

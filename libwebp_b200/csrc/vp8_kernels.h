@@ -39,8 +39,8 @@ void vp8k_emit(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const 
 
 // Images with options.use_scaling (ImgDesc::dst_w != 0; vp8k_emit skips them). max_items = largest per-image work-item
 // count: dst_w for the RGB family, dst_w + 2 * ((dst_w + 1) / 2) (+ dst_w for MODE_YUVA) for the planar modes.
-void vp8k_emit_scaled(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint8_t* yuv, uint8_t* out,
-                      int first, int count, int max_items);
+void vp8k_emit_scaled(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint8_t* yuv, const uint8_t* alpha_arena,
+                      uint8_t* out, int first, int count, int max_items);
 
 // ALPH chunks (vp8l_alpha_core.h): `aimgs` = the `count` image indices that carry one, `plans` = where each of them
 // works (device addresses). Header pass first; the host then sizes tables / planes from the AlphaHdr it

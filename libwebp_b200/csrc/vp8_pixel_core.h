@@ -779,8 +779,17 @@ VP8_UNROLL
 #define RS_MULT_FIX(x, y) ((((uint64_t)(x)) * (uint64_t)(y) + (RS_ONE >> 1)) >> 32)
 #define RS_MULT_FIX_FLOOR(x, y) ((((uint64_t)(x)) * (uint64_t)(y)) >> 32)
 
+// WebPMultRow_C (alpha_processing.c:160-175): x * a / 255 (inverse = 0) or x * 255 / a (inverse = 1) in 24-bit fixed point.
+VP8_PFN uint32_t mult_by_alpha(uint32_t x, uint32_t a, int inverse) {
+  if (a == 255) return x;
+  if (a == 0) return 0;
+  const uint32_t scale = inverse ? (255u << 24) / a : a * ((1u << 24) / 255u);
+  return ((x * scale + (1u << 23)) >> 24) & 0xffu;
+}
+
 struct Rescaler {   // one plane of one image, as seen by one output column (WebPRescalerInit, rescaler_utils.c:24-84)
   const uint8_t* src; int src_stride;
+  const uint8_t* asrc; int asrc_stride;   // MODE_YUVA: the luma is multiplied by this alpha plane on its way in (io_dec.c:258-265)
   int src_w, src_h, dst_w, dst_h;
   int x_expand, y_expand;
   int x_add, x_sub, y_add, y_sub, y_accum;
@@ -790,7 +799,7 @@ struct Rescaler {   // one plane of one image, as seen by one output column (Web
 };
 
 VP8_PFN void rescaler_init(Rescaler& r, const uint8_t* src, int src_stride, int src_w, int src_h, int dst_w, int dst_h) {
-  r.src = src; r.src_stride = src_stride;
+  r.src = src; r.src_stride = src_stride; r.asrc = 0; r.asrc_stride = 0;
   r.src_w = src_w; r.src_h = src_h; r.dst_w = dst_w; r.dst_h = dst_h;
   r.x_expand = src_w < dst_w; r.y_expand = src_h < dst_h;
   r.x_add = r.x_expand ? dst_w - 1 : src_w;
@@ -812,7 +821,8 @@ VP8_PFN void rescaler_init(Rescaler& r, const uint8_t* src, int src_stride, int 
 
 // frow[x] of WebPRescalerImportRowShrink_C (rescaler.c:62-95) for one source row: output k consumes the inputs
 // n(k-1) .. n(k)-1 with n(k) = ceil((k+1) * x_add / x_sub), starting from the fraction the previous output left over.
-VP8_PFN uint32_t import_row_shrink(const Rescaler& r, const uint8_t* row, int x) {
+#define RS_PX(i) (arow ? mult_by_alpha(row[i], arow[i], 0) : (uint32_t)row[i])
+VP8_PFN uint32_t import_row_shrink(const Rescaler& r, const uint8_t* row, const uint8_t* arow, int x) {
   const int64_t t1 = (int64_t)(x + 1) * r.x_add;
   const int n1 = (int)((t1 + r.x_sub - 1) / r.x_sub);
   const int acc1 = (int)(t1 - (int64_t)n1 * r.x_sub);          // accum after this output (<= 0)
@@ -822,22 +832,22 @@ VP8_PFN uint32_t import_row_shrink(const Rescaler& r, const uint8_t* row, int x)
     const int64_t t0 = (int64_t)x * r.x_add;
     n0 = (int)((t0 + r.x_sub - 1) / r.x_sub);
     const int acc0 = (int)(t0 - (int64_t)n0 * r.x_sub);
-    const uint32_t frac0 = (uint32_t)row[n0 - 1] * (uint32_t)(-acc0);
+    const uint32_t frac0 = RS_PX(n0 - 1) * (uint32_t)(-acc0);
     sum = (uint32_t)(int)RS_MULT_FIX(frac0, r.fx_scale);
   }
-  for (int i = n0; i < n1; ++i) sum += row[i];
-  const uint32_t frac = (uint32_t)row[n1 - 1] * (uint32_t)(-acc1);
+  for (int i = n0; i < n1; ++i) sum += RS_PX(i);
+  const uint32_t frac = RS_PX(n1 - 1) * (uint32_t)(-acc1);
   return sum * (uint32_t)r.x_sub - frac;
 }
 
 // frow[x] of WebPRescalerImportRowExpand_C (rescaler.c:29-60): bilinear, the input position advanced a(k) times before
 // output k, a(k) the smallest a >= 0 with x_add - k * x_sub + a * x_add >= 0.
-VP8_PFN uint32_t import_row_expand(const Rescaler& r, const uint8_t* row, int x) {
+VP8_PFN uint32_t import_row_expand(const Rescaler& r, const uint8_t* row, const uint8_t* arow, int x) {
   const int64_t d = (int64_t)x * r.x_sub - r.x_add;
   const int a = (d > 0) ? (int)((d + r.x_add - 1) / r.x_add) : 0;
   const int accum = (int)((int64_t)r.x_add - (int64_t)x * r.x_sub + (int64_t)a * r.x_add);
-  const uint32_t left = row[a];
-  const uint32_t right = (r.src_w > 1) ? row[a + 1 < r.src_w ? a + 1 : r.src_w - 1] : left;
+  const uint32_t left = RS_PX(a);
+  const uint32_t right = (r.src_w > 1) ? RS_PX(a + 1 < r.src_w ? a + 1 : r.src_w - 1) : left;
   return right * (uint32_t)r.x_add + (left - right) * (uint32_t)accum;
 }
 
@@ -846,8 +856,9 @@ VP8_PFN uint32_t import_row_expand(const Rescaler& r, const uint8_t* row, int x)
 VP8_PFN int rescaler_next(Rescaler& r, int x) {
   while (r.y_accum > 0 && r.src_y < r.src_h) {
     const uint8_t* row = r.src + (size_t)r.src_y * r.src_stride;
+    const uint8_t* arow = r.asrc ? r.asrc + (size_t)r.src_y * r.asrc_stride : 0;
     if (r.y_expand) r.irow = r.frow;   // the two work rows swap roles
-    r.frow = r.x_expand ? import_row_expand(r, row, x) : import_row_shrink(r, row, x);
+    r.frow = r.x_expand ? import_row_expand(r, row, arow, x) : import_row_shrink(r, row, arow, x);
     if (!r.y_expand) r.irow += r.frow;
     ++r.src_y;
     r.y_accum -= r.y_sub;
@@ -884,19 +895,19 @@ VP8_PFN int rescaler_next(Rescaler& r, int x) {
   return v > 255 ? 255 : v;
 }
 
-// One pixel of any RGB-family colourspace at column x of output row `orow` (a = 0xff: scaling is only offered for
-// opaque images).
-VP8_PFN void store_rgb_pixel(int csp, int y, int u, int v, uint8_t* orow, int x) {
+// One pixel of any RGB-family colourspace at column x of output row `orow`; a = its alpha (0xff for opaque images; the
+// premultiplied modes scale the colour by it like ExportAlpha + WebPApplyAlphaMultiply, io_dec.c:414-450).
+VP8_PFN void store_rgb_pixel(int csp, int y, int u, int v, int a, uint8_t* orow, int x) {
   int r, g, b;
   yuv_to_rgb(y, u, v, &r, &g, &b);
   if (csp == 0 || csp == 2) {
     uint8_t* o = orow + 3 * x;
     if (csp == 0) { o[0] = (uint8_t)r; o[1] = (uint8_t)g; o[2] = (uint8_t)b; } else { o[0] = (uint8_t)b; o[1] = (uint8_t)g; o[2] = (uint8_t)r; }
   } else if (csp == 5 || csp == 6 || csp == 10) {
-    const uint32_t p2 = pack_pixel2(csp, r, g, b, 0xff);
+    const uint32_t p2 = pack_pixel2(csp, r, g, b, a);
     orow[2 * x] = (uint8_t)p2; orow[2 * x + 1] = (uint8_t)(p2 >> 8);
   } else {
-    const uint32_t p4 = pack_pixel4(csp, r, g, b, 0xff);
+    const uint32_t p4 = pack_pixel4(csp, r, g, b, a);
     uint8_t* o = orow + 4 * x;
     o[0] = (uint8_t)p4; o[1] = (uint8_t)(p4 >> 8); o[2] = (uint8_t)(p4 >> 16); o[3] = (uint8_t)(p4 >> 24);
   }
@@ -906,34 +917,54 @@ VP8_PFN void store_rgb_pixel(int csp, int y, int u, int v, uint8_t* orow, int x)
 // then converted). MODE_YUV / MODE_YUVA: t in [0, dst_w) = a Y column, then (dst_w+1)/2 U columns, as many V columns,
 // and for MODE_YUVA dst_w columns of the (opaque) alpha plane. yplane/uplane/vplane = the window's origin.
 VP8_PFN void emit_scaled_column(const ImgDesc& im, const uint8_t* yplane, const uint8_t* uplane, const uint8_t* vplane,
-                                uint8_t* out, int t) {
+                                const uint8_t* alpha /* window origin inside the frame-wide plane, or NULL */, uint8_t* out, int t) {
   const int sw = im.out_w, sh = im.out_h, dw = im.dst_w, dh = im.dst_h;
   const int ys = 16 * im.mb_w, uvs = 8 * im.mb_w;
   const int uv_sw = (sw + 1) >> 1, uv_sh = (sh + 1) >> 1;
   const int flip = (im.flags & VP8B_FLAG_FLIP) != 0;
   if (im.csp == 11 || im.csp == 12) {
     const int uv_dw = (dw + 1) >> 1, uv_dh = (dh + 1) >> 1;
+    uint8_t* uplane_out = out + (size_t)im.out_stride * dh;
+    uint8_t* aplane_out = uplane_out + 2 * (size_t)uv_dw * uv_dh;
     Rescaler r;
     uint8_t* dst; int stride, rows, x;
-    if (t < dw) { rescaler_init(r, yplane, ys, sw, sh, dw, dh); dst = out; stride = im.out_stride; rows = dh; x = t; }
-    else if (t < dw + uv_dw) { rescaler_init(r, uplane, uvs, uv_sw, uv_sh, uv_dw, uv_dh); dst = out + (size_t)im.out_stride * dh; stride = uv_dw; rows = uv_dh; x = t - dw; }
-    else if (t < dw + 2 * uv_dw) { rescaler_init(r, vplane, uvs, uv_sw, uv_sh, uv_dw, uv_dh); dst = out + (size_t)im.out_stride * dh + (size_t)uv_dw * uv_dh; stride = uv_dw; rows = uv_dh; x = t - dw - uv_dw; }
-    else if (im.csp == 12 && t < 2 * dw + 2 * uv_dw) {
-      uint8_t* a = out + (size_t)im.out_stride * dh + 2 * (size_t)uv_dw * uv_dh;
-      for (int k = 0; k < dh; ++k) a[(size_t)k * dw + (t - dw - 2 * uv_dw)] = 0xff;   // FillAlphaPlane, io_dec.c:283-288
+    if (t < dw) {   // a luma column; MODE_YUVA with an alpha plane: multiplied by alpha on the way in, divided by the
+                    // rescaled alpha on the way out (EmitRescaledYUV / EmitRescaledAlphaYUV, io_dec.c:252-300)
+      rescaler_init(r, yplane, ys, sw, sh, dw, dh);
+      if (im.csp == 12 && alpha != 0) {
+        Rescaler ra;
+        rescaler_init(ra, alpha, im.width, sw, sh, dw, dh);
+        r.asrc = alpha; r.asrc_stride = im.width;
+        for (int k = 0; k < dh; ++k) {
+          const uint32_t y = (uint32_t)rescaler_next(r, t), a = (uint32_t)rescaler_next(ra, t);
+          const int kd = flip ? dh - 1 - k : k;
+          out[(size_t)kd * im.out_stride + t] = (uint8_t)mult_by_alpha(y, a, 1);
+          aplane_out[(size_t)kd * dw + t] = (uint8_t)a;
+        }
+        return;
+      }
+      dst = out; stride = im.out_stride; rows = dh; x = t;
+    }
+    else if (t < dw + uv_dw) { rescaler_init(r, uplane, uvs, uv_sw, uv_sh, uv_dw, uv_dh); dst = uplane_out; stride = uv_dw; rows = uv_dh; x = t - dw; }
+    else if (t < dw + 2 * uv_dw) { rescaler_init(r, vplane, uvs, uv_sw, uv_sh, uv_dw, uv_dh); dst = uplane_out + (size_t)uv_dw * uv_dh; stride = uv_dw; rows = uv_dh; x = t - dw - uv_dw; }
+    else if (im.csp == 12 && alpha == 0 && t < 2 * dw + 2 * uv_dw) {
+      for (int k = 0; k < dh; ++k) aplane_out[(size_t)k * dw + (t - dw - 2 * uv_dw)] = 0xff;   // FillAlphaPlane, io_dec.c:283-288
       return;
     } else return;
     for (int k = 0; k < rows; ++k) dst[(size_t)(flip ? rows - 1 - k : k) * stride + x] = (uint8_t)rescaler_next(r, x);
     return;
   }
   if (t >= dw) return;
-  Rescaler ry, ru, rv;
+  const int with_alpha = alpha != 0 && (im.csp == 1 || im.csp == 3 || im.csp == 4 || im.csp == 5 || (im.csp >= 7 && im.csp <= 10));
+  Rescaler ry, ru, rv, ra;
   rescaler_init(ry, yplane, ys, sw, sh, dw, dh);
   rescaler_init(ru, uplane, uvs, uv_sw, uv_sh, dw, dh);
   rescaler_init(rv, vplane, uvs, uv_sw, uv_sh, dw, dh);
+  rescaler_init(ra, with_alpha ? alpha : yplane, with_alpha ? im.width : ys, sw, sh, dw, dh);
   for (int k = 0; k < dh; ++k) {
     const int y = rescaler_next(ry, t), u = rescaler_next(ru, t), v = rescaler_next(rv, t);
-    store_rgb_pixel(im.csp, y, u, v, out + (size_t)(flip ? dh - 1 - k : k) * im.out_stride, t);
+    const int a = with_alpha ? rescaler_next(ra, t) : 0xff;
+    store_rgb_pixel(im.csp, y, u, v, a, out + (size_t)(flip ? dh - 1 - k : k) * im.out_stride, t);
   }
 }
 

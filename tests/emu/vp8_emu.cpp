@@ -271,11 +271,10 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
   const uint8_t* wv = vp + (size_t)(im.crop_y >> 1) * (8 * mb_w) + (im.crop_x >> 1);
   if (alpha) alpha += (size_t)im.crop_y * im.width + im.crop_x;
   if (im.dst_w != 0) {
-    if (alpha) return VP8_STATUS_UNSUPPORTED_FEATURE;
     const int dw = im.dst_w, uvdw = (dw + 1) / 2;
     const int items = (csp == MODE_YUV || csp == MODE_YUVA) ? dw + 2 * uvdw + (csp == MODE_YUVA ? dw : 0) : dw;
     if (csp == MODE_YUV || csp == MODE_YUVA) im.out_stride = dw;
-    for (int t = 0; t < items; ++t) emit_scaled_column(im, wy, wu, wv, out, t);
+    for (int t = 0; t < items; ++t) emit_scaled_column(im, wy, wu, wv, alpha, out, t);
     return VP8_STATUS_OK;
   }
   if (csp == MODE_YUV || csp == MODE_YUVA) {

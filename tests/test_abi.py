@@ -87,13 +87,6 @@ def test_host_side_failures_need_no_gpu(product, port, manifest):
     L.WebPInitDecoderConfigInternal(C.byref(cfg), 0x0209)
     cfg.options.use_scaling = 1            # a 0 x 0 scaling request is an invalid parameter (buffer_dec.c:197-205)
     assert L.WebPDecode(d, len(d), C.byref(cfg)) == product.VP8_STATUS_INVALID_PARAM
-    import glob
-    import os
-    alpha = open(sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "alpha_*.webp")))[0], "rb").read()
-    L.WebPInitDecoderConfigInternal(C.byref(cfg), 0x0209)
-    cfg.options.use_scaling = 1            # rescaled alpha is not on the device: refused, never decoded on the host
-    cfg.options.scaled_width, cfg.options.scaled_height = 8, 8
-    assert L.WebPDecode(alpha, len(alpha), C.byref(cfg)) == product.VP8_STATUS_UNSUPPORTED_FEATURE
     L.WebPInitDecoderConfigInternal(C.byref(cfg), 0x0209)
     cfg.options.use_cropping = 1           # an empty crop window is an invalid parameter (buffer_dec.c:184-195)
     assert L.WebPDecode(d, len(d), C.byref(cfg)) == product.VP8_STATUS_INVALID_PARAM

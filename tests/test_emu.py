@@ -166,7 +166,7 @@ def test_emu_crop_and_flip_match_reference(ref, manifest, amanifest):
         del s_emu
 
 
-def test_emu_scaling_matches_reference(ref, manifest):
+def test_emu_scaling_matches_reference(ref, manifest, amanifest):
     """options.use_scaling (io_dec.c:239-556, src/dsp/rescaler.c): up and down, one axis each way, ratio-preserving
     requests, crop + scale, planar and packed colourspaces, flip; the loop filter is dropped for large downscaling ratios
     exactly like WebPIoInitFromOptions does. The device code's host build against the reference, byte for byte."""
@@ -175,7 +175,8 @@ def test_emu_scaling_matches_reference(ref, manifest):
     L.emu_decode_scaled.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_int, C.c_int]
     rng = np.random.default_rng(21)
-    for e in manifest:
+    for e in list(manifest) + list(amanifest):
+        has_alpha = bool(e["features"].get("has_alpha"))
         W, H = e["features"]["width"], e["features"]["height"]
         for it in range(6):
             crop = None
@@ -186,7 +187,9 @@ def test_emu_scaling_matches_reference(ref, manifest):
             req = [(max(1, w // 2), max(1, h // 3)), (w * 2 + 1, h + 7), (max(1, w - 1), h * 3), (0, max(1, h // 2)), (w + 5, 0),
                    (int(rng.integers(1, 2 * w + 2)), int(rng.integers(1, 2 * h + 2)))][it]
             flip = int(rng.integers(0, 2))
-            for csp in (1, 0, 11, 6, 12, 4):
+            # files with an ALPH chunk: the alpha plane is rescaled too, premultiplied modes multiply after scaling, MODE_YUVA
+            # multiplies the luma before and divides it after (io_dec.c:252-300, 414-470)
+            for csp in ((1, 7, 12, 10, 5, 9, 0) if has_alpha else (1, 0, 11, 6, 12, 4)):
                 s_ref, (sw, sh), want = ref.decode_scaled(e["data"], csp, 8 if flip else 0, crop, req)
                 assert s_ref == 0, (e["file"], req, crop, s_ref)
                 n = (sw * sh + 2 * ((sw + 1) // 2) * ((sh + 1) // 2) + (sw * sh if csp == 12 else 0)) if csp in (11, 12) else sw * sh * ref.BPP[csp]

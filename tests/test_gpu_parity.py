@@ -349,7 +349,7 @@ def test_row_bands(ref):
 def test_scaling(W, ref, manifest, amanifest):
     """options.use_scaling through the C ABI: the rescaler runs on the device (one thread per output column), output
     identical to the reference's for up- and downscaling, ratio-preserving requests, crop + scale, flip, packed and
-    planar colourspaces; impossible requests are refused with the reference's status, scaled alpha is not offered."""
+    planar colourspaces; impossible requests are refused with the reference's status; files with an ALPH chunk have their alpha rescaled too."""
     rng = np.random.default_rng(22)
     for e in manifest:
         Wd, Hd = e["features"]["width"], e["features"]["height"]
@@ -372,5 +372,11 @@ def test_scaling(W, ref, manifest, amanifest):
         s_ref, _, _ = ref.decode_scaled(data, W.MODE_RGBA, 0, None, req)
         st, _ = W.WebPDecode(data, W.MODE_RGBA, scaled=req)
         assert st == s_ref != 0, (req, st, s_ref)
-    st, _ = W.WebPDecode(amanifest[0]["data"], W.MODE_RGBA, scaled=(10, 10))
-    assert st == 4   # VP8_STATUS_UNSUPPORTED_FEATURE: refused, never decoded differently
+    for e in amanifest:   # scaled alpha: plain, premultiplied, 4-bit and planar
+        w, h = e["features"]["width"], e["features"]["height"]
+        for req in ((max(1, w // 2), max(1, h // 2)), (w + 9, 2 * h), (0, max(1, h - 3))):
+            for csp in (W.MODE_RGBA, W.MODE_rgbA, W.MODE_YUVA, W.MODE_rgbA_4444, W.MODE_Argb):
+                s_ref, (sw, sh), want = ref.decode_scaled(e["data"], csp, 0, None, req)
+                st, out = W.WebPDecode(e["data"], csp, scaled=req)
+                assert st == s_ref == 0, (e["file"], req, csp, st, s_ref, W.last_error())
+                assert np.array_equal(out.reshape(-1)[:want.size], want), (e["file"], req, csp, (sw, sh))
