@@ -164,7 +164,8 @@ def scaled_dims(w, h, scaled):
     return sw, sh
 
 
-def _new_config(csp, bypass_filtering, no_fancy_upsampling, dithering_strength=0, crop=None, flip=False, scaled=None):
+def _new_config(csp, bypass_filtering, no_fancy_upsampling, dithering_strength=0, crop=None, flip=False, scaled=None,
+                alpha_dithering_strength=0):
     cfg = WebPDecoderConfig()
     if not lib().WebPInitDecoderConfigInternal(C.byref(cfg), WEBP_DECODER_ABI_VERSION):
         raise RuntimeError("WebPInitDecoderConfig failed (ABI mismatch)")
@@ -172,6 +173,7 @@ def _new_config(csp, bypass_filtering, no_fancy_upsampling, dithering_strength=0
     cfg.options.bypass_filtering = int(bool(bypass_filtering))
     cfg.options.no_fancy_upsampling = int(bool(no_fancy_upsampling))
     cfg.options.dithering_strength = dithering_strength
+    cfg.options.alpha_dithering_strength = alpha_dithering_strength
     cfg.options.flip = int(bool(flip))
     if crop is not None:
         cfg.options.use_cropping = 1
@@ -207,12 +209,12 @@ def out_bytes(csp, w, h, stride=None):
 
 
 def WebPDecode(data, csp=MODE_RGBA, bypass_filtering=False, no_fancy_upsampling=False, stride=None, external=True,
-               dithering_strength=0, crop=None, flip=False, scaled=None):
+               dithering_strength=0, crop=None, flip=False, scaled=None, alpha_dithering_strength=0):
     """One image through the C-ABI WebPDecode (a GPU batch of one). Returns (status, ndarray or None):
     (h, stride) bytes for RGB-family modes, flat y|u|v for MODE_YUV. crop = (left, top, width, height);
     scaled = (width, height) turns options.use_scaling on (0 = keep the ratio)."""
     L = lib()
-    cfg = _new_config(csp, bypass_filtering, no_fancy_upsampling, dithering_strength, crop, flip, scaled)
+    cfg = _new_config(csp, bypass_filtering, no_fancy_upsampling, dithering_strength, crop, flip, scaled, alpha_dithering_strength)
     st, f = WebPGetFeatures(data)
     if st != VP8_STATUS_OK:
         return L.WebPDecode(data, len(data), C.byref(cfg)), None

@@ -240,6 +240,8 @@ struct WebPBatch {
   std::vector<int> ids;            // token-parse launch lists
   std::vector<int> statuses;       // host copy of FrameHdr::status
   Owned d_in, d_imgs, d_hdrs, d_ids, d_mbinfo, d_coeffs, d_yuv, d_out;
+  Owned d_dither; // options.dithering_strength: 128 offsets per macroblock of a wave (allocated when an item asks for it)
+  bool any_dither = false;
   Owned d_band;   // row bands: TokResume[m] | uint16 top contexts [m][max_mb_w] | unfiltered top pixels [m][32 * max_mb_w]
   // images with an ALPH chunk
   std::vector<int> aimgs;              // their image indices
@@ -271,7 +273,10 @@ static VP8StatusCode plan_item(WebPBatchItem* it, const WebPBatchOptions& opt, V
   if (st != VP8_STATUS_OK) return st;
   if (c->has_animation) return VP8_STATUS_UNSUPPORTED_FEATURE;             // webp_dec.c:427-429
   if (c->is_lossless) return VP8_STATUS_UNSUPPORTED_FEATURE;               // lossless: not on this path
-  if (c->has_alph_chunk && cfg->options.alpha_dithering_strength > 0) return VP8_STATUS_UNSUPPORTED_FEATURE;   // alpha de-banding
+  // alpha de-banding (WebPDequantizeLevels) only ever runs on planes whose levels were quantised by the encoder
+  // (ALPH header: pre-processing = 1, alpha_dec.c:71,200-210); dwebp asks for it by default, so refuse exactly those
+  if (c->has_alph_chunk && cfg->options.alpha_dithering_strength > 0 && c->alpha_size > 0 &&
+      ((it->data[c->alpha_offset] >> 4) & 3) == 1) return VP8_STATUS_UNSUPPORTED_FEATURE;
   if (c->part0_size > c->frame_size - 10) return VP8_STATUS_NOT_ENOUGH_DATA;   // vp8_dec.c:345-348
   const WebPDecoderOptions* o = &cfg->options;
   const int csp = cfg->output.colorspace;
@@ -375,6 +380,7 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
     }
     const int ds = cfg->options.dithering_strength;
     d.dither_f = (uint8_t)(ds < 0 ? 0 : ds > 100 ? 255 : ds * 255 / 100);
+    if (d.dither_f != 0) b->any_dither = true;
     d.num_parts = (uint8_t)vp8b_prescan_partitions(b->items[i].data + c.frame_offset + 10, c.part0_size);
     d.alpha_plane = VP8B_NO_ALPHA;
     if (c.has_alph_chunk) {
@@ -469,6 +475,7 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
   }
   if (!own_alloc(ctx, b->d_mbinfo, max_wave_mbs * 16) || !own_alloc(ctx, b->d_coeffs, max_wave_mbs * 2 * VP8B_COEFFS_PER_MB) ||
       !own_alloc(ctx, b->d_yuv, max_wave_mbs * 384)) return false;
+  if (b->any_dither && !own_alloc(ctx, b->d_dither, max_wave_mbs * 128 + 256)) return false;
   if (!own_alloc(ctx, b->d_band, align_up((size_t)m * sizeof(TokResume), 256) + align_up((size_t)m * 2 * b->max_mb_w, 256) +
                                      (size_t)m * 32 * b->max_mb_w + 256)) return false;
   // ---- uploads
@@ -488,7 +495,7 @@ static void batch_release(WebPBatch* b) {
   if (b->ctx != nullptr) {
     DeviceCtx* c = b->ctx;
     own_free(c, b->d_in); own_free(c, b->d_imgs); own_free(c, b->d_hdrs); own_free(c, b->d_ids);
-    own_free(c, b->d_mbinfo); own_free(c, b->d_coeffs); own_free(c, b->d_yuv); own_free(c, b->d_out); own_free(c, b->d_band);
+    own_free(c, b->d_mbinfo); own_free(c, b->d_coeffs); own_free(c, b->d_yuv); own_free(c, b->d_out); own_free(c, b->d_band); own_free(c, b->d_dither);
     own_free(c, b->d_aimgs); own_free(c, b->d_aplans); own_free(c, b->d_ahdrs); own_free(c, b->d_awork); own_free(c, b->d_awork2); own_free(c, b->d_alpha);
     for (auto e : b->ev) if (e) cudaEventDestroy(e);
   }
@@ -759,7 +766,7 @@ static bool batch_decode(WebPBatch* b, bool download) {
     {
       static int env_bands = -1;
       if (env_bands < 0) { const char* e = getenv("WEBP_B200_BANDS"); env_bands = e ? atoi(e) : 1; }
-      bool ok = env_bands > 1 && b->aimgs.empty() && w.ids_cnt[0] == w.count && vp8k_tokens_take_bands(w.count, 1) && w.max_mb_h >= 16;
+      bool ok = env_bands > 1 && !b->any_dither && b->aimgs.empty() && w.ids_cnt[0] == w.count && vp8k_tokens_take_bands(w.count, 1) && w.max_mb_h >= 16;
       for (int k = w.first; ok && k < w.first + w.count; ++k) {
         const ImgDesc& d = b->imgs[k];
         const bool pairs = !(d.flags & VP8B_FLAG_NO_FANCY) && kBpp[d.csp] == 4 && d.csp != MODE_YUVA;
@@ -795,7 +802,7 @@ static bool batch_decode(WebPBatch* b, bool download) {
         const int q0 = ev_mark(b, ps); if (q0 < 0) return false;
         vp8k_reconstruct(ps, imgs, hdrs, mbinfo, coeffs, yuv, w.first, w.count, w.max_mb_w, w.max_mb_h, r0, r1, band_ctx);
         const int q1 = ev_mark(b, ps); if (q1 < 0) return false;
-        vp8k_loop_filter(ps, imgs, hdrs, mbinfo, yuv, w.first, w.count, w.max_mb_h, r0, r1);
+        vp8k_loop_filter(ps, imgs, hdrs, mbinfo, yuv, w.first, w.count, w.max_mb_h, r0, r1, nullptr);
         const int q2 = ev_mark(b, ps); if (q2 < 0) return false;
         const int band_pairs = (p1 == 0x7fffffff ? (16 * w.max_mb_h) / 2 + 1 : p1) - p0;
         vp8k_emit(ps, imgs, hdrs, yuv, (const uint8_t*)b->d_alpha.p, (uint8_t*)b->d_out.p, w.first, w.count,
@@ -815,6 +822,7 @@ static bool batch_decode(WebPBatch* b, bool download) {
       if (ps != s) CU_TRY(cudaStreamWaitEvent(s, b->ev[last_px], 0), "cudaStreamWaitEvent");   // the scratch arrays are free again
       continue;
     }
+    if (b->any_dither) { vp8k_dither_plan(s, imgs, hdrs, mbinfo, (int8_t*)b->d_dither.p, w.first, w.count); ++launches; }
     MARK(e2);
     b->spans.push_back({ ST_MODES, e0, e1 });
     b->spans.push_back({ ST_TOKENS, e1, e2 });
@@ -829,7 +837,7 @@ static bool batch_decode(WebPBatch* b, bool download) {
       const int cnt = c1 - c0;
       vp8k_reconstruct(s, imgs, hdrs, mbinfo, coeffs, yuv, c0, cnt, w.max_mb_w, w.max_mb_h, 0, 0x7fffffff, (uint8_t*)b->d_band.p);
       MARK(e3);
-      vp8k_loop_filter(s, imgs, hdrs, mbinfo, yuv, c0, cnt, w.max_mb_h, 0, 0x7fffffff);
+      vp8k_loop_filter(s, imgs, hdrs, mbinfo, yuv, c0, cnt, w.max_mb_h, 0, 0x7fffffff, (const int8_t*)b->d_dither.p);
       MARK(e4);
       vp8k_emit(s, imgs, hdrs, yuv, (const uint8_t*)b->d_alpha.p, (uint8_t*)b->d_out.p, c0, cnt, w.max_units, 0, 0x7fffffff);
       if (w.max_scaled_items > 0) { vp8k_emit_scaled(s, imgs, hdrs, yuv, (const uint8_t*)b->d_alpha.p, (uint8_t*)b->d_out.p, c0, cnt, w.max_scaled_items); ++launches; }

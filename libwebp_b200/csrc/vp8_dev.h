@@ -70,6 +70,7 @@ typedef struct FrameHdr {
   uint32_t part_off[VP8B_MAX_PARTS];   // token partitions, relative to the frame tag
   uint32_t part_size[VP8B_MAX_PARTS];
   uint8_t prob[4 * 8 * 3 * 11]; // [type][band][ctx][node]
+  uint8_t dither[4];            // per segment: amplitude of the random chroma dithering (VP8InitDithering, frame_dec.c:328-349), 0 = none
   int32_t rows;                 // macroblock rows that get decoded: all of them, or down to the bottom of the crop
                                 // window plus the filter's reach (VP8EnterCritical, frame_dec.c:571-596)
 } FrameHdr;
@@ -79,12 +80,14 @@ typedef struct FrameHdr {
 //   z    : non_zero_y, 2 bits per luma block, block 0 in the top bits (reference: vp8i_dec.h:150-158)
 //   w    : bits 0-15 non_zero_uv | bit16 is_i4x4 | bits17-18 uvmode | bit19 skip | bits20-21 segment
 //          | bit22 has_y2 (i16 with a non-empty Y2 block) | bit23 filter-inner (set by the reconstruction)
+//          | bit24 dithered (set by the dither plan)
 #define MBW_I4X4 (1u << 16)
 #define MBW_UVMODE_SHIFT 17
 #define MBW_SKIP (1u << 19)
 #define MBW_SEG_SHIFT 20
 #define MBW_HAS_Y2 (1u << 22)
 #define MBW_INNER (1u << 23)
+#define MBW_DITHER (1u << 24)   // chroma gets dithered; its 128 offsets sit in the dither plane (dither_plan_image)
 
 // intra modes (RFC 6386 numbering as used by the reference, src/dec/common_dec.h:18-40)
 enum { M_DC = 0, M_TM = 1, M_VE = 2, M_HE = 3, M_RD = 4, M_VR = 5, M_LD = 6, M_VL = 7, M_HD = 8, M_HU = 9 };

@@ -418,12 +418,15 @@ __global__ void __launch_bounds__(32 * RECON_WARPS) k_reconstruct(const ImgDesc*
 
 __global__ void __launch_bounds__(32 * FILTER_WARPS) k_loop_filter(const ImgDesc* __restrict__ imgs, const FrameHdr* __restrict__ hdrs,
                                                                    const uint32_t* __restrict__ mbinfo, uint8_t* yuv, int first,
-                                                                   int row_begin, int row_end) {
+                                                                   int row_begin, int row_end, const int8_t* __restrict__ dither_plane) {
   __shared__ __align__(16) FilterWs wss[FILTER_WARPS];
   __shared__ uint8_t fstr[32];
   const int img = first + blockIdx.x;
   const FrameHdr* h = &hdrs[img];
-  if (h->status != VP8B_OK || h->filter_type == 0) return;
+  // options.dithering_strength: the planned offsets (dither_plan_image) go onto a macroblock's chroma once its own row
+  // has finished with it, i.e. after the macroblock to its right has been filtered, and before the row below may touch it
+  const int dithering = dither_plane != nullptr && (h->dither[0] | h->dither[1] | h->dither[2] | h->dither[3]) != 0;
+  if (h->status != VP8B_OK || (h->filter_type == 0 && !dithering)) return;
   const ImgDesc im = imgs[img];
   const int mb_w = im.mb_w, mb_h = h->rows;
   const int filter_type = h->filter_type;
@@ -456,12 +459,30 @@ __global__ void __launch_bounds__(32 * FILTER_WARPS) k_loop_filter(const ImgDesc
       }
       const uint32_t w = mbi[4 * ((size_t)my * mb_w + mx) + 3];
       const uint8_t* fs = fstr + 8 * ((w >> MBW_SEG_SHIFT) & 3) + ((w & MBW_I4X4) ? 4 : 0);
-      filter_macroblock(ws, mx, my, mb_w, filter_type, fs, (w & MBW_INNER) != 0, yp, up, vp);
+      if (filter_type != 0) filter_macroblock(ws, mx, my, mb_w, filter_type, fs, (w & MBW_INNER) != 0, yp, up, vp);
+      if (dithering) {
+        const int8_t* dp = dither_plane + (size_t)im.mb_base * 128;
+        __syncwarp();
+        if (mx > 0 && (mbi[4 * ((size_t)my * mb_w + mx - 1) + 3] & MBW_DITHER)) dither_macroblock(mx - 1, my, mb_w, dp, up, vp);
+        if (mx == mb_w - 1 && (w & MBW_DITHER)) dither_macroblock(mx, my, mb_w, dp, up, vp);
+      }
       __syncwarp();
       __threadfence_block();
       if ((threadIdx.x & 31) == 0) row_done[ly] = mx + 1;
     }
   }
+}
+
+// options.dithering_strength: one thread per image lays the random offsets down (vp8_pixel_core.h:dither_plan_image).
+__global__ void __launch_bounds__(32) k_dither_plan(const ImgDesc* __restrict__ imgs, const FrameHdr* __restrict__ hdrs,
+                                                    uint32_t* mbinfo, int8_t* dither_plane, int first, int count) {
+  __shared__ uint32_t tabs[32][55];
+  const int k = blockIdx.x * 32 + threadIdx.x;
+  if (k >= count) return;
+  const int img = first + k;
+  if (hdrs[img].status != VP8B_OK) return;
+  const ImgDesc im = imgs[img];
+  dither_plan_image(im, &hdrs[img], mbinfo + 4 * (size_t)im.mb_base, dither_plane + (size_t)im.mb_base * 128, tabs[threadIdx.x]);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -687,8 +708,13 @@ extern "C" void vp8k_reconstruct(cudaStream_t s, const ImgDesc* imgs, const Fram
 }
 
 extern "C" void vp8k_loop_filter(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint32_t* mbinfo, uint8_t* yuv,
-                                 int first, int count, int max_mb_h, int row_begin, int row_end) {
-  k_loop_filter<<<count, 32 * FILTER_WARPS, (size_t)max_mb_h * 4 + 16, s>>>(imgs, hdrs, mbinfo, yuv, first, row_begin, row_end);
+                                 int first, int count, int max_mb_h, int row_begin, int row_end, const int8_t* dither_plane) {
+  k_loop_filter<<<count, 32 * FILTER_WARPS, (size_t)max_mb_h * 4 + 16, s>>>(imgs, hdrs, mbinfo, yuv, first, row_begin, row_end, dither_plane);
+}
+
+extern "C" void vp8k_dither_plan(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, uint32_t* mbinfo, int8_t* dither_plane,
+                                 int first, int count) {
+  k_dither_plan<<<(count + 31) / 32, 32, 0, s>>>(imgs, hdrs, mbinfo, dither_plane, first, count);
 }
 
 extern "C" void vp8k_emit(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint8_t* yuv, const uint8_t* alpha_arena,

@@ -32,7 +32,11 @@ void vp8k_parse_tokens_band(cudaStream_t s, const uint8_t* arena, const ImgDesc*
 void vp8k_reconstruct(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, uint32_t* mbinfo, const int16_t* coeffs,
                       uint8_t* yuv, int first, int count, int max_mb_w, int max_mb_h, int row_begin, int row_end, uint8_t* band_ctx);
 void vp8k_loop_filter(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint32_t* mbinfo, uint8_t* yuv,
-                      int first, int count, int max_mb_h, int row_begin, int row_end);
+                      int first, int count, int max_mb_h, int row_begin, int row_end, const int8_t* dither_plane);
+// options.dithering_strength: after the token parse of the whole image, before the loop filter. dither_plane = 128 bytes
+// per macroblock of the wave (NULL to vp8k_loop_filter: no image of the wave asked for dithering).
+void vp8k_dither_plan(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, uint32_t* mbinfo, int8_t* dither_plane,
+                      int first, int count);
 // max_units = largest per-image work-item count (RGB: ceil(w/4)*h; YUV: 16-byte chunks of the three planes).
 void vp8k_emit(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint8_t* yuv, const uint8_t* alpha_arena,
                uint8_t* out, int first, int count, int max_units, int pair_begin, int pair_end);

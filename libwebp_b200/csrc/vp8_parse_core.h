@@ -242,15 +242,15 @@ VP8_FN int parse_frame_header(BoolDec& br, const uint8_t* frame, const ImgDesc& 
     const int dy2ac = bd_bit(br, 0x80) ? bd_signed(br, 4) : 0;
     const int duvdc = bd_bit(br, 0x80) ? bd_signed(br, 4) : 0;
     const int duvac = bd_bit(br, 0x80) ? bd_signed(br, 4) : 0;
-    int dither_amp = 0;
     for (int s = 0; s < 4; ++s) {
       int q = base;
       if (use_segment) q = seg_quant[s] + (absolute_delta ? 0 : base);
-      else if (s > 0) { for (int k = 0; k < 6; ++k) h->dq[s][k] = h->dq[0][k]; continue; }
-      if (im.dither_f > 0 && q + duvac < 12) {   // VP8InitDithering, frame_dec.c:328-349
+      else if (s > 0) { for (int k = 0; k < 6; ++k) h->dq[s][k] = h->dq[0][k]; h->dither[s] = h->dither[0]; continue; }
+      h->dither[s] = 0;
+      if (im.dither_f > 0 && q + duvac < 12) {   // VP8InitDithering, frame_dec.c:328-349 (uv_quant_ = q + dquv_ac)
         const int idx = (q + duvac < 0) ? 0 : q + duvac;
         const int amp = (idx < 3) ? 8 - idx : (idx < 5) ? 4 : (idx < 8) ? 2 : 1;   // kQuantToDitherAmp
-        dither_amp |= (im.dither_f * amp) >> 3;
+        h->dither[s] = (uint8_t)((im.dither_f * amp) >> 3);
       }
       int y2ac = (kVp8AcQ[clampi(q + dy2ac, 0, 127)] * 101581) >> 16;
       if (y2ac < 8) y2ac = 8;
@@ -261,8 +261,6 @@ VP8_FN int parse_frame_header(BoolDec& br, const uint8_t* frame, const ImgDesc& 
       h->dq[s][4] = kVp8DcQ[clampi(q + duvdc, 0, 117)];
       h->dq[s][5] = (int16_t)kVp8AcQ[clampi(q + duvac, 0, 127)];
     }
-    // Dithering that would change pixels is not implemented on the device: refuse rather than differ.
-    if (dither_amp != 0) return VP8B_UNSUPPORTED;
   }
   bd_bit(br, 0x80);   // update_proba: ignored on key frames
   // coefficient probabilities (tree_dec.c:515-538)

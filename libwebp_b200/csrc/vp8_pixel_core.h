@@ -768,6 +768,74 @@ VP8_UNROLL
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// options.dithering_strength (frame_dec.c:319-386): the chroma of macroblocks without AC chroma coefficients gets a
+// pseudo-random offset per pixel, amplitude by the segment's quantiser. The generator (D. Knuth's subtractive one,
+// src/utils/random_utils.[ch]) is ONE sequence per picture, consumed in raster order by the macroblocks that are
+// dithered (128 numbers each, U then V), so a serial pass per image lays the offsets down first (dither_plan_image) and
+// the loop-filter kernel adds them where the reference does: after a macroblock row has been filtered, before the row
+// below filters across their common edge.
+VP8_PTABLE uint32_t kDitherRandomTable[55] = {
+  0x0de15230, 0x03b31886, 0x775faccb, 0x1c88626a, 0x68385c55, 0x14b3b828, 0x4a85fef8, 0x49ddb84b, 0x64fcf397, 0x5c550289,
+  0x4a290000, 0x0d7ec1da, 0x5940b7ab, 0x5492577d, 0x4e19ca72, 0x38d38c69, 0x0c01ee65, 0x32a1755f, 0x5437f652, 0x5abb2c32,
+  0x0faa57b1, 0x73f533e7, 0x685feeda, 0x7563cce2, 0x6e990e83, 0x4730a7ed, 0x4fc0d9c6, 0x496b153c, 0x4f1403fa, 0x541afb0c,
+  0x73990b32, 0x26d7cb1c, 0x6fcc3706, 0x2cbb77d8, 0x75762f2a, 0x6425ccdd, 0x24b35461, 0x0a7d8715, 0x220414a8, 0x141ebf67,
+  0x56b41583, 0x73e502e3, 0x44cab16f, 0x28264d42, 0x73baaefb, 0x0a50ebed, 0x1d6ab6fb, 0x0d3ad40b, 0x35db3b68, 0x2b081e83,
+  0x77ce6b95, 0x5181e5f0, 0x78853bbc, 0x009f9494, 0x27e5ed3c
+};
+#define VP8B_MIN_DITHER_AMP 4
+
+// One image, one thread. `tab` = 55 words of scratch (shared memory on the device). Marks the dithered macroblocks in
+// MbInfo (MBW_DITHER) and writes their 128 offsets (what DitherCombine8x8_C adds, dsp/dec.c:698-711) to `plane`
+// (128 int8 per macroblock of the image). Rows [0, rows), columns [tl_x, br_x) (VP8EnterCritical, frame_dec.c:571-596).
+VP8_PFN void dither_plan_image(const ImgDesc& im, const FrameHdr* h, uint32_t* mbinfo, int8_t* plane, uint32_t* tab) {
+  if (!(h->dither[0] | h->dither[1] | h->dither[2] | h->dither[3])) return;
+  const int mb_w = im.mb_w, rows = h->rows;
+  const int extra = (h->filter_type == 2) ? 8 : (h->filter_type == 1) ? 2 : 0;   // kFilterExtraRows
+  int tl_x = (h->filter_type == 2) ? 0 : ((int)im.crop_x - extra) >> 4;
+  if (tl_x < 0) tl_x = 0;
+  int br_x = ((int)im.crop_x + (int)im.out_w + 15 + extra) >> 4;
+  if (br_x > mb_w) br_x = mb_w;
+  for (int k = 0; k < 55; ++k) tab[k] = kDitherRandomTable[k];
+  int i1 = 0, i2 = 31;
+  for (int my = 0; my < rows; ++my) {
+    for (int mx = tl_x; mx < br_x; ++mx) {
+      const size_t idx = (size_t)my * mb_w + mx;
+      const uint32_t w = mbinfo[4 * idx + 3];
+      // VP8DecodeMB, vp8_dec.c:603,626: skipped macroblocks and those with AC chroma coefficients are left alone
+      const int skipped = h->use_skip && (w & MBW_SKIP);
+      const int amp = (skipped || (w & 0xaaaau)) ? 0 : (int)h->dither[(w >> MBW_SEG_SHIFT) & 3];
+      if (amp < VP8B_MIN_DITHER_AMP) continue;
+      mbinfo[4 * idx + 3] = w | MBW_DITHER;
+      int8_t* out = plane + idx * 128;
+      for (int k = 0; k < 128; ++k) {   // VP8RandomBits2(rg, 8, amp), random_utils.h:39-53
+        int diff = (int)(tab[i1] - tab[i2]);
+        if (diff < 0) diff += (int)(1u << 31);
+        tab[i1] = (uint32_t)diff;
+        if (++i1 == 55) i1 = 0;
+        if (++i2 == 55) i2 = 0;
+        diff = (int)((uint32_t)diff << 1) >> (32 - 8);
+        diff = (diff * amp) >> 8;
+        diff += 1 << 7;
+        out[k] = (int8_t)(((diff - 128) + 8) >> 4);   // delta1 of DitherCombine8x8_C
+      }
+    }
+  }
+}
+
+// Adds the planned offsets to the U and V blocks of macroblock (mx, my): lane l handles row l & 7 of U (l < 8) / V (l < 16).
+VP8_PFN void dither_macroblock(int mx, int my, int mb_w, const int8_t* plane, uint8_t* uplane, uint8_t* vplane) {
+  const int uvs = 8 * mb_w;
+  const int8_t* d = plane + ((size_t)my * mb_w + mx) * 128;
+  WARP_PHASE(lane)
+    if (lane < 16) {
+      uint8_t* p = (lane < 8 ? uplane : vplane) + (size_t)(8 * my + (lane & 7)) * uvs + 8 * mx;
+      const int8_t* dd = d + 8 * lane;   // U rows 0-7 then V rows 0-7: exactly 64 + 64 offsets in generation order
+      for (int k = 0; k < 8; ++k) p[k] = (uint8_t)clip8i((int)p[k] + (int)dd[k]);
+    }
+  WARP_PHASE_END
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // options.use_scaling. The reference rescales Y, U and V with one WebPRescaler each (src/utils/rescaler_utils.c,
 // src/dsp/rescaler.c: fixed point, 32 fractional bits) as the rows arrive and converts YUV444 -> RGB row by row
 // (EmitRescaledRGB / ExportRGB, io_dec.c:357-412), or stores the planes (EmitRescaledYUV, io_dec.c:252-270).

@@ -301,6 +301,46 @@ int reft_decode_scaled(const uint8_t* data, size_t size, int csp, int flags, con
   return WebPDecode(data, size, &cfg);
 }
 
+/* reft_decode_window with options.dithering_strength = strength and options.alpha_dithering_strength = alpha_strength. */
+int reft_decode_dithered(const uint8_t* data, size_t size, int csp, int flags, const int* crop4, int strength, int alpha_strength,
+                         uint8_t* out, size_t out_size) {
+  WebPDecoderConfig cfg;
+  int st, w, h;
+  if (!WebPInitDecoderConfig(&cfg)) return -1;
+  st = WebPGetFeatures(data, size, &cfg.input);
+  if (st != VP8_STATUS_OK) return WebPDecode(data, size, &cfg);
+  cfg.options.bypass_filtering = flags & 1;
+  cfg.options.no_fancy_upsampling = (flags >> 1) & 1;
+  cfg.options.flip = (flags >> 3) & 1;
+  cfg.options.dithering_strength = strength;
+  cfg.options.alpha_dithering_strength = alpha_strength;
+  w = cfg.input.width; h = cfg.input.height;
+  if (crop4 != NULL && crop4[2] > 0) {
+    cfg.options.use_cropping = 1;
+    cfg.options.crop_left = crop4[0]; cfg.options.crop_top = crop4[1];
+    cfg.options.crop_width = crop4[2]; cfg.options.crop_height = crop4[3];
+    w = crop4[2]; h = crop4[3];
+  }
+  cfg.output.colorspace = (WEBP_CSP_MODE)csp;
+  cfg.output.is_external_memory = 1;
+  if (csp == MODE_YUV || csp == MODE_YUVA) {
+    const int uvw = (w + 1) / 2, uvh = (h + 1) / 2;
+    if (out_size < (size_t)w * h + 2 * (size_t)uvw * uvh + (csp == MODE_YUVA ? (size_t)w * h : 0)) return -2;
+    cfg.output.u.YUVA.y = out; cfg.output.u.YUVA.y_stride = w; cfg.output.u.YUVA.y_size = (size_t)w * h;
+    cfg.output.u.YUVA.u = out + (size_t)w * h; cfg.output.u.YUVA.u_stride = uvw; cfg.output.u.YUVA.u_size = (size_t)uvw * uvh;
+    cfg.output.u.YUVA.v = cfg.output.u.YUVA.u + (size_t)uvw * uvh; cfg.output.u.YUVA.v_stride = uvw; cfg.output.u.YUVA.v_size = (size_t)uvw * uvh;
+    if (csp == MODE_YUVA) {
+      cfg.output.u.YUVA.a = cfg.output.u.YUVA.v + (size_t)uvw * uvh; cfg.output.u.YUVA.a_stride = w; cfg.output.u.YUVA.a_size = (size_t)w * h;
+    }
+  } else {
+    const int bpp = (csp == MODE_RGB || csp == MODE_BGR) ? 3
+                  : (csp == MODE_RGBA_4444 || csp == MODE_RGB_565 || csp == MODE_rgbA_4444) ? 2 : 4;
+    if (out_size < (size_t)w * h * bpp) return -2;
+    cfg.output.u.RGBA.rgba = out; cfg.output.u.RGBA.stride = w * bpp; cfg.output.u.RGBA.size = out_size;
+  }
+  return WebPDecode(data, size, &cfg);
+}
+
 int reft_features(const uint8_t* data, size_t size, int* feat5) {
   WebPBitstreamFeatures f;
   const int st = WebPGetFeatures(data, size, &f);

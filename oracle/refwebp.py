@@ -77,6 +77,9 @@ def lib():
         L.reft_features.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int)]
         if hasattr(L, "reft_decode_window"):
             L.reft_decode_window.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_size_t]
+        if hasattr(L, "reft_decode_dithered"):
+            L.reft_decode_dithered.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int,
+                                               C.c_void_p, C.c_size_t]
         if hasattr(L, "reft_decode_scaled"):
             L.reft_decode_scaled.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                              C.POINTER(C.c_int), C.c_void_p, C.c_size_t]
@@ -166,6 +169,21 @@ def decode_window(data, csp=MODE_RGBA, flags=0, crop=None):
     out = np.zeros(max(n, 16), np.uint8)
     c4 = (C.c_int * 4)(*(crop if crop else (0, 0, 0, 0)))
     st = L.reft_decode_window(data, len(data), csp, flags, c4, out.ctypes.data, out.size)
+    return st, (out[:n] if st == 0 else None)
+
+
+def decode_dithered(data, csp=MODE_RGBA, flags=0, crop=None, strength=50, alpha_strength=0):
+    """decode_window with options.dithering_strength / options.alpha_dithering_strength (dwebp's defaults are 50 / 100)."""
+    L = lib()
+    st, f = features(data)
+    w, h = (crop[2], crop[3]) if crop else (f["width"], f["height"])
+    if st != 0 or w <= 0 or h <= 0:
+        w = h = 4
+    n = (w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2) + (w * h if csp == MODE_YUVA else 0)) if csp in (MODE_YUV, MODE_YUVA) \
+        else w * h * BPP[csp]
+    out = np.zeros(max(n, 16), np.uint8)
+    c4 = (C.c_int * 4)(*(crop if crop else (0, 0, 0, 0)))
+    st = L.reft_decode_dithered(data, len(data), csp, flags, c4, strength, alpha_strength, out.ctypes.data, out.size)
     return st, (out[:n] if st == 0 else None)
 
 

@@ -78,3 +78,17 @@ def product():
 def truncated(data, n):
     """A RIFF file cut to n bytes with the RIFF size field left alone (what a short read looks like)."""
     return data[:n]
+
+
+def smooth_image(w, h, seed):
+    """A picture of slow sinusoids with one noisy patch: at fine quantisers most macroblocks end up without AC chroma
+    coefficients, which is what the decoder's random dithering looks for (vp8_dec.c:603)."""
+    import numpy as np
+    y, x = np.mgrid[0:h, 0:w].astype(np.float64)
+    rng = np.random.default_rng(seed)
+    img = np.zeros((h, w, 3), np.uint8)
+    for c in range(3):
+        a, b, ph = rng.uniform(0.5, 2, 3)
+        img[..., c] = np.clip(128 + 100 * np.sin(x * a * 0.01 + ph) * np.cos(y * b * 0.012), 0, 255)
+    img[h // 3:h // 2, w // 4:w // 2] = rng.integers(0, 255, (h // 2 - h // 3, w // 2 - w // 4, 3), dtype=np.uint8)
+    return img

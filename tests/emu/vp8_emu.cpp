@@ -41,6 +41,11 @@ extern "C" int emu_decode_window(const uint8_t* data, size_t size, int csp, int 
 
 // options.use_scaling: the (cropped) picture rescaled to scaled_w x scaled_h (both given); `stride` and `out` describe
 // the scaled picture.
+// options.dithering_strength = strength (0..100) on the whole picture.
+static int g_emu_dither_f = 0;
+extern "C" int emu_decode_dithered(const uint8_t* data, size_t size, int csp, int flags, uint8_t* out, size_t out_size,
+                                   int stride, int strength, int crop_x, int crop_y, int crop_w, int crop_h);
+
 extern "C" int emu_decode_scaled(const uint8_t* data, size_t size, int csp, int flags, uint8_t* out, size_t out_size,
                                  int stride, int crop_x, int crop_y, int crop_w, int crop_h, int scaled_w, int scaled_h) {
   return emu_decode_crop(data, size, csp, flags, out, out_size, stride, 0, nullptr, crop_x, crop_y, crop_w, crop_h, scaled_w, scaled_h);
@@ -73,6 +78,7 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
     im.dst_w = (uint16_t)scaled_w; im.dst_h = (uint16_t)scaled_h;
     if (scaled_w < c.width * 3 / 4 && scaled_h < c.height * 3 / 4) im.flags |= VP8B_FLAG_BYPASS_FILTER;
   }
+  im.dither_f = (uint8_t)g_emu_dither_f;
   im.num_parts = (uint8_t)vp8b_prescan_partitions(data + c.frame_offset + 10, c.part0_size);
   const int mb_w = im.mb_w, mb_h = im.mb_h;
   const size_t nmb = (size_t)mb_w * mb_h;
@@ -222,6 +228,25 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
   }
   if (unfiltered) memcpy(unfiltered, yuv.data(), yuv.size());
 
+  // options.dithering_strength: the plan (one serial pass), then filter and dither in the reference's order (row by
+  // row: FilterRow, then DitherRow, frame_dec.c:424-430); the device interleaves the two inside its wavefront
+  const bool dithering = (hdr.dither[0] | hdr.dither[1] | hdr.dither[2] | hdr.dither[3]) != 0;
+  if (dithering) {
+    std::vector<int8_t> dplane(nmb * 128, 0);
+    uint32_t tab[55];
+    dither_plan_image(im, &hdr, mbinfo.data(), dplane.data(), tab);
+    FilterWs ws;
+    for (int my = 0; my < rows; ++my) {
+      for (int mx = 0; mx < mb_w && hdr.filter_type > 0; ++mx) {
+        const uint32_t w = mbinfo[4 * ((size_t)my * mb_w + mx) + 3];
+        const uint8_t* fs = hdr.fstr[(w >> MBW_SEG_SHIFT) & 3][(w & MBW_I4X4) ? 1 : 0];
+        filter_macroblock(ws, mx, my, mb_w, hdr.filter_type, fs, (w & MBW_INNER) != 0, yp, up, vp);
+      }
+      for (int mx = 0; mx < mb_w; ++mx) {
+        if (mbinfo[4 * ((size_t)my * mb_w + mx) + 3] & MBW_DITHER) dither_macroblock(mx, my, mb_w, dplane.data(), up, vp);
+      }
+    }
+  } else
   // K4: loop-filter wavefront
   if (hdr.filter_type > 0) {
     FilterWs ws;
@@ -291,4 +316,12 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
     for (int j = 0; j < h; ++j) for (int q = 0; q < (w + 3) / 4; ++q) emit_rgb_quad(im, wy, wu, wv, alpha, out, q, j);
   }
   return VP8_STATUS_OK;
+}
+
+extern "C" int emu_decode_dithered(const uint8_t* data, size_t size, int csp, int flags, uint8_t* out, size_t out_size,
+                                   int stride, int strength, int crop_x, int crop_y, int crop_w, int crop_h) {
+  g_emu_dither_f = strength < 0 ? 0 : strength > 100 ? 255 : strength * 255 / 100;
+  const int st = emu_decode_crop(data, size, csp, flags, out, out_size, stride, 0, nullptr, crop_x, crop_y, crop_w, crop_h);
+  g_emu_dither_f = 0;
+  return st;
 }

@@ -9,7 +9,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import ROOT, sha
+from conftest import ROOT, sha, smooth_image
 
 EMU_DIR = os.path.join(ROOT, "tests", "emu")
 
@@ -199,3 +199,36 @@ def test_emu_scaling_matches_reference(ref, manifest, amanifest):
                                          sw if csp in (11, 12) else sw * ref.BPP[csp], c[0], c[1], c[2], c[3], sw, sh)
                 assert st == 0, (e["file"], req, crop, csp, st)
                 assert np.array_equal(out[:n], want), (e["file"], req, crop, flip, csp, (sw, sh))
+
+
+def test_emu_dithering_matches_reference(ref):
+    """options.dithering_strength (frame_dec.c:319-386): one pseudo-random sequence per picture, consumed in raster order by
+    the macroblocks without AC chroma coefficients inside the crop window's macroblock range, added after a row has been
+    filtered and before the next row filters across the common edge. Smooth pictures at fine quantisers, both loop filters,
+    1-4 segments, strengths 50 (dwebp's default) and 100, crop windows; the device code's host build against the reference."""
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR])
+    L = C.CDLL(os.path.join(EMU_DIR, "libvp8_emu.so"))
+    L.emu_decode_dithered.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                      C.c_int, C.c_int, C.c_int]
+    rng = np.random.default_rng(31)
+    changed = 0
+    for k, (q, segs, flt, w, h) in enumerate(((100, 1, 0, 200, 136), (99, 4, 1, 177, 93), (97, 4, 1, 64, 200), (95, 2, 0, 320, 48), (90, 4, 1, 130, 130))):
+        data = ref.encode(smooth_image(w, h, 40 + k), ref.EncCfg(q, 4, segments=segs, filter_type=flt, filter_strength=40))
+        for strength in (50, 100):
+            for it in range(3):
+                crop = None
+                if it > 0:
+                    cw, ch = int(rng.integers(1, w + 1)), int(rng.integers(1, h + 1))
+                    crop = (int(rng.integers(0, w - cw + 1)), int(rng.integers(0, h - ch + 1)), cw, ch)
+                ow, oh = (crop[2], crop[3]) if crop else (w, h)
+                for csp in (1, 11):
+                    s_ref, want = ref.decode_dithered(data, csp, 0, crop, strength)
+                    _, plain = ref.decode_dithered(data, csp, 0, crop, 0)
+                    changed += int((want != plain).sum())
+                    n = want.size
+                    out = np.zeros(max(n, 16), np.uint8)
+                    c = crop or (0, 0, 0, 0)
+                    st = L.emu_decode_dithered(data, len(data), csp, 0, out.ctypes.data, out.size, ow if csp == 11 else ow * 4,
+                                               strength, c[0], c[1], c[2], c[3])
+                    assert st == s_ref == 0 and np.array_equal(out[:n], want), (q, segs, flt, strength, crop, csp)
+    assert changed > 10000   # the cases do exercise the dithering

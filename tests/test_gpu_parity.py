@@ -129,15 +129,43 @@ def test_waves_small_scratch(W, port, manifest):
         b.close()
 
 
-def test_dithering_option_is_exact_or_refused(W, ref, manifest):
-    """dwebp's default dithering_strength=50 only changes pixels for very fine quantisers (frame_dec.c:328-349).
-    Where it would, the product refuses; elsewhere the output equals the reference's."""
+def test_dithering(W, ref, manifest, amanifest):
+    """options.dithering_strength on the device (dwebp's default is 50): identical to the reference where it changes
+    pixels (smooth pictures at fine quantisers, both loop filters, crop windows) and where it does not (the manifest);
+    options.alpha_dithering_strength (dwebp: 100) is a no-op unless the encoder quantised the alpha levels, which is
+    the one case refused."""
+    from conftest import smooth_image
     for e in manifest:
         st, out = W.WebPDecode(e["data"], W.MODE_RGBA, dithering_strength=50)
-        if st == 0:
-            assert sha(out) == e["sha256"]["1:0"], e["file"]
+        s_ref, want = ref.decode_dithered(e["data"], W.MODE_RGBA, 0, None, 50)
+        assert st == s_ref == 0 and np.array_equal(out.reshape(-1), want), e["file"]
+    rng = np.random.default_rng(32)
+    changed = 0
+    for k, (q, segs, flt, w, h) in enumerate(((100, 1, 0, 200, 136), (99, 4, 1, 177, 93), (97, 4, 1, 64, 200), (95, 2, 0, 320, 48), (90, 4, 1, 1920, 1080))):
+        data = ref.encode(smooth_image(w, h, 40 + k), ref.EncCfg(q, 4, segments=segs, filter_type=flt, filter_strength=40))
+        for strength in (50, 100):
+            for it in range(3):
+                crop = None
+                if it > 0:
+                    cw, ch = int(rng.integers(1, w + 1)), int(rng.integers(1, h + 1))
+                    crop = (int(rng.integers(0, w - cw + 1)), int(rng.integers(0, h - ch + 1)), cw, ch)
+                for csp in (W.MODE_RGBA, W.MODE_YUV):
+                    s_ref, want = ref.decode_dithered(data, csp, 0, crop, strength)
+                    _, plain = ref.decode_dithered(data, csp, 0, crop, 0)
+                    changed += int((want != plain).sum())
+                    st, out = W.WebPDecode(data, csp, dithering_strength=strength, crop=crop)
+                    assert st == s_ref == 0, (q, strength, crop, csp, st, W.last_error())
+                    assert np.array_equal(out.reshape(-1)[:want.size], want), (q, segs, flt, strength, crop, csp)
+    assert changed > 10000
+    for e in amanifest:
+        i = e["data"].find(b"ALPH")
+        quantised = ((e["data"][i + 8] >> 4) & 3) == 1
+        st, out = W.WebPDecode(e["data"], W.MODE_RGBA, dithering_strength=50, alpha_dithering_strength=100)
+        if quantised:
+            assert st == W.VP8_STATUS_UNSUPPORTED_FEATURE, e["file"]
         else:
-            assert st == W.VP8_STATUS_UNSUPPORTED_FEATURE
+            s_ref, want = ref.decode_dithered(e["data"], W.MODE_RGBA, 0, None, 50, 100)
+            assert st == s_ref == 0 and np.array_equal(out.reshape(-1)[:want.size], want), e["file"]
 
 
 def test_full_size_batch_properties(W, ref):
