@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(32) k_dither_plan(const ImgDesc* __restrict__ 
 // ---------------------------------------------------------------------------------------------------------
 #define EMIT_THREADS 256
 
-__global__ void __launch_bounds__(EMIT_THREADS, 4) k_emit(const ImgDesc* __restrict__ imgs, const FrameHdr* __restrict__ hdrs,
+__global__ void __launch_bounds__(EMIT_THREADS, 5) k_emit(const ImgDesc* __restrict__ imgs, const FrameHdr* __restrict__ hdrs,
                                                        const uint8_t* __restrict__ yuv, const uint8_t* __restrict__ alpha_arena,
                                                        uint8_t* out, int first, int blocks_per_image, int pair_begin, int pair_end) {
   const int img = first + blockIdx.x / blocks_per_image;
