@@ -128,6 +128,19 @@ WEBP_EXTERN WebPIDecoder* WebPIDecode(const uint8_t* data, size_t data_size, Web
 WEBP_EXTERN void WebPIDelete(WebPIDecoder* idec);
 WEBP_EXTERN VP8StatusCode WebPIAppend(WebPIDecoder* idec, const uint8_t* data, size_t data_size);
 WEBP_EXTERN VP8StatusCode WebPIUpdate(WebPIDecoder* idec, const uint8_t* data, size_t data_size);
+WEBP_EXTERN WebPIDecoder* WebPINewRGB(WEBP_CSP_MODE csp, uint8_t* output_buffer, size_t output_buffer_size, int output_stride); /* decode.h:297 */
+WEBP_EXTERN WebPIDecoder* WebPINewYUVA(uint8_t* luma, size_t luma_size, int luma_stride, uint8_t* u, size_t u_size, int u_stride,
+                                       uint8_t* v, size_t v_size, int v_stride, uint8_t* a, size_t a_size, int a_stride); /* decode.h:312 */
+WEBP_EXTERN WebPIDecoder* WebPINewYUV(uint8_t* luma, size_t luma_size, int luma_stride, uint8_t* u, size_t u_size, int u_stride,
+                                      uint8_t* v, size_t v_size, int v_stride); /* decode.h:320 */
+WEBP_EXTERN uint8_t* WebPIDecGetRGB(const WebPIDecoder* idec, int* last_y, int* width, int* height, int* stride); /* decode.h:350 */
+WEBP_EXTERN uint8_t* WebPIDecGetYUVA(const WebPIDecoder* idec, int* last_y, uint8_t** u, uint8_t** v, uint8_t** a,
+                                     int* width, int* height, int* stride, int* uv_stride, int* a_stride); /* decode.h:357 */
+static WEBP_INLINE uint8_t* WebPIDecGetYUV(const WebPIDecoder* idec, int* last_y, uint8_t** u, uint8_t** v,
+                                           int* width, int* height, int* stride, int* uv_stride) { /* decode.h:364 */
+  return WebPIDecGetYUVA(idec, last_y, u, v, NULL, width, height, stride, uv_stride, NULL);
+}
+WEBP_EXTERN const WebPDecBuffer* WebPIDecodedArea(const WebPIDecoder* idec, int* left, int* top, int* width, int* height); /* decode.h:377 */
 
 struct WebPBitstreamFeatures { /* decode.h:414-422 */
   int width;

@@ -93,7 +93,8 @@ EXPORTS = [  # every symbol include/webp/*.h declares
     "WebPGetDecoderVersion", "WebPGetInfo", "WebPDecodeRGBA", "WebPDecodeARGB", "WebPDecodeBGRA", "WebPDecodeRGB",
     "WebPDecodeBGR", "WebPDecodeYUV", "WebPDecodeRGBAInto", "WebPDecodeARGBInto", "WebPDecodeBGRAInto",
     "WebPDecodeRGBInto", "WebPDecodeBGRInto", "WebPDecodeYUVInto", "WebPInitDecBufferInternal", "WebPFreeDecBuffer",
-    "WebPINewDecoder", "WebPIDecode", "WebPIDelete", "WebPIAppend", "WebPIUpdate", "WebPGetFeaturesInternal",
+    "WebPINewDecoder", "WebPIDecode", "WebPIDelete", "WebPIAppend", "WebPIUpdate", "WebPINewRGB", "WebPINewYUVA", "WebPINewYUV",
+    "WebPIDecGetRGB", "WebPIDecGetYUVA", "WebPIDecodedArea", "WebPGetFeaturesInternal",
     "WebPInitDecoderConfigInternal", "WebPDecode", "WebPMalloc", "WebPFree", "VP8GetCPUInfo",
     "WebPBatchOptionsInitInternal", "WebPDecodeBatch", "WebPBatchCreate", "WebPBatchDecode", "WebPBatchDownload",
     "WebPBatchDestroy", "WebPBatchOutput", "WebPBatchGetTimings", "WebPBatchHostAlloc", "WebPBatchHostFree",

@@ -235,3 +235,106 @@ VP8StatusCode WebPIUpdate(WebPIDecoder* idec, const uint8_t* data, size_t data_s
   idec->mode = 2;
   return IDecodeNow(idec, data, data_size);
 }
+
+/* ---- the rest of the incremental interface (idec_dec.c:626-700, 840-909). Constructors that describe the output up
+ * front, and the getters: before the image has been decoded there is no displayable area (the reference answers NULL
+ * until the first rows are out), afterwards it is the whole picture (last_y = height). */
+WebPIDecoder* WebPINewRGB(WEBP_CSP_MODE csp, uint8_t* output_buffer, size_t output_buffer_size, int output_stride) {
+  const int is_external_memory = (output_buffer != NULL) ? 1 : 0;
+  WebPIDecoder* idec;
+  if (csp >= MODE_YUV) return NULL;
+  if (is_external_memory == 0) {      /* overrule the size and stride of an absent buffer */
+    output_buffer_size = 0;
+    output_stride = 0;
+  } else if (output_stride == 0 || output_buffer_size == 0) {
+    return NULL;
+  }
+  idec = WebPINewDecoder(NULL);
+  if (idec == NULL) return NULL;
+  idec->own_config.output.colorspace = csp;
+  idec->own_config.output.is_external_memory = is_external_memory;
+  idec->own_config.output.u.RGBA.rgba = output_buffer;
+  idec->own_config.output.u.RGBA.stride = output_stride;
+  idec->own_config.output.u.RGBA.size = output_buffer_size;
+  return idec;
+}
+
+WebPIDecoder* WebPINewYUVA(uint8_t* luma, size_t luma_size, int luma_stride, uint8_t* u, size_t u_size, int u_stride,
+                           uint8_t* v, size_t v_size, int v_stride, uint8_t* a, size_t a_size, int a_stride) {
+  const int is_external_memory = (luma != NULL) ? 1 : 0;
+  WebPIDecoder* idec;
+  WEBP_CSP_MODE colorspace;
+  if (is_external_memory == 0) {      /* overrule everything: the library allocates */
+    luma_size = u_size = v_size = a_size = 0;
+    luma_stride = u_stride = v_stride = a_stride = 0;
+    u = v = a = NULL;
+    colorspace = MODE_YUVA;
+  } else {
+    if (u == NULL || v == NULL) return NULL;
+    if (luma_size == 0 || u_size == 0 || v_size == 0) return NULL;
+    if (luma_stride == 0 || u_stride == 0 || v_stride == 0) return NULL;
+    if (a != NULL && (a_size == 0 || a_stride == 0)) return NULL;
+    colorspace = (a == NULL) ? MODE_YUV : MODE_YUVA;
+  }
+  idec = WebPINewDecoder(NULL);
+  if (idec == NULL) return NULL;
+  idec->own_config.output.colorspace = colorspace;
+  idec->own_config.output.is_external_memory = is_external_memory;
+  idec->own_config.output.u.YUVA.y = luma; idec->own_config.output.u.YUVA.y_stride = luma_stride; idec->own_config.output.u.YUVA.y_size = luma_size;
+  idec->own_config.output.u.YUVA.u = u; idec->own_config.output.u.YUVA.u_stride = u_stride; idec->own_config.output.u.YUVA.u_size = u_size;
+  idec->own_config.output.u.YUVA.v = v; idec->own_config.output.u.YUVA.v_stride = v_stride; idec->own_config.output.u.YUVA.v_size = v_size;
+  idec->own_config.output.u.YUVA.a = a; idec->own_config.output.u.YUVA.a_stride = a_stride; idec->own_config.output.u.YUVA.a_size = a_size;
+  return idec;
+}
+
+WebPIDecoder* WebPINewYUV(uint8_t* luma, size_t luma_size, int luma_stride, uint8_t* u, size_t u_size, int u_stride,
+                          uint8_t* v, size_t v_size, int v_stride) {
+  return WebPINewYUVA(luma, luma_size, luma_stride, u, u_size, u_stride, v, v_size, v_stride, NULL, 0, 0);
+}
+
+static const WebPDecBuffer* IDecOutput(const WebPIDecoder* idec) {
+  if (idec == NULL || idec->status != VP8_STATUS_OK) return NULL;   /* nothing displayable before the one decode */
+  if (idec->config != NULL) return &idec->config->output;
+  if (idec->final_output != NULL) return idec->final_output;
+  return &idec->own_config.output;
+}
+
+const WebPDecBuffer* WebPIDecodedArea(const WebPIDecoder* idec, int* left, int* top, int* width, int* height) {
+  const WebPDecBuffer* const src = IDecOutput(idec);
+  if (left != NULL) *left = 0;
+  if (top != NULL) *top = 0;
+  if (src != NULL) {
+    if (width != NULL) *width = src->width;
+    if (height != NULL) *height = src->height;
+  } else {
+    if (width != NULL) *width = 0;
+    if (height != NULL) *height = 0;
+  }
+  return src;
+}
+
+uint8_t* WebPIDecGetRGB(const WebPIDecoder* idec, int* last_y, int* width, int* height, int* stride) {
+  const WebPDecBuffer* const output = IDecOutput(idec);
+  if (output == NULL || output->colorspace >= MODE_YUV) return NULL;
+  if (last_y != NULL) *last_y = output->height;
+  if (width != NULL) *width = output->width;
+  if (height != NULL) *height = output->height;
+  if (stride != NULL) *stride = output->u.RGBA.stride;
+  return output->u.RGBA.rgba;
+}
+
+uint8_t* WebPIDecGetYUVA(const WebPIDecoder* idec, int* last_y, uint8_t** u, uint8_t** v, uint8_t** a,
+                         int* width, int* height, int* stride, int* uv_stride, int* a_stride) {
+  const WebPDecBuffer* const output = IDecOutput(idec);
+  if (output == NULL || output->colorspace < MODE_YUV) return NULL;
+  if (last_y != NULL) *last_y = output->height;
+  if (u != NULL) *u = output->u.YUVA.u;
+  if (v != NULL) *v = output->u.YUVA.v;
+  if (a != NULL) *a = output->u.YUVA.a;
+  if (width != NULL) *width = output->width;
+  if (height != NULL) *height = output->height;
+  if (stride != NULL) *stride = output->u.YUVA.y_stride;
+  if (uv_stride != NULL) *uv_stride = output->u.YUVA.u_stride;
+  if (a_stride != NULL) *a_stride = output->u.YUVA.a_stride;
+  return output->u.YUVA.y;
+}

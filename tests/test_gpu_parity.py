@@ -272,6 +272,42 @@ def test_incremental_api(W, port, manifest, amanifest):
         L.WebPIDelete(idec)
         L.WebPFreeDecBuffer(C.byref(buf))
         assert np.array_equal(got[:, :w * 4], want[:, :w * 4])
+        # WebPINewRGB with an external buffer + the getters: nothing displayable before the last byte, the whole picture after
+        L.WebPINewRGB.restype = C.c_void_p
+        L.WebPINewRGB.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_int]
+        L.WebPIDecGetRGB.restype = C.c_void_p
+        L.WebPIDecGetRGB.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
+        L.WebPIDecodedArea.restype = C.c_void_p
+        L.WebPIDecodedArea.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
+        ext = np.zeros((h, w * 4 + 16), np.uint8)
+        idec = L.WebPINewRGB(W.MODE_RGBA, ext.ctypes.data, ext.size, w * 4 + 16)
+        assert idec and not L.WebPINewRGB(W.MODE_YUV, None, 0, 0) and not L.WebPINewRGB(W.MODE_RGBA, ext.ctypes.data, 0, 0)
+        ly, ww, hh, ss = C.c_int(-1), C.c_int(-1), C.c_int(-1), C.c_int(-1)
+        assert L.WebPIAppend(idec, data[:len(data) // 2], len(data) // 2) == W.VP8_STATUS_SUSPENDED
+        assert not L.WebPIDecGetRGB(idec, C.byref(ly), C.byref(ww), C.byref(hh), C.byref(ss))
+        assert not L.WebPIDecodedArea(idec, None, None, C.byref(ww), C.byref(hh)) and ww.value == 0 and hh.value == 0
+        assert L.WebPIAppend(idec, data[len(data) // 2:], len(data) - len(data) // 2) == W.VP8_STATUS_OK
+        p = L.WebPIDecGetRGB(idec, C.byref(ly), C.byref(ww), C.byref(hh), C.byref(ss))
+        assert p == ext.ctypes.data and (ly.value, ww.value, hh.value, ss.value) == (h, w, h, w * 4 + 16)
+        assert L.WebPIDecodedArea(idec, None, None, C.byref(ww), C.byref(hh)) and (ww.value, hh.value) == (w, h)
+        L.WebPIDelete(idec)
+        assert np.array_equal(ext[:, :w * 4], want[:, :w * 4])
+        # WebPINewYUVA with library-allocated planes
+        L.WebPINewYUVA.restype = C.c_void_p
+        L.WebPINewYUVA.argtypes = [C.c_void_p, C.c_size_t, C.c_int] * 4
+        L.WebPIDecGetYUVA.restype = C.c_void_p
+        L.WebPIDecGetYUVA.argtypes = [C.c_void_p, C.POINTER(C.c_int)] + [C.POINTER(C.c_void_p)] * 3 + [C.POINTER(C.c_int)] * 5
+        idec = L.WebPINewYUVA(None, 0, 0, None, 0, 0, None, 0, 0, None, 0, 0)
+        assert idec and L.WebPIAppend(idec, data, len(data)) == W.VP8_STATUS_OK
+        up, vp, ap = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        st_, uvs, as_ = C.c_int(), C.c_int(), C.c_int()
+        yp = L.WebPIDecGetYUVA(idec, C.byref(ly), C.byref(up), C.byref(vp), C.byref(ap), C.byref(ww), C.byref(hh), C.byref(st_), C.byref(uvs), C.byref(as_))
+        assert yp and up.value and vp.value and (ly.value, ww.value, hh.value) == (h, w, h)
+        _, want_yuv = W.WebPDecode(data, W.MODE_YUVA)
+        got_y = np.ctypeslib.as_array(C.cast(yp, C.POINTER(C.c_uint8)), (h, st_.value))[:, :w]
+        assert np.array_equal(got_y.reshape(-1), want_yuv[:w * h])
+        assert not L.WebPIDecGetRGB(idec, None, None, None, None)   # wrong family
+        L.WebPIDelete(idec)
 
 
 def test_crop_and_flip(W, ref, manifest, amanifest):
