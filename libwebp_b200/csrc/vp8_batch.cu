@@ -273,10 +273,6 @@ static VP8StatusCode plan_item(WebPBatchItem* it, const WebPBatchOptions& opt, V
   if (st != VP8_STATUS_OK) return st;
   if (c->has_animation) return VP8_STATUS_UNSUPPORTED_FEATURE;             // webp_dec.c:427-429
   if (c->is_lossless) return VP8_STATUS_UNSUPPORTED_FEATURE;               // lossless: not on this path
-  // alpha de-banding (WebPDequantizeLevels) only ever runs on planes whose levels were quantised by the encoder
-  // (ALPH header: pre-processing = 1, alpha_dec.c:71,200-210); dwebp asks for it by default, so refuse exactly those
-  if (c->has_alph_chunk && cfg->options.alpha_dithering_strength > 0 && c->alpha_size > 0 &&
-      ((it->data[c->alpha_offset] >> 4) & 3) == 1) return VP8_STATUS_UNSUPPORTED_FEATURE;
   if (c->part0_size > c->frame_size - 10) return VP8_STATUS_NOT_ENOUGH_DATA;   // vp8_dec.c:345-348
   const WebPDecoderOptions* o = &cfg->options;
   const int csp = cfg->output.colorspace;
@@ -387,6 +383,10 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
       d.alpha_in = ranges[item_range[i]].dev_off + (size_t)(b->items[i].data - ranges[item_range[i]].base) + c.alpha_offset;
       d.alpha_size = (uint32_t)c.alpha_size;
       d.alpha_index = (uint32_t)b->aimgs.size();
+      // alpha de-banding only ever runs on planes whose levels were quantised by the encoder (ALPH header:
+      // pre-processing = 1, alpha_dec.c:71,200-210); dwebp asks for it by default
+      const int ad = cfg->options.alpha_dithering_strength;
+      if (ad > 0 && c.alpha_size > 0 && ((b->items[i].data[c.alpha_offset] >> 4) & 3) == 1) d.alpha_dither = (uint8_t)(ad > 100 ? 100 : ad);
       b->aimgs.push_back((int)b->imgs.size());
     }
     size_t bytes;
@@ -687,7 +687,7 @@ static bool batch_alpha(WebPBatch* b) {
     CU_TRY(cudaMemcpyAsync(b->ahdrs.data(), b->d_ahdrs.p, sizeof(AlphaHdr) * na, cudaMemcpyDeviceToHost, s), "D2H alpha headers");
     CU_TRY(cudaStreamSynchronize(s), "alpha header pass");
     size_t work2 = 0, planes = 0;
-    std::vector<size_t> tab(na, 0), grp(na, 0), cod(na, 0);
+    std::vector<size_t> tab(na, 0), grp(na, 0), cod(na, 0), smo(na, 0);
     for (int a = 0; a < na; ++a) {
       const AlphaHdr& h = b->ahdrs[a];
       ImgDesc& d = b->imgs[b->aimgs[a]];
@@ -697,6 +697,7 @@ static bool batch_alpha(WebPBatch* b) {
         grp[a] = work2; work2 += align_up((size_t)h.num_groups * sizeof(AlGroup), 256);
         cod[a] = work2; work2 += align_up(4 * ((size_t)h.xsize * d.height + 4), 256);
       }
+      if (d.alpha_dither != 0) { smo[a] = work2 + 1; work2 += align_up(2 * (size_t)d.out_w * d.out_h + 16, 256); }   // +1: 0 means none
       d.alpha_plane = planes;
       planes += align_up((size_t)d.width * d.height, 256);
     }
@@ -706,6 +707,7 @@ static bool batch_alpha(WebPBatch* b) {
     for (int a = 0; a < na; ++a) {
       const uint64_t base = (uint64_t)(uintptr_t)b->d_awork2.p;
       b->aplans[a].tables = base + tab[a]; b->aplans[a].groups = base + grp[a]; b->aplans[a].coded = base + cod[a];
+      b->aplans[a].smooth = smo[a] ? base + smo[a] - 1 : 0;
     }
     CU_TRY(cudaMemcpyAsync(b->d_aplans.p, b->aplans.data(), sizeof(AlphaPlan) * na, cudaMemcpyHostToDevice, s), "H2D alpha plans");
     CU_TRY(cudaMemcpyAsync(b->d_imgs.p, b->imgs.data(), sizeof(ImgDesc) * b->imgs.size(), cudaMemcpyHostToDevice, s), "H2D descriptors");

@@ -54,7 +54,8 @@ typedef struct ImgDesc {
   // options.use_scaling: the window above is rescaled to dst_w x dst_h (io_dec.c:239-556, src/dsp/rescaler.c); 0 = no scaling.
   // out_stride / out_off then describe the scaled picture.
   uint16_t dst_w, dst_h;
-  uint32_t pad_;
+  uint8_t alpha_dither;   // options.alpha_dithering_strength (1..100) when the ALPH chunk's levels were quantised, else 0
+  uint8_t pad_[3];
 } ImgDesc;
 #define VP8B_NO_ALPHA 0xffffffffffffffffull
 

@@ -770,6 +770,21 @@ __global__ void __launch_bounds__(ALPHA_FINISH_THREADS) k_alpha_finish(const uin
               alpha_arena + im.alpha_plane, (int)threadIdx.x, (int)blockDim.x);
 }
 
+// options.alpha_dithering_strength (vp8l_alpha_core.h:alph_smooth) on the crop window of the finished plane.
+__global__ void __launch_bounds__(ALPHA_FINISH_THREADS) k_alpha_smooth(const ImgDesc* __restrict__ imgs, const int* __restrict__ aimgs,
+                                                                       const AlphaPlan* __restrict__ plans, const AlphaHdr* __restrict__ ahdrs,
+                                                                       uint8_t* alpha_arena) {
+  __shared__ int16_t lut[2048];
+  __shared__ uint32_t used[256];
+  const int a = blockIdx.x;
+  if (ahdrs[a].status != AL_OK) return;
+  const ImgDesc im = imgs[aimgs[a]];
+  const AlphaPlan pl = plans[a];
+  if (im.alpha_dither == 0 || pl.smooth == 0 || im.alpha_plane == VP8B_NO_ALPHA) return;
+  alph_smooth(alpha_arena + im.alpha_plane + (size_t)im.crop_y * im.width + im.crop_x, im.width, im.out_w, im.out_h, im.alpha_dither,
+              (uint16_t*)pl.smooth, lut, used, (int)threadIdx.x, (int)blockDim.x);
+}
+
 extern "C" void vp8k_alpha_header(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, const int* aimgs, const AlphaPlan* plans,
                                   AlphaHdr* ahdrs, int count) {
   k_alpha_header<<<count, 32, 0, s>>>(arena, imgs, aimgs, plans, ahdrs);
@@ -778,4 +793,5 @@ extern "C" void vp8k_alpha_decode(cudaStream_t s, const uint8_t* arena, const Im
                                   AlphaHdr* ahdrs, uint8_t* alpha_arena, int count) {
   k_alpha_pixels<<<count, 32, 0, s>>>(arena, imgs, aimgs, plans, ahdrs);
   k_alpha_finish<<<count, ALPHA_FINISH_THREADS, 0, s>>>(arena, imgs, aimgs, plans, ahdrs, alpha_arena);
+  k_alpha_smooth<<<count, ALPHA_FINISH_THREADS, 0, s>>>(imgs, aimgs, plans, ahdrs, alpha_arena);
 }

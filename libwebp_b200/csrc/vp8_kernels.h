@@ -57,6 +57,7 @@ typedef struct AlphaPlan {
   uint64_t tables;    // num_groups * group_entries words                 (after the header pass)
   uint64_t groups;    // num_groups AlGroup                               (after the header pass)
   uint64_t coded;     // xsize * height ARGB words                        (after the header pass)
+  uint64_t smooth;    // 2 * out_w * out_h bytes for alpha de-banding (ImgDesc::alpha_dither), 0 = none
 } AlphaPlan;
 void vp8k_alpha_header(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, const int* aimgs, const AlphaPlan* plans,
                        struct AlphaHdr* ahdrs, int count);

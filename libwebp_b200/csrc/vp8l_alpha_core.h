@@ -819,4 +819,78 @@ AL_FN void alph_finish(const AlphaHdr* hd, const uint8_t* raw /* method 0 */, ui
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// options.alpha_dithering_strength on planes whose levels the encoder quantised (ALPH header pre-processing = 1):
+// WebPDequantizeLevels (src/utils/quant_levels_dec_utils.c:262-291; alpha_dec.c:200-230 applies it to the crop
+// window of the finished plane). A (2r+1)^2 box average, r = 4 * strength / 100, pulls every pixel that is neither the
+// plane's minimum nor its maximum towards the local mean through a correction curve that vanishes beyond the
+// smallest distance between two used levels. The reference runs it as a rolling integral image in 16-bit modular
+// arithmetic; the same numbers fall out of: (1) per row, prefix sums modulo 2^16 (`pre`, w x h uint16 of scratch);
+// (2) per pixel, the sum of those over the 2r+1 rows around it (rows above the top replicate row 0; the last r rows
+// are never filtered, exactly like the reference's loop) at the two or three columns its HFilter looks at.
+// One thread block per plane; lut = 2047 int16 of shared memory, used = 256 bytes of shared memory.
+AL_FN void alph_smooth(uint8_t* plane, int stride, int w, int h, int strength, uint16_t* pre, int16_t* lut, uint32_t* used,
+                       int tid, int nt) {
+  int radius = 4 * strength / 100;
+  if (strength < 0 || strength > 100 || w <= 0 || h <= 0) return;
+  if (2 * radius + 1 > w) radius = (w - 1) >> 1;
+  if (2 * radius + 1 > h) radius = (h - 1) >> 1;
+  if (radius <= 0) return;
+  const int r = radius, R = 2 * r + 1;
+  // ---- CountLevels (quant_levels_dec_utils.c:178-210)
+  for (int k = tid; k < 256; k += nt) used[k] = 0;
+  AL_BLOCK_SYNC();
+  for (size_t i = (size_t)tid; i < (size_t)w * (size_t)h; i += (size_t)nt) used[plane[(i / (size_t)w) * (size_t)stride + (i % (size_t)w)]] = 1;
+  AL_BLOCK_SYNC();
+  int vmin = 255, vmax = 0, num_levels = 0, last = -1;
+  for (int k = 0; k < 256; ++k) if (used[k]) { if (k < vmin) vmin = k; if (k > vmax) vmax = k; }
+  int min_dist = vmax - vmin;
+  for (int k = 0; k < 256; ++k) if (used[k]) { ++num_levels; if (last >= 0 && k - last < min_dist) min_dist = k - last; last = k; }
+  if (num_levels <= 2) return;
+  // ---- InitCorrectionLUT (:160-176), lut[i + 1023] = correction for a difference of i quarter-levels
+  {
+    const int threshold1 = min_dist << 2, threshold2 = (3 * threshold1) >> 2, delta = threshold1 - threshold2;
+    for (int i = 1 + tid; i <= 1023; i += nt) {
+      int c = (i <= threshold2) ? i : (i < threshold1) ? threshold2 * (threshold1 - i) / delta : 0;
+      c >>= 2;
+      lut[1023 + i] = (int16_t)c; lut[1023 - i] = (int16_t)-c;
+    }
+    if (tid == 0) lut[1023] = 0;
+  }
+  // ---- prefix sums of every row, modulo 2^16 (VFilter's `sum`, :79-91)
+  for (int y = tid; y < h; y += nt) {
+    const uint8_t* row = plane + (size_t)y * stride;
+    uint16_t* o = pre + (size_t)y * w;
+    uint32_t acc = 0;
+    for (int x = 0; x < w; ++x) { acc += row[x]; o[x] = (uint16_t)acc; }
+  }
+  AL_BLOCK_SYNC();
+  // ---- HFilter + ApplyFilter (:104-154) for the rows the reference's loop reaches
+  const uint32_t scale = (uint32_t)((1 << 18) / (R * R));
+  const int rows_out = h - r;
+  for (size_t i = (size_t)tid; i < (size_t)w * (size_t)rows_out; i += (size_t)nt) {
+    const int x = (int)(i % (size_t)w), d = (int)(i / (size_t)w);
+    int xa, xb, xc = -1;   // delta = in[xa] + in[xb] (left), in[xa] - in[xb] (middle), 2 * in[w-1] - in[xb] - in[xc] (right)
+    int kind;
+    if (x <= r) { kind = 0; xa = x + r - 1; xb = r - x; }
+    else if (x < w - r) { kind = 1; xa = x + r; xb = x - r - 1; }
+    else { kind = 2; xa = w - 1; xb = 2 * w - 2 - r - x; xc = x - r - 1; }
+    uint32_t sa = 0, sb = 0, sc = 0;
+    for (int j = d - r; j <= d + r; ++j) {
+      const uint16_t* prow = pre + (size_t)(j < 0 ? 0 : j) * w;
+      sa += prow[xa]; sb += prow[xb];
+      if (kind == 2) sc += prow[xc];
+    }
+    const uint16_t delta = (uint16_t)(kind == 0 ? sa + sb : kind == 1 ? sa - sb : 2u * sa - sb - sc);
+    const uint16_t average = (uint16_t)(((uint32_t)delta * scale) >> 16);
+    uint8_t* px = plane + (size_t)d * stride + x;
+    const int v = *px;
+    if (v < vmax && v > vmin) {
+      const int c = v + (int)lut[1023 + (int)average - (v << 2)];
+      *px = (uint8_t)(c < 0 ? 0 : c > 255 ? 255 : c);
+    }
+  }
+  AL_BLOCK_SYNC();
+}
+
 #endif  // LIBWEBP_B200_VP8L_ALPHA_CORE_H_

@@ -42,7 +42,7 @@ extern "C" int emu_decode_window(const uint8_t* data, size_t size, int csp, int 
 // options.use_scaling: the (cropped) picture rescaled to scaled_w x scaled_h (both given); `stride` and `out` describe
 // the scaled picture.
 // options.dithering_strength = strength (0..100) on the whole picture.
-static int g_emu_dither_f = 0;
+static int g_emu_dither_f = 0, g_emu_alpha_dither = 0;
 extern "C" int emu_decode_dithered(const uint8_t* data, size_t size, int csp, int flags, uint8_t* out, size_t out_size,
                                    int stride, int strength, int crop_x, int crop_y, int crop_w, int crop_h);
 
@@ -286,6 +286,13 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
     if (ah.status != AL_OK) return ah.status;
     alpha_plane.assign((size_t)im.width * im.height, 0);
     alph_finish(&ah, alph + 1, coded.data(), tdata.data(), im.width, im.height, im.crop_y, alpha_plane.data(), 0, 1);
+    if (g_emu_alpha_dither > 0 && ((alph[0] >> 4) & 3) == 1) {   // options.alpha_dithering_strength, alpha_dec.c:200-230
+      std::vector<uint16_t> pre((size_t)im.out_w * im.out_h);
+      std::vector<int16_t> lut(2047);
+      uint32_t used[256];
+      alph_smooth(alpha_plane.data() + (size_t)im.crop_y * im.width + im.crop_x, im.width, im.out_w, im.out_h,
+                  g_emu_alpha_dither > 100 ? 100 : g_emu_alpha_dither, pre.data(), lut.data(), used, 0, 1);
+    }
     alpha = alpha_plane.data();
   }
 
@@ -317,6 +324,8 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
   }
   return VP8_STATUS_OK;
 }
+
+extern "C" void emu_set_alpha_dithering(int strength) { g_emu_alpha_dither = strength; }
 
 extern "C" int emu_decode_dithered(const uint8_t* data, size_t size, int csp, int flags, uint8_t* out, size_t out_size,
                                    int stride, int strength, int crop_x, int crop_y, int crop_w, int crop_h) {

@@ -232,3 +232,51 @@ def test_emu_dithering_matches_reference(ref):
                                                strength, c[0], c[1], c[2], c[3])
                     assert st == s_ref == 0 and np.array_equal(out[:n], want), (q, segs, flt, strength, crop, csp)
     assert changed > 10000   # the cases do exercise the dithering
+
+
+def test_emu_alpha_dithering_matches_reference(ref, amanifest):
+    """options.alpha_dithering_strength (dwebp's default is 100) on ALPH planes whose levels the encoder quantised
+    (alpha_q < 100: ALPH header pre-processing = 1, alpha_dec.c:200-230): WebPDequantizeLevels on the crop window of the
+    finished plane (quant_levels_dec_utils.c:262-291). Smooth alpha ramps so that the box average does move pixels; several
+    strengths (radius 0..4), crop windows smaller than the filter, premultiplied and plain output, MODE_YUVA."""
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR])
+    L = C.CDLL(os.path.join(EMU_DIR, "libvp8_emu.so"))
+    L.emu_decode_window.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_int]
+    L.emu_set_alpha_dithering.argtypes = [C.c_int]
+    rng = np.random.default_rng(77)
+    cases = [e["data"] for e in amanifest]
+    for k, (w, h, aq) in enumerate(((160, 120, 30), (97, 203, 60), (64, 64, 10), (300, 40, 80), (33, 9, 50))):
+        y, x = np.mgrid[0:h, 0:w].astype(np.float64)
+        pix = np.zeros((h, w, 4), np.uint8)
+        pix[..., :3] = ref.synth(w, h, 500 + k)
+        pix[..., 3] = np.clip(128 + 120 * np.sin(x * 0.03 + k) * np.cos(y * 0.025), 0, 255)
+        cases.append(ref.encode(pix, ref.EncCfg(80, 4, alpha_quality=aq, alpha_filtering=k % 3)))
+    changed = 0
+    try:
+        for data in cases:
+            st0, f = ref.features(data)
+            W, H = f["width"], f["height"]
+            for strength in (100, 50, 30, 20, 150):
+                L.emu_set_alpha_dithering(strength)
+                for it in range(3):
+                    crop = None
+                    if it > 0:
+                        cw, ch = int(rng.integers(1, W + 1)), int(rng.integers(1, H + 1))
+                        if it == 2:
+                            cw, ch = min(cw, 7), min(ch, 5)
+                        crop = (int(rng.integers(0, W - cw + 1)), int(rng.integers(0, H - ch + 1)), cw, ch)
+                    ow, oh = (crop[2], crop[3]) if crop else (W, H)
+                    for csp in (1, 7, 12):
+                        s_ref, want = ref.decode_dithered(data, csp, 0, crop, 0, strength)
+                        _, plain = ref.decode_dithered(data, csp, 0, crop, 0, 0)
+                        changed += int((want != plain).sum())
+                        n = want.size
+                        out = np.zeros(max(n, 16), np.uint8)
+                        c = crop or (0, 0, 0, 0)
+                        st = L.emu_decode_window(data, len(data), csp, 0, out.ctypes.data, out.size, ow if csp == 12 else ow * 4,
+                                                 c[0], c[1], c[2], c[3])
+                        assert st == s_ref == 0 and np.array_equal(out[:n], want), (len(data), strength, crop, csp)
+    finally:
+        L.emu_set_alpha_dithering(0)
+    assert changed > 10000   # the cases do exercise the de-banding

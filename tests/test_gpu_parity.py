@@ -132,8 +132,8 @@ def test_waves_small_scratch(W, port, manifest):
 def test_dithering(W, ref, manifest, amanifest):
     """options.dithering_strength on the device (dwebp's default is 50): identical to the reference where it changes
     pixels (smooth pictures at fine quantisers, both loop filters, crop windows) and where it does not (the manifest);
-    options.alpha_dithering_strength (dwebp: 100) is a no-op unless the encoder quantised the alpha levels, which is
-    the one case refused."""
+    options.alpha_dithering_strength (dwebp: 100) is a no-op unless the encoder quantised the alpha levels; where it
+    did, the plane is de-banded on the device exactly like WebPDequantizeLevels (k_alpha_smooth)."""
     from conftest import smooth_image
     for e in manifest:
         st, out = W.WebPDecode(e["data"], W.MODE_RGBA, dithering_strength=50)
@@ -160,12 +160,15 @@ def test_dithering(W, ref, manifest, amanifest):
     for e in amanifest:
         i = e["data"].find(b"ALPH")
         quantised = ((e["data"][i + 8] >> 4) & 3) == 1
-        st, out = W.WebPDecode(e["data"], W.MODE_RGBA, dithering_strength=50, alpha_dithering_strength=100)
-        if quantised:
-            assert st == W.VP8_STATUS_UNSUPPORTED_FEATURE, e["file"]
-        else:
-            s_ref, want = ref.decode_dithered(e["data"], W.MODE_RGBA, 0, None, 50, 100)
-            assert st == s_ref == 0 and np.array_equal(out.reshape(-1)[:want.size], want), e["file"]
+        for csp, crop, ad in ((W.MODE_RGBA, None, 100), (W.MODE_rgbA, (3, 5, 90, 60), 50), (W.MODE_YUVA, None, 30)):
+            if crop is not None and (e["features"]["width"] < 100 or e["features"]["height"] < 70):
+                crop = None
+            st, out = W.WebPDecode(e["data"], csp, dithering_strength=50, alpha_dithering_strength=ad, crop=crop)
+            s_ref, want = ref.decode_dithered(e["data"], csp, 0, crop, 50, ad)
+            assert st == s_ref == 0 and np.array_equal(out.reshape(-1)[:want.size], want), (e["file"], csp, crop, ad)
+            if quantised and csp == W.MODE_RGBA:
+                _, plain = ref.decode_dithered(e["data"], csp, 0, crop, 50, 0)
+                assert (want != plain).any(), e["file"]     # the de-banding does move pixels on these planes
 
 
 def test_full_size_batch_properties(W, ref):
