@@ -19,8 +19,23 @@ VP8CPUInfo VP8GetCPUInfo = NoCpuFeature;
 
 int WebPGetDecoderVersion(void) { return (1 << 16) | (3 << 8) | 2; }
 
-void* WebPMalloc(size_t size) { return malloc(size); }
-void WebPFree(void* ptr) { free(ptr); }
+/* src/utils/utils.c:171-231. The three WebPSafe* entry points are WEBP_EXTERN in the reference (src/utils/utils.h:52-61)
+ * because libwebpdemux and libwebpmux allocate through the library they are linked beside; exported here so that the
+ * reference's demuxer / WebPAnimDecoder link against this library alone (oracle/Makefile: libanim_b200.so). */
+#define WEBP_B200_MAX_ALLOCABLE_MEMORY (1ULL << 34)   /* utils.h:44: WEBP_MAX_ALLOCABLE_MEMORY on 64-bit hosts */
+static int alloc_args_ok(uint64_t nmemb, size_t size) {
+  if (nmemb == 0) return 1;
+  if ((uint64_t)size > WEBP_B200_MAX_ALLOCABLE_MEMORY / nmemb) return 0;
+  return 1;   /* size_t is 64-bit on every host this library builds for: nmemb * size <= 2^34 fits */
+}
+WEBP_EXTERN void* WebPSafeMalloc(uint64_t nmemb, size_t size);
+WEBP_EXTERN void* WebPSafeCalloc(uint64_t nmemb, size_t size);
+WEBP_EXTERN void WebPSafeFree(void* const ptr);
+void* WebPSafeMalloc(uint64_t nmemb, size_t size) { return alloc_args_ok(nmemb, size) ? malloc((size_t)(nmemb * size)) : NULL; }
+void* WebPSafeCalloc(uint64_t nmemb, size_t size) { return alloc_args_ok(nmemb, size) ? calloc((size_t)nmemb, size) : NULL; }
+void WebPSafeFree(void* const ptr) { free(ptr); }
+void* WebPMalloc(size_t size) { return WebPSafeMalloc(1, size); }
+void WebPFree(void* ptr) { WebPSafeFree(ptr); }
 
 int WebPInitDecBufferInternal(WebPDecBuffer* buffer, int version) {
   if (WEBP_ABI_IS_INCOMPATIBLE(version, WEBP_DECODER_ABI_VERSION)) return 0;

@@ -221,3 +221,60 @@ def decode_bench(datas, nthreads, csp=MODE_RGBA, passes=1, simd=True):
     L.reft_set_simd(1)
     return dict(seconds=sec, mpix_per_pass=mpix.value, mpix_s=mpix.value * passes / max(sec, 1e-12),
                 errors=errs.value, threads=nthreads)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Animated WebP (oracle/animtool.c): the reference's WebPAnimEncoder / WebPAnimDecoder, and the same WebPAnimDecoder objects
+# relinked over the CUDA decoder (oracle/_ref/libanim_b200.so) -- tests only.
+REF_DIR = os.path.dirname(LIB_PATH)
+ANIM_B200_PATH = os.path.join(REF_DIR, "libanim_b200.so")
+DWEBP_REF = os.path.join(REF_DIR, "dwebp_ref")
+DWEBP_B200 = os.path.join(REF_DIR, "dwebp_b200")
+_anim = {}
+
+
+def _anim_lib(which):
+    """which = 'reft' (everything is the reference) or 'b200' (reference demuxer + WebPAnimDecoder over libwebpdecoder_b200)."""
+    if which not in _anim:
+        L = lib() if which == "reft" else C.CDLL(ANIM_B200_PATH)
+        for name, res, args in (("anim_decoder_library", C.c_char_p, []),
+                                ("anim_info", C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_int)]),
+                                ("anim_decode_all", C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)])):
+            fn = getattr(L, f"{which}_{name}")
+            fn.restype, fn.argtypes = res, args
+        _anim[which] = L
+    return _anim[which]
+
+
+def anim_encode(frames, quality=75.0, method=4, kmin=3, kmax=5, minimize_size=0):
+    """frames: (n, h, w, 4) uint8 RGBA -> animated WebP bytes, every frame lossy (reference WebPAnimEncoder)."""
+    L = lib()
+    L.reft_anim_encode.restype = C.c_size_t
+    L.reft_anim_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.POINTER(C.c_void_p)]
+    frames = np.ascontiguousarray(frames)
+    n, h, w, _ = frames.shape
+    p = C.c_void_p()
+    size = L.reft_anim_encode(frames.ctypes.data, n, w, h, quality, method, kmin, kmax, minimize_size, C.byref(p))
+    if size == 0:
+        raise RuntimeError("WebPAnimEncoder failed")
+    data = C.string_at(p, size)
+    L.reft_free(p)
+    return data
+
+
+def anim_decoder_library(which="reft"):
+    return getattr(_anim_lib(which), f"{which}_anim_decoder_library")().decode()
+
+
+def anim_decode(data, csp=MODE_RGBA, which="reft"):
+    """-> (frames delivered or -1 - delivered on failure, (n, h, w, 4) uint8 canvases, time stamps)."""
+    L = _anim_lib(which)
+    info = (C.c_int * 3)()
+    if not getattr(L, f"{which}_anim_info")(data, len(data), info):
+        return -1, None, None
+    w, h, n = info[0], info[1], info[2]
+    out = np.zeros((max(n, 1), h, w, 4), np.uint8)
+    ts = (C.c_int * max(n, 1))()
+    got = getattr(L, f"{which}_anim_decode_all")(data, len(data), csp, out.ctypes.data, out.size, ts)
+    return got, out, list(ts)
