@@ -21,7 +21,7 @@ int WebPGetDecoderVersion(void) { return (1 << 16) | (3 << 8) | 2; }
 
 /* src/utils/utils.c:171-231. The three WebPSafe* entry points are WEBP_EXTERN in the reference (src/utils/utils.h:52-61)
  * because libwebpdemux and libwebpmux allocate through the library they are linked beside; exported here so that the
- * reference's demuxer / WebPAnimDecoder link against this library alone (oracle/Makefile: libanim_b200.so). */
+ * reference's demuxer / WebPAnimDecoder link against this library alone. */
 #define WEBP_B200_MAX_ALLOCABLE_MEMORY (1ULL << 34)   /* utils.h:44: WEBP_MAX_ALLOCABLE_MEMORY on 64-bit hosts */
 static int alloc_args_ok(uint64_t nmemb, size_t size) {
   if (nmemb == 0) return 1;
