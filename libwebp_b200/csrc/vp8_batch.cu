@@ -242,6 +242,7 @@ struct WebPBatch {
   Owned d_in, d_imgs, d_hdrs, d_ids, d_mbinfo, d_coeffs, d_yuv, d_out;
   Owned d_dither; // options.dithering_strength: 128 offsets per macroblock of a wave (allocated when an item asks for it)
   bool any_dither = false;
+  bool any_lossless = false;   // whole-picture VP8L images ride the ALPH machinery (VP8B_FLAG_LOSSLESS)
   Owned d_band;   // row bands: TokResume[m] | uint16 top contexts [m][max_mb_w] | unfiltered top pixels [m][32 * max_mb_w]
   // images with an ALPH chunk
   std::vector<int> aimgs;              // their image indices
@@ -272,12 +273,13 @@ static VP8StatusCode plan_item(WebPBatchItem* it, const WebPBatchOptions& opt, V
   st = (VP8StatusCode)vp8b_parse_container(it->data, it->data_size, 1, c);
   if (st != VP8_STATUS_OK) return st;
   if (c->has_animation) return VP8_STATUS_UNSUPPORTED_FEATURE;             // webp_dec.c:427-429
-  if (c->is_lossless) return VP8_STATUS_UNSUPPORTED_FEATURE;               // lossless: not on this path
-  if (c->part0_size > c->frame_size - 10) return VP8_STATUS_NOT_ENOUGH_DATA;   // vp8_dec.c:345-348
+  if (!c->is_lossless && c->part0_size > c->frame_size - 10) return VP8_STATUS_NOT_ENOUGH_DATA;   // vp8_dec.c:345-348
   const WebPDecoderOptions* o = &cfg->options;
   const int csp = cfg->output.colorspace;
   if (csp < MODE_RGB || csp >= MODE_LAST) return VP8_STATUS_INVALID_PARAM;
   if (!csp_supported(csp)) return VP8_STATUS_UNSUPPORTED_FEATURE;
+  // whole-picture VP8L (vp8l_lossless_core.h): the RGB family at the picture's own size; YUV output and the rescaler are not built
+  if (c->is_lossless && (csp == MODE_YUV || csp == MODE_YUVA || o->use_scaling)) return VP8_STATUS_UNSUPPORTED_FEATURE;
   int ow = c->width, oh = c->height;
   if (o->use_cropping) {   // WebPAllocateDecBuffer, buffer_dec.c:184-195 (x, y snapped to even like the decoder's own io)
     const int x = o->crop_left & ~1, y = o->crop_top & ~1;
@@ -357,7 +359,7 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
     d.vp8_size = (uint32_t)c.frame_size;
     d.part0_size = c.part0_size;
     d.width = (uint16_t)c.width; d.height = (uint16_t)c.height;
-    d.mb_w = (uint16_t)((c.width + 15) >> 4); d.mb_h = (uint16_t)((c.height + 15) >> 4);
+    if (!c.is_lossless) { d.mb_w = (uint16_t)((c.width + 15) >> 4); d.mb_h = (uint16_t)((c.height + 15) >> 4); }
     d.csp = (uint8_t)cfg->output.colorspace;
     d.flags = (uint8_t)((cfg->options.bypass_filtering ? VP8B_FLAG_BYPASS_FILTER : 0) |
                         (cfg->options.no_fancy_upsampling ? VP8B_FLAG_NO_FANCY : 0) |
@@ -366,6 +368,8 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
     if (cfg->options.use_cropping) {
       d.crop_x = (uint16_t)(cfg->options.crop_left & ~1); d.crop_y = (uint16_t)(cfg->options.crop_top & ~1);
       d.out_w = (uint16_t)cfg->options.crop_width; d.out_h = (uint16_t)cfg->options.crop_height;
+      // a lossless picture is cropped where the caller said (WebPIoInitFromOptions only snaps YUV420 sources, webp_dec.c:816-820)
+      if (c.is_lossless) { d.crop_x = (uint16_t)cfg->options.crop_left; d.crop_y = (uint16_t)cfg->options.crop_top; }
     }
     int fw = d.out_w, fh = d.out_h;   // the picture that leaves the device
     if (cfg->options.use_scaling) {
@@ -377,9 +381,17 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
     const int ds = cfg->options.dithering_strength;
     d.dither_f = (uint8_t)(ds < 0 ? 0 : ds > 100 ? 255 : ds * 255 / 100);
     if (d.dither_f != 0) b->any_dither = true;
-    d.num_parts = (uint8_t)vp8b_prescan_partitions(b->items[i].data + c.frame_offset + 10, c.part0_size);
+    d.num_parts = c.is_lossless ? 0 : (uint8_t)vp8b_prescan_partitions(b->items[i].data + c.frame_offset + 10, c.part0_size);
     d.alpha_plane = VP8B_NO_ALPHA;
-    if (c.has_alph_chunk) {
+    if (c.is_lossless) {   // the VP8L passes find the bitstream through the alpha fields; no VP8 kernel touches the image
+      d.flags |= VP8B_FLAG_LOSSLESS;
+      d.dither_f = 0;
+      d.alpha_in = d.in_off;
+      d.alpha_size = (uint32_t)c.frame_size;
+      d.alpha_index = (uint32_t)b->aimgs.size();
+      b->aimgs.push_back((int)b->imgs.size());
+      b->any_lossless = true;
+    } else if (c.has_alph_chunk) {
       d.alpha_in = ranges[item_range[i]].dev_off + (size_t)(b->items[i].data - ranges[item_range[i]].base) + c.alpha_offset;
       d.alpha_size = (uint32_t)c.alpha_size;
       d.alpha_index = (uint32_t)b->aimgs.size();
@@ -697,6 +709,7 @@ static bool batch_alpha(WebPBatch* b) {
         grp[a] = work2; work2 += align_up((size_t)h.num_groups * sizeof(AlGroup), 256);
         cod[a] = work2; work2 += align_up(4 * ((size_t)h.xsize * d.height + 4), 256);
       }
+      if (d.flags & VP8B_FLAG_LOSSLESS) continue;   // its pixels go straight to the output arena (vp8k_lossless_finish)
       if (d.alpha_dither != 0) { smo[a] = work2 + 1; work2 += align_up(2 * (size_t)d.out_w * d.out_h + 16, 256); }   // +1: 0 means none
       d.alpha_plane = planes;
       planes += align_up((size_t)d.width * d.height, 256);
@@ -715,6 +728,8 @@ static bool batch_alpha(WebPBatch* b) {
   }
   vp8k_alpha_decode(s, arena, (const ImgDesc*)b->d_imgs.p, (const int*)b->d_aimgs.p, (const AlphaPlan*)b->d_aplans.p,
                     (AlphaHdr*)b->d_ahdrs.p, (uint8_t*)b->d_alpha.p, na);
+  if (b->any_lossless) vp8k_lossless_finish(s, (const ImgDesc*)b->d_imgs.p, (const int*)b->d_aimgs.p, (const AlphaPlan*)b->d_aplans.p,
+                                            (const AlphaHdr*)b->d_ahdrs.p, (uint8_t*)b->d_out.p, na);
   CU_TRY(cudaMemcpyAsync(b->ahdrs.data(), b->d_ahdrs.p, sizeof(AlphaHdr) * na, cudaMemcpyDeviceToHost, s), "D2H alpha status");
   return true;
 }
@@ -879,6 +894,12 @@ static bool batch_decode(WebPBatch* b, bool download) {
   for (int k = 0; k < m; ++k) {
     WebPBatchItem* it = &b->items[b->img_item[k]];
     it->status = (VP8StatusCode)b->statuses[k];
+    if (b->imgs[k].flags & VP8B_FLAG_LOSSLESS) {
+      // every failure of a whole-picture VP8L decode is a bitstream error (vp8l_dec.c:1292,1479-1488: nothing suspends
+      // outside the incremental decoder); the two limits of vp8l_alpha_core.h stay UNSUPPORTED_FEATURE
+      const int ls = b->ahdrs[b->imgs[k].alpha_index].status;
+      it->status = ls == AL_OK ? VP8_STATUS_OK : ls == AL_UNSUPPORTED ? VP8_STATUS_UNSUPPORTED_FEATURE : VP8_STATUS_BITSTREAM_ERROR;
+    } else
     // a lost alpha plane loses the image (frame_dec.c:452-460), unless the VP8 stream had already failed
     if (it->status == VP8_STATUS_OK && b->imgs[k].alpha_size != 0) it->status = (VP8StatusCode)b->ahdrs[b->imgs[k].alpha_index].status;
     if (it->status != VP8_STATUS_OK && b->opt.output == WEBP_BATCH_HOST) WebPFreeDecBuffer(&it->config->output);

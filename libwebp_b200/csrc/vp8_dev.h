@@ -25,11 +25,14 @@
 #define VP8B_BITSTREAM_ERROR 3
 #define VP8B_UNSUPPORTED 4
 #define VP8B_NOT_ENOUGH_DATA 7
+#define VP8B_NOT_A_VP8_FRAME (-2)   // FrameHdr::status of a VP8B_FLAG_LOSSLESS image (never leaves the library)
 
 // ImgDesc::flags
 #define VP8B_FLAG_BYPASS_FILTER 1
 #define VP8B_FLAG_NO_FANCY 2
 #define VP8B_FLAG_FLIP 4     // options.flip: output rows bottom-up (WebPFlipBuffer, buffer_dec.c:152-175)
+#define VP8B_FLAG_LOSSLESS 8 // a whole VP8L picture: no macroblocks (mb_w = mb_h = 0, the VP8 kernels pass it by); alpha_in /
+                             // alpha_size locate the VP8L bitstream and the picture leaves through vp8l_lossless_core.h
 
 typedef struct ImgDesc {
   uint64_t in_off;     // byte offset of the VP8 frame tag inside the input arena

@@ -32,6 +32,7 @@
 #include "vp8_tokens_lockstep.h"
 #define AL_BLOCK_SYNC() __syncthreads()
 #include "vp8l_alpha_core.h"
+#include "vp8l_lossless_core.h"
 
 // ---------------------------------------------------------------------------------------------------------
 #define MODES_WARPS 28   // one image per warp, seven per SM sub-partition (see k_parse_tokens)
@@ -47,6 +48,9 @@ __global__ void __launch_bounds__(32 * MODES_WARPS, 1) k_parse_modes(const uint8
   if (i >= count || (threadIdx.x & 31) != 0) return;
   const ImgDesc im = imgs[first + i];
   FrameHdr* h = &hdrs[first + i];
+  // a whole-picture VP8L image has no VP8 frame: a status that is not OK makes every pixel kernel pass it by; its own
+  // status comes from the VP8L passes (k_alpha_header / k_alpha_pixels / k_lossless_finish)
+  if (im.flags & VP8B_FLAG_LOSSLESS) { h->status = VP8B_NOT_A_VP8_FRAME; return; }
   BoolDec br;
   int st = parse_frame_header(br, arena + im.in_off, im, h);
   if (st == VP8B_OK) st = parse_intra_modes(br, im, h, top_modes_all + (size_t)warp * max_mb_w, bprob, mbinfo + 4 * (size_t)im.mb_base);
@@ -740,7 +744,7 @@ __global__ void __launch_bounds__(32) k_alpha_header(const uint8_t* __restrict__
   const ImgDesc im = imgs[aimgs[a]];
   const AlphaPlan pl = plans[a];
   alph_parse_header(arena + im.alpha_in, im.alpha_size, im.width, im.height, (uint8_t*)pl.scratch, (uint16_t*)pl.meta,
-                    (uint32_t*)pl.tdata, &ahdrs[a]);
+                    (uint32_t*)pl.tdata, &ahdrs[a], (im.flags & VP8B_FLAG_LOSSLESS) ? 1 : 0);
 }
 
 __global__ void __launch_bounds__(32) k_alpha_pixels(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
@@ -785,6 +789,18 @@ __global__ void __launch_bounds__(ALPHA_FINISH_THREADS) k_alpha_smooth(const Img
               (uint16_t*)pl.smooth, lut, used, (int)threadIdx.x, (int)blockDim.x);
 }
 
+// Whole-picture VP8L (vp8l_lossless_core.h): inverse transforms, palette, colourspace conversion into the output arena.
+__global__ void __launch_bounds__(ALPHA_FINISH_THREADS) k_lossless_finish(const ImgDesc* __restrict__ imgs, const int* __restrict__ aimgs,
+                                                                          const AlphaPlan* __restrict__ plans, const AlphaHdr* __restrict__ ahdrs,
+                                                                          uint8_t* out) {
+  const int a = blockIdx.x;
+  const AlphaHdr* hd = &ahdrs[a];
+  if (hd->status != AL_OK || !hd->lossless) return;
+  const ImgDesc im = imgs[aimgs[a]];
+  const AlphaPlan pl = plans[a];
+  vp8l_finish_picture(hd, im, (uint32_t*)pl.coded, (const uint32_t*)pl.tdata, out + im.out_off, (int)threadIdx.x, (int)blockDim.x);
+}
+
 extern "C" void vp8k_alpha_header(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, const int* aimgs, const AlphaPlan* plans,
                                   AlphaHdr* ahdrs, int count) {
   k_alpha_header<<<count, 32, 0, s>>>(arena, imgs, aimgs, plans, ahdrs);
@@ -794,4 +810,8 @@ extern "C" void vp8k_alpha_decode(cudaStream_t s, const uint8_t* arena, const Im
   k_alpha_pixels<<<count, 32, 0, s>>>(arena, imgs, aimgs, plans, ahdrs);
   k_alpha_finish<<<count, ALPHA_FINISH_THREADS, 0, s>>>(arena, imgs, aimgs, plans, ahdrs, alpha_arena);
   k_alpha_smooth<<<count, ALPHA_FINISH_THREADS, 0, s>>>(imgs, aimgs, plans, ahdrs, alpha_arena);
+}
+extern "C" void vp8k_lossless_finish(cudaStream_t s, const ImgDesc* imgs, const int* aimgs, const AlphaPlan* plans, const AlphaHdr* ahdrs,
+                                     uint8_t* out, int count) {
+  k_lossless_finish<<<count, ALPHA_FINISH_THREADS, 0, s>>>(imgs, aimgs, plans, ahdrs, out);
 }

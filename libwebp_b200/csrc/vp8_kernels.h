@@ -59,6 +59,8 @@ typedef struct AlphaPlan {
   uint64_t coded;     // xsize * height ARGB words                        (after the header pass)
   uint64_t smooth;    // 2 * out_w * out_h bytes for alpha de-banding (ImgDesc::alpha_dither), 0 = none
 } AlphaPlan;
+void vp8k_lossless_finish(cudaStream_t s, const ImgDesc* imgs, const int* aimgs, const AlphaPlan* plans, const struct AlphaHdr* ahdrs,
+                          uint8_t* out, int count);
 void vp8k_alpha_header(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, const int* aimgs, const AlphaPlan* plans,
                        struct AlphaHdr* ahdrs, int count);
 void vp8k_alpha_decode(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, const int* aimgs, const AlphaPlan* plans,

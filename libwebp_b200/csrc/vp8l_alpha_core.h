@@ -415,7 +415,8 @@ struct AlphaHdr {
   uint8_t ttype[4];         // transform types
   uint8_t tbits[4];         // tile bits (predictor, cross colour) or bundling bits (colour indexing)
   uint8_t use_8b;           // set by the pixel pass: the reference would have taken its 8-bit path (DecodeAlphaData)
-  uint8_t pad[2];
+  uint8_t lossless;         // the stream is a whole VP8L picture (5-byte header instead of the ALPH byte), see vp8l_lossless_core.h
+  uint8_t pad[1];
   int32_t txsize[4];        // image width the transform applies to
   uint32_t tdata[4];        // word offset of the transform's tile image inside the transform-data area
   int32_t xsize;            // width of the coded image (after bundling)
@@ -427,6 +428,7 @@ struct AlphaHdr {
   uint32_t br_pos;
   int32_t br_bit_pos;
   uint8_t palette_alpha[256];   // alpha (= green) of palette entry i, zero beyond the coded colours
+  uint32_t palette[256];        // the expanded colour map (ExpandColorMap, vp8l_dec.c:1305-1328), zero beyond the coded colours
 };
 
 #define AL_PASSA_FIXED_WORDS (AL_SUB_TABLE_ENTRIES + (1 << AL_MAX_CACHE_BITS) + 256)
@@ -440,26 +442,39 @@ struct AlphaHdr {
 // meta = 4 * AL_META_PIXELS_BOUND(w, h) bytes: decoded as 32-bit pixels, compacted in place to one uint16 group
 // index per meta pixel (kept for pass B). tdata = 2 * AL_META_PIXELS_BOUND(w, h) words for the tile images of the
 // predictor and cross-colour transforms (kept for alph_finish).
+// lossless != 0: `alph` is a whole VP8L picture (VP8LDecodeHeader, vp8l_dec.c:1672-1704): the reader starts at the
+// signature byte and ReadImageInfo (:115-124) takes 8 + 14 + 14 + 1 + 3 bits before the same image stream follows.
 AL_NOINLINE void alph_parse_header(const uint8_t* alph, uint32_t alph_size, int w, int h, uint8_t* scratch, uint16_t* meta,
-                                   uint32_t* tdata, AlphaHdr* hd) {
+                                   uint32_t* tdata, AlphaHdr* hd, int lossless = 0) {
   hd->status = AL_OUT_OF_MEMORY;   // every failure in here is a header failure (see the top of this file)
   hd->method = 0; hd->filter = 0; hd->ntrans = 0; hd->cache_bits = 0; hd->huff_bits = 0; hd->use_8b = 0;
+  hd->lossless = (uint8_t)(lossless != 0);
   hd->xsize = w; hd->huff_xsize = 0; hd->num_groups = 1; hd->group_entries = AL_GROUP_ENTRIES(0);
   hd->br_val = 0; hd->br_pos = 0; hd->br_bit_pos = 0;
-  if (alph_size <= 1) return;
-  const int method = alph[0] & 3, filter = (alph[0] >> 2) & 3, pre = (alph[0] >> 4) & 3, rsrv = (alph[0] >> 6) & 3;
-  if (method > 1 || pre > 1 || rsrv != 0) return;
-  hd->method = (uint8_t)method; hd->filter = (uint8_t)filter;
-  if (method == 0) {
-    if ((uint64_t)(alph_size - 1) >= (uint64_t)w * (uint64_t)h) hd->status = AL_OK;
-    return;
-  }
   uint32_t* tables = (uint32_t*)scratch;
   uint32_t* cache = tables + AL_SUB_TABLE_ENTRIES;
   uint32_t* pal = cache + (1 << AL_MAX_CACHE_BITS);
   AlScratch* sc = (AlScratch*)(pal + 256);
   LBits b;
-  lb_init(b, alph + 1, alph_size - 1);
+  if (!lossless) {
+    if (alph_size <= 1) return;
+    const int method = alph[0] & 3, filter = (alph[0] >> 2) & 3, pre = (alph[0] >> 4) & 3, rsrv = (alph[0] >> 6) & 3;
+    if (method > 1 || pre > 1 || rsrv != 0) return;
+    hd->method = (uint8_t)method; hd->filter = (uint8_t)filter;
+    if (method == 0) {
+      if ((uint64_t)(alph_size - 1) >= (uint64_t)w * (uint64_t)h) hd->status = AL_OK;
+      return;
+    }
+    lb_init(b, alph + 1, alph_size - 1);
+  } else {
+    hd->method = 1;
+    lb_init(b, alph, alph_size);
+    if (lb_read(b, 8) != 0x2f) return;
+    const int sw = (int)lb_read(b, 14) + 1, sh = (int)lb_read(b, 14) + 1;
+    lb_read(b, 1);   // alpha hint
+    if (lb_read(b, 3) != 0 || b.eos) return;
+    if (sw != w || sh != h) return;   // the container walk took the same fields (vp8_container.c)
+  }
   // transforms (ReadTransform, vp8l_dec.c:1330-1384); each type at most once
   int xsize = w;
   uint32_t seen = 0, tdata_used = 0;
@@ -483,10 +498,13 @@ AL_NOINLINE void alph_parse_header(const uint8_t* alph, uint32_t alph_size, int 
       hd->tbits[n] = (uint8_t)bits;
       if (!al_decode_subimage(b, num_colors, 1, pal, tables, cache, sc)) return;
       // ExpandColorMap (vp8l_dec.c:1305-1328): entries are byte-wise deltas; only green matters for alpha
-      uint32_t g = 0;
+      uint32_t g = 0, full = 0;
       for (int i = 0; i < 256; ++i) {
-        if (i < num_colors) { g = (g + ((pal[i] >> 8) & 0xff)) & 0xff; hd->palette_alpha[i] = (uint8_t)g; }
-        else hd->palette_alpha[i] = 0;
+        if (i < num_colors) {
+          g = (g + ((pal[i] >> 8) & 0xff)) & 0xff; hd->palette_alpha[i] = (uint8_t)g;
+          full = (((full & 0xff00ff00u) + (pal[i] & 0xff00ff00u)) & 0xff00ff00u) | (((full & 0x00ff00ffu) + (pal[i] & 0x00ff00ffu)) & 0x00ff00ffu);
+          hd->palette[i] = full;
+        } else { hd->palette_alpha[i] = 0; hd->palette[i] = 0; }
       }
       if (n != 0) unsupported = 1;   // pixels would have to widen between two in-place transforms
     }
@@ -533,7 +551,7 @@ AL_NOINLINE int alph_decode_pixels(const uint8_t* alph, uint32_t alph_size, int 
   uint32_t* cache = (uint32_t*)scratch + AL_SUB_TABLE_ENTRIES;
   AlScratch* sc = (AlScratch*)(cache + (1 << AL_MAX_CACHE_BITS) + 256);
   LBits b;
-  b.buf = alph + 1; b.len = alph_size - 1; b.val = hd->br_val; b.pos = hd->br_pos; b.bit_pos = hd->br_bit_pos; b.eos = 0;
+  b.buf = alph + (hd->lossless ? 0 : 1); b.len = alph_size - (hd->lossless ? 0u : 1u); b.val = hd->br_val; b.pos = hd->br_pos; b.bit_pos = hd->br_bit_pos; b.eos = 0;
   const int num_groups = hd->num_groups, stride = hd->group_entries, cache_bits = hd->cache_bits;
   // codes of every group (still part of the header as far as the status goes)
   for (int g = 0; g < num_groups; ++g) {
@@ -715,6 +733,40 @@ AL_FN void al_inverse_predictor(uint32_t* px, int width, int h, const uint32_t* 
 
 AL_FN int al_color_delta(int8_t pred, int8_t color) { return ((int)pred * (int)color) >> 5; }
 
+// The inverse transforms of a VP8L stream, last read first, in place on the coded ARGB words (VP8LInverseTransform,
+// lossless.c:391-442). COLOR_INDEXING is always transform 0 here and is folded into the caller's extraction.
+AL_FN void al_inverse_transforms(const AlphaHdr* hd, uint32_t* px, const uint32_t* tdata, int h, int tid, int nt) {
+  for (int n = (int)hd->ntrans - 1; n >= 0; --n) {
+    const int type = hd->ttype[n], bits = hd->tbits[n], tw = hd->txsize[n];
+    const uint32_t* tiles = tdata + hd->tdata[n];
+    const size_t count = (size_t)tw * (size_t)h;
+    if (type == AL_T_PREDICTOR) {
+      al_inverse_predictor(px, tw, h, tiles, bits, tid, nt);
+    } else if (type == AL_T_CROSS_COLOR) {   // ColorSpaceInverseTransform_C, lossless.c:284-338
+      const int tiles_per_row = (tw + (1 << bits) - 1) >> bits;
+      for (size_t i = (size_t)tid; i < count; i += (size_t)nt) {
+        const int x = (int)(i % (size_t)tw), y = (int)(i / (size_t)tw);
+        const uint32_t code = tiles[(size_t)(y >> bits) * tiles_per_row + (x >> bits)];
+        const uint32_t argb = px[i];
+        const int8_t green = (int8_t)(argb >> 8);
+        int new_red = (int)((argb >> 16) & 0xff), new_blue = (int)(argb & 0xff);
+        new_red = (new_red + al_color_delta((int8_t)(code & 0xff), green)) & 0xff;
+        new_blue += al_color_delta((int8_t)((code >> 8) & 0xff), green);
+        new_blue += al_color_delta((int8_t)((code >> 16) & 0xff), (int8_t)new_red);
+        new_blue &= 0xff;
+        px[i] = (argb & 0xff00ff00u) | ((uint32_t)new_red << 16) | (uint32_t)new_blue;
+      }
+    } else if (type == AL_T_SUBTRACT_GREEN) {   // VP8LAddGreenToBlueAndRed_C
+      for (size_t i = (size_t)tid; i < count; i += (size_t)nt) {
+        const uint32_t argb = px[i], green = (argb >> 8) & 0xff;
+        px[i] = (argb & 0xff00ff00u) | (((argb & 0x00ff00ffu) + ((green << 16) | green)) & 0x00ff00ffu);
+      }
+    }
+    // AL_T_COLOR_INDEXING is always transform 0 here and is folded into the extraction below
+    AL_BLOCK_SYNC();
+  }
+}
+
 // Coded ARGB plane (or the raw payload, method 0) -> the final w x h alpha plane: inverse transforms in place in
 // reverse reading order, palette/unbundle + green extraction, then the row unfilter in place. Runs on `nt`
 // cooperating threads of one block (tid = 0..nt-1; AL_BLOCK_SYNC between phases), or on one host thread (nt = 1)
@@ -733,35 +785,7 @@ AL_FN void alph_finish(const AlphaHdr* hd, const uint8_t* raw /* method 0 */, ui
   if (hd->method == 0) {
     for (size_t i = (size_t)tid; i < total; i += (size_t)nt) plane[i] = raw[i];
   } else {
-    for (int n = (int)hd->ntrans - 1; n >= 0; --n) {
-      const int type = hd->ttype[n], bits = hd->tbits[n], tw = hd->txsize[n];
-      const uint32_t* tiles = tdata + hd->tdata[n];
-      const size_t count = (size_t)tw * (size_t)h;
-      if (type == AL_T_PREDICTOR) {
-        al_inverse_predictor(px, tw, h, tiles, bits, tid, nt);
-      } else if (type == AL_T_CROSS_COLOR) {   // ColorSpaceInverseTransform_C, lossless.c:284-338
-        const int tiles_per_row = (tw + (1 << bits) - 1) >> bits;
-        for (size_t i = (size_t)tid; i < count; i += (size_t)nt) {
-          const int x = (int)(i % (size_t)tw), y = (int)(i / (size_t)tw);
-          const uint32_t code = tiles[(size_t)(y >> bits) * tiles_per_row + (x >> bits)];
-          const uint32_t argb = px[i];
-          const int8_t green = (int8_t)(argb >> 8);
-          int new_red = (int)((argb >> 16) & 0xff), new_blue = (int)(argb & 0xff);
-          new_red = (new_red + al_color_delta((int8_t)(code & 0xff), green)) & 0xff;
-          new_blue += al_color_delta((int8_t)((code >> 8) & 0xff), green);
-          new_blue += al_color_delta((int8_t)((code >> 16) & 0xff), (int8_t)new_red);
-          new_blue &= 0xff;
-          px[i] = (argb & 0xff00ff00u) | ((uint32_t)new_red << 16) | (uint32_t)new_blue;
-        }
-      } else if (type == AL_T_SUBTRACT_GREEN) {   // VP8LAddGreenToBlueAndRed_C
-        for (size_t i = (size_t)tid; i < count; i += (size_t)nt) {
-          const uint32_t argb = px[i], green = (argb >> 8) & 0xff;
-          px[i] = (argb & 0xff00ff00u) | (((argb & 0x00ff00ffu) + ((green << 16) | green)) & 0x00ff00ffu);
-        }
-      }
-      // AL_T_COLOR_INDEXING is always transform 0 here and is folded into the extraction below
-      AL_BLOCK_SYNC();
-    }
+    al_inverse_transforms(hd, px, tdata, h, tid, nt);
     const int has_palette = hd->ntrans > 0 && hd->ttype[0] == AL_T_COLOR_INDEXING;
     const int bits = has_palette ? hd->tbits[0] : 0, bpp = 8 >> bits;
     const int xs = hd->xsize;

@@ -109,6 +109,7 @@ typedef struct {
   float quality;
   int method, segments, filter_type, filter_strength, filter_sharpness, partitions, low_memory;
   int alpha_filtering, alpha_quality, sns_strength;
+  int lossless;   // 1: VP8L (quality / method then steer the lossless encoder's effort)
 } ReftEncCfg;
 
 size_t reft_encode(const uint8_t* pix, int w, int h, int bpp, const ReftEncCfg* c, uint8_t** out) {
@@ -129,8 +130,10 @@ size_t reft_encode(const uint8_t* pix, int w, int h, int bpp, const ReftEncCfg* 
   if (c->alpha_filtering >= 0) config.alpha_filtering = c->alpha_filtering;
   if (c->alpha_quality >= 0) config.alpha_quality = c->alpha_quality;
   if (c->sns_strength >= 0) config.sns_strength = c->sns_strength;
+  if (c->lossless > 0) config.lossless = 1;
   if (!WebPValidateConfig(&config)) return 0;
   pic.width = w; pic.height = h;
+  if (c->lossless > 0) pic.use_argb = 1;
   if (bpp == 4 ? !WebPPictureImportRGBA(&pic, pix, w * 4) : !WebPPictureImportRGB(&pic, pix, w * 3)) return 0;
   WebPMemoryWriterInit(&wr);
   pic.writer = WebPMemoryWrite;

@@ -26,7 +26,7 @@ class EncCfg(C.Structure):
     _fields_ = [("quality", C.c_float), ("method", C.c_int), ("segments", C.c_int), ("filter_type", C.c_int),
                 ("filter_strength", C.c_int), ("filter_sharpness", C.c_int), ("partitions", C.c_int),
                 ("low_memory", C.c_int), ("alpha_filtering", C.c_int), ("alpha_quality", C.c_int),
-                ("sns_strength", C.c_int)]
+                ("sns_strength", C.c_int), ("lossless", C.c_int)]
 
     def __init__(self, quality=75.0, method=4, **kw):
         super().__init__()

@@ -19,6 +19,8 @@
 #include "vp8_tokens_fsm.h"
 #include "vp8_tokens_lockstep.h"
 #include "vp8l_alpha_core.h"
+#include "vp8l_lossless_core.h"
+#include "vp8l_alpha_core.h"
 
 // variant bit 0: visit the macroblocks of a wavefront step in reverse order
 // variant bit 1: token parse with the row-at-a-time reference port (parse_token_row) instead of the lane FSM
@@ -58,7 +60,38 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
   Vp8Container c;
   int st = vp8b_parse_container(data, size, 1, &c);
   if (st != VP8_STATUS_OK) return st;
-  if (c.has_animation || c.is_lossless) return VP8_STATUS_UNSUPPORTED_FEATURE;
+  if (c.has_animation) return VP8_STATUS_UNSUPPORTED_FEATURE;
+  if (c.is_lossless) {   // whole-picture VP8L: passes A and B of the ALPH decoder, then vp8l_lossless_core.h (like k_lossless_finish)
+    if (csp == 11 || csp == 12 || scaled_w > 0) return VP8_STATUS_UNSUPPORTED_FEATURE;
+    ImgDesc im;
+    memset(&im, 0, sizeof(im));
+    im.width = (uint16_t)c.width; im.height = (uint16_t)c.height;
+    im.csp = (uint8_t)csp; im.flags = (uint8_t)(flags | VP8B_FLAG_LOSSLESS); im.out_stride = stride;
+    im.out_w = im.width; im.out_h = im.height;
+    if (crop_w > 0) { im.crop_x = (uint16_t)crop_x; im.crop_y = (uint16_t)crop_y; im.out_w = (uint16_t)crop_w; im.out_h = (uint16_t)crop_h; }
+    const uint8_t* bits = data + c.frame_offset;
+    const uint32_t nbits = (uint32_t)c.frame_size;
+    std::vector<uint8_t> scratch(AL_SCRATCH_BYTES + 64);
+    uint8_t* sc16 = (uint8_t*)(((uintptr_t)scratch.data() + 15) & ~(uintptr_t)15);
+    std::vector<uint32_t> meta(AL_META_PIXELS_BOUND(im.width, im.height) + 8);
+    std::vector<uint32_t> tdata(2 * (size_t)AL_META_PIXELS_BOUND(im.width, im.height) + 8);
+    AlphaHdr ah;
+    alph_parse_header(bits, nbits, im.width, im.height, sc16, (uint16_t*)meta.data(), tdata.data(), &ah, 1);
+    std::vector<uint32_t> coded;
+    if (ah.status == AL_OK) {
+      std::vector<uint32_t> tables((size_t)ah.num_groups * ah.group_entries);
+      std::vector<AlGroup> groups(ah.num_groups);
+      coded.assign((size_t)ah.xsize * im.height + 4, 0);
+      ah.status = alph_decode_pixels(bits, nbits, im.height, (int)im.crop_y + (int)im.out_h, &ah, (const uint16_t*)meta.data(), tables.data(),
+                                     groups.data(), sc16, coded.data());
+    }
+    // every failure of a whole-picture decode is a bitstream error (vp8l_dec.c:1292,1479-1488; nothing suspends outside idec)
+    if (ah.status != AL_OK) return ah.status == AL_UNSUPPORTED ? VP8_STATUS_UNSUPPORTED_FEATURE : VP8_STATUS_BITSTREAM_ERROR;
+    const size_t need = (size_t)im.out_stride * (im.out_h - 1) + (size_t)im.out_w * ((csp == 0 || csp == 2) ? 3 : (csp == 5 || csp == 6 || csp == 10) ? 2 : 4);
+    if (need > out_size) return VP8_STATUS_INVALID_PARAM;
+    vp8l_finish_picture(&ah, im, coded.data(), tdata.data(), out, 0, 1);
+    return VP8_STATUS_OK;
+  }
   if (c.part0_size > c.frame_size - 10) return VP8_STATUS_NOT_ENOUGH_DATA;
 
   // input arena with padding on both sides, like the device arena

@@ -280,3 +280,81 @@ def test_emu_alpha_dithering_matches_reference(ref, amanifest):
     finally:
         L.emu_set_alpha_dithering(0)
     assert changed > 10000   # the cases do exercise the de-banding
+
+
+def lossless_cases(ref):
+    """Lossless (VP8L) pictures that between them use every transform, the colour cache, meta-Huffman groups and all pixel
+    bundlings: photo-like synthetic pictures (predictor + cross-colour + subtract-green), palettes of 2 / 4 / 16 / 40 / 256
+    colours, translucent alpha, odd sizes down to 1x1, encoder methods 0..6."""
+    rng = np.random.default_rng(123)
+    cases = []
+    for k, (w, h, q, m) in enumerate(((64, 48, 75, 4), (131, 77, 100, 6), (200, 150, 20, 0), (33, 91, 50, 2), (1, 1, 75, 4), (7, 3, 90, 3))):
+        pix = np.zeros((h, w, 4), np.uint8)
+        pix[..., :3] = ref.synth(w, h, 900 + k)
+        pix[..., 3] = 255 if k % 2 == 0 else np.clip(rng.integers(0, 400, (h, w)), 0, 255)
+        cases.append(ref.encode(pix, ref.EncCfg(q, m, lossless=1)))
+    for k, ncol in enumerate((2, 4, 16, 40, 256)):
+        w, h = 97 + 10 * k, 61 + 7 * k
+        pal = rng.integers(0, 256, (ncol, 4), dtype=np.uint8)
+        if k % 2 == 0:
+            pal[:, 3] = 255
+        y, x = np.mgrid[0:h, 0:w]
+        idx = ((x // 5 + y // 3) + rng.integers(0, 2, (h, w))) % ncol
+        cases.append(ref.encode(pal[idx], ref.EncCfg(75, 4 + k % 3, lossless=1)))
+    big = np.zeros((300, 400, 4), np.uint8)
+    big[..., :3] = ref.synth(400, 300, 77)
+    big[..., 3] = 255
+    big[100:200, 50:350, :3] = 40          # flat area: LZ77 runs + colour cache
+    cases.append(ref.encode(big, ref.EncCfg(100, 6, lossless=1)))
+    return cases
+
+
+def test_emu_lossless_matches_reference(ref):
+    """Whole-picture VP8L through the device code's host build: every RGB-family colourspace (premultiplied and 16-bit ones
+    included), crop windows at odd offsets (not snapped for lossless), flip; damaged and truncated files end with the
+    reference's status; MODE_YUV and scaling are refused."""
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR])
+    L = C.CDLL(os.path.join(EMU_DIR, "libvp8_emu.so"))
+    L.emu_decode_window.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_int]
+
+    def emu_window(data, csp, dev_flags, crop, W, H):
+        w, h = (crop[2], crop[3]) if crop else (W, H)
+        bpp = ref.BPP.get(csp, 4)
+        n = w * h * bpp
+        out = np.zeros(max(n, 16), np.uint8)
+        c = crop or (0, 0, 0, 0)
+        st = L.emu_decode_window(data, len(data), csp, dev_flags, out.ctypes.data, out.size, w * bpp, c[0], c[1], c[2], c[3])
+        return st, out[:n]
+
+    rng = np.random.default_rng(5)
+    for data in lossless_cases(ref):
+        st0, f = ref.features(data)
+        assert st0 == 0 and f["format"] == 2
+        W, H = f["width"], f["height"]
+        for it in range(3):
+            crop = None
+            if it > 0:
+                cw, ch = int(rng.integers(1, W + 1)), int(rng.integers(1, H + 1))
+                crop = (int(rng.integers(0, W - cw + 1)), int(rng.integers(0, H - ch + 1)), cw, ch)
+            flip = int(rng.integers(0, 2))
+            for csp in (1, 7, 0, 2, 3, 8, 4, 9, 5, 6, 10):
+                s_ref, want = ref.decode_window(data, csp, 8 if flip else 0, crop)
+                s_emu, got = emu_window(data, csp, 4 if flip else 0, crop, W, H)
+                assert s_emu == s_ref == 0, (len(data), crop, flip, csp, s_ref, s_emu)
+                assert np.array_equal(want, got), (len(data), W, H, crop, flip, csp)
+        assert emu_window(data, 11, 0, None, W, H)[0] == 4     # MODE_YUV from a lossless picture: refused
+        # damage: flipped bytes and truncation
+        for k in range(12):
+            b = bytearray(data)
+            if k % 3 == 2 and len(b) > 40:
+                b = b[: int(rng.integers(30, len(b)))]
+            else:
+                b[int(rng.integers(20, len(b)))] ^= int(rng.integers(1, 256))
+            b = bytes(b)
+            s_ref, want = ref.decode(b, 1, 0)
+            sf, fb = ref.features(b)     # the damage may have hit the dimensions
+            s_emu, got = emu_window(b, 1, 0, None, fb["width"] if sf == 0 else W, fb["height"] if sf == 0 else H)
+            assert s_emu == s_ref, (len(data), k, s_ref, s_emu)
+            if s_ref == 0:
+                assert np.array_equal(want.reshape(-1), got)

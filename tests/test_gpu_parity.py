@@ -447,3 +447,56 @@ def test_scaling(W, ref, manifest, amanifest):
                 st, out = W.WebPDecode(e["data"], csp, scaled=req)
                 assert st == s_ref == 0, (e["file"], req, csp, st, s_ref, W.last_error())
                 assert np.array_equal(out.reshape(-1)[:want.size], want), (e["file"], req, csp, (sw, sh))
+
+
+@pytest.mark.gpu
+def test_lossless_pictures(W, ref, manifest, amanifest):
+    """Whole-picture VP8L on the device: every transform, colour cache, meta-Huffman groups and
+    palette bundling (tests/test_emu.py:lossless_cases), every RGB-family colourspace, crop windows at odd offsets, flip;
+    then one batch mixing lossless, lossy, alpha and damaged lossless files (per-item status as the reference's), decoded
+    twice on the resident path; MODE_YUV and scaling from a lossless picture are refused."""
+    from test_emu import lossless_cases
+    cases = lossless_cases(ref)
+    rng = np.random.default_rng(6)
+    for data in cases:
+        _, f = ref.features(data)
+        w, h = f["width"], f["height"]
+        for it in range(3):
+            crop = None
+            if it > 0:
+                cw, ch = int(rng.integers(1, w + 1)), int(rng.integers(1, h + 1))
+                crop = (int(rng.integers(0, w - cw + 1)), int(rng.integers(0, h - ch + 1)), cw, ch)
+            flip = bool(rng.integers(0, 2))
+            for csp in (1, 7, 0, 2, 3, 8, 4, 9, 5, 6, 10):
+                s_ref, want = ref.decode_window(data, csp, 8 if flip else 0, crop)
+                st, out = W.WebPDecode(data, csp, crop=crop, flip=flip)
+                assert st == s_ref == 0, (len(data), crop, flip, csp, st, W.last_error())
+                assert np.array_equal(out.reshape(-1)[:want.size], want), (len(data), w, h, crop, flip, csp)
+        assert W.WebPDecode(data, W.MODE_YUV)[0] == W.VP8_STATUS_UNSUPPORTED_FEATURE
+        assert W.WebPDecode(data, W.MODE_RGBA, scaled=(max(1, w // 2), max(1, h // 2)))[0] == W.VP8_STATUS_UNSUPPORTED_FEATURE
+    datas = list(cases) + [e["data"] for e in manifest[:3]] + [e["data"] for e in amanifest[:3]]
+    for data in cases[:8]:
+        for k in range(4):
+            b = bytearray(data)
+            if k == 3 and len(b) > 40:
+                b = b[: int(rng.integers(30, len(b)))]
+            else:
+                b[int(rng.integers(20, len(b)))] ^= int(rng.integers(1, 256))
+            datas.append(bytes(b))
+    order = rng.permutation(len(datas))
+    datas = [datas[i] for i in order]
+    for csp in (W.MODE_RGBA, W.MODE_bgrA):
+        for rep in range(2):
+            sts, outs = W.decode_batch(datas, csp, device=0)
+            for d, st, out in zip(datas, sts, outs):
+                s_ref, want = ref.decode(d, csp, 0)
+                assert st == s_ref, (len(d), st, s_ref)
+                if s_ref == 0:
+                    assert np.array_equal(out.reshape(-1), want.reshape(-1)), len(d)
+    # a 1080p lossless picture and the incremental shim
+    big = np.zeros((1080, 1920, 4), np.uint8)
+    big[..., :3] = ref.synth(1920, 1080, 4242)
+    big[..., 3] = 255
+    data = ref.encode(big, ref.EncCfg(50, 2, lossless=1))
+    st, out = W.WebPDecode(data, W.MODE_RGBA)
+    assert st == 0 and np.array_equal(out.reshape(1080, 1920, 4), big)
