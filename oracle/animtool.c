@@ -72,10 +72,11 @@ int FN(anim_decode_all)(const uint8_t* data, size_t size, int csp, uint8_t* out,
 #ifdef ANIM_WITH_ENCODER
 #include "src/webp/encode.h"
 #include "src/webp/mux.h"
-// n RGBA frames (w x h, tightly packed, one after the other) -> animated WebP, every frame lossy at `quality`
-// (allow_mixed = 0), key frames every `kmax` frames at most so that sub-rectangle frames with blending and ALPH chunks occur.
+// n RGBA frames (w x h, tightly packed, one after the other) -> animated WebP, key frames every `kmax` frames at most so that
+// sub-rectangle frames with blending and ALPH chunks occur. lossless: 0 = every frame lossy at `quality`, 1 = every frame
+// lossless, 2 = the encoder picks per frame (allow_mixed).
 size_t FN(anim_encode)(const uint8_t* frames, int n, int w, int h, float quality, int method, int kmin, int kmax,
-                       int minimize_size, uint8_t** out) {
+                       int minimize_size, int lossless, uint8_t** out) {
   WebPAnimEncoderOptions eo;
   WebPAnimEncoder* enc;
   WebPData wd;
@@ -83,14 +84,14 @@ size_t FN(anim_encode)(const uint8_t* frames, int n, int w, int h, float quality
   int i, ok = 1;
   *out = NULL;
   if (!WebPAnimEncoderOptionsInit(&eo)) return 0;
-  eo.kmin = kmin; eo.kmax = kmax; eo.minimize_size = minimize_size; eo.allow_mixed = 0;
+  eo.kmin = kmin; eo.kmax = kmax; eo.minimize_size = minimize_size; eo.allow_mixed = (lossless == 2);
   enc = WebPAnimEncoderNew(w, h, &eo);
   if (enc == NULL) return 0;
   for (i = 0; ok && i < n; ++i) {
     WebPConfig config;
     WebPPicture pic;
     if (!WebPConfigInit(&config) || !WebPPictureInit(&pic)) { ok = 0; break; }
-    config.lossless = 0; config.quality = quality; config.method = method;
+    config.lossless = (lossless == 1); config.quality = quality; config.method = method;
     pic.use_argb = 1; pic.width = w; pic.height = h;
     if (!WebPPictureImportRGBA(&pic, frames + (size_t)i * 4 * w * h, 4 * w)) { ok = 0; break; }
     ok = WebPAnimEncoderAdd(enc, &pic, 40 * i, &config);

@@ -246,16 +246,17 @@ def _anim_lib(which):
     return _anim[which]
 
 
-def anim_encode(frames, quality=75.0, method=4, kmin=3, kmax=5, minimize_size=0):
-    """frames: (n, h, w, 4) uint8 RGBA -> animated WebP bytes, every frame lossy (reference WebPAnimEncoder)."""
+def anim_encode(frames, quality=75.0, method=4, kmin=3, kmax=5, minimize_size=0, lossless=0):
+    """frames: (n, h, w, 4) uint8 RGBA -> animated WebP bytes (reference WebPAnimEncoder); lossless: 0 lossy frames,
+    1 lossless frames, 2 the encoder picks per frame."""
     L = lib()
     L.reft_anim_encode.restype = C.c_size_t
-    L.reft_anim_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
+    L.reft_anim_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.POINTER(C.c_void_p)]
     frames = np.ascontiguousarray(frames)
     n, h, w, _ = frames.shape
     p = C.c_void_p()
-    size = L.reft_anim_encode(frames.ctypes.data, n, w, h, quality, method, kmin, kmax, minimize_size, C.byref(p))
+    size = L.reft_anim_encode(frames.ctypes.data, n, w, h, quality, method, kmin, kmax, minimize_size, lossless, C.byref(p))
     if size == 0:
         raise RuntimeError("WebPAnimEncoder failed")
     data = C.string_at(p, size)

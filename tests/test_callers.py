@@ -95,19 +95,28 @@ def test_dwebp_over_the_cuda_decoder(callers, manifest, amanifest, tmp_path):
                 ["-yuv", "-resize", "301", "0"], ["-pam", "-incremental"], ["-alpha", "-pgm"], ["-pam", "-noasm"],
                 ["-pam", "-external_memory", "1"], ["-ppm", "-external_memory", "2"],
                 ["-pam", "-crop", "2", "2", "60", "40", "-resize", "33", "90", "-flip", "-alpha_dither"])
-    # every start of the relinked dwebp creates a CUDA context (~1 s): all variants on one opaque and one alpha file,
-    # the default PAM output on every other fixture
-    full = ("normal_8part_400x300.webp", "alpha_lowq_200x150.webp")
+    # every start of the relinked dwebp creates a CUDA context (~2 s): all variants on one file with quantised alpha, a few
+    # on an opaque one and on a lossless one, the default PAM output on some other fixtures
+    some = variants[:1] + variants[5:7] + variants[13:16]
+    lossless = str(tmp_path / "lossless.webp")
+    pix = np.zeros((90, 120, 4), np.uint8)
+    pix[..., :3] = callers.synth(120, 90, 11)
+    pix[..., 3] = np.linspace(0, 255, 120, dtype=np.uint8)[None, :]
+    with open(lossless, "wb") as f:
+        f.write(callers.encode(pix, callers.EncCfg(75, 4, lossless=1)))
+    jobs = [(os.path.join(GOLDEN, "alpha_lowq_200x150.webp"), variants), (os.path.join(GOLDEN, "normal_8part_400x300.webp"), some),
+            (lossless, variants[1:3] + variants[12:14] + variants[16:17])]
+    jobs += [(os.path.join(GOLDEN, e["file"]), (["-pam"],)) for e in (manifest[0], manifest[3], amanifest[0], amanifest[2])]
     n = 0
-    for e in list(manifest) + list(amanifest):
-        src = os.path.join(GOLDEN, e["file"])
-        for args in (variants if e["file"] in full else (["-pam"],)):
+    for src, todo in jobs:
+        e = {"file": os.path.basename(src)}
+        for args in todo:
             rc_ref, want, _ = run_dwebp(callers.DWEBP_REF, src, args, str(tmp_path / "r.out"))
             rc, got, err = run_dwebp(callers.DWEBP_B200, src, args, str(tmp_path / "b.out"))
             assert rc == rc_ref, (e["file"], args, rc_ref, rc, err)
             assert got == want, (e["file"], args)
             n += want is not None
-    assert n >= 50
+    assert n >= 35
 
 
 @pytest.mark.gpu
@@ -117,7 +126,8 @@ def test_anim_decoder_over_the_cuda_decoder(callers):
     assert "libwebpdecoder_b200" in callers.anim_decoder_library("b200")
     files = [animation(callers), animation(callers, n=12, w=200, h=150, seed=21, quality=50.0, kmin=0, kmax=0),
              animation(callers, n=5, w=64, h=64, seed=33, quality=90.0, kmin=1, kmax=1),
-             animation(callers, n=6, w=321, h=123, seed=5, minimize_size=1)]
+             animation(callers, n=6, w=321, h=123, seed=5, minimize_size=1),
+             animation(callers, n=6, w=96, h=80, seed=8, lossless=1), animation(callers, n=9, w=150, h=100, seed=9, lossless=2, quality=30.0)]
     for data in files:
         for csp in (callers.MODE_RGBA, callers.MODE_BGRA, callers.MODE_rgbA, callers.MODE_bgrA):
             n_ref, want, ts_ref = callers.anim_decode(data, csp, "reft")
