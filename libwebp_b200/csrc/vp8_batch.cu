@@ -278,8 +278,8 @@ static VP8StatusCode plan_item(WebPBatchItem* it, const WebPBatchOptions& opt, V
   const int csp = cfg->output.colorspace;
   if (csp < MODE_RGB || csp >= MODE_LAST) return VP8_STATUS_INVALID_PARAM;
   if (!csp_supported(csp)) return VP8_STATUS_UNSUPPORTED_FEATURE;
-  // whole-picture VP8L (vp8l_lossless_core.h): the RGB family at the picture's own size; YUV output and the rescaler are not built
-  if (c->is_lossless && (csp == MODE_YUV || csp == MODE_YUVA || o->use_scaling)) return VP8_STATUS_UNSUPPORTED_FEATURE;
+  // whole-picture VP8L (vp8l_lossless_core.h): every colourspace at the picture's own size; the ARGB rescaler is not built
+  if (c->is_lossless && o->use_scaling) return VP8_STATUS_UNSUPPORTED_FEATURE;
   int ow = c->width, oh = c->height;
   if (o->use_cropping) {   // WebPAllocateDecBuffer, buffer_dec.c:184-195 (x, y snapped to even like the decoder's own io)
     const int x = o->crop_left & ~1, y = o->crop_top & ~1;

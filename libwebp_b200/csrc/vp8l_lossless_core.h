@@ -11,7 +11,7 @@
 // one thread per pixel of the output window (options.use_cropping: the window is NOT snapped to even coordinates for
 // lossless pictures, webp_dec.c:816-820; options.flip: rows written bottom-up).
 // Rows below the window are never decoded (DecodeImageData stops at io->crop_bottom), so whatever the transforms make of
-// them is never looked at. MODE_YUV / MODE_YUVA output and options.use_scaling are refused by the host planner.
+// them is never looked at. options.use_scaling on a lossless picture is refused by the host planner.
 #ifndef LIBWEBP_B200_VP8L_LOSSLESS_CORE_H_
 #define LIBWEBP_B200_VP8L_LOSSLESS_CORE_H_
 
@@ -19,25 +19,86 @@
 #include "vp8_pixel_core.h"
 #include "vp8l_alpha_core.h"
 
+// ARGB of picture pixel (sx, sy) after the inverse transforms: the palette look-up / unbundling of a COLOR_INDEXING
+// transform happens here (VP8LColorIndexInverseTransform, lossless.c:341-385: the index travels in green).
+AL_FN uint32_t vp8l_fetch(const AlphaHdr* hd, const uint32_t* px, int sx, int sy) {
+  const int xs = hd->xsize;
+  if (hd->ntrans > 0 && hd->ttype[0] == AL_T_COLOR_INDEXING) {
+    const int bits = hd->tbits[0], bpp = 8 >> bits;
+    const uint32_t packed = (px[(size_t)sy * xs + (sx >> bits)] >> 8) & 0xff;
+    return hd->palette[(packed >> ((sx & ((1 << bits) - 1)) * bpp)) & ((1u << bpp) - 1u)];
+  }
+  return px[(size_t)sy * xs + sx];
+}
+
+// VP8RGBToY / VP8RGBToU / VP8RGBToV (src/dsp/yuv.h:186-204), YUV_FIX = 16.
+AL_FN int vp8l_clip_uv(int uv, int rounding) {
+  uv = (uv + rounding + (128 << 18)) >> 18;
+  return ((uv & ~0xff) == 0) ? uv : (uv < 0) ? 0 : 255;
+}
+// One row's contribution to chroma sample ux: two pixels summed and doubled, the last pixel of an odd width times four
+// (WebPConvertARGBToUV_C, src/dsp/yuv.c:129-170).
+AL_FN void vp8l_row_uv(const AlphaHdr* hd, const uint32_t* px, const ImgDesc& im, int ux, int y, int* u, int* v) {
+  const int x0 = 2 * ux;
+  const uint32_t v0 = vp8l_fetch(hd, px, x0 + im.crop_x, y + im.crop_y);
+  int r, g, b;
+  if (x0 + 1 < im.out_w) {
+    const uint32_t v1 = vp8l_fetch(hd, px, x0 + 1 + im.crop_x, y + im.crop_y);
+    r = (int)(((v0 >> 15) & 0x1fe) + ((v1 >> 15) & 0x1fe)); g = (int)(((v0 >> 7) & 0x1fe) + ((v1 >> 7) & 0x1fe));
+    b = (int)(((v0 << 1) & 0x1fe) + ((v1 << 1) & 0x1fe));
+  } else {
+    r = (int)((v0 >> 14) & 0x3fc); g = (int)((v0 >> 6) & 0x3fc); b = (int)((v0 << 2) & 0x3fc);
+  }
+  *u = vp8l_clip_uv(-9719 * r - 19081 * g + 28800 * b, 1 << 17);
+  *v = vp8l_clip_uv(28800 * r - 24116 * g - 4684 * b, 1 << 17);
+}
+
+// MODE_YUV / MODE_YUVA from a lossless picture (EmitRowsYUVA / ConvertToYUVA, vp8l_dec.c:660-686): luma per pixel; chroma
+// per row from horizontal pairs, even rows stored, odd rows averaged into them with rounding; alpha copied.
+// Layout as the VP8 output stage writes it: y | u | v [| a], strides w, (w+1)/2, (w+1)/2, w; flip reverses every plane.
+AL_FN void vp8l_emit_yuva(const AlphaHdr* hd, const ImgDesc& im, const uint32_t* px, uint8_t* out, int tid, int nt) {
+  const int w = im.out_w, h = im.out_h, uvw = (w + 1) >> 1, uvh = (h + 1) >> 1;
+  const int flip = (im.flags & VP8B_FLAG_FLIP) != 0;
+  uint8_t* yo = out;
+  uint8_t* uo = out + (size_t)im.out_stride * h;
+  uint8_t* vo = uo + (size_t)uvw * uvh;
+  uint8_t* ao = vo + (size_t)uvw * uvh;
+  const size_t total = (size_t)w * (size_t)h;
+  for (size_t i = (size_t)tid; i < total; i += (size_t)nt) {
+    const int x = (int)(i % (size_t)w), y = (int)(i / (size_t)w);
+    const uint32_t p = vp8l_fetch(hd, px, x + im.crop_x, y + im.crop_y);
+    const int luma = 16839 * (int)((p >> 16) & 0xff) + 33059 * (int)((p >> 8) & 0xff) + 6420 * (int)(p & 0xff);
+    const int yd = flip ? h - 1 - y : y;
+    yo[(size_t)yd * im.out_stride + x] = (uint8_t)((luma + (1 << 15) + (16 << 16)) >> 16);
+    if (im.csp == 12) ao[(size_t)yd * w + x] = (uint8_t)(p >> 24);
+  }
+  const size_t uv_total = (size_t)uvw * (size_t)uvh;
+  for (size_t i = (size_t)tid; i < uv_total; i += (size_t)nt) {
+    const int ux = (int)(i % (size_t)uvw), uy = (int)(i / (size_t)uvw);
+    int u, v;
+    vp8l_row_uv(hd, px, im, ux, 2 * uy, &u, &v);
+    if (2 * uy + 1 < h) {
+      int u1, v1;
+      vp8l_row_uv(hd, px, im, ux, 2 * uy + 1, &u1, &v1);
+      u = (u + u1 + 1) >> 1; v = (v + v1 + 1) >> 1;
+    }
+    const int yd = flip ? uvh - 1 - uy : uy;
+    uo[(size_t)yd * uvw + ux] = (uint8_t)u;
+    vo[(size_t)yd * uvw + ux] = (uint8_t)v;
+  }
+}
+
 // px = xsize x height coded words (pass B), out = the picture's slot in the output arena.
 AL_FN void vp8l_finish_picture(const AlphaHdr* hd, const ImgDesc& im, uint32_t* px, const uint32_t* tdata, uint8_t* out, int tid, int nt) {
   al_inverse_transforms(hd, px, tdata, im.height, tid, nt);
-  const int has_palette = hd->ntrans > 0 && hd->ttype[0] == AL_T_COLOR_INDEXING;
-  const int bits = has_palette ? hd->tbits[0] : 0, bpp = 8 >> bits;
-  const int xs = hd->xsize;
   const int w = im.out_w, h = im.out_h, csp = im.csp;
+  if (csp == 11 || csp == 12) { vp8l_emit_yuva(hd, im, px, out, tid, nt); return; }
   const int obpp = (csp == 0 || csp == 2) ? 3 : (csp == 5 || csp == 6 || csp == 10) ? 2 : 4;
   const size_t total = (size_t)w * (size_t)h;
   for (size_t i = (size_t)tid; i < total; i += (size_t)nt) {
     const int x = (int)(i % (size_t)w), y = (int)(i / (size_t)w);
     const int sx = x + im.crop_x, sy = y + im.crop_y;
-    uint32_t argb;
-    if (has_palette) {   // VP8LColorIndexInverseTransform, lossless.c:341-385: the index travels in green
-      const uint32_t packed = (px[(size_t)sy * xs + (sx >> bits)] >> 8) & 0xff;
-      argb = hd->palette[(packed >> ((sx & ((1 << bits) - 1)) * bpp)) & ((1u << bpp) - 1u)];
-    } else {
-      argb = px[(size_t)sy * xs + sx];
-    }
+    const uint32_t argb = vp8l_fetch(hd, px, sx, sy);
     const int a = (int)(argb >> 24), r = (int)((argb >> 16) & 0xff), g = (int)((argb >> 8) & 0xff), b = (int)(argb & 0xff);
     uint8_t* o = out + (size_t)((im.flags & VP8B_FLAG_FLIP) ? h - 1 - y : y) * im.out_stride + (size_t)x * obpp;
     if (obpp == 4) {

@@ -62,7 +62,7 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
   if (st != VP8_STATUS_OK) return st;
   if (c.has_animation) return VP8_STATUS_UNSUPPORTED_FEATURE;
   if (c.is_lossless) {   // whole-picture VP8L: passes A and B of the ALPH decoder, then vp8l_lossless_core.h (like k_lossless_finish)
-    if (csp == 11 || csp == 12 || scaled_w > 0) return VP8_STATUS_UNSUPPORTED_FEATURE;
+    if (scaled_w > 0) return VP8_STATUS_UNSUPPORTED_FEATURE;
     ImgDesc im;
     memset(&im, 0, sizeof(im));
     im.width = (uint16_t)c.width; im.height = (uint16_t)c.height;
@@ -87,7 +87,9 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
     }
     // every failure of a whole-picture decode is a bitstream error (vp8l_dec.c:1292,1479-1488; nothing suspends outside idec)
     if (ah.status != AL_OK) return ah.status == AL_UNSUPPORTED ? VP8_STATUS_UNSUPPORTED_FEATURE : VP8_STATUS_BITSTREAM_ERROR;
-    const size_t need = (size_t)im.out_stride * (im.out_h - 1) + (size_t)im.out_w * ((csp == 0 || csp == 2) ? 3 : (csp == 5 || csp == 6 || csp == 10) ? 2 : 4);
+    const size_t need = (csp == 11 || csp == 12)
+        ? (size_t)im.out_stride * im.out_h + 2 * (size_t)((im.out_w + 1) / 2) * ((im.out_h + 1) / 2) + (csp == 12 ? (size_t)im.out_w * im.out_h : 0)
+        : (size_t)im.out_stride * (im.out_h - 1) + (size_t)im.out_w * ((csp == 0 || csp == 2) ? 3 : (csp == 5 || csp == 6 || csp == 10) ? 2 : 4);
     if (need > out_size) return VP8_STATUS_INVALID_PARAM;
     vp8l_finish_picture(&ah, im, coded.data(), tdata.data(), out, 0, 1);
     return VP8_STATUS_OK;

@@ -311,8 +311,8 @@ def lossless_cases(ref):
 
 def test_emu_lossless_matches_reference(ref):
     """Whole-picture VP8L through the device code's host build: every RGB-family colourspace (premultiplied and 16-bit ones
-    included), crop windows at odd offsets (not snapped for lossless), flip; damaged and truncated files end with the
-    reference's status; MODE_YUV and scaling are refused."""
+    included) and MODE_YUV / MODE_YUVA, crop windows at odd offsets (not snapped for lossless), flip; damaged and truncated
+    files end with the reference's status."""
     subprocess.check_call(["make", "-s", "-C", EMU_DIR])
     L = C.CDLL(os.path.join(EMU_DIR, "libvp8_emu.so"))
     L.emu_decode_window.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
@@ -320,8 +320,8 @@ def test_emu_lossless_matches_reference(ref):
 
     def emu_window(data, csp, dev_flags, crop, W, H):
         w, h = (crop[2], crop[3]) if crop else (W, H)
-        bpp = ref.BPP.get(csp, 4)
-        n = w * h * bpp
+        bpp = 1 if csp in (11, 12) else ref.BPP[csp]
+        n = (w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2) + (w * h if csp == 12 else 0)) if csp in (11, 12) else w * h * bpp
         out = np.zeros(max(n, 16), np.uint8)
         c = crop or (0, 0, 0, 0)
         st = L.emu_decode_window(data, len(data), csp, dev_flags, out.ctypes.data, out.size, w * bpp, c[0], c[1], c[2], c[3])
@@ -338,12 +338,11 @@ def test_emu_lossless_matches_reference(ref):
                 cw, ch = int(rng.integers(1, W + 1)), int(rng.integers(1, H + 1))
                 crop = (int(rng.integers(0, W - cw + 1)), int(rng.integers(0, H - ch + 1)), cw, ch)
             flip = int(rng.integers(0, 2))
-            for csp in (1, 7, 0, 2, 3, 8, 4, 9, 5, 6, 10):
+            for csp in (1, 7, 0, 2, 3, 8, 4, 9, 5, 6, 10, 11, 12):
                 s_ref, want = ref.decode_window(data, csp, 8 if flip else 0, crop)
                 s_emu, got = emu_window(data, csp, 4 if flip else 0, crop, W, H)
                 assert s_emu == s_ref == 0, (len(data), crop, flip, csp, s_ref, s_emu)
                 assert np.array_equal(want, got), (len(data), W, H, crop, flip, csp)
-        assert emu_window(data, 11, 0, None, W, H)[0] == 4     # MODE_YUV from a lossless picture: refused
         # damage: flipped bytes and truncation
         for k in range(12):
             b = bytearray(data)

@@ -452,9 +452,9 @@ def test_scaling(W, ref, manifest, amanifest):
 @pytest.mark.gpu
 def test_lossless_pictures(W, ref, manifest, amanifest):
     """Whole-picture VP8L on the device: every transform, colour cache, meta-Huffman groups and
-    palette bundling (tests/test_emu.py:lossless_cases), every RGB-family colourspace, crop windows at odd offsets, flip;
+    palette bundling (tests/test_emu.py:lossless_cases), every colourspace incl. MODE_YUV / MODE_YUVA, crop windows at odd offsets, flip;
     then one batch mixing lossless, lossy, alpha and damaged lossless files (per-item status as the reference's), decoded
-    twice on the resident path; MODE_YUV and scaling from a lossless picture are refused."""
+    twice on the resident path; scaling a lossless picture is refused."""
     from test_emu import lossless_cases
     cases = lossless_cases(ref)
     rng = np.random.default_rng(6)
@@ -467,12 +467,11 @@ def test_lossless_pictures(W, ref, manifest, amanifest):
                 cw, ch = int(rng.integers(1, w + 1)), int(rng.integers(1, h + 1))
                 crop = (int(rng.integers(0, w - cw + 1)), int(rng.integers(0, h - ch + 1)), cw, ch)
             flip = bool(rng.integers(0, 2))
-            for csp in (1, 7, 0, 2, 3, 8, 4, 9, 5, 6, 10):
+            for csp in (1, 7, 0, 2, 3, 8, 4, 9, 5, 6, 10, 11, 12):
                 s_ref, want = ref.decode_window(data, csp, 8 if flip else 0, crop)
                 st, out = W.WebPDecode(data, csp, crop=crop, flip=flip)
                 assert st == s_ref == 0, (len(data), crop, flip, csp, st, W.last_error())
                 assert np.array_equal(out.reshape(-1)[:want.size], want), (len(data), w, h, crop, flip, csp)
-        assert W.WebPDecode(data, W.MODE_YUV)[0] == W.VP8_STATUS_UNSUPPORTED_FEATURE
         assert W.WebPDecode(data, W.MODE_RGBA, scaled=(max(1, w // 2), max(1, h // 2)))[0] == W.VP8_STATUS_UNSUPPORTED_FEATURE
     datas = list(cases) + [e["data"] for e in manifest[:3]] + [e["data"] for e in amanifest[:3]]
     for data in cases[:8]:
