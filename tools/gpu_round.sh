@@ -2,7 +2,7 @@
 # GPU box: what the driver runs at round end (tests, smoke, both bench arms), plus the ncu launch list.
 TAG=${1:-r01e}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3 > gpurun_out/${TAG}_pytest_gpu.log; cat gpurun_out/${TAG}_pytest_gpu.log
+timeout 1200 python -m pytest tests -x -q -m gpu --durations=6 2>&1 | tail -12 > gpurun_out/${TAG}_pytest_gpu.log; cat gpurun_out/${TAG}_pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; tail -1 gpurun_out/${TAG}_smoke.log
 python bench.py --impl reference > gpurun_out/${TAG}_bench_reference.log 2>&1; tail -1 gpurun_out/${TAG}_bench_reference.log | cut -c1-300
 python bench.py > gpurun_out/${TAG}_bench.log 2>&1; tail -1 gpurun_out/${TAG}_bench.log | cut -c1-2500
