@@ -278,8 +278,6 @@ static VP8StatusCode plan_item(WebPBatchItem* it, const WebPBatchOptions& opt, V
   const int csp = cfg->output.colorspace;
   if (csp < MODE_RGB || csp >= MODE_LAST) return VP8_STATUS_INVALID_PARAM;
   if (!csp_supported(csp)) return VP8_STATUS_UNSUPPORTED_FEATURE;
-  // whole-picture VP8L (vp8l_lossless_core.h): every colourspace at the picture's own size; the ARGB rescaler is not built
-  if (c->is_lossless && o->use_scaling) return VP8_STATUS_UNSUPPORTED_FEATURE;
   int ow = c->width, oh = c->height;
   if (o->use_cropping) {   // WebPAllocateDecBuffer, buffer_dec.c:184-195 (x, y snapped to even like the decoder's own io)
     const int x = o->crop_left & ~1, y = o->crop_top & ~1;
@@ -709,7 +707,10 @@ static bool batch_alpha(WebPBatch* b) {
         grp[a] = work2; work2 += align_up((size_t)h.num_groups * sizeof(AlGroup), 256);
         cod[a] = work2; work2 += align_up(4 * ((size_t)h.xsize * d.height + 4), 256);
       }
-      if (d.flags & VP8B_FLAG_LOSSLESS) continue;   // its pixels go straight to the output arena (vp8k_lossless_finish)
+      if (d.flags & VP8B_FLAG_LOSSLESS) {   // its pixels go straight to the output arena (vp8k_lossless_finish)
+        if (d.dst_w != 0) { smo[a] = work2 + 1; work2 += align_up(4 * (size_t)d.out_w * d.out_h + 16, 256); }
+        continue;
+      }
       if (d.alpha_dither != 0) { smo[a] = work2 + 1; work2 += align_up(2 * (size_t)d.out_w * d.out_h + 16, 256); }   // +1: 0 means none
       d.alpha_plane = planes;
       planes += align_up((size_t)d.width * d.height, 256);

@@ -798,7 +798,7 @@ __global__ void __launch_bounds__(ALPHA_FINISH_THREADS) k_lossless_finish(const 
   if (hd->status != AL_OK || !hd->lossless) return;
   const ImgDesc im = imgs[aimgs[a]];
   const AlphaPlan pl = plans[a];
-  vp8l_finish_picture(hd, im, (uint32_t*)pl.coded, (const uint32_t*)pl.tdata, out + im.out_off, (int)threadIdx.x, (int)blockDim.x);
+  vp8l_finish_picture(hd, im, (uint32_t*)pl.coded, (const uint32_t*)pl.tdata, out + im.out_off, (uint8_t*)pl.smooth, (int)threadIdx.x, (int)blockDim.x);
 }
 
 extern "C" void vp8k_alpha_header(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, const int* aimgs, const AlphaPlan* plans,

@@ -57,7 +57,8 @@ typedef struct AlphaPlan {
   uint64_t tables;    // num_groups * group_entries words                 (after the header pass)
   uint64_t groups;    // num_groups AlGroup                               (after the header pass)
   uint64_t coded;     // xsize * height ARGB words                        (after the header pass)
-  uint64_t smooth;    // 2 * out_w * out_h bytes for alpha de-banding (ImgDesc::alpha_dither), 0 = none
+  uint64_t smooth;    // 2 * out_w * out_h bytes for alpha de-banding (ImgDesc::alpha_dither), 0 = none;
+                      // lossless pictures with options.use_scaling: 4 * out_w * out_h bytes, the premultiplied window
 } AlphaPlan;
 void vp8k_lossless_finish(cudaStream_t s, const ImgDesc* imgs, const int* aimgs, const AlphaPlan* plans, const struct AlphaHdr* ahdrs,
                           uint8_t* out, int count);

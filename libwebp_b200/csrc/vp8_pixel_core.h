@@ -857,6 +857,7 @@ VP8_PFN uint32_t mult_by_alpha(uint32_t x, uint32_t a, int inverse) {
 
 struct Rescaler {   // one plane of one image, as seen by one output column (WebPRescalerInit, rescaler_utils.c:24-84)
   const uint8_t* src; int src_stride;
+  int px_step;                            // bytes between horizontally adjacent samples (4: one channel of interleaved BGRA)
   const uint8_t* asrc; int asrc_stride;   // MODE_YUVA: the luma is multiplied by this alpha plane on its way in (io_dec.c:258-265)
   int src_w, src_h, dst_w, dst_h;
   int x_expand, y_expand;
@@ -867,7 +868,7 @@ struct Rescaler {   // one plane of one image, as seen by one output column (Web
 };
 
 VP8_PFN void rescaler_init(Rescaler& r, const uint8_t* src, int src_stride, int src_w, int src_h, int dst_w, int dst_h) {
-  r.src = src; r.src_stride = src_stride; r.asrc = 0; r.asrc_stride = 0;
+  r.src = src; r.src_stride = src_stride; r.px_step = 1; r.asrc = 0; r.asrc_stride = 0;
   r.src_w = src_w; r.src_h = src_h; r.dst_w = dst_w; r.dst_h = dst_h;
   r.x_expand = src_w < dst_w; r.y_expand = src_h < dst_h;
   r.x_add = r.x_expand ? dst_w - 1 : src_w;
@@ -889,7 +890,7 @@ VP8_PFN void rescaler_init(Rescaler& r, const uint8_t* src, int src_stride, int 
 
 // frow[x] of WebPRescalerImportRowShrink_C (rescaler.c:62-95) for one source row: output k consumes the inputs
 // n(k-1) .. n(k)-1 with n(k) = ceil((k+1) * x_add / x_sub), starting from the fraction the previous output left over.
-#define RS_PX(i) (arow ? mult_by_alpha(row[i], arow[i], 0) : (uint32_t)row[i])
+#define RS_PX(i) (arow ? mult_by_alpha(row[i], arow[i], 0) : (uint32_t)row[(i) * r.px_step])
 VP8_PFN uint32_t import_row_shrink(const Rescaler& r, const uint8_t* row, const uint8_t* arow, int x) {
   const int64_t t1 = (int64_t)(x + 1) * r.x_add;
   const int n1 = (int)((t1 + r.x_sub - 1) / r.x_sub);

@@ -11,7 +11,7 @@
 // one thread per pixel of the output window (options.use_cropping: the window is NOT snapped to even coordinates for
 // lossless pictures, webp_dec.c:816-820; options.flip: rows written bottom-up).
 // Rows below the window are never decoded (DecodeImageData stops at io->crop_bottom), so whatever the transforms make of
-// them is never looked at. options.use_scaling on a lossless picture is refused by the host planner.
+// them is never looked at.
 #ifndef LIBWEBP_B200_VP8L_LOSSLESS_CORE_H_
 #define LIBWEBP_B200_VP8L_LOSSLESS_CORE_H_
 
@@ -88,9 +88,120 @@ AL_FN void vp8l_emit_yuva(const AlphaHdr* hd, const ImgDesc& im, const uint32_t*
   }
 }
 
-// px = xsize x height coded words (pass B), out = the picture's slot in the output arena.
-AL_FN void vp8l_finish_picture(const AlphaHdr* hd, const ImgDesc& im, uint32_t* px, const uint32_t* tdata, uint8_t* out, int tid, int nt) {
+// ---------------------------------------------------------------------------------------------------------
+// options.use_scaling on a lossless picture (AllocateAndInitRescaler, EmitRescaledRowsRGBA / EmitRescaledRowsYUVA, Export /
+// ExportYUVA, vp8l_dec.c:560-645, 688-737): the window's ARGB words are multiplied by their alpha (WebPMultARGBRows,
+// alpha_processing.c:140-158), the four byte channels go through four rescalers of the same geometry (num_channels = 4),
+// every exported row is divided by its rescaled alpha again (WebPMultARGBRow inverse) and converted like an unscaled row.
+// `pm` = the premultiplied window as interleaved B, G, R, A bytes (4 * out_w * out_h bytes of scratch).
+AL_FN uint32_t vp8l_premultiply(uint32_t argb) {
+  if (argb >= 0xff000000u) return argb;
+  if (argb <= 0x00ffffffu) return 0;
+  const uint32_t a = argb >> 24;
+  return (argb & 0xff000000u) | mult_by_alpha(argb & 0xff, a, 0) | (mult_by_alpha((argb >> 8) & 0xff, a, 0) << 8) |
+         (mult_by_alpha((argb >> 16) & 0xff, a, 0) << 16);
+}
+// The inverse on an exported pixel: 32-bit wrap-around products, and quotients above 255 spill into the next channel,
+// both exactly as WebPMultARGBRow_C leaves them.
+AL_FN uint32_t vp8l_unmultiply(uint32_t argb) {
+  if (argb >= 0xff000000u) return argb;
+  if (argb <= 0x00ffffffu) return 0;
+  const uint32_t scale = (255u << 24) / (argb >> 24);
+  uint32_t out = argb & 0xff000000u;
+  out |= (((argb & 0xff) * scale + (1u << 23)) >> 24);
+  out |= ((((argb >> 8) & 0xff) * scale + (1u << 23)) >> 24) << 8;
+  out |= ((((argb >> 16) & 0xff) * scale + (1u << 23)) >> 24) << 16;
+  return out;
+}
+struct Vp8lScaledColumn { Rescaler ch[4]; };
+AL_FN void vp8l_column_init(Vp8lScaledColumn& c, const ImgDesc& im, const uint8_t* pm) {
+  for (int k = 0; k < 4; ++k) {
+    rescaler_init(c.ch[k], pm + k, 4 * im.out_w, im.out_w, im.out_h, im.dst_w, im.dst_h);
+    c.ch[k].px_step = 4;
+  }
+}
+AL_FN uint32_t vp8l_column_next(Vp8lScaledColumn& c, int x) {   // the next exported pixel of output column x
+  const uint32_t b = (uint32_t)rescaler_next(c.ch[0], x) & 0xff, g = (uint32_t)rescaler_next(c.ch[1], x) & 0xff;
+  const uint32_t r = (uint32_t)rescaler_next(c.ch[2], x) & 0xff, a = (uint32_t)rescaler_next(c.ch[3], x) & 0xff;
+  return vp8l_unmultiply((a << 24) | (r << 16) | (g << 8) | b);
+}
+AL_FN void vp8l_uv_of(uint32_t v0, uint32_t v1, int pair, int* u, int* v) {   // WebPConvertARGBToUV_C on one or two pixels
+  int r, g, b;
+  if (pair) {
+    r = (int)(((v0 >> 15) & 0x1fe) + ((v1 >> 15) & 0x1fe)); g = (int)(((v0 >> 7) & 0x1fe) + ((v1 >> 7) & 0x1fe));
+    b = (int)(((v0 << 1) & 0x1fe) + ((v1 << 1) & 0x1fe));
+  } else {
+    r = (int)((v0 >> 14) & 0x3fc); g = (int)((v0 >> 6) & 0x3fc); b = (int)((v0 << 2) & 0x3fc);
+  }
+  *u = vp8l_clip_uv(-9719 * r - 19081 * g + 28800 * b, 1 << 17);
+  *v = vp8l_clip_uv(28800 * r - 24116 * g - 4684 * b, 1 << 17);
+}
+AL_FN void vp8l_store_pixel(int csp, uint32_t argb, uint8_t* orow, int x) {   // VP8LConvertFromBGRA, one pixel
+  const int a = (int)(argb >> 24), r = (int)((argb >> 16) & 0xff), g = (int)((argb >> 8) & 0xff), b = (int)(argb & 0xff);
+  if (csp == 0 || csp == 2) {
+    uint8_t* o = orow + 3 * x;
+    if (csp == 0) { o[0] = (uint8_t)r; o[1] = (uint8_t)g; o[2] = (uint8_t)b; } else { o[0] = (uint8_t)b; o[1] = (uint8_t)g; o[2] = (uint8_t)r; }
+  } else if (csp == 5 || csp == 6 || csp == 10) {
+    const uint32_t p2 = pack_pixel2(csp, r, g, b, a);
+    orow[2 * x] = (uint8_t)p2; orow[2 * x + 1] = (uint8_t)(p2 >> 8);
+  } else {
+    const uint32_t p4 = pack_pixel4(csp, r, g, b, a);
+    uint8_t* o = orow + 4 * x;
+    o[0] = (uint8_t)p4; o[1] = (uint8_t)(p4 >> 8); o[2] = (uint8_t)(p4 >> 16); o[3] = (uint8_t)(p4 >> 24);
+  }
+}
+AL_FN void vp8l_emit_scaled(const AlphaHdr* hd, const ImgDesc& im, const uint32_t* px, uint8_t* pm, uint8_t* out, int tid, int nt) {
+  const int sw = im.out_w, sh = im.out_h, dw = im.dst_w, dh = im.dst_h;
+  const int flip = (im.flags & VP8B_FLAG_FLIP) != 0;
+  const size_t total = (size_t)sw * (size_t)sh;
+  for (size_t i = (size_t)tid; i < total; i += (size_t)nt) {
+    const uint32_t p = vp8l_premultiply(vp8l_fetch(hd, px, (int)(i % (size_t)sw) + im.crop_x, (int)(i / (size_t)sw) + im.crop_y));
+    pm[4 * i] = (uint8_t)p; pm[4 * i + 1] = (uint8_t)(p >> 8); pm[4 * i + 2] = (uint8_t)(p >> 16); pm[4 * i + 3] = (uint8_t)(p >> 24);
+  }
+  AL_BLOCK_SYNC();
+  if (im.csp != 11 && im.csp != 12) {
+    for (int x = tid; x < dw; x += nt) {
+      Vp8lScaledColumn c;
+      vp8l_column_init(c, im, pm);
+      for (int k = 0; k < dh; ++k) vp8l_store_pixel(im.csp, vp8l_column_next(c, x), out + (size_t)(flip ? dh - 1 - k : k) * im.out_stride, x);
+    }
+    return;
+  }
+  // MODE_YUV / MODE_YUVA: one work item per chroma column = two luma columns (ConvertToYUVA on every exported row)
+  const int uvw = (dw + 1) >> 1, uvh = (dh + 1) >> 1;
+  uint8_t* uo = out + (size_t)im.out_stride * dh;
+  uint8_t* vo = uo + (size_t)uvw * uvh;
+  uint8_t* ao = vo + (size_t)uvw * uvh;
+  for (int ux = tid; ux < uvw; ux += nt) {
+    const int x0 = 2 * ux, pair = x0 + 1 < dw;
+    Vp8lScaledColumn c0, c1;
+    vp8l_column_init(c0, im, pm);
+    if (pair) vp8l_column_init(c1, im, pm);
+    int u_even = 0, v_even = 0;
+    for (int k = 0; k < dh; ++k) {
+      const uint32_t p0 = vp8l_column_next(c0, x0), p1 = pair ? vp8l_column_next(c1, x0 + 1) : 0;
+      const int kd = flip ? dh - 1 - k : k;
+      for (int j = 0; j <= pair; ++j) {
+        const uint32_t p = j ? p1 : p0;
+        const int luma = 16839 * (int)((p >> 16) & 0xff) + 33059 * (int)((p >> 8) & 0xff) + 6420 * (int)(p & 0xff);
+        out[(size_t)kd * im.out_stride + x0 + j] = (uint8_t)((luma + (1 << 15) + (16 << 16)) >> 16);
+        if (im.csp == 12) ao[(size_t)kd * dw + x0 + j] = (uint8_t)(p >> 24);
+      }
+      int u, v;
+      vp8l_uv_of(p0, p1, pair, &u, &v);
+      if (k & 1) { u = (u_even + u + 1) >> 1; v = (v_even + v + 1) >> 1; } else { u_even = u; v_even = v; }
+      const int uyd = flip ? uvh - 1 - (k >> 1) : (k >> 1);
+      uo[(size_t)uyd * uvw + ux] = (uint8_t)u;
+      vo[(size_t)uyd * uvw + ux] = (uint8_t)v;
+    }
+  }
+}
+
+// px = xsize x height coded words (pass B), out = the picture's slot in the output arena; pm = scratch for options.use_scaling.
+AL_FN void vp8l_finish_picture(const AlphaHdr* hd, const ImgDesc& im, uint32_t* px, const uint32_t* tdata, uint8_t* out, uint8_t* pm,
+                               int tid, int nt) {
   al_inverse_transforms(hd, px, tdata, im.height, tid, nt);
+  if (im.dst_w != 0) { vp8l_emit_scaled(hd, im, px, pm, out, tid, nt); return; }
   const int w = im.out_w, h = im.out_h, csp = im.csp;
   if (csp == 11 || csp == 12) { vp8l_emit_yuva(hd, im, px, out, tid, nt); return; }
   const int obpp = (csp == 0 || csp == 2) ? 3 : (csp == 5 || csp == 6 || csp == 10) ? 2 : 4;

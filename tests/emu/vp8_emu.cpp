@@ -62,13 +62,13 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
   if (st != VP8_STATUS_OK) return st;
   if (c.has_animation) return VP8_STATUS_UNSUPPORTED_FEATURE;
   if (c.is_lossless) {   // whole-picture VP8L: passes A and B of the ALPH decoder, then vp8l_lossless_core.h (like k_lossless_finish)
-    if (scaled_w > 0) return VP8_STATUS_UNSUPPORTED_FEATURE;
     ImgDesc im;
     memset(&im, 0, sizeof(im));
     im.width = (uint16_t)c.width; im.height = (uint16_t)c.height;
     im.csp = (uint8_t)csp; im.flags = (uint8_t)(flags | VP8B_FLAG_LOSSLESS); im.out_stride = stride;
     im.out_w = im.width; im.out_h = im.height;
     if (crop_w > 0) { im.crop_x = (uint16_t)crop_x; im.crop_y = (uint16_t)crop_y; im.out_w = (uint16_t)crop_w; im.out_h = (uint16_t)crop_h; }
+    if (scaled_w > 0) { im.dst_w = (uint16_t)scaled_w; im.dst_h = (uint16_t)scaled_h; }
     const uint8_t* bits = data + c.frame_offset;
     const uint32_t nbits = (uint32_t)c.frame_size;
     std::vector<uint8_t> scratch(AL_SCRATCH_BYTES + 64);
@@ -87,11 +87,13 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
     }
     // every failure of a whole-picture decode is a bitstream error (vp8l_dec.c:1292,1479-1488; nothing suspends outside idec)
     if (ah.status != AL_OK) return ah.status == AL_UNSUPPORTED ? VP8_STATUS_UNSUPPORTED_FEATURE : VP8_STATUS_BITSTREAM_ERROR;
+    const int fw = im.dst_w ? im.dst_w : im.out_w, fh = im.dst_h ? im.dst_h : im.out_h;
     const size_t need = (csp == 11 || csp == 12)
-        ? (size_t)im.out_stride * im.out_h + 2 * (size_t)((im.out_w + 1) / 2) * ((im.out_h + 1) / 2) + (csp == 12 ? (size_t)im.out_w * im.out_h : 0)
-        : (size_t)im.out_stride * (im.out_h - 1) + (size_t)im.out_w * ((csp == 0 || csp == 2) ? 3 : (csp == 5 || csp == 6 || csp == 10) ? 2 : 4);
+        ? (size_t)im.out_stride * fh + 2 * (size_t)((fw + 1) / 2) * ((fh + 1) / 2) + (csp == 12 ? (size_t)fw * fh : 0)
+        : (size_t)im.out_stride * (fh - 1) + (size_t)fw * ((csp == 0 || csp == 2) ? 3 : (csp == 5 || csp == 6 || csp == 10) ? 2 : 4);
     if (need > out_size) return VP8_STATUS_INVALID_PARAM;
-    vp8l_finish_picture(&ah, im, coded.data(), tdata.data(), out, 0, 1);
+    std::vector<uint8_t> pm(im.dst_w ? 4 * (size_t)im.out_w * im.out_h + 16 : 16);
+    vp8l_finish_picture(&ah, im, coded.data(), tdata.data(), out, pm.data(), 0, 1);
     return VP8_STATUS_OK;
   }
   if (c.part0_size > c.frame_size - 10) return VP8_STATUS_NOT_ENOUGH_DATA;

@@ -357,3 +357,36 @@ def test_emu_lossless_matches_reference(ref):
             assert s_emu == s_ref, (len(data), k, s_ref, s_emu)
             if s_ref == 0:
                 assert np.array_equal(want.reshape(-1), got)
+
+
+def test_emu_lossless_scaling_matches_reference(ref):
+    """options.use_scaling on lossless pictures (vp8l_dec.c:560-737): premultiply, four-channel rescaler, un-premultiply with
+    the reference's spill-over, then the colourspace conversion or ConvertToYUVA on the scaled rows; up and down, crop + scale,
+    flip, translucent and opaque pictures."""
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR])
+    L = C.CDLL(os.path.join(EMU_DIR, "libvp8_emu.so"))
+    L.emu_decode_scaled.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_int, C.c_int, C.c_int]
+    rng = np.random.default_rng(22)
+    for data in lossless_cases(ref)[:9]:
+        _, f = ref.features(data)
+        W, H = f["width"], f["height"]
+        for it in range(6):
+            crop = None
+            if it >= 4:
+                cw, ch = int(rng.integers(1, W + 1)), int(rng.integers(1, H + 1))
+                crop = (int(rng.integers(0, W - cw + 1)), int(rng.integers(0, H - ch + 1)), cw, ch)
+            w, h = (crop[2], crop[3]) if crop else (W, H)
+            req = [(max(1, w // 2), max(1, h // 3)), (w * 2 + 1, h + 7), (max(1, w - 1), h * 3), (0, max(1, h // 2)), (w + 5, 0),
+                   (int(rng.integers(1, 2 * w + 2)), int(rng.integers(1, 2 * h + 2)))][it]
+            flip = int(rng.integers(0, 2))
+            for csp in (1, 7, 12, 10, 9, 0, 11, 6):
+                s_ref, (sw, sh), want = ref.decode_scaled(data, csp, 8 if flip else 0, crop, req)
+                assert s_ref == 0, (len(data), req, crop, s_ref)
+                n = (sw * sh + 2 * ((sw + 1) // 2) * ((sh + 1) // 2) + (sw * sh if csp == 12 else 0)) if csp in (11, 12) else sw * sh * ref.BPP[csp]
+                out = np.zeros(max(n, 16), np.uint8)
+                c = crop or (0, 0, 0, 0)
+                st = L.emu_decode_scaled(data, len(data), csp, 4 if flip else 0, out.ctypes.data, out.size,
+                                         sw if csp in (11, 12) else sw * ref.BPP[csp], c[0], c[1], c[2], c[3], sw, sh)
+                assert st == 0, (len(data), req, crop, csp, st)
+                assert np.array_equal(out[:n], want), (len(data), W, H, req, crop, flip, csp, (sw, sh))

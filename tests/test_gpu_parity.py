@@ -454,7 +454,7 @@ def test_lossless_pictures(W, ref, manifest, amanifest):
     """Whole-picture VP8L on the device: every transform, colour cache, meta-Huffman groups and
     palette bundling (tests/test_emu.py:lossless_cases), every colourspace incl. MODE_YUV / MODE_YUVA, crop windows at odd offsets, flip;
     then one batch mixing lossless, lossy, alpha and damaged lossless files (per-item status as the reference's), decoded
-    twice on the resident path; scaling a lossless picture is refused."""
+    twice on the resident path; options.use_scaling on lossless pictures (four-channel rescaler between premultiply and un-premultiply)."""
     from test_emu import lossless_cases
     cases = lossless_cases(ref)
     rng = np.random.default_rng(6)
@@ -472,7 +472,12 @@ def test_lossless_pictures(W, ref, manifest, amanifest):
                 st, out = W.WebPDecode(data, csp, crop=crop, flip=flip)
                 assert st == s_ref == 0, (len(data), crop, flip, csp, st, W.last_error())
                 assert np.array_equal(out.reshape(-1)[:want.size], want), (len(data), w, h, crop, flip, csp)
-        assert W.WebPDecode(data, W.MODE_RGBA, scaled=(max(1, w // 2), max(1, h // 2)))[0] == W.VP8_STATUS_UNSUPPORTED_FEATURE
+        for csp, req, crop in ((W.MODE_RGBA, (max(1, w // 2), max(1, h // 3)), None), (W.MODE_rgbA, (w * 2 + 1, h + 7), None),
+                               (W.MODE_YUVA, (max(1, w - 1), 0), None), (W.MODE_BGR, (w + 3, max(1, h // 2)), (w // 4, h // 4, max(1, w // 2), max(1, h // 2)))):
+            s_ref, (sw, sh), want = ref.decode_scaled(data, csp, 0, crop, req)
+            st, out = W.WebPDecode(data, csp, crop=crop, scaled=req)
+            assert st == s_ref == 0, (len(data), csp, req, crop, st, W.last_error())
+            assert np.array_equal(out.reshape(-1)[:want.size], want), (len(data), w, h, csp, req, crop)
     datas = list(cases) + [e["data"] for e in manifest[:3]] + [e["data"] for e in amanifest[:3]]
     for data in cases[:8]:
         for k in range(4):
