@@ -105,7 +105,7 @@ def test_dwebp_over_the_cuda_decoder(callers, manifest, amanifest, tmp_path):
     with open(lossless, "wb") as f:
         f.write(callers.encode(pix, callers.EncCfg(75, 4, lossless=1)))
     jobs = [(os.path.join(GOLDEN, "alpha_lowq_200x150.webp"), variants), (os.path.join(GOLDEN, "normal_8part_400x300.webp"), some),
-            (lossless, variants[1:3] + variants[5:6] + variants[12:14] + variants[16:17])]
+            (lossless, variants[1:3] + variants[5:6] + variants[12:17])]
     jobs += [(os.path.join(GOLDEN, e["file"]), (["-pam"],)) for e in (manifest[0], manifest[3], amanifest[0], amanifest[2])]
     n = 0
     for src, todo in jobs:
