@@ -32,6 +32,8 @@ WORKLOADS = {
     "vp8_1080p_q75_m4_8part_normal_rgba": (1920, 1080, 4096, "cfg_normal_8part", "RGBA"),
     "vp8_256x256_q80_rgbA": (256, 256, 65536, "cfg_default", "rgbA"),
     "vp8_4096x4096_q90_alpha_rgba": (4096, 4096, 256, "cfg_alpha_q90", "RGBA"),
+    # not a BASELINE config: whole-picture VP8L through the same entry point, one thread per picture
+    "vp8l_1080p_lossless_rgba": (1920, 1080, 1024, "cfg_lossless", "RGBA"),
 }
 METRIC = "webp_lossy_decode_mpix_per_s_rgba"
 UNIT = "Mpix/s"
@@ -301,7 +303,8 @@ def main():
         "recon_ms": 1.5 * px + 16 * n_mb,                             # planes out (+ the non-zero coefficients in)
         "filter_ms": 3.0 * px,                                        # planes read + written
         "emit_ms": 5.5 * px,                                          # 1.5 B/px in, 4 B/px out
-        "alpha_ms": 1.0 * px if "alpha" in args.workload else 0.0,    # one alpha byte per pixel out (the chunk itself is tiny)
+        # ALPH: one alpha byte per pixel out (the chunk itself is tiny); whole-picture VP8L: file in, 4 B/px out
+        "alpha_ms": 1.0 * px if "alpha" in args.workload else (file_bytes + 4.0 * px) if "vp8l" in args.workload else 0.0,
     }
     kernels = {k[:-3]: {"ms": round(per[k], 3), "alg_GBps": round(alg[k] / (per[k] * 1e-3) / 1e9, 1) if per[k] > 0 else None,
                         "share": round(per[k] / max(sum(per.values()), 1e-9), 3)} for k in per}

@@ -54,6 +54,10 @@ def cfg_alpha_q90():                     # config 5: q90 with an ALPH chunk, gra
     return EncCfg(90.0, 4, alpha_filtering=2)
 
 
+def cfg_lossless(quality=75.0):          # whole-picture VP8L (not a BASELINE config)
+    return EncCfg(quality, 4, lossless=1)
+
+
 _lib = None
 
 
