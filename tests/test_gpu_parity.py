@@ -504,3 +504,40 @@ def test_lossless_pictures(W, ref, manifest, amanifest):
     data = ref.encode(big, ref.EncCfg(50, 2, lossless=1))
     st, out = W.WebPDecode(data, W.MODE_RGBA)
     assert st == 0 and np.array_equal(out.reshape(1080, 1920, 4), big)
+
+
+def test_concurrent_callers(W, ref, manifest, amanifest):
+    """SURVEY.md 8(b) threading row: WebPDecode / WebPDecodeBatch are callable from many host threads at once (ctypes drops
+    the GIL around the call; the library serialises batches per device). Eight threads, each decoding its own mix of
+    files in its own colourspace, several rounds; every result equals the reference's."""
+    import threading
+    files = [e["data"] for e in list(manifest) + list(amanifest)]
+    csps = (W.MODE_RGBA, W.MODE_BGR, W.MODE_YUV, W.MODE_rgbA, W.MODE_RGB_565, W.MODE_ARGB, W.MODE_YUVA, W.MODE_bgrA)
+    want = {(i, csp): ref.decode(d, csp, 0) for i, d in enumerate(files) for csp in csps}
+    errors = []
+
+    def worker(t):
+        try:
+            csp = csps[t]
+            for rnd in range(3):
+                if (t + rnd) % 2 == 0:
+                    for i in range(t % 3, len(files), 3):
+                        st, out = W.WebPDecode(files[i], csp)
+                        s_ref, w = want[(i, csp)]
+                        if st != s_ref or (st == 0 and not np.array_equal(out.reshape(-1)[:w.size], w.reshape(-1))):
+                            errors.append((t, rnd, i, st, s_ref))
+                else:
+                    sts, outs = W.decode_batch(files, csp, device=0)
+                    for i, (st, out) in enumerate(zip(sts, outs)):
+                        s_ref, w = want[(i, csp)]
+                        if st != s_ref or (st == 0 and not np.array_equal(out.reshape(-1)[:w.size], w.reshape(-1))):
+                            errors.append((t, rnd, i, st, s_ref))
+        except Exception as e:   # noqa: BLE001 - report whatever a thread hit
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors[:5]
