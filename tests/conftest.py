@@ -44,6 +44,17 @@ def amanifest():
 
 
 @pytest.fixture(scope="session")
+def lmanifest():
+    """Lossless (VP8L) fixtures (reference-produced hashes, tests/golden/make_golden_lossless.py)."""
+    with open(os.path.join(GOLDEN, "manifest_lossless.json")) as f:
+        m = json.load(f)
+    for e in m:
+        with open(os.path.join(GOLDEN, e["file"]), "rb") as f:
+            e["data"] = f.read()
+    return m
+
+
+@pytest.fixture(scope="session")
 def port():
     """The plain-C oracle (oracle/vp8_oracle.c); compiled on demand with gcc."""
     from oracle import portwebp

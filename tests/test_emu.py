@@ -390,3 +390,23 @@ def test_emu_lossless_scaling_matches_reference(ref):
                                          sw if csp in (11, 12) else sw * ref.BPP[csp], c[0], c[1], c[2], c[3], sw, sh)
                 assert st == 0, (len(data), req, crop, csp, st)
                 assert np.array_equal(out[:n], want), (len(data), W, H, req, crop, flip, csp, (sw, sh))
+
+
+def test_emu_lossless_matches_manifest(lmanifest):
+    """The committed lossless fixtures through the device code's host build: sha256 of every (colourspace, flags) combination
+    equals the reference's recorded one (no reference library needed at run time)."""
+    import hashlib
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR])
+    L = C.CDLL(os.path.join(EMU_DIR, "libvp8_emu.so"))
+    L.emu_decode_window.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_int]
+    bpps = {0: 3, 1: 4, 2: 3, 3: 4, 4: 4, 5: 2, 6: 2, 7: 4, 8: 4, 9: 4, 10: 2}
+    for e in lmanifest:
+        w, h = e["features"]["width"], e["features"]["height"]
+        for key, want in e["sha256"].items():
+            csp, fl = map(int, key.split(":"))
+            n = (w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2) + (w * h if csp == 12 else 0)) if csp in (11, 12) else w * h * bpps[csp]
+            out = np.zeros(max(n, 16), np.uint8)
+            st = L.emu_decode_window(e["data"], len(e["data"]), csp, 0, out.ctypes.data, out.size, w if csp in (11, 12) else w * bpps[csp],
+                                     0, 0, 0, 0)
+            assert st == 0 and hashlib.sha256(out[:n].tobytes()).hexdigest() == want, (e["file"], key)

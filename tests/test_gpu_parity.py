@@ -541,3 +541,14 @@ def test_concurrent_callers(W, ref, manifest, amanifest):
     for th in threads:
         th.join()
     assert not errors, errors[:5]
+
+
+def test_lossless_matches_manifest(W, lmanifest):
+    for e in lmanifest:
+        st, f = W.WebPGetFeatures(e["data"])
+        assert st == 0 and f == e["features"]
+        for key, want in e["sha256"].items():
+            csp, fl = map(int, key.split(":"))
+            st, out = W.WebPDecode(e["data"], csp)
+            assert st == 0, (e["file"], key, st, W.last_error())
+            assert sha(out) == want, (e["file"], key)

@@ -92,3 +92,13 @@ def test_port_equals_reference_on_damaged_files(ref, port, manifest):
             assert np.array_equal(a, b)
         f1, f2 = ref.features(c), port.features(c)
         assert f1[0] == f2[0] and (f1[0] != 0 or f1[1] == f2[1]), (len(c), f1, f2)
+
+
+def test_reference_matches_lossless_manifest(ref, lmanifest):
+    for e in lmanifest:
+        st, f = ref.features(e["data"])
+        assert st == 0 and f == e["features"]
+        for key, want in e["sha256"].items():
+            csp, fl = map(int, key.split(":"))
+            st, out = ref.decode(e["data"], csp, fl)
+            assert st == 0 and sha(out) == want, (e["file"], key)
