@@ -36,16 +36,18 @@
 
 // ---------------------------------------------------------------------------------------------------------
 #define MODES_WARPS 28   // one image per warp, seven per SM sub-partition (see k_parse_tokens)
+// `lanes` images per warp (lanes 0 .. lanes-1 each parse their own image, SIMT-divergent where their syntax differs).
 __global__ void __launch_bounds__(32 * MODES_WARPS, 1) k_parse_modes(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
                                                                      FrameHdr* hdrs, uint32_t* mbinfo, int first, int count, int ipb,
-                                                                     int max_mb_w) {
+                                                                     int max_mb_w, int lanes) {
   extern __shared__ uint32_t top_modes_all[];   // ipb x max_mb_w words
   __shared__ uint8_t bprob[900];                // kVp8BModeProba, out of the constant bank (indexed per decode)
-  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int warp = (threadIdx.x >> 5) * lanes + lane;   // slot of this lane's image inside the block
   const int i = blockIdx.x * ipb + warp;
   for (int k = threadIdx.x; k < 900; k += blockDim.x) bprob[k] = kVp8BModeProba[k];
   __syncthreads();
-  if (i >= count || (threadIdx.x & 31) != 0) return;
+  if (i >= count || lane >= lanes || warp >= ipb) return;
   const ImgDesc im = imgs[first + i];
   FrameHdr* h = &hdrs[first + i];
   // a whole-picture VP8L image has no VP8 frame: a status that is not OK makes every pixel kernel pass it by; its own
@@ -569,18 +571,43 @@ static int pack_per_block(int count, int max_per_block) {   // as many as fit, b
   return ipb;
 }
 
+// Images per warp of the mode parse. The kernel is issue-bound (one dependent chain per image, ~27 instructions per decode),
+// so with enough images to keep ~3.5 warps on every SM sub-partition anyway, several images share one warp's instruction
+// stream as SIMT lanes: they diverge where their syntax differs (an i4x4 macroblock beside an i16 one) and meet again at
+// every macroblock end. Measured (profiles/r01t_modes_lanes.log): 65536 thumbnails 25.6 -> 3.9 ms at 32 lanes, 16384: 6.4 ->
+// 2.5 ms at 8, 8192: 3.2 -> 2.0 ms at 4; 4096 full-HD images are best left at one image per warp (30.3 ms; 31.3 at 2 lanes,
+// 43.7 at 7: too few warps left to hide the chain's latency). WEBP_B200_MODES_LANES forces a value.
+static int modes_lanes_for(int count) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("WEBP_B200_MODES_LANES"); forced = (e != NULL && atoi(e) >= 1 && atoi(e) <= 32) ? atoi(e) : 0; }
+  if (forced > 0) return forced;
+  if (count < 6144) return 1;
+  int want = (count + 1036) / 2072, lanes = 1;   // 2072 = 148 SMs x 4 sub-partitions x 3.5 warps
+  while (lanes * 2 <= want && lanes < 32) lanes *= 2;
+  return lanes;
+}
+
 extern "C" void vp8k_parse_modes(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,
                                  int first, int count, int max_mb_w) {
-  int ipb = MODES_WARPS;
-  while (ipb > 1 && (size_t)ipb * max_mb_w * 4 > 200u * 1024u) --ipb;
-  ipb = pack_per_block(count, ipb);
+  int lanes = modes_lanes_for(count);
+  if ((size_t)lanes * max_mb_w * 4 > 200u * 1024u) lanes = 1;   // the lanes' top-mode rows share the block's shared memory
+  int ipb;
+  if (lanes == 1) {
+    ipb = MODES_WARPS;
+    while (ipb > 1 && (size_t)ipb * max_mb_w * 4 > 200u * 1024u) --ipb;
+    ipb = pack_per_block(count, ipb);
+  } else {
+    ipb = 4 * lanes;   // one warp per sub-partition and block; many blocks per SM
+    while (ipb > lanes && (size_t)ipb * max_mb_w * 4 > 200u * 1024u) ipb -= lanes;
+  }
   static size_t configured = 0;
   const size_t smem = (size_t)ipb * max_mb_w * 4;
   if (smem > configured) {
     cudaFuncSetAttribute(k_parse_modes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  k_parse_modes<<<(count + ipb - 1) / ipb, 32 * ipb, smem, s>>>(arena, imgs, hdrs, mbinfo, first, count, ipb, max_mb_w);
+  const int warps = (ipb + lanes - 1) / lanes;
+  k_parse_modes<<<(count + ipb - 1) / ipb, 32 * warps, smem, s>>>(arena, imgs, hdrs, mbinfo, first, count, ipb, max_mb_w, lanes);
 }
 
 static int env_int(const char* name) {
