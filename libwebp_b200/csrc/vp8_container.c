@@ -134,7 +134,8 @@ VP8StatusCode vp8b_get_features(const uint8_t* data, size_t size, WebPBitstreamF
   memset(f, 0, sizeof(*f));
   if (st == VP8_STATUS_OK || (st == VP8_STATUS_NOT_ENOUGH_DATA && c.found_vp8x)) {
     f->width = c.width; f->height = c.height;
-    f->has_alpha = c.has_alpha; f->has_animation = c.has_animation; f->format = c.format;
+    /* an ALPH chunk seen before the data ran out counts too (webp_dec.c:397-404) */
+    f->has_alpha = c.has_alpha | c.has_alph_chunk; f->has_animation = c.has_animation; f->format = c.format;
     return VP8_STATUS_OK;
   }
   return (VP8StatusCode)st;

@@ -560,8 +560,9 @@ AL_NOINLINE int alph_decode_pixels(const uint8_t* alph, uint32_t alph_size, int 
   // The reference runs DecodeAlphaData (vp8l_dec.c:1035-1116) when the only transform is the palette, there is no
   // colour cache and every group's R, B and A codes are zero-bit (Is8bOptimizable, :857-870), DecodeImageData
   // (:1138-1293) otherwise. Same symbols either way; what differs is when running out of data counts as a failure,
-  // so keep both shapes.
-  int use_8b = (hd->ntrans == 1 && hd->ttype[0] == AL_T_COLOR_INDEXING && cache_bits == 0);
+  // so keep both shapes. A whole VP8L picture always goes through DecodeImageData (VP8LDecodeImage, :1761-1765; the 8-bit
+  // path is chosen by VP8LDecodeAlphaHeader alone, :1633-1641): there, data that runs out on the last symbol is an error.
+  int use_8b = (!hd->lossless && hd->ntrans == 1 && hd->ttype[0] == AL_T_COLOR_INDEXING && cache_bits == 0);
   for (int g = 0; g < num_groups && use_8b; ++g) use_8b = groups[g].trivial_literal;
   hd->use_8b = (uint8_t)use_8b;
   const int cache_size = cache_bits ? (1 << cache_bits) : 0, cache_shift = 32 - cache_bits;

@@ -68,6 +68,23 @@ def test_features_match_oracle(product, port, manifest):
     assert (w.value, h.value) == (manifest[0]["features"]["width"], manifest[0]["features"]["height"])
 
 
+def test_features_of_a_vp8x_file_cut_before_the_frame(product, ref, amanifest):
+    """WebPGetFeatures answers from the VP8X chunk when the data ends before the frame header (webp_dec.c:397-404): has_alpha is
+    the VP8X flag OR "an ALPH chunk went by", so a file whose flag was cleared still reports alpha once its ALPH chunk is in.
+    (Found by tools/fuzz_emu.py.)"""
+    for e in amanifest:
+        d = bytearray(e["data"])
+        i = d.find(b"ALPH")
+        vp8 = i + 8 + int.from_bytes(d[i + 4:i + 8], "little")
+        vp8 += vp8 & 1
+        assert d[vp8:vp8 + 4] == b"VP8 "
+        for flags in (d[20], d[20] & ~0x10, 0x8d):
+            d[20] = flags
+            for n in (i + 4, vp8 - 1, vp8, vp8 + 8, vp8 + 10, vp8 + 17, vp8 + 18, len(d)):
+                cut = bytes(d[:n])
+                assert product.WebPGetFeatures(cut) == ref.features(cut), (e["file"], hex(flags), n)
+
+
 def test_host_side_failures_need_no_gpu(product, port, manifest):
     """Errors decided by the container walk come back with the reference's status codes without touching a GPU."""
     d = manifest[1]["data"]

@@ -359,6 +359,45 @@ def test_emu_lossless_matches_reference(ref):
                 assert np.array_equal(want.reshape(-1), got)
 
 
+def test_emu_lossless_palette_picture_losing_its_last_bits(ref, lmanifest):
+    """A whole VP8L picture always runs the reference's 32-bit pixel loop (VP8LDecodeImage -> DecodeImageData, vp8l_dec.c:1761-1765);
+    only an ALPH payload may take the 8-bit one. They differ in when running out of data is an error: the 32-bit loop fails as
+    soon as the reader is past the end, even with every pixel decoded. Palette pictures (the 8-bit loop's shape) with the tail
+    cut off or damaged must therefore end like the reference. (Found by tools/fuzz_emu.py.)"""
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR])
+    L = C.CDLL(os.path.join(EMU_DIR, "libvp8_emu.so"))
+    L.emu_decode_window.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_int]
+    rng = np.random.default_rng(17)
+    seen = {0: 0, 3: 0}
+    golden = next(e["data"] for e in lmanifest if e["file"] == "lossless_palette5_121x50.webp")
+    known = []
+    for at, val in ((704, 0x97), (1476, 0xfd), (755, 0xd5), (1436, 0xd7), (235, 0xb0)):   # decoded to the last pixel, reader past the end
+        b = bytearray(golden)
+        b[at] = val
+        known.append(bytes(b))
+    for data in [golden] + lossless_cases(ref)[6:11]:      # palette pictures
+        _, f = ref.features(data)
+        W, H = f["width"], f["height"]
+        cases = [data[:-k] for k in range(1, 12)] + (known if data is golden else [])
+        for _ in range(200 if data is golden else 60):
+            b = bytearray(data)
+            b[int(rng.integers(len(b) // 4, len(b)))] ^= int(rng.integers(1, 256))
+            cases.append(bytes(b))
+        for b in cases:
+            s_ref, want = ref.decode(b, 1, 0)
+            out = np.zeros(W * H * 4, np.uint8)
+            s_emu = L.emu_decode_window(b, len(b), 1, 0, out.ctypes.data, out.size, W * 4, 0, 0, 0, 0)
+            if ref.features(b)[0] == 7:
+                assert s_ref == 3          # WebPDecode's mapping of the probe's NOT_ENOUGH_DATA (the harness has no probe)
+                continue
+            assert s_emu == s_ref, (len(data), len(b), s_ref, s_emu)
+            seen[s_ref] = seen.get(s_ref, 0) + 1
+            if s_ref == 0:
+                assert np.array_equal(want.reshape(-1), out)
+    assert seen[0] > 20 and seen[3] > 20
+
+
 def test_emu_lossless_scaling_matches_reference(ref):
     """options.use_scaling on lossless pictures (vp8l_dec.c:560-737): premultiply, four-channel rescaler, un-premultiply with
     the reference's spill-over, then the colourspace conversion or ConvertToYUVA on the scaled rows; up and down, crop + scale,

@@ -552,3 +552,24 @@ def test_lossless_matches_manifest(W, lmanifest):
             st, out = W.WebPDecode(e["data"], csp)
             assert st == 0, (e["file"], key, st, W.last_error())
             assert sha(out) == want, (e["file"], key)
+
+
+@pytest.mark.gpu
+def test_lossless_palette_picture_losing_its_last_bits(W, lmanifest):
+    """A whole VP8L picture runs the reference's 32-bit pixel loop even when it is a plain palette picture (VP8LDecodeImage,
+    vp8l_dec.c:1761-1765): decoded to the last pixel with the reader past the end of the data is a BITSTREAM_ERROR there, unlike
+    in an ALPH payload. The reference's statuses for these five damaged copies of a golden file were recorded by
+    tools/fuzz_emu.py (all 3); the intact file and a copy damaged where it still decodes ride along in the same batch."""
+    golden = next(e for e in lmanifest if e["file"] == "lossless_palette5_121x50.webp")
+    datas, want = [golden["data"]], [0]
+    for at, val in ((704, 0x97), (1476, 0xfd), (755, 0xd5), (1436, 0xd7), (235, 0xb0)):
+        b = bytearray(golden["data"])
+        b[at] = val
+        datas.append(bytes(b))
+        want.append(3)
+    sts, outs = W.decode_batch(datas, W.MODE_RGBA)
+    assert list(sts) == want, list(sts)
+    assert sha(outs[0]) == golden["sha256"]["1:0"]
+    for d, s_want in zip(datas, want):      # and one at a time through WebPDecode
+        st, out = W.WebPDecode(d, W.MODE_RGBA)
+        assert st == s_want, (st, s_want)
