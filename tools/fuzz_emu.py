@@ -215,7 +215,7 @@ def worker(args):
         elif differs and feat_ok and s_emu != s_ref and damaged_in_both_chunks(R, b, data, s_ref, s_emu):
             hist["known_both_chunks_damaged"] = hist.get("known_both_chunks_damaged", 0) + 1
             ok += 1
-        elif differs and feat_ok and s_emu == 4 and f["format"] == 2:
+        elif differs and feat_ok and s_emu == 4 and (f["format"] == 2 or b"ALPH" in chunk_spans(b)):
             # a damaged VP8L header that announces more than the two limits of vp8l_alpha_core.h allow (> 4096 prefix-code groups,
             # a palette that is not the first transform): refused before the reference would have met the damage
             hist["known_vp8l_limit"] = hist.get("known_vp8l_limit", 0) + 1
