@@ -3,7 +3,8 @@
 with random settings (quality 0..100, method 0..6, 1..4 segments, both loop filters at every strength and sharpness, 1..8
 token partitions, sns, alpha quality / filtering, lossless) are decoded by the compiled reference (oracle/_ref) and by the
 host build of the device code (tests/emu) with random decoding options: every colourspace, crop window, flip,
-no_fancy_upsampling, bypass_filtering, each token-parse run style. Status and bytes must be equal. Exit code 1 otherwise.
+no_fancy_upsampling, bypass_filtering, each token-parse run style, use_scaling (up, down, one axis derived, 1x1, on a crop
+window), dithering_strength and alpha_dithering_strength. Status and bytes must be equal. Exit code 1 otherwise.
 
     python tools/fuzz_encode.py --seconds 300 --jobs 7 [--seed 1]
 """
@@ -65,6 +66,11 @@ def worker(args):
     L.emu_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
     L.emu_decode_window.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_int]
+    L.emu_decode_scaled.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_int, C.c_int, C.c_int]
+    L.emu_decode_dithered.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                      C.c_int, C.c_int, C.c_int]
+    L.emu_set_alpha_dithering.argtypes = [C.c_int]
     rng = np.random.default_rng(seed * 1000 + wid)
     t0 = time.time()
     files = decodes = 0
@@ -84,6 +90,46 @@ def worker(args):
         cfg = R.EncCfg(q, int(rng.integers(0, 7)), **kw)
         data = R.encode(picture(R, rng, w, h, alpha), cfg)
         files += 1
+        # options.use_scaling (on a crop window half of the time) and options.dithering_strength / alpha_dithering_strength
+        for it in range(2):
+            csp = CSPS[int(rng.integers(0, len(CSPS)))]
+            crop = None
+            if rng.random() < 0.5:
+                cw, ch = int(rng.integers(1, w + 1)), int(rng.integers(1, h + 1))
+                crop = (int(rng.integers(0, w - cw + 1)), int(rng.integers(0, h - ch + 1)), cw, ch)
+            cw, ch = (crop[2], crop[3]) if crop else (w, h)
+            c = crop or (0, 0, 0, 0)
+            flip = int(rng.integers(0, 2))
+            if it == 0:
+                req = [(int(rng.integers(1, 2 * cw + 2)), int(rng.integers(1, 2 * ch + 2))), (0, int(rng.integers(1, 2 * ch + 2))),
+                       (int(rng.integers(1, 2 * cw + 2)), 0), (1, 1), (int(rng.integers(1, 9)), int(rng.integers(1, 9))),
+                       (cw, ch), (int(rng.integers(1, 6 * cw + 2)), int(rng.integers(1, 3)))][int(rng.integers(0, 7))]
+                s_ref, (sw, sh), want = R.decode_scaled(data, csp, 8 if flip else 0, crop, req)
+                bpp = 1 if csp in (11, 12) else R.BPP[csp]
+                n = (sw * sh + 2 * ((sw + 1) // 2) * ((sh + 1) // 2) + (sw * sh if csp == 12 else 0)) if csp in (11, 12) else sw * sh * bpp
+                out = np.zeros(max(n, 16), np.uint8)
+                s_emu = L.emu_decode_scaled(data, len(data), csp, 4 if flip else 0, out.ctypes.data, out.size, sw * bpp,
+                                            c[0], c[1], c[2], c[3], sw, sh) if s_ref == 0 else s_ref
+                what = "scale%s" % (req,)
+            else:
+                if lossless:
+                    continue
+                strength, astrength = int(rng.choice([50, 100, 30, 1])), int(rng.choice([0, 100, 50])) if alpha else 0
+                s_ref, want = R.decode_dithered(data, csp, 8 if flip else 0, crop, strength, astrength)
+                bpp = 1 if csp in (11, 12) else R.BPP[csp]
+                n = want.size if s_ref == 0 else 16
+                out = np.zeros(max(n, 16), np.uint8)
+                L.emu_set_alpha_dithering(astrength)
+                s_emu = L.emu_decode_dithered(data, len(data), csp, 4 if flip else 0, out.ctypes.data, out.size, cw * bpp, strength,
+                                              c[0], c[1], c[2], c[3])
+                L.emu_set_alpha_dithering(0)
+                what = "dither(%d,%d)" % (strength, astrength)
+            decodes += 1
+            if s_emu != s_ref or s_ref != 0 or not np.array_equal(want.reshape(-1)[:n], out[:n]):
+                tag = "enc_w%d_%d_%s" % (wid, files, "s" if it == 0 else "d")
+                bad.append((tag, w, h, q, cfg.method, json.dumps(kw) + " " + what, csp, str(crop), flip, 0, 0, 0, s_ref, s_emu))
+                os.makedirs(os.path.join(ROOT, "gpurun_out", "fuzz"), exist_ok=True)
+                open(os.path.join(ROOT, "gpurun_out", "fuzz", tag + ".webp"), "wb").write(data)
         for it in range(4):
             csp = CSPS[int(rng.integers(0, len(CSPS)))]
             crop = None
