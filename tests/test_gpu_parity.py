@@ -573,3 +573,46 @@ def test_lossless_palette_picture_losing_its_last_bits(W, lmanifest):
     for d, s_want in zip(datas, want):      # and one at a time through WebPDecode
         st, out = W.WebPDecode(d, W.MODE_RGBA)
         assert st == s_want, (st, s_want)
+
+
+@pytest.mark.gpu
+def test_extreme_dimensions(W, ref):
+    """The format's largest dimensions (14 bits: 16383) on one axis at a time -- 1024 macroblocks per row, 1024 macroblock rows --
+    lossy with 1 and 8 token partitions and both loop filters, with an ALPH chunk, and lossless; alone, mixed into one batch with
+    small pictures (the wave's shared-memory layouts are sized by its widest picture), and as enough streams for the lockstep
+    parser to be the default choice. Every picture against the compiled reference."""
+    rng = np.random.default_rng(5)
+
+    def pic(w, h, alpha=False):
+        p = np.zeros((h, w, 4), np.uint8)
+        p[..., :3] = rng.integers(0, 256, (h, w, 3), dtype=np.uint8) // 4 * 2 + (np.arange(w)[None, :, None] // 64 % 2 * 60).astype(np.uint8)
+        p[..., 3] = (np.arange(w)[None, :] * 7 + np.arange(h)[:, None] * 3) % 256 if alpha else 255
+        return p
+
+    big = [ref.encode(pic(16383, 17), ref.EncCfg(60, 2, partitions=3, segments=4, filter_type=1)),
+           ref.encode(pic(17, 16383), ref.EncCfg(60, 2, partitions=3, segments=4, filter_type=1)),
+           ref.encode(pic(16383, 33), ref.EncCfg(75, 4, partitions=0, segments=1, filter_type=0)),
+           ref.encode(pic(16383, 20, True), ref.EncCfg(80, 4, alpha_filtering=2)),
+           ref.encode(pic(21, 16383, True), ref.EncCfg(80, 4, alpha_filtering=1, alpha_quality=50)),
+           ref.encode(pic(16383, 9), ref.EncCfg(75, 2, lossless=1)),
+           ref.encode(pic(9, 16383, True), ref.EncCfg(75, 2, lossless=1))]
+    small = [ref.encode(ref.synth(48 + 16 * k, 40 + 8 * k, 7700 + k), ref.cfg_default(60 + 5 * k)) for k in range(6)]
+    for csp in (W.MODE_RGBA, W.MODE_YUV, W.MODE_rgbA):
+        wants = [ref.decode(d, csp, 0) for d in big + small]
+        for d, (st_want, want) in zip(big, wants):       # one at a time
+            st, out = W.WebPDecode(d, csp)
+            assert st == st_want == 0, (csp, len(d), st)
+            assert np.array_equal(out.reshape(-1), want.reshape(-1)), (csp, len(d))
+        datas = [x for pair in zip(big, small) for x in pair] + big[len(small):]
+        order = [(big + small).index(d) for d in datas]
+        sts, outs = W.decode_batch(datas, csp)
+        for i, j in enumerate(order):
+            assert sts[i] == 0, (csp, i, sts[i])
+            assert np.array_equal(outs[i].reshape(-1), wants[j][1].reshape(-1)), (csp, i)
+    # many wide streams: the lockstep parser with 1024-macroblock context rows
+    for d in (big[0], big[2]):
+        st_want, want = ref.decode(d, W.MODE_RGBA, 0)
+        sts, outs = W.decode_batch([d] * 300, W.MODE_RGBA)
+        assert st_want == 0 and all(s == 0 for s in sts)
+        for i in (0, 1, 149, 298, 299):
+            assert np.array_equal(outs[i].reshape(-1), want.reshape(-1)), i
