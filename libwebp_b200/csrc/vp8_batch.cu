@@ -284,6 +284,10 @@ static VP8StatusCode plan_item(WebPBatchItem* it, const WebPBatchOptions& opt, V
     const int cw = o->crop_width, ch = o->crop_height;
     if (x < 0 || y < 0 || cw <= 0 || ch <= 0 || x >= ow || cw > ow || cw > ow - x || y >= oh || ch > oh || ch > oh - y)
       return VP8_STATUS_INVALID_PARAM;
+    // a lossless picture is cropped at the offsets as given, not snapped (WebPIoInitFromOptions snaps for YUV420 sources
+    // only, webp_dec.c:809-817; VP8LDecodeImage hands it MODE_BGRA, vp8l_dec.c:1722-1726): the window must fit there too
+    if (c->is_lossless && (o->crop_left >= ow || cw > ow - o->crop_left || o->crop_top >= oh || ch > oh - o->crop_top))
+      return VP8_STATUS_INVALID_PARAM;
     ow = cw; oh = ch;
   }
   if (o->use_scaling) {   // WebPAllocateDecBuffer, buffer_dec.c:197-205; WebPRescalerGetScaledDimensions, rescaler_utils.c:86-118

@@ -165,3 +165,37 @@ def test_incremental_protocol_without_device(product, manifest):
     L.WebPIDelete(idec)
     assert not L.WebPIDecode(b"junkjunkjunkjunkjunk", 20, None)                                  # features must parse
     assert L.WebPIAppend(None, data, 10) == product.VP8_STATUS_INVALID_PARAM
+
+
+def test_lossless_crop_window_is_checked_at_the_offsets_as_given(product, lmanifest):
+    """WebPAllocateDecBuffer checks the crop window at offsets snapped to even (buffer_dec.c:184-195), the lossless decoder
+    then crops at the offsets as given (WebPIoInitFromOptions snaps for YUV420 sources only, webp_dec.c:809-817) and refuses a
+    window that overhangs there: INVALID_PARAM, decided on the host. (Found by tools/fuzz_options.py.)"""
+    L = product.lib()
+    e = next(x for x in lmanifest if x["file"] == "lossless_alpha_83x61.webp")
+    for (x, y, cw, ch), want in (((61, 3, 23, 57), 2), ((60, 3, 23, 57), product.VP8_STATUS_USER_ABORT), ((10, 41, 18, 21), 2),
+                                 ((10, 40, 18, 21), product.VP8_STATUS_USER_ABORT), ((83, 0, 1, 1), 2), ((0, 61, 1, 1), 2)):
+        cfg = product.WebPDecoderConfig()
+        L.WebPInitDecoderConfigInternal(C.byref(cfg), 0x0209)
+        cfg.options.use_cropping = 1
+        cfg.options.crop_left, cfg.options.crop_top, cfg.options.crop_width, cfg.options.crop_height = x, y, cw, ch
+        st = L.WebPDecode(e["data"], len(e["data"]), C.byref(cfg))
+        L.WebPFreeDecBuffer(C.byref(cfg.output))
+        if product.device_count() > 0 and want == product.VP8_STATUS_USER_ABORT:
+            want = 0      # a GPU is present: the window is legal, so it decodes
+        assert st == want, ((x, y, cw, ch), st, want)
+
+
+def test_option_and_buffer_screening_matches_reference(product, ref):
+    """A short run of tools/fuzz_options.py: random WebPDecoderConfig contents (colourspace, crop, scaling, flip, internal /
+    external buffers with strides and sizes around the smallest legal values, missing planes) through the reference and the
+    product's host side; every refusal equal, nothing the reference decodes refused. Needs a machine without a GPU (there
+    "let through" shows as USER_ABORT)."""
+    import subprocess
+    import sys
+    if product.device_count() > 0:
+        pytest.skip("compares host-side refusals where no device can decode")
+    from conftest import ROOT
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_options.py"), "--cases", "6000", "--seed", "11"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
