@@ -26,6 +26,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=100000)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--damage", type=float, default=0.0, help="fraction of cases that use a mutated file (tools/fuzz_emu.py)")
     a = ap.parse_args()
     import libwebp_b200 as W
     from oracle import refwebp as R
@@ -44,6 +45,9 @@ def main():
     arena = np.zeros(1 << 24, np.uint8)      # external buffers live here; sizes are claimed, never more than the arena
     base = arena.ctypes.data
     hist, bad = {}, []
+    seen_pairs = set()
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from fuzz_emu import mutate
 
     def near(v):
         r = rng.random()
@@ -51,6 +55,12 @@ def main():
 
     for case in range(a.cases):
         name, data, f = files[int(rng.integers(0, len(files)))]
+        damaged = rng.random() < a.damage
+        if damaged:
+            data = mutate(rng, data)
+            sf, f2 = R.features(data)
+            if sf == 0 and f2["width"] * f2["height"] <= (1 << 18):
+                f = f2
         w, h = f["width"], f["height"]
         csp = int(rng.integers(0, 13)) if rng.random() < 0.95 else int(rng.integers(-2, 16))
         opt = {}
@@ -113,12 +123,20 @@ def main():
             P.WebPFreeDecBuffer(C.byref(cfgs[1].output))
         hist[s_ref] = hist.get(s_ref, 0) + 1
         want = W.VP8_STATUS_USER_ABORT if s_ref == 0 else s_ref
+        if damaged and s_prod == W.VP8_STATUS_USER_ABORT:
+            continue      # a damaged payload is judged on the device: nothing to compare here
+        if damaged and s_prod != want:
+            hist["damaged_order"] = hist.get("damaged_order", 0) + 1
+            if len(bad) < 1000 and (s_ref, s_prod) not in seen_pairs:
+                seen_pairs.add((s_ref, s_prod))
+                print("DAMAGED %s ref=%d product=%d opt=%s" % (name, s_ref, s_prod, json.dumps(opt)))
+            continue
         if s_prod != want:
             bad.append((name, csp, external, json.dumps(opt), json.dumps({k: v for k, v in buf.items() if k not in ("rgba", "y", "u", "v", "a")}),
                         [k for k in ("rgba", "y", "u", "v", "a") if k in buf and buf[k] is None], (w, h), s_ref, s_prod))
     for t in bad[:40]:
         print("MISMATCH %s csp=%d external=%d opt=%s buf=%s null=%s size=%s ref=%d product=%d" % t)
-    print(json.dumps({"cases": a.cases, "mismatches": len(bad), "reference_status_histogram": {str(k): v for k, v in sorted(hist.items())},
+    print(json.dumps({"cases": a.cases, "mismatches": len(bad), "reference_status_histogram": {str(k): v for k, v in sorted(hist.items(), key=lambda kv: str(kv[0]))},
                       "seed": a.seed}))
     sys.exit(1 if bad else 0)
 
