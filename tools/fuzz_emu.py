@@ -173,9 +173,11 @@ def damaged_in_both_chunks(R, b, data, s_ref, s_emu):
 
 
 def worker(args):
-    wid, seed, seconds, kinds = args
+    wid, seed, seconds, kinds, use_port = args
     from oracle import refwebp as R
     L = load_emu()
+    if use_port:      # the plain-C restatement (oracle/vp8_oracle.c) in the emulation's place: pins the oracle itself (lossy, opaque)
+        from oracle import portwebp as PORT
     rng = np.random.default_rng(seed * 1000 + wid)
     S = seeds(kinds)
     t0 = time.time()
@@ -193,6 +195,27 @@ def worker(args):
         variant = (0, 2, 8, 24, 56)[int(rng.integers(0, 5))]
         # the product's order (plan_item, vp8_batch.cu): feature probe first, its NOT_ENOUGH_DATA becomes BITSTREAM_ERROR
         # (webp_dec.c:761-767), any other failure is returned as it is; only then the decode proper
+        if use_port:
+            if sf == 0 and (f["format"] != 1 or f["has_alpha"]):
+                continue      # the restatement covers opaque lossy pictures only
+            n += 1
+            hist[s_ref] = hist.get(s_ref, 0) + 1
+            s_port, got = PORT.decode(b, PORT.RGBA, 0)
+            same = s_port == s_ref and PORT.features(b) == (sf, f if sf == 0 else PORT.features(b)[1])
+            if same and s_ref == 0 and not np.array_equal(want.reshape(-1), got.reshape(-1)):
+                _, want = R.decode(b, R.MODE_RGBA, 0, simd=False)
+                hist["simd_vs_c"] = hist.get("simd_vs_c", 0) + 1
+                same = np.array_equal(want.reshape(-1), got.reshape(-1))
+            if not same and sf == 0 and partition_starts_with_ff(b):     # the restatement reads byte by byte: same class as the product's
+                hist["known_ff_first_byte"] = hist.get("known_ff_first_byte", 0) + 1
+                same = True
+            if same:
+                ok += 1
+            else:
+                bad.append(("port_%s_w%d_%d" % (name, wid, n), s_ref, s_port, -1))
+                os.makedirs(os.path.join(ROOT, "gpurun_out", "fuzz"), exist_ok=True)
+                open(os.path.join(ROOT, "gpurun_out", "fuzz", "port_%s_w%d_%d.webp" % (name, wid, n)), "wb").write(b)
+            continue
         pf = (C.c_int * 10)()
         s_emu = L.vp8b_get_features(b, len(b), pf)
         feat_ok = s_emu == sf and (sf != 0 or list(pf[:5]) == [f["width"], f["height"], f["has_alpha"], f["has_animation"], f["format"]])
@@ -236,11 +259,12 @@ def main():
     ap.add_argument("--jobs", type=int, default=max(1, (os.cpu_count() or 2) - 1))
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--kinds", default="lossy,alpha,lossless")
+    ap.add_argument("--port", action="store_true", help="check the oracle's C restatement instead (use with --kinds lossy)")
     a = ap.parse_args()
     subprocess.check_call(["make", "-s", "-C", EMU_DIR])
     kinds = a.kinds.split(",")
     with mp.get_context("spawn").Pool(a.jobs) as p:
-        res = p.map(worker, [(i, a.seed, a.seconds, kinds) for i in range(a.jobs)])
+        res = p.map(worker, [(i, a.seed, a.seconds, kinds, a.port) for i in range(a.jobs)])
     n = sum(r[0] for r in res); ok = sum(r[1] for r in res)
     hist = {}
     for r in res:
@@ -249,7 +273,7 @@ def main():
         for t in r[2]:
             print("MISMATCH file=%s ref=%d emu=%d variant=%d" % t)
     print(json.dumps({"cases": n, "equal": ok, "mismatches": n - ok, "reference_status_histogram": {str(k): v for k, v in sorted(hist.items(), key=lambda kv: str(kv[0]))},
-                      "seed": a.seed, "jobs": a.jobs, "seconds": a.seconds, "kinds": kinds}))
+                      "seed": a.seed, "jobs": a.jobs, "seconds": a.seconds, "kinds": kinds, "decoder": "port" if a.port else "emu"}))
     sys.exit(0 if n == ok else 1)
 
 
