@@ -616,3 +616,16 @@ def test_extreme_dimensions(W, ref):
         assert st_want == 0 and all(s == 0 for s in sts)
         for i in (0, 1, 149, 298, 299):
             assert np.array_equal(outs[i].reshape(-1), want.reshape(-1)), i
+
+
+@pytest.mark.gpu
+def test_damage_campaign_prefix(ref):
+    """The first batches of tools/fuzz_gpu.py (seed 1: a prefix of the run logged in profiles/r01u_fuzz_gpu.log): mutated golden
+    files, every eighth one intact, 2048 per WebPDecodeBatch call; per-item status and pixels against the compiled reference."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_gpu.py"), "--seconds", "8", "--batch", "2048", "--seed", "1"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-1000:])
