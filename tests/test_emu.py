@@ -449,3 +449,16 @@ def test_emu_lossless_matches_manifest(lmanifest):
             st = L.emu_decode_window(e["data"], len(e["data"]), csp, 0, out.ctypes.data, out.size, w if csp in (11, 12) else w * bpps[csp],
                                      0, 0, 0, 0)
             assert st == 0 and hashlib.sha256(out[:n].tobytes()).hexdigest() == want, (e["file"], key)
+
+
+@pytest.mark.parametrize("tool,args", [("fuzz_emu.py", ["--seed", "3"]), ("fuzz_encode.py", ["--seed", "4"]),
+                                       ("fuzz_emu.py", ["--seed", "5", "--port", "--kinds", "lossy"])])
+def test_campaign_prefix(ref, tool, args):
+    """A few seconds of each parity campaign under tools/ (seeds whose long runs are logged in profiles/r01u_fuzz_*.log): mutated
+    files and random encoder settings x decoding options, compiled reference against the device code's host build; the
+    oracle's C restatement against the compiled reference. The case sequence per worker is fixed by the seed; only how far it
+    gets depends on the machine."""
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", tool), "--seconds", "6", "--jobs", "2"] + args,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-1000:])
