@@ -6,10 +6,12 @@
  * reference line it replaces. What actually runs underneath is different: WebPDecode() is a batch of one on
  * the GPU (see webp/decode_batch.h); there is no CPU decode path.
  *
- * Supported here: VP8 lossy key frames, colourspaces RGB/RGBA/BGR/BGRA/ARGB/rgbA/bgrA/Argb/YUV, options
- * bypass_filtering and no_fancy_upsampling, internal or external output memory. Anything else (lossless,
- * ALPH chunks, animation, crop/scale/flip/dither, 565/4444, the incremental API) fails loudly with
- * VP8_STATUS_UNSUPPORTED_FEATURE; nothing falls back to the host. */
+ * Supported here: everything the reference's decoder takes through this header -- VP8 lossy key frames with or without
+ * an ALPH chunk, whole-picture VP8L, all thirteen colourspaces, bypass_filtering, no_fancy_upsampling, cropping,
+ * scaling, flip, dithering_strength, alpha_dithering_strength, internal or external output memory, the incremental
+ * API (as a buffering shim: pixels appear when the last byte has arrived). A top-level animated file is
+ * VP8_STATUS_UNSUPPORTED_FEATURE here as in the reference (webp_dec.c:427-429). Nothing falls back to the host:
+ * without a usable CUDA device every decode fails with VP8_STATUS_USER_ABORT. */
 #ifndef WEBP_WEBP_DECODE_H_
 #define WEBP_WEBP_DECODE_H_
 

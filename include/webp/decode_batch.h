@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define WEBP_BATCH_ABI_VERSION 0x0100
+#define WEBP_BATCH_ABI_VERSION 0x0101   /* 0x0101: devices / num_devices / stream carved out of WebPBatchOptions::pad (same size) */
 
 typedef struct WebPBatchItem {
   const uint8_t* data;       /* one complete .webp file (RIFF or bare VP8), host memory */
@@ -38,7 +38,15 @@ typedef struct WebPBatchOptions {
   size_t scratch_bytes;      /* cap on device scratch per wave (0 = default: 85% of free memory) */
   int pipeline_waves;        /* split the batch into this many waves (0 = default: one wave unless scratch memory
                                 forces more; downloads overlap the pixel stages chunk by chunk either way) */
-  uint32_t pad[7];
+  int num_devices;           /* > 1: shard the items over `devices`, item i on devices[i % num_devices]; one host
+                                thread per device inside the call, no collective, no peer access (images are
+                                independent). 0 = `device` alone. */
+  const int* devices;        /* num_devices CUDA ordinals (read during the call only) */
+  void* stream;              /* cudaStream_t of the caller on `device` (single device only), NULL = the library's own:
+                                uploads and kernels are queued on it, so the batch runs behind whatever the caller
+                                queued there before and ahead of what it queues after WebPBatchSubmit()/WebPBatchDecode()
+                                returned; host-output pixel copies travel on the library's copy stream either way */
+  uint32_t pad[2];
 } WebPBatchOptions;
 
 WEBP_EXTERN int WebPBatchOptionsInitInternal(WebPBatchOptions*, int);
@@ -66,12 +74,26 @@ WEBP_EXTERN VP8StatusCode WebPBatchDecode(WebPBatch* batch);
 WEBP_EXTERN VP8StatusCode WebPBatchDownload(WebPBatch* batch);
 WEBP_EXTERN void WebPBatchDestroy(WebPBatch* batch);
 
+/* Asynchronous form of WebPDecodeBatch(), for callers that keep the device busy:
+ *   WebPBatchSubmit  = WebPBatchCreate + everything queued on the device (uploads, kernels and, for WEBP_BATCH_HOST,
+ *                      the pixel copies) WITHOUT waiting for any of it;
+ *   WebPBatchWait    waits, fills items[i].status, returns what WebPDecodeBatch() would have returned;
+ *   WebPBatchDestroy releases the batch.
+ * Between Submit and Wait the input bytes and the output buffers of the items belong to the library (page-locked
+ * memory keeps the copies asynchronous). Batches submitted to one device run in submission order, and the pixels of
+ * batch k travel to the host while the kernels of batch k+1 run: two batches in flight hide the whole download.
+ * Two host threads calling WebPDecodeBatch() on one device pipeline the same way. */
+WEBP_EXTERN WebPBatch* WebPBatchSubmit(WebPBatchItem* items, int num_items, const WebPBatchOptions* options,
+                                       VP8StatusCode* status);
+WEBP_EXTERN VP8StatusCode WebPBatchWait(WebPBatch* batch);
+
 typedef struct WebPBatchPlane {
   void* y_or_rgba; /* device pointer: RGB-family pixels, or the Y plane for MODE_YUV */
   void* u;
   void* v;
   int stride, uv_stride;
   int width, height;
+  int device;      /* CUDA ordinal the pointers belong to (differs per item when the batch was sharded) */
 } WebPBatchPlane;
 WEBP_EXTERN int WebPBatchOutput(const WebPBatch* batch, int index, WebPBatchPlane* plane);
 
@@ -93,6 +115,14 @@ WEBP_EXTERN int WebPBatchGetTimings(const WebPBatch* batch, WebPBatchTimings* t)
 /* Page-locked host memory for inputs/outputs (plain malloc works too, just slower over PCIe). */
 WEBP_EXTERN void* WebPBatchHostAlloc(size_t size);
 WEBP_EXTERN void WebPBatchHostFree(void* ptr);
+
+/* Device memory kept between calls. Blocks released by a finished batch are cached (cudaMalloc/cudaFree of tens of GB
+ * cost 0.1-1 s) up to a limit, by default a quarter of the device's memory (environment: WEBP_B200_CACHE_GB).
+ * WebPBatchSetCacheLimit returns the previous limit; WebPBatchTrimCache gives every cached block, the shared wave
+ * scratch and the library's page-locked staging back to the driver and returns the device bytes released.
+ * device -1 = the calling thread's current device. */
+WEBP_EXTERN size_t WebPBatchSetCacheLimit(int device, size_t bytes);
+WEBP_EXTERN size_t WebPBatchTrimCache(int device);
 
 /* Number of CUDA devices visible to the library; 0 means WebPDecode*() will fail (there is no CPU path). */
 WEBP_EXTERN int WebPBatchDeviceCount(void);

@@ -28,7 +28,7 @@ BPP = {MODE_RGB: 3, MODE_RGBA: 4, MODE_BGR: 3, MODE_BGRA: 4, MODE_ARGB: 4, MODE_
  VP8_STATUS_UNSUPPORTED_FEATURE, VP8_STATUS_SUSPENDED, VP8_STATUS_USER_ABORT, VP8_STATUS_NOT_ENOUGH_DATA) = range(8)
 
 WEBP_DECODER_ABI_VERSION = 0x0209
-WEBP_BATCH_ABI_VERSION = 0x0100
+WEBP_BATCH_ABI_VERSION = 0x0101
 WEBP_BATCH_HOST, WEBP_BATCH_DEVICE = 0, 1
 
 
@@ -75,12 +75,13 @@ class WebPBatchItem(C.Structure):
 
 class WebPBatchOptions(C.Structure):
     _fields_ = [("device", C.c_int), ("output", C.c_int), ("scratch_bytes", C.c_size_t),
-                ("pipeline_waves", C.c_int), ("pad", C.c_uint32 * 7)]
+                ("pipeline_waves", C.c_int), ("num_devices", C.c_int), ("devices", C.POINTER(C.c_int)),
+                ("stream", C.c_void_p), ("pad", C.c_uint32 * 2)]
 
 
 class WebPBatchPlane(C.Structure):
     _fields_ = [("y_or_rgba", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p), ("stride", C.c_int),
-                ("uv_stride", C.c_int), ("width", C.c_int), ("height", C.c_int)]
+                ("uv_stride", C.c_int), ("width", C.c_int), ("height", C.c_int), ("device", C.c_int)]
 
 
 class WebPBatchTimings(C.Structure):
@@ -98,7 +99,8 @@ EXPORTS = [  # every symbol include/webp/*.h declares
     "WebPInitDecoderConfigInternal", "WebPDecode", "WebPMalloc", "WebPFree", "VP8GetCPUInfo",
     "WebPBatchOptionsInitInternal", "WebPDecodeBatch", "WebPBatchCreate", "WebPBatchDecode", "WebPBatchDownload",
     "WebPBatchDestroy", "WebPBatchOutput", "WebPBatchGetTimings", "WebPBatchHostAlloc", "WebPBatchHostFree",
-    "WebPBatchDeviceCount", "WebPBatchLastError",
+    "WebPBatchDeviceCount", "WebPBatchLastError", "WebPBatchSubmit", "WebPBatchWait", "WebPBatchSetCacheLimit",
+    "WebPBatchTrimCache",
 ]
 
 _lib = None
@@ -136,12 +138,29 @@ def lib():
         L.WebPBatchHostAlloc.argtypes = [C.c_size_t]
         L.WebPBatchHostFree.argtypes = [C.c_void_p]
         L.WebPBatchLastError.restype = C.c_char_p
+        L.WebPBatchSubmit.restype = C.c_void_p
+        L.WebPBatchSubmit.argtypes = [C.POINTER(WebPBatchItem), C.c_int, C.POINTER(WebPBatchOptions), C.POINTER(C.c_int)]
+        L.WebPBatchWait.argtypes = [C.c_void_p]
+        L.WebPBatchSetCacheLimit.restype = C.c_size_t
+        L.WebPBatchSetCacheLimit.argtypes = [C.c_int, C.c_size_t]
+        L.WebPBatchTrimCache.restype = C.c_size_t
+        L.WebPBatchTrimCache.argtypes = [C.c_int]
         _lib = L
     return _lib
 
 
 def device_count():
     return lib().WebPBatchDeviceCount()
+
+
+def set_cache_limit(nbytes, device=-1):
+    """WebPBatchSetCacheLimit: device memory the library may keep between batches; returns the previous limit."""
+    return lib().WebPBatchSetCacheLimit(device, int(nbytes))
+
+
+def trim_cache(device=-1):
+    """WebPBatchTrimCache: give cached device blocks back to the driver; returns the bytes released."""
+    return lib().WebPBatchTrimCache(device)
 
 
 def last_error():
@@ -264,6 +283,29 @@ class HostBuffer:
             self.ptr = None
 
 
+class HostArena:
+    """One page-locked allocation handed out in pieces (page-locking tens of GB takes seconds: a caller that runs
+    many batches does it once). take() never frees; reset() starts over."""
+
+    def __init__(self, nbytes):
+        self.buf = HostBuffer(nbytes)
+        self.used = 0
+
+    def take(self, nbytes):
+        nbytes = max(int(nbytes), 1)
+        start = (self.used + 4095) & ~4095
+        if start + nbytes > self.buf.nbytes:
+            raise MemoryError(f"HostArena: {nbytes} bytes wanted, {self.buf.nbytes - start} left")
+        self.used = start + nbytes
+        return self.buf.array[start:start + nbytes]
+
+    def reset(self):
+        self.used = 0
+
+    def free(self):
+        self.buf.free()
+
+
 class Batch:
     """A batch of .webp files bound to one device: items, configs, packed input and output host buffers.
 
@@ -271,7 +313,7 @@ class Batch:
     back to back in another (one D2H copy per 256 MiB run). `datas` may repeat the same bytes object."""
 
     def __init__(self, datas, csp=MODE_RGBA, bypass_filtering=False, no_fancy_upsampling=False, device=-1,
-                 output=WEBP_BATCH_HOST, pinned=True, scratch_bytes=0):
+                 output=WEBP_BATCH_HOST, pinned=True, scratch_bytes=0, devices=None, stream=None, arena=None):
         L = lib()
         self.n = len(datas)
         self.csp = csp
@@ -279,8 +321,9 @@ class Batch:
         self.configs = (WebPDecoderConfig * self.n)()
         sizes = [len(d) for d in datas]
         offs = np.concatenate([[0], np.cumsum([(s + 15) & ~15 for s in sizes])]).astype(np.int64)
-        self.in_buf = HostBuffer(int(offs[-1]) + 64) if pinned else None
-        in_arr = self.in_buf.array if pinned else np.zeros(int(offs[-1]) + 64, np.uint8)
+        self.in_buf = HostBuffer(int(offs[-1]) + 64) if (pinned and arena is None) else None
+        in_arr = (arena.take(int(offs[-1]) + 64) if arena is not None else
+                  self.in_buf.array if pinned else np.zeros(int(offs[-1]) + 64, np.uint8))
         self._in_arr = in_arr
         self.dims = []
         out_off = [0]
@@ -295,8 +338,9 @@ class Batch:
         self.output_mode = output
         self.out_buf = None
         if output == WEBP_BATCH_HOST:
-            self.out_buf = HostBuffer(out_off[-1] + 64) if pinned else None
-            self._out_arr = self.out_buf.array if pinned else np.zeros(out_off[-1] + 64, np.uint8)
+            self.out_buf = HostBuffer(out_off[-1] + 64) if (pinned and arena is None) else None
+            self._out_arr = (arena.take(out_off[-1] + 64) if arena is not None else
+                             self.out_buf.array if pinned else np.zeros(out_off[-1] + 64, np.uint8))
         base_in = in_arr.ctypes.data
         for i in range(self.n):
             cfg = self.configs[i]
@@ -315,6 +359,12 @@ class Batch:
         self.opt.device = device
         self.opt.output = output
         self.opt.scratch_bytes = scratch_bytes
+        if devices:   # WebPBatchOptions::devices: item i on devices[i % len(devices)], sharded inside the library
+            self._devices = (C.c_int * len(devices))(*devices)
+            self.opt.devices = C.cast(self._devices, C.POINTER(C.c_int))
+            self.opt.num_devices = len(devices)
+        if stream:
+            self.opt.stream = stream
         self.handle = None
         self.h2d_bytes = int(sum(sizes))
         self.d2h_bytes = int(sum(out_bytes(csp, w, h) for (w, h) in self.dims)) if output == WEBP_BATCH_HOST else 0
@@ -323,6 +373,19 @@ class Batch:
     # -- one-shot path: what a caller of the C API does (host buffers in, host buffers out)
     def decode_oneshot(self):
         return lib().WebPDecodeBatch(self.items, self.n, C.byref(self.opt))
+
+    # -- asynchronous pair: everything queued by submit(), collected by wait() (two batches in flight hide the download)
+    def submit(self):
+        st = C.c_int()
+        self.handle = lib().WebPBatchSubmit(self.items, self.n, C.byref(self.opt), C.byref(st))
+        if not self.handle and st.value in (VP8_STATUS_USER_ABORT, VP8_STATUS_OUT_OF_MEMORY):
+            raise RuntimeError(f"WebPBatchSubmit failed ({st.value}): {last_error()}")
+        return st.value
+
+    def wait(self):
+        st = lib().WebPBatchWait(self.handle)
+        self.destroy()
+        return st
 
     # -- resident path
     def create(self):

@@ -12,7 +12,12 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "vp8_container.h"
@@ -63,21 +68,70 @@ extern "C" int WebPBatchOptionsInitInternal(WebPBatchOptions* o, int version) {
 // Per-device state: two streams and a small cache of device allocations so that repeated WebPDecode() calls
 // do not pay cudaMalloc/cudaFree every time.
 struct CachedBlock { void* p; size_t cap; };
+struct Owned { void* p = nullptr; size_t cap = 0; };
 
+// One per device. `mu` guards the ORDER in which work is queued on the streams, the block caches and the wave scratch;
+// it is held while a batch is planned into the streams, never while the host waits for the device. Several batches can
+// therefore be in flight on one device: their kernels run back to back on `stream`, and the pixels of batch k travel
+// to the host on `copy_stream` while the kernels of batch k+1 run (WebPBatchSubmit / WebPBatchWait, or simply two
+// caller threads in WebPDecodeBatch).
 struct DeviceCtx {
   int device = -1;
   bool ok = false;
   cudaStream_t stream = nullptr;        // kernels, uploads
-  cudaStream_t copy_stream = nullptr;   // pixel downloads, overlapped with the kernels of the next wave
+  cudaStream_t copy_stream = nullptr;   // pixel downloads, overlapped with the kernels of the next chunk / wave / batch
   cudaStream_t pixel_stream = nullptr;  // row bands: reconstruction / filter / output of one band while the next is parsed
-  std::mutex mu;          // one batch at a time per device
-  std::vector<CachedBlock> cache;
+  std::mutex mu;
+  std::vector<CachedBlock> cache;       // device blocks released by finished batches
   size_t cached_bytes = 0;
-  size_t cache_limit = 0;   // released blocks are kept for the next batch up to this many bytes
+  size_t cache_limit = 0;               // released blocks are kept for the next batch up to this many bytes
+  std::vector<CachedBlock> pinned;      // small page-locked host blocks (descriptors up, status words down)
+  // Per-wave scratch (MbInfo, coefficient tokens, planes, ...) is shared by every batch on the device: only the kernels
+  // touch it, and kernels of different batches are ordered (same stream, or through `scratch_free` when a caller
+  // brought a stream of its own).
+  Owned s_mbinfo, s_coeffs, s_tokens, s_mbtok, s_yuv, s_dither, s_band;
+  cudaEvent_t scratch_free = nullptr;   // recorded behind the last kernel queued so far
+  bool scratch_used = false;
+  // Pixel downloads are queued by a thread of their own. cudaMemcpyAsync returns at once only while the driver's queue
+  // has room: the 34 GB of a full batch are far more than it holds, and the caller that queued them inline sat in the
+  // call until most of them had MOVED -- which is why, in round 1, kernels launched after a download looked slow.
+  std::thread copier;
+  std::mutex copy_mu;
+  std::condition_variable copy_cv;
+  std::deque<std::function<void()>> copy_jobs;
 };
+
+static void copier_main(DeviceCtx* c) {
+  cudaSetDevice(c->device);
+  for (;;) {
+    std::function<void()> job;
+    {
+      std::unique_lock<std::mutex> lk(c->copy_mu);
+      c->copy_cv.wait(lk, [&]() { return !c->copy_jobs.empty(); });
+      job = std::move(c->copy_jobs.front());
+      c->copy_jobs.pop_front();
+    }
+    job();
+  }
+}
+
+static void copier_post(DeviceCtx* c, std::function<void()> job) {
+  { std::lock_guard<std::mutex> lk(c->copy_mu); c->copy_jobs.push_back(std::move(job)); }
+  c->copy_cv.notify_one();
+}
 
 static std::mutex g_ctx_mu;
 static DeviceCtx* g_ctx[64];
+
+// The calling thread's current device is put back when a library call returns.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+    if (prev != device) cudaSetDevice(device);
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 static DeviceCtx* get_ctx(int device) {
   if (device < 0) {
@@ -88,18 +142,33 @@ static DeviceCtx* get_ctx(int device) {
   if (g_ctx[device] == nullptr) {
     DeviceCtx* c = new DeviceCtx();
     c->device = device;
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->pixel_stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { set_error("CUDA device init (no usable GPU; this library has no CPU path)", e); cudaGetLastError(); delete c; return nullptr; }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->scratch_free, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = vp8k_init_device();   // per-device kernel attributes (dynamic shared memory opt-in)
+    if (e != cudaSuccess) {
+      set_error("CUDA device init (no usable GPU; this library has no CPU path)", e); cudaGetLastError();
+      if (prev >= 0) cudaSetDevice(prev);
+      delete c;
+      return nullptr;
+    }
     {
+      // Released device blocks are kept for the next batch (cudaMalloc / cudaFree of tens of GB cost 0.1-1 s) up to a
+      // quarter of the device's memory by default; WebPBatchSetCacheLimit() / WEBP_B200_CACHE_GB change it and
+      // WebPBatchTrimCache() gives everything back.
       size_t free_b = 0, total_b = 0;
       const char* env = getenv("WEBP_B200_CACHE_GB");
-      if (env != NULL) c->cache_limit = (size_t)atof(env) << 30;
-      else if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) c->cache_limit = (size_t)((double)free_b * 0.80);
+      if (env != NULL) c->cache_limit = (size_t)(atof(env) * (double)(1u << 30));
+      else if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) c->cache_limit = total_b / 4;
       cudaGetLastError();
     }
+    if (prev >= 0) cudaSetDevice(prev);
+    c->copier = std::thread(copier_main, c);
+    c->copier.detach();   // lives as long as the process, like the context
     c->ok = true;
     g_ctx[device] = c;
   }
@@ -131,8 +200,6 @@ static void* dev_alloc(DeviceCtx* c, size_t bytes) {
   return p;
 }
 
-struct Owned { void* p = nullptr; size_t cap = 0; };
-
 static bool own_alloc(DeviceCtx* c, Owned& o, size_t bytes) {
   o.cap = bytes ? bytes : 256;
   o.p = dev_alloc(c, o.cap);
@@ -148,6 +215,68 @@ static void own_free(DeviceCtx* c, Owned& o) {
     cudaFree(o.p);
   }
   o.p = nullptr; o.cap = 0;
+}
+
+// Small page-locked host blocks: what the library itself sends up (descriptors, launch lists) and brings down (status
+// words) must not sit in pageable memory, or cudaMemcpyAsync turns into a host-side wait in the middle of the queue.
+static void* pinned_alloc(DeviceCtx* c, size_t bytes, size_t* cap) {
+  bytes = (bytes + 4095) & ~(size_t)4095;
+  int best = -1;
+  for (size_t i = 0; i < c->pinned.size(); ++i) {
+    if (c->pinned[i].cap >= bytes && c->pinned[i].cap <= 4 * bytes && (best < 0 || c->pinned[i].cap < c->pinned[best].cap)) best = (int)i;
+  }
+  if (best >= 0) {
+    void* p = c->pinned[best].p; *cap = c->pinned[best].cap;
+    c->pinned.erase(c->pinned.begin() + best);
+    return p;
+  }
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { set_error("cudaHostAlloc", cudaGetLastError()); return nullptr; }
+  *cap = bytes;
+  return p;
+}
+static void pinned_free(DeviceCtx* c, void* p, size_t cap) {
+  if (p == nullptr) return;
+  if (c->pinned.size() < 32 && cap <= ((size_t)64 << 20)) c->pinned.push_back({ p, cap });
+  else cudaFreeHost(p);
+}
+
+static int resolve_device(int device) {
+  if (device >= 0) return device;
+  if (cudaGetDevice(&device) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return device;
+}
+
+// Gives every cached block of `device` (-1: the calling thread's current device) back to the driver. Blocks of batches
+// that are still alive are not touched. Returns the number of bytes released.
+extern "C" size_t WebPBatchTrimCache(int device) {
+  device = resolve_device(device);
+  if (device < 0 || device >= 64) return 0;
+  DeviceCtx* c;
+  { std::lock_guard<std::mutex> lk(g_ctx_mu); c = g_ctx[device]; }
+  if (c == nullptr) return 0;
+  DeviceGuard g(c->device);
+  std::lock_guard<std::mutex> lk(c->mu);
+  size_t released = c->cached_bytes;
+  cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->pixel_stream); cudaStreamSynchronize(c->copy_stream);
+  for (auto& b : c->cache) cudaFree(b.p);
+  c->cache.clear(); c->cached_bytes = 0;
+  Owned* scratch[] = { &c->s_mbinfo, &c->s_coeffs, &c->s_tokens, &c->s_mbtok, &c->s_yuv, &c->s_dither, &c->s_band };
+  for (Owned* o : scratch) { if (o->p != nullptr) { released += o->cap; cudaFree(o->p); o->p = nullptr; o->cap = 0; } }
+  for (auto& b : c->pinned) cudaFreeHost(b.p);
+  c->pinned.clear();
+  cudaGetLastError();
+  return released;
+}
+
+// Upper bound on the device memory the library keeps between batches on `device`; returns the previous bound.
+extern "C" size_t WebPBatchSetCacheLimit(int device, size_t bytes) {
+  DeviceCtx* c = get_ctx(device);
+  if (c == nullptr) return 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const size_t prev = c->cache_limit;
+  c->cache_limit = bytes;
+  return prev;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -233,21 +362,24 @@ struct WebPBatch {
   WebPBatchItem* items = nullptr;
   int n = 0;
   WebPBatchOptions opt;
+  cudaStream_t stream = nullptr;   // compute stream of this batch: the device's own, or the caller's (WebPBatchOptions::stream)
   std::vector<ItemPlan> plan;
   std::vector<ImgDesc> imgs;       // device images, wave-major
   std::vector<int> img_item;       // device image -> item
   std::vector<Wave> waves;
   std::vector<int> ids;            // token-parse launch lists
-  std::vector<int> statuses;       // host copy of FrameHdr::status
-  Owned d_in, d_imgs, d_hdrs, d_ids, d_mbinfo, d_coeffs, d_yuv, d_out;
-  Owned d_dither; // options.dithering_strength: 128 offsets per macroblock of a wave (allocated when an item asks for it)
-  bool any_dither = false;
+  int* statuses = nullptr;         // page-locked host copy of FrameHdr::status (m ints)
+  void* h_stage = nullptr;         // page-locked staging of the descriptors and launch lists on their way up
+  size_t h_status_cap = 0, h_stage_cap = 0;
+  Owned d_in, d_imgs, d_hdrs, d_ids, d_out;
+  size_t max_wave_mbs = 0;
+  bool any_dither = false;     // options.dithering_strength: 128 offsets per macroblock of a wave
   bool any_lossless = false;   // whole-picture VP8L images ride the ALPH machinery (VP8B_FLAG_LOSSLESS)
-  Owned d_band;   // row bands: TokResume[m] | uint16 top contexts [m][max_mb_w] | unfiltered top pixels [m][32 * max_mb_w]
   // images with an ALPH chunk
   std::vector<int> aimgs;              // their image indices
   std::vector<AlphaPlan> aplans;
-  std::vector<AlphaHdr> ahdrs;         // host copy after the header pass / after the decode
+  AlphaHdr* ahdrs = nullptr;           // page-locked host copy after the header pass / after the decode
+  size_t h_ahdrs_cap = 0;
   Owned d_aimgs, d_aplans, d_ahdrs, d_awork, d_awork2, d_alpha;
   bool alpha_planned = false;          // work areas sized from the headers (kept across repeated decodes)
   size_t out_total = 0;
@@ -256,8 +388,22 @@ struct WebPBatch {
   size_t ev_used = 0;
   struct Span { int stage, a, b; };
   std::vector<Span> spans;         // (stage, first event, second event) of every timed launch of the last decode
+  int e_begin = -1, e_end = -1;    // first / last event of the last decode on the compute stream
+  cudaEvent_t copy_done = nullptr; // behind the last pixel download of the last decode
+  bool copies_queued = false;
+  std::mutex job_mu;               // download jobs handed to the device's copier thread and not yet queued by it
+  std::condition_variable job_cv;
+  int jobs_pending = 0;
+  bool job_failed = false;
+  char job_error[256] = "";
+  int launches = 0;
   WebPBatchTimings timings;
+  bool queued = false;             // kernels are in the streams, results not yet collected (WebPBatchWait)
   bool decoded = false;
+  // WebPBatchOptions::devices: the parent only shards. Child g owns items g, g + G, ... (copies of the caller's
+  // WebPBatchItem; the configs they point to are the caller's) on devices[g].
+  std::vector<WebPBatch*> shards;
+  std::vector<WebPBatchItem> shard_items;
 };
 
 static void fail_all(WebPBatchItem* items, int n, VP8StatusCode st) {
@@ -267,7 +413,7 @@ static void fail_all(WebPBatchItem* items, int n, VP8StatusCode st) {
 // Host-side part of one item: container walk, option/colourspace screening, output buffer.
 static VP8StatusCode plan_item(WebPBatchItem* it, const WebPBatchOptions& opt, Vp8Container* c) {
   WebPDecoderConfig* cfg = it->config;
-  if (cfg == NULL) return VP8_STATUS_INVALID_PARAM;
+  if (cfg == NULL || it->data == NULL) return VP8_STATUS_INVALID_PARAM;   // webp_dec.c:756, GetFeatures webp_dec.c:693-695
   VP8StatusCode st = vp8b_get_features(it->data, it->data_size, &cfg->input);
   if (st != VP8_STATUS_OK) return st == VP8_STATUS_NOT_ENOUGH_DATA ? VP8_STATUS_BITSTREAM_ERROR : st;   // webp_dec.c:761-767
   st = (VP8StatusCode)vp8b_parse_container(it->data, it->data_size, 1, c);
@@ -323,10 +469,38 @@ static int batch_plan(WebPBatch* b, std::vector<Vp8Container>& cont) {
   return alive;
 }
 
+// The CUDA allocation (page-locked or registered host memory) that contains `p`, if CUDA knows one. One cudaMemcpyAsync
+// must not reach outside the allocation its first byte lies in: the bytes between two caller buffers are only ours to
+// read when both buffers sit in the same allocation (merged ranges used to span allocations).
+struct HostAlloc { const uint8_t* base = nullptr; size_t size = 0; bool known = false; };
+typedef int (*PointerGetAttributeFn)(void* data, int attribute, unsigned long long ptr);   // cuPointerGetAttribute
+static PointerGetAttributeFn pointer_get_attribute() {
+  static PointerGetAttributeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &f, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess) fn = (PointerGetAttributeFn)f;
+    cudaGetLastError();
+  });
+  return fn;
+}
+static HostAlloc host_alloc_of(const void* p) {
+  HostAlloc a;
+  PointerGetAttributeFn fn = pointer_get_attribute();
+  if (fn == nullptr) return a;
+  unsigned long long start = 0; size_t size = 0;
+  // CU_POINTER_ATTRIBUTE_RANGE_START_ADDR = 11, CU_POINTER_ATTRIBUTE_RANGE_SIZE = 12
+  if (fn(&start, 11, (unsigned long long)(uintptr_t)p) != 0 || fn(&size, 12, (unsigned long long)(uintptr_t)p) != 0 || size == 0) return a;
+  a.base = (const uint8_t*)(uintptr_t)start; a.size = size; a.known = true;
+  return a;
+}
+static inline uintptr_t page_of(const uint8_t* p) { return (uintptr_t)p >> 12; }
+
 static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
   DeviceCtx* ctx = b->ctx;
   const int n = b->n;
-  // ---- input ranges: merge host buffers that sit (almost) next to each other into single H2D copies
+  // ---- input ranges: host buffers that lie in the same allocation, close to each other, travel in one H2D copy
   std::vector<int> order;
   for (int i = 0; i < n; ++i) if (b->items[i].status == VP8_STATUS_OK) order.push_back(i);
   std::vector<int> by_addr(order);
@@ -334,12 +508,22 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
   std::vector<HostRange> ranges;
   std::vector<int> item_range(n, -1);
   size_t in_total = 256;
+  HostAlloc cur_alloc;
   for (int i : by_addr) {
     const uint8_t* p = b->items[i].data;
     const size_t sz = b->items[i].data_size;
     if (!ranges.empty()) {
       HostRange& r = ranges.back();
-      if (p >= r.base && p <= r.base + r.size + 4096) {
+      const uint8_t* rend = r.base + r.size;
+      bool merge = false;
+      if (p >= r.base && p + sz <= rend) merge = true;                          // inside what is copied anyway
+      else if (cur_alloc.known) merge = p >= r.base && p <= rend + 65536 && p + sz <= cur_alloc.base + cur_alloc.size;
+      else if (p >= r.base && p <= rend + 4095 && (p <= rend || page_of(p) - page_of(rend - 1) <= 1)) {
+        // memory CUDA does not know (pageable): the gap is readable when each of its bytes shares a page with a byte of
+        // one of the two buffers; the neighbour must be pageable as well
+        merge = !host_alloc_of(p).known;
+      }
+      if (merge) {
         const size_t end = (size_t)(p - r.base) + sz;
         if (end > r.size) r.size = end;
         item_range[i] = (int)ranges.size() - 1;
@@ -347,6 +531,8 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
       }
     }
     ranges.push_back({ p, sz, 0 });
+    cur_alloc = host_alloc_of(p);
+    if (cur_alloc.known && p + sz > cur_alloc.base + cur_alloc.size) cur_alloc.known = false;   // never expected
     item_range[i] = (int)ranges.size() - 1;
   }
   for (auto& r : ranges) { r.dev_off = in_total; in_total += align_up(r.size, 256) + 256; }
@@ -423,21 +609,27 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
     b->max_mb_h = std::max(b->max_mb_h, (int)d.mb_h);
   }
   const int m = (int)b->imgs.size();
-  b->statuses.assign(m, 0);
   if (m == 0) return true;
 
-  CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
+  // ---- page-locked staging for what the library itself moves: descriptors + launch lists up, status words down
+  b->statuses = (int*)pinned_alloc(ctx, sizeof(int) * (size_t)m, &b->h_status_cap);
+  b->h_stage = pinned_alloc(ctx, (sizeof(ImgDesc) + sizeof(int)) * (size_t)m, &b->h_stage_cap);
+  if (b->statuses == nullptr || b->h_stage == nullptr) return false;
+  memset(b->statuses, 0, sizeof(int) * (size_t)m);
   // ---- resident allocations: input (64 KB tail padding, see vp8_tokens_fsm.h:tk_lane_init), descriptors, headers, output
   if (!own_alloc(ctx, b->d_in, in_total + 65536) || !own_alloc(ctx, b->d_imgs, sizeof(ImgDesc) * m) ||
       !own_alloc(ctx, b->d_hdrs, sizeof(FrameHdr) * m) || !own_alloc(ctx, b->d_ids, sizeof(int) * m) ||
       !own_alloc(ctx, b->d_out, b->out_total + 256)) return false;
-  // ---- waves: per-macroblock scratch = 16 (MbInfo) + 800 (coefficients) + 384 (planes) bytes
-  const size_t per_mb = 16 + 2 * VP8B_COEFFS_PER_MB + 384;
+  // ---- waves: per-macroblock scratch = 16 (MbInfo) + 384 (planes) bytes + the levels: 8 (MbTok) + 4 * 384 reserved for
+  // the token stream (only what a macroblock really has is ever touched), or the 800-byte dense plane of the older parsers
+  const size_t per_mb = 16 + 384 + (vp8k_tokens_use_stream() ? 8 + 4 * VP8B_TOKENS_PER_MB : 2 * VP8B_COEFFS_PER_MB);
   size_t budget = b->opt.scratch_bytes;
   if (budget == 0) {
     size_t free_b = 0, total_b = 0;
     CU_TRY(cudaMemGetInfo(&free_b, &total_b), "cudaMemGetInfo");
-    budget = (size_t)((double)(free_b + ctx->cached_bytes) * 0.85);
+    const size_t scratch_now = ctx->s_mbinfo.cap + ctx->s_coeffs.cap + ctx->s_tokens.cap + ctx->s_mbtok.cap + ctx->s_yuv.cap +
+                               ctx->s_dither.cap + ctx->s_band.cap;
+    budget = (size_t)((double)(free_b + ctx->cached_bytes + scratch_now) * 0.85);
   }
   size_t wave_cap_mbs = std::max<size_t>(budget / per_mb, (size_t)b->max_mb_w * b->max_mb_h);
   {
@@ -476,10 +668,10 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
     }
     b->waves.push_back(w);
   }
-  size_t max_wave_mbs = 0;
+  b->max_wave_mbs = 0;
   b->ids.resize(m);
   for (auto& w : b->waves) {
-    max_wave_mbs = std::max(max_wave_mbs, w.mbs);
+    b->max_wave_mbs = std::max(b->max_wave_mbs, w.mbs);
     int pos = w.first;
     for (int lg = 0; lg < 4; ++lg) {
       w.ids_off[lg] = pos;
@@ -487,43 +679,54 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
       w.ids_cnt[lg] = pos - w.ids_off[lg];
     }
   }
-  if (!own_alloc(ctx, b->d_mbinfo, max_wave_mbs * 16) || !own_alloc(ctx, b->d_coeffs, max_wave_mbs * 2 * VP8B_COEFFS_PER_MB) ||
-      !own_alloc(ctx, b->d_yuv, max_wave_mbs * 384)) return false;
-  if (b->any_dither && !own_alloc(ctx, b->d_dither, max_wave_mbs * 128 + 256)) return false;
-  if (!own_alloc(ctx, b->d_band, align_up((size_t)m * sizeof(TokResume), 256) + align_up((size_t)m * 2 * b->max_mb_w, 256) +
-                                     (size_t)m * 32 * b->max_mb_w + 256)) return false;
-  // ---- uploads
-  cudaStream_t s = ctx->stream;
+  // ---- uploads: queued, not waited for (the caller's input buffers stay untouched until the batch is collected)
+  cudaStream_t s = b->stream;
   for (const auto& r : ranges) {
     CU_TRY(cudaMemcpyAsync((uint8_t*)b->d_in.p + r.dev_off, r.base, r.size, cudaMemcpyHostToDevice, s), "H2D input");
   }
-  CU_TRY(cudaMemcpyAsync(b->d_imgs.p, b->imgs.data(), sizeof(ImgDesc) * m, cudaMemcpyHostToDevice, s), "H2D descriptors");
-  CU_TRY(cudaMemcpyAsync(b->d_ids.p, b->ids.data(), sizeof(int) * m, cudaMemcpyHostToDevice, s), "H2D ids");
-  CU_TRY(vp8k_configure(b->max_mb_w, b->max_mb_h), "cudaFuncSetAttribute");
-  CU_TRY(cudaStreamSynchronize(s), "upload sync");
+  memcpy(b->h_stage, b->imgs.data(), sizeof(ImgDesc) * (size_t)m);
+  memcpy((uint8_t*)b->h_stage + sizeof(ImgDesc) * (size_t)m, b->ids.data(), sizeof(int) * (size_t)m);
+  CU_TRY(cudaMemcpyAsync(b->d_imgs.p, b->h_stage, sizeof(ImgDesc) * (size_t)m, cudaMemcpyHostToDevice, s), "H2D descriptors");
+  CU_TRY(cudaMemcpyAsync(b->d_ids.p, (uint8_t*)b->h_stage + sizeof(ImgDesc) * (size_t)m, sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, s), "H2D ids");
   return true;
+}
+
+// The device's wave scratch, grown to what this batch needs. Called with ctx->mu held, before the batch's kernels are
+// queued. A block that is replaced goes back to the cache (or to the driver, which waits for the device first), and
+// whoever gets it next uses it behind the kernels already queued: same stream, or behind `scratch_free`.
+static bool ensure_scratch(WebPBatch* b) {
+  DeviceCtx* c = b->ctx;
+  const int m = (int)b->imgs.size();
+  auto grow = [&](Owned& o, size_t bytes) -> bool {
+    if (o.p != nullptr && o.cap >= bytes) return true;
+    own_free(c, o);
+    return own_alloc(c, o, bytes);
+  };
+  if (!grow(c->s_mbinfo, b->max_wave_mbs * 16 + 256) || !grow(c->s_yuv, b->max_wave_mbs * 384 + 256)) return false;
+  if (vp8k_tokens_use_stream()) {
+    if (!grow(c->s_tokens, b->max_wave_mbs * 4 * VP8B_TOKENS_PER_MB + 256) || !grow(c->s_mbtok, b->max_wave_mbs * 8 + 256)) return false;
+  } else if (!grow(c->s_coeffs, b->max_wave_mbs * 2 * VP8B_COEFFS_PER_MB + 256)) return false;
+  if (b->any_dither && !grow(c->s_dither, b->max_wave_mbs * 128 + 256)) return false;
+  return grow(c->s_band, align_up((size_t)m * sizeof(TokResume), 256) + align_up((size_t)m * 2 * b->max_mb_w, 256) +
+                             (size_t)m * 32 * b->max_mb_w + 256);
 }
 
 static void batch_release(WebPBatch* b) {
   if (b == nullptr) return;
   if (b->ctx != nullptr) {
     DeviceCtx* c = b->ctx;
-    own_free(c, b->d_in); own_free(c, b->d_imgs); own_free(c, b->d_hdrs); own_free(c, b->d_ids);
-    own_free(c, b->d_mbinfo); own_free(c, b->d_coeffs); own_free(c, b->d_yuv); own_free(c, b->d_out); own_free(c, b->d_band); own_free(c, b->d_dither);
+    own_free(c, b->d_in); own_free(c, b->d_imgs); own_free(c, b->d_hdrs); own_free(c, b->d_ids); own_free(c, b->d_out);
+    pinned_free(c, b->statuses, b->h_status_cap); pinned_free(c, b->h_stage, b->h_stage_cap); pinned_free(c, b->ahdrs, b->h_ahdrs_cap);
+    if (b->copy_done != nullptr) cudaEventDestroy(b->copy_done);
     own_free(c, b->d_aimgs); own_free(c, b->d_aplans); own_free(c, b->d_ahdrs); own_free(c, b->d_awork); own_free(c, b->d_awork2); own_free(c, b->d_alpha);
     for (auto e : b->ev) if (e) cudaEventDestroy(e);
   }
   delete b;
 }
 
-extern "C" WebPBatch* WebPBatchCreate(WebPBatchItem* items, int num_items, const WebPBatchOptions* options,
-                                      VP8StatusCode* status) {
-  VP8StatusCode dummy;
-  if (status == NULL) status = &dummy;
+// One device: host checks, device memory, uploads queued. *status = OK with a batch, or why there is none.
+static WebPBatch* create_single(WebPBatchItem* items, int num_items, const WebPBatchOptions& opt, VP8StatusCode* status) {
   *status = VP8_STATUS_INVALID_PARAM;
-  if (items == NULL || num_items <= 0) return NULL;
-  WebPBatchOptions opt;
-  if (options != NULL) opt = *options; else WebPBatchOptionsInit(&opt);
   g_last_error[0] = 0;
   WebPBatch* b = new WebPBatch();
   b->items = items; b->n = num_items; b->opt = opt;
@@ -547,11 +750,13 @@ extern "C" WebPBatch* WebPBatchCreate(WebPBatchItem* items, int num_items, const
     return NULL;
   }
   b->ctx = ctx;
+  b->stream = opt.stream != NULL ? (cudaStream_t)opt.stream : ctx->stream;
+  DeviceGuard guard(ctx->device);
   ctx->mu.lock();
   const bool ok = batch_build(b, cont);
   ctx->mu.unlock();
   if (!ok) {
-    const VP8StatusCode st = strstr(g_last_error, "cudaMalloc") ? VP8_STATUS_OUT_OF_MEMORY : VP8_STATUS_USER_ABORT;
+    const VP8StatusCode st = (strstr(g_last_error, "cudaMalloc") || strstr(g_last_error, "cudaHostAlloc")) ? VP8_STATUS_OUT_OF_MEMORY : VP8_STATUS_USER_ABORT;
     for (int i = 0; i < num_items; ++i) {
       if (items[i].status == VP8_STATUS_OK) {
         items[i].status = st;
@@ -559,6 +764,7 @@ extern "C" WebPBatch* WebPBatchCreate(WebPBatchItem* items, int num_items, const
       }
     }
     *status = st;
+    cudaStreamSynchronize(b->stream); cudaGetLastError();   // uploads already queued read the caller's memory
     ctx->mu.lock(); batch_release(b); ctx->mu.unlock();
     return NULL;
   }
@@ -573,6 +779,7 @@ extern "C" WebPBatch* WebPBatchCreate(WebPBatchItem* items, int num_items, const
 static bool enqueue_download(WebPBatch* b, int first, int count, cudaStream_t s, bool check_status) {
   const uint8_t* dout = (const uint8_t*)b->d_out.p;
   uint8_t* run_host = nullptr; const uint8_t* run_dev = nullptr; size_t run_bytes = 0;
+  HostAlloc run_alloc;   // a run never leaves the allocation it started in (see batch_build)
   auto flush = [&]() -> bool {
     if (run_bytes > 0) CU_TRY(cudaMemcpyAsync(run_host, run_dev, run_bytes, cudaMemcpyDeviceToHost, s), "D2H pixels");
     run_bytes = 0;
@@ -599,11 +806,13 @@ static bool enqueue_download(WebPBatch* b, int first, int count, cudaStream_t s,
     const size_t row = (size_t)d.out_stride;
     const size_t bytes = row * final_h(d);
     if ((size_t)o->u.RGBA.stride == row) {
-      if (run_bytes > 0 && o->u.RGBA.rgba == run_host + run_bytes && src == run_dev + run_bytes) {
+      if (run_bytes > 0 && o->u.RGBA.rgba == run_host + run_bytes && src == run_dev + run_bytes &&
+          (run_alloc.known ? o->u.RGBA.rgba + bytes <= run_alloc.base + run_alloc.size : !host_alloc_of(o->u.RGBA.rgba).known)) {
         run_bytes += bytes;
       } else {
         if (!flush()) return false;
         run_host = o->u.RGBA.rgba; run_dev = src; run_bytes = bytes;
+        run_alloc = host_alloc_of(run_host);
       }
       if (run_bytes >= ((size_t)256 << 20)) { if (!flush()) return false; }
     } else {
@@ -673,11 +882,12 @@ static bool batch_alpha(WebPBatch* b) {
   DeviceCtx* ctx = b->ctx;
   const int na = (int)b->aimgs.size();
   if (na == 0) return true;
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = b->stream;
   const uint8_t* arena = (const uint8_t*)b->d_in.p;
   if (!b->alpha_planned) {
     b->aplans.assign(na, AlphaPlan());
-    b->ahdrs.resize(na);
+    if (b->ahdrs == nullptr) b->ahdrs = (AlphaHdr*)pinned_alloc(ctx, sizeof(AlphaHdr) * (size_t)na, &b->h_ahdrs_cap);
+    if (b->ahdrs == nullptr) return false;
     size_t work1 = 0;
     for (int a = 0; a < na; ++a) {
       const ImgDesc& d = b->imgs[b->aimgs[a]];
@@ -698,7 +908,7 @@ static bool batch_alpha(WebPBatch* b) {
   vp8k_alpha_header(s, arena, (const ImgDesc*)b->d_imgs.p, (const int*)b->d_aimgs.p, (const AlphaPlan*)b->d_aplans.p,
                     (AlphaHdr*)b->d_ahdrs.p, na);
   if (!b->alpha_planned) {
-    CU_TRY(cudaMemcpyAsync(b->ahdrs.data(), b->d_ahdrs.p, sizeof(AlphaHdr) * na, cudaMemcpyDeviceToHost, s), "D2H alpha headers");
+    CU_TRY(cudaMemcpyAsync(b->ahdrs, b->d_ahdrs.p, sizeof(AlphaHdr) * na, cudaMemcpyDeviceToHost, s), "D2H alpha headers");
     CU_TRY(cudaStreamSynchronize(s), "alpha header pass");
     size_t work2 = 0, planes = 0;
     std::vector<size_t> tab(na, 0), grp(na, 0), cod(na, 0), smo(na, 0);
@@ -735,7 +945,7 @@ static bool batch_alpha(WebPBatch* b) {
                     (AlphaHdr*)b->d_ahdrs.p, (uint8_t*)b->d_alpha.p, na);
   if (b->any_lossless) vp8k_lossless_finish(s, (const ImgDesc*)b->d_imgs.p, (const int*)b->d_aimgs.p, (const AlphaPlan*)b->d_aplans.p,
                                             (const AlphaHdr*)b->d_ahdrs.p, (uint8_t*)b->d_out.p, na);
-  CU_TRY(cudaMemcpyAsync(b->ahdrs.data(), b->d_ahdrs.p, sizeof(AlphaHdr) * na, cudaMemcpyDeviceToHost, s), "D2H alpha status");
+  CU_TRY(cudaMemcpyAsync(b->ahdrs, b->d_ahdrs.p, sizeof(AlphaHdr) * na, cudaMemcpyDeviceToHost, s), "D2H alpha status");
   return true;
 }
 
@@ -743,19 +953,52 @@ static bool batch_alpha(WebPBatch* b) {
 // serial entropy decode needs every stream it can get in flight); the pixel stages then walk the wave in
 // chunks, and with `download` (one-shot host-output path) each chunk's pixels start their way back on the copy
 // stream as soon as its emit kernel has finished, while the next chunk is reconstructed / the next wave parsed.
-static bool batch_decode(WebPBatch* b, bool download) {
+// Hands one download step to the device's copier thread: wait (on the copy stream) for `after`, then queue the copies.
+// Jobs of all batches run in the order they were posted, so the copy stream sees the same order as before.
+static void post_download(WebPBatch* b, cudaEvent_t after, std::function<bool()> copies) {
+  DeviceCtx* ctx = b->ctx;
+  { std::lock_guard<std::mutex> lk(b->job_mu); ++b->jobs_pending; }
+  copier_post(ctx, [=]() {
+    bool ok = true;
+    g_last_error[0] = 0;
+    if (after != nullptr && cudaStreamWaitEvent(ctx->copy_stream, after, 0) != cudaSuccess) { set_error("cudaStreamWaitEvent", cudaGetLastError()); ok = false; }
+    if (ok) ok = copies();
+    std::lock_guard<std::mutex> lk(b->job_mu);
+    if (!ok && !b->job_failed) { b->job_failed = true; snprintf(b->job_error, sizeof(b->job_error), "%s", g_last_error); }
+    --b->jobs_pending;
+    b->job_cv.notify_all();
+  });
+}
+
+static bool jobs_drain(WebPBatch* b) {   // every download job of the batch has been queued on the copy stream
+  std::unique_lock<std::mutex> lk(b->job_mu);
+  b->job_cv.wait(lk, [&]() { return b->jobs_pending == 0; });
+  if (b->job_failed) { snprintf(g_last_error, sizeof(g_last_error), "%s", b->job_error); b->job_failed = false; return false; }
+  return true;
+}
+
+static bool batch_enqueue(WebPBatch* b, bool download) {
   DeviceCtx* ctx = b->ctx;
   const int m = (int)b->imgs.size();
   memset(&b->timings, 0, sizeof(b->timings));
+  b->e_begin = b->e_end = -1;
+  b->copies_queued = false;
+  b->launches = 0;
   if (m == 0) return true;
-  CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
-  cudaStream_t s = ctx->stream;
+  if (!ensure_scratch(b)) return false;
+  cudaStream_t s = b->stream;
+  if (ctx->scratch_used) CU_TRY(cudaStreamWaitEvent(s, ctx->scratch_free, 0), "cudaStreamWaitEvent");   // no-op on the device's own stream
   const uint8_t* arena = (const uint8_t*)b->d_in.p;
   const ImgDesc* imgs = (const ImgDesc*)b->d_imgs.p;
   FrameHdr* hdrs = (FrameHdr*)b->d_hdrs.p;
-  uint32_t* mbinfo = (uint32_t*)b->d_mbinfo.p;
-  int16_t* coeffs = (int16_t*)b->d_coeffs.p;
-  uint8_t* yuv = (uint8_t*)b->d_yuv.p;
+  uint32_t* mbinfo = (uint32_t*)ctx->s_mbinfo.p;
+  const bool stream_tokens = vp8k_tokens_use_stream() != 0;
+  int16_t* coeffs = (int16_t*)ctx->s_coeffs.p;
+  uint32_t* tokens = stream_tokens ? (uint32_t*)ctx->s_tokens.p : nullptr;
+  void* mbtok = stream_tokens ? ctx->s_mbtok.p : nullptr;
+  uint8_t* yuv = (uint8_t*)ctx->s_yuv.p;
+  int8_t* dither = b->any_dither ? (int8_t*)ctx->s_dither.p : nullptr;
+  uint8_t* band = (uint8_t*)ctx->s_band.p;
   int launches = 0;
   b->ev_used = 0;
   b->spans.clear();
@@ -764,6 +1007,7 @@ static bool batch_decode(WebPBatch* b, bool download) {
   { const char* e = getenv("WEBP_B200_CHUNK_MB"); if (e != NULL && atoi(e) > 0) chunk_bytes = (size_t)atoi(e) << 20; }
 #define MARK(var) const int var = ev_mark(b, s); if (var < 0) return false
   MARK(e_begin);
+  b->e_begin = e_begin;
   if (!b->aimgs.empty()) {
     MARK(ea0);
     if (!batch_alpha(b)) return false;
@@ -776,10 +1020,11 @@ static bool batch_decode(WebPBatch* b, bool download) {
     vp8k_parse_modes(s, arena, imgs, hdrs, mbinfo, w.first, w.count, w.max_mb_w);
     ++launches;
     MARK(e1);
-    CU_TRY(cudaMemsetAsync(coeffs, 0, w.mbs * 2 * VP8B_COEFFS_PER_MB, s), "memset coefficients");
+    if (!stream_tokens) CU_TRY(cudaMemsetAsync(coeffs, 0, w.mbs * 2 * VP8B_COEFFS_PER_MB, s), "memset coefficients");
     for (int lg = 0; lg < 4; ++lg) {
       if (w.ids_cnt[lg] == 0) continue;
-      vp8k_parse_tokens(s, arena, imgs, hdrs, mbinfo, coeffs, (const int*)b->d_ids.p + w.ids_off[lg], w.ids_cnt[lg], 1 << lg, w.max_mb_w);
+      if (stream_tokens) vp8k_parse_tokens_stream(s, arena, imgs, hdrs, mbinfo, tokens, mbtok, (const int*)b->d_ids.p + w.ids_off[lg], w.ids_cnt[lg], 1 << lg, w.max_mb_w);
+      else vp8k_parse_tokens(s, arena, imgs, hdrs, mbinfo, coeffs, (const int*)b->d_ids.p + w.ids_off[lg], w.ids_cnt[lg], 1 << lg, w.max_mb_w);
       ++launches;
     }
     // ---- row bands: see vp8_kernels.h. The wave qualifies when every image has one token partition, the lockstep
@@ -788,7 +1033,7 @@ static bool batch_decode(WebPBatch* b, bool download) {
     {
       static int env_bands = -1;
       if (env_bands < 0) { const char* e = getenv("WEBP_B200_BANDS"); env_bands = e ? atoi(e) : 1; }
-      bool ok = env_bands > 1 && !b->any_dither && b->aimgs.empty() && w.ids_cnt[0] == w.count && vp8k_tokens_take_bands(w.count, 1) && w.max_mb_h >= 16;
+      bool ok = env_bands > 1 && !stream_tokens && !b->any_dither && b->aimgs.empty() && w.ids_cnt[0] == w.count && vp8k_tokens_take_bands(w.count, 1) && w.max_mb_h >= 16;
       for (int k = w.first; ok && k < w.first + w.count; ++k) {
         const ImgDesc& d = b->imgs[k];
         const bool pairs = !(d.flags & VP8B_FLAG_NO_FANCY) && kBpp[d.csp] == 4 && d.csp != MODE_YUVA;
@@ -805,8 +1050,8 @@ static bool batch_decode(WebPBatch* b, bool download) {
       static int overlap = -1;
       if (overlap < 0) { const char* e = getenv("WEBP_B200_BAND_OVERLAP"); overlap = (e != NULL && atoi(e) > 0) ? 1 : 0; }
       cudaStream_t ps = overlap ? ctx->pixel_stream : s;
-      TokResume* resume = (TokResume*)b->d_band.p;
-      uint16_t* resume_ctx = (uint16_t*)((uint8_t*)b->d_band.p + align_up((size_t)m * sizeof(TokResume), 256));
+      TokResume* resume = (TokResume*)band;
+      uint16_t* resume_ctx = (uint16_t*)(band + align_up((size_t)m * sizeof(TokResume), 256));
       uint8_t* band_ctx = (uint8_t*)resume_ctx + align_up((size_t)m * 2 * b->max_mb_w, 256);
       b->spans.push_back({ ST_MODES, e0, e1 });
       int prev_tok = e1, last_px = -1;
@@ -822,7 +1067,7 @@ static bool batch_decode(WebPBatch* b, bool download) {
         b->spans.push_back({ ST_TOKENS, prev_tok, et });
         if (ps != s) CU_TRY(cudaStreamWaitEvent(ps, b->ev[et], 0), "cudaStreamWaitEvent");
         const int q0 = ev_mark(b, ps); if (q0 < 0) return false;
-        vp8k_reconstruct(ps, imgs, hdrs, mbinfo, coeffs, yuv, w.first, w.count, w.max_mb_w, w.max_mb_h, r0, r1, band_ctx);
+        vp8k_reconstruct(ps, imgs, hdrs, mbinfo, coeffs, yuv, w.first, w.count, w.max_mb_w, w.max_mb_h, r0, r1, band_ctx, nullptr, nullptr);
         const int q1 = ev_mark(b, ps); if (q1 < 0) return false;
         vp8k_loop_filter(ps, imgs, hdrs, mbinfo, yuv, w.first, w.count, w.max_mb_h, r0, r1, nullptr);
         const int q2 = ev_mark(b, ps); if (q2 < 0) return false;
@@ -837,14 +1082,14 @@ static bool batch_decode(WebPBatch* b, bool download) {
         last_px = q3;
         prev_tok = (ps == s) ? q3 : et;
         if (download) {
-          CU_TRY(cudaStreamWaitEvent(ctx->copy_stream, b->ev[q3], 0), "cudaStreamWaitEvent");
-          if (!enqueue_download_rows(b, w.first, w.count, p0, p1, ctx->copy_stream)) return false;
+          const int first = w.first, count = w.count;
+          post_download(b, b->ev[q3], [=]() { return enqueue_download_rows(b, first, count, p0, p1, ctx->copy_stream); });
         }
       }
       if (ps != s) CU_TRY(cudaStreamWaitEvent(s, b->ev[last_px], 0), "cudaStreamWaitEvent");   // the scratch arrays are free again
       continue;
     }
-    if (b->any_dither) { vp8k_dither_plan(s, imgs, hdrs, mbinfo, (int8_t*)b->d_dither.p, w.first, w.count); ++launches; }
+    if (b->any_dither) { vp8k_dither_plan(s, imgs, hdrs, mbinfo, dither, w.first, w.count); ++launches; }
     MARK(e2);
     b->spans.push_back({ ST_MODES, e0, e1 });
     b->spans.push_back({ ST_TOKENS, e1, e2 });
@@ -857,9 +1102,9 @@ static bool batch_decode(WebPBatch* b, bool download) {
           acc += b->plan[b->img_item[c1]].out_bytes;
       }
       const int cnt = c1 - c0;
-      vp8k_reconstruct(s, imgs, hdrs, mbinfo, coeffs, yuv, c0, cnt, w.max_mb_w, w.max_mb_h, 0, 0x7fffffff, (uint8_t*)b->d_band.p);
+      vp8k_reconstruct(s, imgs, hdrs, mbinfo, coeffs, yuv, c0, cnt, w.max_mb_w, w.max_mb_h, 0, 0x7fffffff, band, tokens, mbtok);
       MARK(e3);
-      vp8k_loop_filter(s, imgs, hdrs, mbinfo, yuv, c0, cnt, w.max_mb_h, 0, 0x7fffffff, (const int8_t*)b->d_dither.p);
+      vp8k_loop_filter(s, imgs, hdrs, mbinfo, yuv, c0, cnt, w.max_mb_h, 0, 0x7fffffff, dither);
       MARK(e4);
       vp8k_emit(s, imgs, hdrs, yuv, (const uint8_t*)b->d_alpha.p, (uint8_t*)b->d_out.p, c0, cnt, w.max_units, 0, 0x7fffffff);
       if (w.max_scaled_items > 0) { vp8k_emit_scaled(s, imgs, hdrs, yuv, (const uint8_t*)b->d_alpha.p, (uint8_t*)b->d_out.p, c0, cnt, w.max_scaled_items); ++launches; }
@@ -869,21 +1114,44 @@ static bool batch_decode(WebPBatch* b, bool download) {
       b->spans.push_back({ ST_FILTER, e3, e4 });
       b->spans.push_back({ ST_EMIT, e4, e5 });
       prev = e5;
-      if (download) {
-        CU_TRY(cudaStreamWaitEvent(ctx->copy_stream, b->ev[e5], 0), "cudaStreamWaitEvent");
-        if (!enqueue_download(b, c0, cnt, ctx->copy_stream, false)) return false;
-      }
+      if (download) post_download(b, b->ev[e5], [=]() { return enqueue_download(b, c0, cnt, ctx->copy_stream, false); });
       c0 = c1;
     }
   }
 #undef MARK
   const int e_end = ev_mark(b, s); if (e_end < 0) return false;
+  b->e_end = e_end;
+  b->launches = launches;
+  CU_TRY(cudaEventRecord(ctx->scratch_free, s), "cudaEventRecord");
+  ctx->scratch_used = true;
   // per-image status words: FrameHdr::status is the first field
-  CU_TRY(cudaMemcpy2DAsync(b->statuses.data(), sizeof(int), hdrs, sizeof(FrameHdr), sizeof(int), m, cudaMemcpyDeviceToHost, s),
-         "D2H status");
-  CU_TRY(cudaStreamSynchronize(s), "kernel execution");
-  CU_TRY(cudaGetLastError(), "kernel launch");
-  if (download) CU_TRY(cudaStreamSynchronize(ctx->copy_stream), "download sync");
+  CU_TRY(cudaMemcpy2DAsync(b->statuses, sizeof(int), hdrs, sizeof(FrameHdr), sizeof(int), m, cudaMemcpyDeviceToHost, s), "D2H status");
+  const int e_status = ev_mark(b, s); if (e_status < 0) return false;
+  (void)e_status;   // the last event of the pool on the compute stream: batch_finish waits for it
+  if (download) {
+    if (b->copy_done == nullptr) CU_TRY(cudaEventCreateWithFlags(&b->copy_done, cudaEventDisableTiming), "cudaEventCreate");
+    cudaEvent_t done = b->copy_done;
+    post_download(b, nullptr, [=]() {
+      if (cudaEventRecord(done, ctx->copy_stream) != cudaSuccess) { set_error("cudaEventRecord", cudaGetLastError()); return false; }
+      return true;
+    });
+    b->copies_queued = true;
+  }
+  b->queued = true;
+  return true;
+}
+
+// Waits for what batch_enqueue put into the streams (no lock held: other batches may be queued meanwhile), then turns
+// the status words into per-item VP8StatusCodes and the events into stage times.
+static bool batch_finish(WebPBatch* b) {
+  if (!b->queued) return true;
+  b->queued = false;
+  const int m = (int)b->imgs.size();
+  CU_TRY(cudaEventSynchronize(b->ev[b->ev_used - 1]), "kernel execution");
+  if (b->copies_queued) {
+    if (!jobs_drain(b)) return false;
+    CU_TRY(cudaEventSynchronize(b->copy_done), "download sync");
+  }
   float acc[ST_COUNT] = { 0, 0, 0, 0, 0, 0 };
   for (const auto& sp : b->spans) {
     float ms = 0;
@@ -894,8 +1162,8 @@ static bool batch_decode(WebPBatch* b, bool download) {
   b->timings.filter_ms = acc[ST_FILTER]; b->timings.emit_ms = acc[ST_EMIT];
   b->timings.alpha_ms = acc[ST_ALPHA];
   // with row bands the pixel stages of one band overlap the parse of the next: the step is what the stream saw end to end
-  { float ms = 0; CU_TRY(cudaEventElapsedTime(&ms, b->ev[e_begin], b->ev[e_end]), "cudaEventElapsedTime"); b->timings.total_ms = ms; }
-  b->timings.launches = launches;
+  { float ms = 0; CU_TRY(cudaEventElapsedTime(&ms, b->ev[b->e_begin], b->ev[b->e_end]), "cudaEventElapsedTime"); b->timings.total_ms = ms; }
+  b->timings.launches = b->launches;
   for (int k = 0; k < m; ++k) {
     WebPBatchItem* it = &b->items[b->img_item[k]];
     it->status = (VP8StatusCode)b->statuses[k];
@@ -913,59 +1181,223 @@ static bool batch_decode(WebPBatch* b, bool download) {
   return true;
 }
 
-static VP8StatusCode batch_decode_locked(WebPBatch* b, bool download) {
-  bool ok = true;
-  if (b->ctx != nullptr) {
-    b->ctx->mu.lock();
-    ok = batch_decode(b, download);
-    if (!ok) { cudaStreamSynchronize(b->ctx->stream); cudaStreamSynchronize(b->ctx->pixel_stream); cudaStreamSynchronize(b->ctx->copy_stream); cudaGetLastError(); }
-    b->ctx->mu.unlock();
-  }
+static VP8StatusCode first_failure(const WebPBatchItem* items, int n) {
+  for (int i = 0; i < n; ++i) if (items[i].status != VP8_STATUS_OK) return items[i].status;
+  return VP8_STATUS_OK;
+}
+
+static void drain_after_failure(WebPBatch* b) {
+  jobs_drain(b);
+  cudaStreamSynchronize(b->stream); cudaStreamSynchronize(b->ctx->pixel_stream); cudaStreamSynchronize(b->ctx->copy_stream);
+  cudaGetLastError();
+  b->queued = false;
+}
+
+// Queues one decode of a single-device batch (kernels, and with `download` the pixel copies).
+static bool submit_single(WebPBatch* b, bool download) {
+  if (b->ctx == nullptr) return true;   // nothing reached the device
+  DeviceGuard guard(b->ctx->device);
+  b->ctx->mu.lock();
+  const bool ok = batch_enqueue(b, download);
+  if (!ok) drain_after_failure(b);
+  b->ctx->mu.unlock();
   if (!ok) {
     fprintf(stderr, "libwebp_b200: %s\n", g_last_error);
-    fail_all(b->items, b->n, VP8_STATUS_USER_ABORT);
-    return VP8_STATUS_USER_ABORT;
+    fail_all(b->items, b->n, strstr(g_last_error, "cudaMalloc") ? VP8_STATUS_OUT_OF_MEMORY : VP8_STATUS_USER_ABORT);
   }
-  for (int i = 0; i < b->n; ++i) if (b->items[i].status != VP8_STATUS_OK) return b->items[i].status;
-  return VP8_STATUS_OK;
+  return ok;
 }
 
-extern "C" VP8StatusCode WebPBatchDecode(WebPBatch* b) {
-  if (b == NULL) return VP8_STATUS_INVALID_PARAM;
-  return batch_decode_locked(b, false);
+static VP8StatusCode wait_single(WebPBatch* b) {
+  if (b->ctx != nullptr && b->queued) {
+    DeviceGuard guard(b->ctx->device);
+    if (!batch_finish(b)) {
+      b->ctx->mu.lock(); drain_after_failure(b); b->ctx->mu.unlock();
+      fprintf(stderr, "libwebp_b200: %s\n", g_last_error);
+      fail_all(b->items, b->n, VP8_STATUS_USER_ABORT);
+      return VP8_STATUS_USER_ABORT;
+    }
+  }
+  return first_failure(b->items, b->n);
 }
 
-static bool batch_download(WebPBatch* b) {
-  DeviceCtx* ctx = b->ctx;
-  if (b->opt.output != WEBP_BATCH_HOST || b->imgs.empty()) return true;
-  CU_TRY(cudaSetDevice(ctx->device), "cudaSetDevice");
-  if (!enqueue_download(b, 0, (int)b->imgs.size(), ctx->copy_stream, true)) return false;
-  CU_TRY(cudaStreamSynchronize(ctx->copy_stream), "download sync");
-  return true;
-}
-
-extern "C" VP8StatusCode WebPBatchDownload(WebPBatch* b) {
-  if (b == NULL || !b->decoded) return VP8_STATUS_INVALID_PARAM;
-  if (b->ctx == nullptr) return VP8_STATUS_OK;
-  b->ctx->mu.lock();
-  const bool ok = batch_download(b);
-  if (!ok) { cudaStreamSynchronize(b->ctx->copy_stream); cudaGetLastError(); }
-  b->ctx->mu.unlock();
-  if (!ok) { fprintf(stderr, "libwebp_b200: %s\n", g_last_error); return VP8_STATUS_USER_ABORT; }
-  return VP8_STATUS_OK;
-}
-
-extern "C" void WebPBatchDestroy(WebPBatch* b) {
-  if (b == NULL) return;
+static void destroy_single(WebPBatch* b) {
   DeviceCtx* c = b->ctx;
   if (c == nullptr) { delete b; return; }
+  DeviceGuard guard(c->device);
+  if (b->queued) { batch_finish(b); }   // never free what the streams still use
   c->mu.lock();
   batch_release(b);
   c->mu.unlock();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// WebPBatchOptions::devices: item i goes to devices[i % num_devices]. One host thread per device plans, uploads and
+// queues its shard; nothing is exchanged between the devices (images are independent: SURVEY.md 8e).
+static bool wants_shards(const WebPBatchOptions& o) { return o.devices != NULL && o.num_devices > 1; }
+
+template <typename F>
+static void for_each_shard(WebPBatch* parent, F fn) {
+  std::vector<std::thread> th;
+  for (size_t g = 1; g < parent->shards.size(); ++g) th.emplace_back([&, g]() { fn(parent->shards[g], (int)g); });
+  fn(parent->shards[0], 0);
+  for (auto& t : th) t.join();
+}
+
+static void shards_pull_statuses(WebPBatch* parent) {
+  const int G = (int)parent->shards.size();
+  std::vector<int> pos(G, 0);
+  for (int i = 0; i < parent->n; ++i) { const int g = i % G; parent->items[i].status = parent->shards[g]->items[pos[g]++].status; }
+}
+
+static WebPBatch* create_any(WebPBatchItem* items, int num_items, const WebPBatchOptions* options, VP8StatusCode* status) {
+  VP8StatusCode dummy;
+  if (status == NULL) status = &dummy;
+  *status = VP8_STATUS_INVALID_PARAM;
+  if (items == NULL || num_items <= 0) return NULL;
+  WebPBatchOptions opt;
+  if (options != NULL) opt = *options; else WebPBatchOptionsInit(&opt);
+  if (opt.num_devices < 0 || (opt.num_devices > 0 && opt.devices == NULL)) return NULL;
+  if (opt.num_devices == 1) { opt.device = opt.devices[0]; }
+  if (!wants_shards(opt)) { opt.devices = NULL; opt.num_devices = 0; return create_single(items, num_items, opt, status); }
+  if (opt.stream != NULL) return NULL;   // a caller's stream belongs to one device
+  const int G = std::min(opt.num_devices, num_items);
+  WebPBatch* parent = new WebPBatch();
+  parent->items = items; parent->n = num_items; parent->opt = opt;
+  memset(&parent->timings, 0, sizeof(parent->timings));
+  parent->shard_items.resize(num_items);
+  std::vector<int> first(G + 1, 0);
+  for (int g = 0; g < G; ++g) first[g + 1] = first[g] + (num_items - g + G - 1) / G;
+  { std::vector<int> pos(first.begin(), first.end() - 1); for (int i = 0; i < num_items; ++i) parent->shard_items[pos[i % G]++] = items[i]; }
+  parent->shards.assign(G, nullptr);
+  std::vector<VP8StatusCode> sts(G, VP8_STATUS_OK);
+  std::vector<std::string> errs(G);
+  {
+    std::vector<std::thread> th;
+    auto make = [&](int g) {
+      WebPBatchOptions o = opt;
+      o.device = opt.devices[g]; o.devices = NULL; o.num_devices = 0;
+      parent->shards[g] = create_single(parent->shard_items.data() + first[g], first[g + 1] - first[g], o, &sts[g]);
+      errs[g] = g_last_error;
+    };
+    for (int g = 1; g < G; ++g) th.emplace_back(make, g);
+    make(0);
+    for (auto& t : th) t.join();
+  }
+  bool ok = true;
+  for (int g = 0; g < G; ++g) if (parent->shards[g] == nullptr) { ok = false; *status = sts[g]; snprintf(g_last_error, sizeof(g_last_error), "%s", errs[g].c_str()); }
+  if (!ok) {   // a shard without a batch has already marked its items; the others are given up as well (one call, one answer)
+    for (int g = 0; g < G; ++g) {
+      if (parent->shards[g] == nullptr) continue;
+      WebPBatch* sb = parent->shards[g];
+      for (int i = 0; i < sb->n; ++i) if (sb->items[i].status == VP8_STATUS_OK) {
+        sb->items[i].status = *status;
+        if (sb->items[i].config != NULL && opt.output == WEBP_BATCH_HOST) WebPFreeDecBuffer(&sb->items[i].config->output);
+      }
+    }
+    std::vector<int> pos(first.begin(), first.end() - 1);
+    for (int i = 0; i < num_items; ++i) items[i].status = parent->shard_items[pos[i % G]++].status;
+    for (int g = 0; g < G; ++g) if (parent->shards[g] != nullptr) destroy_single(parent->shards[g]);
+    delete parent;
+    return NULL;
+  }
+  shards_pull_statuses(parent);
+  *status = VP8_STATUS_OK;
+  return parent;
+}
+
+static bool submit_any(WebPBatch* b, bool download) {
+  if (b->shards.empty()) return submit_single(b, download);
+  std::vector<char> ok(b->shards.size(), 1);
+  for_each_shard(b, [&](WebPBatch* sb, int g) { ok[g] = submit_single(sb, download) ? 1 : 0; });
+  b->queued = true;
+  for (char c : ok) if (!c) return false;
+  return true;
+}
+
+static VP8StatusCode wait_any(WebPBatch* b) {
+  if (b->shards.empty()) return wait_single(b);
+  for_each_shard(b, [&](WebPBatch* sb, int) { wait_single(sb); });
+  b->queued = false; b->decoded = true;
+  shards_pull_statuses(b);
+  // stage times: the slowest shard's (the devices run side by side)
+  memset(&b->timings, 0, sizeof(b->timings));
+  for (WebPBatch* sb : b->shards) {
+    if (sb->timings.total_ms >= b->timings.total_ms) { const int l = b->timings.launches; b->timings = sb->timings; b->timings.launches = l; }
+    b->timings.launches += sb->timings.launches;
+  }
+  return first_failure(b->items, b->n);
+}
+
+extern "C" WebPBatch* WebPBatchCreate(WebPBatchItem* items, int num_items, const WebPBatchOptions* options,
+                                      VP8StatusCode* status) {
+  return create_any(items, num_items, options, status);
+}
+
+extern "C" VP8StatusCode WebPBatchDecode(WebPBatch* b) {
+  if (b == NULL) return VP8_STATUS_INVALID_PARAM;
+  if (b->queued) wait_any(b);
+  submit_any(b, false);
+  return wait_any(b);
+}
+
+// Asynchronous pair: WebPBatchSubmit = WebPBatchCreate + everything queued (uploads, kernels and, for host output, the
+// pixel copies) without waiting; WebPBatchWait collects the statuses. Between the two the caller's input and output
+// buffers belong to the library. Several submitted batches per device pipeline: see DeviceCtx.
+extern "C" WebPBatch* WebPBatchSubmit(WebPBatchItem* items, int num_items, const WebPBatchOptions* options, VP8StatusCode* status) {
+  VP8StatusCode dummy;
+  if (status == NULL) status = &dummy;
+  WebPBatch* b = create_any(items, num_items, options, status);
+  if (b == NULL) return NULL;
+  submit_any(b, b->opt.output == WEBP_BATCH_HOST);
+  return b;
+}
+
+extern "C" VP8StatusCode WebPBatchWait(WebPBatch* b) {
+  if (b == NULL) return VP8_STATUS_INVALID_PARAM;
+  return wait_any(b);
+}
+
+static bool batch_download(WebPBatch* b) {
+  DeviceCtx* ctx = b->ctx;
+  if (b->opt.output != WEBP_BATCH_HOST || b->imgs.empty()) return true;
+  if (!enqueue_download(b, 0, (int)b->imgs.size(), ctx->copy_stream, true)) return false;
+  if (b->copy_done == nullptr) CU_TRY(cudaEventCreateWithFlags(&b->copy_done, cudaEventDisableTiming), "cudaEventCreate");
+  CU_TRY(cudaEventRecord(b->copy_done, ctx->copy_stream), "cudaEventRecord");
+  return true;
+}
+
+static VP8StatusCode download_single(WebPBatch* b) {
+  if (b->ctx == nullptr) return VP8_STATUS_OK;
+  DeviceGuard guard(b->ctx->device);
+  b->ctx->mu.lock();
+  bool ok = batch_download(b);
+  b->ctx->mu.unlock();
+  if (ok && b->copy_done != nullptr && cudaEventSynchronize(b->copy_done) != cudaSuccess) { set_error("download sync", cudaGetLastError()); ok = false; }
+  if (!ok) { cudaStreamSynchronize(b->ctx->copy_stream); cudaGetLastError(); fprintf(stderr, "libwebp_b200: %s\n", g_last_error); return VP8_STATUS_USER_ABORT; }
+  return VP8_STATUS_OK;
+}
+
+extern "C" VP8StatusCode WebPBatchDownload(WebPBatch* b) {
+  if (b == NULL || !b->decoded) return VP8_STATUS_INVALID_PARAM;
+  if (b->shards.empty()) return download_single(b);
+  std::vector<VP8StatusCode> st(b->shards.size(), VP8_STATUS_OK);
+  for_each_shard(b, [&](WebPBatch* sb, int g) { st[g] = download_single(sb); });
+  for (VP8StatusCode s : st) if (s != VP8_STATUS_OK) return s;
+  return VP8_STATUS_OK;
+}
+
+extern "C" void WebPBatchDestroy(WebPBatch* b) {
+  if (b == NULL) return;
+  if (b->shards.empty()) { destroy_single(b); return; }
+  for (WebPBatch* sb : b->shards) destroy_single(sb);
+  delete b;
+}
+
 extern "C" int WebPBatchOutput(const WebPBatch* b, int index, WebPBatchPlane* p) {
-  if (b == NULL || p == NULL || index < 0 || index >= b->n || b->plan[index].img < 0) return 0;
+  if (b == NULL || p == NULL || index < 0 || index >= b->n) return 0;
+  if (!b->shards.empty()) { const int G = (int)b->shards.size(); return WebPBatchOutput(b->shards[index % G], index / G, p); }
+  if (b->plan[index].img < 0) return 0;
   const ImgDesc& d = b->imgs[b->plan[index].img];
   uint8_t* base = (uint8_t*)b->d_out.p + d.out_off;
   memset(p, 0, sizeof(*p));
@@ -978,6 +1410,7 @@ extern "C" int WebPBatchOutput(const WebPBatch* b, int index, WebPBatchPlane* p)
     p->v = base + (size_t)fw * fh + (size_t)uvw * uvh;
     p->uv_stride = uvw;
   }
+  p->device = b->ctx != nullptr ? b->ctx->device : -1;
   return 1;
 }
 
@@ -987,32 +1420,105 @@ extern "C" int WebPBatchGetTimings(const WebPBatch* b, WebPBatchTimings* t) {
   return 1;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// One-shot entry point. A batch whose device memory would not fit is cut into groups that run one after the other, and
+// an image that cannot fit on its own fails alone (VP8_STATUS_OUT_OF_MEMORY): "one bad image never poisons the others"
+// also holds for files that merely DECLARE huge dimensions.
+static size_t item_device_bytes(const WebPBatchItem* it) {
+  WebPBitstreamFeatures f;
+  if (it->data == NULL || it->config == NULL || vp8b_get_features(it->data, it->data_size, &f) != VP8_STATUS_OK) return 0;
+  const size_t w = (size_t)f.width, h = (size_t)f.height;
+  size_t ow = w, oh = h;
+  const WebPDecoderOptions* o = &it->config->options;
+  if (o->use_cropping && o->crop_width > 0 && o->crop_height > 0) { ow = std::min(ow, (size_t)o->crop_width); oh = std::min(oh, (size_t)o->crop_height); }
+  if (o->use_scaling && o->scaled_width > 0 && o->scaled_height > 0 && o->scaled_width <= 16383 && o->scaled_height <= 16383) { ow = (size_t)o->scaled_width; oh = (size_t)o->scaled_height; }
+  size_t bytes = it->data_size + 4 * ow * oh + 4096;                       // input + output (at most 4 bytes per pixel)
+  if (f.has_alpha || f.format == 2) bytes += 9 * w * h + (1u << 20);      // alpha plane, coded ARGB, de-banding / tile work
+  return bytes;
+}
+
+static size_t device_room(int device) {   // free + what the library could give back on that device
+  DeviceCtx* c = get_ctx(device);
+  if (c == nullptr) return 0;
+  DeviceGuard guard(c->device);
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return 0; }
+  std::lock_guard<std::mutex> lk(c->mu);
+  return free_b + c->cached_bytes;
+}
+
+static VP8StatusCode decode_group(WebPBatchItem* items, int n, const WebPBatchOptions* options, WebPBatchTimings* tm, size_t* nwaves) {
+  VP8StatusCode st;
+  WebPBatch* b = create_any(items, n, options, &st);
+  if (b == NULL) {
+    if (st == VP8_STATUS_OUT_OF_MEMORY && n > 1) {   // halve and retry: whatever cannot fit ends up alone and fails alone
+      for (int i = 0; i < n; ++i) if (items[i].status == VP8_STATUS_OUT_OF_MEMORY) items[i].status = VP8_STATUS_OK;
+      const int h = n / 2;
+      const VP8StatusCode a = decode_group(items, h, options, tm, nwaves), c = decode_group(items + h, n - h, options, tm, nwaves);
+      return a != VP8_STATUS_OK ? a : c;
+    }
+    return st != VP8_STATUS_OK ? st : VP8_STATUS_INVALID_PARAM;
+  }
+  submit_any(b, b->opt.output == WEBP_BATCH_HOST);   // downloads ride along, chunk by chunk
+  st = wait_any(b);
+  if (tm != NULL) *tm = b->timings;
+  if (nwaves != NULL) *nwaves = b->waves.size();
+  WebPBatchDestroy(b);
+  return st;
+}
+
 extern "C" VP8StatusCode WebPDecodeBatch(WebPBatchItem* items, int num_items, const WebPBatchOptions* options) {
   static int trace = -1;
   if (trace < 0) trace = getenv("WEBP_B200_TRACE") != NULL;
+  if (items == NULL || num_items <= 0) return VP8_STATUS_INVALID_PARAM;
   const auto t0 = std::chrono::steady_clock::now();
-  VP8StatusCode st;
-  WebPBatch* b = WebPBatchCreate(items, num_items, options, &st);
-  if (b == NULL) {
-    if (st != VP8_STATUS_OK) return st;
-    return VP8_STATUS_INVALID_PARAM;
+  WebPBatchTimings tm;
+  memset(&tm, 0, sizeof(tm));
+  size_t nwaves = 0;
+  for (int i = 0; i < num_items; ++i) items[i].status = VP8_STATUS_OK;
+  // ---- how much device memory the resident part of each item takes; groups of at most half of what is there
+  const int ndev = (options != NULL && options->devices != NULL && options->num_devices > 1) ? options->num_devices : 1;
+  size_t room = (size_t)-1;
+  bool sized = false;
+  std::vector<size_t> need;
+  size_t total = 0;
+  need.resize(num_items);
+  for (int i = 0; i < num_items; ++i) { need[i] = item_device_bytes(&items[i]); total += need[i]; }
+  if (total > ((size_t)1 << 30)) {   // small batches never come near the limit: skip the device query
+    for (int g = 0; g < ndev; ++g) {
+      const int dev = ndev > 1 ? options->devices[g] : (options != NULL ? options->device : -1);
+      const size_t r = device_room(dev);
+      if (r > 0) { room = std::min(room, r); sized = true; }
+    }
   }
-  const auto t1 = std::chrono::steady_clock::now();
-  st = batch_decode_locked(b, b->opt.output == WEBP_BATCH_HOST);   // downloads ride along, wave by wave
-  const auto t2 = std::chrono::steady_clock::now();
-  const WebPBatchTimings tm = b->timings;
-  const size_t nwaves = b->waves.size();
-  WebPBatchDestroy(b);
+  VP8StatusCode result = VP8_STATUS_OK;
+  if (!sized || total / ndev <= room / 2) {
+    result = decode_group(items, num_items, options, &tm, &nwaves);
+  } else {
+    const size_t cap = room / 2 * ndev;
+    int i0 = 0;
+    while (i0 < num_items) {
+      if (need[i0] > room / 2) {   // cannot fit even alone
+        WebPBatchItem* it = &items[i0];
+        it->status = VP8_STATUS_OUT_OF_MEMORY;
+        WebPBitstreamFeatures f;   // the reference fills config->input before it allocates (webp_dec.c:761-767)
+        if (it->config != NULL && vp8b_get_features(it->data, it->data_size, &f) == VP8_STATUS_OK) it->config->input = f;
+        ++i0;
+        continue;
+      }
+      int i1 = i0; size_t acc = 0;
+      while (i1 < num_items && need[i1] <= room / 2 && (i1 == i0 || acc + need[i1] <= cap)) acc += need[i1++];
+      decode_group(items + i0, i1 - i0, options, &tm, &nwaves);
+      i0 = i1;
+    }
+    result = first_failure(items, num_items);
+  }
   if (trace) {
-    const auto t3 = std::chrono::steady_clock::now();
-    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point c) {
-      return std::chrono::duration<double, std::milli>(c - a).count();
-    };
-    fprintf(stderr, "libwebp_b200 trace: %d items, %zu waves: create(plan+alloc+H2D) %.1f ms, decode+download %.1f ms "
-            "(kernels %.1f = modes %.1f tokens %.1f recon %.1f filter %.1f emit %.1f), destroy %.1f ms\n",
-            num_items, nwaves, ms(t0, t1), ms(t1, t2), tm.total_ms, tm.modes_ms, tm.tokens_ms, tm.recon_ms, tm.filter_ms,
-            tm.emit_ms, ms(t2, t3));
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "libwebp_b200 trace: %d items, %zu waves: %.1f ms in the call (kernels %.1f = modes %.1f tokens %.1f recon %.1f filter %.1f emit %.1f alpha %.1f)\n",
+            num_items, nwaves, std::chrono::duration<double, std::milli>(t1 - t0).count(), tm.total_ms, tm.modes_ms, tm.tokens_ms, tm.recon_ms,
+            tm.filter_ms, tm.emit_ms, tm.alpha_ms);
   }
-  for (int i = 0; i < num_items; ++i) if (items[i].status != VP8_STATUS_OK) return items[i].status;
-  return st;
+  const VP8StatusCode ff = first_failure(items, num_items);
+  return ff != VP8_STATUS_OK ? ff : result;
 }

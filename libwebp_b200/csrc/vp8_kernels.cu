@@ -30,6 +30,7 @@
 #include "vp8_pixel_core.h"
 #include "vp8_tokens_fsm.h"
 #include "vp8_tokens_lockstep.h"
+#include "vp8_tokens_fp.h"
 #define AL_BLOCK_SYNC() __syncthreads()
 #include "vp8l_alpha_core.h"
 #include "vp8l_lossless_core.h"
@@ -369,12 +370,99 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_lockstep(const uint
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Lockstep lanes with the fp32 boolean decoder and token-stream output (vp8_tokens_fp.h): the default token parser.
+// A block owns ipb images x P partitions = S streams; stream j sits in warp j % cw, lane j / cw.
+struct TfLayout {   // byte offsets from the 1024-byte aligned start of the block's dynamic shared memory
+  uint32_t images, progress, ctx, total;
+};
+__host__ __device__ static inline TfLayout tf_layout(int P, int ipb, int ctx_stride) {
+  TfLayout t;
+  t.images = 1024;                                         // TfTables in front
+  t.progress = t.images + (uint32_t)ipb * TF_IMG_BYTES;
+  t.ctx = t.progress + (uint32_t)ipb * VP8B_MAX_PARTS * 4u;
+  t.total = t.ctx + (uint32_t)ipb * (uint32_t)(P + 1) * (uint32_t)ctx_stride * 2u + 1024u;   // + alignment slack
+  return t;
+}
+
+__global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_fp(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
+                                                            FrameHdr* hdrs, uint32_t* mbinfo, uint32_t* tokens, MbTok* mbtok,
+                                                            const int* __restrict__ ids, int count, int P, int ipb, int lpw,
+                                                            int cw, int ctx_stride) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tk_saddr_of(smem_raw) & 1023u)) & 1023u);   // the rows' addresses carry the position in bits 6-9
+  const TfLayout lay = tf_layout(P, ipb, ctx_stride);
+  TfTables* tables = reinterpret_cast<TfTables*>(smem);
+  int* progress = reinterpret_cast<int*>(smem + lay.progress);
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  tf_tables_fill(tables, tid, nthreads);
+  for (int k = tid; k < ipb * VP8B_MAX_PARTS; k += nthreads) progress[k] = 0;
+  for (int slot = 0; slot < ipb; ++slot) {
+    const int g = blockIdx.x * ipb + slot;
+    if (g < count) tf_image_fill(smem + lay.images + (size_t)slot * TF_IMG_BYTES, &hdrs[ids[g]], tid, nthreads);
+  }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5;
+  const int j = lane * cw + warp;           // stream inside the block
+  const int slot = j / P, part = j % P;
+  const int g = blockIdx.x * ipb + slot;
+  int have = lane < lpw && j < ipb * P && g < count;
+  const int img = have ? ids[g] : 0;
+  FrameHdr* h = &hdrs[img];
+  if (have && !(h->status == VP8B_OK && h->num_parts == P)) {   // header failed (or, never expected, the host pre-scan disagreed)
+    if (part == 0 && h->status == VP8B_OK) h->status = VP8B_BITSTREAM_ERROR;
+    have = 0;
+  }
+  const ImgDesc im = imgs[img];
+  TfCtx c;
+  c.img_s = tk_saddr_of(smem + lay.images + (size_t)(have ? slot : 0) * TF_IMG_BYTES);
+  c.tab_s = tk_saddr_of(tables);
+  c.k.mant_mask = 0x007fffffu; c.k.exp128 = 0x43000000u;
+  asm volatile("" : "+r"(c.img_s), "+r"(c.tab_s), "+r"(c.k.mant_mask), "+r"(c.k.exp128));   // plain registers: no per-step cvta, one LOP3 in fd_bit
+  c.topctx = reinterpret_cast<uint16_t*>(smem + lay.ctx) + (size_t)(have ? slot : 0) * (P + 1) * ctx_stride;
+  c.progress = progress + (have ? slot : 0) * VP8B_MAX_PARTS;
+  c.mbinfo = mbinfo + 4 * (size_t)im.mb_base;
+  c.mbtok = mbtok + (size_t)im.mb_base;
+  c.tokens = tokens + (size_t)im.mb_base * TF_TOKENS_PER_MB;
+  c.mb_w = im.mb_w; c.rows = have ? h->rows : 0; c.P = P; c.part = part; c.use_skip = h->use_skip;
+  c.ctx_stride = ctx_stride;
+  if (part >= c.rows) have = 0;
+  asm volatile("" : "+r"(c.P), "+r"(c.ctx_stride), "+r"(c.mb_w), "+l"(c.mbinfo), "+l"(c.tokens), "+l"(c.mbtok));
+  __builtin_assume(__isGlobal(c.mbinfo));
+  __builtin_assume(__isGlobal(c.tokens));
+  __builtin_assume(__isGlobal(c.mbtok));
+  TfLane L;
+  if (have) tf_lane_init(L, c, arena + im.in_off, h); else tf_lane_idle(L, c, arena);
+  // The loop counter starts from a per-thread value (always 0) so that the compiler does not fence the body with
+  // WARPSYNC.ALL; the vote costs as much as half a step and is taken every 32 steps.
+  const int r0 = (int)(L.sink >> 31);
+  if (P > 1) {
+    while (__any_sync(0xffffffffu, L.alive)) {
+      for (int r = r0; r < 8; ++r) {
+        fd_fill(L.d);
+        tf_step_inline<1>(L, c); tf_step_inline<1>(L, c); tf_step_inline<1>(L, c); tf_step_inline<1>(L, c);
+      }
+    }
+  } else {
+    if (have && !tf_mb_next<0>(L, c)) tf_lane_park(L, c);
+    while (__any_sync(0xffffffffu, L.alive)) {
+      for (int r = r0; r < 8; ++r) {
+        fd_fill(L.d);
+        tf_step_inline<0>(L, c); tf_step_inline<0>(L, c); tf_step_inline<0>(L, c); tf_step_inline<0>(L, c);
+      }
+    }
+  }
+  if (have && L.status != VP8B_OK) h->status = L.status;
+  if (L.sink == 0xffffffffu) h->status = VP8B_BITSTREAM_ERROR;   // never true (an XOR of bytes): keeps TfLane::sink alive
+}
+
+// ---------------------------------------------------------------------------------------------------------
 #define RECON_WARPS 8
 
 __global__ void __launch_bounds__(32 * RECON_WARPS) k_reconstruct(const ImgDesc* __restrict__ imgs, const FrameHdr* __restrict__ hdrs,
                                                                   uint32_t* mbinfo, const int16_t* __restrict__ coeffs,
                                                                   uint8_t* yuv, int first, int row_begin, int row_end,
-                                                                  uint8_t* band_ctx, int band_ctx_stride) {
+                                                                  uint8_t* band_ctx, int band_ctx_stride,
+                                                                  const uint32_t* __restrict__ tokens, const MbTok* __restrict__ mbtok) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int img = first + blockIdx.x;
   if (hdrs[img].status != VP8B_OK) return;
@@ -399,6 +487,8 @@ __global__ void __launch_bounds__(32 * RECON_WARPS) k_reconstruct(const ImgDesc*
   uint8_t* vp = up + nmb * 64;
   uint32_t* mbi = mbinfo + 4 * (size_t)im.mb_base;
   const int16_t* cf = coeffs + (size_t)im.mb_base * VP8B_COEFFS_PER_MB;
+  const uint32_t* tk = tokens != nullptr ? tokens + (size_t)im.mb_base * TF_TOKENS_PER_MB : nullptr;   // token stream instead of the dense plane
+  const MbTok* mt = mbtok + (size_t)im.mb_base;
   // Lag-2 anti-diagonal wavefront with a block-wide barrier per step. (A barrier-free variant -- one warp per row,
   // progress counters in shared memory, as k_loop_filter does now -- measured 52 -> 72 ms here: this kernel is issue-bound
   // and the warps that spin on a counter take issue slots from the ones that work; at a barrier they sleep.)
@@ -412,7 +502,12 @@ __global__ void __launch_bounds__(32 * RECON_WARPS) k_reconstruct(const ImgDesc*
       const int mx = d - 2 * ly, my = r0 + ly;
       const size_t idx = (size_t)my * mb_w + mx;
       const int16_t* dq6 = dqs + 6 * ((mbi[4 * idx + 3] >> MBW_SEG_SHIFT) & 3);
-      recon_macroblock(ws, cx, mx, my, mb_w, mbi + 4 * idx, cf + idx * VP8B_COEFFS_PER_MB, dq6, yp, up, vp);
+      if (tk != nullptr) {
+        const MbTok t = mt[idx];
+        recon_macroblock(ws, cx, mx, my, mb_w, mbi + 4 * idx, nullptr, dq6, yp, up, vp, tk + t.first, t.count);
+      } else {
+        recon_macroblock(ws, cx, mx, my, mb_w, mbi + 4 * idx, cf + idx * VP8B_COEFFS_PER_MB, dq6, yp, up, vp);
+      }
     }
     __syncthreads();
   }
@@ -558,10 +653,18 @@ static size_t tokens_slot_bytes(int P, int max_mb_w) {
   return (TOKW_CTX + (size_t)(P + 1) * max_mb_w * 2 + 15) & ~(size_t)15;
 }
 
-extern "C" cudaError_t vp8k_configure(int max_mb_w, int max_mb_h) {
-  cudaError_t e = cudaFuncSetAttribute(k_reconstruct, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)recon_smem_bytes(max_mb_w, max_mb_h));
-  if (e != cudaSuccess) return e;
+#define VP8K_MAX_DYN_SMEM (227 * 1024)   // opt-in ceiling per block on sm_100
+extern "C" cudaError_t vp8k_init_device(void) {
+  const void* kernels[] = { (const void*)k_parse_modes, (const void*)k_parse_tokens, (const void*)k_parse_tokens_fsm,
+                            (const void*)k_parse_tokens_lockstep, (const void*)k_parse_tokens_fp, (const void*)k_reconstruct,
+                            (const void*)k_loop_filter };
+  for (const void* k : kernels) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, k);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, VP8K_MAX_DYN_SMEM - (int)fa.sharedSizeBytes);
+    if (e != cudaSuccess) return e;
+  }
   return cudaSuccess;
 }
 
@@ -600,12 +703,7 @@ extern "C" void vp8k_parse_modes(cudaStream_t s, const uint8_t* arena, const Img
     ipb = 4 * lanes;   // one warp per sub-partition and block; many blocks per SM
     while (ipb > lanes && (size_t)ipb * max_mb_w * 4 > 200u * 1024u) ipb -= lanes;
   }
-  static size_t configured = 0;
   const size_t smem = (size_t)ipb * max_mb_w * 4;
-  if (smem > configured) {
-    cudaFuncSetAttribute(k_parse_modes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
   const int warps = (ipb + lanes - 1) / lanes;
   k_parse_modes<<<(count + ipb - 1) / ipb, 32 * warps, smem, s>>>(arena, imgs, hdrs, mbinfo, first, count, ipb, max_mb_w, lanes);
 }
@@ -633,11 +731,6 @@ static void launch_tokens_fsm(cudaStream_t s, const uint8_t* arena, const ImgDes
   while (ipb > 1 && tok_layout(P, ipb, max_mb_w).total > 200u * 1024u) --ipb;
   const TokLayout lay = tok_layout(P, ipb, max_mb_w);
   const int blocks = (count + ipb - 1) / ipb;
-  static size_t configured = 0;
-  if (lay.total > configured) {
-    cudaFuncSetAttribute(k_parse_tokens_fsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
-    configured = lay.total;
-  }
   k_parse_tokens_fsm<<<blocks, 32 * (cw + 1), lay.total, s>>>(arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, ipb, lpw, cw, max_mb_w);
 }
 
@@ -661,11 +754,6 @@ static void launch_tokens_lockstep(cudaStream_t s, const uint8_t* arena, const I
   while (ipb > 1 && tl_layout(P, ipb, max_mb_w).total > 200u * 1024u) --ipb;
   const TlLayout lay = tl_layout(P, ipb, max_mb_w);
   const int blocks = (count + ipb - 1) / ipb;
-  static size_t configured = 0;
-  if (lay.total > configured) {
-    cudaFuncSetAttribute(k_parse_tokens_lockstep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
-    configured = lay.total;
-  }
   // How the lanes are run (vp8_tokens_lockstep.h): 0 = block ends on the spot, while a warp has few lanes; 2 = groups of four
   // straight-line steps with one event point, when it has many (the event point's cost is shared by all the lanes that have
   // a block end pending); 1 = the same with branches around the steps of lanes that are not running. Measured per 4096
@@ -677,6 +765,37 @@ static void launch_tokens_lockstep(cudaStream_t s, const uint8_t* arena, const I
   const int grouped = f_grouped >= 0 ? f_grouped : (lanes_per_warp >= 16 ? 2 : 0);
   k_parse_tokens_lockstep<<<blocks, 32 * cw, lay.total, s>>>(arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, ipb, lpw, cw, max_mb_w, grouped,
                                                              row_begin, row_end, resume, resume_ctx);
+}
+
+// Launch geometry of the fp parser: cw warps per block (one per SM sub-partition while the streams fit eight to a warp, then
+// more), lpw streams per warp so that one block per SM holds the whole launch where shared memory allows it.
+static void launch_tokens_fp(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,
+                             uint32_t* tokens, MbTok* mbtok, const int* ids, int count, int P, int max_mb_w) {
+  const int f_lpw = env_int("WEBP_B200_TOKEN_LPW"), f_cw = env_int("WEBP_B200_TOKEN_CW");
+  const long streams = (long)count * P;
+  int cw = (f_cw >= 1 && f_cw <= 16) ? f_cw : (streams <= 148L * 4 * 8 ? 4 : 8);
+  int lpw = (int)((streams + 148L * cw - 1) / (148L * cw));
+  if (f_lpw >= 1 && f_lpw <= 32) lpw = f_lpw;
+  if (lpw < 1) lpw = 1;
+  if (lpw > 32) lpw = 32;
+  while (cw * lpw < P) ++lpw;               // a block holds at least one image
+  int ipb = (cw * lpw) / P;                  // images per block
+  while (ipb > 1 && tf_layout(P, ipb, max_mb_w).total > (uint32_t)VP8K_MAX_DYN_SMEM - 1024u) --ipb;
+  const TfLayout lay = tf_layout(P, ipb, max_mb_w);
+  const int blocks = (count + ipb - 1) / ipb;
+  k_parse_tokens_fp<<<blocks, 32 * cw, lay.total, s>>>(arena, imgs, hdrs, mbinfo, tokens, mbtok, ids, count, P, ipb, lpw, cw, max_mb_w);
+}
+
+// Which token parser a wave takes: 1 = the fp parser (token stream out), 0 = one of the older mappings (dense level plane),
+// forced by WEBP_B200_TOKEN_MAP=warp|k|lanes (A/B runs, and the row-band pipeline, which only the older lockstep parser has).
+extern "C" int vp8k_tokens_use_stream(void) {
+  const char* e = getenv("WEBP_B200_TOKEN_MAP");
+  return e == NULL || e[0] == 'f';
+}
+
+extern "C" void vp8k_parse_tokens_stream(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,
+                                         uint32_t* tokens, void* mbtok, const int* ids, int count, int P, int max_mb_w) {
+  launch_tokens_fp(s, arena, imgs, hdrs, mbinfo, tokens, (MbTok*)mbtok, ids, count, P, max_mb_w);
 }
 
 extern "C" int vp8k_tokens_take_bands(int count, int P) {   // does vp8k_parse_tokens pick the mapping that can parse by row bands?
@@ -720,11 +839,6 @@ extern "C" void vp8k_parse_tokens(cudaStream_t s, const uint8_t* arena, const Im
     if (f_ipb >= 1 && f_ipb <= ipb) ipb = f_ipb;
     while (ipb > 1 && (size_t)ipb * slot > 200u * 1024u) --ipb;
     ipb = pack_per_block(count, ipb);
-    static size_t configured = 0;
-    if ((size_t)ipb * slot > configured) {
-      cudaFuncSetAttribute(k_parse_tokens, cudaFuncAttributeMaxDynamicSharedMemorySize, ipb * slot);
-      configured = (size_t)ipb * slot;
-    }
     k_parse_tokens<<<(count + ipb - 1) / ipb, 32 * ipb * P, (size_t)ipb * slot, s>>>(arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, ipb, slot);
     return;
   }
@@ -733,9 +847,9 @@ extern "C" void vp8k_parse_tokens(cudaStream_t s, const uint8_t* arena, const Im
 
 extern "C" void vp8k_reconstruct(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, uint32_t* mbinfo, const int16_t* coeffs,
                                  uint8_t* yuv, int first, int count, int max_mb_w, int max_mb_h, int row_begin, int row_end,
-                                 uint8_t* band_ctx) {
+                                 uint8_t* band_ctx, const uint32_t* tokens, const void* mbtok) {
   k_reconstruct<<<count, 32 * RECON_WARPS, recon_smem_bytes(max_mb_w, max_mb_h), s>>>(imgs, hdrs, mbinfo, coeffs, yuv, first, row_begin,
-                                                                                      row_end, band_ctx, 32 * max_mb_w);
+                                                                                      row_end, band_ctx, 32 * max_mb_w, tokens, (const MbTok*)mbtok);
 }
 
 extern "C" void vp8k_loop_filter(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint32_t* mbinfo, uint8_t* yuv,

@@ -10,8 +10,9 @@
 extern "C" {
 #endif
 
-// Raises the dynamic shared-memory limits for the largest image of the batch (in macroblocks).
-cudaError_t vp8k_configure(int max_mb_w, int max_mb_h);
+// Once per device (the calling thread's current one): opts every kernel that sizes its shared memory at launch into the
+// full 227 KB. The attribute belongs to the device's context, so nothing about it may live in process-wide statics.
+cudaError_t vp8k_init_device(void);
 
 // Images [first, first+count) of the wave. All launches are asynchronous on `s`.
 void vp8k_parse_modes(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,
@@ -29,8 +30,16 @@ int vp8k_tokens_take_bands(int count, int P);
 void vp8k_parse_tokens_band(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,
                             int16_t* coeffs, const int* ids, int count, int max_mb_w, int row_begin, int row_end,
                             TokResume* resume, uint16_t* resume_ctx);
+// `tokens` != NULL: the levels come from the token stream (VP8B_TOKENS_PER_MB words reserved per macroblock) and `mbtok`
+// (two words per macroblock: first token inside the image's area, count), as vp8k_parse_tokens_stream left them; else
+// from the dense plane `coeffs` of the older parsers.
 void vp8k_reconstruct(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, uint32_t* mbinfo, const int16_t* coeffs,
-                      uint8_t* yuv, int first, int count, int max_mb_w, int max_mb_h, int row_begin, int row_end, uint8_t* band_ctx);
+                      uint8_t* yuv, int first, int count, int max_mb_w, int max_mb_h, int row_begin, int row_end, uint8_t* band_ctx,
+                      const uint32_t* tokens, const void* mbtok);
+// The default token parser (vp8_tokens_fp.h): lockstep lanes, fp32 boolean decoder, one 32-bit token per non-zero level.
+int vp8k_tokens_use_stream(void);
+void vp8k_parse_tokens_stream(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,
+                              uint32_t* tokens, void* mbtok, const int* ids, int count, int P, int max_mb_w);
 void vp8k_loop_filter(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint32_t* mbinfo, uint8_t* yuv,
                       int first, int count, int max_mb_h, int row_begin, int row_end, const int8_t* dither_plane);
 // options.dithering_strength: after the token parse of the whole image, before the loop filter. dither_plane = 128 bytes

@@ -48,6 +48,8 @@ VP8_PFN int mul2(int a) { return (a * 35468) >> 16; }
 // the four pixels above-right (replicated at rows 4, 8, 12 for the right-most sub-blocks, frame_dec.c:131-141).
 // Chroma: u at uv[(r + 1) * 32 + c + 4], v at uv[(r + 1) * 32 + c + 20].
 struct ReconWs {
+  int16_t lv[25 * 16];                // the macroblock's coefficient LEVELS, parse order inside a block (blocks 0-23, 24 = Y2): the
+                                      // token parser's stream scattered out by recon_load_tokens (16-byte aligned: first member)
   int16_t res[24 * 16];               // residual (IDCT output, already >> 3) of blocks 0-23, raster order inside a block
   uint8_t y[17 * 32];
   uint8_t uv[9 * 32];
@@ -102,6 +104,23 @@ VP8_PFN void load_block_coeffs(const int16_t* levels, int q_dc, int q_ac, int in
     const int lvl = (n & 1) ? ((int)wd[n >> 1] >> 16) : (int)(int16_t)(wd[n >> 1] & 0xffffu);
     in[zz[n]] = (int)(int16_t)(lvl * (n == 0 ? q_dc : q_ac));
   }
+}
+
+// A macroblock's tokens (vp8_tokens_fp.h: {sign 31, block 29:25, magnitude 24:13, position 9:6}, `count` words at
+// `toks`) -> ws.lv, the dense 25 x 16 level array load_block_coeffs reads. One warp; the caller's next phase may read.
+VP8_PFN void recon_load_tokens(ReconWs& ws, const uint32_t* toks, uint32_t count) {
+  WARP_PHASE(lane)
+    uint4 z; z.x = 0; z.y = 0; z.z = 0; z.w = 0;
+    uint4* dst = (uint4*)ws.lv;
+    if (lane < 25) { dst[2 * lane] = z; dst[2 * lane + 1] = z; }
+  WARP_PHASE_END
+  WARP_PHASE(lane)
+    for (uint32_t k = (uint32_t)lane; k < count; k += 32) {
+      const uint32_t t = toks[k];
+      const int mag = (int)((t >> 13) & 0xfffu);
+      ws.lv[((t >> 25) & 31u) * 16u + ((t >> 6) & 15u)] = (int16_t)((t >> 31) ? -mag : mag);
+    }
+  WARP_PHASE_END
 }
 
 // TransformOne_C (dsp/dec.c:44-82) without the prediction: out = the 16 residuals to add, raster order.
@@ -184,7 +203,8 @@ VP8_PFN int check_mode(int mx, int my, int mode) {
 // Also finalises MbInfo: the filter-inner bit (vp8_dec.c:629-633), which needs the lone-DC rule
 // NzCodeBits(nz, dst[0] != 0) (vp8_dec.c:511-515) evaluated on the dequantised int16.
 VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, int mb_w, uint32_t* info,
-                              const int16_t* coeffs, const int16_t* dq6, uint8_t* yplane, uint8_t* uplane, uint8_t* vplane) {
+                              const int16_t* coeffs, const int16_t* dq6, uint8_t* yplane, uint8_t* uplane, uint8_t* vplane,
+                              const uint32_t* toks = nullptr, uint32_t ntok = 0) {
   const uint32_t w = info[3];
   const uint32_t m0 = info[0], m1 = info[1];
   const uint32_t nzy = info[2];
@@ -193,6 +213,11 @@ VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, i
   const int has_y2 = (w & MBW_HAS_Y2) != 0;
   const int any_coef = (nzy | nzuv) != 0 || has_y2;
   const int ys = 16 * mb_w, uvs = 8 * mb_w;
+  // levels: the dense plane of the older token parsers, or this macroblock's slice of the token stream
+  if (toks != nullptr) {
+    if (any_coef) recon_load_tokens(ws, toks, ntok);
+    coeffs = ws.lv;
+  }
 
   // ---- phase 0: neighbour pixels -> tile; inverse WHT of the Y2 block (lane 21)
   WARP_PHASE(lane)

@@ -1,0 +1,517 @@
+// vp8_tokens_fp.h -- coefficient-token parser, fourth mapping: lockstep lanes, fp32 boolean decoder, token stream out.
+//
+// Same shape as vp8_tokens_lockstep.h (one LANE per token partition, one boolean decode per lane per step, the token
+// syntax of GetCoeffs / GetLargeValue, src/dec/vp8_dec.c:411-469, as a table of states), rebuilt around what
+// tools/chain_floor.cu measured on the B200 (profiles/r02b_chain_floor.json):
+//
+//  * One warp alone on an SM sub-partition issues an integer-pipe instruction every 2 cycles whatever the number of
+//    active lanes, and the chain of one decode through IMAD.HI (9 cycles) and FLO (17 cycles) takes 58 cycles. The
+//    decoder here keeps the range as two floats and gets the split from one FFMA.RZ and the renormalisation shift
+//    from the exponent field (bit-exact: every quantity is an integer below 2^24; 3 * 10^9 random decodes against
+//    the integer form, zero differences):
+//        Rs = (range-1)/256, Rp = (range-1) + 2^23, pf = float(prob)
+//        m  = fma.rz(Rs, pf, 2^23)          = 2^23 + split                 (rz truncates: floor)
+//        s1 = bits(m) * 2^24 + 2^24         = (split + 1) << 24            (the 0x4B exponent byte falls off the top)
+//        bit = V >= s1
+//        f  = bit ? Rp - m : m - (2^23-1)   = new range as a float         (range-1-split, or split+1)
+//        shift = 134 - (bits(f) >> 23);  new range = mantissa of f under exponent 2^7
+//  * A step spends its integer-pipe slots on selects, so the rest is moved to the FMA pipe or dropped:
+//      - the magnitude is not assembled per step: `acc += entry` (one IMAD.IADD) adds the whole transition entry, whose
+//        fields are laid out so that the junk of the low fields never carries into the addend field; the magnitude
+//        is masked out at the emit
+//      - no row pointer: the address of the pending probability is the state, an entry carries the distance to the
+//        next one (rows are 64 bytes apart, so the coefficient position is bits 6-9 of that address)
+//  * Levels are not stored into a zero-filled 800-byte plane any more. Every non-zero level is appended as one
+//    32-bit token {sign, block, position, magnitude} to the partition's token stream (worst case 384 per macroblock
+//    reserved, only what is written is ever touched), and MbTok[mb] = {first token, count}: the reconstruction
+//    kernel scatters a macroblock's tokens into shared memory (vp8_pixel_core.h:recon_load_tokens).
+//
+// Replaces VP8DecodeMB / ParseResiduals / GetCoeffs / GetLargeValue (src/dec/vp8_dec.c:400-635) for a batch.
+// Dual build like the other cores: nvcc for the product, g++ -DVP8_EMU for tests/emu.
+#ifndef LIBWEBP_B200_VP8_TOKENS_FP_H_
+#define LIBWEBP_B200_VP8_TOKENS_FP_H_
+
+#include "vp8_dev.h"
+#include "vp8_parse_core.h"
+#include "vp8_tokens_fsm.h"   // TK_FN, tk_saddr and the shared-memory access helpers
+
+#if defined(__GNUC__) || defined(__CUDACC__)
+#define TF_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#else
+#define TF_UNLIKELY(x) (x)
+#endif
+
+// ---- states: 0..32 = [ctx 3][node 11] of the position's band; then the fixed probabilities. Numbered so that every
+// transition that stays at its position moves UP (the distance field of an entry is unsigned).
+#define TF_C159 33
+#define TF_C165 34
+#define TF_C145 35
+#define TF_CAT3 36     // 3 extra bits
+#define TF_CAT4 39     // 4
+#define TF_CAT5 43     // 5
+#define TF_CAT6 48     // 11
+#define TF_SIGN1 59    // sign of a coefficient of magnitude 1 (next context 1)
+#define TF_SIGN2 60    // sign of a larger one (next context 2)
+#define TF_STATES 61
+#define TF_DEAD 63u
+#define TF_ROW_BYTES 64
+#define TF_TYPE_BYTES (16 * TF_ROW_BYTES)   // 1024: the position of a probability is bits 6-9 of its address
+#define TF_IMG_BYTES (4 * TF_TYPE_BYTES)    // per image, 1024-byte aligned
+
+// ---- transition entry
+//   [31:25] distance in bytes from the pending probability to the next one: next s + 64 * (n advances) - s
+//   [24:13] addend of the magnitude          (the sums of the fields below stay under 2^13 between two resets of acc)
+//   [8:3]   next s, i.e. the offset of the next state's entry pair in the table
+//   1       end of block      0  emit at the current position
+#define TF_EMIT 1u
+#define TF_EOB 2u
+#define TF_ADD_SHIFT 13
+#define TF_ADD_MASK 0x01ffe000u
+#define TF_E(s, next, adv, flags, add) \
+  ((((uint32_t)(next) + ((adv) ? 64u : 0u) - (uint32_t)(s)) << 25) | ((uint32_t)(add) << TF_ADD_SHIFT) | ((uint32_t)(next) << 3) | (uint32_t)(flags))
+#define TF_E_DIST(e) ((e) >> 25)
+#define TF_E_TAB(e) ((e) & 0x1f8u)
+
+TK_FN uint32_t tf_trans_entry(int s, int b) {
+  if (s < 33) {
+    const int base = (s / 11) * 11, k = s % 11;
+    switch (k) {
+      case 0: return b ? TF_E(s, s + 1, 0, 0, 0) : TF_E(s, s, 0, TF_EOB, 0);
+      case 1: return b ? TF_E(s, s + 1, 0, 0, 0) : TF_E(s, 1, 1, 0, 0);            // a zero: next position, ctx 0, node 1
+      case 2: return b ? TF_E(s, s + 1, 0, 0, 0) : TF_E(s, TF_SIGN1, 0, 0, 1);
+      case 3: return b ? TF_E(s, base + 6, 0, 0, 0) : TF_E(s, base + 4, 0, 0, 0);
+      case 4: return b ? TF_E(s, base + 5, 0, 0, 0) : TF_E(s, TF_SIGN2, 0, 0, 2);
+      case 5: return b ? TF_E(s, TF_SIGN2, 0, 0, 4) : TF_E(s, TF_SIGN2, 0, 0, 3);
+      case 6: return b ? TF_E(s, base + 8, 0, 0, 0) : TF_E(s, base + 7, 0, 0, 0);
+      case 7: return b ? TF_E(s, TF_C165, 0, 0, 7) : TF_E(s, TF_C159, 0, 0, 5);
+      case 8: return b ? TF_E(s, base + 10, 0, 0, 0) : TF_E(s, base + 9, 0, 0, 0);
+      case 9: return b ? TF_E(s, TF_CAT4, 0, 0, 3 + 16) : TF_E(s, TF_CAT3, 0, 0, 3 + 8);
+      default: return b ? TF_E(s, TF_CAT6, 0, 0, 3 + 64) : TF_E(s, TF_CAT5, 0, 0, 3 + 32);
+    }
+  }
+  if (s == TF_SIGN1) return TF_E(s, 11, 1, TF_EMIT, 0);
+  if (s == TF_SIGN2) return TF_E(s, 22, 1, TF_EMIT, 0);
+  if (s == TF_C159) return TF_E(s, TF_SIGN2, 0, 0, b);
+  if (s == TF_C165) return TF_E(s, TF_C145, 0, 0, 2 * b);
+  if (s == TF_C145) return TF_E(s, TF_SIGN2, 0, 0, b);
+  int first, nb;
+  if (s < TF_CAT4) { first = TF_CAT3; nb = 3; }
+  else if (s < TF_CAT5) { first = TF_CAT4; nb = 4; }
+  else if (s < TF_CAT6) { first = TF_CAT5; nb = 5; }
+  else { first = TF_CAT6; nb = 11; }
+  const int i = s - first;
+  return TF_E(s, i == nb - 1 ? TF_SIGN2 : s + 1, 0, 0, b << (nb - 1 - i));
+}
+
+// byte s of the row of (type t, position n)
+TK_FN uint8_t tf_row_byte(const uint8_t* prob /* [4][8][3][11] */, int t, int n, int s) {
+  const uint8_t fixed[28] = { 159, 165, 145, 173, 148, 140, 176, 155, 140, 135, 180, 157, 141, 134, 130,
+                              254, 254, 243, 230, 196, 177, 153, 140, 133, 130, 129, 128, 128 };
+  const uint8_t bands[16] = { 0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7 };
+  if (s < 33) return prob[t * 264 + bands[n] * 33 + s];
+  if (s < TF_STATES) return fixed[s - 33];
+  return 0;
+}
+
+// Block-wide tables in shared memory.
+struct TfTables {
+  uint32_t trans[64][2];   // [s][bit]; states 61..63 are dead (probability 0 for ever, nothing emitted, no block end)
+  uint32_t seqmask[28];    // block seq (0 = Y2, 1..16 luma, 17..24 chroma): its two context bits inside TfLane::cx
+};
+#define TFT_SEQMASK 512
+#define TF_TAB_BYTES 624    // sizeof(TfTables)
+
+TK_FN uint32_t tf_seqmask(int k) {
+  if (k == 0) return (1u << 8) | (1u << 24);
+  if (k <= 16) { const uint32_t blk = (uint32_t)k - 1; return (1u << (blk & 3)) | (1u << (16 + (blk >> 2))); }
+  if (k <= 24) {
+    const uint32_t c = (uint32_t)k - 17;
+    return (1u << (4 + (c & 1) + 2 * (c >> 2))) | (1u << (16 + 4 + ((c >> 1) & 1) + 2 * (c >> 2)));
+  }
+  return 0;
+}
+
+TK_FN void tf_tables_fill(TfTables* t, int tid, int nthreads) {
+  for (int k = tid; k < 128; k += nthreads) {
+    const int st = k >> 1;
+    t->trans[st][k & 1] = st < TF_STATES ? tf_trans_entry(st, k & 1) : TF_E(st, st, 0, 0, 0);
+  }
+  for (int k = tid; k < 28; k += nthreads) t->seqmask[k] = tf_seqmask(k);
+}
+
+// One image's rows (TF_IMG_BYTES at `dst`, 1024-byte aligned) from the parsed header; any thread subset.
+TK_FN void tf_image_fill(uint8_t* dst, const FrameHdr* h, int tid, int nthreads) {
+  for (int k = tid; k < TF_IMG_BYTES / 4; k += nthreads) {
+    const int t = k >> 8, n = (k >> 4) & 15, s0 = (k & 15) * 4;
+    uint32_t w = 0;
+    for (int j = 0; j < 4; ++j) w |= (uint32_t)tf_row_byte(h->prob, t, n, s0 + j) << (8 * j);
+    ((uint32_t*)dst)[k] = w;
+  }
+}
+
+// ---- fp32 boolean decoder (see the file header). The window, its refill and the end-of-stream rule are BoolDec's.
+#if defined(__CUDACC__) && !defined(VP8_EMU)
+TK_FN float tf_fma_rz(float a, float b, float c) { return __fmaf_rz(a, b, c); }
+TK_FN float tf_as_float(uint32_t u) { return __uint_as_float(u); }
+TK_FN uint32_t tf_as_uint(float f) { return __float_as_uint(f); }
+// (x & m) | o with the two constants in registers: ONE LOP3 (with immediates the assembler needs two)
+TK_FN uint32_t tf_and_or(uint32_t x, uint32_t m, uint32_t o) { uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(x), "r"(m), "r"(o)); return r; }
+TK_FN float tf_u8_to_float(uint32_t p) { return __uint_as_float(0x4b000000u | p) - 8388608.0f; }
+#else
+#include <math.h>
+TK_FN float tf_fma_rz(float a, float b, float c) {   // a*b + c is exact in double here (integers below 2^24 and their 1/256ths)
+  const double d = (double)a * (double)b + (double)c;
+  float f = (float)d;
+  if ((double)f > d) f = nextafterf(f, 0.0f);
+  return f;
+}
+TK_FN float tf_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+TK_FN uint32_t tf_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+TK_FN uint32_t tf_and_or(uint32_t x, uint32_t m, uint32_t o) { return (x & m) | o; }
+TK_FN float tf_u8_to_float(uint32_t p) { return (float)p; }
+#endif
+
+struct FpDec {
+  const uint32_t* wp;    // word after `nxt`
+  const uint32_t* wend;  // first word wholly past the stream: from there on zeros are shifted in
+  const uint32_t* wbase; // stream bits moved into the window so far = 32 * (wp - wbase) - bias8
+  uint32_t V, vlo, nxt;  // 64-bit left-aligned window V:vlo, nxt = the next raw (little-endian) word
+  int nbits;             // valid bits in V:vlo
+  float Rs, Rp;          // (range - 1) / 256 and (range - 1) + 2^23
+  int last_shift;        // renormalisation shift of the most recent decode
+  int bias8;
+  int64_t limit;         // 8*size - 8: a decode starting beyond this bit position reads past the end
+};
+
+TK_FN void fd_init(FpDec& d, const uint8_t* start, uint32_t size) {
+  BoolDec b;
+  bd_init(b, start, size);
+  d.wp = b.wp; d.wend = b.wend; d.wbase = b.wbase; d.V = b.V; d.vlo = b.vlo; d.nxt = b.nxt; d.nbits = b.nbits;
+  d.Rs = 254.0f / 256.0f; d.Rp = 254.0f + 8388608.0f;
+  d.last_shift = 0; d.bias8 = b.bias8; d.limit = b.limit;
+}
+
+TK_FN int fd_eof(const FpDec& d) {   // bd_eof
+  const int64_t loaded = 32 * (int64_t)(d.wp - d.wbase) - d.bias8;
+  return (loaded - d.nbits - d.last_shift) > d.limit;
+}
+
+// bd_fill_lookahead: tops the window up to > 32 valid bits; the word fetched here is not looked at before the next fill.
+TK_FN void fd_fill(FpDec& d) {
+  if (d.nbits <= 32) {
+    const uint32_t* p = d.wp;   // d.nxt came from p - 1
+    const uint32_t w = (p - 1 < d.wend) ? VP8_BSWAP(d.nxt) : 0u;
+    d.nxt = VP8_LDG(p < d.wend ? p : d.wend);   // wend itself lies inside the arena's tail padding
+    d.wp = p + 1;
+    d.V |= vp8_shr_clamp(w, d.nbits);
+    d.vlo = vp8_shl_clamp(w, 32 - d.nbits);
+    d.nbits += 32;
+  }
+}
+
+// Constants of the decode step that must sit in registers (see tf_and_or).
+struct FpConst { uint32_t mant_mask, exp128; };
+
+// One decode; pf = float(probability). Needs >= 8 valid bits in the window.
+TK_FN int fd_bit(FpDec& d, float pf, const FpConst& k) {
+  const float m = tf_fma_rz(d.Rs, pf, 8388608.0f);
+  const uint32_t s1 = tf_as_uint(m) * 0x01000000u + 0x01000000u;
+  const int bit = d.V >= s1;
+  const float f0 = m - 8388607.0f, f1 = d.Rp - m;
+  const float f = bit ? f1 : f0;
+  const uint32_t fb = tf_as_uint(f);
+  const float fn = tf_as_float(tf_and_or(fb, k.mant_mask, k.exp128));   // the new range, normalised into [128, 256)
+  const int shift = 134 - (int)(fb >> 23);
+  d.Rs = fn * 0.00390625f - 0.00390625f;
+  d.Rp = fn + 8388607.0f;
+  d.V = vp8_shl_pair(d.V - (bit ? s1 : 0u), d.vlo, shift);
+  d.vlo <<= shift;
+  d.nbits -= shift;
+  d.last_shift = shift;
+  return bit;
+}
+
+// ---- one token as the reconstruction kernel reads it
+//   31 sign   [29:25] block (0..15 luma, 16..23 chroma, 24 = Y2)   [24:13] magnitude   [9:6] position in parse (zigzag) order
+#define TF_TOK_BLOCK(t) (((t) >> 25) & 31u)
+#define TF_TOK_POS(t) (((t) >> 6) & 15u)
+#define TF_TOK_MAG(t) (((t) >> TF_ADD_SHIFT) & 0xfffu)
+#define TF_TOKENS_PER_MB 384   // 16 x 15 + 16 (i16) or 16 x 16 (i4x4) luma levels + 128 chroma levels
+
+// Lane phases as in vp8_tokens_lockstep.h.
+#define TF_RUN 0
+#define TF_BLOCK_END 1
+#define TF_NEED_MB 2
+#define TF_FINISHED 3
+
+// ---- per-lane state (registers)
+struct TfLane {
+  FpDec d;
+  tk_saddr a;             // address of the pending probability: row of (type, position) + state
+  tk_saddr rowend;        // first address of position 16 of the current block type
+  float pf;               // the pending probability
+  uint32_t e0, e1;        // the transition entries of the pending decode's two outcomes
+  uint32_t sink;          // see tf_decode (never meaningful)
+  uint32_t acc;           // sum of the entries taken since the last emit / block start: magnitude in TF_ADD_MASK
+  uint32_t blktag;        // block index << 25
+  uint32_t tokoff;        // next token of this partition, counted from the image's first token
+  uint32_t mbtok0;        // first token of the current macroblock
+  uint32_t cx;            // non-zero contexts: top in bits 0-8 (0-3 luma, 4-5 U, 6-7 V, 8 Y2), left in bits 16-24
+  uint32_t acc_lo, acc_hi;// 2-bit nz codes of the macroblock's blocks shifted in, in parse order
+  uint32_t m, m_next;     // context bits of the current / the next block (seqmask)
+  uint32_t lut;           // nz -> 2-bit code of the current block: 2-bit fields indexed by min(nz, 4)
+  int seq;                // 0 = Y2, 1..16 luma, 17..24 chroma
+  // macroblock
+  tk_saddr yrow, yend;    // luma rows of this macroblock: first one parsed, end
+  uint32_t ylut;
+  uint32_t w, w_next;     // MbInfo word 3 of this / the partition's next macroblock
+  int mx, my;
+  int done_mbs;
+  int pend;
+  int waiting;            // P > 1: the partition owning the row above has not got far enough yet
+  int alive;              // 0 once parked
+  int status;
+};
+#define TF_LUT_FROM0 0x3a4u   // nz 0 -> 0, 1 -> 1 (a lone DC level: re-examined after dequantisation, recon_macroblock), 2,3 -> 2, >= 4 -> 3
+#define TF_LUT_FROM1 0x3a0u   // luma blocks of i16 macroblocks start at coefficient 1: nz = 1 means empty
+
+// One macroblock's slice of its partition's token stream.
+struct MbTok { uint32_t first, count; };
+
+// Per-lane constants.
+struct TfCtx {
+  tk_saddr img_s;         // this image's rows
+  tk_saddr tab_s;         // TfTables
+  uint16_t* topctx;       // (P + 1) x ctx_stride ring
+  volatile int* progress; // P counters
+  uint32_t* mbinfo;       // this image's MbInfo
+  MbTok* mbtok;           // this image's MbTok
+  uint32_t* tokens;       // this image's token area (TF_TOKENS_PER_MB per macroblock)
+  int mb_w, rows, P, part, use_skip, ctx_stride;
+  FpConst k;
+};
+
+TK_FN void tf_lane_reset(TfLane& L, const TfCtx& c) {
+  L.a = c.img_s; L.rowend = 0; L.pf = 0.f; L.e0 = 0; L.e1 = 0; L.acc = 0; L.sink = 0; L.blktag = 0; L.cx = 0;
+  L.acc_lo = 0; L.acc_hi = 0; L.m = 0; L.m_next = 0; L.lut = 0; L.seq = 0;
+  L.yrow = 0; L.yend = 0; L.ylut = 0;
+  L.mx = 0; L.my = c.part; L.done_mbs = 0; L.waiting = 1; L.alive = 1; L.status = VP8B_OK;
+  L.pend = TF_NEED_MB;
+  L.w = 0; L.w_next = 0;
+  // partition p owns rows p, p + P, ...: its tokens follow those of the partitions before it
+  uint32_t rows_before = 0;
+  for (int q = 0; q < c.part; ++q) rows_before += (uint32_t)((c.rows - q + c.P - 1) / c.P);
+  L.tokoff = rows_before * (uint32_t)c.mb_w * TF_TOKENS_PER_MB;
+  L.mbtok0 = L.tokoff;
+}
+
+TK_FN void tf_lane_init(TfLane& L, const TfCtx& c, const uint8_t* frame, const FrameHdr* h) {
+  fd_init(L.d, frame + h->part_off[c.part], h->part_size[c.part]);
+  tf_lane_reset(L, c);
+  L.w_next = (c.part < c.rows) ? VP8_LDG(c.mbinfo + 4 * ((size_t)c.part * c.mb_w) + 3) : 0;
+}
+
+// Loads the pending decode (probability, both transition entries) of state s at address L.a.
+TK_FN void tf_prime(TfLane& L, const TfCtx& c, uint32_t s) {
+  L.pf = tf_u8_to_float(tk_lds_u8(L.a));
+  tk_lds_v2(c.tab_s + s * 8u, L.e0, L.e1);
+}
+
+TK_FN uint32_t tf_popc(uint32_t x) {
+#if defined(__CUDACC__) && !defined(VP8_EMU)
+  return (uint32_t)__popc(x);
+#else
+  return (uint32_t)__builtin_popcount(x);
+#endif
+}
+
+// Sets up block L.seq >= 1 (contexts in L.cx are final for it). Luma block k is block k - 1, chroma blocks follow.
+TK_FN void tf_block_setup(TfLane& L, const TfCtx& c) {
+  const int chroma = L.seq >= 17;
+  const tk_saddr crow = c.img_s + 2 * TF_TYPE_BYTES;
+  L.m = L.m_next;   // fetched while the previous block was parsed
+  L.m_next = tk_lds_u32(c.tab_s + TFT_SEQMASK + 4u * (uint32_t)L.seq + 4u);
+  L.rowend = chroma ? crow + TF_TYPE_BYTES : L.yend;
+  L.lut = chroma ? TF_LUT_FROM0 : L.ylut;
+  L.blktag = ((uint32_t)L.seq - 1u) << 25;
+  L.acc = 0;
+  const uint32_t s = tf_popc(L.cx & L.m) * 11u;
+  L.a = (chroma ? crow : L.yrow) + s;
+  tf_prime(L, c, s);
+}
+
+// The Y2 block of an i16 macroblock (seq 0): type 1, block 24.
+TK_FN void tf_y2_setup(TfLane& L, const TfCtx& c) {
+  L.m = (1u << 8) | (1u << 24);
+  L.m_next = (1u << 0) | (1u << 16);   // seq 1
+  const tk_saddr row = c.img_s + 1 * TF_TYPE_BYTES;
+  L.rowend = row + TF_TYPE_BYTES;
+  L.lut = TF_LUT_FROM0;
+  L.blktag = 24u << 25;
+  L.acc = 0;
+  const uint32_t s = tf_popc(L.cx & L.m) * 11u;
+  L.a = row + s;
+  tf_prime(L, c, s);
+}
+
+// Stores a finished (or skipped) macroblock's results and steps to the partition's next macroblock.
+template <int MULTI>
+TK_FN void tf_mb_store(TfLane& L, const TfCtx& c, uint32_t nzy, uint32_t w3) {
+  const int P = MULTI ? c.P : 1, mb_w = c.mb_w;
+  const size_t idx = (size_t)L.my * mb_w + L.mx;
+  c.mbinfo[4 * idx + 2] = nzy;
+  c.mbinfo[4 * idx + 3] = w3;
+  MbTok mt; mt.first = L.mbtok0; mt.count = L.tokoff - L.mbtok0;
+  c.mbtok[idx] = mt;
+  L.mbtok0 = L.tokoff;
+  const int ring_row = MULTI ? L.my % (P + 1) : (L.my & 1);
+  c.topctx[(size_t)ring_row * c.ctx_stride + L.mx] = (uint16_t)(L.cx & 0x1ffu);
+  L.done_mbs++;
+  if (++L.mx == mb_w) { L.mx = 0; L.my += P; }
+  if (fd_eof(L.d)) {
+    // Ran past the end of the partition: the image is lost (vp8_dec.c:651-659); release whoever waits on us.
+    L.status = VP8B_NOT_ENOUGH_DATA;
+    if (MULTI) { TK_FENCE(); c.progress[c.part] = 0x7fffffff; }
+  } else if (MULTI) { TK_FENCE(); c.progress[c.part] = L.done_mbs; }
+}
+
+// Leaves the lane either with a block set up (returns 1), waiting for the row above (returns 0, L.waiting = 1) or
+// finished (returns 0, L.waiting = 0, L.my >= rows or L.status != OK). Skipped macroblocks are consumed here.
+template <int MULTI>
+TK_FN int tf_mb_next(TfLane& L, const TfCtx& c) {
+  const int P = MULTI ? c.P : 1, mb_w = c.mb_w;
+  for (;;) {
+    if (L.my >= c.rows || L.status != VP8B_OK) { L.waiting = 0; return 0; }
+    uint32_t tctx = 0;
+    if (L.my > 0) {
+      if (MULTI) {
+        const int prev = (c.part + P - 1) % P;
+        const int need = ((L.my - 1 - prev) / P) * mb_w + L.mx + 1;
+        if (c.progress[prev] < need) { L.waiting = 1; return 0; }
+        TK_FENCE();
+      }
+      const int ring_row = MULTI ? (L.my + P) % (P + 1) : ((L.my + 1) & 1);
+      tctx = c.topctx[(size_t)ring_row * c.ctx_stride + L.mx];
+    }
+    L.waiting = 0;
+    L.w = L.w_next;
+    {   // flags of this partition's next macroblock: needed one macroblock from here
+      int nx = L.mx + 1, ny = L.my;
+      if (nx == mb_w) { nx = 0; ny += P; }
+      if (ny < c.rows) L.w_next = VP8_LDG(c.mbinfo + 4 * ((size_t)ny * mb_w + nx) + 3);
+    }
+    if (L.mx == 0) L.cx = 0;
+    L.cx = (L.cx & 0xffff0000u) | tctx;
+    const int is_i4 = (L.w & MBW_I4X4) != 0;
+    if (!(c.use_skip && (L.w & MBW_SKIP))) {
+      L.acc_lo = 0; L.acc_hi = 0;
+      // luma: type 3 from coefficient 0 (i4x4) or type 0 from coefficient 1 (after the Y2 block)
+      const tk_saddr ybase = c.img_s + (is_i4 ? 3u : 0u) * TF_TYPE_BYTES;
+      L.yend = ybase + TF_TYPE_BYTES;
+      L.yrow = ybase + (is_i4 ? 0u : (uint32_t)TF_ROW_BYTES);
+      L.ylut = is_i4 ? TF_LUT_FROM0 : TF_LUT_FROM1;
+      if (is_i4) { L.seq = 1; L.m_next = (1u << 0) | (1u << 16); tf_block_setup(L, c); } else { L.seq = 0; tf_y2_setup(L, c); }
+      return 1;
+    }
+    L.cx &= is_i4 ? 0x01000100u : 0u;
+    tf_mb_store<MULTI>(L, c, 0u, L.w & 0xffff0000u);
+  }
+}
+
+// The macroblock's last block has ended: store its results, move on.
+template <int MULTI>
+TK_FN void tf_mb_finish(TfLane& L, const TfCtx& c) {
+  const uint32_t nzy = (L.acc_hi << 16) | (L.acc_lo >> 16);
+  const uint32_t uv = L.acc_lo & 0xffffu;                      // U codes in bits 15-8, V in 7-0
+  const uint32_t nzuv = (uv >> 8) | ((uv & 0xffu) << 8);       // reference order: U bits 0-7, V bits 8-15
+  uint32_t w = L.w;
+  if ((L.acc_hi >> 16) & 3u) w |= MBW_HAS_Y2;                  // the Y2 block's code, shifted in first
+  tf_mb_store<MULTI>(L, c, nzy, (w & 0xffff0000u) | nzuv);
+}
+
+// Parks a lane that has nothing (more) to do: it keeps decoding in the dead state (probability 0 for ever, never
+// emits, never ends a block) and its reader only shifts in zeros.
+TK_FN void tf_lane_park(TfLane& L, const TfCtx& c) {
+  L.pend = TF_FINISHED; L.alive = 0; L.waiting = 0;
+  L.a = c.img_s + TF_DEAD; L.rowend = ~(tk_saddr)0;
+  tf_prime(L, c, TF_DEAD);
+  L.pf = 0.f;
+}
+
+// A lane without a stream: finished from the start (`any` = some valid address for its reader).
+TK_FN void tf_lane_idle(TfLane& L, const TfCtx& c, const uint8_t* any) {
+  fd_init(L.d, any, 0);
+  tf_lane_reset(L, c);
+  tf_lane_park(L, c);
+}
+
+// One boolean decode and the transition it selects; returns the transition entry. The caller has topped the window up
+// (fd_fill) within the last three decodes.
+TK_FN uint32_t tf_decode(TfLane& L, const TfCtx& c) {
+  // ---- what the NEXT decode needs, fetched for both outcomes of this one before its bit is known
+  uint32_t e00, e01, e10, e11;
+  tk_lds_v2_pinned(c.tab_s + TF_E_TAB(L.e0), e00, e01);
+  tk_lds_v2_pinned(c.tab_s + TF_E_TAB(L.e1), e10, e11);
+  const tk_saddr a0 = L.a + TF_E_DIST(L.e0), a1 = L.a + TF_E_DIST(L.e1);
+  const uint32_t p0 = tk_lds_u8_pinned(a0), p1 = tk_lds_u8_pinned(a1);
+  // ---- boolean decode
+  const int bit = fd_bit(L.d, L.pf, c.k);
+  // ---- transition
+  const uint32_t e = bit ? L.e1 : L.e0;
+  const tk_saddr a_emit = L.a;
+  L.a = bit ? a1 : a0;
+  L.pf = tf_u8_to_float(bit ? p1 : p0);
+  L.sink ^= p1;   // an unconditional use: without it the assembler folds the select into a load of p1 predicated on the
+                  // bit, which puts the shared-memory latency straight back on the dependent chain
+  L.e0 = bit ? e10 : e00;
+  L.e1 = bit ? e11 : e01;
+  L.acc += e;
+  if (e & TF_EMIT) {   // the sign has just been decoded: one token
+    c.tokens[L.tokoff++] = (L.acc & TF_ADD_MASK) | L.blktag | ((uint32_t)a_emit & 0x3c0u) | ((uint32_t)bit << 31);
+    L.acc = 0;
+  }
+  return e;
+}
+
+// ParseResiduals' bookkeeping at the end of a block (vp8_dec.c:517-609) with GetCoeffs' return value nz, then the next
+// block. Returns 1 when the macroblock's last block has ended instead (tf_mb_finish + tf_mb_next are due).
+// nz = position of the last decoded coefficient + 1 = the position the walk stands at: after an emit the address has
+// already moved to the next position; at an end-of-block decision it still stands at the position that was asked.
+TK_FN int tf_block_end(TfLane& L, const TfCtx& c) {
+  const uint32_t nz2 = 32u - (uint32_t)((L.rowend - (L.a & ~(tk_saddr)63)) >> 5);   // 2 * nz
+  const uint32_t code = (L.lut >> (nz2 < 8u ? nz2 : 8u)) & 3u;       // non-zero exactly when the block counts as non-empty
+  L.acc_hi = (L.acc_hi << 2) | (L.acc_lo >> 30);
+  L.acc_lo = (L.acc_lo << 2) | code;
+  L.cx = (L.cx & ~L.m) | (code ? L.m : 0u);
+  L.seq++;
+  if (TF_UNLIKELY(L.seq == 25)) return 1;
+  tf_block_setup(L, c);
+  return 0;
+}
+
+// ---- every lane executes every step; a lane whose block has ended does its bookkeeping on the spot while the others
+// wait. Returns 0 once the lane has finished (parked).
+template <int MULTI>
+TK_FN int tf_step_inline(TfLane& L, const TfCtx& c) {
+  if (MULTI) {
+    if (L.waiting) {
+      if (!tf_mb_next<MULTI>(L, c)) {
+        if (!L.waiting) tf_lane_park(L, c);
+        return L.alive;
+      }
+    }
+  }
+  const uint32_t e = tf_decode(L, c);
+  if (TF_UNLIKELY((e & TF_EOB) || L.a >= L.rowend)) {
+    if (tf_block_end(L, c)) {
+      tf_mb_finish<MULTI>(L, c);
+      if (!tf_mb_next<MULTI>(L, c)) {
+        if (!(MULTI && L.waiting)) tf_lane_park(L, c);
+        return L.alive;
+      }
+    }
+  }
+  return 1;
+}
+
+#endif  // LIBWEBP_B200_VP8_TOKENS_FP_H_

@@ -74,7 +74,7 @@ int WebPInitDecoderConfigInternal(WebPDecoderConfig* config, int version) {
 
 VP8StatusCode WebPDecode(const uint8_t* data, size_t data_size, WebPDecoderConfig* config) {
   WebPBatchItem item;
-  if (config == NULL) return VP8_STATUS_INVALID_PARAM;
+  if (config == NULL || data == NULL) return VP8_STATUS_INVALID_PARAM;   /* webp_dec.c:756; GetFeatures webp_dec.c:693-695 */
   item.data = data;
   item.data_size = data_size;
   item.config = config;

@@ -42,6 +42,7 @@ def lib():
         L.vp8o_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
         L.vp8o_dump.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(Dump)]
         L.vp8o_dump_free.argtypes = [C.POINTER(Dump)]
+        L.vp8o_count_decodes.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
@@ -67,6 +68,13 @@ def decode(data, csp=RGBA, flags=0, stride=None):
         out = np.zeros((h, stride), np.uint8)
         st = lib().vp8o_decode(data, len(data), csp, flags, out.ctypes.data, out.size, stride)
     return st, (out if st == 0 else None)
+
+
+def count_decodes(data):
+    """-> (status, first-partition decodes, [decodes of each token partition]): the lengths of the frame's dependent chains."""
+    out = (C.c_uint64 * 10)()
+    st = lib().vp8o_count_decodes(data, len(data), out)
+    return st, int(out[0]), [int(out[1 + p]) for p in range(int(out[9]))]
 
 
 def dump(data):

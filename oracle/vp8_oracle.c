@@ -21,6 +21,7 @@ typedef struct {
   uint64_t value;
   int bits;   // number of not-yet-consumed bits in `value`, minus 8
   int eof;
+  uint64_t decodes;   // boolean decodes so far (vp8o_count_decodes: the length of this stream's dependent chain)
 } BoolDec;
 
 static void bd_refill(BoolDec* d) {
@@ -43,6 +44,7 @@ static void bd_init(BoolDec* d, const uint8_t* start, size_t size) {
   d->value = 0;
   d->bits = -8;
   d->eof = 0;
+  d->decodes = 0;
   bd_refill(d);
 }
 
@@ -57,6 +59,7 @@ static int bd_bit(BoolDec* d, int prob) {   // bit_reader_inl_utils.h:107-136
   uint32_t split, top;
   int bit, shift;
   if (d->bits < 0) bd_refill(d);
+  ++d->decodes;
   split = (range * (uint32_t)prob) >> 8;
   top = (uint32_t)(d->value >> d->bits);
   if (top > split) {
@@ -1163,6 +1166,23 @@ int vp8o_dump(const uint8_t* data, size_t size, Vp8oDump* d) {
   memcpy(d->filtered, f.y, plane);
   frame_free(&f);
   return VP8O_OK;
+}
+
+// Boolean decodes per entropy-coded stream of the frame: out[0] = first partition (headers + intra modes),
+// out[1..8] = token partitions, out[9] = number of token partitions. bench.py turns these into "cycles per decode".
+int vp8o_count_decodes(const uint8_t* data, size_t size, uint64_t out[10]) {
+  Frame f;
+  Container c;
+  int p;
+  const int st = decode_frame(data, size, 0, 1, &f, &c);
+  memset(out, 0, 10 * sizeof(out[0]));
+  if (st == VP8O_OK) {
+    out[0] = f.br.decodes;
+    for (p = 0; p < f.num_parts && p < 8; ++p) out[1 + p] = f.parts[p].decodes;
+    out[9] = (uint64_t)f.num_parts;
+  }
+  frame_free(&f);
+  return st;
 }
 
 void vp8o_dump_free(Vp8oDump* d) {

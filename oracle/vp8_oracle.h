@@ -55,6 +55,9 @@ typedef struct {
 } Vp8oDump;
 
 int vp8o_dump(const uint8_t* data, size_t size, Vp8oDump* d);
+// Length of every dependent chain of the frame, in boolean decodes: out[0] first partition, out[1..8] token
+// partitions, out[9] their number.
+int vp8o_count_decodes(const uint8_t* data, size_t size, uint64_t out[10]);
 void vp8o_dump_free(Vp8oDump* d);
 
 #ifdef __cplusplus

@@ -18,6 +18,7 @@
 #include "vp8_pixel_core.h"
 #include "vp8_tokens_fsm.h"
 #include "vp8_tokens_lockstep.h"
+#include "vp8_tokens_fp.h"
 #include "vp8l_alpha_core.h"
 #include "vp8l_lossless_core.h"
 #include "vp8l_alpha_core.h"
@@ -26,6 +27,7 @@
 // variant bit 1: token parse with the row-at-a-time reference port (parse_token_row) instead of the lane FSM
 // variant bit 2: lane FSM with a lazy ring producer
 // variant bit 3: lockstep lane parser (vp8_tokens_lockstep.h), lanes advanced round-robin; with bit 4 its grouped event points
+// variant bit 6: the fp parser (vp8_tokens_fp.h): fp32 boolean decoder, token stream out, read back by recon_load_tokens
 static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags, uint8_t* out, size_t out_size,
                            int stride, int variant, uint8_t* unfiltered, int crop_x, int crop_y, int crop_w, int crop_h,
                            int scaled_w = 0, int scaled_h = 0);
@@ -140,7 +142,48 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
   const int rows = hdr.rows;   // macroblock rows that get decoded (all of them unless cropping)
 
   // K2: tokens
-  if (variant & 8) {   // lockstep parser: one lane per partition, one decode per lane per round
+  std::vector<uint32_t> tokens;
+  std::vector<MbTok> mbtok;
+  if (variant & 64) {   // fp parser: one lane per partition, one decode per lane per round, levels as a token stream
+    const int P = hdr.num_parts;
+    tokens.assign(nmb * TF_TOKENS_PER_MB, 0xffffffffu);
+    mbtok.assign(nmb, MbTok{ 0xffffffffu, 0xffffffffu });
+    std::vector<uint8_t> imgmem(TF_IMG_BYTES + 1024 + 128);
+    uint8_t* img = (uint8_t*)(((uintptr_t)imgmem.data() + 1023) & ~(uintptr_t)1023);
+    std::vector<uint64_t> tabmem((sizeof(TfTables) + 7) / 8);
+    TfTables* ttab = (TfTables*)tabmem.data();
+    tf_image_fill(img, &hdr, 0, 1);
+    tf_tables_fill(ttab, 0, 1);
+    std::vector<uint16_t> topctx((size_t)(P + 1) * mb_w, 0);
+    std::vector<int> progress(VP8B_MAX_PARTS, 0);
+    std::vector<TfLane> lanes(P);
+    std::vector<TfCtx> ctxs(P);
+    std::vector<int> live(P, 0);
+    for (int p = 0; p < P && p < rows; ++p) {
+      TfCtx& cc = ctxs[p];
+      cc.img_s = tk_saddr_of(img); cc.tab_s = tk_saddr_of(ttab);
+      cc.k.mant_mask = 0x007fffffu; cc.k.exp128 = 0x43000000u;
+      cc.topctx = topctx.data(); cc.progress = progress.data();
+      cc.mbinfo = mbinfo.data(); cc.mbtok = mbtok.data(); cc.tokens = tokens.data();
+      cc.mb_w = mb_w; cc.rows = rows; cc.P = P; cc.part = p; cc.use_skip = hdr.use_skip; cc.ctx_stride = mb_w;
+      tf_lane_init(lanes[p], cc, frame, &hdr);
+      live[p] = 1;
+    }
+    if (P == 1 && live[0] && !tf_mb_next<0>(lanes[0], ctxs[0])) { tf_lane_park(lanes[0], ctxs[0]); live[0] = 0; }
+    for (bool any = true; any;) {
+      any = false;
+      for (int p = P - 1; p >= 0; --p) {   // reverse order: exercises the wait-for-progress path
+        if (!live[p]) continue;
+        any = true;
+        fd_fill(lanes[p].d);
+        for (int k = 0; k < 4; ++k) {   // parked lanes keep stepping, harmlessly, like on the device
+          if (P > 1) tf_step_inline<1>(lanes[p], ctxs[p]); else tf_step_inline<0>(lanes[p], ctxs[p]);
+        }
+        live[p] = lanes[p].alive;
+      }
+    }
+    for (int p = 0; p < P && p < rows; ++p) if (lanes[p].status != VP8B_OK) hdr.status = lanes[p].status;
+  } else if (variant & 8) {   // lockstep parser: one lane per partition, one decode per lane per round
     const int P = hdr.num_parts;
     std::vector<uint8_t> imgmem(TL_IMG_BYTES + 16 + 128);   // the look-ahead loads run up to 63 bytes past the rows
     uint8_t* img16 = (uint8_t*)(((uintptr_t)imgmem.data() + 15) & ~(uintptr_t)15);
@@ -259,7 +302,11 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
         if (mx < 0 || mx >= mb_w) continue;
         const size_t idx = (size_t)my * mb_w + mx;
         const int16_t* dq6 = hdr.dq[(mbinfo[4 * idx + 3] >> MBW_SEG_SHIFT) & 3];
-        recon_macroblock(ws, cx, mx, my, mb_w, mbinfo.data() + 4 * idx, coeffs.data() + idx * VP8B_COEFFS_PER_MB, dq6, yp, up, vp);
+        if (variant & 64) {
+          recon_macroblock(ws, cx, mx, my, mb_w, mbinfo.data() + 4 * idx, nullptr, dq6, yp, up, vp, tokens.data() + mbtok[idx].first, mbtok[idx].count);
+        } else {
+          recon_macroblock(ws, cx, mx, my, mb_w, mbinfo.data() + 4 * idx, coeffs.data() + idx * VP8B_COEFFS_PER_MB, dq6, yp, up, vp);
+        }
       }
     }
   }

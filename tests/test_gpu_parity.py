@@ -629,3 +629,171 @@ def test_damage_campaign_prefix(ref):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_gpu.py"), "--seconds", "8", "--batch", "2048", "--seed", "1"],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-1000:])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Round 2: BASELINE configs at their stated shapes, the asynchronous pair, in-library sharding, hygiene.
+
+def _compare_all(W, ref, datas, csp, sts, outs, distinct=None):
+    """Every image of a batch against the compiled reference; `distinct` = the batch tiles that many images."""
+    cache = {}
+    for i, data in enumerate(datas):
+        key = i % distinct if distinct else i
+        if key not in cache:
+            cache[key] = ref.decode(data, csp, 0)
+        s_ref, want = cache[key]
+        assert sts[i] == s_ref, (i, sts[i], s_ref)
+        if s_ref == 0:
+            assert np.array_equal(outs[i].reshape(-1), want.reshape(-1)), (i, csp)
+
+
+def test_config3_shape_8_partitions_normal_filter_yuv_and_rgba(W, ref):
+    """BASELINE config 3: 1080p, 8 token partitions, 4 segments, normal loop filter, decoded to MODE_YUV and RGBA as one
+    batch of 64 (16 distinct images tiled, every item compared)."""
+    corpus = ref.encode_corpus(16, 1920, 1080, ref.cfg_normal_8part(), seed0=3100)
+    datas = [corpus[i % 16] for i in range(64)]
+    for csp in (W.MODE_YUV, W.MODE_RGBA):
+        sts, outs = W.decode_batch(datas, csp)
+        _compare_all(W, ref, datas, csp, sts, outs, distinct=16)
+
+
+def test_config4_shape_4096_thumbnails_premultiplied(W, ref):
+    """BASELINE config 4: 4096 thumbnails of 256x256 q80, fancy upsampling to premultiplied rgbA (64 distinct, all compared)."""
+    corpus = ref.encode_corpus(64, 256, 256, ref.cfg_default(), seed0=4100)
+    datas = [corpus[i % 64] for i in range(4096)]
+    sts, outs = W.decode_batch(datas, W.MODE_rgbA)
+    _compare_all(W, ref, datas, W.MODE_rgbA, sts, outs, distinct=64)
+
+
+def test_config5_shape_4096x4096_alpha(W, ref):
+    """BASELINE config 5 at its stated shape: two 4096x4096 q90 images with a gradient-filtered ALPH chunk -> RGBA."""
+    cfg = ref.cfg_alpha_q90()
+    datas = ref.encode_corpus(2, 4096, 4096, cfg, seed0=5100, alpha=True)
+    assert all(W.WebPGetFeatures(d)[1]["has_alpha"] for d in datas)
+    sts, outs = W.decode_batch(datas, W.MODE_RGBA)
+    _compare_all(W, ref, datas, W.MODE_RGBA, sts, outs)
+
+
+def test_submit_wait_pipeline(W, ref, manifest):
+    """WebPBatchSubmit / WebPBatchWait with two batches in flight on one device: same bytes as the blocking call, in any
+    interleaving, also when one of the batches holds damaged files."""
+    corpus = ref.encode_corpus(6, 640, 360, ref.cfg_simple_1part(), seed0=6100)
+    d = manifest[0]["data"]
+    a = [corpus[i % 6] for i in range(48)]
+    b = [corpus[(i + 3) % 6] for i in range(40)] + [d[:len(d) // 2], b"junkjunkjunkjunk"]
+    want = {id(x): W.decode_batch(x, W.MODE_RGBA) for x in (a, b)}
+    slots = [W.Batch(a, W.MODE_RGBA, device=0), W.Batch(b, W.MODE_RGBA, device=0)]
+    try:
+        for rounds in range(3):
+            for s in slots:
+                s.submit()
+            for s, datas in zip(slots, (a, b)):
+                s.wait()
+                sts, outs = want[id(datas)]
+                assert s.statuses() == sts
+                for i in range(s.n):
+                    if sts[i] == 0:
+                        assert np.array_equal(s.host_output(i), outs[i]), (rounds, i)
+                s._out_arr[:] = 0
+    finally:
+        for s in slots:
+            s.close()
+
+
+def test_two_devices_in_one_process(W, ref):
+    """WebPBatchOptions::devices: one call shards the items i % G over G devices (host thread per device, no collective);
+    every image compared. Also plain per-device calls from one process (the per-device kernel attributes)."""
+    if W.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    corpus = ref.encode_corpus(8, 1920, 1080, ref.cfg_simple_1part(), seed0=7100)
+    datas = [corpus[i % 8] for i in range(1300)]   # enough streams per device for the lockstep parser (> 48 KB of shared memory)
+    b = W.Batch(datas, W.MODE_RGBA, devices=[0, 1])
+    try:
+        assert b.decode_oneshot() == 0
+        sts = b.statuses()
+        outs = [b.host_output(i).copy() for i in range(b.n)]
+    finally:
+        b.close()
+    _compare_all(W, ref, datas, W.MODE_RGBA, sts, outs, distinct=8)
+    for dev in (1, 0):
+        sts, outs = W.decode_batch(datas[:1200], W.MODE_RGBA, device=dev)
+        _compare_all(W, ref, datas[:1200], W.MODE_RGBA, sts, outs, distinct=8)
+    # resident form, sharded: device pointers of item i live on devices[i % G]
+    r = W.Batch(datas[:64], W.MODE_RGBA, devices=[0, 1], output=W.WEBP_BATCH_DEVICE)
+    try:
+        assert r.create() == 0 and r.decode() == 0
+        assert [r.device_output(i).device for i in range(4)] == [0, 1, 0, 1]
+    finally:
+        r.close()
+
+
+def test_separately_allocated_buffers(W, ref, manifest):
+    """One page-locked allocation per file and per output (merged copies used to span allocations), and plain
+    pageable buffers."""
+    datas = [e["data"] for e in manifest]
+    want = [ref.decode(d, ref.MODE_RGBA, 0) for d in datas]
+    L = W.lib()
+    n = len(datas)
+    items = (W.WebPBatchItem * n)()
+    cfgs = (W.WebPDecoderConfig * n)()
+    ins, outs = [], []
+    try:
+        for i, d in enumerate(datas):
+            ib = W.HostBuffer(len(d)); ib.array[:len(d)] = np.frombuffer(d, np.uint8); ins.append(ib)
+            _, f = W.WebPGetFeatures(d)
+            ob = W.HostBuffer(f["width"] * f["height"] * 4); outs.append(ob)
+            L.WebPInitDecoderConfigInternal(C.byref(cfgs[i]), W.WEBP_DECODER_ABI_VERSION)
+            cfgs[i].output.colorspace = W.MODE_RGBA
+            W._attach_external(cfgs[i], W.MODE_RGBA, f["width"], f["height"], ob.ptr, f["width"] * 4)
+            items[i].data = ib.ptr; items[i].data_size = len(d); items[i].config = C.pointer(cfgs[i])
+        assert L.WebPDecodeBatch(items, n, None) == 0, W.last_error()
+        for i in range(n):
+            _, f = W.WebPGetFeatures(datas[i])
+            assert items[i].status == want[i][0] == 0
+            assert np.array_equal(outs[i].array[:f["width"] * f["height"] * 4].reshape(f["height"], -1), want[i][1]), i
+    finally:
+        for b in ins + outs:
+            b.free()
+    sts, got = W.decode_batch(datas, W.MODE_RGBA, pinned=False)
+    assert all(s == 0 and np.array_equal(g, w[1]) for s, g, w in zip(sts, got, want))
+
+
+def test_header_only_giant_images_fail_alone(W, port, manifest):
+    """Files of a few hundred bytes that declare 16383x16383 pixels: each gets the reference's status and the
+    real images beside them decode."""
+    good = [e["data"] for e in manifest[:6]]
+    d = bytearray(next(m for m in manifest if m["file"] == "simple_1part_320x200.webp")["data"][:400])
+    i = bytes(d).find(b"VP8 ")
+    # 14-bit width / height fields of the frame header (vp8_dec.c:107-160): bytes 6..9 after the 3-byte frame tag
+    d[i + 8 + 6] = 0xff; d[i + 8 + 7] = 0x3f; d[i + 8 + 8] = 0xff; d[i + 8 + 9] = 0x3f
+    tag = int.from_bytes(d[i + 8:i + 11], "little")
+    tag = (tag & 0x1f) | (100 << 5)   # a first partition that fits the 400 bytes, so that the file reaches the device planning
+    d[i + 8:i + 11] = tag.to_bytes(3, "little")
+    giant = bytes(d)
+    st, f = W.WebPGetFeatures(giant)
+    assert st == 0 and (f["width"], f["height"]) == (16383, 16383)
+    datas = []
+    for g in good:
+        datas += [g, giant]
+    # 90 giants declare 96 GB of RGBA between them: more than half the device, so the call runs in groups
+    sts, outs = W.decode_batch(datas * 15, W.MODE_RGBA)
+    for k, data in enumerate(datas * 15):
+        if data is giant:
+            assert sts[k] != 0
+        else:
+            want_st, want = port.decode(data, port.RGBA, 0)
+            assert sts[k] == want_st == 0 and np.array_equal(outs[k], want), k
+
+
+def test_cache_limit_and_trim(W, manifest):
+    datas = [e["data"] for e in manifest]
+    prev = W.set_cache_limit(1 << 30, 0)
+    try:
+        sts, _ = W.decode_batch(datas, W.MODE_RGBA, device=0)
+        assert all(s == 0 for s in sts)
+        assert W.trim_cache(0) > 0
+        assert W.trim_cache(0) == 0
+        sts, _ = W.decode_batch(datas, W.MODE_RGBA, device=0)   # works again after a trim
+        assert all(s == 0 for s in sts)
+    finally:
+        W.set_cache_limit(prev, 0)
