@@ -329,17 +329,24 @@ def measure(args, workload, rank, world, device, steps, warmup, e2e_steps, cpu_s
         barrier()
         t1 = time.perf_counter()
         inflight = []
+        host_submit_ms, host_wait_ms = [], []
         for k in range(e2e_steps):
             sl = slots[k % 2]
             if len(inflight) == 2:
+                tw = time.perf_counter()
                 if inflight.pop(0).wait() != 0:
                     raise SystemExit("WebPBatchWait failed in the timed region")
+                host_wait_ms.append(round((time.perf_counter() - tw) * 1e3, 1))
+            tw = time.perf_counter()
             if sl.submit() != 0:
                 raise SystemExit(f"WebPBatchSubmit failed in the timed region: {W.last_error()}")
+            host_submit_ms.append(round((time.perf_counter() - tw) * 1e3, 1))
             inflight.append(sl)
         for sl in inflight:
+            tw = time.perf_counter()
             if sl.wait() != 0:
                 raise SystemExit("WebPBatchWait failed in the timed region")
+            host_wait_ms.append(round((time.perf_counter() - tw) * 1e3, 1))
         barrier()
         e2e_ms_step = reduce_max((time.perf_counter() - t1) * 1e3 / e2e_steps)
         # spot-check the bytes that came back against the reference (not timed)
@@ -351,6 +358,7 @@ def measure(args, workload, rank, world, device, steps, warmup, e2e_steps, cpu_s
         e2e = {"value": round(e2e_mpix * world / (e2e_ms_step * 1e-3), 1), "unit": UNIT, "h2d_bytes_per_step": slots[0].h2d_bytes,
                "d2h_bytes_per_step": slots[0].d2h_bytes, "ms_per_step": round(e2e_ms_step, 3), "steps": e2e_steps,
                "batch_per_gpu": e2e_n, "bit_exact_spot_check": ok, "blocking_ms": round(blocking_ms, 3),
+               "host_submit_ms": host_submit_ms[:8], "host_wait_ms": host_wait_ms[:8],
                "d2h_floor_ms": None,
                "api": "WebPBatchSubmit/WebPBatchWait, two batches in flight, host buffers in and out (pinned); "
                       "blocking_ms = one WebPDecodeBatch call"}

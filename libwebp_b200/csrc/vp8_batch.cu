@@ -231,7 +231,7 @@ static void* pinned_alloc(DeviceCtx* c, size_t bytes, size_t* cap) {
     return p;
   }
   void* p = nullptr;
-  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { set_error("cudaHostAlloc", cudaGetLastError()); return nullptr; }
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { set_error("cudaHostAlloc", cudaGetLastError()); return nullptr; }
   *cap = bytes;
   return p;
 }
@@ -908,7 +908,7 @@ static bool batch_alpha(WebPBatch* b) {
   vp8k_alpha_header(s, arena, (const ImgDesc*)b->d_imgs.p, (const int*)b->d_aimgs.p, (const AlphaPlan*)b->d_aplans.p,
                     (AlphaHdr*)b->d_ahdrs.p, na);
   if (!b->alpha_planned) {
-    CU_TRY(cudaMemcpyAsync(b->ahdrs, b->d_ahdrs.p, sizeof(AlphaHdr) * na, cudaMemcpyDeviceToHost, s), "D2H alpha headers");
+    vp8k_copy_to_host(s, b->d_ahdrs.p, b->ahdrs, sizeof(AlphaHdr) * na);   // page-locked + mapped: no copy engine (see k_collect_status)
     CU_TRY(cudaStreamSynchronize(s), "alpha header pass");
     size_t work2 = 0, planes = 0;
     std::vector<size_t> tab(na, 0), grp(na, 0), cod(na, 0), smo(na, 0);
@@ -945,7 +945,7 @@ static bool batch_alpha(WebPBatch* b) {
                     (AlphaHdr*)b->d_ahdrs.p, (uint8_t*)b->d_alpha.p, na);
   if (b->any_lossless) vp8k_lossless_finish(s, (const ImgDesc*)b->d_imgs.p, (const int*)b->d_aimgs.p, (const AlphaPlan*)b->d_aplans.p,
                                             (const AlphaHdr*)b->d_ahdrs.p, (uint8_t*)b->d_out.p, na);
-  CU_TRY(cudaMemcpyAsync(b->ahdrs, b->d_ahdrs.p, sizeof(AlphaHdr) * na, cudaMemcpyDeviceToHost, s), "D2H alpha status");
+  vp8k_copy_to_host(s, b->d_ahdrs.p, b->ahdrs, sizeof(AlphaHdr) * na);
   return true;
 }
 
@@ -1124,8 +1124,12 @@ static bool batch_enqueue(WebPBatch* b, bool download) {
   b->launches = launches;
   CU_TRY(cudaEventRecord(ctx->scratch_free, s), "cudaEventRecord");
   ctx->scratch_used = true;
-  // per-image status words: FrameHdr::status is the first field
-  CU_TRY(cudaMemcpy2DAsync(b->statuses, sizeof(int), hdrs, sizeof(FrameHdr), sizeof(int), m, cudaMemcpyDeviceToHost, s), "D2H status");
+  // per-image status words, written into page-locked host memory by the device (see k_collect_status)
+  {
+    int* dev_view = nullptr;
+    CU_TRY(cudaHostGetDevicePointer((void**)&dev_view, b->statuses, 0), "cudaHostGetDevicePointer");
+    vp8k_collect_status(s, hdrs, dev_view, m);
+  }
   const int e_status = ev_mark(b, s); if (e_status < 0) return false;
   (void)e_status;   // the last event of the pool on the compute stream: batch_finish waits for it
   if (download) {

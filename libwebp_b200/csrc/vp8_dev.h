@@ -18,7 +18,8 @@
 #include <stdint.h>
 
 #define VP8B_COEFFS_PER_MB 400
-#define VP8B_TOKENS_PER_MB 384   // token stream: at most 16 x 15 + 16 (or 16 x 16) luma + 128 chroma non-zero levels per macroblock
+#define VP8B_TOKENS_PER_MB 388   // token stream: at most 16 x 15 + 16 (or 16 x 16) luma + 128 chroma = 384 non-zero levels per macroblock,
+                                 // + 4 of slack (a lane whose block has ended writes up to three stray tokens past its last one, vp8_tokens_fp.h)
 #define VP8B_MAX_PARTS 8
 
 // VP8StatusCode values used on the device (include/webp/decode.h).

@@ -387,7 +387,7 @@ __host__ __device__ static inline TfLayout tf_layout(int P, int ipb, int ctx_str
 __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_fp(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
                                                             FrameHdr* hdrs, uint32_t* mbinfo, uint32_t* tokens, MbTok* mbtok,
                                                             const int* __restrict__ ids, int count, int P, int ipb, int lpw,
-                                                            int cw, int ctx_stride) {
+                                                            int cw, int ctx_stride, int flat) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tk_saddr_of(smem_raw) & 1023u)) & 1023u);   // the rows' addresses carry the position in bits 6-9
   const TfLayout lay = tf_layout(P, ipb, ctx_stride);
@@ -416,8 +416,8 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_fp(const uint8_t* _
   TfCtx c;
   c.img_s = tk_saddr_of(smem + lay.images + (size_t)(have ? slot : 0) * TF_IMG_BYTES);
   c.tab_s = tk_saddr_of(tables);
-  c.k.mant_mask = 0x007fffffu; c.k.exp128 = 0x43000000u;
-  asm volatile("" : "+r"(c.img_s), "+r"(c.tab_s), "+r"(c.k.mant_mask), "+r"(c.k.exp128));   // plain registers: no per-step cvta, one LOP3 in fd_bit
+  c.k.mant_mask = 0x007fffffu; c.k.exp46 = TF_EXP46;
+  asm volatile("" : "+r"(c.img_s), "+r"(c.tab_s), "+r"(c.k.mant_mask), "+r"(c.k.exp46));   // plain registers: no per-step cvta, one LOP3 in fd_bit
   c.topctx = reinterpret_cast<uint16_t*>(smem + lay.ctx) + (size_t)(have ? slot : 0) * (P + 1) * ctx_stride;
   c.progress = progress + (have ? slot : 0) * VP8B_MAX_PARTS;
   c.mbinfo = mbinfo + 4 * (size_t)im.mb_base;
@@ -435,20 +435,21 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_fp(const uint8_t* _
   // The loop counter starts from a per-thread value (always 0) so that the compiler does not fence the body with
   // WARPSYNC.ALL; the vote costs as much as half a step and is taken every 32 steps.
   const int r0 = (int)(L.sink >> 31);
-  if (P > 1) {
+  if (flat) {
+    // Straight-line groups of four decodes with one event point (vp8_tokens_fp.h:tf_group_flat): the default.
+    if (P > 1) {
+      while (__any_sync(0xffffffffu, L.alive)) { for (int r = r0; r < 8; ++r) tf_group_flat<1>(L, c); }
+    } else {
+      while (__any_sync(0xffffffffu, L.alive)) { for (int r = r0; r < 8; ++r) tf_group_flat<0>(L, c); }
+    }
+  } else if (P > 1) {
     while (__any_sync(0xffffffffu, L.alive)) {
-      for (int r = r0; r < 8; ++r) {
-        fd_fill(L.d);
-        tf_step_inline<1>(L, c); tf_step_inline<1>(L, c); tf_step_inline<1>(L, c); tf_step_inline<1>(L, c);
-      }
+      for (int r = r0; r < 8; ++r) tf_group_inline<1>(L, c);
     }
   } else {
     if (have && !tf_mb_next<0>(L, c)) tf_lane_park(L, c);
     while (__any_sync(0xffffffffu, L.alive)) {
-      for (int r = r0; r < 8; ++r) {
-        fd_fill(L.d);
-        tf_step_inline<0>(L, c); tf_step_inline<0>(L, c); tf_step_inline<0>(L, c); tf_step_inline<0>(L, c);
-      }
+      for (int r = r0; r < 8; ++r) tf_group_inline<0>(L, c);
     }
   }
   if (have && L.status != VP8B_OK) h->status = L.status;
@@ -504,6 +505,14 @@ __global__ void __launch_bounds__(32 * RECON_WARPS) k_reconstruct(const ImgDesc*
       const int16_t* dq6 = dqs + 6 * ((mbi[4 * idx + 3] >> MBW_SEG_SHIFT) & 3);
       if (tk != nullptr) {
         const MbTok t = mt[idx];
+        // the macroblock to the right is this warp's next one in this row, and its tokens follow these in the partition's
+        // stream: start them (and its MbInfo / MbTok) on their way from HBM now, two barriers ahead of their use
+        {
+          const int lane = threadIdx.x & 31;
+          const void* pf = lane < 4 ? (const void*)(tk + t.first + t.count + 32 * lane)
+                                    : lane == 4 ? (const void*)(mbi + 4 * (idx + 1)) : (const void*)(mt + idx + 1);
+          if (lane < 6 && mx + 1 < mb_w) asm volatile("prefetch.global.L2 [%0];" :: "l"(pf));
+        }
         recon_macroblock(ws, cx, mx, my, mb_w, mbi + 4 * idx, nullptr, dq6, yp, up, vp, tk + t.first, t.count);
       } else {
         recon_macroblock(ws, cx, mx, my, mb_w, mbi + 4 * idx, cf + idx * VP8B_COEFFS_PER_MB, dq6, yp, up, vp);
@@ -641,6 +650,19 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit_scaled(const ImgDesc* __r
   yp += (size_t)im.crop_y * (16 * im.mb_w) + im.crop_x;
   const uint8_t* alpha = (im.alpha_plane != VP8B_NO_ALPHA) ? alpha_arena + im.alpha_plane + (size_t)im.crop_y * im.width + im.crop_x : nullptr;
   emit_scaled_column(im, yp, up, vp, alpha, out + im.out_off, chunk * EMIT_THREADS + threadIdx.x);
+}
+
+// Per-image status words -> page-locked host memory, written by the device itself. (A cudaMemcpyAsync here would queue
+// behind the pixel downloads on the device-to-host copy engine and hold the COMPUTE stream up until they are through:
+// that is what kept batch k+1 from starting under batch k's download.)
+__global__ void __launch_bounds__(256) k_collect_status(const FrameHdr* __restrict__ hdrs, int* host_statuses, int count) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < count) host_statuses[k] = hdrs[k].status;
+}
+
+// Small device -> mapped host copies of the same kind (the ALPH headers the host sizes its work areas from).
+__global__ void __launch_bounds__(256) k_copy_to_host(const uint8_t* __restrict__ src, uint8_t* host_dst, size_t bytes) {
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < bytes; k += (size_t)gridDim.x * blockDim.x) host_dst[k] = src[k];
 }
 
 // =========================================================================================================
@@ -783,7 +805,15 @@ static void launch_tokens_fp(cudaStream_t s, const uint8_t* arena, const ImgDesc
   while (ipb > 1 && tf_layout(P, ipb, max_mb_w).total > (uint32_t)VP8K_MAX_DYN_SMEM - 1024u) --ipb;
   const TfLayout lay = tf_layout(P, ipb, max_mb_w);
   const int blocks = (count + ipb - 1) / ipb;
-  k_parse_tokens_fp<<<blocks, 32 * cw, lay.total, s>>>(arena, imgs, hdrs, mbinfo, tokens, mbtok, ids, count, P, ipb, lpw, cw, max_mb_w);
+  // How the lanes are run (vp8_tokens_fp.h): a branch per decode with the block ends handled on the spot while a warp has
+  // few lanes, straight-line groups of four decodes with one event point when it has many (the event point's cost is
+  // shared by all the lanes that have a block end pending, and lanes that sit out the rest of a group cost nothing extra).
+  // Measured per 4096 full-HD images (profiles/r02g): 1 partition (7 lanes per warp) 267 / 335 ms, 8 partitions (28 lanes)
+  // 163 / 82 ms. WEBP_B200_TOKEN_GROUPED=0|1 forces one.
+  const char* eg = getenv("WEBP_B200_TOKEN_GROUPED");
+  const int lanes_per_warp = (ipb * P + cw - 1) / cw;
+  const int flat = eg != NULL ? (atoi(eg) != 0) : (lanes_per_warp >= 16);
+  k_parse_tokens_fp<<<blocks, 32 * cw, lay.total, s>>>(arena, imgs, hdrs, mbinfo, tokens, mbtok, ids, count, P, ipb, lpw, cw, max_mb_w, flat);
 }
 
 // Which token parser a wave takes: 1 = the fp parser (token stream out), 0 = one of the older mappings (dense level plane),
@@ -855,6 +885,15 @@ extern "C" void vp8k_reconstruct(cudaStream_t s, const ImgDesc* imgs, const Fram
 extern "C" void vp8k_loop_filter(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint32_t* mbinfo, uint8_t* yuv,
                                  int first, int count, int max_mb_h, int row_begin, int row_end, const int8_t* dither_plane) {
   k_loop_filter<<<count, 32 * FILTER_WARPS, (size_t)max_mb_h * 4 + 16, s>>>(imgs, hdrs, mbinfo, yuv, first, row_begin, row_end, dither_plane);
+}
+
+extern "C" void vp8k_collect_status(cudaStream_t s, const FrameHdr* hdrs, int* host_statuses, int count) {
+  k_collect_status<<<(count + 255) / 256, 256, 0, s>>>(hdrs, host_statuses, count);
+}
+
+extern "C" void vp8k_copy_to_host(cudaStream_t s, const void* src, void* host_dst, size_t bytes) {
+  const size_t blocks = (bytes + 255) / 256;
+  k_copy_to_host<<<(unsigned)(blocks < 1024 ? (blocks ? blocks : 1) : 1024), 256, 0, s>>>((const uint8_t*)src, (uint8_t*)host_dst, bytes);
 }
 
 extern "C" void vp8k_dither_plan(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, uint32_t* mbinfo, int8_t* dither_plane,

@@ -42,6 +42,9 @@ void vp8k_parse_tokens_stream(cudaStream_t s, const uint8_t* arena, const ImgDes
                               uint32_t* tokens, void* mbtok, const int* ids, int count, int P, int max_mb_w);
 void vp8k_loop_filter(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint32_t* mbinfo, uint8_t* yuv,
                       int first, int count, int max_mb_h, int row_begin, int row_end, const int8_t* dither_plane);
+// FrameHdr::status of images [0, count) into mapped page-locked host memory (no copy engine involved).
+void vp8k_collect_status(cudaStream_t s, const FrameHdr* hdrs, int* host_statuses, int count);
+void vp8k_copy_to_host(cudaStream_t s, const void* src, void* host_dst, size_t bytes);
 // options.dithering_strength: after the token parse of the whole image, before the loop filter. dither_plane = 128 bytes
 // per macroblock of the wave (NULL to vp8k_loop_filter: no image of the wave asked for dithering).
 void vp8k_dither_plan(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, uint32_t* mbinfo, int8_t* dither_plane,

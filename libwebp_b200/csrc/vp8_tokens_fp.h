@@ -9,12 +9,15 @@
 //    decoder here keeps the range as two floats and gets the split from one FFMA.RZ and the renormalisation shift
 //    from the exponent field (bit-exact: every quantity is an integer below 2^24; 3 * 10^9 random decodes against
 //    the integer form, zero differences):
-//        Rs = (range-1)/256, Rp = (range-1) + 2^23, pf = float(prob)
-//        m  = fma.rz(Rs, pf, 2^23)          = 2^23 + split                 (rz truncates: floor)
-//        s1 = bits(m) * 2^24 + 2^24         = (split + 1) << 24            (the 0x4B exponent byte falls off the top)
-//        bit = V >= s1
-//        f  = bit ? Rp - m : m - (2^23-1)   = new range as a float         (range-1-split, or split+1)
-//        shift = 134 - (bits(f) >> 23);  new range = mantissa of f under exponent 2^7
+//        everything is kept scaled by S = 2^-102, so that the exponent field of the new range IS the shift count:
+//        Ra = (range-1) * 2^39, Rp = S * ((range-1) + 2^23), pd = the probability byte read as a DENORMAL float (p * 2^-149:
+//        no integer-to-float conversion at all; FFMA takes denormals at full speed)
+//        m  = fma.rz(Ra, pd, S * 2^23)      = S * (2^23 + split)           (rz truncates: floor; 2^39 * 2^-149 = S / 256)
+//        s1 = bits(m) * 2^24 + 2^24         = (split + 1) << 24            (the exponent byte falls off the top)
+//        bit = V >= s1;  V = min(V, V - s1) (the subtraction wraps exactly when the bit is 0)
+//        f  = bit ? Rp - m : m - S*(2^23-1) = S * new range                (range-1-split, or split+1)
+//        k  = bits(f) >> 23 = 32 - shift:   V:vlo = (V:vlo) >> k as a clamped funnel shift, no subtraction
+//        new Ra = (mantissa of f under exponent 2^46) - 2^39, new Rp = fma(that, 2^-141, S * (2^23-1))
 //  * A step spends its integer-pipe slots on selects, so the rest is moved to the FMA pipe or dropped:
 //      - the magnitude is not assembled per step: `acc += entry` (one IMAD.IADD) adds the whole transition entry, whose
 //        fields are laid out so that the junk of the low fields never carries into the addend field; the magnitude
@@ -152,33 +155,45 @@ TK_FN void tf_image_fill(uint8_t* dst, const FrameHdr* h, int tid, int nthreads)
 // ---- fp32 boolean decoder (see the file header). The window, its refill and the end-of-stream rule are BoolDec's.
 #if defined(__CUDACC__) && !defined(VP8_EMU)
 TK_FN float tf_fma_rz(float a, float b, float c) { return __fmaf_rz(a, b, c); }
+TK_FN float tf_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 TK_FN float tf_as_float(uint32_t u) { return __uint_as_float(u); }
 TK_FN uint32_t tf_as_uint(float f) { return __float_as_uint(f); }
 // (x & m) | o with the two constants in registers: ONE LOP3 (with immediates the assembler needs two)
 TK_FN uint32_t tf_and_or(uint32_t x, uint32_t m, uint32_t o) { uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(x), "r"(m), "r"(o)); return r; }
-TK_FN float tf_u8_to_float(uint32_t p) { return __uint_as_float(0x4b000000u | p) - 8388608.0f; }
+TK_FN uint32_t tf_mad(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+TK_FN uint32_t tf_umin(uint32_t a, uint32_t b) { return min(a, b); }
+TK_FN uint32_t tf_shr_pair(uint32_t hi, uint32_t lo, uint32_t n) { return __funnelshift_rc(lo, hi, n); }   // low word of (hi:lo) >> min(n, 32)
 #else
 #include <math.h>
-TK_FN float tf_fma_rz(float a, float b, float c) {   // a*b + c is exact in double here (integers below 2^24 and their 1/256ths)
+TK_FN float tf_fma_rz(float a, float b, float c) {   // a*b + c is exact in double here (at most 32 significant bits)
   const double d = (double)a * (double)b + (double)c;
   float f = (float)d;
   if ((double)f > d) f = nextafterf(f, 0.0f);
   return f;
 }
+TK_FN float tf_fma(float a, float b, float c) { return (float)((double)a * (double)b + (double)c); }
 TK_FN float tf_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 TK_FN uint32_t tf_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 TK_FN uint32_t tf_and_or(uint32_t x, uint32_t m, uint32_t o) { return (x & m) | o; }
-TK_FN float tf_u8_to_float(uint32_t p) { return (float)p; }
+TK_FN uint32_t tf_mad(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
+TK_FN uint32_t tf_umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
+TK_FN uint32_t tf_shr_pair(uint32_t hi, uint32_t lo, uint32_t n) { return n >= 32 ? hi : n == 0 ? lo : ((hi << (32 - n)) | (lo >> n)); }
 #endif
+
+#define TF_S_2P23 0x1p-79f          // S * 2^23
+#define TF_S_2P23M1 0x1.fffffcp-80f // S * (2^23 - 1)
+#define TF_2P39 0x1p39f
+#define TF_EXP46 0x56800000u        // exponent field of 2^46
+#define TF_2PM141_BITS 0x00000100u  // 2^-141 (a denormal)
 
 struct FpDec {
   const uint32_t* wp;    // word after `nxt`
   const uint32_t* wend;  // first word wholly past the stream: from there on zeros are shifted in
   const uint32_t* wbase; // stream bits moved into the window so far = 32 * (wp - wbase) - bias8
   uint32_t V, vlo, nxt;  // 64-bit left-aligned window V:vlo, nxt = the next raw (little-endian) word
-  int nbits;             // valid bits in V:vlo
-  float Rs, Rp;          // (range - 1) / 256 and (range - 1) + 2^23
-  int last_shift;        // renormalisation shift of the most recent decode
+  int nb;                // valid bits in V:vlo, plus 32 for every decode since the last fd_fill (a step adds k = 32 - shift)
+  int nb_prev;           // nb before the most recent decode
+  float Ra, Rp;          // (range - 1) * 2^39 and S * ((range - 1) + 2^23)
   int bias8;
   int64_t limit;         // 8*size - 8: a decode starting beyond this bit position reads past the end
 };
@@ -186,48 +201,77 @@ struct FpDec {
 TK_FN void fd_init(FpDec& d, const uint8_t* start, uint32_t size) {
   BoolDec b;
   bd_init(b, start, size);
-  d.wp = b.wp; d.wend = b.wend; d.wbase = b.wbase; d.V = b.V; d.vlo = b.vlo; d.nxt = b.nxt; d.nbits = b.nbits;
-  d.Rs = 254.0f / 256.0f; d.Rp = 254.0f + 8388608.0f;
-  d.last_shift = 0; d.bias8 = b.bias8; d.limit = b.limit;
+  d.wp = b.wp; d.wend = b.wend; d.wbase = b.wbase; d.V = b.V; d.vlo = b.vlo; d.nxt = b.nxt; d.nb = b.nbits; d.nb_prev = b.nbits;
+  d.Ra = 254.0f * TF_2P39; d.Rp = tf_fma(254.0f * TF_2P39, tf_as_float(TF_2PM141_BITS), TF_S_2P23);
+  d.bias8 = b.bias8; d.limit = b.limit;
 }
 
-TK_FN int fd_eof(const FpDec& d) {   // bd_eof
+// True when the reference's reader would have raised eof_ (bd_eof): the most recent decode STARTED with fewer than 8
+// real bits left. Only valid right after a decode that followed an fd_fill by at most four steps; `since` = decodes
+// since that fill (nb carries 32 extra per decode).
+TK_FN int fd_eof(const FpDec& d, int since) {
   const int64_t loaded = 32 * (int64_t)(d.wp - d.wbase) - d.bias8;
-  return (loaded - d.nbits - d.last_shift) > d.limit;
+  return (loaded - (d.nb_prev - 32 * (since - 1))) > d.limit;
 }
 
 // bd_fill_lookahead: tops the window up to > 32 valid bits; the word fetched here is not looked at before the next fill.
+// Call with nb holding the true count (fd_settle).
 TK_FN void fd_fill(FpDec& d) {
-  if (d.nbits <= 32) {
+  if (d.nb <= 32) {
     const uint32_t* p = d.wp;   // d.nxt came from p - 1
     const uint32_t w = (p - 1 < d.wend) ? VP8_BSWAP(d.nxt) : 0u;
     d.nxt = VP8_LDG(p < d.wend ? p : d.wend);   // wend itself lies inside the arena's tail padding
     d.wp = p + 1;
-    d.V |= vp8_shr_clamp(w, d.nbits);
-    d.vlo = vp8_shl_clamp(w, 32 - d.nbits);
-    d.nbits += 32;
+    d.V |= vp8_shr_clamp(w, d.nb);
+    d.vlo = vp8_shl_clamp(w, 32 - d.nb);
+    d.nb += 32;
   }
 }
+TK_FN void fd_settle(FpDec& d, int decodes) { d.nb -= 32 * decodes; }   // after `decodes` steps: nb is the true count again
 
 // Constants of the decode step that must sit in registers (see tf_and_or).
-struct FpConst { uint32_t mant_mask, exp128; };
+struct FpConst { uint32_t mant_mask, exp46; };
 
-// One decode; pf = float(probability). Needs >= 8 valid bits in the window.
-TK_FN int fd_bit(FpDec& d, float pf, const FpConst& k) {
-  const float m = tf_fma_rz(d.Rs, pf, 8388608.0f);
-  const uint32_t s1 = tf_as_uint(m) * 0x01000000u + 0x01000000u;
+// fd_bit for the straight-line groups (tf_group_flat): the decode is computed, the reader only moves when `run`.
+// nb stays the true count here (one three-input add).
+TK_FN int fd_bit_guarded(FpDec& d, uint32_t prob_bits, const FpConst& k, bool run) {
+  const float m = tf_fma_rz(d.Ra, tf_as_float(prob_bits), TF_S_2P23);
+  const uint32_t s1 = tf_mad(tf_as_uint(m), 0x01000000u, 0x01000000u);
   const int bit = d.V >= s1;
-  const float f0 = m - 8388607.0f, f1 = d.Rp - m;
+  const float f0 = m - TF_S_2P23M1, f1 = d.Rp - m;
   const float f = bit ? f1 : f0;
   const uint32_t fb = tf_as_uint(f);
-  const float fn = tf_as_float(tf_and_or(fb, k.mant_mask, k.exp128));   // the new range, normalised into [128, 256)
-  const int shift = 134 - (int)(fb >> 23);
-  d.Rs = fn * 0.00390625f - 0.00390625f;
-  d.Rp = fn + 8388607.0f;
-  d.V = vp8_shl_pair(d.V - (bit ? s1 : 0u), d.vlo, shift);
-  d.vlo <<= shift;
-  d.nbits -= shift;
-  d.last_shift = shift;
+  const float fa = tf_as_float(tf_and_or(fb, k.mant_mask, k.exp46));
+  const uint32_t kk = fb >> 23;
+  const uint32_t vs = tf_umin(d.V, d.V - s1);
+  if (run) {
+    d.Ra = fa - TF_2P39;
+    d.Rp = tf_fma(fa, tf_as_float(TF_2PM141_BITS), TF_S_2P23M1);
+    d.V = tf_shr_pair(vs, d.vlo, kk);
+    d.vlo = tf_shr_pair(d.vlo, 0u, kk);
+    d.nb_prev = d.nb;
+    d.nb = d.nb + (int)kk - 32;
+  }
+  return bit;
+}
+
+// One decode; pd = the probability byte as float BITS (a denormal). Needs >= 8 valid bits in the window.
+TK_FN int fd_bit(FpDec& d, uint32_t prob_bits, const FpConst& k) {
+  const float m = tf_fma_rz(d.Ra, tf_as_float(prob_bits), TF_S_2P23);
+  const uint32_t s1 = tf_mad(tf_as_uint(m), 0x01000000u, 0x01000000u);
+  const int bit = d.V >= s1;
+  const float f0 = m - TF_S_2P23M1, f1 = d.Rp - m;
+  const float f = bit ? f1 : f0;
+  const uint32_t fb = tf_as_uint(f);
+  const float fa = tf_as_float(tf_and_or(fb, k.mant_mask, k.exp46));   // 2^39 * the new range normalised into [128, 256)
+  const uint32_t kk = fb >> 23;                                          // 32 - shift
+  d.Ra = fa - TF_2P39;
+  d.Rp = tf_fma(fa, tf_as_float(TF_2PM141_BITS), TF_S_2P23M1);
+  const uint32_t vs = tf_umin(d.V, d.V - s1);
+  d.V = tf_shr_pair(vs, d.vlo, kk);
+  d.vlo = tf_shr_pair(d.vlo, 0u, kk);
+  d.nb_prev = d.nb;
+  d.nb += (int)kk;
   return bit;
 }
 
@@ -236,7 +280,7 @@ TK_FN int fd_bit(FpDec& d, float pf, const FpConst& k) {
 #define TF_TOK_BLOCK(t) (((t) >> 25) & 31u)
 #define TF_TOK_POS(t) (((t) >> 6) & 15u)
 #define TF_TOK_MAG(t) (((t) >> TF_ADD_SHIFT) & 0xfffu)
-#define TF_TOKENS_PER_MB 384   // 16 x 15 + 16 (i16) or 16 x 16 (i4x4) luma levels + 128 chroma levels
+#define TF_TOKENS_PER_MB VP8B_TOKENS_PER_MB
 
 // Lane phases as in vp8_tokens_lockstep.h.
 #define TF_RUN 0
@@ -249,11 +293,14 @@ struct TfLane {
   FpDec d;
   tk_saddr a;             // address of the pending probability: row of (type, position) + state
   tk_saddr rowend;        // first address of position 16 of the current block type
-  float pf;               // the pending probability
+  tk_saddr a_end;         // straight-line groups: where the block ended (L.a wanders on afterwards)
+  uint32_t tok_end;       // ... and the token count at that point
+  uint32_t pb;            // the pending probability: the byte, i.e. the bits of a denormal float
+  uint32_t tag, tag_s;    // block index << 25, and the same with the sign bit set
+  int eofs;               // fd_eof() of the most recent decode, taken where a macroblock ends
   uint32_t e0, e1;        // the transition entries of the pending decode's two outcomes
   uint32_t sink;          // see tf_decode (never meaningful)
   uint32_t acc;           // sum of the entries taken since the last emit / block start: magnitude in TF_ADD_MASK
-  uint32_t blktag;        // block index << 25
   uint32_t tokoff;        // next token of this partition, counted from the image's first token
   uint32_t mbtok0;        // first token of the current macroblock
   uint32_t cx;            // non-zero contexts: top in bits 0-8 (0-3 luma, 4-5 U, 6-7 V, 8 Y2), left in bits 16-24
@@ -292,7 +339,7 @@ struct TfCtx {
 };
 
 TK_FN void tf_lane_reset(TfLane& L, const TfCtx& c) {
-  L.a = c.img_s; L.rowend = 0; L.pf = 0.f; L.e0 = 0; L.e1 = 0; L.acc = 0; L.sink = 0; L.blktag = 0; L.cx = 0;
+  L.a = c.img_s; L.rowend = 0; L.a_end = 0; L.tok_end = 0; L.pb = 0; L.e0 = 0; L.e1 = 0; L.acc = 0; L.sink = 0; L.tag = 0; L.tag_s = 0; L.cx = 0;
   L.acc_lo = 0; L.acc_hi = 0; L.m = 0; L.m_next = 0; L.lut = 0; L.seq = 0;
   L.yrow = 0; L.yend = 0; L.ylut = 0;
   L.mx = 0; L.my = c.part; L.done_mbs = 0; L.waiting = 1; L.alive = 1; L.status = VP8B_OK;
@@ -308,12 +355,13 @@ TK_FN void tf_lane_reset(TfLane& L, const TfCtx& c) {
 TK_FN void tf_lane_init(TfLane& L, const TfCtx& c, const uint8_t* frame, const FrameHdr* h) {
   fd_init(L.d, frame + h->part_off[c.part], h->part_size[c.part]);
   tf_lane_reset(L, c);
+  L.eofs = fd_eof(L.d, 1);
   L.w_next = (c.part < c.rows) ? VP8_LDG(c.mbinfo + 4 * ((size_t)c.part * c.mb_w) + 3) : 0;
 }
 
 // Loads the pending decode (probability, both transition entries) of state s at address L.a.
 TK_FN void tf_prime(TfLane& L, const TfCtx& c, uint32_t s) {
-  L.pf = tf_u8_to_float(tk_lds_u8(L.a));
+  L.pb = tk_lds_u8(L.a);
   tk_lds_v2(c.tab_s + s * 8u, L.e0, L.e1);
 }
 
@@ -333,7 +381,7 @@ TK_FN void tf_block_setup(TfLane& L, const TfCtx& c) {
   L.m_next = tk_lds_u32(c.tab_s + TFT_SEQMASK + 4u * (uint32_t)L.seq + 4u);
   L.rowend = chroma ? crow + TF_TYPE_BYTES : L.yend;
   L.lut = chroma ? TF_LUT_FROM0 : L.ylut;
-  L.blktag = ((uint32_t)L.seq - 1u) << 25;
+  L.tag = ((uint32_t)L.seq - 1u) << 25; L.tag_s = L.tag | 0x80000000u;
   L.acc = 0;
   const uint32_t s = tf_popc(L.cx & L.m) * 11u;
   L.a = (chroma ? crow : L.yrow) + s;
@@ -347,7 +395,7 @@ TK_FN void tf_y2_setup(TfLane& L, const TfCtx& c) {
   const tk_saddr row = c.img_s + 1 * TF_TYPE_BYTES;
   L.rowend = row + TF_TYPE_BYTES;
   L.lut = TF_LUT_FROM0;
-  L.blktag = 24u << 25;
+  L.tag = 24u << 25; L.tag_s = L.tag | 0x80000000u;
   L.acc = 0;
   const uint32_t s = tf_popc(L.cx & L.m) * 11u;
   L.a = row + s;
@@ -368,7 +416,7 @@ TK_FN void tf_mb_store(TfLane& L, const TfCtx& c, uint32_t nzy, uint32_t w3) {
   c.topctx[(size_t)ring_row * c.ctx_stride + L.mx] = (uint16_t)(L.cx & 0x1ffu);
   L.done_mbs++;
   if (++L.mx == mb_w) { L.mx = 0; L.my += P; }
-  if (fd_eof(L.d)) {
+  if (L.eofs) {
     // Ran past the end of the partition: the image is lost (vp8_dec.c:651-659); release whoever waits on us.
     L.status = VP8B_NOT_ENOUGH_DATA;
     if (MULTI) { TK_FENCE(); c.progress[c.part] = 0x7fffffff; }
@@ -420,7 +468,8 @@ TK_FN int tf_mb_next(TfLane& L, const TfCtx& c) {
 
 // The macroblock's last block has ended: store its results, move on.
 template <int MULTI>
-TK_FN void tf_mb_finish(TfLane& L, const TfCtx& c) {
+TK_FN void tf_mb_finish(TfLane& L, const TfCtx& c, int since) {
+  L.eofs = fd_eof(L.d, since);
   const uint32_t nzy = (L.acc_hi << 16) | (L.acc_lo >> 16);
   const uint32_t uv = L.acc_lo & 0xffffu;                      // U codes in bits 15-8, V in 7-0
   const uint32_t nzuv = (uv >> 8) | ((uv & 0xffu) << 8);       // reference order: U bits 0-7, V bits 8-15
@@ -435,39 +484,41 @@ TK_FN void tf_lane_park(TfLane& L, const TfCtx& c) {
   L.pend = TF_FINISHED; L.alive = 0; L.waiting = 0;
   L.a = c.img_s + TF_DEAD; L.rowend = ~(tk_saddr)0;
   tf_prime(L, c, TF_DEAD);
-  L.pf = 0.f;
+  L.pb = 0;
 }
 
 // A lane without a stream: finished from the start (`any` = some valid address for its reader).
 TK_FN void tf_lane_idle(TfLane& L, const TfCtx& c, const uint8_t* any) {
   fd_init(L.d, any, 0);
   tf_lane_reset(L, c);
+  L.eofs = 0;
   tf_lane_park(L, c);
 }
 
 // One boolean decode and the transition it selects; returns the transition entry. The caller has topped the window up
 // (fd_fill) within the last three decodes.
+//
+// What the next decode needs (its probability, the entries of its two outcomes) is loaded AFTER the bit is known, at
+// an address picked by the bit: one shared-memory latency per step on the dependent chain (23 cycles, about half of
+// it). The alternative -- loading for both outcomes ahead of the bit and selecting -- takes the latency off the chain
+// but costs ten more integer-pipe instructions per step, and one warp alone on a sub-partition gets an integer-pipe
+// slot only every other cycle: measured 102 cycles per step against this form's (profiles/r02e, r02f).
 TK_FN uint32_t tf_decode(TfLane& L, const TfCtx& c) {
-  // ---- what the NEXT decode needs, fetched for both outcomes of this one before its bit is known
-  uint32_t e00, e01, e10, e11;
-  tk_lds_v2_pinned(c.tab_s + TF_E_TAB(L.e0), e00, e01);
-  tk_lds_v2_pinned(c.tab_s + TF_E_TAB(L.e1), e10, e11);
   const tk_saddr a0 = L.a + TF_E_DIST(L.e0), a1 = L.a + TF_E_DIST(L.e1);
-  const uint32_t p0 = tk_lds_u8_pinned(a0), p1 = tk_lds_u8_pinned(a1);
+  const tk_saddr t0 = c.tab_s + TF_E_TAB(L.e0), t1 = c.tab_s + TF_E_TAB(L.e1);
   // ---- boolean decode
-  const int bit = fd_bit(L.d, L.pf, c.k);
+  const int bit = fd_bit(L.d, L.pb, c.k);
   // ---- transition
   const uint32_t e = bit ? L.e1 : L.e0;
   const tk_saddr a_emit = L.a;
   L.a = bit ? a1 : a0;
-  L.pf = tf_u8_to_float(bit ? p1 : p0);
-  L.sink ^= p1;   // an unconditional use: without it the assembler folds the select into a load of p1 predicated on the
-                  // bit, which puts the shared-memory latency straight back on the dependent chain
-  L.e0 = bit ? e10 : e00;
-  L.e1 = bit ? e11 : e01;
+  L.pb = tk_lds_u8(L.a);
+  tk_lds_v2(bit ? t1 : t0, L.e0, L.e1);
   L.acc += e;
   if (e & TF_EMIT) {   // the sign has just been decoded: one token
-    c.tokens[L.tokoff++] = (L.acc & TF_ADD_MASK) | L.blktag | ((uint32_t)a_emit & 0x3c0u) | ((uint32_t)bit << 31);
+    const uint32_t t = (L.acc & TF_ADD_MASK) | (bit ? L.tag_s : L.tag);
+    c.tokens[L.tokoff] = t | ((uint32_t)a_emit & 0x3c0u);
+    L.tokoff += 1;
     L.acc = 0;
   }
   return e;
@@ -492,11 +543,12 @@ TK_FN int tf_block_end(TfLane& L, const TfCtx& c) {
 // ---- every lane executes every step; a lane whose block has ended does its bookkeeping on the spot while the others
 // wait. Returns 0 once the lane has finished (parked).
 template <int MULTI>
-TK_FN int tf_step_inline(TfLane& L, const TfCtx& c) {
+TK_FN int tf_step_inline(TfLane& L, const TfCtx& c, int since /* decodes since the last fd_fill, this one included */) {
   if (MULTI) {
     if (L.waiting) {
       if (!tf_mb_next<MULTI>(L, c)) {
         if (!L.waiting) tf_lane_park(L, c);
+        L.d.nb += 32;   // a step without a decode: fd_settle counts 32 per step
         return L.alive;
       }
     }
@@ -504,7 +556,7 @@ TK_FN int tf_step_inline(TfLane& L, const TfCtx& c) {
   const uint32_t e = tf_decode(L, c);
   if (TF_UNLIKELY((e & TF_EOB) || L.a >= L.rowend)) {
     if (tf_block_end(L, c)) {
-      tf_mb_finish<MULTI>(L, c);
+      tf_mb_finish<MULTI>(L, c, since);
       if (!tf_mb_next<MULTI>(L, c)) {
         if (!(MULTI && L.waiting)) tf_lane_park(L, c);
         return L.alive;
@@ -512,6 +564,79 @@ TK_FN int tf_step_inline(TfLane& L, const TfCtx& c) {
     }
   }
   return 1;
+}
+
+// One group: top the window up, four decodes.
+template <int MULTI>
+TK_FN void tf_group_inline(TfLane& L, const TfCtx& c) {
+  fd_fill(L.d);
+  tf_step_inline<MULTI>(L, c, 1); tf_step_inline<MULTI>(L, c, 2); tf_step_inline<MULTI>(L, c, 3); tf_step_inline<MULTI>(L, c, 4);
+  fd_settle(L.d, 4);
+}
+
+// ---- second way of running the lanes: groups of four straight-line steps, nothing branches between them.
+// One warp alone on a sub-partition pays ~18 cycles for every branch it executes (resolve + reconverge) and cannot
+// overlap anything across it, so the end-of-block test per step cost more than the decode it guards (profiles/r02f).
+// Here a lane whose block ends inside a group is switched to the dead state on the spot (probability 0, entries that
+// neither emit nor end a block) and its READER is frozen by predication (fd_bit_guarded: `run`); it sits out the rest
+// of the group, and all lanes that ended do their bookkeeping together at the group's one event point. A lane that has
+// to wait for the row above (several partitions) or has finished is in the dead state from the start of the group.
+#define TF_DEAD_ENTRY TF_E(TF_DEAD, TF_DEAD, 0, 0, 0)
+
+TK_FN void tf_go_dead(TfLane& L, const TfCtx& c) {   // the decode state of a lane that is not running
+  L.a = c.img_s + TF_DEAD; L.rowend = ~(tk_saddr)0;
+  L.pb = 0; L.e0 = TF_DEAD_ENTRY; L.e1 = TF_DEAD_ENTRY;
+}
+
+TK_FN bool tf_step_flat(TfLane& L, const TfCtx& c, const bool run) {
+  const tk_saddr a0 = L.a + TF_E_DIST(L.e0), a1 = L.a + TF_E_DIST(L.e1);
+  const tk_saddr t0 = c.tab_s + TF_E_TAB(L.e0), t1 = c.tab_s + TF_E_TAB(L.e1);
+  const int bit = fd_bit_guarded(L.d, L.pb, c.k, run);
+  const uint32_t e = bit ? L.e1 : L.e0;
+  const tk_saddr a_emit = L.a;
+  const tk_saddr an = bit ? a1 : a0;
+  L.a = an;
+  L.pb = tk_lds_u8(an);
+  tk_lds_v2(bit ? t1 : t0, L.e0, L.e1);
+  L.acc += e;
+  if (e & TF_EMIT) {   // the sign has just been decoded: one token. A lane that is not running writes its garbage into the
+                       // slots after its last real token, which the next real tokens overwrite (tf_events puts tokoff back)
+    const uint32_t t = (L.acc & TF_ADD_MASK) | (bit ? L.tag_s : L.tag);
+    c.tokens[L.tokoff] = t | ((uint32_t)a_emit & 0x3c0u);
+    L.tokoff += 1;
+    L.acc = 0;
+  }
+  const bool end = ((e & TF_EOB) != 0u) || (an >= L.rowend);
+  if (run && end) { L.a_end = an; L.tok_end = L.tokoff; }   // the block has ended here: the position gives nz
+  return run && !end;
+}
+
+// The group's event point: lanes whose block has ended do ParseResiduals' bookkeeping and start their next block or
+// macroblock; lanes that wait for the row above try again.
+template <int MULTI>
+TK_FN void tf_events(TfLane& L, const TfCtx& c, int ended) {
+  int need_mb = (L.pend == TF_NEED_MB);
+  L.pend = TF_RUN;
+  if (ended) {
+    L.a = L.a_end; L.tokoff = L.tok_end;
+    if (tf_block_end(L, c)) { tf_mb_finish<MULTI>(L, c, 1); need_mb = 1; }
+  }
+  if (TF_UNLIKELY(need_mb)) {
+    if (!tf_mb_next<MULTI>(L, c)) {
+      if (MULTI && L.waiting) { L.pend = TF_NEED_MB; tf_go_dead(L, c); } else tf_lane_park(L, c);
+    }
+  }
+}
+
+// One group: four decodes, then the event point for the lanes that need it. A running lane whose block ends inside the
+// group keeps stepping on garbage with its reader frozen (fd_bit_guarded) until the event point puts it right.
+template <int MULTI>
+TK_FN void tf_group_flat(TfLane& L, const TfCtx& c) {
+  const bool run0 = L.pend == TF_RUN;
+  if (run0) fd_fill(L.d);
+  bool run = run0;
+  run = tf_step_flat(L, c, run); run = tf_step_flat(L, c, run); run = tf_step_flat(L, c, run); run = tf_step_flat(L, c, run);
+  if ((run0 && !run) || L.pend == TF_NEED_MB) tf_events<MULTI>(L, c, run0 && !run);
 }
 
 #endif  // LIBWEBP_B200_VP8_TOKENS_FP_H_

@@ -162,23 +162,23 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
     for (int p = 0; p < P && p < rows; ++p) {
       TfCtx& cc = ctxs[p];
       cc.img_s = tk_saddr_of(img); cc.tab_s = tk_saddr_of(ttab);
-      cc.k.mant_mask = 0x007fffffu; cc.k.exp128 = 0x43000000u;
+      cc.k.mant_mask = 0x007fffffu; cc.k.exp46 = TF_EXP46;
       cc.topctx = topctx.data(); cc.progress = progress.data();
       cc.mbinfo = mbinfo.data(); cc.mbtok = mbtok.data(); cc.tokens = tokens.data();
       cc.mb_w = mb_w; cc.rows = rows; cc.P = P; cc.part = p; cc.use_skip = hdr.use_skip; cc.ctx_stride = mb_w;
       tf_lane_init(lanes[p], cc, frame, &hdr);
       live[p] = 1;
     }
-    if (P == 1 && live[0] && !tf_mb_next<0>(lanes[0], ctxs[0])) { tf_lane_park(lanes[0], ctxs[0]); live[0] = 0; }
+    const bool inline_style = (variant & 16) != 0;   // variant bit 4: a branch per decode instead of the straight-line groups
+    if (inline_style && P == 1 && live[0] && !tf_mb_next<0>(lanes[0], ctxs[0])) { tf_lane_park(lanes[0], ctxs[0]); live[0] = 0; }
     for (bool any = true; any;) {
       any = false;
       for (int p = P - 1; p >= 0; --p) {   // reverse order: exercises the wait-for-progress path
         if (!live[p]) continue;
         any = true;
-        fd_fill(lanes[p].d);
-        for (int k = 0; k < 4; ++k) {   // parked lanes keep stepping, harmlessly, like on the device
-          if (P > 1) tf_step_inline<1>(lanes[p], ctxs[p]); else tf_step_inline<0>(lanes[p], ctxs[p]);
-        }
+        // parked lanes keep stepping, harmlessly, like on the device
+        if (inline_style) { if (P > 1) tf_group_inline<1>(lanes[p], ctxs[p]); else tf_group_inline<0>(lanes[p], ctxs[p]); }
+        else { if (P > 1) tf_group_flat<1>(lanes[p], ctxs[p]); else tf_group_flat<0>(lanes[p], ctxs[p]); }
         live[p] = lanes[p].alive;
       }
     }

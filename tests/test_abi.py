@@ -199,3 +199,32 @@ def test_option_and_buffer_screening_matches_reference(product, ref):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_options.py"), "--cases", "6000", "--seed", "11"],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:]
+
+
+def test_packaged_as_libwebpdecoder(product, tmp_path):
+    """`make dist`: the library under the reference's own name -- libwebpdecoder.so.3.1.8 with soname libwebpdecoder.so.3
+    (src/Makefile.am:51), a static archive and libwebpdecoder.pc (src/libwebpdecoder.pc.in) -- so that an application
+    which links -lwebpdecoder needs no change to its build. A C program compiled against it runs without a device."""
+    import subprocess
+    csrc = os.path.join(ROOT, "libwebp_b200", "csrc")
+    subprocess.check_call(["make", "-s", "-C", csrc, "dist"])
+    dist = os.path.join(ROOT, "libwebp_b200", "dist")
+    so = os.path.join(dist, "lib", "libwebpdecoder.so.3.1.8")
+    assert os.path.exists(so) and os.path.exists(os.path.join(dist, "lib", "libwebpdecoder.a"))
+    assert os.path.realpath(os.path.join(dist, "lib", "libwebpdecoder.so")) == os.path.realpath(so)
+    dyn = subprocess.run(["readelf", "-d", so], capture_output=True, text=True).stdout
+    assert "libwebpdecoder.so.3" in dyn and "SONAME" in dyn
+    pc = open(os.path.join(dist, "lib", "pkgconfig", "libwebpdecoder.pc")).read()
+    assert "Name: libwebpdecoder" in pc and "-lwebpdecoder" in pc and "Version: 1.3.2" in pc
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include "webp/decode.h"\n#include "webp/decode_batch.h"\n'
+                   'int main(void) { WebPDecoderConfig c; WebPBatchOptions o;\n'
+                   '  if (!WebPInitDecoderConfig(&c) || !WebPBatchOptionsInit(&o)) return 1;\n'
+                   '  printf("%x %d\\n", WebPGetDecoderVersion(), (int)sizeof(o)); return 0; }\n')
+    exe = tmp_path / "t"
+    subprocess.check_call(["gcc", str(src), "-I", os.path.join(dist, "include"), "-L", os.path.join(dist, "lib"),
+                           "-lwebpdecoder", "-Wl,-rpath," + os.path.join(dist, "lib"), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split() == ["10302", "48"], out.stdout + out.stderr
+    needed = subprocess.run(["readelf", "-d", str(exe)], capture_output=True, text=True).stdout
+    assert "libwebpdecoder.so.3" in needed

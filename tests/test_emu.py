@@ -39,7 +39,7 @@ def test_emu_matches_manifest(emu, manifest):
         w, h = e["features"]["width"], e["features"]["height"]
         for key, want in e["sha256"].items():
             csp, fl = map(int, key.split(":"))
-            for rev in (0, 1, 2, 3, 4, 8, 9, 24, 25, 56, 64, 65):   # 64 = the fp parser (fp32 boolean decoder, token stream); 2 = row-at-a-time token parser, 4 = lazy ring producer (lanes find the ring dry), 8 = lockstep lanes, 24 = lockstep lanes with grouped event points, 56 = the same as straight-line groups
+            for rev in (0, 1, 2, 3, 4, 8, 9, 24, 25, 56, 64, 65, 80):   # 64 = the fp parser (fp32 boolean decoder, token stream; 80 = with a branch per decode); 2 = row-at-a-time token parser, 4 = lazy ring producer (lanes find the ring dry), 8 = lockstep lanes, 24 = lockstep lanes with grouped event points, 56 = the same as straight-line groups
                 st, out = emu(e["data"], w, h, csp, fl, rev)
                 assert st == 0 and sha(out) == want, (e["file"], key, rev)
 
@@ -68,7 +68,7 @@ def test_emu_status_on_damaged_files(emu, port, manifest):
     for c in cases:
         s_ref, a = port.decode(c, port.RGBA, 0)
         w, h = port.features(c)[1]["width"], port.features(c)[1]["height"]
-        for variant in (0, 2, 8, 24, 56, 64):   # lane state machine / row-at-a-time parser / lockstep lanes (block ends on the spot, grouped) / fp parser
+        for variant in (0, 2, 8, 24, 56, 64, 80):   # lane state machine / row-at-a-time parser / lockstep lanes (block ends on the spot, grouped) / fp parser
             s_emu, b = emu(c, max(w, 1), max(h, 1), 1, 0, variant)
             assert s_emu == s_ref, (len(c), s_ref, s_emu, variant)
             if s_ref == 0:
