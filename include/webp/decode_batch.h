@@ -97,6 +97,22 @@ typedef struct WebPBatchPlane {
 } WebPBatchPlane;
 WEBP_EXTERN int WebPBatchOutput(const WebPBatch* batch, int index, WebPBatchPlane* plane);
 
+/* Animated files: every frame of the file decoded as ONE batch, then the reference's canvas reconstruction
+ * (WebPAnimDecoderGetNext, src/demux/anim_decode.c:325-440: key-frame rule, blending, disposal) replayed on the host.
+ * canvases receives frame_count canvases of 4 * canvas_width * canvas_height bytes one after the other, exactly what
+ * successive WebPAnimDecoderGetNext() calls return; timestamps (may be NULL) their end times in ms. mode is one of
+ * MODE_RGBA, MODE_BGRA, MODE_rgbA, MODE_bgrA (WebPAnimDecoderOptions::color_mode). Not an animated file, or a file the
+ * reference's demuxer would refuse: VP8_STATUS_BITSTREAM_ERROR. (The reference's own WebPAnimDecoder also works on top
+ * of this library, one GPU round trip per frame.) */
+typedef struct WebPAnimBatchInfo {
+  int canvas_width, canvas_height, frame_count, loop_count;
+  uint32_t bgcolor;
+  uint32_t pad[3];
+} WebPAnimBatchInfo;
+WEBP_EXTERN int WebPAnimBatchGetInfo(const uint8_t* data, size_t data_size, WebPAnimBatchInfo* info);
+WEBP_EXTERN VP8StatusCode WebPAnimDecodeBatch(const uint8_t* data, size_t data_size, WEBP_CSP_MODE mode, uint8_t* canvases,
+                                              size_t canvases_size, int* timestamps, const WebPBatchOptions* options);
+
 /* Per-stage device time of the last WebPBatchDecode() on this batch, from CUDA events recorded on the
  * batch's own stream around each kernel (milliseconds; `launches` = kernels launched). */
 typedef struct WebPBatchTimings {

@@ -100,7 +100,7 @@ EXPORTS = [  # every symbol include/webp/*.h declares
     "WebPBatchOptionsInitInternal", "WebPDecodeBatch", "WebPBatchCreate", "WebPBatchDecode", "WebPBatchDownload",
     "WebPBatchDestroy", "WebPBatchOutput", "WebPBatchGetTimings", "WebPBatchHostAlloc", "WebPBatchHostFree",
     "WebPBatchDeviceCount", "WebPBatchLastError", "WebPBatchSubmit", "WebPBatchWait", "WebPBatchSetCacheLimit",
-    "WebPBatchTrimCache",
+    "WebPBatchTrimCache", "WebPAnimBatchGetInfo", "WebPAnimDecodeBatch",
 ]
 
 _lib = None
@@ -432,6 +432,30 @@ class Batch:
             if b is not None:
                 b.free()
         self.in_buf = self.out_buf = None
+
+
+class WebPAnimBatchInfo(C.Structure):
+    _fields_ = [("canvas_width", C.c_int), ("canvas_height", C.c_int), ("frame_count", C.c_int), ("loop_count", C.c_int),
+                ("bgcolor", C.c_uint32), ("pad", C.c_uint32 * 3)]
+
+
+def anim_decode_batch(data, csp=MODE_RGBA, device=-1):
+    """WebPAnimDecodeBatch: all frames of an animated file in one batch -> (status, canvases [n, h, w, 4] or None, timestamps)."""
+    L = lib()
+    L.WebPAnimBatchGetInfo.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(WebPAnimBatchInfo)]
+    L.WebPAnimDecodeBatch.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_int),
+                                      C.POINTER(WebPBatchOptions)]
+    info = WebPAnimBatchInfo()
+    if not L.WebPAnimBatchGetInfo(data, len(data), C.byref(info)):
+        return VP8_STATUS_BITSTREAM_ERROR, None, None
+    n, w, h = info.frame_count, info.canvas_width, info.canvas_height
+    out = np.zeros((n, h, w, 4), np.uint8)
+    ts = (C.c_int * n)()
+    opt = WebPBatchOptions()
+    L.WebPBatchOptionsInitInternal(C.byref(opt), WEBP_BATCH_ABI_VERSION)
+    opt.device = device
+    st = L.WebPAnimDecodeBatch(data, len(data), csp, out.ctypes.data, out.size, ts, C.byref(opt))
+    return st, (out if st == VP8_STATUS_OK else None), list(ts)
 
 
 def shard_indices(n_items, rank, world):

@@ -878,11 +878,10 @@ static int ev_mark(WebPBatch* b, cudaStream_t s) {   // records the next pooled 
 // ALPH chunks of the batch: header pass, host-side sizing of the work areas (first decode only), then the pixel
 // pass + unfilter, all queued on the compute stream ahead of the VP8 kernels. Leaves every image's w x h alpha
 // plane in d_alpha; k_emit picks it up through ImgDesc::alpha_plane.
-static bool batch_alpha(WebPBatch* b) {
+static bool batch_alpha(WebPBatch* b, cudaStream_t s) {
   DeviceCtx* ctx = b->ctx;
   const int na = (int)b->aimgs.size();
   if (na == 0) return true;
-  cudaStream_t s = b->stream;
   const uint8_t* arena = (const uint8_t*)b->d_in.p;
   if (!b->alpha_planned) {
     b->aplans.assign(na, AlphaPlan());
@@ -1008,9 +1007,14 @@ static bool batch_enqueue(WebPBatch* b, bool download) {
 #define MARK(var) const int var = ev_mark(b, s); if (var < 0) return false
   MARK(e_begin);
   b->e_begin = e_begin;
+  // ALPH chunks and whole VP8L pictures first, on the compute stream. (Decoding them on a stream of their own beside the
+  // VP8 parse was measured and dropped, profiles/r02h: the VP8L loops are a few hundred single-thread warps, and a second
+  // warp on a sub-partition more than doubles the time of the latency-bound parser -- 4096x4096 + ALPH: tokens 1324 ->
+  // 2932 ms, modes 93 -> 184 ms, for 309 ms of alpha work hidden.)
+  int alpha_done = -1;
   if (!b->aimgs.empty()) {
     MARK(ea0);
-    if (!batch_alpha(b)) return false;
+    if (!batch_alpha(b, s)) return false;
     MARK(ea1);
     b->spans.push_back({ ST_ALPHA, ea0, ea1 });
     launches += 3;
@@ -1047,6 +1051,7 @@ static bool batch_enqueue(WebPBatch* b, bool download) {
       if (ok) bands = std::min(env_bands, w.max_mb_h / 8);
     }
     if (bands > 1) {
+      if (alpha_done >= 0) { CU_TRY(cudaStreamWaitEvent(s, b->ev[alpha_done], 0), "cudaStreamWaitEvent"); alpha_done = -1; }
       static int overlap = -1;
       if (overlap < 0) { const char* e = getenv("WEBP_B200_BAND_OVERLAP"); overlap = (e != NULL && atoi(e) > 0) ? 1 : 0; }
       cudaStream_t ps = overlap ? ctx->pixel_stream : s;
@@ -1090,6 +1095,7 @@ static bool batch_enqueue(WebPBatch* b, bool download) {
       continue;
     }
     if (b->any_dither) { vp8k_dither_plan(s, imgs, hdrs, mbinfo, dither, w.first, w.count); ++launches; }
+    if (alpha_done >= 0) { CU_TRY(cudaStreamWaitEvent(s, b->ev[alpha_done], 0), "cudaStreamWaitEvent"); alpha_done = -1; }
     MARK(e2);
     b->spans.push_back({ ST_MODES, e0, e1 });
     b->spans.push_back({ ST_TOKENS, e1, e2 });
@@ -1119,6 +1125,7 @@ static bool batch_enqueue(WebPBatch* b, bool download) {
     }
   }
 #undef MARK
+  if (alpha_done >= 0) CU_TRY(cudaStreamWaitEvent(s, b->ev[alpha_done], 0), "cudaStreamWaitEvent");
   const int e_end = ev_mark(b, s); if (e_end < 0) return false;
   b->e_end = e_end;
   b->launches = launches;

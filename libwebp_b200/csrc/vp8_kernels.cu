@@ -505,14 +505,6 @@ __global__ void __launch_bounds__(32 * RECON_WARPS) k_reconstruct(const ImgDesc*
       const int16_t* dq6 = dqs + 6 * ((mbi[4 * idx + 3] >> MBW_SEG_SHIFT) & 3);
       if (tk != nullptr) {
         const MbTok t = mt[idx];
-        // the macroblock to the right is this warp's next one in this row, and its tokens follow these in the partition's
-        // stream: start them (and its MbInfo / MbTok) on their way from HBM now, two barriers ahead of their use
-        {
-          const int lane = threadIdx.x & 31;
-          const void* pf = lane < 4 ? (const void*)(tk + t.first + t.count + 32 * lane)
-                                    : lane == 4 ? (const void*)(mbi + 4 * (idx + 1)) : (const void*)(mt + idx + 1);
-          if (lane < 6 && mx + 1 < mb_w) asm volatile("prefetch.global.L2 [%0];" :: "l"(pf));
-        }
         recon_macroblock(ws, cx, mx, my, mb_w, mbi + 4 * idx, nullptr, dq6, yp, up, vp, tk + t.first, t.count);
       } else {
         recon_macroblock(ws, cx, mx, my, mb_w, mbi + 4 * idx, cf + idx * VP8B_COEFFS_PER_MB, dq6, yp, up, vp);

@@ -3,6 +3,7 @@
 `dwebp examples/test.webp -ppm`), and src/demux's WebPAnimDecoder (anim_decode.c:376: one WebPDecode per frame into a
 sub-rectangle of the canvas, blended on the host). oracle/Makefile `tools` builds them into oracle/_ref/ from the sources
 under /root/reference; on the GPU box the prebuilt files travel with the snapshot. Test infrastructure only."""
+import ctypes as C
 import hashlib
 import os
 import subprocess
@@ -134,3 +135,38 @@ def test_anim_decoder_over_the_cuda_decoder(callers):
             n, got, ts = callers.anim_decode(data, csp, "b200")
             assert n == n_ref > 0 and ts == ts_ref
             assert np.array_equal(got, want), (len(data), csp)
+
+
+def test_anim_batch_info_matches_the_reference_demuxer(callers, product):
+    """WebPAnimBatchGetInfo's container walk against the reference's demuxer (no GPU needed): canvas, frame count; still
+    pictures and damaged files are refused."""
+    for kw in (dict(), dict(n=12, w=200, h=150, seed=21, kmin=0, kmax=0), dict(n=6, w=321, h=123, seed=5, minimize_size=1),
+               dict(n=6, w=96, h=80, seed=8, lossless=1)):
+        data = animation(callers, **kw)
+        n_ref, want, _ = callers.anim_decode(data, callers.MODE_RGBA, "reft")
+        info = product.WebPAnimBatchInfo()
+        L = product.lib()
+        L.WebPAnimBatchGetInfo.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(product.WebPAnimBatchInfo)]
+        assert L.WebPAnimBatchGetInfo(data, len(data), C.byref(info)) == 1
+        assert (info.frame_count, info.canvas_height, info.canvas_width) == (n_ref, want.shape[1], want.shape[2])
+        assert L.WebPAnimBatchGetInfo(data[:len(data) // 2], len(data) // 2, C.byref(info)) == 0
+    still = open(os.path.join(ROOT, "tests", "golden", "simple_1part_320x200.webp"), "rb").read()
+    assert L.WebPAnimBatchGetInfo(still, len(still), C.byref(info)) == 0
+
+
+@pytest.mark.gpu
+def test_anim_decode_batch(callers, product):
+    """WebPAnimDecodeBatch: all frames of a file in ONE batch, canvases rebuilt on the host by the reference's rules --
+    every canvas and time stamp equal to successive WebPAnimDecoderGetNext() calls of the all-reference build
+    (sub-rectangle frames, blend / no-blend, dispose-to-background, ALPH, lossless and mixed frames, four colour modes)."""
+    files = [animation(callers), animation(callers, n=12, w=200, h=150, seed=21, quality=50.0, kmin=0, kmax=0),
+             animation(callers, n=5, w=64, h=64, seed=33, quality=90.0, kmin=1, kmax=1),
+             animation(callers, n=6, w=321, h=123, seed=5, minimize_size=1),
+             animation(callers, n=6, w=96, h=80, seed=8, lossless=1), animation(callers, n=9, w=150, h=100, seed=9, lossless=2, quality=30.0)]
+    for data in files:
+        for csp in (callers.MODE_RGBA, callers.MODE_BGRA, callers.MODE_rgbA, callers.MODE_bgrA):
+            n_ref, want, ts_ref = callers.anim_decode(data, csp, "reft")
+            st, got, ts = product.anim_decode_batch(data, csp)
+            assert st == 0 and got.shape[0] == n_ref and ts == ts_ref, (st, csp)
+            assert np.array_equal(got, want), (len(data), csp)
+    assert product.anim_decode_batch(files[0], product.MODE_RGB)[0] == product.VP8_STATUS_INVALID_PARAM
