@@ -373,24 +373,27 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_lockstep(const uint
 // Lockstep lanes with the fp32 boolean decoder and token-stream output (vp8_tokens_fp.h): the default token parser.
 // A block owns ipb images x P partitions = S streams; stream j sits in warp j % cw, lane j / cw.
 struct TfLayout {   // byte offsets from the 1024-byte aligned start of the block's dynamic shared memory
-  uint32_t images, progress, ctx, total;
+  uint32_t images, rings, bars, progress, ctx, total;
 };
-__host__ __device__ static inline TfLayout tf_layout(int P, int ipb, int ctx_stride) {
+__host__ __device__ static inline TfLayout tf_layout(int P, int ipb, int ctx_stride, int ring) {
   TfLayout t;
   t.images = 1024;                                         // TfTables in front
-  t.progress = t.images + (uint32_t)ipb * TF_IMG_BYTES;
+  t.rings = t.images + (uint32_t)ipb * TF_IMG_BYTES;      // RING: per stream a 256-byte input ring (256-byte aligned)
+  t.bars = t.rings + (ring ? (uint32_t)(ipb * P) * 256u : 0u);          // ... and two mbarriers
+  t.progress = t.bars + (ring ? (uint32_t)(ipb * P) * 16u : 0u);
   t.ctx = t.progress + (uint32_t)ipb * VP8B_MAX_PARTS * 4u;
   t.total = t.ctx + (uint32_t)ipb * (uint32_t)(P + 1) * (uint32_t)ctx_stride * 2u + 1024u;   // + alignment slack
   return t;
 }
 
+template <int RING>
 __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_fp(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
                                                             FrameHdr* hdrs, uint32_t* mbinfo, uint32_t* tokens, MbTok* mbtok,
                                                             const int* __restrict__ ids, int count, int P, int ipb, int lpw,
                                                             int cw, int ctx_stride, int flat) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tk_saddr_of(smem_raw) & 1023u)) & 1023u);   // the rows' addresses carry the position in bits 6-9
-  const TfLayout lay = tf_layout(P, ipb, ctx_stride);
+  const TfLayout lay = tf_layout(P, ipb, ctx_stride, RING);
   TfTables* tables = reinterpret_cast<TfTables*>(smem);
   int* progress = reinterpret_cast<int*>(smem + lay.progress);
   const int tid = threadIdx.x, nthreads = blockDim.x;
@@ -431,25 +434,30 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_fp(const uint8_t* _
   __builtin_assume(__isGlobal(c.tokens));
   __builtin_assume(__isGlobal(c.mbtok));
   TfLane L;
-  if (have) tf_lane_init(L, c, arena + im.in_off, h); else tf_lane_idle(L, c, arena);
+  if (have) {
+    tf_lane_init(L, c, arena + im.in_off, h);
+    if (RING) fd_ring_open(L.d, tk_saddr_of(smem + lay.rings) + (uint32_t)j * 256u, tk_saddr_of(smem + lay.bars) + (uint32_t)j * 16u);
+  } else {
+    tf_lane_idle(L, c, arena);
+  }
   // The loop counter starts from a per-thread value (always 0) so that the compiler does not fence the body with
   // WARPSYNC.ALL; the vote costs as much as half a step and is taken every 32 steps.
   const int r0 = (int)(L.sink >> 31);
   if (flat) {
     // Straight-line groups of four decodes with one event point (vp8_tokens_fp.h:tf_group_flat): the default.
     if (P > 1) {
-      while (__any_sync(0xffffffffu, L.alive)) { for (int r = r0; r < 8; ++r) tf_group_flat<1>(L, c); }
+      while (__any_sync(0xffffffffu, L.alive)) { for (int r = r0; r < 8; ++r) tf_group_flat<1, RING>(L, c); }
     } else {
-      while (__any_sync(0xffffffffu, L.alive)) { for (int r = r0; r < 8; ++r) tf_group_flat<0>(L, c); }
+      while (__any_sync(0xffffffffu, L.alive)) { for (int r = r0; r < 8; ++r) tf_group_flat<0, RING>(L, c); }
     }
   } else if (P > 1) {
     while (__any_sync(0xffffffffu, L.alive)) {
-      for (int r = r0; r < 8; ++r) tf_group_inline<1>(L, c);
+      for (int r = r0; r < 8; ++r) tf_group_inline<1, RING>(L, c);
     }
   } else {
     if (have && !tf_mb_next<0>(L, c)) tf_lane_park(L, c);
     while (__any_sync(0xffffffffu, L.alive)) {
-      for (int r = r0; r < 8; ++r) tf_group_inline<0>(L, c);
+      for (int r = r0; r < 8; ++r) tf_group_inline<0, RING>(L, c);
     }
   }
   if (have && L.status != VP8B_OK) h->status = L.status;
@@ -670,7 +678,8 @@ static size_t tokens_slot_bytes(int P, int max_mb_w) {
 #define VP8K_MAX_DYN_SMEM (227 * 1024)   // opt-in ceiling per block on sm_100
 extern "C" cudaError_t vp8k_init_device(void) {
   const void* kernels[] = { (const void*)k_parse_modes, (const void*)k_parse_tokens, (const void*)k_parse_tokens_fsm,
-                            (const void*)k_parse_tokens_lockstep, (const void*)k_parse_tokens_fp, (const void*)k_reconstruct,
+                            (const void*)k_parse_tokens_lockstep, (const void*)k_parse_tokens_fp<0>, (const void*)k_parse_tokens_fp<1>,
+                            (const void*)k_reconstruct,
                             (const void*)k_loop_filter };
   for (const void* k : kernels) {
     cudaFuncAttributes fa;
@@ -794,8 +803,10 @@ static void launch_tokens_fp(cudaStream_t s, const uint8_t* arena, const ImgDesc
   if (lpw > 32) lpw = 32;
   while (cw * lpw < P) ++lpw;               // a block holds at least one image
   int ipb = (cw * lpw) / P;                  // images per block
-  while (ipb > 1 && tf_layout(P, ipb, max_mb_w).total > (uint32_t)VP8K_MAX_DYN_SMEM - 1024u) --ipb;
-  const TfLayout lay = tf_layout(P, ipb, max_mb_w);
+  const char* er = getenv("WEBP_B200_TOKEN_RING");
+  const int ring = (er != NULL && atoi(er) != 0) ? 1 : 0;
+  while (ipb > 1 && tf_layout(P, ipb, max_mb_w, ring).total > (uint32_t)VP8K_MAX_DYN_SMEM - 1024u) --ipb;
+  const TfLayout lay = tf_layout(P, ipb, max_mb_w, ring);
   const int blocks = (count + ipb - 1) / ipb;
   // How the lanes are run (vp8_tokens_fp.h): a branch per decode with the block ends handled on the spot while a warp has
   // few lanes, straight-line groups of four decodes with one event point when it has many (the event point's cost is
@@ -805,7 +816,17 @@ static void launch_tokens_fp(cudaStream_t s, const uint8_t* arena, const ImgDesc
   const char* eg = getenv("WEBP_B200_TOKEN_GROUPED");
   const int lanes_per_warp = (ipb * P + cw - 1) / cw;
   const int flat = eg != NULL ? (atoi(eg) != 0) : (lanes_per_warp >= 16);
-  k_parse_tokens_fp<<<blocks, 32 * cw, lay.total, s>>>(arena, imgs, hdrs, mbinfo, tokens, mbtok, ids, count, P, ipb, lpw, cw, max_mb_w, flat);
+  // How the compressed bytes reach the reader: one read-only global load per 32-bit refill, issued one refill ahead of
+  // its use (default), or (WEBP_B200_TOKEN_RING=1) per-stream shared-memory rings filled 128 bytes at a time by
+  // cp.async.bulk with mbarrier completion (vp8_tokens_fp.h:FpDec). Both are built and parity-tested; measured per 4096
+  // full-HD images (profiles/r02k): 1 partition 267 ms / 347 ms, 8 partitions 82 / 195, 65536 thumbnails 132 / 162 -- a
+  // stream consumes 0.8 bits per decode, so the ring saves one load per ~40 decodes and pays for it with a longer refill path
+  // inside a warp whose every instruction is on the critical path.
+  if (ring) {
+    k_parse_tokens_fp<1><<<blocks, 32 * cw, lay.total, s>>>(arena, imgs, hdrs, mbinfo, tokens, mbtok, ids, count, P, ipb, lpw, cw, max_mb_w, flat);
+  } else {
+    k_parse_tokens_fp<0><<<blocks, 32 * cw, lay.total, s>>>(arena, imgs, hdrs, mbinfo, tokens, mbtok, ids, count, P, ipb, lpw, cw, max_mb_w, flat);
+  }
 }
 
 // Which token parser a wave takes: 1 = the fp parser (token stream out), 0 = one of the older mappings (dense level plane),

@@ -196,11 +196,62 @@ struct FpDec {
   float Ra, Rp;          // (range - 1) * 2^39 and S * ((range - 1) + 2^23)
   int bias8;
   int64_t limit;         // 8*size - 8: a decode starting beyond this bit position reads past the end
+  // The compressed bytes reach the reader through a 256-byte shared-memory ring per stream, filled 128 bytes at a time by
+  // bulk asynchronous copies (cp.async.bulk, the 1-D form of TMA: one instruction per 128 bytes, completion on an mbarrier
+  // per ring half) that the lane itself issues a whole chunk ahead of its reads: no per-word global load on the parser's
+  // path. Chunk k (counted from the 128-byte aligned chunk of the stream's first word, `gbase`) lives in half k & 1 and
+  // completes phase (k >> 1) & 1 of that half's barrier. (Host build: plain loads.)
+  tk_saddr ring, bars;   // 256-byte aligned ring, two mbarriers
+  uintptr_t gbase;       // global address of chunk 0
+  uint32_t roff;         // ring offset (0..255) of the next word the reader takes
+  int chunk;             // chunk that word lies in; chunk + 1 has been requested
 };
+
+#if defined(__CUDACC__) && !defined(VP8_EMU)
+TK_FN void fd_ring_fetch(const FpDec& d, int chunk) {
+  const tk_saddr dst = d.ring + (uint32_t)(chunk & 1) * 128u, bar = d.bars + (uint32_t)(chunk & 1) * 8u;
+  const uintptr_t src = d.gbase + (uintptr_t)chunk * 128u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the half's earlier reads (generic proxy) before the async write
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 128;" :: "r"(bar) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 128, [%2];"
+               :: "r"(dst), "l"(src), "r"(bar) : "memory");
+}
+TK_FN int fd_ring_wait(const FpDec& d, int chunk) {   // 0 if the copy never lands (never expected: the caller fails the stream)
+  const tk_saddr bar = d.bars + (uint32_t)(chunk & 1) * 8u;
+  const uint32_t parity = (uint32_t)(chunk >> 1) & 1u;
+  uint32_t done = 0;
+  int spins = 0;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done && ++spins < (1 << 22));
+  return (int)done;
+}
+// After fd_init: the words from d.wp on come through the ring.
+TK_FN void fd_ring_open(FpDec& d, tk_saddr ring, tk_saddr bars) {
+  d.ring = ring; d.bars = bars; d.chunk = 0;
+  d.gbase = (uintptr_t)d.wp & ~(uintptr_t)127;
+  d.roff = (uint32_t)((uintptr_t)d.wp & 127u);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bars) : "memory");
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bars + 8u) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  if (d.wp < d.wend) {
+    fd_ring_fetch(d, 0); fd_ring_fetch(d, 1);
+    if (!fd_ring_wait(d, 0)) { d.limit = -0x4000000000000000ll; d.wend = d.wp; }
+  }
+}
+// The reader steps into the next chunk (every 32nd word): it must have landed; the half behind it takes the chunk after.
+TK_FN void fd_ring_cross(FpDec& d, const uint32_t* p) {
+  d.chunk += 1;
+  if (!fd_ring_wait(d, d.chunk)) { d.limit = -0x4000000000000000ll; d.wend = p; return; }   // given up: reads as "past the end"
+  fd_ring_fetch(d, d.chunk + 1);
+}
+#endif
 
 TK_FN void fd_init(FpDec& d, const uint8_t* start, uint32_t size) {
   BoolDec b;
   bd_init(b, start, size);
+  d.ring = 0; d.bars = 0; d.gbase = 0; d.roff = 0; d.chunk = 0;
   d.wp = b.wp; d.wend = b.wend; d.wbase = b.wbase; d.V = b.V; d.vlo = b.vlo; d.nxt = b.nxt; d.nb = b.nbits; d.nb_prev = b.nbits;
   d.Ra = 254.0f * TF_2P39; d.Rp = tf_fma(254.0f * TF_2P39, tf_as_float(TF_2PM141_BITS), TF_S_2P23);
   d.bias8 = b.bias8; d.limit = b.limit;
@@ -215,12 +266,22 @@ TK_FN int fd_eof(const FpDec& d, int since) {
 }
 
 // bd_fill_lookahead: tops the window up to > 32 valid bits; the word fetched here is not looked at before the next fill.
-// Call with nb holding the true count (fd_settle).
+// Call with nb holding the true count (fd_settle). RING = 1: the words come through the shared-memory ring (device only).
+template <int RING>
 TK_FN void fd_fill(FpDec& d) {
   if (d.nb <= 32) {
     const uint32_t* p = d.wp;   // d.nxt came from p - 1
     const uint32_t w = (p - 1 < d.wend) ? VP8_BSWAP(d.nxt) : 0u;
-    d.nxt = VP8_LDG(p < d.wend ? p : d.wend);   // wend itself lies inside the arena's tail padding
+#if defined(__CUDACC__) && !defined(VP8_EMU)
+    if (RING) {
+      if (p < d.wend) {   // a word at or past wend is never looked at (w above)
+        if (TF_UNLIKELY((d.roff & 127u) == 0u && p != (const uint32_t*)d.gbase)) fd_ring_cross(d, p);
+        if (p < d.wend) d.nxt = tk_lds_u32(d.ring + d.roff);
+        d.roff = (d.roff + 4u) & 255u;
+      }
+    } else
+#endif
+    d.nxt = VP8_LDG(p < d.wend ? p : d.wend);   // straight from HBM through the read-only path; wend itself lies inside the arena's tail padding
     d.wp = p + 1;
     d.V |= vp8_shr_clamp(w, d.nb);
     d.vlo = vp8_shl_clamp(w, 32 - d.nb);
@@ -374,6 +435,9 @@ TK_FN uint32_t tf_popc(uint32_t x) {
 }
 
 // Sets up block L.seq >= 1 (contexts in L.cx are final for it). Luma block k is block k - 1, chroma blocks follow.
+// (Preparing the next block's start state while the current one is parsed -- everything of its context but the one bit
+// this block sets -- takes the POPC and a load off the block end's critical path, but costs 16 registers and four
+// instructions per block: measured 267 -> 276 ms per 4096 full-HD images, profiles/r02l, and dropped.)
 TK_FN void tf_block_setup(TfLane& L, const TfCtx& c) {
   const int chroma = L.seq >= 17;
   const tk_saddr crow = c.img_s + 2 * TF_TYPE_BYTES;
@@ -567,9 +631,9 @@ TK_FN int tf_step_inline(TfLane& L, const TfCtx& c, int since /* decodes since t
 }
 
 // One group: top the window up, four decodes.
-template <int MULTI>
+template <int MULTI, int RING>
 TK_FN void tf_group_inline(TfLane& L, const TfCtx& c) {
-  fd_fill(L.d);
+  fd_fill<RING>(L.d);
   tf_step_inline<MULTI>(L, c, 1); tf_step_inline<MULTI>(L, c, 2); tf_step_inline<MULTI>(L, c, 3); tf_step_inline<MULTI>(L, c, 4);
   fd_settle(L.d, 4);
 }
@@ -630,10 +694,10 @@ TK_FN void tf_events(TfLane& L, const TfCtx& c, int ended) {
 
 // One group: four decodes, then the event point for the lanes that need it. A running lane whose block ends inside the
 // group keeps stepping on garbage with its reader frozen (fd_bit_guarded) until the event point puts it right.
-template <int MULTI>
+template <int MULTI, int RING>
 TK_FN void tf_group_flat(TfLane& L, const TfCtx& c) {
   const bool run0 = L.pend == TF_RUN;
-  if (run0) fd_fill(L.d);
+  if (run0) fd_fill<RING>(L.d);
   bool run = run0;
   run = tf_step_flat(L, c, run); run = tf_step_flat(L, c, run); run = tf_step_flat(L, c, run); run = tf_step_flat(L, c, run);
   if ((run0 && !run) || L.pend == TF_NEED_MB) tf_events<MULTI>(L, c, run0 && !run);

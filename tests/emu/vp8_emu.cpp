@@ -177,8 +177,8 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
         if (!live[p]) continue;
         any = true;
         // parked lanes keep stepping, harmlessly, like on the device
-        if (inline_style) { if (P > 1) tf_group_inline<1>(lanes[p], ctxs[p]); else tf_group_inline<0>(lanes[p], ctxs[p]); }
-        else { if (P > 1) tf_group_flat<1>(lanes[p], ctxs[p]); else tf_group_flat<0>(lanes[p], ctxs[p]); }
+        if (inline_style) { if (P > 1) tf_group_inline<1, 0>(lanes[p], ctxs[p]); else tf_group_inline<0, 0>(lanes[p], ctxs[p]); }
+        else { if (P > 1) tf_group_flat<1, 0>(lanes[p], ctxs[p]); else tf_group_flat<0, 0>(lanes[p], ctxs[p]); }
         live[p] = lanes[p].alive;
       }
     }

@@ -344,10 +344,11 @@ def test_crop_and_flip(W, ref, manifest, amanifest):
             assert np.array_equal(want, got.reshape(-1))
 
 
-@pytest.mark.parametrize("mapping", ["warp", "k", "k:1", "k:2", "lanes"])
+@pytest.mark.parametrize("mapping", ["f:0", "f:1", "f:0:ring", "f:1:ring", "warp", "k", "k:1", "k:2", "lanes"])
 def test_every_token_mapping(mapping):
-    """The three mappings of the token parse (one warp per partition, lockstep lanes, lane state machine) are picked by
-    stream count; here each is forced in turn (WEBP_B200_TOKEN_MAP is read once per process, hence the subprocess) and
+    """The default token parser (f: lockstep lanes with the fp32 boolean decoder and token-stream output) picks its run style
+    by lanes per warp; here both are forced in turn (f:0 a branch per decode, f:1 straight-line groups), and so is each of
+    the older mappings that write the dense level plane (one warp per partition, lockstep lanes, lane state machine) (WEBP_B200_TOKEN_MAP is read once per process, hence the subprocess) and
     must pass the manifest, mixed-batch and fresh-corpus parity tests above."""
     import os
     import subprocess
@@ -355,8 +356,10 @@ def test_every_token_mapping(mapping):
     if os.environ.get("WEBP_B200_TOKEN_MAP_INNER"):
         pytest.skip("inner run")
     env = dict(os.environ, WEBP_B200_TOKEN_MAP=mapping.split(":")[0], WEBP_B200_TOKEN_MAP_INNER="1")
-    if ":" in mapping:   # the lockstep parser's other two ways of running its lanes (grouped event points, straight-line groups)
+    if ":" in mapping:   # the lockstep parsers' ways of running their lanes (block ends on the spot, grouped event points, straight-line groups)
         env["WEBP_B200_TOKEN_GROUPED"] = mapping.split(":")[1]
+    if mapping.endswith(":ring"):   # compressed bytes through shared-memory rings filled by cp.async.bulk instead of global loads
+        env["WEBP_B200_TOKEN_RING"] = "1"
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
                         "manifest or mixed_sizes or fresh_corpora or full_size or damaged or many_streams"], env=env, capture_output=True, text=True,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -408,7 +411,7 @@ def test_row_bands(ref):
         "print('bands ok')\n"
     ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for overlap in ("0", "1"):
-        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, WEBP_B200_BANDS="4", WEBP_B200_BAND_OVERLAP=overlap),
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, WEBP_B200_BANDS="4", WEBP_B200_BAND_OVERLAP=overlap, WEBP_B200_TOKEN_MAP="k"),   # row bands: the older lockstep parser
                            capture_output=True, text=True)
         assert r.returncode == 0 and "bands ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
 
