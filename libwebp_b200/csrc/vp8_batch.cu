@@ -368,7 +368,7 @@ struct WebPBatch {
   std::vector<int> img_item;       // device image -> item
   std::vector<Wave> waves;
   std::vector<int> ids;            // token-parse launch lists
-  int* statuses = nullptr;         // page-locked host copy of FrameHdr::status (m ints)
+  int* statuses = nullptr;         // page-locked: status, fail_row, rows << 8 | filter_type of every FrameHdr (3 m ints, k_collect_status)
   void* h_stage = nullptr;         // page-locked staging of the descriptors and launch lists on their way up
   size_t h_status_cap = 0, h_stage_cap = 0;
   Owned d_in, d_imgs, d_hdrs, d_ids, d_out;
@@ -612,10 +612,10 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
   if (m == 0) return true;
 
   // ---- page-locked staging for what the library itself moves: descriptors + launch lists up, status words down
-  b->statuses = (int*)pinned_alloc(ctx, sizeof(int) * (size_t)m, &b->h_status_cap);
+  b->statuses = (int*)pinned_alloc(ctx, 3 * sizeof(int) * (size_t)m, &b->h_status_cap);
   b->h_stage = pinned_alloc(ctx, (sizeof(ImgDesc) + sizeof(int)) * (size_t)m, &b->h_stage_cap);
   if (b->statuses == nullptr || b->h_stage == nullptr) return false;
-  memset(b->statuses, 0, sizeof(int) * (size_t)m);
+  memset(b->statuses, 0, 3 * sizeof(int) * (size_t)m);
   // ---- resident allocations: input (64 KB tail padding, see vp8_tokens_fsm.h:tk_lane_init), descriptors, headers, output
   if (!own_alloc(ctx, b->d_in, in_total + 65536) || !own_alloc(ctx, b->d_imgs, sizeof(ImgDesc) * m) ||
       !own_alloc(ctx, b->d_hdrs, sizeof(FrameHdr) * m) || !own_alloc(ctx, b->d_ids, sizeof(int) * m) ||
@@ -1177,15 +1177,27 @@ static bool batch_finish(WebPBatch* b) {
   b->timings.launches = b->launches;
   for (int k = 0; k < m; ++k) {
     WebPBatchItem* it = &b->items[b->img_item[k]];
-    it->status = (VP8StatusCode)b->statuses[k];
+    it->status = (VP8StatusCode)b->statuses[3 * k];
     if (b->imgs[k].flags & VP8B_FLAG_LOSSLESS) {
       // every failure of a whole-picture VP8L decode is a bitstream error (vp8l_dec.c:1292,1479-1488: nothing suspends
       // outside the incremental decoder); the two limits of vp8l_alpha_core.h stay UNSUPPORTED_FEATURE
       const int ls = b->ahdrs[b->imgs[k].alpha_index].status;
       it->status = ls == AL_OK ? VP8_STATUS_OK : ls == AL_UNSUPPORTED ? VP8_STATUS_UNSUPPORTED_FEATURE : VP8_STATUS_BITSTREAM_ERROR;
     } else
-    // a lost alpha plane loses the image (frame_dec.c:452-460), unless the VP8 stream had already failed
-    if (it->status == VP8_STATUS_OK && b->imgs[k].alpha_size != 0) it->status = (VP8StatusCode)b->ahdrs[b->imgs[k].alpha_index].status;
+    // a lost alpha plane loses the image (frame_dec.c:452-460), unless the VP8 stream fails first: the reference decodes alpha
+    // rows as the macroblock rows above them finish, so with both chunks damaged the rows of the two failures decide
+    if (b->imgs[k].alpha_size != 0) {
+      const ImgDesc& d = b->imgs[k];
+      const AlphaHdr& ah = b->ahdrs[d.alpha_index];
+      if (it->status == VP8_STATUS_OK) it->status = (VP8StatusCode)ah.status;
+      else if (ah.status != AL_OK) {
+        int vrow = b->statuses[3 * k + 1];
+        if (vrow == VP8B_FAIL_NONE) vrow = VP8B_FAIL_HEADERS;   // a parser that keeps no rows (the WEBP_B200_TOKEN_MAP debug paths)
+        const int meta = b->statuses[3 * k + 2];
+        if (!vp8b_vp8_failure_first(vrow, ah.fail_row, meta & 3, meta >> 8, (int)d.crop_y + (int)d.out_h, ah.levels != 0))
+          it->status = (VP8StatusCode)ah.status;
+      }
+    }
     if (it->status != VP8_STATUS_OK && b->opt.output == WEBP_BATCH_HOST) WebPFreeDecBuffer(&it->config->output);
   }
   b->decoded = true;

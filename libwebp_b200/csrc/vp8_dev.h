@@ -79,7 +79,31 @@ typedef struct FrameHdr {
   uint8_t dither[4];            // per segment: amplitude of the random chroma dithering (VP8InitDithering, frame_dec.c:328-349), 0 = none
   int32_t rows;                 // macroblock rows that get decoded: all of them, or down to the bottom of the crop
                                 // window plus the filter's reach (VP8EnterCritical, frame_dec.c:571-596)
+  int32_t fail_row;             // where the reference's row loop (vp8_dec.c:646-674) would meet this frame's failure:
+                                // VP8B_FAIL_NONE, VP8B_FAIL_HEADERS (before any row), or the macroblock row whose intra
+                                // modes (K1) or tokens (K2, the smallest over the partitions) ran out of data
 } FrameHdr;
+#define VP8B_FAIL_NONE 0x7fffffff
+#define VP8B_FAIL_HEADERS (-1)
+
+// A file whose ALPH chunk AND VP8 payload are both damaged: the reference decodes alpha rows as the macroblock rows above
+// them finish (FinishRow, frame_dec.c:440-460: rows [y_start, y_end) of macroblock row r right after its tokens) and reports
+// whichever failure its row loop meets first. vp8_fail_row as in FrameHdr; alpha_fail_row = the ALPHA row whose decode fails
+// (-1: the ALPH header, met by the first FinishRow); alpha_all_at_once: the plane's levels were quantised, which makes the
+// reference decode all of it at the first request (alpha_dec.c:196-203). Returns 1 when the VP8 failure comes first.
+static inline int vp8b_vp8_failure_first(int vp8_fail_row, int alpha_fail_row, int filter_type, int rows, int crop_bottom,
+                                         int alpha_all_at_once) {
+  const int extra = (filter_type == 2) ? 8 : (filter_type == 1) ? 2 : 0;   /* kFilterExtraRows, frame_dec.c:201 */
+  int r;
+  if (vp8_fail_row < 0) return 1;                       /* VP8GetHeaders: before the first row */
+  if (alpha_fail_row < 0 || alpha_all_at_once) return vp8_fail_row <= 0;   /* alpha fails in FinishRow(0) */
+  for (r = 0; r < rows; ++r) {                          /* first macroblock row whose FinishRow asks for the failing alpha row */
+    int y_end = 16 * (r + 1) - ((r >= rows - 1) ? 0 : extra);
+    if (y_end > crop_bottom) y_end = crop_bottom;
+    if (y_end > alpha_fail_row) break;
+  }
+  return vp8_fail_row <= r;
+}
 
 // MbInfo words (one uint4 per macroblock):
 //   x, y : sixteen 4-bit sub-block modes, mode n at bits 4*(n&7) of word n>>3 (i16: mode in the low nibble of x)

@@ -56,7 +56,9 @@ __global__ void __launch_bounds__(32 * MODES_WARPS, 1) k_parse_modes(const uint8
   if (im.flags & VP8B_FLAG_LOSSLESS) { h->status = VP8B_NOT_A_VP8_FRAME; return; }
   BoolDec br;
   int st = parse_frame_header(br, arena + im.in_off, im, h);
-  if (st == VP8B_OK) st = parse_intra_modes(br, im, h, top_modes_all + (size_t)warp * max_mb_w, bprob, mbinfo + 4 * (size_t)im.mb_base);
+  int fail_row = st == VP8B_OK ? VP8B_FAIL_NONE : VP8B_FAIL_HEADERS;
+  if (st == VP8B_OK) st = parse_intra_modes(br, im, h, top_modes_all + (size_t)warp * max_mb_w, bprob, mbinfo + 4 * (size_t)im.mb_base, &fail_row);
+  h->fail_row = fail_row;
   h->status = st;
 }
 
@@ -411,7 +413,10 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_fp(const uint8_t* _
   int have = lane < lpw && j < ipb * P && g < count;
   const int img = have ? ids[g] : 0;
   FrameHdr* h = &hdrs[img];
-  if (have && !(h->status == VP8B_OK && h->num_parts == P)) {   // header failed (or, never expected, the host pre-scan disagreed)
+  // An image whose intra modes ran out of data at macroblock row r > 0 still gets the tokens of the rows before it parsed:
+  // the reference would meet a token failure there first (fail_row, vp8_dev.h:vp8b_vp8_failure_first).
+  const int modes_failed_at = (have && h->status == VP8B_NOT_ENOUGH_DATA && h->fail_row > 0 && h->fail_row != VP8B_FAIL_NONE) ? h->fail_row : 0;
+  if (have && !((h->status == VP8B_OK || modes_failed_at > 0) && h->num_parts == P)) {   // header failed (or, never expected, the host pre-scan disagreed)
     if (part == 0 && h->status == VP8B_OK) h->status = VP8B_BITSTREAM_ERROR;
     have = 0;
   }
@@ -426,8 +431,9 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_fp(const uint8_t* _
   c.mbinfo = mbinfo + 4 * (size_t)im.mb_base;
   c.mbtok = mbtok + (size_t)im.mb_base;
   c.tokens = tokens + (size_t)im.mb_base * TF_TOKENS_PER_MB;
-  c.mb_w = im.mb_w; c.rows = have ? h->rows : 0; c.P = P; c.part = part; c.use_skip = h->use_skip;
+  c.mb_w = im.mb_w; c.rows = have ? (modes_failed_at > 0 && modes_failed_at < h->rows ? modes_failed_at : h->rows) : 0; c.P = P; c.part = part; c.use_skip = h->use_skip;
   c.ctx_stride = ctx_stride;
+  c.fail_row = &h->fail_row;
   if (part >= c.rows) have = 0;
   asm volatile("" : "+r"(c.P), "+r"(c.ctx_stride), "+r"(c.mb_w), "+l"(c.mbinfo), "+l"(c.tokens), "+l"(c.mbtok));
   __builtin_assume(__isGlobal(c.mbinfo));
@@ -655,9 +661,14 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit_scaled(const ImgDesc* __r
 // Per-image status words -> page-locked host memory, written by the device itself. (A cudaMemcpyAsync here would queue
 // behind the pixel downloads on the device-to-host copy engine and hold the COMPUTE stream up until they are through:
 // that is what kept batch k+1 from starting under batch k's download.)
+// Three words per image: status, fail_row, rows << 8 | filter_type (what vp8b_vp8_failure_first needs on the host).
 __global__ void __launch_bounds__(256) k_collect_status(const FrameHdr* __restrict__ hdrs, int* host_statuses, int count) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < count) host_statuses[k] = hdrs[k].status;
+  if (k < count) {
+    host_statuses[3 * k] = hdrs[k].status;
+    host_statuses[3 * k + 1] = hdrs[k].fail_row;
+    host_statuses[3 * k + 2] = (hdrs[k].rows << 8) | hdrs[k].filter_type;
+  }
 }
 
 // Small device -> mapped host copies of the same kind (the ALPH headers the host sizes its work areas from).

@@ -325,7 +325,7 @@ VP8_FN uint32_t parse_bmode(BoolDec& d, const uint8_t* p) {
 }
 
 VP8_FN int parse_intra_modes(BoolDec& br, const ImgDesc& im, const FrameHdr* h, uint32_t* top, const uint8_t* bprob,
-                             uint32_t* mbinfo /* 4 words per MB */) {
+                             uint32_t* mbinfo /* 4 words per MB */, int* fail_row = 0) {
   const int mb_w = im.mb_w, mb_h = h->rows;
   const int update_map = h->update_map, use_skip = h->use_skip, skip_p = h->skip_p;
   const uint32_t sp0 = h->seg_prob[0], sp1 = h->seg_prob[1], sp2 = h->seg_prob[2];
@@ -370,7 +370,7 @@ VP8_FN int parse_intra_modes(BoolDec& br, const ImgDesc& im, const FrameHdr* h, 
       uint4 o4; o4.x = m0; o4.y = m1; o4.z = 0; o4.w = w;
       *(uint4*)out = o4;
     }
-    if (bd_eof(br)) return VP8B_NOT_ENOUGH_DATA;
+    if (bd_eof(br)) { if (fail_row) *fail_row = my; return VP8B_NOT_ENOUGH_DATA; }
   }
   return VP8B_OK;
 }

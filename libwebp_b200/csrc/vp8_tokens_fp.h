@@ -396,6 +396,7 @@ struct TfCtx {
   MbTok* mbtok;           // this image's MbTok
   uint32_t* tokens;       // this image's token area (TF_TOKENS_PER_MB per macroblock)
   int mb_w, rows, P, part, use_skip, ctx_stride;
+  int* fail_row;          // FrameHdr::fail_row of the image
   FpConst k;
 };
 
@@ -481,7 +482,16 @@ TK_FN void tf_mb_store(TfLane& L, const TfCtx& c, uint32_t nzy, uint32_t w3) {
   L.done_mbs++;
   if (++L.mx == mb_w) { L.mx = 0; L.my += P; }
   if (L.eofs) {
-    // Ran past the end of the partition: the image is lost (vp8_dec.c:651-659); release whoever waits on us.
+    // Ran past the end of the partition: the image is lost (vp8_dec.c:651-659); release whoever waits on us. The row goes on
+    // record: with a damaged ALPH chunk as well, the reference reports whichever failure its row loop meets first.
+    if (L.status == VP8B_OK) {
+      const int row = (int)(idx / (size_t)mb_w);
+#if defined(__CUDACC__) && !defined(VP8_EMU)
+      atomicMin(c.fail_row, row);
+#else
+      if (row < *c.fail_row) *c.fail_row = row;
+#endif
+    }
     L.status = VP8B_NOT_ENOUGH_DATA;
     if (MULTI) { TK_FENCE(); c.progress[c.part] = 0x7fffffff; }
   } else if (MULTI) { TK_FENCE(); c.progress[c.part] = L.done_mbs; }

@@ -416,7 +416,10 @@ struct AlphaHdr {
   uint8_t tbits[4];         // tile bits (predictor, cross colour) or bundling bits (colour indexing)
   uint8_t use_8b;           // set by the pixel pass: the reference would have taken its 8-bit path (DecodeAlphaData)
   uint8_t lossless;         // the stream is a whole VP8L picture (5-byte header instead of the ALPH byte), see vp8l_lossless_core.h
-  uint8_t pad[1];
+  uint8_t levels;           // ALPH header pre-processing = 1 (quantised levels): the reference then decodes every row at the first
+                            // request (alpha_dec.c:196-203), whether or not alpha dithering was asked for
+  int32_t fail_row;         // status != AL_OK: the alpha row whose decode fails (the reference decodes rows as they are asked for,
+                            // alpha_dec.c:110-135), -1 = the header stage
   int32_t txsize[4];        // image width the transform applies to
   uint32_t tdata[4];        // word offset of the transform's tile image inside the transform-data area
   int32_t xsize;            // width of the coded image (after bundling)
@@ -447,8 +450,10 @@ struct AlphaHdr {
 AL_NOINLINE void alph_parse_header(const uint8_t* alph, uint32_t alph_size, int w, int h, uint8_t* scratch, uint16_t* meta,
                                    uint32_t* tdata, AlphaHdr* hd, int lossless = 0) {
   hd->status = AL_OUT_OF_MEMORY;   // every failure in here is a header failure (see the top of this file)
+  hd->fail_row = -1;
   hd->method = 0; hd->filter = 0; hd->ntrans = 0; hd->cache_bits = 0; hd->huff_bits = 0; hd->use_8b = 0;
   hd->lossless = (uint8_t)(lossless != 0);
+  hd->levels = 0;
   hd->xsize = w; hd->huff_xsize = 0; hd->num_groups = 1; hd->group_entries = AL_GROUP_ENTRIES(0);
   hd->br_val = 0; hd->br_pos = 0; hd->br_bit_pos = 0;
   uint32_t* tables = (uint32_t*)scratch;
@@ -460,7 +465,7 @@ AL_NOINLINE void alph_parse_header(const uint8_t* alph, uint32_t alph_size, int 
     if (alph_size <= 1) return;
     const int method = alph[0] & 3, filter = (alph[0] >> 2) & 3, pre = (alph[0] >> 4) & 3, rsrv = (alph[0] >> 6) & 3;
     if (method > 1 || pre > 1 || rsrv != 0) return;
-    hd->method = (uint8_t)method; hd->filter = (uint8_t)filter;
+    hd->method = (uint8_t)method; hd->filter = (uint8_t)filter; hd->levels = (uint8_t)pre;
     if (method == 0) {
       if ((uint64_t)(alph_size - 1) >= (uint64_t)w * (uint64_t)h) hd->status = AL_OK;
       return;
@@ -573,10 +578,12 @@ AL_NOINLINE int alph_decode_pixels(const uint8_t* alph, uint32_t alph_size, int 
   const int hbits = hd->huff_bits, hxs = hd->huff_xsize;
   const int len_code_limit = AL_NUM_LITERAL + AL_NUM_LENGTH;
   int pos = 0, col = 0, row = 0;
+  int pos0 = 0;   // where the symbol being read starts: the reference meets a failure when asked for that row
   int ok = 1;
   const AlGroup* grp = &groups[hbits ? meta[0] : 0];
   const uint32_t* gt = tables + (size_t)(grp - groups) * stride;
   while (pos < last && !(use_8b && b.eos)) {
+    pos0 = pos;
     if ((col & mask) == 0) {
       grp = &groups[hbits ? meta[hxs * (row >> hbits) + (col >> hbits)] : 0];
       gt = tables + (size_t)(grp - groups) * stride;
@@ -642,6 +649,7 @@ AL_NOINLINE int alph_decode_pixels(const uint8_t* alph, uint32_t alph_size, int 
     if (use_8b) b.eos = lb_at_end(b);
   }
   b.eos = lb_at_end(b);
+  hd->fail_row = pos0 / width;
   if (!ok) return AL_BITSTREAM_ERROR;
   if (use_8b ? (b.eos && pos < end) : b.eos) return AL_BITSTREAM_ERROR;
   return AL_OK;

@@ -9,6 +9,8 @@
 #include <string.h>
 
 #include <vector>
+#include <cstdlib>
+#include <cstdio>
 
 #define VP8_EMU 1
 #define VP8_WAIT_PROGRESS(ptr, need) assert(*(ptr) >= (need))
@@ -47,6 +49,24 @@ extern "C" int emu_decode_window(const uint8_t* data, size_t size, int csp, int 
 // the scaled picture.
 // options.dithering_strength = strength (0..100) on the whole picture.
 static int g_emu_dither_f = 0, g_emu_alpha_dither = 0;
+
+// K6's two serial passes on an ALPH chunk (k_alpha_header, k_alpha_pixels): leaves the status and, after a failure, the alpha
+// row the reference would have been asked for when it met it (AlphaHdr::fail_row).
+static void emu_alpha_passes(const uint8_t* alph, uint32_t alph_size, const ImgDesc& im, AlphaHdr* ah, std::vector<uint32_t>& coded,
+                             std::vector<uint32_t>& tdata) {
+  std::vector<uint8_t> scratch(AL_SCRATCH_BYTES + 64);
+  uint8_t* sc16 = (uint8_t*)(((uintptr_t)scratch.data() + 15) & ~(uintptr_t)15);
+  std::vector<uint32_t> meta(AL_META_PIXELS_BOUND(im.width, im.height) + 8);
+  tdata.assign(2 * (size_t)AL_META_PIXELS_BOUND(im.width, im.height) + 8, 0);
+  alph_parse_header(alph, alph_size, im.width, im.height, sc16, (uint16_t*)meta.data(), tdata.data(), ah);
+  if (ah->status == AL_OK && ah->method == 1) {
+    std::vector<uint32_t> tables((size_t)ah->num_groups * ah->group_entries);
+    std::vector<AlGroup> groups(ah->num_groups);
+    coded.assign((size_t)ah->xsize * im.height + 4, 0);
+    ah->status = alph_decode_pixels(alph, alph_size, im.height, (int)im.crop_y + (int)im.out_h, ah, (const uint16_t*)meta.data(),
+                                    tables.data(), groups.data(), sc16, coded.data());
+  }
+}
 extern "C" int emu_decode_dithered(const uint8_t* data, size_t size, int csp, int flags, uint8_t* out, size_t out_size,
                                    int stride, int strength, int crop_x, int crop_y, int crop_w, int crop_h);
 
@@ -135,11 +155,27 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
     BoolDec br;
     std::vector<uint32_t> top(mb_w);
     hdr.status = parse_frame_header(br, frame, im, &hdr);
-    if (hdr.status == VP8B_OK) hdr.status = parse_intra_modes(br, im, &hdr, top.data(), kVp8BModeProba, mbinfo.data());
+    hdr.fail_row = hdr.status == VP8B_OK ? VP8B_FAIL_NONE : VP8B_FAIL_HEADERS;
+    if (hdr.status == VP8B_OK) hdr.status = parse_intra_modes(br, im, &hdr, top.data(), kVp8BModeProba, mbinfo.data(), &hdr.fail_row);
   }
-  if (hdr.status != VP8B_OK) return hdr.status;
+  // Both chunks damaged: the fp parser keeps the row at which the VP8 stream fails, and the image's status is whichever
+  // failure the reference's row loop meets first (vp8_dev.h:vp8b_vp8_failure_first, like batch_finish in vp8_batch.cu).
+  const auto failed = [&](int vp8_status) -> int {
+    if (!c.has_alph_chunk || !(variant & 64)) return vp8_status;
+    AlphaHdr ah;
+    std::vector<uint32_t> coded, tdata;
+    emu_alpha_passes(data + c.alpha_offset, (uint32_t)c.alpha_size, im, &ah, coded, tdata);
+    if (ah.status == AL_OK) return vp8_status;
+    const int all_at_once = ah.levels != 0;
+    if (getenv("VP8_EMU_DEBUG")) fprintf(stderr, "vp8 status %d row %d | alpha status %d row %d | filter %d rows %d crop_bottom %d\n", vp8_status, hdr.fail_row, ah.status, ah.fail_row, hdr.filter_type, hdr.rows, (int)im.crop_y + (int)im.out_h);
+    return vp8b_vp8_failure_first(hdr.fail_row == VP8B_FAIL_NONE ? VP8B_FAIL_HEADERS : hdr.fail_row, ah.fail_row, hdr.filter_type, hdr.rows,
+                                  (int)im.crop_y + (int)im.out_h, all_at_once) ? vp8_status : ah.status;
+  };
+  // intra modes that ran out at row r > 0: the fp parser still reads the tokens of the rows above (k_parse_tokens_fp)
+  const bool modes_short = hdr.status == VP8B_NOT_ENOUGH_DATA && hdr.fail_row > 0 && hdr.fail_row != VP8B_FAIL_NONE && (variant & 64) && c.has_alph_chunk;
+  if (hdr.status != VP8B_OK && !modes_short) return failed(hdr.status);
   if (hdr.num_parts != im.num_parts) return -100;   // host pre-scan disagrees with the device parse
-  const int rows = hdr.rows;   // macroblock rows that get decoded (all of them unless cropping)
+  const int rows = modes_short && hdr.fail_row < hdr.rows ? hdr.fail_row : hdr.rows;   // macroblock rows that get decoded (all of them unless cropping)
 
   // K2: tokens
   std::vector<uint32_t> tokens;
@@ -166,6 +202,7 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
       cc.topctx = topctx.data(); cc.progress = progress.data();
       cc.mbinfo = mbinfo.data(); cc.mbtok = mbtok.data(); cc.tokens = tokens.data();
       cc.mb_w = mb_w; cc.rows = rows; cc.P = P; cc.part = p; cc.use_skip = hdr.use_skip; cc.ctx_stride = mb_w;
+      cc.fail_row = &hdr.fail_row;
       tf_lane_init(lanes[p], cc, frame, &hdr);
       live[p] = 1;
     }
@@ -286,7 +323,7 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
     }
     for (int p = 0; p < P && p < rows; ++p) if (tp[p].status != VP8B_OK) hdr.status = tp[p].status;
   }
-  if (hdr.status != VP8B_OK) return hdr.status;
+  if (hdr.status != VP8B_OK) return failed(hdr.status);
 
   // K3: reconstruction wavefront (lag 2)
   {
@@ -353,20 +390,10 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
   if (c.has_alph_chunk) {
     const uint8_t* alph = data + c.alpha_offset;
     const uint32_t alph_size = (uint32_t)c.alpha_size;
-    std::vector<uint8_t> scratch(AL_SCRATCH_BYTES + 64);
-    uint8_t* sc16 = (uint8_t*)(((uintptr_t)scratch.data() + 15) & ~(uintptr_t)15);
-    std::vector<uint32_t> meta(AL_META_PIXELS_BOUND(im.width, im.height) + 8);
-    std::vector<uint32_t> tdata(2 * (size_t)AL_META_PIXELS_BOUND(im.width, im.height) + 8);
+    std::vector<uint32_t> tdata;
     AlphaHdr ah;
-    alph_parse_header(alph, alph_size, im.width, im.height, sc16, (uint16_t*)meta.data(), tdata.data(), &ah);
     std::vector<uint32_t> coded;
-    if (ah.status == AL_OK && ah.method == 1) {
-      std::vector<uint32_t> tables((size_t)ah.num_groups * ah.group_entries);
-      std::vector<AlGroup> groups(ah.num_groups);
-      coded.assign((size_t)ah.xsize * im.height + 4, 0);
-      ah.status = alph_decode_pixels(alph, alph_size, im.height, (int)im.crop_y + (int)im.out_h, &ah, (const uint16_t*)meta.data(), tables.data(), groups.data(),
-                                     sc16, coded.data());
-    }
+    emu_alpha_passes(alph, alph_size, im, &ah, coded, tdata);
     if (ah.status != AL_OK) return ah.status;
     alpha_plane.assign((size_t)im.width * im.height, 0);
     alph_finish(&ah, alph + 1, coded.data(), tdata.data(), im.width, im.height, im.crop_y, alpha_plane.data(), 0, 1);

@@ -118,6 +118,39 @@ def test_emu_alpha_status_on_damaged_chunks(emu, ref, amanifest):
                 assert np.array_equal(want.reshape(-1), got.reshape(-1)), e["file"]
 
 
+def test_emu_alpha_and_vp8_both_damaged(emu, ref, amanifest):
+    """Both chunks damaged: the status is the one of the failure the reference's row loop meets first (alpha rows are decoded as
+    the macroblock rows above them finish). The fp parser (variants 64, 80) records the failing rows for that."""
+    rng = np.random.default_rng(29)
+    seen = set()
+    for e in amanifest:
+        data = e["data"]
+        if len(data) < 400:
+            continue
+        i = data.find(b"ALPH")
+        asz = int.from_bytes(data[i + 4:i + 8], "little")
+        v = data.find(b"VP8 ", i + 8 + asz)
+        vsz = int.from_bytes(data[v + 4:v + 8], "little")
+        w, h = e["features"]["width"], e["features"]["height"]
+        for k in range(60):
+            b = bytearray(data)
+            b[i + 8 + int(rng.integers(0, asz))] ^= int(rng.integers(1, 256))
+            if k & 1:
+                b[v + 8 + 10 + int(rng.integers(0, vsz - 10))] ^= int(rng.integers(1, 256))
+            else:
+                keep = int(rng.integers(vsz // 8, vsz))
+                b[v + 8 + keep:v + 8 + vsz] = bytes(vsz - keep)
+            b = bytes(b)
+            s_ref, want = ref.decode(b, ref.MODE_RGBA, 0)
+            seen.add(s_ref)
+            for variant in (64, 80):
+                s_emu, got = emu(b, w, h, 1, 0, variant)
+                assert s_emu == s_ref, (e["file"], k, s_ref, s_emu, variant)
+                if s_ref == 0:
+                    assert np.array_equal(want.reshape(-1), got.reshape(-1)), e["file"]
+    assert {3, 7} <= seen, seen
+
+
 def test_emu_crop_and_flip_match_reference(ref, manifest, amanifest):
     """options.use_cropping / options.flip: the window is upsampled as if it were the picture, rows below it are never
     decoded (so data missing down there goes unnoticed), the 8-bit alpha path restarts its horizontal unfilter at the

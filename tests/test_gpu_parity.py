@@ -800,3 +800,82 @@ def test_cache_limit_and_trim(W, manifest):
         assert all(s == 0 for s in sts)
     finally:
         W.set_cache_limit(prev, 0)
+
+
+def test_callers_stream(W, ref, manifest):
+    """WebPBatchOptions::stream: uploads and kernels are queued on the caller's stream -- behind work the caller queued
+    before (here: a long fill kernel of torch's), the pixels complete when the call returns; device-resident output read
+    back through the same stream. Every image compared."""
+    torch = pytest.importorskip("torch")
+    corpus = ref.encode_corpus(6, 640, 360, ref.cfg_simple_1part(), seed0=8100)
+    datas = [corpus[i % 6] for i in range(60)] + [e["data"] for e in manifest[:4]]
+    want = [ref.decode(d, ref.MODE_RGBA, 0) for d in datas]
+    st = torch.cuda.Stream(device=0)
+    with torch.cuda.stream(st):
+        big = torch.empty(1 << 28, dtype=torch.uint8, device="cuda:0")
+        for _ in range(8):
+            big.fill_(7)          # something for the batch to queue behind
+    b = W.Batch(datas, W.MODE_RGBA, device=0, stream=st.cuda_stream)
+    try:
+        assert b.decode_oneshot() == 0
+        for i in range(b.n):
+            assert b.statuses()[i] == want[i][0] == 0
+            assert np.array_equal(b.host_output(i), want[i][1]), i
+    finally:
+        b.close()
+    r = W.Batch(datas, W.MODE_RGBA, device=0, stream=st.cuda_stream, output=W.WEBP_BATCH_DEVICE)
+    try:
+        assert r.create() == 0 and r.decode() == 0
+        for i in (0, 17, b.n - 1):
+            p = r.device_output(i)
+            w, h = r.dims[i]
+            assert p.device == 0 and (p.width, p.height) == (w, h)
+            t = torch.empty(h * p.stride, dtype=torch.uint8, device="cuda:0")
+            # view the library's device memory as a tensor through the CUDA array interface
+            class _V:
+                __cuda_array_interface__ = {"shape": (h * p.stride,), "typestr": "|u1", "data": (p.y_or_rgba, False), "version": 3}
+            with torch.cuda.stream(st):
+                t.copy_(torch.as_tensor(_V(), device="cuda:0"))
+            st.synchronize()
+            assert np.array_equal(t.cpu().numpy().reshape(h, p.stride), want[i][1]), i
+    finally:
+        r.close()
+
+
+def _damage_both_chunks(rng, d):
+    """One byte of the ALPH payload changed and the VP8 payload damaged too (a changed byte, or the tail cut off)."""
+    b = bytearray(d)
+    i = d.find(b"ALPH")
+    asz = int.from_bytes(d[i + 4:i + 8], "little")
+    b[i + 8 + int(rng.integers(0, asz))] ^= int(rng.integers(1, 256))
+    v = d.find(b"VP8 ", i + 8 + asz)
+    vsz = int.from_bytes(d[v + 4:v + 8], "little")
+    if rng.integers(0, 2):
+        b[v + 8 + 10 + int(rng.integers(0, vsz - 10))] ^= int(rng.integers(1, 256))
+    else:
+        keep = int(rng.integers(vsz // 8, vsz))          # zero the tail: the chunk sizes stay, the partition runs dry
+        b[v + 8 + keep:v + 8 + vsz] = bytes(vsz - keep)
+    return bytes(b)
+
+
+@pytest.mark.gpu
+def test_alpha_and_vp8_both_damaged(W, ref, amanifest):
+    """The reference decodes alpha rows as the macroblock rows above them finish and reports whichever failure its row loop
+    meets first (frame_dec.c:440-460, alpha_dec.c:170-215); the product decodes the two chunks in separate kernels and
+    rebuilds that order from the failing rows (vp8_dev.h:vp8b_vp8_failure_first)."""
+    rng = np.random.default_rng(23)
+    datas = []
+    for e in amanifest:
+        if len(e["data"]) < 400:
+            continue
+        for _ in range(400):
+            datas.append(_damage_both_chunks(rng, e["data"]))
+    sts, outs = W.decode_batch(datas, W.MODE_RGBA, device=0)
+    seen = set()
+    for d, st, out in zip(datas, sts, outs):
+        s_ref, want = ref.decode(d, W.MODE_RGBA, 0)
+        assert st == s_ref, (len(d), st, s_ref)
+        seen.add(s_ref)
+        if s_ref == 0:
+            assert np.array_equal(out.reshape(-1), want.reshape(-1))
+    assert {3, 7} <= seen, seen      # both kinds of failure were met

@@ -159,8 +159,9 @@ def partition_starts_with_ff(b):
 
 def damaged_in_both_chunks(R, b, data, s_ref, s_emu):
     """ALPH chunk and VP8 payload both damaged: the reference reports whichever failure its row loop meets first (the alpha
-    rows are decoded as the macroblock rows above them finish, frame_dec.c:452-460); the product decodes the two in separate
-    passes and reports the VP8 status. Known deviation; confirmed by damaging one chunk at a time."""
+    rows are decoded as the macroblock rows above them finish, frame_dec.c:452-460). The default (fp) token parser keeps the
+    failing rows and reports the same; the older parsers kept as debug paths report the VP8 status. Confirmed by damaging
+    one chunk at a time."""
     sa, so = chunk_spans(b), chunk_spans(data)
     if b"ALPH" not in sa or sa.get(b"ALPH") != so.get(b"ALPH") or sa.get(b"VP8 ") != so.get(b"VP8 ") or len(b) > len(data):
         return False
@@ -235,7 +236,9 @@ def worker(args):
         if differs and feat_ok and partition_starts_with_ff(b):
             hist["known_ff_first_byte"] = hist.get("known_ff_first_byte", 0) + 1
             ok += 1
-        elif differs and feat_ok and s_emu != s_ref and damaged_in_both_chunks(R, b, data, s_ref, s_emu):
+        elif differs and feat_ok and s_emu != s_ref and not (variant & 64) and damaged_in_both_chunks(R, b, data, s_ref, s_emu):
+            # only the older parsers (debug paths) keep this class: the fp parser records the failing row and the rule of
+            # vp8_dev.h:vp8b_vp8_failure_first picks the status the reference reports
             hist["known_both_chunks_damaged"] = hist.get("known_both_chunks_damaged", 0) + 1
             ok += 1
         elif differs and feat_ok and s_emu == 4 and (f["format"] == 2 or b"ALPH" in chunk_spans(b)):

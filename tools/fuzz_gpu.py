@@ -60,8 +60,6 @@ def main():
                 continue
             if sf == 0 and F.partition_starts_with_ff(b):
                 hist["known_ff_first_byte"] = hist.get("known_ff_first_byte", 0) + 1
-            elif sf == 0 and s_gpu != s_ref and F.damaged_in_both_chunks(R, b, data, s_ref, s_gpu):
-                hist["known_both_chunks_damaged"] = hist.get("known_both_chunks_damaged", 0) + 1
             elif sf == 0 and s_gpu == 4 and (f["format"] == 2 or b"ALPH" in F.chunk_spans(b)):
                 hist["known_vp8l_limit"] = hist.get("known_vp8l_limit", 0) + 1
             else:
