@@ -82,7 +82,13 @@ typedef struct FrameHdr {
   int32_t fail_row;             // where the reference's row loop (vp8_dec.c:646-674) would meet this frame's failure:
                                 // VP8B_FAIL_NONE, VP8B_FAIL_HEADERS (before any row), or the macroblock row whose intra
                                 // modes (K1) or tokens (K2, the smallest over the partitions) ran out of data
+  int32_t modes_status;         // intra modes that ran out of data at a row r > 0: K1 leaves status OK, rows = r and the
+                                // failure here, so that K2 still parses the rows above (a token failure there comes first);
+                                // every later stage treats the frame as lost (vp8b_frame_lost)
+  int32_t all_rows;             // `rows` before K1 lowered it
 } FrameHdr;
+#define vp8b_frame_lost(h) ((h)->status != VP8B_OK || (h)->modes_status != VP8B_OK)
+#define vp8b_frame_status(h) ((h)->status != VP8B_OK ? (h)->status : (h)->modes_status)
 #define VP8B_FAIL_NONE 0x7fffffff
 #define VP8B_FAIL_HEADERS (-1)
 

@@ -59,6 +59,13 @@ __global__ void __launch_bounds__(32 * MODES_WARPS, 1) k_parse_modes(const uint8
   int fail_row = st == VP8B_OK ? VP8B_FAIL_NONE : VP8B_FAIL_HEADERS;
   if (st == VP8B_OK) st = parse_intra_modes(br, im, h, top_modes_all + (size_t)warp * max_mb_w, bprob, mbinfo + 4 * (size_t)im.mb_base, &fail_row);
   h->fail_row = fail_row;
+  h->modes_status = VP8B_OK;
+  h->all_rows = h->rows;
+  if (st != VP8B_OK && fail_row > 0 && fail_row != VP8B_FAIL_NONE) {   // see FrameHdr::modes_status
+    h->modes_status = st;
+    h->rows = fail_row;
+    st = VP8B_OK;
+  }
   h->status = st;
 }
 
@@ -413,10 +420,7 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_fp(const uint8_t* _
   int have = lane < lpw && j < ipb * P && g < count;
   const int img = have ? ids[g] : 0;
   FrameHdr* h = &hdrs[img];
-  // An image whose intra modes ran out of data at macroblock row r > 0 still gets the tokens of the rows before it parsed:
-  // the reference would meet a token failure there first (fail_row, vp8_dev.h:vp8b_vp8_failure_first).
-  const int modes_failed_at = (have && h->status == VP8B_NOT_ENOUGH_DATA && h->fail_row > 0 && h->fail_row != VP8B_FAIL_NONE) ? h->fail_row : 0;
-  if (have && !((h->status == VP8B_OK || modes_failed_at > 0) && h->num_parts == P)) {   // header failed (or, never expected, the host pre-scan disagreed)
+  if (have && !(h->status == VP8B_OK && h->num_parts == P)) {   // header failed (or, never expected, the host pre-scan disagreed)
     if (part == 0 && h->status == VP8B_OK) h->status = VP8B_BITSTREAM_ERROR;
     have = 0;
   }
@@ -431,9 +435,8 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_fp(const uint8_t* _
   c.mbinfo = mbinfo + 4 * (size_t)im.mb_base;
   c.mbtok = mbtok + (size_t)im.mb_base;
   c.tokens = tokens + (size_t)im.mb_base * TF_TOKENS_PER_MB;
-  c.mb_w = im.mb_w; c.rows = have ? (modes_failed_at > 0 && modes_failed_at < h->rows ? modes_failed_at : h->rows) : 0; c.P = P; c.part = part; c.use_skip = h->use_skip;
+  c.mb_w = im.mb_w; c.rows = have ? h->rows : 0; c.P = P; c.part = part; c.use_skip = h->use_skip;
   c.ctx_stride = ctx_stride;
-  c.fail_row = &h->fail_row;
   if (part >= c.rows) have = 0;
   asm volatile("" : "+r"(c.P), "+r"(c.ctx_stride), "+r"(c.mb_w), "+l"(c.mbinfo), "+l"(c.tokens), "+l"(c.mbtok));
   __builtin_assume(__isGlobal(c.mbinfo));
@@ -473,14 +476,33 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_fp(const uint8_t* _
 // ---------------------------------------------------------------------------------------------------------
 #define RECON_WARPS 8
 
-__global__ void __launch_bounds__(32 * RECON_WARPS) k_reconstruct(const ImgDesc* __restrict__ imgs, const FrameHdr* __restrict__ hdrs,
+__global__ void __launch_bounds__(32 * RECON_WARPS) k_reconstruct(const ImgDesc* __restrict__ imgs, FrameHdr* hdrs,
                                                                   uint32_t* mbinfo, const int16_t* __restrict__ coeffs,
                                                                   uint8_t* yuv, int first, int row_begin, int row_end,
                                                                   uint8_t* band_ctx, int band_ctx_stride,
                                                                   const uint32_t* __restrict__ tokens, const MbTok* __restrict__ mbtok) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int img = first + blockIdx.x;
-  if (hdrs[img].status != VP8B_OK) return;
+  if (vp8b_frame_lost(&hdrs[img])) {
+    // Nothing to reconstruct; but a frame whose tokens ran out and which carries an ALPH chunk needs the row at which they did
+    // (FrameHdr::fail_row), and this is the last launch that still finds the wave's MbTok entries in place. tf_mb_store marked the
+    // macroblock where each partition stopped; stale marks can only sit below or to the right of a fresh one, so the smallest
+    // marked row is the answer. (Keeping the row inside the parser -- a field of TfLane, a pointer in TfCtx, two spare bytes
+    // of the shared-memory rows, or (mx, my) read back after the loops -- cost its decode loop 2-4 %: 264.7 -> 272-275 ms per
+    // 4096 full-HD images, profiles/r02p_variants.log.)
+    FrameHdr* h = &hdrs[img];
+    if (tokens != nullptr && row_begin == 0 && h->status != VP8B_OK && h->fail_row > 0 && imgs[img].alpha_size != 0) {   // K1's own failures leave fail_row <= 0
+      __shared__ int found;
+      if (threadIdx.x == 0) found = VP8B_FAIL_NONE;
+      __syncthreads();
+      const MbTok* mt = mbtok + (size_t)imgs[img].mb_base;
+      const int w = imgs[img].mb_w, n = w * h->rows;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) if (mt[i].count == TF_MBTOK_FAILED) atomicMin(&found, i / w);
+      __syncthreads();
+      if (threadIdx.x == 0 && found < h->fail_row) h->fail_row = found;
+    }
+    return;
+  }
   const ImgDesc im = imgs[img];
   const int mb_w = im.mb_w, mb_h = hdrs[img].rows;
   // macroblock rows [r0, r1) of this launch (row bands: the top-neighbour pixels of row r0 come from band_ctx, where the
@@ -542,7 +564,7 @@ __global__ void __launch_bounds__(32 * FILTER_WARPS) k_loop_filter(const ImgDesc
   // options.dithering_strength: the planned offsets (dither_plan_image) go onto a macroblock's chroma once its own row
   // has finished with it, i.e. after the macroblock to its right has been filtered, and before the row below may touch it
   const int dithering = dither_plane != nullptr && (h->dither[0] | h->dither[1] | h->dither[2] | h->dither[3]) != 0;
-  if (h->status != VP8B_OK || (h->filter_type == 0 && !dithering)) return;
+  if (vp8b_frame_lost(h) || (h->filter_type == 0 && !dithering)) return;
   const ImgDesc im = imgs[img];
   const int mb_w = im.mb_w, mb_h = h->rows;
   const int filter_type = h->filter_type;
@@ -596,7 +618,7 @@ __global__ void __launch_bounds__(32) k_dither_plan(const ImgDesc* __restrict__ 
   const int k = blockIdx.x * 32 + threadIdx.x;
   if (k >= count) return;
   const int img = first + k;
-  if (hdrs[img].status != VP8B_OK) return;
+  if (vp8b_frame_lost(&hdrs[img])) return;
   const ImgDesc im = imgs[img];
   dither_plan_image(im, &hdrs[img], mbinfo + 4 * (size_t)im.mb_base, dither_plane + (size_t)im.mb_base * 128, tabs[threadIdx.x]);
 }
@@ -609,7 +631,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 5) k_emit(const ImgDesc* __restr
                                                        uint8_t* out, int first, int blocks_per_image, int pair_begin, int pair_end) {
   const int img = first + blockIdx.x / blocks_per_image;
   const int chunk = blockIdx.x % blocks_per_image;
-  if (hdrs[img].status != VP8B_OK) return;
+  if (vp8b_frame_lost(&hdrs[img])) return;
   const ImgDesc im = imgs[img];
   if (im.dst_w != 0) return;   // options.use_scaling: k_emit_scaled
   const size_t nmb = (size_t)im.mb_w * im.mb_h;
@@ -646,7 +668,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit_scaled(const ImgDesc* __r
                                                               uint8_t* out, int first, int blocks_per_image) {
   const int img = first + blockIdx.x / blocks_per_image;
   const int chunk = blockIdx.x % blocks_per_image;
-  if (hdrs[img].status != VP8B_OK) return;
+  if (vp8b_frame_lost(&hdrs[img])) return;
   const ImgDesc im = imgs[img];
   if (im.dst_w == 0) return;
   const size_t nmb = (size_t)im.mb_w * im.mb_h;
@@ -665,9 +687,9 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit_scaled(const ImgDesc* __r
 __global__ void __launch_bounds__(256) k_collect_status(const FrameHdr* __restrict__ hdrs, int* host_statuses, int count) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < count) {
-    host_statuses[3 * k] = hdrs[k].status;
+    host_statuses[3 * k] = vp8b_frame_status(&hdrs[k]);
     host_statuses[3 * k + 1] = hdrs[k].fail_row;
-    host_statuses[3 * k + 2] = (hdrs[k].rows << 8) | hdrs[k].filter_type;
+    host_statuses[3 * k + 2] = (hdrs[k].all_rows << 8) | hdrs[k].filter_type;
   }
 }
 
@@ -899,7 +921,7 @@ extern "C" void vp8k_parse_tokens(cudaStream_t s, const uint8_t* arena, const Im
   launch_tokens_fsm(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, max_mb_w);
 }
 
-extern "C" void vp8k_reconstruct(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, uint32_t* mbinfo, const int16_t* coeffs,
+extern "C" void vp8k_reconstruct(cudaStream_t s, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo, const int16_t* coeffs,
                                  uint8_t* yuv, int first, int count, int max_mb_w, int max_mb_h, int row_begin, int row_end,
                                  uint8_t* band_ctx, const uint32_t* tokens, const void* mbtok) {
   k_reconstruct<<<count, 32 * RECON_WARPS, recon_smem_bytes(max_mb_w, max_mb_h), s>>>(imgs, hdrs, mbinfo, coeffs, yuv, first, row_begin,

@@ -33,7 +33,7 @@ void vp8k_parse_tokens_band(cudaStream_t s, const uint8_t* arena, const ImgDesc*
 // `tokens` != NULL: the levels come from the token stream (VP8B_TOKENS_PER_MB words reserved per macroblock) and `mbtok`
 // (two words per macroblock: first token inside the image's area, count), as vp8k_parse_tokens_stream left them; else
 // from the dense plane `coeffs` of the older parsers.
-void vp8k_reconstruct(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, uint32_t* mbinfo, const int16_t* coeffs,
+void vp8k_reconstruct(cudaStream_t s, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo, const int16_t* coeffs,
                       uint8_t* yuv, int first, int count, int max_mb_w, int max_mb_h, int row_begin, int row_end, uint8_t* band_ctx,
                       const uint32_t* tokens, const void* mbtok);
 // The default token parser (vp8_tokens_fp.h): lockstep lanes, fp32 boolean decoder, one 32-bit token per non-zero level.

@@ -342,6 +342,7 @@ TK_FN int fd_bit(FpDec& d, uint32_t prob_bits, const FpConst& k) {
 #define TF_TOK_POS(t) (((t) >> 6) & 15u)
 #define TF_TOK_MAG(t) (((t) >> TF_ADD_SHIFT) & 0xfffu)
 #define TF_TOKENS_PER_MB VP8B_TOKENS_PER_MB
+#define TF_MBTOK_FAILED 0x80000000u   // MbTok::count of the macroblock at which a partition ran out of data
 
 // Lane phases as in vp8_tokens_lockstep.h.
 #define TF_RUN 0
@@ -396,7 +397,6 @@ struct TfCtx {
   MbTok* mbtok;           // this image's MbTok
   uint32_t* tokens;       // this image's token area (TF_TOKENS_PER_MB per macroblock)
   int mb_w, rows, P, part, use_skip, ctx_stride;
-  int* fail_row;          // FrameHdr::fail_row of the image
   FpConst k;
 };
 
@@ -483,18 +483,18 @@ TK_FN void tf_mb_store(TfLane& L, const TfCtx& c, uint32_t nzy, uint32_t w3) {
   if (++L.mx == mb_w) { L.mx = 0; L.my += P; }
   if (L.eofs) {
     // Ran past the end of the partition: the image is lost (vp8_dec.c:651-659); release whoever waits on us. The row goes on
-    // record: with a damaged ALPH chunk as well, the reference reports whichever failure its row loop meets first.
-    if (L.status == VP8B_OK) {
-      const int row = (int)(idx / (size_t)mb_w);
-#if defined(__CUDACC__) && !defined(VP8_EMU)
-      atomicMin(c.fail_row, row);
-#else
-      if (row < *c.fail_row) *c.fail_row = row;
-#endif
-    }
+    // record (tf_failed_row): with a damaged ALPH chunk as well, the reference reports the failure its row loop meets first.
+    c.mbtok[idx].count = TF_MBTOK_FAILED;
     L.status = VP8B_NOT_ENOUGH_DATA;
     if (MULTI) { TK_FENCE(); c.progress[c.part] = 0x7fffffff; }
   } else if (MULTI) { TK_FENCE(); c.progress[c.part] = L.done_mbs; }
+}
+
+// The macroblock row at which a frame's tokens ran out of data (FrameHdr::fail_row), found afterwards from the marks
+// tf_mb_store leaves (TF_MBTOK_FAILED): k_reconstruct does this block-wide on the device, the emulation with this loop.
+TK_FN int tf_find_failed_row(const MbTok* mbtok, int mb_w, int rows) {
+  for (int i = 0; i < mb_w * rows; ++i) if (mbtok[i].count == TF_MBTOK_FAILED) return i / mb_w;
+  return VP8B_FAIL_NONE;
 }
 
 // Leaves the lane either with a block set up (returns 1), waiting for the row above (returns 0, L.waiting = 1) or

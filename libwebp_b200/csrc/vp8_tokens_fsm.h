@@ -37,6 +37,8 @@ TK_FN void tk_lds_v2(tk_saddr a, uint32_t& x, uint32_t& y) { asm("ld.shared.v2.u
 // ring words and the ring protocol words change under the reader's feet: volatile accesses
 TK_FN uint32_t tk_ldsv_u32(tk_saddr a) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 TK_FN void tk_stsv_u32(tk_saddr a, uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+TK_FN uint32_t tk_ldsv_u8(tk_saddr a) { uint32_t v; asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+TK_FN void tk_stsv_u8(tk_saddr a, uint32_t v) { asm volatile("st.volatile.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 // loads that must stay where they are written (look-ahead loads: the compiler would otherwise sink them under the
 // condition that selects their result)
 TK_FN uint32_t tk_lds_u8_pinned(tk_saddr a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
@@ -63,6 +65,8 @@ TK_FN uint32_t tk_lds_u32(tk_saddr a) { return *(const uint32_t*)a; }
 TK_FN void tk_lds_v2(tk_saddr a, uint32_t& x, uint32_t& y) { x = ((const uint32_t*)a)[0]; y = ((const uint32_t*)a)[1]; }
 TK_FN uint32_t tk_ldsv_u32(tk_saddr a) { return *(volatile const uint32_t*)a; }
 TK_FN void tk_stsv_u32(tk_saddr a, uint32_t v) { *(volatile uint32_t*)a = v; }
+TK_FN uint32_t tk_ldsv_u8(tk_saddr a) { return *(volatile const uint8_t*)a; }
+TK_FN void tk_stsv_u8(tk_saddr a, uint32_t v) { *(volatile uint8_t*)a = (uint8_t)v; }
 TK_FN uint32_t tk_lds_u8_pinned(tk_saddr a) { return *(const uint8_t*)a; }
 TK_FN void tk_lds_v2_pinned(tk_saddr a, uint32_t& x, uint32_t& y) { x = ((const uint32_t*)a)[0]; y = ((const uint32_t*)a)[1]; }
 TK_FN uint32_t tk_shr_clamp(uint32_t w, int n) { return n >= 32 ? 0u : (w >> n); }

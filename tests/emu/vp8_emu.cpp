@@ -202,7 +202,6 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
       cc.topctx = topctx.data(); cc.progress = progress.data();
       cc.mbinfo = mbinfo.data(); cc.mbtok = mbtok.data(); cc.tokens = tokens.data();
       cc.mb_w = mb_w; cc.rows = rows; cc.P = P; cc.part = p; cc.use_skip = hdr.use_skip; cc.ctx_stride = mb_w;
-      cc.fail_row = &hdr.fail_row;
       tf_lane_init(lanes[p], cc, frame, &hdr);
       live[p] = 1;
     }
@@ -220,6 +219,10 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
       }
     }
     for (int p = 0; p < P && p < rows; ++p) if (lanes[p].status != VP8B_OK) hdr.status = lanes[p].status;
+    if (hdr.status != VP8B_OK) {   // like the prologue of k_reconstruct
+      const int row = tf_find_failed_row(mbtok.data(), mb_w, rows);
+      if (row < hdr.fail_row) hdr.fail_row = row;
+    }
   } else if (variant & 8) {   // lockstep parser: one lane per partition, one decode per lane per round
     const int P = hdr.num_parts;
     std::vector<uint8_t> imgmem(TL_IMG_BYTES + 16 + 128);   // the look-ahead loads run up to 63 bytes past the rows

