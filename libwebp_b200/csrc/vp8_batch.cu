@@ -352,6 +352,7 @@ struct Wave {
   size_t mbs = 0;
   int max_mb_w = 0, max_mb_h = 0, max_units = 0;
   int max_scaled_items = 0;   // images with options.use_scaling: work items of vp8k_emit_scaled (0 = none in this wave)
+  int literal = 0;            // images flagged VP8B_FLAG_LITERAL_READER: vp8k_parse_literal goes over the wave
   int ids_off[4] = { 0, 0, 0, 0 }, ids_cnt[4] = { 0, 0, 0, 0 };   // per log2(P) slice of the ids array
 };
 
@@ -570,6 +571,9 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
     d.dither_f = (uint8_t)(ds < 0 ? 0 : ds > 100 ? 255 : ds * 255 / 100);
     if (d.dither_f != 0) b->any_dither = true;
     d.num_parts = c.is_lossless ? 0 : (uint8_t)vp8b_prescan_partitions(b->items[i].data + c.frame_offset + 10, c.part0_size);
+    // a partition that starts with 0xFF (never encoded): the reference's reader leaves its range, see vp8_literal.h
+    if (!c.is_lossless && c.frame_size >= 10 &&
+        vp8b_partition_starts_with_ff(b->items[i].data + c.frame_offset + 10, c.part0_size, c.frame_size - 10, d.num_parts)) d.flags |= VP8B_FLAG_LITERAL_READER;
     d.alpha_plane = VP8B_NO_ALPHA;
     if (c.is_lossless) {   // the VP8L passes find the bitstream through the alpha fields; no VP8 kernel touches the image
       d.flags |= VP8B_FLAG_LOSSLESS;
@@ -652,6 +656,7 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
       b->imgs[k].mb_base = (uint32_t)w.mbs;
       w.mbs += mbs; w.count++;
       w.max_mb_w = std::max(w.max_mb_w, (int)b->imgs[k].mb_w);
+      if (b->imgs[k].flags & VP8B_FLAG_LITERAL_READER) ++w.literal;
       w.max_mb_h = std::max(w.max_mb_h, (int)b->imgs[k].mb_h);
       const ImgDesc& d = b->imgs[k];
       // work items of the output kernel (must match k_emit / emit_uses_pairs in vp8_pixel_core.h)
@@ -1031,6 +1036,7 @@ static bool batch_enqueue(WebPBatch* b, bool download) {
       else vp8k_parse_tokens(s, arena, imgs, hdrs, mbinfo, coeffs, (const int*)b->d_ids.p + w.ids_off[lg], w.ids_cnt[lg], 1 << lg, w.max_mb_w);
       ++launches;
     }
+    if (stream_tokens && w.literal > 0) { vp8k_parse_literal(s, arena, imgs, hdrs, mbinfo, tokens, mbtok, w.first, w.count, w.max_mb_w); ++launches; }
     // ---- row bands: see vp8_kernels.h. The wave qualifies when every image has one token partition, the lockstep
     // parser takes the launch, and every image goes through the row-pair output path unflipped and uncropped.
     int bands = 1;

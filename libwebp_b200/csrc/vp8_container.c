@@ -187,3 +187,32 @@ int vp8b_prescan_partitions(const uint8_t* part0, size_t part0_size) {
   }
   return 1 << mb_lit(&d, 2);
 }
+
+/* ParsePartitions (vp8_dec.c:188-222): the size table (three bytes per partition but the last) follows the first partition,
+   sizes are clipped to what is left. Byte 0xFF at the head of a partition is what no encoder writes and what makes the
+   reference's reader leave its range (vp8_parse_core.h:RefBits). `rest` = bytes of the frame after its 10-byte header. */
+int vp8b_partition_starts_with_ff(const uint8_t* part0, size_t part0_size, size_t rest, int num_parts) {
+  const uint8_t* sz;
+  const uint8_t* start;
+  size_t left;
+  int p;
+  if (part0_size > 0 && part0_size <= rest && part0[0] == 0xFF) return 1;
+  if (part0_size > rest) return 0;
+  sz = part0 + part0_size;
+  left = rest - part0_size;
+  if (left < 3u * (size_t)(num_parts - 1)) return 0;
+  start = sz + 3 * (num_parts - 1);
+  left -= 3u * (size_t)(num_parts - 1);
+  for (p = 0; p < num_parts; ++p) {
+    size_t psize = left;
+    if (p < num_parts - 1) {
+      psize = (size_t)sz[0] | ((size_t)sz[1] << 8) | ((size_t)sz[2] << 16);
+      if (psize > left) psize = left;
+      sz += 3;
+    }
+    if (psize > 0 && start[0] == 0xFF) return 1;
+    start += psize;
+    left -= psize;
+  }
+  return 0;
+}

@@ -33,6 +33,7 @@
 #define VP8B_FLAG_BYPASS_FILTER 1
 #define VP8B_FLAG_NO_FANCY 2
 #define VP8B_FLAG_FLIP 4     // options.flip: output rows bottom-up (WebPFlipBuffer, buffer_dec.c:152-175)
+#define VP8B_FLAG_LITERAL_READER 16   // some partition starts with byte 0xFF: parsed again by k_parse_literal (vp8_parse_core.h:RefBits)
 #define VP8B_FLAG_LOSSLESS 8 // a whole VP8L picture: no macroblocks (mb_w = mb_h = 0, the VP8 kernels pass it by); alpha_in /
                              // alpha_size locate the VP8L bitstream and the picture leaves through vp8l_lossless_core.h
 

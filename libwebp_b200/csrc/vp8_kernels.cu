@@ -31,6 +31,7 @@
 #include "vp8_tokens_fsm.h"
 #include "vp8_tokens_lockstep.h"
 #include "vp8_tokens_fp.h"
+#include "vp8_literal.h"
 #define AL_BLOCK_SYNC() __syncthreads()
 #include "vp8l_alpha_core.h"
 #include "vp8l_lossless_core.h"
@@ -395,6 +396,9 @@ __host__ __device__ static inline TfLayout tf_layout(int P, int ipb, int ctx_str
   return t;
 }
 
+#ifndef TF_GROUPS_PER_VOTE
+#define TF_GROUPS_PER_VOTE 8   // groups of four decodes between two votes on "any lane still alive"
+#endif
 template <int RING>
 __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_fp(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
                                                             FrameHdr* hdrs, uint32_t* mbinfo, uint32_t* tokens, MbTok* mbtok,
@@ -455,22 +459,42 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_fp(const uint8_t* _
   if (flat) {
     // Straight-line groups of four decodes with one event point (vp8_tokens_fp.h:tf_group_flat): the default.
     if (P > 1) {
-      while (__any_sync(0xffffffffu, L.alive)) { for (int r = r0; r < 8; ++r) tf_group_flat<1, RING>(L, c); }
+      while (__any_sync(0xffffffffu, L.alive)) { for (int r = r0; r < TF_GROUPS_PER_VOTE; ++r) tf_group_flat<1, RING>(L, c); }
     } else {
-      while (__any_sync(0xffffffffu, L.alive)) { for (int r = r0; r < 8; ++r) tf_group_flat<0, RING>(L, c); }
+      while (__any_sync(0xffffffffu, L.alive)) { for (int r = r0; r < TF_GROUPS_PER_VOTE; ++r) tf_group_flat<0, RING>(L, c); }
     }
   } else if (P > 1) {
     while (__any_sync(0xffffffffu, L.alive)) {
-      for (int r = r0; r < 8; ++r) tf_group_inline<1, RING>(L, c);
+      for (int r = r0; r < TF_GROUPS_PER_VOTE; ++r) tf_group_inline<1, RING>(L, c);
     }
   } else {
     if (have && !tf_mb_next<0>(L, c)) tf_lane_park(L, c);
     while (__any_sync(0xffffffffu, L.alive)) {
-      for (int r = r0; r < 8; ++r) tf_group_inline<0, RING>(L, c);
+      for (int r = r0; r < TF_GROUPS_PER_VOTE; ++r) tf_group_inline<0, RING>(L, c);
     }
   }
   if (have && L.status != VP8B_OK) h->status = L.status;
   if (L.sink == 0xffffffffu) h->status = VP8B_BITSTREAM_ERROR;   // never true (an XOR of bytes): keeps TfLane::sink alive
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Images flagged VP8B_FLAG_LITERAL_READER, after K1 and the token parser have been over them: parsed once more, header to last
+// token, by lane 0 of a warp with the reference's reader (vp8_literal.h), overwriting what those kernels left. One block of
+// one warp per image of the wave; launched only when the wave holds such an image.
+__global__ void __launch_bounds__(32) k_parse_literal(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs, FrameHdr* hdrs,
+                                                      uint32_t* mbinfo, uint32_t* tokens, MbTok* mbtok, int first) {
+  extern __shared__ __align__(16) uint8_t lit_scratch[];
+  __shared__ uint8_t bprob[900];
+  const int img = first + blockIdx.x;
+  const ImgDesc im = imgs[img];
+  if (!(im.flags & VP8B_FLAG_LITERAL_READER) || (im.flags & VP8B_FLAG_LOSSLESS)) return;
+  for (int k = threadIdx.x; k < 900; k += 32) bprob[k] = kVp8BModeProba[k];
+  for (int k = threadIdx.x; k < VP8B_COEFFS_PER_MB; k += 32) ((int16_t*)(lit_scratch + LIT_LEVELS))[k] = 0;
+  __syncwarp();
+  if (threadIdx.x == 0) {
+    parse_image_literal(arena + im.in_off, im, &hdrs[img], bprob, mbinfo + 4 * (size_t)im.mb_base,
+                        tokens + (size_t)im.mb_base * TF_TOKENS_PER_MB, mbtok + (size_t)im.mb_base, lit_scratch);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -491,7 +515,8 @@ __global__ void __launch_bounds__(32 * RECON_WARPS) k_reconstruct(const ImgDesc*
     // of the shared-memory rows, or (mx, my) read back after the loops -- cost its decode loop 2-4 %: 264.7 -> 272-275 ms per
     // 4096 full-HD images, profiles/r02p_variants.log.)
     FrameHdr* h = &hdrs[img];
-    if (tokens != nullptr && row_begin == 0 && h->status != VP8B_OK && h->fail_row > 0 && imgs[img].alpha_size != 0) {   // K1's own failures leave fail_row <= 0
+    if (tokens != nullptr && row_begin == 0 && h->status != VP8B_OK && h->fail_row > 0 && imgs[img].alpha_size != 0 &&
+        !(imgs[img].flags & VP8B_FLAG_LITERAL_READER)) {   // (k_parse_literal leaves the row itself)   // K1's own failures leave fail_row <= 0
       __shared__ int found;
       if (threadIdx.x == 0) found = VP8B_FAIL_NONE;
       __syncthreads();
@@ -919,6 +944,11 @@ extern "C" void vp8k_parse_tokens(cudaStream_t s, const uint8_t* arena, const Im
     return;
   }
   launch_tokens_fsm(s, arena, imgs, hdrs, mbinfo, coeffs, ids, count, P, max_mb_w);
+}
+
+extern "C" void vp8k_parse_literal(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,
+                                   uint32_t* tokens, void* mbtok, int first, int count, int max_mb_w) {
+  k_parse_literal<<<count, 32, LIT_SCRATCH_BYTES(max_mb_w), s>>>(arena, imgs, hdrs, mbinfo, tokens, (MbTok*)mbtok, first);
 }
 
 extern "C" void vp8k_reconstruct(cudaStream_t s, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo, const int16_t* coeffs,

@@ -36,6 +36,10 @@ void vp8k_parse_tokens_band(cudaStream_t s, const uint8_t* arena, const ImgDesc*
 void vp8k_reconstruct(cudaStream_t s, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo, const int16_t* coeffs,
                       uint8_t* yuv, int first, int count, int max_mb_w, int max_mb_h, int row_begin, int row_end, uint8_t* band_ctx,
                       const uint32_t* tokens, const void* mbtok);
+// Images flagged VP8B_FLAG_LITERAL_READER (a partition that starts with 0xFF), parsed once more with the reference's reader taken
+// literally (vp8_literal.h); after vp8k_parse_modes and vp8k_parse_tokens_stream of the wave, before vp8k_reconstruct.
+void vp8k_parse_literal(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,
+                        uint32_t* tokens, void* mbtok, int first, int count, int max_mb_w);
 // The default token parser (vp8_tokens_fp.h): lockstep lanes, fp32 boolean decoder, one 32-bit token per non-zero level.
 int vp8k_tokens_use_stream(void);
 void vp8k_parse_tokens_stream(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,

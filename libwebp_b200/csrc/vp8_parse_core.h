@@ -19,11 +19,13 @@
 
 #if defined(__CUDACC__) && !defined(VP8_EMU)
 #define VP8_FN __device__ __forceinline__
+#define VP8_MFN __device__ __forceinline__   // member functions
 #define VP8_TABLE static __constant__ const
 #define VP8_CLZ(x) __clz((int)(x))
 #define VP8_BSWAP(x) __byte_perm((x), 0, 0x0123)
 #else
 #define VP8_FN static inline
+#define VP8_MFN inline
 #define VP8_TABLE static const
 #ifndef VP8_EMU_VECTORS
 #define VP8_EMU_VECTORS
@@ -176,12 +178,96 @@ VP8_FN int bd_signed(BoolDec& d, int n) {
   return bd_bit(d, 0x80) ? -v : v;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The reference's reader taken literally, for the one case where the window above is not equivalent: a partition whose
+// first byte is 0xFF. That byte breaks the decoder's invariant value < range from the first bit on (no encoder writes it),
+// and what the reference then decodes depends on the mechanics of its reader (bit_reader_utils.c:26-45,105-119,
+// bit_reader_inl_utils.h:58-136 with BITS = 56): seven bytes enter a 64-bit value at a time while eight or more are left (so
+// whatever overflowed above the low eight bits is dropped at that moment, not earlier), single bytes after that, one zero byte
+// past the end raises eof_; the compare is done on the value cut to 32 bits, and the sign of a coefficient comes from the
+// sign bit of a 32-bit difference. Slow (64-bit arithmetic, a byte at a time): only the images the host flags
+// (VP8B_FLAG_LITERAL_READER) are parsed with it, by k_parse_literal. Same function names as BoolDec, so the parsers below
+// are written once for both.
+struct RefBits {
+  const uint8_t* buf;
+  const uint8_t* end;
+  const uint8_t* wide_end;   // seven bytes at once while buf is below this (eight readable bytes left)
+  uint64_t value;
+  uint32_t range;            // range - 1, as the reference keeps it
+  int bits;                  // position of the bit after the eight in use; negative: load before the next decode
+  int eof;
+};
+
+VP8_FN void rb_load(RefBits& d) {
+  if (d.buf < d.wide_end) {
+    uint64_t w = 0;
+    for (int k = 0; k < 7; ++k) w = (w << 8) | d.buf[k];
+    d.buf += 7;
+    d.value = w | (d.value << 56);
+    d.bits += 56;
+  } else if (d.buf < d.end) {
+    d.value = (uint64_t)(*d.buf++) | (d.value << 8);
+    d.bits += 8;
+  } else if (!d.eof) {
+    d.value <<= 8;
+    d.bits += 8;
+    d.eof = 1;
+  } else {
+    d.bits = 0;
+  }
+}
+
+VP8_FN void bd_init(RefBits& d, const uint8_t* start, uint32_t size) {
+  d.buf = start; d.end = start + size;
+  d.wide_end = size >= 8 ? start + size - 7 : start;
+  d.value = 0; d.range = 254; d.bits = -8; d.eof = 0;
+  rb_load(d);
+}
+VP8_FN int bd_eof(const RefBits& d) { return d.eof; }
+VP8_FN void bd_fill(RefBits&) {}
+VP8_FN int bd_bit(RefBits& d, uint32_t prob) {
+  uint32_t range = d.range;
+  if (d.bits < 0) rb_load(d);
+  const int pos = d.bits;
+  const uint32_t split = (range * prob) >> 8;
+  const uint32_t v32 = (uint32_t)(d.value >> pos);   // cut to 32 bits: part of the behaviour
+  const int bit = v32 > split;
+  if (bit) { range -= split; d.value -= (uint64_t)(split + 1) << pos; } else { range = split + 1; }
+  const int shift = VP8_CLZ(range) - 24;             // range in [1, 255] here
+  d.bits -= shift;
+  d.range = (range << shift) - 1;
+  return bit;
+}
+VP8_FN int bd_bit_nofill(RefBits& d, uint32_t prob) { return bd_bit(d, prob); }
+// the sign of a coefficient (VP8GetSigned): not the same as bd_bit(d, 128) once the value has left its range
+VP8_FN int bd_half_nofill(RefBits& d) {
+  if (d.bits < 0) rb_load(d);
+  const int pos = d.bits;
+  const uint32_t split = d.range >> 1;
+  const uint32_t v32 = (uint32_t)(d.value >> pos);
+  const uint32_t mask = (uint32_t)((int32_t)(split - v32) >> 31);   // all ones: negative
+  d.bits -= 1;
+  d.range = (d.range + mask) | 1u;
+  d.value -= (uint64_t)((split + 1) & mask) << pos;
+  return (int)(mask & 1u);
+}
+VP8_FN uint32_t bd_value(RefBits& d, int n) {
+  uint32_t v = 0;
+  while (n-- > 0) v |= (uint32_t)bd_bit(d, 0x80) << n;
+  return v;
+}
+VP8_FN int bd_signed(RefBits& d, int n) {
+  const int v = (int)bd_value(d, n);
+  return bd_bit(d, 0x80) ? -v : v;
+}
+
 VP8_FN int clampi(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }
 
 // ---------------------------------------------------------------------------------------------------------
 // Frame header (partition 0 prefix). `frame` points at the 3-byte frame tag. Fills *h; returns the status.
 // The host already validated tag, signature, dimensions and part0_size <= available (vp8_container.c).
-VP8_FN int parse_frame_header(BoolDec& br, const uint8_t* frame, const ImgDesc& im, FrameHdr* h) {
+template <class BD>
+VP8_FN int parse_frame_header(BD& br, const uint8_t* frame, const ImgDesc& im, FrameHdr* h) {
   const uint8_t* buf = frame + 10 + im.part0_size;         // first byte after partition 0
   const uint32_t size = im.vp8_size - 10 - im.part0_size;  // bytes left for the token partitions
   int seg_quant[4] = { 0, 0, 0, 0 }, seg_filter[4] = { 0, 0, 0, 0 };
@@ -308,7 +394,8 @@ VP8_FN int parse_frame_header(BoolDec& br, const uint8_t* frame, const ImgDesc& 
 // ([top mode][left mode][9]) staged in shared memory by the kernel (a pointer to the table itself elsewhere).
 // Writes MbInfo x,y,w. Returns VP8B_OK or VP8B_NOT_ENOUGH_DATA (checked once per macroblock row, like
 // vp8_dec.c:651-654). Sub-block mode tree of tree_dec.c:28-36 written out as straight-line decisions.
-VP8_FN uint32_t parse_bmode(BoolDec& d, const uint8_t* p) {
+template <class BD>
+VP8_FN uint32_t parse_bmode(BD& d, const uint8_t* p) {
   bd_fill(d);
   if (!bd_bit_nofill(d, p[0])) return M_DC;
   if (!bd_bit_nofill(d, p[1])) return M_TM;
@@ -324,7 +411,8 @@ VP8_FN uint32_t parse_bmode(BoolDec& d, const uint8_t* p) {
   return bd_bit_nofill(d, p[8]) ? M_HU : M_HD;
 }
 
-VP8_FN int parse_intra_modes(BoolDec& br, const ImgDesc& im, const FrameHdr* h, uint32_t* top, const uint8_t* bprob,
+template <class BD>
+VP8_FN int parse_intra_modes(BD& br, const ImgDesc& im, const FrameHdr* h, uint32_t* top, const uint8_t* bprob,
                              uint32_t* mbinfo /* 4 words per MB */, int* fail_row = 0) {
   const int mb_w = im.mb_w, mb_h = h->rows;
   const int update_map = h->update_map, use_skip = h->use_skip, skip_p = h->skip_p;
@@ -378,7 +466,8 @@ VP8_FN int parse_intra_modes(BoolDec& br, const ImgDesc& im, const FrameHdr* h, 
 // ---------------------------------------------------------------------------------------------------------
 // Coefficient tokens. Window discipline: bd_fill() leaves > 32 valid bits and a decode uses at most 7, so up
 // to four bd_*_nofill() calls may follow one bd_fill().
-VP8_FN int large_value(BoolDec& d, const uint8_t* p) {   // GetLargeValue, vp8_dec.c:411-440; sign decoded by the caller
+template <class BD>
+VP8_FN int large_value(BD& d, const uint8_t* p) {   // GetLargeValue, vp8_dec.c:411-440; sign decoded by the caller
   int v;
   bd_fill(d);
   if (!bd_bit_nofill(d, p[3])) {
@@ -419,7 +508,8 @@ VP8_FN uint8_t posprob_byte(const uint8_t* prob /* [4][8][3][11] */, int k) {
 // HBM (pre-zeroed): the decoded LEVELS in parse (zigzag) order; dequantisation and the zigzag scatter happen
 // where the coefficients are consumed (recon_macroblock). Returns nz = index of the last decoded coefficient
 // + 1 (GetCoeffs, vp8_dec.c:443-469).
-VP8_FN int parse_block(BoolDec& d, const uint8_t* tp, int ctx, int n, int16_t* out) {
+template <class BD>
+VP8_FN int parse_block(BD& d, const uint8_t* tp, int ctx, int n, int16_t* out) {
   const uint8_t* pz = tp + n * 33;       // position n, ctx 0
   const uint8_t* p = pz + ctx * 11;
   for (;;) {
@@ -473,13 +563,16 @@ VP8_TABLE uint32_t kBlockSeq[25] = {
 
 // Non-zero context of one macroblock column / row: bits 0-3 luma, 4-5 U, 6-7 V, bit 8 = Y2 (nz_dc).
 // State of one token partition of an image; it parses macroblock rows part, part+P, ... (vp8_dec.c:649-650).
-struct TokenPart {
-  BoolDec d;
+template <class BD>
+struct TokenPartT {
+  BD d;
   int done;     // macroblocks finished by this partition (published to the partition owning the next row)
   int status;   // VP8B_OK or VP8B_NOT_ENOUGH_DATA
 };
+typedef TokenPartT<BoolDec> TokenPart;
 
-VP8_FN void token_part_init(TokenPart& tp, const uint8_t* frame, const FrameHdr* h, int part) {
+template <class BD>
+VP8_FN void token_part_init(TokenPartT<BD>& tp, const uint8_t* frame, const FrameHdr* h, int part) {
   bd_init(tp.d, frame + h->part_off[part], h->part_size[part]);
   tp.done = 0;
   tp.status = VP8B_OK;
@@ -490,20 +583,28 @@ VP8_FN void token_part_init(TokenPart& tp, const uint8_t* frame, const FrameHdr*
 //   topctx    : (P+1) rows x mb_w uint16 ring of per-column contexts (shared by the image's partitions)
 //   progress  : P counters (shared); see above
 // Writes coefficients and MbInfo z / w.
-VP8_FN void parse_token_row(TokenPart& tp, const ImgDesc& im, const FrameHdr* h, int part, int my, const uint8_t* probs,
-                            uint16_t* topctx, volatile int* progress, uint32_t* mbinfo, int16_t* coeffs) {
+// SINK: what happens to a macroblock's levels once they are parsed. The default leaves them in the dense plane (800 bytes per
+// macroblock at `coeffs`); a sink with kPerMb = 1 gets every macroblock in the same 400-level buffer `coeffs` (handed over
+// all zero, to be left all zero) -- k_parse_literal turns it into the token stream there.
+struct TokDensePlane {
+  static const int kPerMb = 0;
+  VP8_MFN void mb(int, int, int16_t*) {}
+};
+template <class BD, class SINK = TokDensePlane>
+VP8_FN void parse_token_row(TokenPartT<BD>& tp, const ImgDesc& im, const FrameHdr* h, int part, int my, const uint8_t* probs,
+                            uint16_t* topctx, volatile int* progress, uint32_t* mbinfo, int16_t* coeffs, SINK sink = SINK()) {
   const int P = h->num_parts, mb_w = im.mb_w;
   const int use_skip = h->use_skip;
-  BoolDec& d = tp.d;
+  BD& d = tp.d;
   const uint16_t* trow = topctx + (size_t)((my + P) % (P + 1)) * mb_w;   // written by row my-1
   uint16_t* orow = topctx + (size_t)(my % (P + 1)) * mb_w;
   const int prev = (part + P - 1) % P;                // partition that owns row my-1
   const int prev_rows = (my - 1 - prev) / P;          // rows it finished before row my-1 (meaningful if my>0)
   uint32_t lctx = 0;
   uint32_t* info = mbinfo + 4 * ((size_t)my * mb_w);
-  int16_t* dst = coeffs + (size_t)my * mb_w * VP8B_COEFFS_PER_MB;
+  int16_t* dst = SINK::kPerMb ? coeffs : coeffs + (size_t)my * mb_w * VP8B_COEFFS_PER_MB;
   uint32_t w_next = info[3];
-  for (int mx = 0; mx < mb_w; ++mx, info += 4, dst += VP8B_COEFFS_PER_MB) {
+  for (int mx = 0; mx < mb_w; ++mx, info += 4, dst += SINK::kPerMb ? 0 : VP8B_COEFFS_PER_MB) {
     uint32_t w = w_next;
     if (mx + 1 < mb_w) w_next = info[7];   // next macroblock's flags: fetched a whole macroblock ahead of their use
     uint32_t tctx = 0;
@@ -571,6 +672,7 @@ VP8_FN void parse_token_row(TokenPart& tp, const ImgDesc& im, const FrameHdr* h,
     }
     info[2] = nzy;
     info[3] = (w & 0xffff0000u) | nzuv;
+    sink.mb(mx, my, dst);
     orow[mx] = (uint16_t)tctx;
     ++tp.done;
     if (P > 1) VP8_PUBLISH_PROGRESS(&progress[part], tp.done);

@@ -11,12 +11,15 @@
 
 // =====================================================================================================
 // Boolean decoder. State kept as in the reference: range stored minus one, in [127,254] once normalised
-// (src/utils/bit_reader_utils.h:93-103). Bytes are pulled one at a time; the decoded bits do not depend on
-// the refill width (bit_reader_utils.h:50-74), and `eof` is raised exactly when a decode needs a byte that
-// does not exist (bit_reader_utils.c:88-101).
+// (src/utils/bit_reader_utils.h:93-103), a 64-bit value filled seven bytes at a time while eight or more are left and one
+// byte at a time after that (BITS = 56: bit_reader_inl_utils.h:58-103, bit_reader_utils.c:88-101); `eof` is raised exactly
+// when a decode needs a byte that does not exist. On every stream an encoder writes the refill width does not show in the
+// decoded bits; it does when a partition starts with byte 0xFF, which puts the value outside its range from the first bit on
+// (whatever has overflowed above the low eight bits is dropped when the next seven bytes come in), so the width is kept.
 typedef struct {
   const uint8_t* p;
   const uint8_t* end;
+  const uint8_t* wide_end;   // seven bytes at once while p is below this
   uint32_t range;
   uint64_t value;
   int bits;   // number of not-yet-consumed bits in `value`, minus 8
@@ -25,7 +28,14 @@ typedef struct {
 } BoolDec;
 
 static void bd_refill(BoolDec* d) {
-  if (d->p < d->end) {
+  if (d->p < d->wide_end) {
+    uint64_t w = 0;
+    int k;
+    for (k = 0; k < 7; ++k) w = (w << 8) | d->p[k];
+    d->p += 7;
+    d->value = (d->value << 56) | w;
+    d->bits += 56;
+  } else if (d->p < d->end) {
     d->value = (d->value << 8) | *d->p++;
     d->bits += 8;
   } else if (!d->eof) {
@@ -40,6 +50,7 @@ static void bd_refill(BoolDec* d) {
 static void bd_init(BoolDec* d, const uint8_t* start, size_t size) {
   d->p = start;
   d->end = start + size;
+  d->wide_end = size >= 8 ? start + size - 7 : start;
   d->range = 255 - 1;
   d->value = 0;
   d->bits = -8;
@@ -75,6 +86,21 @@ static int bd_bit(BoolDec* d, int prob) {   // bit_reader_inl_utils.h:107-136
   d->bits -= shift;
   d->range = range - 1;
   return bit;
+}
+
+// Sign of a coefficient (VP8GetSigned, bit_reader_inl_utils.h:139-158): an even split decided by the sign bit of a 32-bit
+// difference; the same as bd_bit(d, 0x80) while the value is inside its range. Returns 1 for negative.
+static int bd_sign(BoolDec* d) {
+  uint32_t split, top, mask;
+  if (d->bits < 0) bd_refill(d);
+  ++d->decodes;
+  split = d->range >> 1;
+  top = (uint32_t)(d->value >> d->bits);
+  mask = (uint32_t)((int32_t)(split - top) >> 31);
+  d->value -= (uint64_t)((split + 1) & mask) << d->bits;
+  d->bits -= 1;
+  d->range = (d->range + mask) | 1u;
+  return (int)(mask & 1u);
 }
 
 static uint32_t bd_value(BoolDec* d, int nbits) {   // bit_reader_utils.c:106
@@ -496,7 +522,7 @@ static int block_coeffs(BoolDec* d, uint8_t (*probs)[3][11], int ctx, const int*
         v = large_value(d, p);
         p = probs[kBand[n + 1]][2];
       }
-      out[kZigzag[n]] = (int16_t)((bd_bit(d, 0x80) ? -v : v) * dq[n > 0]);
+      out[kZigzag[n]] = (int16_t)((bd_sign(d) ? -v : v) * dq[n > 0]);
     }
   }
   return 16;

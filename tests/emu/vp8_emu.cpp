@@ -21,6 +21,7 @@
 #include "vp8_tokens_fsm.h"
 #include "vp8_tokens_lockstep.h"
 #include "vp8_tokens_fp.h"
+#include "vp8_literal.h"
 #include "vp8l_alpha_core.h"
 #include "vp8l_lossless_core.h"
 #include "vp8l_alpha_core.h"
@@ -150,8 +151,18 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
   std::vector<uint8_t> yuv(nmb * 384, 0);
   uint8_t* yp = yuv.data(); uint8_t* up = yp + nmb * 256; uint8_t* vp = up + nmb * 64;
 
+  // A partition that starts with 0xFF: the whole image goes through the reference's reader taken literally instead (k_parse_literal)
+  const bool literal = (variant & 64) && c.frame_size >= 10 &&
+                       vp8b_partition_starts_with_ff(data + c.frame_offset + 10, c.part0_size, c.frame_size - 10, im.num_parts);
+  std::vector<uint32_t> tokens;
+  std::vector<MbTok> mbtok;
   // K1: header + intra modes
-  {
+  if (literal) {
+    tokens.assign(nmb * TF_TOKENS_PER_MB, 0xffffffffu);
+    mbtok.assign(nmb, MbTok{ 0xffffffffu, 0xffffffffu });
+    std::vector<uint8_t> scratch(LIT_SCRATCH_BYTES(mb_w) + 16, 0);
+    parse_image_literal(frame, im, &hdr, kVp8BModeProba, mbinfo.data(), tokens.data(), mbtok.data(), scratch.data());
+  } else {
     BoolDec br;
     std::vector<uint32_t> top(mb_w);
     hdr.status = parse_frame_header(br, frame, im, &hdr);
@@ -172,15 +183,14 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
                                   (int)im.crop_y + (int)im.out_h, all_at_once) ? vp8_status : ah.status;
   };
   // intra modes that ran out at row r > 0: the fp parser still reads the tokens of the rows above (k_parse_tokens_fp)
-  const bool modes_short = hdr.status == VP8B_NOT_ENOUGH_DATA && hdr.fail_row > 0 && hdr.fail_row != VP8B_FAIL_NONE && (variant & 64) && c.has_alph_chunk;
+  const bool modes_short = !literal && hdr.status == VP8B_NOT_ENOUGH_DATA && hdr.fail_row > 0 && hdr.fail_row != VP8B_FAIL_NONE && (variant & 64) && c.has_alph_chunk;
   if (hdr.status != VP8B_OK && !modes_short) return failed(hdr.status);
-  if (hdr.num_parts != im.num_parts) return -100;   // host pre-scan disagrees with the device parse
+  if (!literal && hdr.num_parts != im.num_parts) return -100;   // host pre-scan disagrees with the device parse
   const int rows = modes_short && hdr.fail_row < hdr.rows ? hdr.fail_row : hdr.rows;   // macroblock rows that get decoded (all of them unless cropping)
 
   // K2: tokens
-  std::vector<uint32_t> tokens;
-  std::vector<MbTok> mbtok;
-  if (variant & 64) {   // fp parser: one lane per partition, one decode per lane per round, levels as a token stream
+  if (literal) {   // done above
+  } else if (variant & 64) {   // fp parser: one lane per partition, one decode per lane per round, levels as a token stream
     const int P = hdr.num_parts;
     tokens.assign(nmb * TF_TOKENS_PER_MB, 0xffffffffu);
     mbtok.assign(nmb, MbTok{ 0xffffffffu, 0xffffffffu });

@@ -152,6 +152,54 @@ def test_emu_alpha_and_vp8_both_damaged(emu, ref, amanifest):
     assert {3, 7} <= seen, seen
 
 
+
+def _ff_mutants(rng, data, count):
+    """Copies of a lossy file in which the first partition or the (single) token partition starts with byte 0xFF -- what no
+    encoder writes and what makes the reference's reader leave its range (vp8_literal.h) -- alone or with more damage."""
+    i = data.find(b"VP8 ")
+    fo = i + 8
+    part0 = int.from_bytes(data[fo:fo + 3], "little") >> 5
+    out = []
+    for k in range(count):
+        b = bytearray(data)
+        at = fo + 10 if k % 2 == 0 else fo + 10 + part0
+        b[min(at, len(b) - 1)] = 0xFF
+        if k >= 2:
+            for _ in range(int(rng.integers(0, 3))):
+                b[int(rng.integers(fo + 10, len(b)))] ^= int(rng.integers(1, 256))
+        out.append(bytes(b))
+    return out
+
+
+def test_emu_partition_starting_with_ff(emu, ref, port, manifest, amanifest):
+    """The literal reader (vp8_parse_core.h:RefBits, variants 64 and 80 = the default parser): status and pixels of the reference
+    on files whose partitions start with 0xFF; the oracle's restatement reads the same way."""
+    rng = np.random.default_rng(37)
+    seen = {}
+    for e in list(manifest) + list(amanifest):
+        data = e["data"]
+        if data.find(b"VP8 ") < 0 or len(data) < 200:
+            continue
+        w, h = e["features"]["width"], e["features"]["height"]
+        for b in _ff_mutants(rng, data, 24):
+            if ref.features(b)[0] != 0:
+                continue
+            s_ref, want = ref.decode(b, ref.MODE_RGBA, 0)
+            seen[s_ref] = seen.get(s_ref, 0) + 1
+            for variant in (64, 80):
+                s_emu, got = emu(b, w, h, 1, 0, variant)
+                assert s_emu == s_ref, (e["file"], s_ref, s_emu, variant)
+                if s_ref == 0 and not np.array_equal(want.reshape(-1), got.reshape(-1)):
+                    _, want = ref.decode(b, ref.MODE_RGBA, 0, simd=False)   # SSE2 vs C transforms on out-of-range coefficients
+                    assert np.array_equal(want.reshape(-1), got.reshape(-1)), e["file"]
+            if not e["features"].get("has_alpha"):
+                s_port, got = port.decode(b, port.RGBA, 0)
+                assert s_port == s_ref, (e["file"], s_ref, s_port)
+                if s_ref == 0:
+                    assert np.array_equal(want.reshape(-1), got.reshape(-1)), e["file"]
+    assert seen.get(0, 0) > 20 and seen.get(7, 0) > 20, seen
+
+
 def test_emu_crop_and_flip_match_reference(ref, manifest, amanifest):
     """options.use_cropping / options.flip: the window is upsampled as if it were the picture, rows below it are never
     decoded (so data missing down there goes unnoticed), the 8-bit alpha path restarts its horizontal unfilter at the

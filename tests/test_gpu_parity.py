@@ -884,3 +884,44 @@ def test_alpha_and_vp8_both_damaged(W, ref, amanifest):
             _, want = ref.decode(d, W.MODE_RGBA, 0, simd=False)
             assert np.array_equal(out.reshape(-1), want.reshape(-1))
     assert {3, 7} <= seen, seen      # both kinds of failure were met
+
+def _ff_mutants(rng, data, count):
+    """Copies of a lossy file in which the first partition or the (single) token partition starts with byte 0xFF -- what no
+    encoder writes and what makes the reference's reader leave its range (vp8_literal.h) -- alone or with more damage."""
+    i = data.find(b"VP8 ")
+    fo = i + 8
+    part0 = int.from_bytes(data[fo:fo + 3], "little") >> 5
+    out = []
+    for k in range(count):
+        b = bytearray(data)
+        at = fo + 10 if k % 2 == 0 else fo + 10 + part0
+        b[min(at, len(b) - 1)] = 0xFF
+        if k >= 2:
+            for _ in range(int(rng.integers(0, 3))):
+                b[int(rng.integers(fo + 10, len(b)))] ^= int(rng.integers(1, 256))
+        out.append(bytes(b))
+    return out
+
+
+@pytest.mark.gpu
+def test_partition_starting_with_ff(W, ref, manifest, amanifest):
+    """Files whose first or token partition starts with 0xFF go through k_parse_literal (the reference's reader taken literally)
+    after the regular parse, in the same batch as intact files: status and pixels of the reference for all of them."""
+    rng = np.random.default_rng(41)
+    datas = []
+    for e in list(manifest) + list(amanifest):
+        data = e["data"]
+        if data.find(b"VP8 ") < 0 or len(data) < 200:
+            continue
+        datas.append(data)
+        datas += [b for b in _ff_mutants(rng, data, 24) if ref.features(b)[0] == 0]
+    sts, outs = W.decode_batch(datas, W.MODE_RGBA, device=0)
+    seen = {}
+    for d, st, out in zip(datas, sts, outs):
+        s_ref, want = ref.decode(d, W.MODE_RGBA, 0)
+        assert st == s_ref, (len(d), st, s_ref)
+        seen[s_ref] = seen.get(s_ref, 0) + 1
+        if s_ref == 0 and not np.array_equal(out.reshape(-1), want.reshape(-1)):
+            _, want = ref.decode(d, W.MODE_RGBA, 0, simd=False)
+            assert np.array_equal(out.reshape(-1), want.reshape(-1))
+    assert seen.get(0, 0) > 40 and seen.get(7, 0) > 20, seen

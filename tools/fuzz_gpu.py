@@ -58,9 +58,7 @@ def main():
                     same = True
             if same:
                 continue
-            if sf == 0 and F.partition_starts_with_ff(b):
-                hist["known_ff_first_byte"] = hist.get("known_ff_first_byte", 0) + 1
-            elif sf == 0 and s_gpu == 4 and (f["format"] == 2 or b"ALPH" in F.chunk_spans(b)):
+            if sf == 0 and s_gpu == 4 and (f["format"] == 2 or b"ALPH" in F.chunk_spans(b)):
                 hist["known_vp8l_limit"] = hist.get("known_vp8l_limit", 0) + 1
             else:
                 tag = "gpu_%s_%d_%d" % (name, batches, i)
