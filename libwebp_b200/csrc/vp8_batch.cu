@@ -442,10 +442,12 @@ static VP8StatusCode plan_item(WebPBatchItem* it, const WebPBatchOptions& opt, V
     if (sw == 0 && oh > 0) sw = (int)(((uint64_t)ow * sh + oh - 1) / oh);
     if (sh == 0 && ow > 0) sh = (int)(((uint64_t)oh * sw + ow - 1) / ow);
     if (sw <= 0 || sh <= 0 || sw > 0x3fffffff || sh > 0x3fffffff) return VP8_STATUS_INVALID_PARAM;
-    if (sw > 16383 || sh > 16383) return VP8_STATUS_UNSUPPORTED_FEATURE;   // ImgDesc keeps 16-bit dimensions
     ow = sw; oh = sh;
   }
   if (opt.output == WEBP_BATCH_HOST) return prepare_host_buffer(ow, oh, &cfg->output);
+  // device-resident output: the limits the reference's own allocator would have applied (buffer_dec.c:88-116, utils.h:34-41)
+  if ((uint64_t)ow * 4 >= (1ull << 31)) return VP8_STATUS_INVALID_PARAM;
+  if ((uint64_t)ow * 4 * (uint64_t)oh >= (1ull << 34)) return VP8_STATUS_OUT_OF_MEMORY;
   cfg->output.width = ow; cfg->output.height = oh;
   return VP8_STATUS_OK;
 }
@@ -563,7 +565,7 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
     int fw = d.out_w, fh = d.out_h;   // the picture that leaves the device
     if (cfg->options.use_scaling) {
       fw = cfg->output.width; fh = cfg->output.height;   // set by plan_item
-      d.dst_w = (uint16_t)fw; d.dst_h = (uint16_t)fh;
+      d.dst_w = (uint32_t)fw; d.dst_h = (uint32_t)fh;
       // WebPIoInitFromOptions, webp_dec.c:851-856: no loop filter for large downscaling ratios (against the whole picture)
       if (fw < c.width * 3 / 4 && fh < c.height * 3 / 4) d.flags |= VP8B_FLAG_BYPASS_FILTER;
     }
@@ -667,8 +669,8 @@ static bool batch_build(WebPBatch* b, const std::vector<Vp8Container>& cont) {
                                     : ((d.out_w + 3) / 4) * d.out_h;
       w.max_units = std::max(w.max_units, units);
       if (d.dst_w != 0) {
-        const int uvdw = (d.dst_w + 1) / 2;
-        w.max_scaled_items = std::max(w.max_scaled_items, (d.csp == MODE_YUV || d.csp == MODE_YUVA) ? d.dst_w + 2 * uvdw + (d.csp == MODE_YUVA ? d.dst_w : 0) : (int)d.dst_w);
+        const int dw = (int)d.dst_w, uvdw = (dw + 1) / 2;
+        w.max_scaled_items = std::max(w.max_scaled_items, (d.csp == MODE_YUV || d.csp == MODE_YUVA) ? dw + 2 * uvdw + (d.csp == MODE_YUVA ? dw : 0) : dw);
       }
     }
     b->waves.push_back(w);
@@ -921,9 +923,9 @@ static bool batch_alpha(WebPBatch* b, cudaStream_t s) {
       ImgDesc& d = b->imgs[b->aimgs[a]];
       if (h.status != AL_OK) continue;
       if (h.method == 1) {
-        tab[a] = work2; work2 += align_up((size_t)h.num_groups * (size_t)h.group_entries * 4, 256);
-        grp[a] = work2; work2 += align_up((size_t)h.num_groups * sizeof(AlGroup), 256);
-        cod[a] = work2; work2 += align_up(4 * ((size_t)h.xsize * d.height + 4), 256);
+        tab[a] = work2; work2 += align_up((size_t)h.used_groups * (size_t)h.group_entries * 4, 256);
+        grp[a] = work2; work2 += align_up((size_t)h.used_groups * sizeof(AlGroup), 256);
+        cod[a] = work2; work2 += align_up(4 * ((size_t)std::max(h.xsize, h.px_stride) * d.height + 4), 256);
       }
       if (d.flags & VP8B_FLAG_LOSSLESS) {   // its pixels go straight to the output arena (vp8k_lossless_finish)
         if (d.dst_w != 0) { smo[a] = work2 + 1; work2 += align_up(4 * (size_t)d.out_w * d.out_h + 16, 256); }
@@ -1460,7 +1462,7 @@ static size_t item_device_bytes(const WebPBatchItem* it) {
   size_t ow = w, oh = h;
   const WebPDecoderOptions* o = &it->config->options;
   if (o->use_cropping && o->crop_width > 0 && o->crop_height > 0) { ow = std::min(ow, (size_t)o->crop_width); oh = std::min(oh, (size_t)o->crop_height); }
-  if (o->use_scaling && o->scaled_width > 0 && o->scaled_height > 0 && o->scaled_width <= 16383 && o->scaled_height <= 16383) { ow = (size_t)o->scaled_width; oh = (size_t)o->scaled_height; }
+  if (o->use_scaling && o->scaled_width > 0 && o->scaled_height > 0) { ow = (size_t)o->scaled_width; oh = (size_t)o->scaled_height; }
   size_t bytes = it->data_size + 4 * ow * oh + 4096;                       // input + output (at most 4 bytes per pixel)
   if (f.has_alpha || f.format == 2) bytes += 9 * w * h + (1u << 20);      // alpha plane, coded ARGB, de-banding / tile work
   return bytes;

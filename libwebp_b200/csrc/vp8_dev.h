@@ -59,9 +59,9 @@ typedef struct ImgDesc {
   uint16_t crop_x, crop_y, out_w, out_h;
   // options.use_scaling: the window above is rescaled to dst_w x dst_h (io_dec.c:239-556, src/dsp/rescaler.c); 0 = no scaling.
   // out_stride / out_off then describe the scaled picture.
-  uint16_t dst_w, dst_h;
+  uint32_t dst_w, dst_h;  // (32 bits: the reference rescales to anything its allocator accepts, rescaler_utils.c:86-118)
   uint8_t alpha_dither;   // options.alpha_dithering_strength (1..100) when the ALPH chunk's levels were quantised, else 0
-  uint8_t pad_[3];
+  uint8_t pad_[7];
 } ImgDesc;
 #define VP8B_NO_ALPHA 0xffffffffffffffffull
 

@@ -19,9 +19,9 @@
 //                               word per coded pixel
 //   then    alph_finish       : inverse transforms in place (predictor as a lag-2 row wavefront), palette /
 //                               unbundling, green -> alpha, and the row unfilter -> the w x h alpha plane
-// The whole VP8L syntax is accepted (all four transforms, colour cache, meta-Huffman groups) with two limits that
-// report VP8_STATUS_UNSUPPORTED_FEATURE: more than AL_MAX_GROUPS prefix-code groups, and a COLOR_INDEXING transform
-// that is not the first transform of the stream (the reference encoder always writes it first).
+// The whole VP8L syntax is accepted: all four transforms in any order (a COLOR_INDEXING transform that is not the first one
+// widens the rows in place, al_inverse_transforms), colour cache, meta-Huffman groups up to the 65536 the syntax can name
+// (tables only for the ones in use when the reference would have remapped them, alph_parse_header).
 // Status mirrors the reference: a failure while reading the headers/codes surfaces as VP8_STATUS_OUT_OF_MEMORY
 // (alpha_dec.c:190-196: the lossless decoder object was never attached), a failure in the pixel loop as
 // VP8_STATUS_BITSTREAM_ERROR (frame_dec.c:452-460).
@@ -35,9 +35,11 @@
 #define AL_FN __device__ __forceinline__
 #define AL_NOINLINE static __device__ __noinline__
 #define AL_TABLE static __constant__ const
+#define AL_POPC(x) __popc(x)
 #else
 #define AL_FN static inline
 #define AL_NOINLINE static
+#define AL_POPC(x) __builtin_popcount(x)
 #define AL_TABLE static const
 #endif
 
@@ -54,7 +56,7 @@
 #define AL_LENGTHS_ROOT_BITS 7
 #define AL_MAX_CACHE_BITS 11
 #define AL_MAX_ALPHABET (AL_NUM_LITERAL + AL_NUM_LENGTH + (1 << AL_MAX_CACHE_BITS))   // 2328
-#define AL_MAX_GROUPS 4096     // the reference encoder never emits more than 2600 (MAX_HUFF_IMAGE_SIZE)
+#define AL_MAX_GROUPS 65536    // group numbers are 16 bits wide (the reference encoder never emits more than 2600, MAX_HUFF_IMAGE_SIZE)
 // lookup-table entries of one group: 630 * 3 + 410 + the green table, whose worst case grows with the colour cache
 // (kTableSize, vp8l_dec.c:81-96)
 #define AL_FIXED_TABLE_ENTRIES (630 * 3 + 410)
@@ -423,8 +425,13 @@ struct AlphaHdr {
   int32_t txsize[4];        // image width the transform applies to
   uint32_t tdata[4];        // word offset of the transform's tile image inside the transform-data area
   int32_t xsize;            // width of the coded image (after bundling)
+  int32_t px_stride;        // words per row of the pixel buffer once the inverse transforms are done: xsize, or the picture's
+                            // width when a palette transform that is not the first one has widened the rows on the way
   int32_t huff_xsize;       // width of the meta-Huffman image
   int32_t num_groups;       // groups whose codes follow in the stream
+  int32_t used_groups;      // groups that get tables: num_groups, or only the ones the meta-Huffman image names when the
+                            // reference would have remapped them (`mapped`, vp8l_dec.c:399-424)
+  int32_t mapped;
   int32_t group_entries;    // lookup-table entries reserved per group
   // reader state after the meta-Huffman image
   uint64_t br_val;
@@ -436,7 +443,13 @@ struct AlphaHdr {
 
 #define AL_PASSA_FIXED_WORDS (AL_SUB_TABLE_ENTRIES + (1 << AL_MAX_CACHE_BITS) + 256)
 // bytes of per-image scratch: sub-image tables + colour cache + palette pixels + AlScratch (rounded up to 16)
-#define AL_SCRATCH_BYTES (4u * AL_PASSA_FIXED_WORDS + ((uint32_t)sizeof(AlScratch) + 15u) / 16u * 16u)
+#define AL_SCRATCH_FIXED_BYTES (4u * AL_PASSA_FIXED_WORDS + ((uint32_t)sizeof(AlScratch) + 15u) / 16u * 16u)
+// ... + which group numbers the meta-Huffman image uses: one bit each, and the count of used numbers below every 32
+#define AL_USED_BITS_WORDS (AL_MAX_GROUPS / 32)
+#define AL_SCRATCH_BYTES (AL_SCRATCH_FIXED_BYTES + 4u * AL_USED_BITS_WORDS + 2u * AL_USED_BITS_WORDS)
+// dense index of group g among the used ones
+#define AL_USED_BITS(scratch) ((uint32_t*)((uint8_t*)(scratch) + AL_SCRATCH_FIXED_BYTES))
+#define AL_USED_BELOW(scratch) ((uint16_t*)(AL_USED_BITS(scratch) + AL_USED_BITS_WORDS))
 // upper bound of a sub-sampled image (meta-Huffman, predictor or cross-colour tiles; precision >= 2 bits) of a
 // w x h picture, in pixels
 #define AL_META_PIXELS_BOUND(w, h) ((uint32_t)(((w) + 3) >> 2) * (uint32_t)(((h) + 3) >> 2))
@@ -454,7 +467,7 @@ AL_NOINLINE void alph_parse_header(const uint8_t* alph, uint32_t alph_size, int 
   hd->method = 0; hd->filter = 0; hd->ntrans = 0; hd->cache_bits = 0; hd->huff_bits = 0; hd->use_8b = 0;
   hd->lossless = (uint8_t)(lossless != 0);
   hd->levels = 0;
-  hd->xsize = w; hd->huff_xsize = 0; hd->num_groups = 1; hd->group_entries = AL_GROUP_ENTRIES(0);
+  hd->xsize = w; hd->px_stride = w; hd->huff_xsize = 0; hd->num_groups = 1; hd->used_groups = 1; hd->mapped = 0; hd->group_entries = AL_GROUP_ENTRIES(0);
   hd->br_val = 0; hd->br_pos = 0; hd->br_bit_pos = 0;
   uint32_t* tables = (uint32_t*)scratch;
   uint32_t* cache = tables + AL_SUB_TABLE_ENTRIES;
@@ -483,7 +496,7 @@ AL_NOINLINE void alph_parse_header(const uint8_t* alph, uint32_t alph_size, int 
   // transforms (ReadTransform, vp8l_dec.c:1330-1384); each type at most once
   int xsize = w;
   uint32_t seen = 0, tdata_used = 0;
-  int unsupported = 0;
+  int px_stride = 0;
   while (lb_read(b, 1)) {
     const uint32_t type = lb_read(b, 2);
     if (seen & (1u << type)) return;
@@ -511,7 +524,8 @@ AL_NOINLINE void alph_parse_header(const uint8_t* alph, uint32_t alph_size, int 
           hd->palette[i] = full;
         } else { hd->palette_alpha[i] = 0; hd->palette[i] = 0; }
       }
-      if (n != 0) unsupported = 1;   // pixels would have to widen between two in-place transforms
+      if (n != 0) px_stride = hd->txsize[n];   // not the first transform (no encoder of the reference writes that): the pixels
+                                               // widen to this width between two in-place transforms (al_inverse_transforms)
     }
   }
   // colour cache of the main image
@@ -521,7 +535,8 @@ AL_NOINLINE void alph_parse_header(const uint8_t* alph, uint32_t alph_size, int 
     hd->cache_bits = (uint8_t)cache_bits;
   }
   // meta-Huffman image (ReadHuffmanCodes, vp8l_dec.c:365-451)
-  int num_groups = 1;
+  int num_groups = 1, used_groups = 1;
+  hd->mapped = 0;
   if (lb_read(b, 1)) {
     const int precision = (int)lb_read(b, 3) + 2;
     const int hx = (xsize + (1 << precision) - 1) >> precision, hy = (h + (1 << precision) - 1) >> precision;
@@ -536,18 +551,35 @@ AL_NOINLINE void alph_parse_header(const uint8_t* alph, uint32_t alph_size, int 
     num_groups = max_group + 1;
     hd->huff_bits = (uint8_t)precision;
     hd->huff_xsize = hx;
-    if (num_groups > AL_MAX_GROUPS) unsupported = 1;
+    // Many group numbers, or more than there are pixels: the reference keeps tables only for the numbers the image uses (it
+    // still reads, and checks, the codes of the others) and looks at those alone when it picks its pixel loop
+    // (vp8l_dec.c:399-424, 857-870). Dense numbers in increasing order here, in order of first appearance there: the same set.
+    if (num_groups > 1000 || num_groups > xsize * h) {
+      uint32_t* bits = AL_USED_BITS(scratch);
+      uint16_t* below = AL_USED_BELOW(scratch);
+      const int words = (num_groups + 31) >> 5;
+      for (int k = 0; k < words; ++k) bits[k] = 0;
+      for (int i = 0; i < hx * hy; ++i) bits[meta[i] >> 5] |= 1u << (meta[i] & 31);
+      int used = 0;
+      for (int k = 0; k < words; ++k) { below[k] = (uint16_t)used; used += AL_POPC(bits[k]); }
+      for (int i = 0; i < hx * hy; ++i) meta[i] = (uint16_t)(below[meta[i] >> 5] + AL_POPC(bits[meta[i] >> 5] & ((1u << (meta[i] & 31)) - 1u)));
+      used_groups = used;
+      hd->mapped = 1;
+    } else {
+      used_groups = num_groups;
+    }
   }
   if (b.eos) return;
-  if (unsupported) { hd->status = AL_UNSUPPORTED; return; }
   hd->xsize = xsize;
+  hd->px_stride = px_stride ? px_stride : xsize;
   hd->num_groups = num_groups;
+  hd->used_groups = used_groups;
   hd->group_entries = AL_GROUP_ENTRIES(hd->cache_bits);
   hd->br_val = b.val; hd->br_pos = b.pos; hd->br_bit_pos = b.bit_pos;
   hd->status = AL_OK;
 }
 
-// Pass B. tables = num_groups * group_entries words, groups = num_groups AlGroup, scratch as in pass A (its
+// Pass B. tables = used_groups * group_entries words, groups = used_groups AlGroup, scratch as in pass A (its
 // colour-cache area and AlScratch are reused), out = xsize * h ARGB words. last_row = rows the caller needs (the
 // bottom of the crop window, h without cropping): like the reference, decoding stops there, so data missing further
 // down is never noticed. Returns the image status.
@@ -557,10 +589,20 @@ AL_NOINLINE int alph_decode_pixels(const uint8_t* alph, uint32_t alph_size, int 
   AlScratch* sc = (AlScratch*)(cache + (1 << AL_MAX_CACHE_BITS) + 256);
   LBits b;
   b.buf = alph + (hd->lossless ? 0 : 1); b.len = alph_size - (hd->lossless ? 0u : 1u); b.val = hd->br_val; b.pos = hd->br_pos; b.bit_pos = hd->br_bit_pos; b.eos = 0;
-  const int num_groups = hd->num_groups, stride = hd->group_entries, cache_bits = hd->cache_bits;
-  // codes of every group (still part of the header as far as the status goes)
-  for (int g = 0; g < num_groups; ++g) {
-    if (al_read_group(b, cache_bits, tables + (size_t)g * stride, stride, &groups[g], sc) == 0) return AL_OUT_OF_MEMORY;
+  const int num_groups = hd->num_groups, used_groups = hd->used_groups, stride = hd->group_entries, cache_bits = hd->cache_bits;
+  // codes of every group (still part of the header as far as the status goes); the groups the meta-Huffman image never names are
+  // read and checked like the others but kept nowhere when the reference would have remapped them (alph_parse_header)
+  {
+    const uint32_t* bits = AL_USED_BITS(scratch);
+    const uint16_t* below = AL_USED_BELOW(scratch);
+    AlGroup unused;
+    for (int g = 0; g < num_groups; ++g) {
+      int slot = g;
+      if (hd->mapped) slot = ((bits[g >> 5] >> (g & 31)) & 1u) ? (int)(below[g >> 5] + AL_POPC(bits[g >> 5] & ((1u << (g & 31)) - 1u))) : -1;
+      const int ok = slot >= 0 ? al_read_group(b, cache_bits, tables + (size_t)slot * stride, stride, &groups[slot], sc)
+                               : al_read_group(b, cache_bits, (uint32_t*)scratch, stride, &unused, sc);   // pass A's table area is free now
+      if (ok == 0) return AL_OUT_OF_MEMORY;
+    }
   }
   // The reference runs DecodeAlphaData (vp8l_dec.c:1035-1116) when the only transform is the palette, there is no
   // colour cache and every group's R, B and A codes are zero-bit (Is8bOptimizable, :857-870), DecodeImageData
@@ -568,7 +610,7 @@ AL_NOINLINE int alph_decode_pixels(const uint8_t* alph, uint32_t alph_size, int 
   // so keep both shapes. A whole VP8L picture always goes through DecodeImageData (VP8LDecodeImage, :1761-1765; the 8-bit
   // path is chosen by VP8LDecodeAlphaHeader alone, :1633-1641): there, data that runs out on the last symbol is an error.
   int use_8b = (!hd->lossless && hd->ntrans == 1 && hd->ttype[0] == AL_T_COLOR_INDEXING && cache_bits == 0);
-  for (int g = 0; g < num_groups && use_8b; ++g) use_8b = groups[g].trivial_literal;
+  for (int g = 0; g < used_groups && use_8b; ++g) use_8b = groups[g].trivial_literal;
   hd->use_8b = (uint8_t)use_8b;
   const int cache_size = cache_bits ? (1 << cache_bits) : 0, cache_shift = 32 - cache_bits;
   for (int i = 0; i < cache_size; ++i) cache[i] = 0;
@@ -771,7 +813,22 @@ AL_FN void al_inverse_transforms(const AlphaHdr* hd, uint32_t* px, const uint32_
         px[i] = (argb & 0xff00ff00u) | (((argb & 0x00ff00ffu) + ((green << 16) | green)) & 0x00ff00ffu);
       }
     }
-    // AL_T_COLOR_INDEXING is always transform 0 here and is folded into the extraction below
+    else if (type == AL_T_COLOR_INDEXING && n != 0) {
+      // VP8LColorIndexInverseTransform in place (lossless.c:341-385, vp8l_dec.c:... the reference moves the packed rows to the
+      // end of the buffer first): rows of `xs` packed words become rows of `tw` pixels. Backwards, so that a word is read
+      // before anything lands on it (the write position never falls below the read position). One thread: no encoder of the
+      // reference writes this order.
+      if (tid == 0) {
+        const int xs = (tw + (1 << bits) - 1) >> bits, bpp = 8 >> bits;
+        for (int y = h - 1; y >= 0; --y) {
+          for (int x = tw - 1; x >= 0; --x) {
+            const uint32_t packed = (px[(size_t)y * xs + (x >> bits)] >> 8) & 0xff;
+            px[(size_t)y * tw + x] = hd->palette[(packed >> ((x & ((1 << bits) - 1)) * bpp)) & ((1u << bpp) - 1u)];
+          }
+        }
+      }
+    }
+    // AL_T_COLOR_INDEXING as transform 0 is folded into the extraction below
     AL_BLOCK_SYNC();
   }
 }
@@ -797,7 +854,7 @@ AL_FN void alph_finish(const AlphaHdr* hd, const uint8_t* raw /* method 0 */, ui
     al_inverse_transforms(hd, px, tdata, h, tid, nt);
     const int has_palette = hd->ntrans > 0 && hd->ttype[0] == AL_T_COLOR_INDEXING;
     const int bits = has_palette ? hd->tbits[0] : 0, bpp = 8 >> bits;
-    const int xs = hd->xsize;
+    const int xs = hd->px_stride;
     for (size_t i = (size_t)tid; i < total; i += (size_t)nt) {
       const int x = (int)(i % (size_t)w), y = (int)(i / (size_t)w);
       if (has_palette) {   // VP8LColorIndexInverseTransform + green, lossless.c:341-385

@@ -22,7 +22,7 @@
 // ARGB of picture pixel (sx, sy) after the inverse transforms: the palette look-up / unbundling of a COLOR_INDEXING
 // transform happens here (VP8LColorIndexInverseTransform, lossless.c:341-385: the index travels in green).
 AL_FN uint32_t vp8l_fetch(const AlphaHdr* hd, const uint32_t* px, int sx, int sy) {
-  const int xs = hd->xsize;
+  const int xs = hd->px_stride;
   if (hd->ntrans > 0 && hd->ttype[0] == AL_T_COLOR_INDEXING) {
     const int bits = hd->tbits[0], bpp = 8 >> bits;
     const uint32_t packed = (px[(size_t)sy * xs + (sx >> bits)] >> 8) & 0xff;

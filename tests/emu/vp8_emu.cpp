@@ -61,9 +61,9 @@ static void emu_alpha_passes(const uint8_t* alph, uint32_t alph_size, const ImgD
   tdata.assign(2 * (size_t)AL_META_PIXELS_BOUND(im.width, im.height) + 8, 0);
   alph_parse_header(alph, alph_size, im.width, im.height, sc16, (uint16_t*)meta.data(), tdata.data(), ah);
   if (ah->status == AL_OK && ah->method == 1) {
-    std::vector<uint32_t> tables((size_t)ah->num_groups * ah->group_entries);
-    std::vector<AlGroup> groups(ah->num_groups);
-    coded.assign((size_t)ah->xsize * im.height + 4, 0);
+    std::vector<uint32_t> tables((size_t)ah->used_groups * ah->group_entries);
+    std::vector<AlGroup> groups(ah->used_groups);
+    coded.assign((size_t)(ah->xsize > ah->px_stride ? ah->xsize : ah->px_stride) * im.height + 4, 0);
     ah->status = alph_decode_pixels(alph, alph_size, im.height, (int)im.crop_y + (int)im.out_h, ah, (const uint16_t*)meta.data(),
                                     tables.data(), groups.data(), sc16, coded.data());
   }
@@ -91,7 +91,7 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
     im.csp = (uint8_t)csp; im.flags = (uint8_t)(flags | VP8B_FLAG_LOSSLESS); im.out_stride = stride;
     im.out_w = im.width; im.out_h = im.height;
     if (crop_w > 0) { im.crop_x = (uint16_t)crop_x; im.crop_y = (uint16_t)crop_y; im.out_w = (uint16_t)crop_w; im.out_h = (uint16_t)crop_h; }
-    if (scaled_w > 0) { im.dst_w = (uint16_t)scaled_w; im.dst_h = (uint16_t)scaled_h; }
+    if (scaled_w > 0) { im.dst_w = (uint32_t)scaled_w; im.dst_h = (uint32_t)scaled_h; }
     const uint8_t* bits = data + c.frame_offset;
     const uint32_t nbits = (uint32_t)c.frame_size;
     std::vector<uint8_t> scratch(AL_SCRATCH_BYTES + 64);
@@ -102,9 +102,9 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
     alph_parse_header(bits, nbits, im.width, im.height, sc16, (uint16_t*)meta.data(), tdata.data(), &ah, 1);
     std::vector<uint32_t> coded;
     if (ah.status == AL_OK) {
-      std::vector<uint32_t> tables((size_t)ah.num_groups * ah.group_entries);
-      std::vector<AlGroup> groups(ah.num_groups);
-      coded.assign((size_t)ah.xsize * im.height + 4, 0);
+      std::vector<uint32_t> tables((size_t)ah.used_groups * ah.group_entries);
+      std::vector<AlGroup> groups(ah.used_groups);
+      coded.assign((size_t)(ah.xsize > ah.px_stride ? ah.xsize : ah.px_stride) * im.height + 4, 0);
       ah.status = alph_decode_pixels(bits, nbits, im.height, (int)im.crop_y + (int)im.out_h, &ah, (const uint16_t*)meta.data(), tables.data(),
                                      groups.data(), sc16, coded.data());
     }
@@ -135,7 +135,7 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
   im.out_w = im.width; im.out_h = im.height;
   if (crop_w > 0) { im.crop_x = (uint16_t)(crop_x & ~1); im.crop_y = (uint16_t)(crop_y & ~1); im.out_w = (uint16_t)crop_w; im.out_h = (uint16_t)crop_h; }
   if (scaled_w > 0) {   // like batch_build (vp8_batch.cu): scaled dimensions, and no loop filter for large downscaling ratios
-    im.dst_w = (uint16_t)scaled_w; im.dst_h = (uint16_t)scaled_h;
+    im.dst_w = (uint32_t)scaled_w; im.dst_h = (uint32_t)scaled_h;
     if (scaled_w < c.width * 3 / 4 && scaled_h < c.height * 3 / 4) im.flags |= VP8B_FLAG_BYPASS_FILTER;
   }
   im.dither_f = (uint8_t)g_emu_dither_f;

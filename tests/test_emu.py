@@ -262,14 +262,14 @@ def test_emu_scaling_matches_reference(ref, manifest, amanifest):
     for e in list(manifest) + list(amanifest):
         has_alpha = bool(e["features"].get("has_alpha"))
         W, H = e["features"]["width"], e["features"]["height"]
-        for it in range(6):
+        for it in range(6 + (2 if W * H <= 4096 else 0)):   # two requests beyond 16383 on the small pictures
             crop = None
-            if it >= 4:
+            if it >= 4 and it < 6:
                 cw, ch = int(rng.integers(1, W + 1)), int(rng.integers(1, H + 1))
                 crop = (int(rng.integers(0, W - cw + 1)), int(rng.integers(0, H - ch + 1)), cw, ch)
             w, h = (crop[2], crop[3]) if crop else (W, H)
             req = [(max(1, w // 2), max(1, h // 3)), (w * 2 + 1, h + 7), (max(1, w - 1), h * 3), (0, max(1, h // 2)), (w + 5, 0),
-                   (int(rng.integers(1, 2 * w + 2)), int(rng.integers(1, 2 * h + 2)))][it]
+                   (int(rng.integers(1, 2 * w + 2)), int(rng.integers(1, 2 * h + 2))), (20001, max(1, h // 2)), (3, 16500)][it]
             flip = int(rng.integers(0, 2))
             # files with an ALPH chunk: the alpha plane is rescaled too, premultiplied modes multiply after scaling, MODE_YUVA
             # multiplies the luma before and divides it after (io_dec.c:252-300, 414-470)
@@ -443,6 +443,39 @@ def test_emu_lossless_matches_reference(ref):
                 assert np.array_equal(want.reshape(-1), got)
 
 
+def test_emu_crafted_vp8l_corners(ref, amanifest):
+    """Hand-made streams (tests/vp8l_craft.py) for what no encoder of the reference writes but its decoder accepts: group numbers
+    beyond 1000 / beyond the pixel count (remapped to the ones in use, vp8l_dec.c:399-424), a colour-indexing transform that is
+    not the first transform (rows widened in place); whole pictures in every output family and inside ALPH chunks."""
+    import vp8l_craft
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR])
+    L = C.CDLL(os.path.join(EMU_DIR, "libvp8_emu.so"))
+    L.emu_decode_window.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_int]
+    host = [e["data"] for e in amanifest if e["file"] == "alpha_tiny_17x16.webp"][0]
+    for name, data in vp8l_craft.crafted_cases(host):
+        st0, f = ref.features(data)
+        assert st0 == 0, name
+        w, h = f["width"], f["height"]
+        for csp in (1, 7, 0, 5, 11, 12):
+            s_ref, want = ref.decode_window(data, csp, 0, None)
+            assert s_ref == 0, (name, csp, s_ref)      # the reference does decode these
+            bpp = 1 if csp in (11, 12) else ref.BPP[csp]
+            n = (w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2) + (w * h if csp == 12 else 0)) if csp in (11, 12) else w * h * bpp
+            out = np.zeros(max(n, 16), np.uint8)
+            st = L.emu_decode_window(data, len(data), csp, 0, out.ctypes.data, out.size, w * bpp, 0, 0, 0, 0)
+            assert st == 0, (name, csp, st)
+            assert np.array_equal(want, out[:n]), (name, csp)
+        for k in range(1, 6):   # cut short: same status
+            b = data[: len(data) - 2 * k]
+            if ref.features(b)[0] != 0:
+                continue
+            s_ref, _ = ref.decode(b, 1, 0)
+            out = np.zeros(max(w * h * 4, 16), np.uint8)
+            st = L.emu_decode_window(b, len(b), 1, 0, out.ctypes.data, out.size, w * 4, 0, 0, 0, 0)
+            assert st == s_ref, (name, k, s_ref, st)
+
+
 def test_emu_lossless_palette_picture_losing_its_last_bits(ref, lmanifest):
     """A whole VP8L picture always runs the reference's 32-bit pixel loop (VP8LDecodeImage -> DecodeImageData, vp8l_dec.c:1761-1765);
     only an ALPH payload may take the 8-bit one. They differ in when running out of data is an error: the 32-bit loop fails as
@@ -494,14 +527,14 @@ def test_emu_lossless_scaling_matches_reference(ref):
     for data in lossless_cases(ref)[:9]:
         _, f = ref.features(data)
         W, H = f["width"], f["height"]
-        for it in range(6):
+        for it in range(6 + (2 if W * H <= 4096 else 0)):   # two requests beyond 16383 on the small pictures
             crop = None
-            if it >= 4:
+            if it >= 4 and it < 6:
                 cw, ch = int(rng.integers(1, W + 1)), int(rng.integers(1, H + 1))
                 crop = (int(rng.integers(0, W - cw + 1)), int(rng.integers(0, H - ch + 1)), cw, ch)
             w, h = (crop[2], crop[3]) if crop else (W, H)
             req = [(max(1, w // 2), max(1, h // 3)), (w * 2 + 1, h + 7), (max(1, w - 1), h * 3), (0, max(1, h // 2)), (w + 5, 0),
-                   (int(rng.integers(1, 2 * w + 2)), int(rng.integers(1, 2 * h + 2)))][it]
+                   (int(rng.integers(1, 2 * w + 2)), int(rng.integers(1, 2 * h + 2))), (20001, max(1, h // 2)), (3, 16500)][it]
             flip = int(rng.integers(0, 2))
             for csp in (1, 7, 12, 10, 9, 0, 11, 6):
                 s_ref, (sw, sh), want = ref.decode_scaled(data, csp, 8 if flip else 0, crop, req)

@@ -439,6 +439,15 @@ def test_scaling(W, ref, manifest, amanifest):
                 st, out = W.WebPDecode(e["data"], csp, crop=crop, flip=flip, scaled=req)
                 assert st == s_ref == 0, (e["file"], req, crop, csp, st, s_ref, W.last_error())
                 assert np.array_equal(out.reshape(-1)[:want.size], want), (e["file"], req, crop, flip, csp, (sw, sh))
+    for e in manifest:   # beyond 16383 (round 1 refused these): the reference rescales to anything its allocator accepts
+        if e["features"]["width"] * e["features"]["height"] > 4096:
+            continue
+        for req in ((20001, 5), (3, 16500), (40000, 0)):
+            for csp in (W.MODE_RGBA, W.MODE_YUV):
+                s_ref, (sw, sh), want = ref.decode_scaled(e["data"], csp, 0, None, req)
+                st, out = W.WebPDecode(e["data"], csp, scaled=req)
+                assert st == s_ref == 0, (e["file"], req, csp, st, s_ref, W.last_error())
+                assert np.array_equal(out.reshape(-1)[:want.size], want), (e["file"], req, csp, (sw, sh))
     data = manifest[0]["data"]
     for req in ((0, 0), (-3, 10)):
         s_ref, _, _ = ref.decode_scaled(data, W.MODE_RGBA, 0, None, req)
@@ -925,3 +934,18 @@ def test_partition_starting_with_ff(W, ref, manifest, amanifest):
             _, want = ref.decode(d, W.MODE_RGBA, 0, simd=False)
             assert np.array_equal(out.reshape(-1), want.reshape(-1))
     assert seen.get(0, 0) > 40 and seen.get(7, 0) > 20, seen
+
+
+@pytest.mark.gpu
+def test_crafted_vp8l_corners(W, ref, amanifest):
+    """Hand-made VP8L streams (tests/vp8l_craft.py): group numbers beyond 1000 / beyond the pixel count, a colour-indexing transform
+    that is not the first one; round 1 refused these (UNSUPPORTED_FEATURE), the reference decodes them."""
+    import vp8l_craft
+    host = [e["data"] for e in amanifest if e["file"] == "alpha_tiny_17x16.webp"][0]
+    cases = vp8l_craft.crafted_cases(host)
+    for csp in (W.MODE_RGBA, W.MODE_rgbA, W.MODE_YUV):
+        sts, outs = W.decode_batch([d for _, d in cases], csp, device=0)
+        for (name, data), st, out in zip(cases, sts, outs):
+            s_ref, want = ref.decode(data, csp, 0)
+            assert st == s_ref == 0, (name, csp, st, s_ref)
+            assert np.array_equal(out.reshape(-1)[:want.size], want.reshape(-1)), (name, csp)

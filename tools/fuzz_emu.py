@@ -252,11 +252,6 @@ def worker(args):
             # vp8_dev.h:vp8b_vp8_failure_first picks the status the reference reports
             hist["known_both_chunks_damaged"] = hist.get("known_both_chunks_damaged", 0) + 1
             ok += 1
-        elif differs and feat_ok and s_emu == 4 and (f["format"] == 2 or b"ALPH" in chunk_spans(b)):
-            # a damaged VP8L header that announces more than the two limits of vp8l_alpha_core.h allow (> 4096 prefix-code groups,
-            # a palette that is not the first transform): refused before the reference would have met the damage
-            hist["known_vp8l_limit"] = hist.get("known_vp8l_limit", 0) + 1
-            ok += 1
         elif differs:
             tag = "%s_w%d_%d" % (name, wid, n)
             bad.append((tag, s_ref, s_emu, variant))

@@ -58,13 +58,10 @@ def main():
                     same = True
             if same:
                 continue
-            if sf == 0 and s_gpu == 4 and (f["format"] == 2 or b"ALPH" in F.chunk_spans(b)):
-                hist["known_vp8l_limit"] = hist.get("known_vp8l_limit", 0) + 1
-            else:
-                tag = "gpu_%s_%d_%d" % (name, batches, i)
-                bad.append((tag, s_ref, s_gpu))
-                os.makedirs(os.path.join(ROOT, "gpurun_out", "fuzz"), exist_ok=True)
-                open(os.path.join(ROOT, "gpurun_out", "fuzz", tag + ".webp"), "wb").write(b)
+            tag = "gpu_%s_%d_%d" % (name, batches, i)
+            bad.append((tag, s_ref, s_gpu))
+            os.makedirs(os.path.join(ROOT, "gpurun_out", "fuzz"), exist_ok=True)
+            open(os.path.join(ROOT, "gpurun_out", "fuzz", tag + ".webp"), "wb").write(b)
     for t in bad[:50]:
         print("MISMATCH file=%s ref=%d gpu=%d" % t)
     print(json.dumps({"cases": cases, "batches": batches, "batch": a.batch, "mismatches": len(bad),
