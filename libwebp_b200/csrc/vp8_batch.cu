@@ -345,6 +345,10 @@ struct ItemPlan {
   int img = -1;            // index among the device images, -1 when the item failed on the host
   size_t frame_offset = 0; // VP8 frame tag inside the file
   size_t out_bytes = 0;    // bytes of this image in the device output arena (tight strides)
+  bool discard = false;    // decode, but copy nothing out and end with VP8_STATUS_INVALID_PARAM unless the decode itself fails: a
+                           // caller's buffer that is unusable, in the one case where the reference only finds out AFTER decoding
+                           // (is_external_memory >= 2 + premultiplied output + a file with alpha: WebPDecode goes through a buffer
+                           // of its own and copies at the end, webp_dec.c:769-786, buffer_dec.c:270-310)
 };
 
 struct Wave {
@@ -412,7 +416,12 @@ static void fail_all(WebPBatchItem* items, int n, VP8StatusCode st) {
 }
 
 // Host-side part of one item: container walk, option/colourspace screening, output buffer.
-static VP8StatusCode plan_item(WebPBatchItem* it, const WebPBatchOptions& opt, Vp8Container* c) {
+extern "C" int vp8b_host_headers_status(const uint8_t* frame, size_t frame_size, uint32_t part0_size, int width, int height, int is_lossless);
+
+// The output request of one item against the picture's dimensions: what WebPAllocateDecBuffer would say (buffer_dec.c:41-227).
+static VP8StatusCode check_request(WebPBatchItem* it, const WebPBatchOptions& opt, const Vp8Container* c, bool* discard);
+
+static VP8StatusCode plan_item(WebPBatchItem* it, const WebPBatchOptions& opt, Vp8Container* c, bool* discard) {
   WebPDecoderConfig* cfg = it->config;
   if (cfg == NULL || it->data == NULL) return VP8_STATUS_INVALID_PARAM;   // webp_dec.c:756, GetFeatures webp_dec.c:693-695
   VP8StatusCode st = vp8b_get_features(it->data, it->data_size, &cfg->input);
@@ -421,6 +430,19 @@ static VP8StatusCode plan_item(WebPBatchItem* it, const WebPBatchOptions& opt, V
   if (st != VP8_STATUS_OK) return st;
   if (c->has_animation) return VP8_STATUS_UNSUPPORTED_FEATURE;             // webp_dec.c:427-429
   if (!c->is_lossless && c->part0_size > c->frame_size - 10) return VP8_STATUS_NOT_ENOUGH_DATA;   // vp8_dec.c:345-348
+  st = check_request(it, opt, c, discard);
+  if (st != VP8_STATUS_OK) {
+    // The reference parses the frame header / the VP8L header BEFORE it looks at the request (webp_dec.c:469-481): a file
+    // whose header is damaged reports that, whatever was asked for. Decided on the host (vp8_host_probe.cpp): nothing of
+    // this item reaches the device either way.
+    const int hs = vp8b_host_headers_status(it->data + c->frame_offset, c->frame_size, c->part0_size, c->width, c->height, c->is_lossless);
+    if (hs != 0) return (VP8StatusCode)hs;
+  }
+  return st;
+}
+
+static VP8StatusCode check_request(WebPBatchItem* it, const WebPBatchOptions& opt, const Vp8Container* c, bool* discard) {
+  WebPDecoderConfig* cfg = it->config;
   const WebPDecoderOptions* o = &cfg->options;
   const int csp = cfg->output.colorspace;
   if (csp < MODE_RGB || csp >= MODE_LAST) return VP8_STATUS_INVALID_PARAM;
@@ -444,7 +466,14 @@ static VP8StatusCode plan_item(WebPBatchItem* it, const WebPBatchOptions& opt, V
     if (sw <= 0 || sh <= 0 || sw > 0x3fffffff || sh > 0x3fffffff) return VP8_STATUS_INVALID_PARAM;
     ow = sw; oh = sh;
   }
-  if (opt.output == WEBP_BATCH_HOST) return prepare_host_buffer(ow, oh, &cfg->output);
+  if (opt.output == WEBP_BATCH_HOST) {
+    const VP8StatusCode bs = prepare_host_buffer(ow, oh, &cfg->output);
+    if (bs == VP8_STATUS_INVALID_PARAM && cfg->output.is_external_memory >= 2 && WebPIsPremultipliedMode((WEBP_CSP_MODE)csp) && cfg->input.has_alpha) {
+      *discard = true;   // see ItemPlan::discard
+      return VP8_STATUS_OK;
+    }
+    return bs;
+  }
   // device-resident output: the limits the reference's own allocator would have applied (buffer_dec.c:88-116, utils.h:34-41)
   if ((uint64_t)ow * 4 >= (1ull << 31)) return VP8_STATUS_INVALID_PARAM;
   if ((uint64_t)ow * 4 * (uint64_t)oh >= (1ull << 34)) return VP8_STATUS_OUT_OF_MEMORY;
@@ -463,7 +492,7 @@ static int batch_plan(WebPBatch* b, std::vector<Vp8Container>& cont) {
   b->plan.resize(n);
   cont.resize(n);
   for (int i = 0; i < n; ++i) {
-    b->items[i].status = plan_item(&b->items[i], b->opt, &cont[i]);
+    b->items[i].status = plan_item(&b->items[i], b->opt, &cont[i], &b->plan[i].discard);
     if (b->items[i].status == VP8_STATUS_OK) ++alive;
     else if (b->items[i].config != NULL && b->opt.output == WEBP_BATCH_HOST) {
       WebPFreeDecBuffer(&b->items[i].config->output);   // webp_dec.c:513-515
@@ -795,6 +824,7 @@ static bool enqueue_download(WebPBatch* b, int first, int count, cudaStream_t s,
   for (int k = first; k < first + count; ++k) {
     const WebPBatchItem* it = &b->items[b->img_item[k]];
     if (check_status && it->status != VP8_STATUS_OK) continue;
+    if (b->plan[b->img_item[k]].discard) continue;
     const ImgDesc& d = b->imgs[k];
     const WebPDecBuffer* o = &it->config->output;
     const uint8_t* src = dout + d.out_off;
@@ -845,7 +875,7 @@ static bool enqueue_download_rows(WebPBatch* b, int first, int count, int pair_b
   for (int k = first; k < first + count && uniform; ++k) {
     const ImgDesc& d = b->imgs[k];
     const WebPDecBuffer* o = &b->items[b->img_item[k]].config->output;
-    if (d.out_h != d0.out_h || d.out_stride != d0.out_stride || o->u.RGBA.stride != d.out_stride) uniform = false;
+    if (d.out_h != d0.out_h || d.out_stride != d0.out_stride || o->u.RGBA.stride != d.out_stride || b->plan[b->img_item[k]].discard) uniform = false;
     if (k == first + 1) { hpitch = o->u.RGBA.rgba - o0->u.RGBA.rgba; dpitch = (ptrdiff_t)(d.out_off - d0.out_off); }
     if (k > first && (o->u.RGBA.rgba - o0->u.RGBA.rgba != hpitch * (k - first) || (ptrdiff_t)(d.out_off - d0.out_off) != dpitch * (k - first)))
       uniform = false;
@@ -862,7 +892,7 @@ static bool enqueue_download_rows(WebPBatch* b, int first, int count, int pair_b
     const ImgDesc& d = b->imgs[k];
     const WebPDecBuffer* o = &b->items[b->img_item[k]].config->output;
     int lo, hi; rows_of(d, &lo, &hi);
-    if (hi <= lo) continue;
+    if (hi <= lo || b->plan[b->img_item[k]].discard) continue;
     const size_t row = (size_t)d.out_stride;
     CU_TRY(cudaMemcpy2DAsync(o->u.RGBA.rgba + (size_t)lo * o->u.RGBA.stride, (size_t)o->u.RGBA.stride, dout + d.out_off + lo * row, row, row,
                              (size_t)(hi - lo), cudaMemcpyDeviceToHost, s), "D2H pixel band");
@@ -1206,6 +1236,7 @@ static bool batch_finish(WebPBatch* b) {
           it->status = (VP8StatusCode)ah.status;
       }
     }
+    if (it->status == VP8_STATUS_OK && b->plan[b->img_item[k]].discard) it->status = VP8_STATUS_INVALID_PARAM;
     if (it->status != VP8_STATUS_OK && b->opt.output == WEBP_BATCH_HOST) WebPFreeDecBuffer(&it->config->output);
   }
   b->decoded = true;

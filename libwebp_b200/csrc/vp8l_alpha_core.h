@@ -583,27 +583,32 @@ AL_NOINLINE void alph_parse_header(const uint8_t* alph, uint32_t alph_size, int 
 // colour-cache area and AlScratch are reused), out = xsize * h ARGB words. last_row = rows the caller needs (the
 // bottom of the crop window, h without cropping): like the reference, decoding stops there, so data missing further
 // down is never noticed. Returns the image status.
+// The codes of every group, the last thing the reference counts as header (VP8LDecodeHeader / VP8LDecodeAlphaHeader end here). The
+// groups the meta-Huffman image never names are read and checked like the others but kept nowhere when the reference would have
+// remapped them (alph_parse_header). Returns 0 on a bad code.
+AL_NOINLINE int alph_read_groups(LBits& b, const AlphaHdr* hd, uint32_t* tables, AlGroup* groups, uint8_t* scratch, AlScratch* sc) {
+  const int num_groups = hd->num_groups, stride = hd->group_entries, cache_bits = hd->cache_bits;
+  const uint32_t* bits = AL_USED_BITS(scratch);
+  const uint16_t* below = AL_USED_BELOW(scratch);
+  AlGroup unused;
+  for (int g = 0; g < num_groups; ++g) {
+    int slot = g;
+    if (hd->mapped) slot = ((bits[g >> 5] >> (g & 31)) & 1u) ? (int)(below[g >> 5] + AL_POPC(bits[g >> 5] & ((1u << (g & 31)) - 1u))) : -1;
+    const int ok = slot >= 0 ? al_read_group(b, cache_bits, tables + (size_t)slot * stride, stride, &groups[slot], sc)
+                             : al_read_group(b, cache_bits, (uint32_t*)scratch, stride, &unused, sc);   // pass A's table area is free now
+    if (ok == 0) return 0;
+  }
+  return 1;
+}
+
 AL_NOINLINE int alph_decode_pixels(const uint8_t* alph, uint32_t alph_size, int h, int last_row, AlphaHdr* hd, const uint16_t* meta,
                                    uint32_t* tables, AlGroup* groups, uint8_t* scratch, uint32_t* out) {
   uint32_t* cache = (uint32_t*)scratch + AL_SUB_TABLE_ENTRIES;
   AlScratch* sc = (AlScratch*)(cache + (1 << AL_MAX_CACHE_BITS) + 256);
   LBits b;
   b.buf = alph + (hd->lossless ? 0 : 1); b.len = alph_size - (hd->lossless ? 0u : 1u); b.val = hd->br_val; b.pos = hd->br_pos; b.bit_pos = hd->br_bit_pos; b.eos = 0;
-  const int num_groups = hd->num_groups, used_groups = hd->used_groups, stride = hd->group_entries, cache_bits = hd->cache_bits;
-  // codes of every group (still part of the header as far as the status goes); the groups the meta-Huffman image never names are
-  // read and checked like the others but kept nowhere when the reference would have remapped them (alph_parse_header)
-  {
-    const uint32_t* bits = AL_USED_BITS(scratch);
-    const uint16_t* below = AL_USED_BELOW(scratch);
-    AlGroup unused;
-    for (int g = 0; g < num_groups; ++g) {
-      int slot = g;
-      if (hd->mapped) slot = ((bits[g >> 5] >> (g & 31)) & 1u) ? (int)(below[g >> 5] + AL_POPC(bits[g >> 5] & ((1u << (g & 31)) - 1u))) : -1;
-      const int ok = slot >= 0 ? al_read_group(b, cache_bits, tables + (size_t)slot * stride, stride, &groups[slot], sc)
-                               : al_read_group(b, cache_bits, (uint32_t*)scratch, stride, &unused, sc);   // pass A's table area is free now
-      if (ok == 0) return AL_OUT_OF_MEMORY;
-    }
-  }
+  const int used_groups = hd->used_groups, stride = hd->group_entries, cache_bits = hd->cache_bits;
+  if (!alph_read_groups(b, hd, tables, groups, scratch, sc)) return AL_OUT_OF_MEMORY;   // (still part of the header as far as the status goes)
   // The reference runs DecodeAlphaData (vp8l_dec.c:1035-1116) when the only transform is the palette, there is no
   // colour cache and every group's R, B and A codes are zero-bit (Is8bOptimizable, :857-870), DecodeImageData
   // (:1138-1293) otherwise. Same symbols either way; what differs is when running out of data counts as a failure,

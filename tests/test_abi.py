@@ -199,6 +199,11 @@ def test_option_and_buffer_screening_matches_reference(product, ref):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_options.py"), "--cases", "6000", "--seed", "11"],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:]
+    # the same with damaged files mixed in: a damaged HEADER is reported before an illegal request, like the reference does
+    # (webp_dec.c:469-481: VP8GetHeaders / VP8LDecodeHeader run before WebPAllocateDecBuffer; vp8_host_probe.cpp)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_options.py"), "--cases", "6000", "--seed", "12", "--damage", "0.6"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
 
 
 def test_packaged_as_libwebpdecoder(product, tmp_path):

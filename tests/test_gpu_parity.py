@@ -949,3 +949,43 @@ def test_crafted_vp8l_corners(W, ref, amanifest):
             s_ref, want = ref.decode(data, csp, 0)
             assert st == s_ref == 0, (name, csp, st, s_ref)
             assert np.array_equal(out.reshape(-1)[:want.size], want.reshape(-1)), (name, csp)
+
+
+@pytest.mark.gpu
+def test_unusable_slow_memory_buffer_is_reported_after_the_decode(W, ref, amanifest):
+    """is_external_memory = 2 + premultiplied output + a file with alpha: the reference decodes into a buffer of its own and looks
+    at the caller's only when it copies (webp_dec.c:769-786). So a caller's buffer that is too small ends in INVALID_PARAM when
+    the file is sound, and in the file's own failure when it is not -- the product decodes (and copies nothing) to find out."""
+    import ctypes as C
+    L = W.lib()
+    Q = ref.lib()
+    for L_ in (L, Q):
+        L_.WebPInitDecoderConfigInternal.argtypes = [C.POINTER(W.WebPDecoderConfig), C.c_int]
+        L_.WebPDecode.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(W.WebPDecoderConfig)]
+    e = [x for x in amanifest if x["file"] == "alpha_gradient_130x97.webp"][0]
+    w, h = e["features"]["width"], e["features"]["height"]
+    sound = e["data"]
+    cut = sound[: len(sound) - 600]                       # the VP8 payload runs dry
+    i = sound.find(b"ALPH")
+    bad_alpha = bytearray(sound); bad_alpha[i + 9] ^= 0x55; bad_alpha = bytes(bad_alpha)
+    arena = np.zeros(4 * w * h + 64, np.uint8)
+    seen = set()
+    for data in (sound, cut, bad_alpha):
+        for stride, size in ((4 * w - 8, 4 * w * h), (4 * w, 4 * w * h - 5), (4 * w, 4 * w * h)):
+            got = []
+            for lib in (Q, L):
+                cfg = W.WebPDecoderConfig()
+                lib.WebPInitDecoderConfigInternal(C.byref(cfg), W.WEBP_DECODER_ABI_VERSION)
+                cfg.output.colorspace = W.MODE_rgbA
+                cfg.output.is_external_memory = 2
+                cfg.output.u.RGBA.rgba = arena.ctypes.data
+                cfg.output.u.RGBA.stride = stride
+                cfg.output.u.RGBA.size = size
+                arena[:] = 0
+                st = lib.WebPDecode(data, len(data), C.byref(cfg))
+                got.append((st, arena.copy() if st == 0 else None))
+            assert got[0][0] == got[1][0], (len(data), stride, size, got[0][0], got[1][0])
+            seen.add(got[0][0])
+            if got[0][0] == 0:
+                assert np.array_equal(got[0][1], got[1][1])
+    assert {0, 2, 7} <= seen, seen
