@@ -385,10 +385,10 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_lockstep(const uint
 struct TfLayout {   // byte offsets from the 1024-byte aligned start of the block's dynamic shared memory
   uint32_t images, rings, bars, progress, ctx, total;
 };
-__host__ __device__ static inline TfLayout tf_layout(int P, int ipb, int ctx_stride, int ring) {
+__host__ __device__ static inline TfLayout tf_layout(int P, int ipb, int ctx_stride, int ring, int band) {
   TfLayout t;
   t.images = 1024;                                         // TfTables in front
-  t.rings = t.images + (uint32_t)ipb * TF_IMG_BYTES;      // RING: per stream a 256-byte input ring (256-byte aligned)
+  t.rings = t.images + (uint32_t)ipb * TF_IMG_BYTES_B(band);   // RING: per stream a 256-byte input ring (256-byte aligned)
   t.bars = t.rings + (ring ? (uint32_t)(ipb * P) * 256u : 0u);          // ... and two mbarriers
   t.progress = t.bars + (ring ? (uint32_t)(ipb * P) * 16u : 0u);
   t.ctx = t.progress + (uint32_t)ipb * VP8B_MAX_PARTS * 4u;
@@ -399,14 +399,14 @@ __host__ __device__ static inline TfLayout tf_layout(int P, int ipb, int ctx_str
 #ifndef TF_GROUPS_PER_VOTE
 #define TF_GROUPS_PER_VOTE 8   // groups of four decodes between two votes on "any lane still alive"
 #endif
-template <int RING>
+template <int RING, int BAND>
 __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_fp(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
                                                             FrameHdr* hdrs, uint32_t* mbinfo, uint32_t* tokens, MbTok* mbtok,
                                                             const int* __restrict__ ids, int count, int P, int ipb, int lpw,
                                                             int cw, int ctx_stride, int flat) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tk_saddr_of(smem_raw) & 1023u)) & 1023u);   // the rows' addresses carry the position in bits 6-9
-  const TfLayout lay = tf_layout(P, ipb, ctx_stride, RING);
+  const TfLayout lay = tf_layout(P, ipb, ctx_stride, RING, BAND);
   TfTables* tables = reinterpret_cast<TfTables*>(smem);
   int* progress = reinterpret_cast<int*>(smem + lay.progress);
   const int tid = threadIdx.x, nthreads = blockDim.x;
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_fp(const uint8_t* _
   for (int k = tid; k < ipb * VP8B_MAX_PARTS; k += nthreads) progress[k] = 0;
   for (int slot = 0; slot < ipb; ++slot) {
     const int g = blockIdx.x * ipb + slot;
-    if (g < count) tf_image_fill(smem + lay.images + (size_t)slot * TF_IMG_BYTES, &hdrs[ids[g]], tid, nthreads);
+    if (g < count) tf_image_fill(smem + lay.images + (size_t)slot * TF_IMG_BYTES_B(BAND), &hdrs[ids[g]], tid, nthreads, BAND);
   }
   __syncthreads();
   const int lane = tid & 31, warp = tid >> 5;
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_fp(const uint8_t* _
   }
   const ImgDesc im = imgs[img];
   TfCtx c;
-  c.img_s = tk_saddr_of(smem + lay.images + (size_t)(have ? slot : 0) * TF_IMG_BYTES);
+  c.img_s = tk_saddr_of(smem + lay.images + (size_t)(have ? slot : 0) * TF_IMG_BYTES_B(BAND));
   c.tab_s = tk_saddr_of(tables);
   c.k.mant_mask = 0x007fffffu; c.k.exp46 = TF_EXP46;
   asm volatile("" : "+r"(c.img_s), "+r"(c.tab_s), "+r"(c.k.mant_mask), "+r"(c.k.exp46));   // plain registers: no per-step cvta, one LOP3 in fd_bit
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(32 * 16, 1) k_parse_tokens_fp(const uint8_t* _
   __builtin_assume(__isGlobal(c.mbinfo));
   __builtin_assume(__isGlobal(c.tokens));
   __builtin_assume(__isGlobal(c.mbtok));
-  TfLane L;
+  TfLaneT<BAND> L;
   if (have) {
     tf_lane_init(L, c, arena + im.in_off, h);
     if (RING) fd_ring_open(L.d, tk_saddr_of(smem + lay.rings) + (uint32_t)j * 256u, tk_saddr_of(smem + lay.bars) + (uint32_t)j * 16u);
@@ -736,7 +736,8 @@ static size_t tokens_slot_bytes(int P, int max_mb_w) {
 #define VP8K_MAX_DYN_SMEM (227 * 1024)   // opt-in ceiling per block on sm_100
 extern "C" cudaError_t vp8k_init_device(void) {
   const void* kernels[] = { (const void*)k_parse_modes, (const void*)k_parse_tokens, (const void*)k_parse_tokens_fsm,
-                            (const void*)k_parse_tokens_lockstep, (const void*)k_parse_tokens_fp<0>, (const void*)k_parse_tokens_fp<1>,
+                            (const void*)k_parse_tokens_lockstep, (const void*)k_parse_tokens_fp<0, 0>, (const void*)k_parse_tokens_fp<1, 0>,
+                            (const void*)k_parse_tokens_fp<0, 1>,
                             (const void*)k_reconstruct,
                             (const void*)k_loop_filter };
   for (const void* k : kernels) {
@@ -863,8 +864,24 @@ static void launch_tokens_fp(cudaStream_t s, const uint8_t* arena, const ImgDesc
   int ipb = (cw * lpw) / P;                  // images per block
   const char* er = getenv("WEBP_B200_TOKEN_RING");
   const int ring = (er != NULL && atoi(er) != 0) ? 1 : 0;
-  while (ipb > 1 && tf_layout(P, ipb, max_mb_w, ring).total > (uint32_t)VP8K_MAX_DYN_SMEM - 1024u) --ipb;
-  const TfLayout lay = tf_layout(P, ipb, max_mb_w, ring);
+  const int want = ipb;
+  while (ipb > 1 && tf_layout(P, ipb, max_mb_w, ring, 0).total > (uint32_t)VP8K_MAX_DYN_SMEM - 1024u) --ipb;
+  // Shared memory seats fewer images than there are lanes for them (tens of thousands of small images): the banded layout of the
+  // probability rows (2 KB per image instead of 4, vp8_tokens_fp.h:TF_TYPE_BYTES_B) seats twice as many, in half as many warps
+  // (one per sub-partition, up to 32 lanes each: the instruction stream is shared by all of a warp's lanes).
+  // WEBP_B200_TOKEN_BAND=0|1 forces it. Measured on 65536 256x256 thumbnails: profiles/r02u.
+  const char* eb = getenv("WEBP_B200_TOKEN_BAND");
+  const int band = ring ? 0 : (eb != NULL ? (atoi(eb) != 0) : (ipb < want && streams >= 148L * 4 * 16));
+  if (band) {
+    cw = (f_cw >= 1 && f_cw <= 16) ? f_cw : 4;
+    lpw = (int)((streams + 148L * cw - 1) / (148L * cw));
+    if (f_lpw >= 1 && f_lpw <= 32) lpw = f_lpw;
+    lpw = lpw < 1 ? 1 : lpw > 32 ? 32 : lpw;
+    while (cw * lpw < P) ++lpw;
+    ipb = (cw * lpw) / P;
+    while (ipb > 1 && tf_layout(P, ipb, max_mb_w, 0, 1).total > (uint32_t)VP8K_MAX_DYN_SMEM - 1024u) --ipb;
+  }
+  const TfLayout lay = tf_layout(P, ipb, max_mb_w, ring, band);
   const int blocks = (count + ipb - 1) / ipb;
   // How the lanes are run (vp8_tokens_fp.h): a branch per decode with the block ends handled on the spot while a warp has
   // few lanes, straight-line groups of four decodes with one event point when it has many (the event point's cost is
@@ -881,9 +898,11 @@ static void launch_tokens_fp(cudaStream_t s, const uint8_t* arena, const ImgDesc
   // stream consumes 0.8 bits per decode, so the ring saves one load per ~40 decodes and pays for it with a longer refill path
   // inside a warp whose every instruction is on the critical path.
   if (ring) {
-    k_parse_tokens_fp<1><<<blocks, 32 * cw, lay.total, s>>>(arena, imgs, hdrs, mbinfo, tokens, mbtok, ids, count, P, ipb, lpw, cw, max_mb_w, flat);
+    k_parse_tokens_fp<1, 0><<<blocks, 32 * cw, lay.total, s>>>(arena, imgs, hdrs, mbinfo, tokens, mbtok, ids, count, P, ipb, lpw, cw, max_mb_w, flat);
+  } else if (band) {
+    k_parse_tokens_fp<0, 1><<<blocks, 32 * cw, lay.total, s>>>(arena, imgs, hdrs, mbinfo, tokens, mbtok, ids, count, P, ipb, lpw, cw, max_mb_w, flat);
   } else {
-    k_parse_tokens_fp<0><<<blocks, 32 * cw, lay.total, s>>>(arena, imgs, hdrs, mbinfo, tokens, mbtok, ids, count, P, ipb, lpw, cw, max_mb_w, flat);
+    k_parse_tokens_fp<0, 0><<<blocks, 32 * cw, lay.total, s>>>(arena, imgs, hdrs, mbinfo, tokens, mbtok, ids, count, P, ipb, lpw, cw, max_mb_w, flat);
   }
 }
 

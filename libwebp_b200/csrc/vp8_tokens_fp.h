@@ -60,18 +60,29 @@
 #define TF_ROW_BYTES 64
 #define TF_TYPE_BYTES (16 * TF_ROW_BYTES)   // 1024: the position of a probability is bits 6-9 of its address
 #define TF_IMG_BYTES (4 * TF_TYPE_BYTES)    // per image, 1024-byte aligned
+// Second layout (BAND = 1 below): one row per probability BAND instead of per position -- 8 rows per type, 2 KB per image.
+// Positions 7..14 (and 4) share band 6, so the 16-row layout holds that row nine times; with tens of thousands of small
+// images in a batch the 4 KB per image are what limits the lanes per SM (227 KB: 54 images), and half the size doubles
+// them. The price: the position no longer sits in the address, so the lane counts it (pos6), and the step to the next
+// position's row is no longer a constant 64 bytes but 64 * (band[n+1] - band[n]), looked up per position (TfTables::delta)
+// one decode ahead. All of it off the dependent chain (both outcomes' addresses are formed before the bit is known), but
+// six more instructions per decode: only launches with more streams than the 16-row layout can seat use it.
+#define TF_TYPE_BYTES_B(BAND) ((BAND) ? 8 * TF_ROW_BYTES : 16 * TF_ROW_BYTES)
+#define TF_IMG_BYTES_B(BAND) (4 * TF_TYPE_BYTES_B(BAND))
 
 // ---- transition entry
 //   [31:25] distance in bytes from the pending probability to the next one: next s + 64 * (n advances) - s
 //   [24:13] addend of the magnitude          (the sums of the fields below stay under 2^13 between two resets of acc)
 //   [8:3]   next s, i.e. the offset of the next state's entry pair in the table
+//   2       the walk moves to the next position (the 64 of the distance; only the banded layout looks at it)
 //   1       end of block      0  emit at the current position
 #define TF_EMIT 1u
 #define TF_EOB 2u
+#define TF_ADV 4u
 #define TF_ADD_SHIFT 13
 #define TF_ADD_MASK 0x01ffe000u
 #define TF_E(s, next, adv, flags, add) \
-  ((((uint32_t)(next) + ((adv) ? 64u : 0u) - (uint32_t)(s)) << 25) | ((uint32_t)(add) << TF_ADD_SHIFT) | ((uint32_t)(next) << 3) | (uint32_t)(flags))
+  ((((uint32_t)(next) + ((adv) ? 64u : 0u) - (uint32_t)(s)) << 25) | ((uint32_t)(add) << TF_ADD_SHIFT) | ((uint32_t)(next) << 3) | ((adv) ? TF_ADV : 0u) | (uint32_t)(flags))
 #define TF_E_DIST(e) ((e) >> 25)
 #define TF_E_TAB(e) ((e) & 0x1f8u)
 
@@ -111,7 +122,7 @@ TK_FN uint8_t tf_row_byte(const uint8_t* prob /* [4][8][3][11] */, int t, int n,
   const uint8_t fixed[28] = { 159, 165, 145, 173, 148, 140, 176, 155, 140, 135, 180, 157, 141, 134, 130,
                               254, 254, 243, 230, 196, 177, 153, 140, 133, 130, 129, 128, 128 };
   const uint8_t bands[16] = { 0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7 };
-  if (s < 33) return prob[t * 264 + bands[n] * 33 + s];
+  if (s < 33) return prob[t * 264 + (n < 0 ? -1 - n : bands[n]) * 33 + s];   // n < 0: band -1 - n itself (banded layout)
   if (s < TF_STATES) return fixed[s - 33];
   return 0;
 }
@@ -120,9 +131,12 @@ TK_FN uint8_t tf_row_byte(const uint8_t* prob /* [4][8][3][11] */, int t, int n,
 struct TfTables {
   uint32_t trans[64][2];   // [s][bit]; states 61..63 are dead (probability 0 for ever, nothing emitted, no block end)
   uint32_t seqmask[28];    // block seq (0 = Y2, 1..16 luma, 17..24 chroma): its two context bits inside TfLane::cx
+  int16_t delta[16];       // banded layout: bytes from the row of position n to the row of position n + 1, minus the 64 the
+                           // transition entries already carry
 };
 #define TFT_SEQMASK 512
-#define TF_TAB_BYTES 624    // sizeof(TfTables)
+#define TFT_DELTA 624
+#define TF_TAB_BYTES 656    // sizeof(TfTables)
 
 TK_FN uint32_t tf_seqmask(int k) {
   if (k == 0) return (1u << 8) | (1u << 24);
@@ -140,12 +154,16 @@ TK_FN void tf_tables_fill(TfTables* t, int tid, int nthreads) {
     t->trans[st][k & 1] = st < TF_STATES ? tf_trans_entry(st, k & 1) : TF_E(st, st, 0, 0, 0);
   }
   for (int k = tid; k < 28; k += nthreads) t->seqmask[k] = tf_seqmask(k);
+  for (int k = tid; k < 16; k += nthreads) {
+    const int bands[17] = { 0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7, 8 };   // "position 16" lies one row past band 7
+    t->delta[k] = (int16_t)(TF_ROW_BYTES * (bands[k + 1] - bands[k]) - 64);
+  }
 }
 
 // One image's rows (TF_IMG_BYTES at `dst`, 1024-byte aligned) from the parsed header; any thread subset.
-TK_FN void tf_image_fill(uint8_t* dst, const FrameHdr* h, int tid, int nthreads) {
-  for (int k = tid; k < TF_IMG_BYTES / 4; k += nthreads) {
-    const int t = k >> 8, n = (k >> 4) & 15, s0 = (k & 15) * 4;
+TK_FN void tf_image_fill(uint8_t* dst, const FrameHdr* h, int tid, int nthreads, int band = 0) {
+  for (int k = tid; k < TF_IMG_BYTES_B(band) / 4; k += nthreads) {
+    const int t = band ? k >> 7 : k >> 8, n = band ? -1 - ((k >> 4) & 7) : (k >> 4) & 15, s0 = (k & 15) * 4;
     uint32_t w = 0;
     for (int j = 0; j < 4; ++j) w |= (uint32_t)tf_row_byte(h->prob, t, n, s0 + j) << (8 * j);
     ((uint32_t*)dst)[k] = w;
@@ -350,13 +368,16 @@ TK_FN int fd_bit(FpDec& d, uint32_t prob_bits, const FpConst& k) {
 #define TF_NEED_MB 2
 #define TF_FINISHED 3
 
-// ---- per-lane state (registers)
-struct TfLane {
+// ---- per-lane state (registers). BAND: the banded layout (see TF_TYPE_BYTES_B).
+template <int BAND>
+struct TfLaneT {
   FpDec d;
   tk_saddr a;             // address of the pending probability: row of (type, position) + state
   tk_saddr rowend;        // first address of position 16 of the current block type
   tk_saddr a_end;         // straight-line groups: where the block ended (L.a wanders on afterwards)
   uint32_t tok_end;       // ... and the token count at that point
+  uint32_t pos6, pos_end; // BAND: position of the pending probability << 6 (the 16-row layout reads it off the address); at a_end
+  int32_t dm64;           // BAND: TfTables::delta of that position
   uint32_t pb;            // the pending probability: the byte, i.e. the bits of a denormal float
   uint32_t tag, tag_s;    // block index << 25, and the same with the sign bit set
   int eofs;               // fd_eof() of the most recent decode, taken where a macroblock ends
@@ -381,6 +402,7 @@ struct TfLane {
   int alive;              // 0 once parked
   int status;
 };
+typedef TfLaneT<0> TfLane;
 #define TF_LUT_FROM0 0x3a4u   // nz 0 -> 0, 1 -> 1 (a lone DC level: re-examined after dequantisation, recon_macroblock), 2,3 -> 2, >= 4 -> 3
 #define TF_LUT_FROM1 0x3a0u   // luma blocks of i16 macroblocks start at coefficient 1: nz = 1 means empty
 
@@ -400,7 +422,9 @@ struct TfCtx {
   FpConst k;
 };
 
-TK_FN void tf_lane_reset(TfLane& L, const TfCtx& c) {
+template <int BAND>
+TK_FN void tf_lane_reset(TfLaneT<BAND>& L, const TfCtx& c) {
+  L.pos6 = 0; L.pos_end = 0; L.dm64 = 0;
   L.a = c.img_s; L.rowend = 0; L.a_end = 0; L.tok_end = 0; L.pb = 0; L.e0 = 0; L.e1 = 0; L.acc = 0; L.sink = 0; L.tag = 0; L.tag_s = 0; L.cx = 0;
   L.acc_lo = 0; L.acc_hi = 0; L.m = 0; L.m_next = 0; L.lut = 0; L.seq = 0;
   L.yrow = 0; L.yend = 0; L.ylut = 0;
@@ -414,7 +438,8 @@ TK_FN void tf_lane_reset(TfLane& L, const TfCtx& c) {
   L.mbtok0 = L.tokoff;
 }
 
-TK_FN void tf_lane_init(TfLane& L, const TfCtx& c, const uint8_t* frame, const FrameHdr* h) {
+template <int BAND>
+TK_FN void tf_lane_init(TfLaneT<BAND>& L, const TfCtx& c, const uint8_t* frame, const FrameHdr* h) {
   fd_init(L.d, frame + h->part_off[c.part], h->part_size[c.part]);
   tf_lane_reset(L, c);
   L.eofs = fd_eof(L.d, 1);
@@ -422,9 +447,11 @@ TK_FN void tf_lane_init(TfLane& L, const TfCtx& c, const uint8_t* frame, const F
 }
 
 // Loads the pending decode (probability, both transition entries) of state s at address L.a.
-TK_FN void tf_prime(TfLane& L, const TfCtx& c, uint32_t s) {
+template <int BAND>
+TK_FN void tf_prime(TfLaneT<BAND>& L, const TfCtx& c, uint32_t s) {
   L.pb = tk_lds_u8(L.a);
   tk_lds_v2(c.tab_s + s * 8u, L.e0, L.e1);
+  if (BAND) L.dm64 = tk_lds_s16(c.tab_s + TFT_DELTA + (L.pos6 >> 5));
 }
 
 TK_FN uint32_t tf_popc(uint32_t x) {
@@ -439,12 +466,14 @@ TK_FN uint32_t tf_popc(uint32_t x) {
 // (Preparing the next block's start state while the current one is parsed -- everything of its context but the one bit
 // this block sets -- takes the POPC and a load off the block end's critical path, but costs 16 registers and four
 // instructions per block: measured 267 -> 276 ms per 4096 full-HD images, profiles/r02l, and dropped.)
-TK_FN void tf_block_setup(TfLane& L, const TfCtx& c) {
+template <int BAND>
+TK_FN void tf_block_setup(TfLaneT<BAND>& L, const TfCtx& c) {
   const int chroma = L.seq >= 17;
-  const tk_saddr crow = c.img_s + 2 * TF_TYPE_BYTES;
+  const tk_saddr crow = c.img_s + 2 * TF_TYPE_BYTES_B(BAND);
   L.m = L.m_next;   // fetched while the previous block was parsed
   L.m_next = tk_lds_u32(c.tab_s + TFT_SEQMASK + 4u * (uint32_t)L.seq + 4u);
-  L.rowend = chroma ? crow + TF_TYPE_BYTES : L.yend;
+  L.rowend = chroma ? crow + TF_TYPE_BYTES_B(BAND) : L.yend;
+  if (BAND) L.pos6 = chroma ? 0u : (L.ylut == TF_LUT_FROM1 ? 64u : 0u);   // luma of an i16 macroblock starts at coefficient 1
   L.lut = chroma ? TF_LUT_FROM0 : L.ylut;
   L.tag = ((uint32_t)L.seq - 1u) << 25; L.tag_s = L.tag | 0x80000000u;
   L.acc = 0;
@@ -454,11 +483,13 @@ TK_FN void tf_block_setup(TfLane& L, const TfCtx& c) {
 }
 
 // The Y2 block of an i16 macroblock (seq 0): type 1, block 24.
-TK_FN void tf_y2_setup(TfLane& L, const TfCtx& c) {
+template <int BAND>
+TK_FN void tf_y2_setup(TfLaneT<BAND>& L, const TfCtx& c) {
   L.m = (1u << 8) | (1u << 24);
   L.m_next = (1u << 0) | (1u << 16);   // seq 1
-  const tk_saddr row = c.img_s + 1 * TF_TYPE_BYTES;
-  L.rowend = row + TF_TYPE_BYTES;
+  const tk_saddr row = c.img_s + 1 * TF_TYPE_BYTES_B(BAND);
+  L.rowend = row + TF_TYPE_BYTES_B(BAND);
+  if (BAND) L.pos6 = 0;
   L.lut = TF_LUT_FROM0;
   L.tag = 24u << 25; L.tag_s = L.tag | 0x80000000u;
   L.acc = 0;
@@ -468,8 +499,8 @@ TK_FN void tf_y2_setup(TfLane& L, const TfCtx& c) {
 }
 
 // Stores a finished (or skipped) macroblock's results and steps to the partition's next macroblock.
-template <int MULTI>
-TK_FN void tf_mb_store(TfLane& L, const TfCtx& c, uint32_t nzy, uint32_t w3) {
+template <int MULTI, int BAND>
+TK_FN void tf_mb_store(TfLaneT<BAND>& L, const TfCtx& c, uint32_t nzy, uint32_t w3) {
   const int P = MULTI ? c.P : 1, mb_w = c.mb_w;
   const size_t idx = (size_t)L.my * mb_w + L.mx;
   c.mbinfo[4 * idx + 2] = nzy;
@@ -499,8 +530,8 @@ TK_FN int tf_find_failed_row(const MbTok* mbtok, int mb_w, int rows) {
 
 // Leaves the lane either with a block set up (returns 1), waiting for the row above (returns 0, L.waiting = 1) or
 // finished (returns 0, L.waiting = 0, L.my >= rows or L.status != OK). Skipped macroblocks are consumed here.
-template <int MULTI>
-TK_FN int tf_mb_next(TfLane& L, const TfCtx& c) {
+template <int MULTI, int BAND>
+TK_FN int tf_mb_next(TfLaneT<BAND>& L, const TfCtx& c) {
   const int P = MULTI ? c.P : 1, mb_w = c.mb_w;
   for (;;) {
     if (L.my >= c.rows || L.status != VP8B_OK) { L.waiting = 0; return 0; }
@@ -528,8 +559,8 @@ TK_FN int tf_mb_next(TfLane& L, const TfCtx& c) {
     if (!(c.use_skip && (L.w & MBW_SKIP))) {
       L.acc_lo = 0; L.acc_hi = 0;
       // luma: type 3 from coefficient 0 (i4x4) or type 0 from coefficient 1 (after the Y2 block)
-      const tk_saddr ybase = c.img_s + (is_i4 ? 3u : 0u) * TF_TYPE_BYTES;
-      L.yend = ybase + TF_TYPE_BYTES;
+      const tk_saddr ybase = c.img_s + (is_i4 ? 3u : 0u) * TF_TYPE_BYTES_B(BAND);
+      L.yend = ybase + TF_TYPE_BYTES_B(BAND);
       L.yrow = ybase + (is_i4 ? 0u : (uint32_t)TF_ROW_BYTES);
       L.ylut = is_i4 ? TF_LUT_FROM0 : TF_LUT_FROM1;
       if (is_i4) { L.seq = 1; L.m_next = (1u << 0) | (1u << 16); tf_block_setup(L, c); } else { L.seq = 0; tf_y2_setup(L, c); }
@@ -541,8 +572,8 @@ TK_FN int tf_mb_next(TfLane& L, const TfCtx& c) {
 }
 
 // The macroblock's last block has ended: store its results, move on.
-template <int MULTI>
-TK_FN void tf_mb_finish(TfLane& L, const TfCtx& c, int since) {
+template <int MULTI, int BAND>
+TK_FN void tf_mb_finish(TfLaneT<BAND>& L, const TfCtx& c, int since) {
   L.eofs = fd_eof(L.d, since);
   const uint32_t nzy = (L.acc_hi << 16) | (L.acc_lo >> 16);
   const uint32_t uv = L.acc_lo & 0xffffu;                      // U codes in bits 15-8, V in 7-0
@@ -554,15 +585,18 @@ TK_FN void tf_mb_finish(TfLane& L, const TfCtx& c, int since) {
 
 // Parks a lane that has nothing (more) to do: it keeps decoding in the dead state (probability 0 for ever, never
 // emits, never ends a block) and its reader only shifts in zeros.
-TK_FN void tf_lane_park(TfLane& L, const TfCtx& c) {
+template <int BAND>
+TK_FN void tf_lane_park(TfLaneT<BAND>& L, const TfCtx& c) {
   L.pend = TF_FINISHED; L.alive = 0; L.waiting = 0;
   L.a = c.img_s + TF_DEAD; L.rowend = ~(tk_saddr)0;
+  L.pos6 = 0;
   tf_prime(L, c, TF_DEAD);
-  L.pb = 0;
+  L.pb = 0; L.dm64 = 0;
 }
 
 // A lane without a stream: finished from the start (`any` = some valid address for its reader).
-TK_FN void tf_lane_idle(TfLane& L, const TfCtx& c, const uint8_t* any) {
+template <int BAND>
+TK_FN void tf_lane_idle(TfLaneT<BAND>& L, const TfCtx& c, const uint8_t* any) {
   fd_init(L.d, any, 0);
   tf_lane_reset(L, c);
   L.eofs = 0;
@@ -577,21 +611,31 @@ TK_FN void tf_lane_idle(TfLane& L, const TfCtx& c, const uint8_t* any) {
 // it). The alternative -- loading for both outcomes ahead of the bit and selecting -- takes the latency off the chain
 // but costs ten more integer-pipe instructions per step, and one warp alone on a sub-partition gets an integer-pipe
 // slot only every other cycle: measured 102 cycles per step against this form's (profiles/r02e, r02f).
-TK_FN uint32_t tf_decode(TfLane& L, const TfCtx& c) {
-  const tk_saddr a0 = L.a + TF_E_DIST(L.e0), a1 = L.a + TF_E_DIST(L.e1);
+template <int BAND>
+TK_FN uint32_t tf_decode(TfLaneT<BAND>& L, const TfCtx& c) {
+  tk_saddr a0 = L.a + TF_E_DIST(L.e0), a1 = L.a + TF_E_DIST(L.e1);
+  if (BAND) {   // an advancing outcome lands on the next position's BAND row, not 64 bytes further
+    const tk_saddr dm = (tk_saddr)(long long)L.dm64;   // (signed: some steps go back)
+    a0 += (L.e0 & TF_ADV) ? dm : (tk_saddr)0;
+    a1 += (L.e1 & TF_ADV) ? dm : (tk_saddr)0;
+  }
   const tk_saddr t0 = c.tab_s + TF_E_TAB(L.e0), t1 = c.tab_s + TF_E_TAB(L.e1);
   // ---- boolean decode
   const int bit = fd_bit(L.d, L.pb, c.k);
   // ---- transition
   const uint32_t e = bit ? L.e1 : L.e0;
-  const tk_saddr a_emit = L.a;
+  const uint32_t pos_emit = BAND ? L.pos6 : ((uint32_t)L.a & 0x3c0u);
   L.a = bit ? a1 : a0;
   L.pb = tk_lds_u8(L.a);
   tk_lds_v2(bit ? t1 : t0, L.e0, L.e1);
+  if (BAND) {
+    L.pos6 += (e & TF_ADV) << 4;
+    L.dm64 = tk_lds_s16(c.tab_s + TFT_DELTA + (L.pos6 >> 5));   // for the decode after this one
+  }
   L.acc += e;
   if (e & TF_EMIT) {   // the sign has just been decoded: one token
     const uint32_t t = (L.acc & TF_ADD_MASK) | (bit ? L.tag_s : L.tag);
-    c.tokens[L.tokoff] = t | ((uint32_t)a_emit & 0x3c0u);
+    c.tokens[L.tokoff] = t | pos_emit;
     L.tokoff += 1;
     L.acc = 0;
   }
@@ -602,8 +646,9 @@ TK_FN uint32_t tf_decode(TfLane& L, const TfCtx& c) {
 // block. Returns 1 when the macroblock's last block has ended instead (tf_mb_finish + tf_mb_next are due).
 // nz = position of the last decoded coefficient + 1 = the position the walk stands at: after an emit the address has
 // already moved to the next position; at an end-of-block decision it still stands at the position that was asked.
-TK_FN int tf_block_end(TfLane& L, const TfCtx& c) {
-  const uint32_t nz2 = 32u - (uint32_t)((L.rowend - (L.a & ~(tk_saddr)63)) >> 5);   // 2 * nz
+template <int BAND>
+TK_FN int tf_block_end(TfLaneT<BAND>& L, const TfCtx& c) {
+  const uint32_t nz2 = BAND ? (L.pos6 >> 5) : 32u - (uint32_t)((L.rowend - (L.a & ~(tk_saddr)63)) >> 5);   // 2 * nz
   const uint32_t code = (L.lut >> (nz2 < 8u ? nz2 : 8u)) & 3u;       // non-zero exactly when the block counts as non-empty
   L.acc_hi = (L.acc_hi << 2) | (L.acc_lo >> 30);
   L.acc_lo = (L.acc_lo << 2) | code;
@@ -616,8 +661,8 @@ TK_FN int tf_block_end(TfLane& L, const TfCtx& c) {
 
 // ---- every lane executes every step; a lane whose block has ended does its bookkeeping on the spot while the others
 // wait. Returns 0 once the lane has finished (parked).
-template <int MULTI>
-TK_FN int tf_step_inline(TfLane& L, const TfCtx& c, int since /* decodes since the last fd_fill, this one included */) {
+template <int MULTI, int BAND>
+TK_FN int tf_step_inline(TfLaneT<BAND>& L, const TfCtx& c, int since /* decodes since the last fd_fill, this one included */) {
   if (MULTI) {
     if (L.waiting) {
       if (!tf_mb_next<MULTI>(L, c)) {
@@ -628,7 +673,7 @@ TK_FN int tf_step_inline(TfLane& L, const TfCtx& c, int since /* decodes since t
     }
   }
   const uint32_t e = tf_decode(L, c);
-  if (TF_UNLIKELY((e & TF_EOB) || L.a >= L.rowend)) {
+  if (TF_UNLIKELY((e & TF_EOB) || (BAND ? L.pos6 >= 1024u : L.a >= L.rowend))) {
     if (tf_block_end(L, c)) {
       tf_mb_finish<MULTI>(L, c, since);
       if (!tf_mb_next<MULTI>(L, c)) {
@@ -641,8 +686,8 @@ TK_FN int tf_step_inline(TfLane& L, const TfCtx& c, int since /* decodes since t
 }
 
 // One group: top the window up, four decodes.
-template <int MULTI, int RING>
-TK_FN void tf_group_inline(TfLane& L, const TfCtx& c) {
+template <int MULTI, int RING, int BAND>
+TK_FN void tf_group_inline(TfLaneT<BAND>& L, const TfCtx& c) {
   fd_fill<RING>(L.d);
   tf_step_inline<MULTI>(L, c, 1); tf_step_inline<MULTI>(L, c, 2); tf_step_inline<MULTI>(L, c, 3); tf_step_inline<MULTI>(L, c, 4);
   fd_settle(L.d, 4);
@@ -657,42 +702,55 @@ TK_FN void tf_group_inline(TfLane& L, const TfCtx& c) {
 // to wait for the row above (several partitions) or has finished is in the dead state from the start of the group.
 #define TF_DEAD_ENTRY TF_E(TF_DEAD, TF_DEAD, 0, 0, 0)
 
-TK_FN void tf_go_dead(TfLane& L, const TfCtx& c) {   // the decode state of a lane that is not running
+template <int BAND>
+TK_FN void tf_go_dead(TfLaneT<BAND>& L, const TfCtx& c) {   // the decode state of a lane that is not running
   L.a = c.img_s + TF_DEAD; L.rowend = ~(tk_saddr)0;
+  L.pos6 = 0; L.dm64 = 0;
   L.pb = 0; L.e0 = TF_DEAD_ENTRY; L.e1 = TF_DEAD_ENTRY;
 }
 
-TK_FN bool tf_step_flat(TfLane& L, const TfCtx& c, const bool run) {
-  const tk_saddr a0 = L.a + TF_E_DIST(L.e0), a1 = L.a + TF_E_DIST(L.e1);
+template <int BAND>
+TK_FN bool tf_step_flat(TfLaneT<BAND>& L, const TfCtx& c, const bool run) {
+  tk_saddr a0 = L.a + TF_E_DIST(L.e0), a1 = L.a + TF_E_DIST(L.e1);
+  if (BAND) {
+    const tk_saddr dm = (tk_saddr)(long long)L.dm64;   // (signed: some steps go back)
+    a0 += (L.e0 & TF_ADV) ? dm : (tk_saddr)0;
+    a1 += (L.e1 & TF_ADV) ? dm : (tk_saddr)0;
+  }
   const tk_saddr t0 = c.tab_s + TF_E_TAB(L.e0), t1 = c.tab_s + TF_E_TAB(L.e1);
   const int bit = fd_bit_guarded(L.d, L.pb, c.k, run);
   const uint32_t e = bit ? L.e1 : L.e0;
-  const tk_saddr a_emit = L.a;
+  const uint32_t pos_emit = BAND ? (L.pos6 & 0x3c0u) : ((uint32_t)L.a & 0x3c0u);
   const tk_saddr an = bit ? a1 : a0;
   L.a = an;
   L.pb = tk_lds_u8(an);
   tk_lds_v2(bit ? t1 : t0, L.e0, L.e1);
+  if (BAND) {   // (a lane that is not running wanders: the mask keeps its position inside the delta table)
+    L.pos6 = (L.pos6 + ((e & TF_ADV) << 4)) & 0x7c0u;
+    L.dm64 = tk_lds_s16(c.tab_s + TFT_DELTA + ((L.pos6 & 0x3c0u) >> 5));
+  }
   L.acc += e;
   if (e & TF_EMIT) {   // the sign has just been decoded: one token. A lane that is not running writes its garbage into the
                        // slots after its last real token, which the next real tokens overwrite (tf_events puts tokoff back)
     const uint32_t t = (L.acc & TF_ADD_MASK) | (bit ? L.tag_s : L.tag);
-    c.tokens[L.tokoff] = t | ((uint32_t)a_emit & 0x3c0u);
+    c.tokens[L.tokoff] = t | pos_emit;
     L.tokoff += 1;
     L.acc = 0;
   }
-  const bool end = ((e & TF_EOB) != 0u) || (an >= L.rowend);
-  if (run && end) { L.a_end = an; L.tok_end = L.tokoff; }   // the block has ended here: the position gives nz
+  const bool end = ((e & TF_EOB) != 0u) || (BAND ? L.pos6 >= 1024u : an >= L.rowend);
+  if (run && end) { L.a_end = an; L.tok_end = L.tokoff; if (BAND) L.pos_end = L.pos6; }   // the block has ended here: the position gives nz
   return run && !end;
 }
 
 // The group's event point: lanes whose block has ended do ParseResiduals' bookkeeping and start their next block or
 // macroblock; lanes that wait for the row above try again.
-template <int MULTI>
-TK_FN void tf_events(TfLane& L, const TfCtx& c, int ended) {
+template <int MULTI, int BAND>
+TK_FN void tf_events(TfLaneT<BAND>& L, const TfCtx& c, int ended) {
   int need_mb = (L.pend == TF_NEED_MB);
   L.pend = TF_RUN;
   if (ended) {
     L.a = L.a_end; L.tokoff = L.tok_end;
+    if (BAND) L.pos6 = L.pos_end;
     if (tf_block_end(L, c)) { tf_mb_finish<MULTI>(L, c, 1); need_mb = 1; }
   }
   if (TF_UNLIKELY(need_mb)) {
@@ -704,8 +762,8 @@ TK_FN void tf_events(TfLane& L, const TfCtx& c, int ended) {
 
 // One group: four decodes, then the event point for the lanes that need it. A running lane whose block ends inside the
 // group keeps stepping on garbage with its reader frozen (fd_bit_guarded) until the event point puts it right.
-template <int MULTI, int RING>
-TK_FN void tf_group_flat(TfLane& L, const TfCtx& c) {
+template <int MULTI, int RING, int BAND>
+TK_FN void tf_group_flat(TfLaneT<BAND>& L, const TfCtx& c) {
   const bool run0 = L.pend == TF_RUN;
   if (run0) fd_fill<RING>(L.d);
   bool run = run0;

@@ -32,6 +32,7 @@ typedef uint32_t tk_saddr;   // address inside the shared-memory window
 TK_FN tk_saddr tk_saddr_of(const void* p) { return (tk_saddr)__cvta_generic_to_shared(p); }
 TK_FN uint32_t tk_lds_u8(tk_saddr a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 TK_FN uint32_t tk_lds_u16(tk_saddr a) { uint32_t v; asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+TK_FN int32_t tk_lds_s16(tk_saddr a) { int32_t v; asm("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 TK_FN uint32_t tk_lds_u32(tk_saddr a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 TK_FN void tk_lds_v2(tk_saddr a, uint32_t& x, uint32_t& y) { asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(a)); }
 // ring words and the ring protocol words change under the reader's feet: volatile accesses
@@ -61,6 +62,7 @@ typedef uintptr_t tk_saddr;
 TK_FN tk_saddr tk_saddr_of(const void* p) { return (tk_saddr)p; }
 TK_FN uint32_t tk_lds_u8(tk_saddr a) { return *(const uint8_t*)a; }
 TK_FN uint32_t tk_lds_u16(tk_saddr a) { return *(const uint16_t*)a; }
+TK_FN int32_t tk_lds_s16(tk_saddr a) { return *(const int16_t*)a; }
 TK_FN uint32_t tk_lds_u32(tk_saddr a) { return *(const uint32_t*)a; }
 TK_FN void tk_lds_v2(tk_saddr a, uint32_t& x, uint32_t& y) { x = ((const uint32_t*)a)[0]; y = ((const uint32_t*)a)[1]; }
 TK_FN uint32_t tk_ldsv_u32(tk_saddr a) { return *(volatile const uint32_t*)a; }

@@ -51,6 +51,52 @@ extern "C" int emu_decode_window(const uint8_t* data, size_t size, int csp, int 
 // options.dithering_strength = strength (0..100) on the whole picture.
 static int g_emu_dither_f = 0, g_emu_alpha_dither = 0;
 
+// K2 with the fp parser (k_parse_tokens_fp): the image's partitions as lanes advanced round-robin, one group at a time.
+template <int BAND>
+static void emu_fp_tokens(FrameHdr& hdr, const uint8_t* frame, int mb_w, int rows, int variant, std::vector<uint32_t>& mbinfo,
+                          std::vector<uint32_t>& tokens, std::vector<MbTok>& mbtok) {
+  const int P = hdr.num_parts;
+  std::vector<uint8_t> imgmem(TF_IMG_BYTES_B(BAND) + 1024 + 1024 + 128);   // (wandering lanes of the banded layout read a little below the rows)
+  uint8_t* img = (uint8_t*)(((uintptr_t)imgmem.data() + 1024 + 1023) & ~(uintptr_t)1023);
+  std::vector<uint64_t> tabmem((sizeof(TfTables) + 7) / 8);
+  TfTables* ttab = (TfTables*)tabmem.data();
+  tf_image_fill(img, &hdr, 0, 1, BAND);
+  tf_tables_fill(ttab, 0, 1);
+  std::vector<uint16_t> topctx((size_t)(P + 1) * mb_w, 0);
+  std::vector<int> progress(VP8B_MAX_PARTS, 0);
+  std::vector<TfLaneT<BAND>> lanes(P);
+  std::vector<TfCtx> ctxs(P);
+  std::vector<int> live(P, 0);
+  for (int p = 0; p < P && p < rows; ++p) {
+    TfCtx& cc = ctxs[p];
+    cc.img_s = tk_saddr_of(img); cc.tab_s = tk_saddr_of(ttab);
+    cc.k.mant_mask = 0x007fffffu; cc.k.exp46 = TF_EXP46;
+    cc.topctx = topctx.data(); cc.progress = progress.data();
+    cc.mbinfo = mbinfo.data(); cc.mbtok = mbtok.data(); cc.tokens = tokens.data();
+    cc.mb_w = mb_w; cc.rows = rows; cc.P = P; cc.part = p; cc.use_skip = hdr.use_skip; cc.ctx_stride = mb_w;
+    tf_lane_init(lanes[p], cc, frame, &hdr);
+    live[p] = 1;
+  }
+  const bool inline_style = (variant & 16) != 0;   // variant bit 4: a branch per decode instead of the straight-line groups
+  if (inline_style && P == 1 && live[0] && !tf_mb_next<0>(lanes[0], ctxs[0])) { tf_lane_park(lanes[0], ctxs[0]); live[0] = 0; }
+  for (bool any = true; any;) {
+    any = false;
+    for (int p = P - 1; p >= 0; --p) {   // reverse order: exercises the wait-for-progress path
+      if (!live[p]) continue;
+      any = true;
+      // parked lanes keep stepping, harmlessly, like on the device
+      if (inline_style) { if (P > 1) tf_group_inline<1, 0>(lanes[p], ctxs[p]); else tf_group_inline<0, 0>(lanes[p], ctxs[p]); }
+      else { if (P > 1) tf_group_flat<1, 0>(lanes[p], ctxs[p]); else tf_group_flat<0, 0>(lanes[p], ctxs[p]); }
+      live[p] = lanes[p].alive;
+    }
+  }
+  for (int p = 0; p < P && p < rows; ++p) if (lanes[p].status != VP8B_OK) hdr.status = lanes[p].status;
+  if (hdr.status != VP8B_OK) {   // like the prologue of k_reconstruct
+    const int row = tf_find_failed_row(mbtok.data(), mb_w, rows);
+    if (row < hdr.fail_row) hdr.fail_row = row;
+  }
+}
+
 // K6's two serial passes on an ALPH chunk (k_alpha_header, k_alpha_pixels): leaves the status and, after a failure, the alpha
 // row the reference would have been asked for when it met it (AlphaHdr::fail_row).
 static void emu_alpha_passes(const uint8_t* alph, uint32_t alph_size, const ImgDesc& im, AlphaHdr* ah, std::vector<uint32_t>& coded,
@@ -191,48 +237,11 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
   // K2: tokens
   if (literal) {   // done above
   } else if (variant & 64) {   // fp parser: one lane per partition, one decode per lane per round, levels as a token stream
-    const int P = hdr.num_parts;
     tokens.assign(nmb * TF_TOKENS_PER_MB, 0xffffffffu);
     mbtok.assign(nmb, MbTok{ 0xffffffffu, 0xffffffffu });
-    std::vector<uint8_t> imgmem(TF_IMG_BYTES + 1024 + 128);
-    uint8_t* img = (uint8_t*)(((uintptr_t)imgmem.data() + 1023) & ~(uintptr_t)1023);
-    std::vector<uint64_t> tabmem((sizeof(TfTables) + 7) / 8);
-    TfTables* ttab = (TfTables*)tabmem.data();
-    tf_image_fill(img, &hdr, 0, 1);
-    tf_tables_fill(ttab, 0, 1);
-    std::vector<uint16_t> topctx((size_t)(P + 1) * mb_w, 0);
-    std::vector<int> progress(VP8B_MAX_PARTS, 0);
-    std::vector<TfLane> lanes(P);
-    std::vector<TfCtx> ctxs(P);
-    std::vector<int> live(P, 0);
-    for (int p = 0; p < P && p < rows; ++p) {
-      TfCtx& cc = ctxs[p];
-      cc.img_s = tk_saddr_of(img); cc.tab_s = tk_saddr_of(ttab);
-      cc.k.mant_mask = 0x007fffffu; cc.k.exp46 = TF_EXP46;
-      cc.topctx = topctx.data(); cc.progress = progress.data();
-      cc.mbinfo = mbinfo.data(); cc.mbtok = mbtok.data(); cc.tokens = tokens.data();
-      cc.mb_w = mb_w; cc.rows = rows; cc.P = P; cc.part = p; cc.use_skip = hdr.use_skip; cc.ctx_stride = mb_w;
-      tf_lane_init(lanes[p], cc, frame, &hdr);
-      live[p] = 1;
-    }
-    const bool inline_style = (variant & 16) != 0;   // variant bit 4: a branch per decode instead of the straight-line groups
-    if (inline_style && P == 1 && live[0] && !tf_mb_next<0>(lanes[0], ctxs[0])) { tf_lane_park(lanes[0], ctxs[0]); live[0] = 0; }
-    for (bool any = true; any;) {
-      any = false;
-      for (int p = P - 1; p >= 0; --p) {   // reverse order: exercises the wait-for-progress path
-        if (!live[p]) continue;
-        any = true;
-        // parked lanes keep stepping, harmlessly, like on the device
-        if (inline_style) { if (P > 1) tf_group_inline<1, 0>(lanes[p], ctxs[p]); else tf_group_inline<0, 0>(lanes[p], ctxs[p]); }
-        else { if (P > 1) tf_group_flat<1, 0>(lanes[p], ctxs[p]); else tf_group_flat<0, 0>(lanes[p], ctxs[p]); }
-        live[p] = lanes[p].alive;
-      }
-    }
-    for (int p = 0; p < P && p < rows; ++p) if (lanes[p].status != VP8B_OK) hdr.status = lanes[p].status;
-    if (hdr.status != VP8B_OK) {   // like the prologue of k_reconstruct
-      const int row = tf_find_failed_row(mbtok.data(), mb_w, rows);
-      if (row < hdr.fail_row) hdr.fail_row = row;
-    }
+    // variant bit 7: the banded layout of the probability rows (the launches with very many small images)
+    if (variant & 128) emu_fp_tokens<1>(hdr, frame, mb_w, rows, variant, mbinfo, tokens, mbtok);
+    else emu_fp_tokens<0>(hdr, frame, mb_w, rows, variant, mbinfo, tokens, mbtok);
   } else if (variant & 8) {   // lockstep parser: one lane per partition, one decode per lane per round
     const int P = hdr.num_parts;
     std::vector<uint8_t> imgmem(TL_IMG_BYTES + 16 + 128);   // the look-ahead loads run up to 63 bytes past the rows

@@ -344,7 +344,7 @@ def test_crop_and_flip(W, ref, manifest, amanifest):
             assert np.array_equal(want, got.reshape(-1))
 
 
-@pytest.mark.parametrize("mapping", ["f:0", "f:1", "f:0:ring", "f:1:ring", "warp", "k", "k:1", "k:2", "lanes"])
+@pytest.mark.parametrize("mapping", ["f:0", "f:1", "f:0:band", "f:1:band", "f:0:ring", "f:1:ring", "warp", "k", "k:1", "k:2", "lanes"])
 def test_every_token_mapping(mapping):
     """The default token parser (f: lockstep lanes with the fp32 boolean decoder and token-stream output) picks its run style
     by lanes per warp; here both are forced in turn (f:0 a branch per decode, f:1 straight-line groups), and so is each of
@@ -358,6 +358,8 @@ def test_every_token_mapping(mapping):
     env = dict(os.environ, WEBP_B200_TOKEN_MAP=mapping.split(":")[0], WEBP_B200_TOKEN_MAP_INNER="1")
     if ":" in mapping:   # the lockstep parsers' ways of running their lanes (block ends on the spot, grouped event points, straight-line groups)
         env["WEBP_B200_TOKEN_GROUPED"] = mapping.split(":")[1]
+    if mapping.endswith(":band"):   # the banded layout of the probability rows (launches with very many small images take it by themselves)
+        env["WEBP_B200_TOKEN_BAND"] = "1"
     if mapping.endswith(":ring"):   # compressed bytes through shared-memory rings filled by cp.async.bulk instead of global loads
         env["WEBP_B200_TOKEN_RING"] = "1"
     select = "manifest or mixed_sizes or fresh_corpora or full_size or damaged or many_streams"
