@@ -128,6 +128,13 @@ typedef struct WebPBatchTimings {
 } WebPBatchTimings;
 WEBP_EXTERN int WebPBatchGetTimings(const WebPBatch* batch, WebPBatchTimings* t);
 
+/* Test hook (not part of the stable interface): what the two parse kernels left for item `item` of a batch that was just
+   decoded -- MbInfo (4 words per macroblock: intra modes, non-zero codes, flags) and the coefficient LEVELS (400 per
+   macroblock: blocks 0-23 and the Y2 block, parse order inside a block), read back from the device's scratch. Only valid
+   straight after WebPBatchDecode / WebPBatchWait of a single-wave batch, before anything else runs on that device.
+   Returns the number of macroblocks written (<= max_mb), -1 when the scratch is not this batch's any more or cannot be read. */
+WEBP_EXTERN int WebPBatchDebugStages(WebPBatch* batch, int item, uint32_t* mbinfo, int16_t* levels, size_t max_mb);
+
 /* Page-locked host memory for inputs/outputs (plain malloc works too, just slower over PCIe). */
 WEBP_EXTERN void* WebPBatchHostAlloc(size_t size);
 WEBP_EXTERN void WebPBatchHostFree(void* ptr);

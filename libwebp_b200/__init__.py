@@ -100,7 +100,7 @@ EXPORTS = [  # every symbol include/webp/*.h declares
     "WebPBatchOptionsInitInternal", "WebPDecodeBatch", "WebPBatchCreate", "WebPBatchDecode", "WebPBatchDownload",
     "WebPBatchDestroy", "WebPBatchOutput", "WebPBatchGetTimings", "WebPBatchHostAlloc", "WebPBatchHostFree",
     "WebPBatchDeviceCount", "WebPBatchLastError", "WebPBatchSubmit", "WebPBatchWait", "WebPBatchSetCacheLimit",
-    "WebPBatchTrimCache", "WebPAnimBatchGetInfo", "WebPAnimDecodeBatch",
+    "WebPBatchTrimCache", "WebPAnimBatchGetInfo", "WebPAnimDecodeBatch", "WebPBatchDebugStages",
 ]
 
 _lib = None
@@ -134,6 +134,7 @@ def lib():
         L.WebPBatchDestroy.argtypes = [C.c_void_p]
         L.WebPBatchOutput.argtypes = [C.c_void_p, C.c_int, C.POINTER(WebPBatchPlane)]
         L.WebPBatchGetTimings.argtypes = [C.c_void_p, C.POINTER(WebPBatchTimings)]
+        L.WebPBatchDebugStages.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
         L.WebPBatchHostAlloc.restype = C.c_void_p
         L.WebPBatchHostAlloc.argtypes = [C.c_size_t]
         L.WebPBatchHostFree.argtypes = [C.c_void_p]

@@ -90,6 +90,7 @@ struct DeviceCtx {
   // touch it, and kernels of different batches are ordered (same stream, or through `scratch_free` when a caller
   // brought a stream of its own).
   Owned s_mbinfo, s_coeffs, s_tokens, s_mbtok, s_yuv, s_dither, s_band;
+  const void* scratch_owner = nullptr;   // the batch whose kernels wrote the scratch last (WebPBatchDebugStages)
   cudaEvent_t scratch_free = nullptr;   // recorded behind the last kernel queued so far
   bool scratch_used = false;
   // Pixel downloads are queued by a thread of their own. cudaMemcpyAsync returns at once only while the driver's queue
@@ -1169,6 +1170,7 @@ static bool batch_enqueue(WebPBatch* b, bool download) {
   b->launches = launches;
   CU_TRY(cudaEventRecord(ctx->scratch_free, s), "cudaEventRecord");
   ctx->scratch_used = true;
+  ctx->scratch_owner = b;
   // per-image status words, written into page-locked host memory by the device (see k_collect_status)
   {
     int* dev_view = nullptr;
@@ -1480,6 +1482,41 @@ extern "C" int WebPBatchGetTimings(const WebPBatch* b, WebPBatchTimings* t) {
   if (b == NULL || t == NULL) return 0;
   *t = b->timings;
   return 1;
+}
+
+// Test hook: see decode_batch.h. The scratch arrays are the device's, not the batch's: `scratch_owner` says whose data they hold.
+extern "C" int WebPBatchDebugStages(WebPBatch* b, int item, uint32_t* mbinfo, int16_t* levels, size_t max_mb) {
+  if (b == NULL || mbinfo == NULL || levels == NULL || item < 0 || item >= b->n) return -1;
+  if (!b->shards.empty() || b->ctx == nullptr || !b->decoded || b->waves.size() != 1 || !vp8k_tokens_use_stream()) return -1;
+  const int img = b->plan[item].img;
+  if (img < 0) return -1;
+  DeviceCtx* ctx = b->ctx;
+  DeviceGuard guard(ctx->device);
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  if (ctx->scratch_owner != b) return -1;
+  const ImgDesc& d = b->imgs[img];
+  const size_t n = (size_t)d.mb_w * d.mb_h;
+  if (n > max_mb) return -1;
+  if (cudaStreamSynchronize(b->stream) != cudaSuccess) return -1;
+  std::vector<uint32_t> toks(n * VP8B_TOKENS_PER_MB);
+  std::vector<uint32_t> mt(2 * n);
+  if (cudaMemcpy(mbinfo, (const uint8_t*)ctx->s_mbinfo.p + 16 * (size_t)d.mb_base, 16 * n, cudaMemcpyDeviceToHost) != cudaSuccess ||
+      cudaMemcpy(mt.data(), (const uint8_t*)ctx->s_mbtok.p + 8 * (size_t)d.mb_base, 8 * n, cudaMemcpyDeviceToHost) != cudaSuccess ||
+      cudaMemcpy(toks.data(), (const uint8_t*)ctx->s_tokens.p + 4 * (size_t)d.mb_base * VP8B_TOKENS_PER_MB, 4 * toks.size(), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  memset(levels, 0, sizeof(int16_t) * VP8B_COEFFS_PER_MB * n);
+  for (size_t m = 0; m < n; ++m) {
+    const uint32_t first = mt[2 * m], count = mt[2 * m + 1];
+    if (count > VP8B_TOKENS_PER_MB || (size_t)first + count > toks.size()) return -1;
+    for (uint32_t k = 0; k < count; ++k) {
+      const uint32_t t = toks[first + k];
+      const int mag = (int)((t >> 13) & 0xfffu);
+      levels[m * VP8B_COEFFS_PER_MB + ((t >> 25) & 31u) * 16u + ((t >> 6) & 15u)] = (int16_t)((t >> 31) ? -mag : mag);
+    }
+  }
+  return (int)n;
 }
 
 // ---------------------------------------------------------------------------------------------------------

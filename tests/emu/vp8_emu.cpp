@@ -50,6 +50,11 @@ extern "C" int emu_decode_window(const uint8_t* data, size_t size, int csp, int 
 // the scaled picture.
 // options.dithering_strength = strength (0..100) on the whole picture.
 static int g_emu_dither_f = 0, g_emu_alpha_dither = 0;
+// stage dump of the next emu_decode call (what the two parse stages leave: MbInfo, levels), for the device test hook's comparison
+static uint32_t* g_dump_mbinfo = nullptr;
+static int16_t* g_dump_levels = nullptr;
+static size_t g_dump_max_mb = 0;
+extern "C" void emu_set_stage_dump(uint32_t* mbinfo, int16_t* levels, size_t max_mb) { g_dump_mbinfo = mbinfo; g_dump_levels = levels; g_dump_max_mb = max_mb; }
 
 // K2 with the fp parser (k_parse_tokens_fp): the image's partitions as lanes advanced round-robin, one group at a time.
 template <int BAND>
@@ -346,6 +351,21 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
     for (int p = 0; p < P && p < rows; ++p) if (tp[p].status != VP8B_OK) hdr.status = tp[p].status;
   }
   if (hdr.status != VP8B_OK) return failed(hdr.status);
+  if (g_dump_mbinfo != nullptr && nmb <= g_dump_max_mb) {
+    memcpy(g_dump_mbinfo, mbinfo.data(), 16 * nmb);
+    memset(g_dump_levels, 0, sizeof(int16_t) * VP8B_COEFFS_PER_MB * nmb);
+    for (size_t m = 0; m < nmb; ++m) {
+      if (variant & 64) {
+        for (uint32_t k = 0; k < mbtok[m].count; ++k) {
+          const uint32_t t = tokens[mbtok[m].first + k];
+          const int mag = (int)TF_TOK_MAG(t);
+          g_dump_levels[m * VP8B_COEFFS_PER_MB + TF_TOK_BLOCK(t) * 16u + TF_TOK_POS(t)] = (int16_t)((t >> 31) ? -mag : mag);
+        }
+      } else {
+        memcpy(g_dump_levels + m * VP8B_COEFFS_PER_MB, coeffs.data() + m * VP8B_COEFFS_PER_MB, sizeof(int16_t) * VP8B_COEFFS_PER_MB);
+      }
+    }
+  }
 
   // K3: reconstruction wavefront (lag 2)
   {

@@ -4,6 +4,8 @@ plain-C oracle, and the compiled reference when oracle/_ref travelled to the box
 is bit-exact everywhere."""
 import ctypes as C
 
+import os
+
 import numpy as np
 import pytest
 
@@ -991,3 +993,42 @@ def test_unusable_slow_memory_buffer_is_reported_after_the_decode(W, ref, amanif
             if got[0][0] == 0:
                 assert np.array_equal(got[0][1], got[1][1])
     assert {0, 2, 7} <= seen, seen
+
+
+@pytest.mark.gpu
+def test_parse_stages_match_the_host_build(W, manifest, amanifest):
+    """Stage level, not pixels: what K1 and the token parser leave on the device (MbInfo: intra modes, non-zero codes, flags; the
+    coefficient levels of every block) against the same two stages of the device code's host build (tests/emu, itself pinned to
+    the oracle's stage dump by tests/test_emu.py). A regression in either parse shows here before it shows as wrong pixels."""
+    import ctypes as C
+    import subprocess
+    from conftest import ROOT
+    emu_dir = os.path.join(ROOT, "tests", "emu")
+    subprocess.check_call(["make", "-s", "-C", emu_dir])
+    E = C.CDLL(os.path.join(emu_dir, "libvp8_emu.so"))
+    E.emu_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+    E.emu_set_stage_dump.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    entries = [e for e in list(manifest) + list(amanifest) if e["data"].find(b"VP8 ") >= 0]
+    datas = [e["data"] for e in entries]
+    b = W.Batch(datas, W.MODE_RGBA, device=0, output=W.WEBP_BATCH_DEVICE)
+    assert b.create() == 0 and b.decode() == 0, W.last_error()
+    checked = 0
+    for i, e in enumerate(entries):
+        w, h = e["features"]["width"], e["features"]["height"]
+        nmb = ((w + 15) // 16) * ((h + 15) // 16)
+        mi_d = np.zeros((nmb, 4), np.uint32); lv_d = np.zeros((nmb, 400), np.int16)
+        n = W.lib().WebPBatchDebugStages(b.handle, i, mi_d.ctypes.data, lv_d.ctypes.data, nmb)
+        assert n == nmb, (e["file"], n)
+        mi_e = np.zeros((nmb, 4), np.uint32); lv_e = np.zeros((nmb, 400), np.int16)
+        E.emu_set_stage_dump(mi_e.ctypes.data, lv_e.ctypes.data, nmb)
+        out = np.zeros((h, w * 4), np.uint8)
+        st = E.emu_decode(e["data"], len(e["data"]), 1, 0, out.ctypes.data, out.size, w * 4, 64, None)
+        E.emu_set_stage_dump(None, None, 0)
+        assert st == 0, e["file"]
+        assert np.array_equal(mi_d[:, :3], mi_e[:, :3]), e["file"]                       # modes, non-zero codes
+        keep = np.uint32(~((1 << 23) | (1 << 24)) & 0xffffffff)                          # MBW_INNER / MBW_DITHER are K3's and the dither plan's
+        assert np.array_equal(mi_d[:, 3] & keep, mi_e[:, 3] & keep), e["file"]
+        assert np.array_equal(lv_d, lv_e), e["file"]
+        checked += int(np.count_nonzero(lv_e))
+    b.close()
+    assert checked > 100000
