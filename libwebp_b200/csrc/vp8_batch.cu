@@ -341,6 +341,9 @@ static VP8StatusCode prepare_host_buffer(int w, int h, WebPDecBuffer* b) {
   return check_host_buffer(b);
 }
 
+// For the incremental shim (webp_api.c): is this caller's buffer usable for a w x h picture? (hidden symbol)
+extern "C" int vp8b_prepare_host_buffer(int w, int h, WebPDecBuffer* b) { return (int)prepare_host_buffer(w, h, b); }
+
 // ---------------------------------------------------------------------------------------------------------
 struct ItemPlan {
   int img = -1;            // index among the device images, -1 when the item failed on the host

@@ -216,3 +216,26 @@ int vp8b_partition_starts_with_ff(const uint8_t* part0, size_t part0_size, size_
   }
   return 0;
 }
+
+/* Has the LAST token partition begun inside the bytes at hand? That is when VP8GetHeaders stops answering "suspended" for a
+   stream that is still arriving (ParsePartitions, vp8_dec.c:188-222: `part_start < buf_end`), i.e. when the reference's incremental
+   decoder gets its output area. `rest` = bytes at hand after the frame's 10-byte header. */
+int vp8b_last_partition_begun(const uint8_t* part0, size_t part0_size, size_t rest, int num_parts) {
+  const uint8_t* sz;
+  size_t left, start;
+  int p;
+  if (part0_size > rest) return 0;
+  sz = part0 + part0_size;
+  left = rest - part0_size;
+  if (left < 3u * (size_t)(num_parts - 1)) return 0;
+  left -= 3u * (size_t)(num_parts - 1);
+  start = 0;
+  for (p = 0; p < num_parts - 1; ++p) {
+    size_t psize = (size_t)sz[0] | ((size_t)sz[1] << 8) | ((size_t)sz[2] << 16);
+    if (psize > left) psize = left;
+    start += psize; left -= psize;
+    sz += 3;
+  }
+  (void)start;
+  return left > 0;
+}

@@ -29,6 +29,9 @@ VP8StatusCode vp8b_get_features(const uint8_t* data, size_t size, WebPBitstreamF
 /* Number of token partitions (1, 2, 4 or 8) announced in the first partition. */
 int vp8b_prescan_partitions(const uint8_t* part0, size_t part0_size);
 
+/* 1 once the last token partition has begun inside the `rest` bytes at hand after the frame's 10-byte header. */
+int vp8b_last_partition_begun(const uint8_t* part0, size_t part0_size, size_t rest, int num_parts);
+
 /* 1 when the first partition or a token partition starts with byte 0xFF (`rest` = frame bytes after the 10-byte header). */
 int vp8b_partition_starts_with_ff(const uint8_t* part0, size_t part0_size, size_t rest, int num_parts);
 

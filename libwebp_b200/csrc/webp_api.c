@@ -150,14 +150,22 @@ uint8_t* WebPDecodeYUVInto(const uint8_t* data, size_t size, uint8_t* luma, size
  * reference's interface and status protocol and does the work in one go: WebPIAppend() accumulates, WebPIUpdate()
  * looks at the caller's growing buffer, both answer VP8_STATUS_SUSPENDED until the whole file is there (the RIFF
  * size says when; a bare VP8 stream is tried on every call and "not enough data" reads as suspended), then the
- * image is decoded once on the device and the status is VP8_STATUS_OK or the decode error, which sticks. */
+ * image is decoded once on the device and the status is VP8_STATUS_OK or the decode error, which sticks.
+ * The getters follow the reference's protocol as far as a decoder that produces all rows at once can: NULL while the
+ * reference would still be reading headers (idec_dec.c:843-851: state <= STATE_VP8_PARTS0), then the caller's buffer with
+ * "no rows yet" (last_y = 0) until the picture is complete, then all rows. A caller that draws data[0 .. stride * last_y)
+ * after every append (the prefix comparisons of src/tests.zig:676-686) sees nothing wrong, only later. */
 struct WebPIDecoder {
   WebPDecoderConfig* config;     /* caller's config (WebPIDecode) or NULL */
   WebPDecoderConfig own_config;  /* used when the caller gave only an output buffer, or nothing */
   WebPDecBuffer* final_output;   /* WebPINewDecoder(output_buffer): receives the result */
   uint8_t* buf; size_t size, cap; int mode;   /* 0 unset, 1 append, 2 update */
   VP8StatusCode status;          /* SUSPENDED until decoded, then final */
+  int early;                     /* 1: the output area exists (the caller's buffer), no rows in it yet; 2: and its dimensions are known */
 };
+
+int vp8b_prepare_host_buffer(int w, int h, WebPDecBuffer* b);   /* vp8_batch.cu */
+int vp8b_host_headers_status(const uint8_t* frame, size_t frame_size, uint32_t part0_size, int width, int height, int is_lossless);   /* vp8_host_probe.cpp */
 
 static WebPIDecoder* NewIDecoder(WebPDecBuffer* output_buffer, WebPDecoderConfig* config) {
   WebPIDecoder* const idec = (WebPIDecoder*)calloc(1, sizeof(*idec));
@@ -210,6 +218,31 @@ static VP8StatusCode IDecodeNow(WebPIDecoder* idec, const uint8_t* data, size_t 
     WebPBitstreamFeatures f;
     st = WebPGetFeatures(data, size, &f);
     if (st != VP8_STATUS_OK && st != VP8_STATUS_NOT_ENOUGH_DATA) { idec->status = st; return st; }
+    if (st == VP8_STATUS_OK && idec->early < 2) {
+      /* Past the point where the reference starts answering with an output area (the first partition of a VP8 frame is in,
+       * idec_dec.c:DecodePartition0; a VP8L stream: its container header)? Only for a caller's own buffer and a plain request:
+       * the size of an area that depends on crop or scaling options is settled by the one decode. */
+      Vp8Container c;
+      WebPDecBuffer* const out = (idec->config != NULL) ? &idec->config->output
+                               : (idec->final_output != NULL) ? idec->final_output : &idec->own_config.output;
+      const WebPDecoderOptions* const o = &cfg->options;
+      if (out->is_external_memory > 0 && !o->use_cropping && !o->use_scaling &&
+          vp8b_parse_container(data, size, 0, &c) == VP8_STATUS_OK && !c.has_animation) {
+        int dims = 0;
+        if (c.is_lossless) {
+          /* the area is there from the container header on (idec state VP8L_HEADER), its dimensions once the VP8L header --
+           * transforms, colour cache, every group's codes -- has been decoded from what has arrived (idec_dec.c:DecodeVP8LHeader) */
+          idec->early = 1;
+          dims = size > c.frame_offset &&
+                 vp8b_host_headers_status(data + c.frame_offset, size - c.frame_offset, 0, f.width, f.height, 1) == 0;
+        } else {
+          dims = size >= c.frame_offset + 10 + (size_t)c.part0_size &&
+                 vp8b_last_partition_begun(data + c.frame_offset + 10, c.part0_size, size - c.frame_offset - 10,
+                                           vp8b_prescan_partitions(data + c.frame_offset + 10, c.part0_size));
+        }
+        if (dims && vp8b_prepare_host_buffer(f.width, f.height, out) == VP8_STATUS_OK) idec->early = 2;
+      }
+    }
     return VP8_STATUS_SUSPENDED;
   }
   if (idec->config == NULL && idec->final_output != NULL) {   /* decode straight into the caller's buffer */
@@ -307,8 +340,14 @@ WebPIDecoder* WebPINewYUV(uint8_t* luma, size_t luma_size, int luma_stride, uint
   return WebPINewYUVA(luma, luma_size, luma_stride, u, u_size, u_stride, v, v_size, v_stride, NULL, 0, 0);
 }
 
+/* Rows of the output area that hold pixels: none until the one decode, then all of them. */
+static int IDecRows(const WebPIDecoder* idec, const WebPDecBuffer* output) {
+  return (idec->status == VP8_STATUS_OK) ? output->height : 0;
+}
+
 static const WebPDecBuffer* IDecOutput(const WebPIDecoder* idec) {
-  if (idec == NULL || idec->status != VP8_STATUS_OK) return NULL;   /* nothing displayable before the one decode */
+  if (idec == NULL) return NULL;
+  if (idec->status != VP8_STATUS_OK && !(idec->status == VP8_STATUS_SUSPENDED && idec->early)) return NULL;   /* no area yet */
   if (idec->config != NULL) return &idec->config->output;
   if (idec->final_output != NULL) return idec->final_output;
   return &idec->own_config.output;
@@ -320,7 +359,7 @@ const WebPDecBuffer* WebPIDecodedArea(const WebPIDecoder* idec, int* left, int* 
   if (top != NULL) *top = 0;
   if (src != NULL) {
     if (width != NULL) *width = src->width;
-    if (height != NULL) *height = src->height;
+    if (height != NULL) *height = IDecRows(idec, src);   /* idec_dec.c:869: the decoded area ends at last_y */
   } else {
     if (width != NULL) *width = 0;
     if (height != NULL) *height = 0;
@@ -331,7 +370,7 @@ const WebPDecBuffer* WebPIDecodedArea(const WebPIDecoder* idec, int* left, int* 
 uint8_t* WebPIDecGetRGB(const WebPIDecoder* idec, int* last_y, int* width, int* height, int* stride) {
   const WebPDecBuffer* const output = IDecOutput(idec);
   if (output == NULL || output->colorspace >= MODE_YUV) return NULL;
-  if (last_y != NULL) *last_y = output->height;
+  if (last_y != NULL) *last_y = IDecRows(idec, output);
   if (width != NULL) *width = output->width;
   if (height != NULL) *height = output->height;
   if (stride != NULL) *stride = output->u.RGBA.stride;
@@ -342,7 +381,7 @@ uint8_t* WebPIDecGetYUVA(const WebPIDecoder* idec, int* last_y, uint8_t** u, uin
                          int* width, int* height, int* stride, int* uv_stride, int* a_stride) {
   const WebPDecBuffer* const output = IDecOutput(idec);
   if (output == NULL || output->colorspace < MODE_YUV) return NULL;
-  if (last_y != NULL) *last_y = output->height;
+  if (last_y != NULL) *last_y = IDecRows(idec, output);
   if (u != NULL) *u = output->u.YUVA.u;
   if (v != NULL) *v = output->u.YUVA.v;
   if (a != NULL) *a = output->u.YUVA.a;

@@ -167,6 +167,60 @@ def test_incremental_protocol_without_device(product, manifest):
     assert L.WebPIAppend(None, data, 10) == product.VP8_STATUS_INVALID_PARAM
 
 
+def test_incremental_output_area_before_the_last_byte(product, ref, manifest, lmanifest):
+    """The getters of the incremental API against the reference's, append by append (the protocol of src/tests.zig:676-686):
+    NULL while the headers / first partition are still arriving (idec_dec.c:843-851), then the caller's buffer with last_y rows
+    in it. The reference fills rows as data arrives, this library none until the picture is complete: whenever the reference
+    has an area this library has one too, never with more rows than the reference's, and the caller's buffer is what comes back."""
+    import ctypes as C
+    P, Q = product.lib(), ref.lib()
+    for L in (P, Q):
+        L.WebPInitDecoderConfigInternal.argtypes = [C.POINTER(product.WebPDecoderConfig), C.c_int]
+        L.WebPINewDecoder.restype = C.c_void_p
+        L.WebPINewDecoder.argtypes = [C.c_void_p]
+        L.WebPIAppend.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+        L.WebPIDelete.argtypes = [C.c_void_p]
+        L.WebPIDecGetRGB.restype = C.c_void_p
+        L.WebPIDecGetRGB.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
+    phases = [False, False]
+    for e in list(manifest[:6]) + list(lmanifest[:3]):
+        data = e["data"]
+        w, h = e["features"]["width"], e["features"]["height"]
+        areas = []
+        for L in (Q, P):
+            cfg = product.WebPDecoderConfig()
+            L.WebPInitDecoderConfigInternal(C.byref(cfg), product.WEBP_DECODER_ABI_VERSION)
+            buf = np.zeros(w * h * 4, np.uint8)
+            cfg.output.colorspace = product.MODE_RGBA
+            cfg.output.is_external_memory = 1
+            cfg.output.u.RGBA.rgba = buf.ctypes.data
+            cfg.output.u.RGBA.stride = 4 * w
+            cfg.output.u.RGBA.size = buf.size
+            idec = L.WebPINewDecoder(C.addressof(cfg.output))
+            seen = []
+            step = max(64, len(data) // 7)
+            cuts = [0, 16, 40] + list(range(40 + step, len(data) - 1, step)) + [len(data) - 1]   # everything but the last byte: no device needed
+            for lo, hi in zip(cuts[:-1], cuts[1:]):
+                st = L.WebPIAppend(idec, data[lo:hi], hi - lo)
+                if L is Q and st == product.VP8_STATUS_OK:
+                    break                                      # the reference is done once the last macroblock is (padding may follow)
+                assert st == product.VP8_STATUS_SUSPENDED, (e["file"], lo, st)
+                ly, ww, hh, ss = C.c_int(-1), C.c_int(-1), C.c_int(-1), C.c_int(-1)
+                ptr = L.WebPIDecGetRGB(idec, C.byref(ly), C.byref(ww), C.byref(hh), C.byref(ss))
+                seen.append((bool(ptr), ptr == buf.ctypes.data if ptr else None, ly.value if ptr else None, ww.value if ptr else None,
+                             hh.value if ptr else None, ss.value if ptr else None))
+            L.WebPIDelete(idec)
+            areas.append(seen)
+        for r, p in zip(*areas):
+            assert r[0] == p[0], (e["file"], r, p)             # an area exactly when the reference has one
+            if r[0]:
+                assert p[1] and r[1]                            # the caller's buffer
+                assert p[2] == 0 and p[2] <= r[2]               # no rows yet here; the reference may have some
+                assert p[3:] == r[3:], (e["file"], r, p)       # width, height, stride
+        phases[0] |= any(r[0] for r in areas[0]); phases[1] |= not areas[0][0][0]
+    assert phases == [True, True]   # both phases were seen: no area yet / an area before the last byte
+
+
 def test_lossless_crop_window_is_checked_at_the_offsets_as_given(product, lmanifest):
     """WebPAllocateDecBuffer checks the crop window at offsets snapped to even (buffer_dec.c:184-195), the lossless decoder
     then crops at the offsets as given (WebPIoInitFromOptions snaps for YUV420 sources only, webp_dec.c:809-817) and refuses a
