@@ -277,7 +277,7 @@ def test_incremental_api(W, port, manifest, amanifest):
         L.WebPIDelete(idec)
         L.WebPFreeDecBuffer(C.byref(buf))
         assert np.array_equal(got[:, :w * 4], want[:, :w * 4])
-        # WebPINewRGB with an external buffer + the getters: nothing displayable before the last byte, the whole picture after
+        # WebPINewRGB with an external buffer + the getters: no rows before the last byte, the whole picture after
         L.WebPINewRGB.restype = C.c_void_p
         L.WebPINewRGB.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_int]
         L.WebPIDecGetRGB.restype = C.c_void_p
@@ -288,10 +288,17 @@ def test_incremental_api(W, port, manifest, amanifest):
         idec = L.WebPINewRGB(W.MODE_RGBA, ext.ctypes.data, ext.size, w * 4 + 16)
         assert idec and not L.WebPINewRGB(W.MODE_YUV, None, 0, 0) and not L.WebPINewRGB(W.MODE_RGBA, ext.ctypes.data, 0, 0)
         ly, ww, hh, ss = C.c_int(-1), C.c_int(-1), C.c_int(-1), C.c_int(-1)
-        assert L.WebPIAppend(idec, data[:len(data) // 2], len(data) // 2) == W.VP8_STATUS_SUSPENDED
-        assert not L.WebPIDecGetRGB(idec, C.byref(ly), C.byref(ww), C.byref(hh), C.byref(ss))
+        assert L.WebPIAppend(idec, data[:20], 20) == W.VP8_STATUS_SUSPENDED
+        assert not L.WebPIDecGetRGB(idec, C.byref(ly), C.byref(ww), C.byref(hh), C.byref(ss))        # headers still arriving: no area
         assert not L.WebPIDecodedArea(idec, None, None, C.byref(ww), C.byref(hh)) and ww.value == 0 and hh.value == 0
-        assert L.WebPIAppend(idec, data[len(data) // 2:], len(data) - len(data) // 2) == W.VP8_STATUS_OK
+        assert L.WebPIAppend(idec, data[20:len(data) - 1], len(data) - 21) == W.VP8_STATUS_SUSPENDED
+        # all but the last byte in: the caller's buffer with the picture's dimensions and no rows yet (tests/test_abi.py walks this
+        # against the reference append by append)
+        p = L.WebPIDecGetRGB(idec, C.byref(ly), C.byref(ww), C.byref(hh), C.byref(ss))
+        assert p == ext.ctypes.data and (ly.value, ww.value, hh.value, ss.value) == (0, w, h, w * 4 + 16)
+        assert L.WebPIDecodedArea(idec, None, None, C.byref(ww), C.byref(hh)) and (ww.value, hh.value) == (w, 0)
+        assert not ext.any()
+        assert L.WebPIAppend(idec, data[len(data) - 1:], 1) == W.VP8_STATUS_OK
         p = L.WebPIDecGetRGB(idec, C.byref(ly), C.byref(ww), C.byref(hh), C.byref(ss))
         assert p == ext.ctypes.data and (ly.value, ww.value, hh.value, ss.value) == (h, w, h, w * 4 + 16)
         assert L.WebPIDecodedArea(idec, None, None, C.byref(ww), C.byref(hh)) and (ww.value, hh.value) == (w, h)
