@@ -1022,17 +1022,41 @@ __global__ void __launch_bounds__(32) k_alpha_header(const uint8_t* __restrict__
                     (uint32_t*)pl.tdata, &ahdrs[a], (im.flags & VP8B_FLAG_LOSSLESS) ? 1 : 0);
 }
 
+// The pixel loop of a picture is serial (prefix codes, LZ77): one lane per picture. Two kernels over the same list, each passing
+// by the pictures of the other: ALPH planes without a colour cache let lane 0 queue their backward references and the whole warp
+// carry them out (alph_decode_pixels_warp: alpha planes are long runs, 512 planes of 4096x4096 384 -> 150 ms); pictures with
+// a colour cache (the copies feed it in order) and whole VP8L pictures (photographs: literals and short copies, the queued form
+// costs them 20 %) keep the one-lane loop, in a kernel of its own because that loop is one dependent chain whose speed moves by
+// 10-20 % with the code compiled around it (1024 full-HD photographs: 1126 ms alone, 1296 ms sharing a kernel with the other
+// loop; profiles/r02y).
+AL_FN int alpha_takes_the_warp(const AlphaHdr* hd) { return hd->cache_bits == 0 && !hd->lossless; }
+
 __global__ void __launch_bounds__(32) k_alpha_pixels(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
                                                      const int* __restrict__ aimgs, const AlphaPlan* __restrict__ plans,
                                                      AlphaHdr* ahdrs) {
   if (threadIdx.x != 0) return;
   const int a = blockIdx.x;
   AlphaHdr* hd = &ahdrs[a];
-  if (hd->status != AL_OK || hd->method == 0) return;
+  if (hd->status != AL_OK || hd->method == 0 || alpha_takes_the_warp(hd)) return;
   const ImgDesc im = imgs[aimgs[a]];
   const AlphaPlan pl = plans[a];
   hd->status = alph_decode_pixels(arena + im.alpha_in, im.alpha_size, im.height, (int)im.crop_y + (int)im.out_h, hd, (const uint16_t*)pl.meta,
                                   (uint32_t*)pl.tables, (AlGroup*)pl.groups, (uint8_t*)pl.scratch, (uint32_t*)pl.coded);
+}
+
+__global__ void __launch_bounds__(32) k_alpha_pixels_warp(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
+                                                          const int* __restrict__ aimgs, const AlphaPlan* __restrict__ plans,
+                                                          AlphaHdr* ahdrs) {
+  const int a = blockIdx.x;
+  AlphaHdr* hd = &ahdrs[a];
+  if (hd->status != AL_OK || hd->method == 0 || !alpha_takes_the_warp(hd)) return;
+  const ImgDesc im = imgs[aimgs[a]];
+  const AlphaPlan pl = plans[a];
+  const int st = alph_decode_pixels_warp(arena + im.alpha_in, im.alpha_size, im.height, (int)im.crop_y + (int)im.out_h, hd, (const uint16_t*)pl.meta,
+                                         (uint32_t*)pl.tables, (AlGroup*)pl.groups, (uint8_t*)pl.scratch, (uint32_t*)pl.coded,
+                                         AL_COPYQ_PTR(pl.scratch), (int)threadIdx.x);
+  __syncwarp();
+  if (threadIdx.x == 0) hd->status = st;
 }
 
 #define ALPHA_FINISH_THREADS 1024
@@ -1083,6 +1107,7 @@ extern "C" void vp8k_alpha_header(cudaStream_t s, const uint8_t* arena, const Im
 extern "C" void vp8k_alpha_decode(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, const int* aimgs, const AlphaPlan* plans,
                                   AlphaHdr* ahdrs, uint8_t* alpha_arena, int count) {
   k_alpha_pixels<<<count, 32, 0, s>>>(arena, imgs, aimgs, plans, ahdrs);
+  k_alpha_pixels_warp<<<count, 32, 0, s>>>(arena, imgs, aimgs, plans, ahdrs);
   k_alpha_finish<<<count, ALPHA_FINISH_THREADS, 0, s>>>(arena, imgs, aimgs, plans, ahdrs, alpha_arena);
   k_alpha_smooth<<<count, ALPHA_FINISH_THREADS, 0, s>>>(imgs, aimgs, plans, ahdrs, alpha_arena);
 }

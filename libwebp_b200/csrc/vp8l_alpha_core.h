@@ -446,7 +446,13 @@ struct AlphaHdr {
 #define AL_SCRATCH_FIXED_BYTES (4u * AL_PASSA_FIXED_WORDS + ((uint32_t)sizeof(AlScratch) + 15u) / 16u * 16u)
 // ... + which group numbers the meta-Huffman image uses: one bit each, and the count of used numbers below every 32
 #define AL_USED_BITS_WORDS (AL_MAX_GROUPS / 32)
-#define AL_SCRATCH_BYTES (AL_SCRATCH_FIXED_BYTES + 4u * AL_USED_BITS_WORDS + 2u * AL_USED_BITS_WORDS)
+#define AL_COPYQ 256   // queued backward references per flush (alph_decode_pixels_warp): 2 + 3 * AL_COPYQ words
+#define AL_COPYQ_OFFSET (AL_SCRATCH_FIXED_BYTES + 4u * AL_USED_BITS_WORDS + 2u * AL_USED_BITS_WORDS)
+#define AL_SCRATCH_BYTES (AL_COPYQ_OFFSET + 4u * (2u + 3u * AL_COPYQ) + 8u)
+// (the queue lives in the image's scratch, not in shared memory: a kernel that declares shared memory gives up that much
+// L1, and the one-lane pixel loop of the pictures that do not queue lives on L1 hits -- whole-picture VP8L 1125 -> 1375 ms
+// with 3 KB of shared memory per block, profiles/r02y)
+#define AL_COPYQ_PTR(scratch) ((uint32_t*)((uint8_t*)(scratch) + AL_COPYQ_OFFSET))
 // dense index of group g among the used ones
 #define AL_USED_BITS(scratch) ((uint32_t*)((uint8_t*)(scratch) + AL_SCRATCH_FIXED_BYTES))
 #define AL_USED_BELOW(scratch) ((uint16_t*)(AL_USED_BITS(scratch) + AL_USED_BITS_WORDS))
@@ -701,6 +707,178 @@ AL_NOINLINE int alph_decode_pixels(const uint8_t* alph, uint32_t alph_size, int 
   if (use_8b ? (b.eos && pos < end) : b.eos) return AL_BITSTREAM_ERROR;
   return AL_OK;
 }
+
+#if defined(__CUDACC__) && !defined(VP8_EMU)
+// Backward references with more than one lane (the device): the serial decode (lane 0) does not need a single pixel VALUE as long
+// as there is no colour cache -- symbols, positions, group switches and every failure rule depend on positions only -- so it
+// writes its literals straight away, QUEUES the copies (position, distance, length) and runs ahead; when the queue is full or the
+// stream ends, all lanes of the warp carry the queued copies out in order, each copy in parallel: element k of a copy reads
+// out[pos - dist + k mod dist], which lies in the part written before the copy began whatever the overlap. The other lanes
+// wait at the warp barrier meanwhile (no polling). With a colour cache the copies feed the cache in order: such pictures keep the
+// one-lane loop above (alph_decode_pixels), and so does the host build. The two loops are the same text but for the queue; they
+// are kept apart because the one-lane loop is a single dependent chain whose speed moved by 7-17 % with every change of the
+// code around it (whole-picture VP8L, 1024 photographs: 1125 ms as it stands, 1209 / 1315 ms inside the queued form).
+#define AL_COPY_INLINE 24   // shorter copies are done by lane 0 itself while the queue is empty
+
+AL_NOINLINE int alph_decode_pixels_warp(const uint8_t* alph, uint32_t alph_size, int h, int last_row, AlphaHdr* hd, const uint16_t* meta,
+                                   uint32_t* tables, AlGroup* groups, uint8_t* scratch, uint32_t* out,
+                                   uint32_t* copyq, int lane) {
+  uint32_t* cache = (uint32_t*)scratch + AL_SUB_TABLE_ENTRIES;
+  AlScratch* sc = (AlScratch*)(cache + (1 << AL_MAX_CACHE_BITS) + 256);
+  LBits b;
+  b.buf = alph + (hd->lossless ? 0 : 1); b.len = alph_size - (hd->lossless ? 0u : 1u); b.val = hd->br_val; b.pos = hd->br_pos; b.bit_pos = hd->br_bit_pos; b.eos = 0;
+  const int used_groups = hd->used_groups, stride = hd->group_entries, cache_bits = hd->cache_bits;
+  int status = AL_OK, done = 0;
+  int use_8b = 0;
+  if (lane == 0) {
+    if (!alph_read_groups(b, hd, tables, groups, scratch, sc)) { status = AL_OUT_OF_MEMORY; done = 1; }   // (still part of the header as far as the status goes)
+    // The reference runs DecodeAlphaData (vp8l_dec.c:1035-1116) when the only transform is the palette, there is no
+    // colour cache and every group's R, B and A codes are zero-bit (Is8bOptimizable, :857-870), DecodeImageData
+    // (:1138-1293) otherwise. Same symbols either way; what differs is when running out of data counts as a failure,
+    // so keep both shapes. A whole VP8L picture always goes through DecodeImageData (VP8LDecodeImage, :1761-1765; the 8-bit
+    // path is chosen by VP8LDecodeAlphaHeader alone, :1633-1641): there, data that runs out on the last symbol is an error.
+    if (!done) {
+      use_8b = (!hd->lossless && hd->ntrans == 1 && hd->ttype[0] == AL_T_COLOR_INDEXING && cache_bits == 0);
+      for (int g = 0; g < used_groups && use_8b; ++g) use_8b = groups[g].trivial_literal;
+      hd->use_8b = (uint8_t)use_8b;
+    }
+  }
+  const int cache_size = cache_bits ? (1 << cache_bits) : 0, cache_shift = 32 - cache_bits;
+  if (lane == 0 && !done) for (int i = 0; i < cache_size; ++i) cache[i] = 0;
+  const int width = hd->xsize;
+  const int end = width * h, last = width * (last_row < h ? last_row : h);
+  const int mask = hd->huff_bits ? (1 << hd->huff_bits) - 1 : -1;
+  const int hbits = hd->huff_bits, hxs = hd->huff_xsize;
+  const int len_code_limit = AL_NUM_LITERAL + AL_NUM_LENGTH;
+  const int queue = copyq != 0 && cache_size == 0;
+  int pos = 0, col = 0, row = 0;
+  int pos0 = 0;   // where the symbol being read starts: the reference meets a failure when asked for that row
+  int ok = 1;
+  const AlGroup* grp = groups;
+  const uint32_t* gt = tables;
+  if (lane == 0 && !done) {
+    grp = &groups[hbits ? meta[0] : 0];
+    gt = tables + (size_t)(grp - groups) * stride;
+  }
+  for (;;) {
+    int nq = 0;
+    if (lane == 0 && !done) {
+      int full = 0;   // left the loop because the queue filled up, not because the stream ended
+      while (pos < last && !(use_8b && b.eos)) {
+        pos0 = pos;
+        if ((col & mask) == 0) {
+          grp = &groups[hbits ? meta[hxs * (row >> hbits) + (col >> hbits)] : 0];
+          gt = tables + (size_t)(grp - groups) * stride;
+        }
+        int code;
+        uint32_t px = 0;
+        if (!use_8b && grp->trivial_code) {
+          code = 0;
+          px = grp->literal_arb;
+        } else {
+          lb_fill(b);
+          code = hc_read_symbol(gt + grp->off[0], b);
+          if (!use_8b && lb_at_end(b)) break;
+          if (code < AL_NUM_LITERAL) {
+            if (use_8b || grp->trivial_literal) {
+              px = grp->literal_arb | ((uint32_t)code << 8);
+            } else {
+              const uint32_t red = (uint32_t)hc_read_symbol(gt + grp->off[1], b);
+              lb_fill(b);
+              const uint32_t blue = (uint32_t)hc_read_symbol(gt + grp->off[2], b);
+              const uint32_t alpha = (uint32_t)hc_read_symbol(gt + grp->off[3], b);
+              if (lb_at_end(b)) break;
+              px = (alpha << 24) | (red << 16) | ((uint32_t)code << 8) | blue;
+            }
+          }
+        }
+        if (code < AL_NUM_LITERAL) {
+          out[pos++] = px;
+          if (cache_size) cache[(px * 0x1e35a7bdu) >> cache_shift] = px;
+          if (++col >= width) { col = 0; ++row; }
+        } else if (code < len_code_limit) {
+          const int length = al_copy_value(code - AL_NUM_LITERAL, b);
+          const int dist_symbol = hc_read_symbol(gt + grp->off[4], b);
+          lb_fill(b);
+          const int dist = al_plane_to_distance(width, al_copy_value(dist_symbol, b));
+          if (!use_8b && lb_at_end(b)) break;
+          if (pos >= dist && end - pos >= length) {
+            // a short copy with nothing queued before it is cheaper done on the spot (photographs: most copies are a few pixels
+            // long); once something waits in the queue everything after it queues up behind it, to keep the order
+            if (queue && (nq != 0 || length >= AL_COPY_INLINE)) {
+              copyq[2 + 3 * nq] = (uint32_t)pos; copyq[3 + 3 * nq] = (uint32_t)dist; copyq[4 + 3 * nq] = (uint32_t)length;
+              ++nq;
+            } else {
+              for (int k = 0; k < length; ++k) {
+                const uint32_t v = out[pos + k - dist];
+                out[pos + k] = v;
+                if (cache_size) cache[(v * 0x1e35a7bdu) >> cache_shift] = v;
+              }
+            }
+          } else {
+            ok = 0;
+            break;
+          }
+          pos += length;
+          col += length;
+          while (col >= width) { col -= width; ++row; }
+          if (pos < last && (col & mask)) {
+            grp = &groups[hbits ? meta[hxs * (row >> hbits) + (col >> hbits)] : 0];
+            gt = tables + (size_t)(grp - groups) * stride;
+          }
+          if (nq == AL_COPYQ) {   // time to let the warp carry the queued copies out
+            if (use_8b) b.eos = lb_at_end(b);
+            full = 1;
+            break;
+          }
+        } else if (code < len_code_limit + cache_size) {
+          px = cache[code - len_code_limit];
+          out[pos++] = px;
+          cache[(px * 0x1e35a7bdu) >> cache_shift] = px;
+          if (++col >= width) { col = 0; ++row; }
+        } else {
+          ok = 0;
+          break;
+        }
+        if (use_8b) b.eos = lb_at_end(b);
+      }
+      if (!full) {   // the stream has ended, one way or another
+        done = 1;
+        b.eos = lb_at_end(b);
+        hd->fail_row = pos0 / width;
+        if (!ok) status = AL_BITSTREAM_ERROR;
+        else if (use_8b ? (b.eos && pos < end) : b.eos) status = AL_BITSTREAM_ERROR;
+      }
+    }
+    if (copyq == 0) break;   // one lane: nothing was queued, the loop above ran to the end
+#if defined(__CUDACC__) && !defined(VP8_EMU)
+    if (lane == 0) { copyq[0] = (uint32_t)nq; copyq[1] = (uint32_t)done; }
+    __syncwarp();
+    const int n = (int)copyq[0];
+    const int all_done = (int)copyq[1];
+    for (int j = 0; j < n; ++j) {
+      const int p = (int)copyq[2 + 3 * j], d = (int)copyq[3 + 3 * j], l = (int)copyq[4 + 3 * j];
+      const uint32_t* src = out + p - d;
+      uint32_t* dst = out + p;
+      if (d >= l) {
+        for (int k = lane; k < l; k += 32) dst[k] = src[k];
+      } else {
+        int r = lane % d;
+        const int step = 32 % d;
+        for (int k = lane; k < l; k += 32) { dst[k] = src[r]; r += step; if (r >= d) r -= d; }
+      }
+      __syncwarp();   // the next copy may read what this one wrote
+    }
+    __syncwarp();
+    if (all_done) break;
+#else
+    break;
+#endif
+  }
+  return status;
+}
+
+#endif
 
 // ---------------------------------------------------------------------------------------------------------
 // Inverse transforms on ARGB words (src/dsp/lossless.c:28-340).

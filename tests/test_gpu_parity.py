@@ -690,6 +690,17 @@ def test_config4_shape_4096_thumbnails_premultiplied(W, ref):
     _compare_all(W, ref, datas, W.MODE_rgbA, sts, outs, distinct=64)
 
 
+def test_many_small_images_take_the_banded_rows(W, ref):
+    """More streams than the 4 KB-per-image layout of the probability rows can seat (16384 small pictures, one and four token
+    partitions, twelve sizes): the launch picks the banded layout by itself (vp8_kernels.cu:launch_tokens_fp); every image compared."""
+    cfgs = [ref.cfg_simple_1part(55), ref.cfg_default(), ref.EncCfg(70, 3, partitions=0, segments=2, filter_type=1),
+            ref.EncCfg(45, 2, partitions=2, segments=4, filter_type=0)]   # 12288 one-partition streams (banded), 4096 x 4 partitions (not)
+    corpus = [ref.encode(ref.synth(48 + 16 * (k % 3), 32 + 16 * (k % 4), 8200 + k), cfgs[k % 4]) for k in range(96)]
+    datas = [corpus[i % 96] for i in range(16384)]
+    sts, outs = W.decode_batch(datas, W.MODE_RGBA)
+    _compare_all(W, ref, datas, W.MODE_RGBA, sts, outs, distinct=96)
+
+
 def test_config5_shape_4096x4096_alpha(W, ref):
     """BASELINE config 5 at its stated shape: two 4096x4096 q90 images with a gradient-filtered ALPH chunk -> RGBA."""
     cfg = ref.cfg_alpha_q90()
