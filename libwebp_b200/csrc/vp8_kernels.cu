@@ -498,9 +498,10 @@ __global__ void __launch_bounds__(32) k_parse_literal(const uint8_t* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------------
-#define RECON_WARPS 8
-
-__global__ void __launch_bounds__(32 * RECON_WARPS) k_reconstruct(const ImgDesc* __restrict__ imgs, FrameHdr* hdrs,
+// RECON_WARPS warps per image (8 by default; 4 and 16 are compiled for WEBP_B200_RECON_WARPS, an A/B switch): more
+// warps cover a long anti-diagonal in fewer rounds, fewer warps leave fewer of them idle on the short ones.
+template <int RECON_WARPS>
+__global__ void __launch_bounds__(32 * RECON_WARPS, 32 / RECON_WARPS) k_reconstruct(const ImgDesc* __restrict__ imgs, FrameHdr* hdrs,
                                                                   uint32_t* mbinfo, const int16_t* __restrict__ coeffs,
                                                                   uint8_t* yuv, int first, int row_begin, int row_end,
                                                                   uint8_t* band_ctx, int band_ctx_stride,
@@ -540,6 +541,9 @@ __global__ void __launch_bounds__(32 * RECON_WARPS) k_reconstruct(const ImgDesc*
   recon_ctx_bind(cx, smem + sizeof(ReconWs) * RECON_WARPS, mb_w, mb_h);
   __shared__ int16_t dqs[24];   // the frame's dequantisers, [segment][y1 dc/ac, y2 dc/ac, uv dc/ac]
   if (threadIdx.x < 24) dqs[threadIdx.x] = (&hdrs[img].dq[0][0])[threadIdx.x];
+  __shared__ uint32_t pred4[160];   // every lane of a sub-block reads a different word: shared memory, not the constant bank
+  for (int k = threadIdx.x; k < 160; k += blockDim.x) pred4[k] = (&kPred4x[0][0])[k];
+  cx.pred4 = pred4;
   uint8_t* saved = band_ctx + (size_t)img * band_ctx_stride;
   if (r0 > 0) for (int k = threadIdx.x; k < 8 * mb_w; k += blockDim.x) ((uint32_t*)cx.top_y)[k] = ((const uint32_t*)saved)[k];
   __syncthreads();
@@ -725,8 +729,8 @@ __global__ void __launch_bounds__(256) k_copy_to_host(const uint8_t* __restrict_
 
 // =========================================================================================================
 // Launchers (plain C interface for vp8_batch.cu).
-static size_t recon_smem_bytes(int max_mb_w, int max_mb_h) {
-  return sizeof(ReconWs) * RECON_WARPS + ((recon_ctx_bytes(max_mb_w, max_mb_h) + 15) & ~(size_t)15);
+static size_t recon_smem_bytes(int warps, int max_mb_w, int max_mb_h) {
+  return sizeof(ReconWs) * warps + ((recon_ctx_bytes(max_mb_w, max_mb_h) + 15) & ~(size_t)15);
 }
 
 static size_t tokens_slot_bytes(int P, int max_mb_w) {
@@ -738,7 +742,7 @@ extern "C" cudaError_t vp8k_init_device(void) {
   const void* kernels[] = { (const void*)k_parse_modes, (const void*)k_parse_tokens, (const void*)k_parse_tokens_fsm,
                             (const void*)k_parse_tokens_lockstep, (const void*)k_parse_tokens_fp<0, 0>, (const void*)k_parse_tokens_fp<1, 0>,
                             (const void*)k_parse_tokens_fp<0, 1>,
-                            (const void*)k_reconstruct,
+                            (const void*)k_reconstruct<4>, (const void*)k_reconstruct<8>, (const void*)k_reconstruct<16>,
                             (const void*)k_loop_filter };
   for (const void* k : kernels) {
     cudaFuncAttributes fa;
@@ -973,8 +977,14 @@ extern "C" void vp8k_parse_literal(cudaStream_t s, const uint8_t* arena, const I
 extern "C" void vp8k_reconstruct(cudaStream_t s, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo, const int16_t* coeffs,
                                  uint8_t* yuv, int first, int count, int max_mb_w, int max_mb_h, int row_begin, int row_end,
                                  uint8_t* band_ctx, const uint32_t* tokens, const void* mbtok) {
-  k_reconstruct<<<count, 32 * RECON_WARPS, recon_smem_bytes(max_mb_w, max_mb_h), s>>>(imgs, hdrs, mbinfo, coeffs, yuv, first, row_begin,
-                                                                                      row_end, band_ctx, 32 * max_mb_w, tokens, (const MbTok*)mbtok);
+  static int warps = 0;   // process-wide A/B switch, read once
+  if (warps == 0) { const char* e = getenv("WEBP_B200_RECON_WARPS"); const int v = e != NULL ? atoi(e) : 0; warps = (v == 4 || v == 16) ? v : 8; }
+  const size_t smem = recon_smem_bytes(warps, max_mb_w, max_mb_h);
+  const int bctx = 32 * max_mb_w;
+  const MbTok* mt = (const MbTok*)mbtok;
+  if (warps == 4) k_reconstruct<4><<<count, 128, smem, s>>>(imgs, hdrs, mbinfo, coeffs, yuv, first, row_begin, row_end, band_ctx, bctx, tokens, mt);
+  else if (warps == 16) k_reconstruct<16><<<count, 512, smem, s>>>(imgs, hdrs, mbinfo, coeffs, yuv, first, row_begin, row_end, band_ctx, bctx, tokens, mt);
+  else k_reconstruct<8><<<count, 256, smem, s>>>(imgs, hdrs, mbinfo, coeffs, yuv, first, row_begin, row_end, band_ctx, bctx, tokens, mt);
 }
 
 extern "C" void vp8k_loop_filter(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint32_t* mbinfo, uint8_t* yuv,

@@ -39,6 +39,13 @@ struct uint4 { uint32_t x, y, z, w; };
 #endif
 
 VP8_PFN int clip8i(int v) { return v < 0 ? 0 : v > 255 ? 255 : v; }
+VP8_PFN int sum4(uint32_t v) {   // the four bytes of a word added up
+#if defined(__CUDACC__) && !defined(VP8_EMU)
+  return (int)__dp4a(v, 0x01010101u, 0u);
+#else
+  return (int)((v & 255u) + ((v >> 8) & 255u) + ((v >> 16) & 255u) + (v >> 24));
+#endif
+}
 VP8_PFN int mul1(int a) { return ((a * 20091) >> 16) + a; }
 VP8_PFN int mul2(int a) { return (a * 35468) >> 16; }
 
@@ -54,7 +61,7 @@ struct ReconWs {
   uint8_t y[17 * 32];
   uint8_t uv[9 * 32];
   int16_t dc[16];                     // inverse WHT of the Y2 block: DC coefficient of the 16 luma blocks (i16 only)
-  uint8_t edge[2][16];                // 4x4 predictor edges of the two sub-blocks in flight: L L L K J I X A B C D E F G H H
+  uint8_t spare[32];
   uint32_t nz;                        // some block of the macroblock has a non-zero coefficient
   uint32_t pad[3];
 };
@@ -69,6 +76,7 @@ struct ReconCtx {
   uint8_t* left_u;   // 8 * mb_h
   uint8_t* left_v;   // 8 * mb_h
   uint8_t* corner;   // 4 * mb_h : y,u,v pixel above-left of the next macroblock of the row
+  const uint32_t* pred4;   // kPred4x where every lane can read its own word at once (shared memory on the device)
 };
 
 #define recon_ctx_bytes(mb_w, mb_h) ((size_t)32 * (size_t)(mb_w) + (size_t)36 * (size_t)(mb_h))
@@ -79,17 +87,22 @@ VP8_PFN void recon_ctx_bind(ReconCtx& c, uint8_t* mem, int mb_w, int mb_h) {
   c.corner = c.left_v + 8 * mb_h;
 }
 
-// 4x4 predictors as (kind, first edge index) per pixel: 0x80 | a -> (E[a]+E[a+1]+1)>>1, else
-// (E[a]+2E[a+1]+E[a+2]+2)>>2, over the edge L L L K J I X A B C D E F G H H. Rows = modes VE..HU (2..9).
-VP8_PTABLE uint8_t kPred4[8][16] = {
-  /* VE */ { 6, 7, 8, 9, 6, 7, 8, 9, 6, 7, 8, 9, 6, 7, 8, 9 },
-  /* HE */ { 4, 4, 4, 4, 3, 3, 3, 3, 2, 2, 2, 2, 1, 1, 1, 1 },
-  /* RD */ { 5, 6, 7, 8, 4, 5, 6, 7, 3, 4, 5, 6, 2, 3, 4, 5 },
-  /* VR */ { 0x86, 0x87, 0x88, 0x89, 5, 6, 7, 8, 4, 0x86, 0x87, 0x88, 3, 5, 6, 7 },
-  /* LD */ { 7, 8, 9, 10, 8, 9, 10, 11, 9, 10, 11, 12, 10, 11, 12, 13 },
-  /* VL */ { 0x87, 0x88, 0x89, 0x8a, 7, 8, 9, 10, 0x88, 0x89, 0x8a, 11, 8, 9, 10, 12 },
-  /* HD */ { 0x85, 5, 6, 7, 0x84, 4, 0x85, 5, 0x83, 3, 0x84, 4, 0x82, 2, 0x83, 3 },
-  /* HU */ { 0x84, 3, 0x83, 2, 0x83, 2, 0x82, 1, 0x82, 1, 0, 0, 0, 0, 0, 0 }
+// 4x4 predictors, one word per (mode, pixel): three tile offsets (bytes 0-2, each + 64, relative to the sub-block's
+// origin in the 32-byte-stride tile) of the pixels a, b, c the prediction reads directly from the tile:
+// (a + 2b + c + 2) >> 2 for VE..HU (the two-tap averages (a + b + 1) >> 1 are the same formula with c = a), a + b - c
+// clipped for TM. Neighbours by offset: left column I J K L = -1, 31, 63, 95 (L also stands for the pixels below it),
+// corner X = -33, row above A..H = -32..-25 (dsp/dec.c:259-440 restated over one table). Row 0 (DC) is not read.
+VP8_PTABLE uint32_t kPred4x[10][16] = {
+  /* DC */ { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 },
+  /* TM */ { 0x1f3f20, 0x1f3f21, 0x1f3f22, 0x1f3f23, 0x1f5f20, 0x1f5f21, 0x1f5f22, 0x1f5f23, 0x1f7f20, 0x1f7f21, 0x1f7f22, 0x1f7f23, 0x1f9f20, 0x1f9f21, 0x1f9f22, 0x1f9f23 },
+  /* VE */ { 0x21201f, 0x222120, 0x232221, 0x242322, 0x21201f, 0x222120, 0x232221, 0x242322, 0x21201f, 0x222120, 0x232221, 0x242322, 0x21201f, 0x222120, 0x232221, 0x242322 },
+  /* HE */ { 0x1f3f5f, 0x1f3f5f, 0x1f3f5f, 0x1f3f5f, 0x3f5f7f, 0x3f5f7f, 0x3f5f7f, 0x3f5f7f, 0x5f7f9f, 0x5f7f9f, 0x5f7f9f, 0x5f7f9f, 0x7f9f9f, 0x7f9f9f, 0x7f9f9f, 0x7f9f9f },
+  /* RD */ { 0x201f3f, 0x21201f, 0x222120, 0x232221, 0x1f3f5f, 0x201f3f, 0x21201f, 0x222120, 0x3f5f7f, 0x1f3f5f, 0x201f3f, 0x21201f, 0x5f7f9f, 0x3f5f7f, 0x1f3f5f, 0x201f3f },
+  /* VR */ { 0x1f201f, 0x202120, 0x212221, 0x222322, 0x201f3f, 0x21201f, 0x222120, 0x232221, 0x1f3f5f, 0x1f201f, 0x202120, 0x212221, 0x3f5f7f, 0x201f3f, 0x21201f, 0x222120 },
+  /* LD */ { 0x222120, 0x232221, 0x242322, 0x252423, 0x232221, 0x242322, 0x252423, 0x262524, 0x242322, 0x252423, 0x262524, 0x272625, 0x252423, 0x262524, 0x272625, 0x272726 },
+  /* VL */ { 0x202120, 0x212221, 0x222322, 0x232423, 0x222120, 0x232221, 0x242322, 0x252423, 0x212221, 0x222322, 0x232423, 0x262524, 0x232221, 0x242322, 0x252423, 0x272625 },
+  /* HD */ { 0x3f1f3f, 0x201f3f, 0x21201f, 0x222120, 0x5f3f5f, 0x1f3f5f, 0x3f1f3f, 0x201f3f, 0x7f5f7f, 0x3f5f7f, 0x5f3f5f, 0x1f3f5f, 0x9f7f9f, 0x5f7f9f, 0x7f5f7f, 0x3f5f7f },
+  /* HU */ { 0x5f3f5f, 0x3f5f7f, 0x7f5f7f, 0x5f7f9f, 0x7f5f7f, 0x5f7f9f, 0x9f7f9f, 0x7f9f9f, 0x9f7f9f, 0x7f9f9f, 0x9f9f9f, 0x9f9f9f, 0x9f9f9f, 0x9f9f9f, 0x9f9f9f, 0x9f9f9f }
 };
 
 // 16 coefficient levels of one block (parse order, two 16-byte words of HBM) -> dequantised int16 values in raster
@@ -107,19 +120,43 @@ VP8_PFN void load_block_coeffs(const int16_t* levels, int q_dc, int q_ac, int in
 }
 
 // A macroblock's tokens (vp8_tokens_fp.h: {sign 31, block 29:25, magnitude 24:13, position 9:6}, `count` words at
-// `toks`) -> ws.lv, the dense 25 x 16 level array load_block_coeffs reads. One warp; the caller's next phase may read.
-VP8_PFN void recon_load_tokens(ReconWs& ws, const uint32_t* toks, uint32_t count) {
+// `toks`) -> ws.lv, the dense 25 x 16 level array load_block_coeffs reads. One warp, in two parts so that the latency of
+// the loads runs beside the neighbour phase: recon_fetch_tokens issues the loads of the first 96 tokens into registers
+// and clears ws.lv, recon_scatter_tokens (a phase later) writes them out and loops over whatever is left.
+#if defined(__CUDACC__) && !defined(VP8_EMU)
+#define VP8_LANE_SLOTS 1          // a value that lives in a lane across phases: a register on the device,
+#define VP8_LANE_SLOT(lane) 0
+#else
+#define VP8_LANE_SLOTS 32         // one slot per lane in the host build
+#define VP8_LANE_SLOT(lane) (lane)
+#endif
+struct ReconTok { uint32_t t[3][VP8_LANE_SLOTS]; };
+
+VP8_PFN void recon_put_token(ReconWs& ws, uint32_t t) {
+  const int mag = (int)((t >> 13) & 0xfffu);
+  ws.lv[((t >> 25) & 31u) * 16u + ((t >> 6) & 15u)] = (int16_t)((t >> 31) ? -mag : mag);
+}
+
+VP8_PFN void recon_fetch_tokens(ReconWs& ws, ReconTok& rt, const uint32_t* toks, uint32_t count) {
   WARP_PHASE(lane)
+    VP8_UNROLL
+    for (int j = 0; j < 3; ++j) {
+      const uint32_t k = (uint32_t)lane + 32u * (uint32_t)j;
+      rt.t[j][VP8_LANE_SLOT(lane)] = (k < count) ? toks[k] : 0u;
+    }
     uint4 z; z.x = 0; z.y = 0; z.z = 0; z.w = 0;
     uint4* dst = (uint4*)ws.lv;
     if (lane < 25) { dst[2 * lane] = z; dst[2 * lane + 1] = z; }
   WARP_PHASE_END
+}
+
+VP8_PFN void recon_scatter_tokens(ReconWs& ws, const ReconTok& rt, const uint32_t* toks, uint32_t count) {
   WARP_PHASE(lane)
-    for (uint32_t k = (uint32_t)lane; k < count; k += 32) {
-      const uint32_t t = toks[k];
-      const int mag = (int)((t >> 13) & 0xfffu);
-      ws.lv[((t >> 25) & 31u) * 16u + ((t >> 6) & 15u)] = (int16_t)((t >> 31) ? -mag : mag);
+    VP8_UNROLL
+    for (int j = 0; j < 3; ++j) {
+      if ((uint32_t)lane + 32u * (uint32_t)j < count) recon_put_token(ws, rt.t[j][VP8_LANE_SLOT(lane)]);
     }
+    for (uint32_t k = (uint32_t)lane + 96u; k < count; k += 32) recon_put_token(ws, toks[k]);
   WARP_PHASE_END
 }
 
@@ -175,14 +212,16 @@ VP8_PFN int pred_big_pixel(const uint8_t* t, int mode, int dc, int x, int y) {
 VP8_PFN int dc_big(const uint8_t* t, int mode, int size) {   // dsp/dec.c:215-244, 445-474
   const int sh = (size == 16) ? 4 : 3;
   int s = 0;
+  const uint32_t* const above = (const uint32_t*)(t - 32);   // word-aligned in both tiles
   if (mode == 0) {
-    for (int i = 0; i < size; ++i) s += t[i - 32] + t[i * 32 - 1];
+    for (int i = 0; i < size / 4; ++i) s += sum4(above[i]);
+    for (int i = 0; i < size; ++i) s += t[i * 32 - 1];
     return (s + size) >> (sh + 1);
   } else if (mode == 4) {
     for (int i = 0; i < size; ++i) s += t[i * 32 - 1];
     return (s + (size >> 1)) >> sh;
   } else if (mode == 5) {
-    for (int i = 0; i < size; ++i) s += t[i - 32];
+    for (int i = 0; i < size / 4; ++i) s += sum4(above[i]);
     return (s + (size >> 1)) >> sh;
   }
   return 0x80;
@@ -214,40 +253,54 @@ VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, i
   const int any_coef = (nzy | nzuv) != 0 || has_y2;
   const int ys = 16 * mb_w, uvs = 8 * mb_w;
   // levels: the dense plane of the older token parsers, or this macroblock's slice of the token stream
-  if (toks != nullptr) {
-    if (any_coef) recon_load_tokens(ws, toks, ntok);
-    coeffs = ws.lv;
-  }
+  ReconTok rt;
+  const int from_tokens = toks != nullptr && any_coef;
+  if (toks != nullptr) coeffs = ws.lv;
+  if (from_tokens) recon_fetch_tokens(ws, rt, toks, ntok);
 
-  // ---- phase 0: neighbour pixels -> tile; inverse WHT of the Y2 block (lane 21)
+  // ---- phase 0: neighbour pixels -> tile (the token loads are in flight); then the levels, then the inverse WHT of the Y2 block
+  // Left columns: one byte per lane (16 luma, 8 U, 8 V). Rows above: one word per lane (lanes 0-3 luma, 4 the four pixels
+  // above-right, 5-6 U, 7-8 V), corners lanes 9-11. Outside the frame: 127 above, 129 to the left, the corner like the
+  // row above unless that exists and the left does not (frame_dec.c:91-121).
   WARP_PHASE(lane)
     if (lane == 0) ws.nz = 0;
-    if (lane < 16) {
-      ws.y[4 + lane] = (my > 0) ? cx.top_y[16 * mx + lane] : 127;
-      ws.y[(lane + 1) * 32 + 3] = (mx > 0) ? cx.left_y[16 * my + lane] : 129;
-    } else if (lane < 20) {
-      const int k = lane - 16;
-      const uint8_t tr = (my > 0) ? ((mx < mb_w - 1) ? cx.top_y[16 * (mx + 1) + k] : cx.top_y[16 * mx + 15]) : 127;
-      ws.y[20 + k] = tr;
-      if (is_i4) { ws.y[4 * 32 + 20 + k] = tr; ws.y[8 * 32 + 20 + k] = tr; ws.y[12 * 32 + 20 + k] = tr; }
-    } else if (lane == 20) {
-      ws.y[3] = (my > 0) ? ((mx > 0) ? cx.corner[4 * my + 0] : 129) : 127;
-      ws.uv[3] = (my > 0) ? ((mx > 0) ? cx.corner[4 * my + 1] : 129) : 127;
-      ws.uv[19] = (my > 0) ? ((mx > 0) ? cx.corner[4 * my + 2] : 129) : 127;
-    } else if (lane == 21) {
-      if (!is_i4 && has_y2) {
+    {
+      const uint8_t* src = lane < 16 ? cx.left_y + 16 * my + lane : (lane < 24 ? cx.left_u : cx.left_v) + 8 * my + (lane & 7);
+      uint8_t* dst = lane < 16 ? ws.y + (lane + 1) * 32 + 3 : ws.uv + ((lane & 7) + 1) * 32 + (lane < 24 ? 3 : 19);
+      *dst = (mx > 0) ? *src : 129;
+    }
+    if (lane < 9) {
+      uint32_t v = 0x7f7f7f7fu;
+      uint32_t* dst;
+      if (lane < 5) {
+        dst = (uint32_t*)(ws.y + 4 + 4 * lane);
+        if (my > 0) {
+          v = (lane < 4 || mx < mb_w - 1) ? *(const uint32_t*)(cx.top_y + 16 * mx + 4 * lane) : cx.top_y[16 * mx + 15] * 0x01010101u;
+          if (lane == 4 && is_i4) { dst[32] = v; dst[64] = v; dst[96] = v; }   // rows 4, 8, 12 of the tile: above-right of the right-most sub-blocks
+        } else if (lane == 4 && is_i4) {
+          dst[32] = v; dst[64] = v; dst[96] = v;
+        }
+      } else {
+        const int k = lane - 5;   // 0, 1: U words; 2, 3: V words
+        dst = (uint32_t*)(ws.uv + 4 + 4 * (k & 1) + 16 * (k >> 1));
+        if (my > 0) v = *(const uint32_t*)((k < 2 ? cx.top_u : cx.top_v) + 8 * mx + 4 * (k & 1));
+      }
+      *dst = v;
+    } else if (lane < 12) {
+      const int k = lane - 9;   // corner of y, u, v
+      (k == 0 ? ws.y : ws.uv)[k == 2 ? 19 : 3] = (my > 0) ? ((mx > 0) ? cx.corner[4 * my + k] : 129) : 127;
+    }
+  WARP_PHASE_END
+  if (from_tokens) recon_scatter_tokens(ws, rt, toks, ntok);
+  if (!is_i4 && has_y2) {
+    WARP_PHASE(lane)
+      if (lane == 0) {
         int in[16];
         load_block_coeffs(coeffs + 24 * 16, dq6[2], dq6[3], in);
         wht_block(in, ws.dc);
       }
-    } else if (lane >= 24) {
-      const int k = lane - 24;
-      ws.uv[4 + k] = (my > 0) ? cx.top_u[8 * mx + k] : 127;
-      ws.uv[20 + k] = (my > 0) ? cx.top_v[8 * mx + k] : 127;
-      ws.uv[(k + 1) * 32 + 3] = (mx > 0) ? cx.left_u[8 * my + k] : 129;
-      ws.uv[(k + 1) * 32 + 19] = (mx > 0) ? cx.left_v[8 * my + k] : 129;
-    }
-  WARP_PHASE_END
+    WARP_PHASE_END
+  }
 
   // ---- phase 1: residuals of all 24 blocks, one lane per block
   if (any_coef) {
@@ -290,40 +343,34 @@ VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, i
 
   // ---- phase 2: luma
   if (is_i4) {
+    // Ten anti-diagonals bx + 2*by = step, two sub-blocks on each: lanes 0-15 take (bx0, by0), lanes 16-31 the one a row
+    // down and two columns left (n + 2; 120 bytes further on in the tile), where there is one. Both read only pixels
+    // outside themselves (finished in earlier steps), straight from the tile, and write only their own 16: one phase per
+    // step. Unrolled, everything but the lane's half is a constant of the step.
+    VP8_UNROLL
     for (int step = 0; step < 10; ++step) {
-      const int by0 = (step > 2) ? (step - 2) >> 1 : 0;   // first sub-block row on this anti-diagonal bx + 2*by = step
+      const int by0 = (step > 2) ? (step - 2) >> 1 : 0, bx0 = step - 2 * by0;
+      const int n0 = 4 * by0 + bx0;
+      const int second = (by0 < 3) && (bx0 >= 2);           // lanes 16-31 have a sub-block on this step
+      const int origin = (by0 * 4 + 1) * 32 + bx0 * 4 + 4;  // of sub-block n0 in the tile
       WARP_PHASE(lane)
-        const int by = by0 + (lane >> 4), bx = step - 2 * by;
-        if (by < 4 && bx >= 0 && bx < 4 && lane < 32) {
-          const uint8_t* const t = ws.y + (by * 4 + 1) * 32 + bx * 4 + 4;   // block origin in the tile
-          const int i = lane & 15;   // edge element: L L L K J I X A..H H
-          int off;
-          if (i < 6) off = ((i < 3) ? 3 : 5 - i) * 32 - 1;
-          else if (i == 6) off = -33;
-          else off = -32 + ((i - 7 < 7) ? i - 7 : 7);
-          ws.edge[lane >> 4][i] = t[off];
-        }
-      WARP_PHASE_END
-      WARP_PHASE(lane)
-        const int by = by0 + (lane >> 4), bx = step - 2 * by;
-        if (by < 4 && bx >= 0 && bx < 4) {
-          const int n = by * 4 + bx;
-          const int mode = (int)(((n < 8) ? (m0 >> (4 * n)) : (m1 >> (4 * (n - 8)))) & 15);
-          uint8_t* const t = ws.y + (by * 4 + 1) * 32 + bx * 4 + 4;
-          const int l = lane & 15, px = l & 3, py = l >> 2;
-          const uint8_t* e = ws.edge[lane >> 4];
+        const int half = lane >> 4, l = lane & 15;
+        if (half == 0 || second) {
+          // modes of sub-blocks n0 and n0 + 2: the 64-bit mode word moved down by two nibbles for the second half
+          const uint32_t ma = half ? (m0 >> 8) | (m1 << 24) : m0, mb = half ? (m1 >> 8) : m1;
+          const int mode = (int)(((n0 < 8) ? (ma >> (4 * (n0 & 7))) : (mb >> (4 * (n0 & 7)))) & 15);
+          uint8_t* const t = ws.y + 120 * half + origin;
           int p;
           if (mode == M_DC) {
-            p = (e[2] + e[3] + e[4] + e[5] + e[7] + e[8] + e[9] + e[10] + 4) >> 3;
-          } else if (mode == M_TM) {
-            p = clip8i((int)e[7 + px] + (int)e[5 - py] - (int)e[6]);
+            p = (sum4(*(const uint32_t*)(t - 32)) + t[-1] + t[31] + t[63] + t[95] + 4) >> 3;
           } else {
-            const int k = kPred4[mode - 2][l];
-            const int a = k & 0x7f;
-            p = (k & 0x80) ? (e[a] + e[a + 1] + 1) >> 1 : (e[a] + 2 * e[a + 1] + e[a + 2] + 2) >> 2;
+            const uint32_t e = cx.pred4[mode * 16 + l];
+            const uint8_t* const tb = t - 64;
+            const int a = tb[e & 255u], b = tb[(e >> 8) & 255u], c = tb[e >> 16];
+            p = (mode == M_TM) ? clip8i(a + b - c) : (a + 2 * b + c + 2) >> 2;
           }
-          if (any_coef) p = clip8i(p + (int)ws.res[n * 16 + l]);
-          t[py * 32 + px] = (uint8_t)p;
+          if (any_coef) p = clip8i(p + (int)ws.res[(n0 + 2 * half) * 16 + l]);
+          t[(l >> 2) * 32 + (l & 3)] = (uint8_t)p;
         }
       WARP_PHASE_END
     }
@@ -465,8 +512,27 @@ VP8_PFN void filter_macroblock(FilterWs& ws, int mx, int my, int mb_w, int filte
       }
     }
   WARP_PHASE_END
+  if (!normal) {
+    // Simple filter (luma only): a line reads p1 p0 q0 q1 and writes p0 q0, i.e. columns 4k-2 .. 4k+1 of edge k, so the
+    // four edges of one direction touch disjoint pixels and the reference's edge-after-edge order (frame_dec.c:216-231)
+    // equals all of them at once: two edges x 16 lines per warp pass instead of one. Direction order stays.
+    for (int dir = 0; dir < 2; ++dir) {
+      const int outer = dir == 0 ? (mx > 0) : (my > 0);
+      for (int half = 0; half < 2; ++half) {
+        if (half == 0 ? (outer || inner) : inner) {
+          WARP_PHASE(lane)
+            const int k = 2 * half + (lane >> 4), i = lane & 15;
+            if (k == 0 ? outer : inner) {
+              uint8_t* p = dir == 0 ? ws.y + (4 + i) * 32 + 4 + 4 * k : ws.y + (4 + 4 * k) * 32 + 4 + i;
+              lf_line(p, dir == 0 ? 1 : 32, 0, (k == 0) ? limit + 4 : limit, ilevel, hev_t);
+            }
+          WARP_PHASE_END
+        }
+      }
+    }
+  }
   // ---- vertical edges (filtering across columns): macroblock edge, then the three inner edges
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; normal && k < 4; ++k) {
     if (k == 0 ? (mx > 0) : inner) {
       const int thresh = (k == 0) ? limit + 4 : limit;
       const int kind = normal ? ((k == 0) ? 1 : 2) : 0;
@@ -481,7 +547,7 @@ VP8_PFN void filter_macroblock(FilterWs& ws, int mx, int my, int mb_w, int filte
     }
   }
   // ---- horizontal edges (filtering across rows)
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; normal && k < 4; ++k) {
     if (k == 0 ? (my > 0) : inner) {
       const int thresh = (k == 0) ? limit + 4 : limit;
       const int kind = normal ? ((k == 0) ? 1 : 2) : 0;

@@ -373,6 +373,7 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
     std::vector<uint8_t> ctxmem(recon_ctx_bytes(mb_w, mb_h) + 64, 0);
     ReconCtx cx;
     recon_ctx_bind(cx, ctxmem.data(), mb_w, mb_h);
+    cx.pred4 = &kPred4x[0][0];
     const int steps = mb_w + 2 * (rows - 1);
     for (int d = 0; d < steps; ++d) {
       for (int k = 0; k < rows; ++k) {
