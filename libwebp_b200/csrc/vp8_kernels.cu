@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(32) k_parse_literal(const uint8_t* __restrict_
 // ---------------------------------------------------------------------------------------------------------
 // RECON_WARPS warps per image (8 by default; 4 and 16 are compiled for WEBP_B200_RECON_WARPS, an A/B switch): more
 // warps cover a long anti-diagonal in fewer rounds, fewer warps leave fewer of them idle on the short ones.
-template <int RECON_WARPS>
+template <int RECON_WARPS, int ROWS>
 __global__ void __launch_bounds__(32 * RECON_WARPS, 32 / RECON_WARPS) k_reconstruct(const ImgDesc* __restrict__ imgs, FrameHdr* hdrs,
                                                                   uint32_t* mbinfo, const int16_t* __restrict__ coeffs,
                                                                   uint8_t* yuv, int first, int row_begin, int row_end,
@@ -555,10 +555,42 @@ __global__ void __launch_bounds__(32 * RECON_WARPS, 32 / RECON_WARPS) k_reconstr
   const int16_t* cf = coeffs + (size_t)im.mb_base * VP8B_COEFFS_PER_MB;
   const uint32_t* tk = tokens != nullptr ? tokens + (size_t)im.mb_base * TF_TOKENS_PER_MB : nullptr;   // token stream instead of the dense plane
   const MbTok* mt = mbtok + (size_t)im.mb_base;
-  // Lag-2 anti-diagonal wavefront with a block-wide barrier per step. (A barrier-free variant -- one warp per row,
-  // progress counters in shared memory, as k_loop_filter does now -- measured 52 -> 72 ms here: this kernel is issue-bound
-  // and the warps that spin on a counter take issue slots from the ones that work; at a barrier they sleep.)
   const int nrows = r1 - r0;
+  if (ROWS) {
+    // One warp per macroblock row, no block-wide barrier: warp w owns rows r0 + w, r0 + w + RECON_WARPS, ... and walks each
+    // from left to right; macroblock (mx, my) needs (mx + 1, my - 1) finished (its above-right pixels), whose owner
+    // publishes how many macroblocks of its row are done. Every context entry has one writer and one reader that is also
+    // its next writer, so nothing else orders the rows. The next macroblock's MbInfo and MbTok are fetched while the
+    // current one is reconstructed.
+    volatile int* row_done = reinterpret_cast<volatile int*>(smem + sizeof(ReconWs) * RECON_WARPS + ((recon_ctx_bytes(mb_w, mb_h) + 15) & ~(size_t)15));
+    for (int k = threadIdx.x; k < nrows; k += blockDim.x) row_done[k] = 0;
+    __syncthreads();
+    for (int ly = warp; ly < nrows; ly += RECON_WARPS) {
+      const int my = r0 + ly;
+      const size_t row0 = (size_t)my * mb_w;
+      uint4 iw = *(const uint4*)(mbi + 4 * row0);
+      MbTok t; t.first = 0; t.count = 0;
+      if (tk != nullptr) t = mt[row0];
+      for (int mx = 0; mx < mb_w; ++mx) {
+        const size_t idx = row0 + mx;
+        const uint4 iw_cur = iw;
+        const MbTok t_cur = t;
+        if (mx + 1 < mb_w) { iw = *(const uint4*)(mbi + 4 * (idx + 1)); if (tk != nullptr) t = mt[idx + 1]; }
+        if (ly > 0) {
+          const int need = mx + 2 < mb_w ? mx + 2 : mb_w;
+          while (row_done[ly - 1] < need) __nanosleep(40);
+          __threadfence_block();
+        }
+        const int16_t* dq6 = dqs + 6 * ((iw_cur.w >> MBW_SEG_SHIFT) & 3);
+        if (tk != nullptr) recon_macroblock(ws, cx, mx, my, mb_w, iw_cur, mbi + 4 * idx, nullptr, dq6, yp, up, vp, tk + t_cur.first, t_cur.count);
+        else recon_macroblock(ws, cx, mx, my, mb_w, iw_cur, mbi + 4 * idx, cf + idx * VP8B_COEFFS_PER_MB, dq6, yp, up, vp);
+        __threadfence_block();
+        if ((threadIdx.x & 31) == 0) row_done[ly] = mx + 1;
+      }
+    }
+    __syncthreads();
+  } else {
+  // Lag-2 anti-diagonal wavefront with a block-wide barrier per step.
   const int steps = mb_w + 2 * (nrows - 1);
   for (int d = 0; d < steps; ++d) {
     // rows with a macroblock on this anti-diagonal: mx = d - 2*(my - r0) in [0, mb_w)
@@ -576,6 +608,7 @@ __global__ void __launch_bounds__(32 * RECON_WARPS, 32 / RECON_WARPS) k_reconstr
       }
     }
     __syncthreads();
+  }
   }
   if (r1 < mb_h) for (int k = threadIdx.x; k < 8 * mb_w; k += blockDim.x) ((uint32_t*)saved)[k] = ((const uint32_t*)cx.top_y)[k];
 }
@@ -730,7 +763,7 @@ __global__ void __launch_bounds__(256) k_copy_to_host(const uint8_t* __restrict_
 // =========================================================================================================
 // Launchers (plain C interface for vp8_batch.cu).
 static size_t recon_smem_bytes(int warps, int max_mb_w, int max_mb_h) {
-  return sizeof(ReconWs) * warps + ((recon_ctx_bytes(max_mb_w, max_mb_h) + 15) & ~(size_t)15);
+  return sizeof(ReconWs) * warps + ((recon_ctx_bytes(max_mb_w, max_mb_h) + 15) & ~(size_t)15) + 4 * (size_t)max_mb_h + 16;   // + row_done
 }
 
 static size_t tokens_slot_bytes(int P, int max_mb_w) {
@@ -742,7 +775,8 @@ extern "C" cudaError_t vp8k_init_device(void) {
   const void* kernels[] = { (const void*)k_parse_modes, (const void*)k_parse_tokens, (const void*)k_parse_tokens_fsm,
                             (const void*)k_parse_tokens_lockstep, (const void*)k_parse_tokens_fp<0, 0>, (const void*)k_parse_tokens_fp<1, 0>,
                             (const void*)k_parse_tokens_fp<0, 1>,
-                            (const void*)k_reconstruct<4>, (const void*)k_reconstruct<8>, (const void*)k_reconstruct<16>,
+                            (const void*)k_reconstruct<4, 0>, (const void*)k_reconstruct<8, 0>, (const void*)k_reconstruct<16, 0>,
+                            (const void*)k_reconstruct<4, 1>, (const void*)k_reconstruct<8, 1>, (const void*)k_reconstruct<16, 1>,
                             (const void*)k_loop_filter };
   for (const void* k : kernels) {
     cudaFuncAttributes fa;
@@ -982,9 +1016,12 @@ extern "C" void vp8k_reconstruct(cudaStream_t s, const ImgDesc* imgs, FrameHdr* 
   const size_t smem = recon_smem_bytes(warps, max_mb_w, max_mb_h);
   const int bctx = 32 * max_mb_w;
   const MbTok* mt = (const MbTok*)mbtok;
-  if (warps == 4) k_reconstruct<4><<<count, 128, smem, s>>>(imgs, hdrs, mbinfo, coeffs, yuv, first, row_begin, row_end, band_ctx, bctx, tokens, mt);
-  else if (warps == 16) k_reconstruct<16><<<count, 512, smem, s>>>(imgs, hdrs, mbinfo, coeffs, yuv, first, row_begin, row_end, band_ctx, bctx, tokens, mt);
-  else k_reconstruct<8><<<count, 256, smem, s>>>(imgs, hdrs, mbinfo, coeffs, yuv, first, row_begin, row_end, band_ctx, bctx, tokens, mt);
+  static int rows = -1;
+  if (rows < 0) { const char* e = getenv("WEBP_B200_RECON_ROWS"); rows = e != NULL ? (atoi(e) != 0) : 1; }
+#define RECON_LAUNCH(W, R) k_reconstruct<W, R><<<count, 32 * W, smem, s>>>(imgs, hdrs, mbinfo, coeffs, yuv, first, row_begin, row_end, band_ctx, bctx, tokens, mt)
+  if (rows) { if (warps == 4) RECON_LAUNCH(4, 1); else if (warps == 16) RECON_LAUNCH(16, 1); else RECON_LAUNCH(8, 1); }
+  else { if (warps == 4) RECON_LAUNCH(4, 0); else if (warps == 16) RECON_LAUNCH(16, 0); else RECON_LAUNCH(8, 0); }
+#undef RECON_LAUNCH
 }
 
 extern "C" void vp8k_loop_filter(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint32_t* mbinfo, uint8_t* yuv,

@@ -241,12 +241,13 @@ VP8_PFN int check_mode(int mx, int my, int mode) {
 // once for i16, a 10-step sub-block wavefront (two sub-blocks per step) for i4x4; (3) chroma; (4) tile -> planes.
 // Also finalises MbInfo: the filter-inner bit (vp8_dec.c:629-633), which needs the lone-DC rule
 // NzCodeBits(nz, dst[0] != 0) (vp8_dec.c:511-515) evaluated on the dequantised int16.
-VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, int mb_w, uint32_t* info,
+// `iw` = the four MbInfo words (the caller may have fetched them ahead of time), `info` = where they live (word 3 is rewritten).
+VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, int mb_w, const uint4 iw, uint32_t* info,
                               const int16_t* coeffs, const int16_t* dq6, uint8_t* yplane, uint8_t* uplane, uint8_t* vplane,
                               const uint32_t* toks = nullptr, uint32_t ntok = 0) {
-  const uint32_t w = info[3];
-  const uint32_t m0 = info[0], m1 = info[1];
-  const uint32_t nzy = info[2];
+  const uint32_t w = iw.w;
+  const uint32_t m0 = iw.x, m1 = iw.y;
+  const uint32_t nzy = iw.z;
   const uint32_t nzuv = w & 0xffffu;
   const int is_i4 = (w & MBW_I4X4) != 0;
   const int has_y2 = (w & MBW_HAS_Y2) != 0;
@@ -432,6 +433,13 @@ VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, i
       info[3] = (is_i4 || ws.nz != 0) ? (w | MBW_INNER) : (w & ~MBW_INNER);
     }
   WARP_PHASE_END
+}
+
+VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, int mb_w, uint32_t* info,
+                              const int16_t* coeffs, const int16_t* dq6, uint8_t* yplane, uint8_t* uplane, uint8_t* vplane,
+                              const uint32_t* toks = nullptr, uint32_t ntok = 0) {
+  uint4 iw; iw.x = info[0]; iw.y = info[1]; iw.z = info[2]; iw.w = info[3];
+  recon_macroblock(ws, cx, mx, my, mb_w, iw, info, coeffs, dq6, yplane, uplane, vplane, toks, ntok);
 }
 
 // =========================================================================================================
