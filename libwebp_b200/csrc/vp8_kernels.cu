@@ -33,6 +33,7 @@
 #include "vp8_tokens_fp.h"
 #include "vp8_literal.h"
 #define AL_BLOCK_SYNC() __syncthreads()
+#include "vp8_modes_lockstep.h"
 #include "vp8l_alpha_core.h"
 #include "vp8l_lossless_core.h"
 
@@ -68,6 +69,79 @@ __global__ void __launch_bounds__(32 * MODES_WARPS, 1) k_parse_modes(const uint8
     st = VP8B_OK;
   }
   h->status = st;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1, second mapping (vp8_modes_lockstep.h): `lanes` images per warp as lockstep lanes of one table-driven state machine,
+// four warps per block (one per SM sub-partition when the launch has one block per SM). Shared memory: node table |
+// kVp8BModeProba | one 16-byte row of fixed probabilities per image | the images' top-mode rows.
+#define MODESL_WARPS 4
+#define MODESL_TAB_BYTES 176     // ML_TAB_BYTES padded to 16
+#define MODESL_BPROB_BYTES 912   // 900 padded to 16
+#ifndef ML_GROUPS_PER_VOTE
+#define ML_GROUPS_PER_VOTE 8
+#endif
+__global__ void __launch_bounds__(32 * MODESL_WARPS, 1) k_parse_modes_lockstep(const uint8_t* __restrict__ arena, const ImgDesc* __restrict__ imgs,
+                                                                               FrameHdr* hdrs, uint32_t* mbinfo, int first, int count,
+                                                                               int max_mb_w, int lanes) {
+  extern __shared__ __align__(16) uint8_t msm[];
+  uint32_t* tab = reinterpret_cast<uint32_t*>(msm);
+  uint8_t* bprob = msm + MODESL_TAB_BYTES;
+  const int ipb = MODESL_WARPS * lanes;
+  uint8_t* rows = bprob + MODESL_BPROB_BYTES;
+  uint32_t* tops = reinterpret_cast<uint32_t*>(rows + (size_t)ipb * ML_ROW_BYTES);
+  ml_table_fill(tab, threadIdx.x, blockDim.x);
+  for (int k = threadIdx.x; k < 900; k += blockDim.x) bprob[k] = kVp8BModeProba[k];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int slot = (threadIdx.x >> 5) * lanes + lane;
+  const int i = blockIdx.x * ipb + slot;
+  const bool mine = lane < lanes && i < count;
+  FrameHdr* h = mine ? &hdrs[first + i] : nullptr;
+  ImgDesc im;
+  BoolDec br;
+  int st = VP8B_NOT_A_VP8_FRAME;
+  if (mine) {
+    im = imgs[first + i];
+    // (a whole-picture VP8L image has no VP8 frame, see k_parse_modes)
+    if (!(im.flags & VP8B_FLAG_LOSSLESS)) st = parse_frame_header(br, arena + im.in_off, im, h);
+  }
+  const bool run = mine && st == VP8B_OK;
+  const unsigned mask = __ballot_sync(0xffffffffu, run);
+  if (!run) {
+    if (mine) {
+      h->status = st;
+      if (!(im.flags & VP8B_FLAG_LOSSLESS)) { h->fail_row = VP8B_FAIL_HEADERS; h->modes_status = VP8B_OK; h->all_rows = h->rows; }
+    }
+    return;
+  }
+  MlCtx c;
+  c.tab_s = tk_saddr_of(tab); c.bprob_s = tk_saddr_of(bprob);
+  c.row_s = tk_saddr_of(rows + (size_t)slot * ML_ROW_BYTES);
+  c.top_s = tk_saddr_of(tops + (size_t)slot * max_mb_w);
+  c.out = mbinfo + 4 * (size_t)im.mb_base;
+  c.mb_w = im.mb_w; c.mb_h = h->rows;
+  c.skip_node8 = h->use_skip ? 8u * ML_SKIP : 8u * ML_I16; c.skip_off = h->use_skip ? ML_OFF_SKIP : ML_OFF_I16;
+  c.first_node8 = h->update_map ? 8u * ML_S0 : c.skip_node8; c.first_off = h->update_map ? ML_OFF_S0 : c.skip_off;
+  c.k.mant_mask = 0x007fffffu; c.k.exp46 = TF_EXP46;
+  ml_row_fill(rows + (size_t)slot * ML_ROW_BYTES, h);
+  MlLane L;
+  ml_start(L, c, br);
+  while (__any_sync(mask, L.alive)) {
+    for (int r = 0; r < ML_GROUPS_PER_VOTE; ++r) ml_group(L, c);
+  }
+  // FrameHdr bookkeeping as k_parse_modes leaves it
+  int stm = L.status;
+  const int fail_row = L.fail_row;
+  h->fail_row = fail_row;
+  h->modes_status = VP8B_OK;
+  h->all_rows = h->rows;
+  if (stm != VP8B_OK && fail_row > 0 && fail_row != VP8B_FAIL_NONE) {   // see FrameHdr::modes_status
+    h->modes_status = stm;
+    h->rows = fail_row;
+    stm = VP8B_OK;
+  }
+  h->status = stm;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -570,11 +644,13 @@ __global__ void __launch_bounds__(32 * RECON_WARPS, 32 / RECON_WARPS) k_reconstr
       const size_t row0 = (size_t)my * mb_w;
       uint4 iw = *(const uint4*)(mbi + 4 * row0);
       MbTok t; t.first = 0; t.count = 0;
-      if (tk != nullptr) t = mt[row0];
+      ReconTok rt;
+      if (tk != nullptr) { t = mt[row0]; recon_fetch_tokens(rt, tk + t.first, t.count); }
       for (int mx = 0; mx < mb_w; ++mx) {
         const size_t idx = row0 + mx;
         const uint4 iw_cur = iw;
         const MbTok t_cur = t;
+        t.count = 0;
         if (mx + 1 < mb_w) { iw = *(const uint4*)(mbi + 4 * (idx + 1)); if (tk != nullptr) t = mt[idx + 1]; }
         if (ly > 0) {
           const int need = mx + 2 < mb_w ? mx + 2 : mb_w;
@@ -582,8 +658,8 @@ __global__ void __launch_bounds__(32 * RECON_WARPS, 32 / RECON_WARPS) k_reconstr
           __threadfence_block();
         }
         const int16_t* dq6 = dqs + 6 * ((iw_cur.w >> MBW_SEG_SHIFT) & 3);
-        if (tk != nullptr) recon_macroblock(ws, cx, mx, my, mb_w, iw_cur, mbi + 4 * idx, nullptr, dq6, yp, up, vp, tk + t_cur.first, t_cur.count);
-        else recon_macroblock(ws, cx, mx, my, mb_w, iw_cur, mbi + 4 * idx, cf + idx * VP8B_COEFFS_PER_MB, dq6, yp, up, vp);
+        if (tk != nullptr) recon_macroblock(ws, cx, mx, my, mb_w, iw_cur, mbi + 4 * idx, nullptr, dq6, yp, up, vp, tk + t_cur.first, t_cur.count, rt, tk + t.first, t.count);
+        else recon_macroblock(ws, cx, mx, my, mb_w, iw_cur, mbi + 4 * idx, cf + idx * VP8B_COEFFS_PER_MB, dq6, yp, up, vp, nullptr, 0, rt, nullptr, 0);
         __threadfence_block();
         if ((threadIdx.x & 31) == 0) row_done[ly] = mx + 1;
       }
@@ -772,7 +848,7 @@ static size_t tokens_slot_bytes(int P, int max_mb_w) {
 
 #define VP8K_MAX_DYN_SMEM (227 * 1024)   // opt-in ceiling per block on sm_100
 extern "C" cudaError_t vp8k_init_device(void) {
-  const void* kernels[] = { (const void*)k_parse_modes, (const void*)k_parse_tokens, (const void*)k_parse_tokens_fsm,
+  const void* kernels[] = { (const void*)k_parse_modes, (const void*)k_parse_modes_lockstep, (const void*)k_parse_tokens, (const void*)k_parse_tokens_fsm,
                             (const void*)k_parse_tokens_lockstep, (const void*)k_parse_tokens_fp<0, 0>, (const void*)k_parse_tokens_fp<1, 0>,
                             (const void*)k_parse_tokens_fp<0, 1>,
                             (const void*)k_reconstruct<4, 0>, (const void*)k_reconstruct<8, 0>, (const void*)k_reconstruct<16, 0>,
@@ -812,6 +888,28 @@ static int modes_lanes_for(int count) {
 
 extern "C" void vp8k_parse_modes(cudaStream_t s, const uint8_t* arena, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo,
                                  int first, int count, int max_mb_w) {
+  // Mapping: one image per warp (k_parse_modes) unless WEBP_B200_MODES=lockstep asks for the lockstep lanes
+  // (k_parse_modes_lockstep, vp8_modes_lockstep.h). Measured on the B200 (profiles/r03c, r03d): the table-driven machine pays
+  // two dependent shared-memory loads and a divergent leaf path per decode where the straight-line code pays neither --
+  // 4096 full-HD images 54.4 ms at 7 lanes per warp, 44.5 at 2, 62.6 at 1, against 30.2 ms here; 65536 thumbnails 5.8 against
+  // 4.1 ms. Kept as a second, parity-tested instantiation (GPU test_every_mode_mapping, emulation variants +256), not the default.
+  static int mapping = -1;   // process-wide A/B switch, read once
+  if (mapping < 0) { const char* e = getenv("WEBP_B200_MODES"); mapping = (e != NULL && !strcmp(e, "lockstep")) ? 2 : 1; }
+  if (mapping != 1) {
+    int ll = (count + 148 * MODESL_WARPS - 1) / (148 * MODESL_WARPS);   // one warp per sub-partition, as many lanes as that takes
+    if (ll > 32) ll = 32;
+    static int forced_ll = -1;
+    if (forced_ll < 0) { const char* e = getenv("WEBP_B200_MODES_LANES"); forced_ll = (e != NULL && atoi(e) >= 1 && atoi(e) <= 32) ? atoi(e) : 0; }
+    if (forced_ll > 0) ll = forced_ll;
+    const size_t per_image = (size_t)max_mb_w * 4 + ML_ROW_BYTES;
+    while (ll > 1 && (size_t)MODESL_WARPS * ll * per_image > 190u * 1024u) --ll;
+    const size_t msm = MODESL_TAB_BYTES + MODESL_BPROB_BYTES + (size_t)MODESL_WARPS * ll * per_image;
+    if (msm <= 200u * 1024u && (mapping == 2 || ll >= 2)) {
+      const int ipb = MODESL_WARPS * ll;
+      k_parse_modes_lockstep<<<(count + ipb - 1) / ipb, 32 * MODESL_WARPS, msm, s>>>(arena, imgs, hdrs, mbinfo, first, count, max_mb_w, ll);
+      return;
+    }
+  }
   int lanes = modes_lanes_for(count);
   if ((size_t)lanes * max_mb_w * 4 > 200u * 1024u) lanes = 1;   // the lanes' top-mode rows share the block's shared memory
   int ipb;

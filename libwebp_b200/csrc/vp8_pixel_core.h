@@ -121,8 +121,9 @@ VP8_PFN void load_block_coeffs(const int16_t* levels, int q_dc, int q_ac, int in
 
 // A macroblock's tokens (vp8_tokens_fp.h: {sign 31, block 29:25, magnitude 24:13, position 9:6}, `count` words at
 // `toks`) -> ws.lv, the dense 25 x 16 level array load_block_coeffs reads. One warp, in two parts so that the latency of
-// the loads runs beside the neighbour phase: recon_fetch_tokens issues the loads of the first 96 tokens into registers
-// and clears ws.lv, recon_scatter_tokens (a phase later) writes them out and loops over whatever is left.
+// the loads runs beside other work: recon_fetch_tokens issues the loads of the first 96 tokens into registers (the
+// row-per-warp kernel does that for macroblock k + 1 while it finishes macroblock k), recon_scatter_tokens writes them out
+// once ws.lv has been cleared and loops over whatever is left.
 #if defined(__CUDACC__) && !defined(VP8_EMU)
 #define VP8_LANE_SLOTS 1          // a value that lives in a lane across phases: a register on the device,
 #define VP8_LANE_SLOT(lane) 0
@@ -137,13 +138,18 @@ VP8_PFN void recon_put_token(ReconWs& ws, uint32_t t) {
   ws.lv[((t >> 25) & 31u) * 16u + ((t >> 6) & 15u)] = (int16_t)((t >> 31) ? -mag : mag);
 }
 
-VP8_PFN void recon_fetch_tokens(ReconWs& ws, ReconTok& rt, const uint32_t* toks, uint32_t count) {
+VP8_PFN void recon_fetch_tokens(ReconTok& rt, const uint32_t* toks, uint32_t count) {   // loads only: nothing waits for them here
   WARP_PHASE(lane)
     VP8_UNROLL
     for (int j = 0; j < 3; ++j) {
       const uint32_t k = (uint32_t)lane + 32u * (uint32_t)j;
       rt.t[j][VP8_LANE_SLOT(lane)] = (k < count) ? toks[k] : 0u;
     }
+  WARP_PHASE_END
+}
+
+VP8_PFN void recon_clear_levels(ReconWs& ws) {
+  WARP_PHASE(lane)
     uint4 z; z.x = 0; z.y = 0; z.z = 0; z.w = 0;
     uint4* dst = (uint4*)ws.lv;
     if (lane < 25) { dst[2 * lane] = z; dst[2 * lane + 1] = z; }
@@ -242,9 +248,11 @@ VP8_PFN int check_mode(int mx, int my, int mode) {
 // Also finalises MbInfo: the filter-inner bit (vp8_dec.c:629-633), which needs the lone-DC rule
 // NzCodeBits(nz, dst[0] != 0) (vp8_dec.c:511-515) evaluated on the dequantised int16.
 // `iw` = the four MbInfo words (the caller may have fetched them ahead of time), `info` = where they live (word 3 is rewritten).
+// `rt` = this macroblock's first tokens, fetched by the caller (recon_fetch_tokens); on return it holds those of the
+// macroblock the same warp takes next (`next_toks`, `next_ntok`; 0 for none), their loads still in flight.
 VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, int mb_w, const uint4 iw, uint32_t* info,
                               const int16_t* coeffs, const int16_t* dq6, uint8_t* yplane, uint8_t* uplane, uint8_t* vplane,
-                              const uint32_t* toks = nullptr, uint32_t ntok = 0) {
+                              const uint32_t* toks, uint32_t ntok, ReconTok& rt, const uint32_t* next_toks, uint32_t next_ntok) {
   const uint32_t w = iw.w;
   const uint32_t m0 = iw.x, m1 = iw.y;
   const uint32_t nzy = iw.z;
@@ -254,10 +262,9 @@ VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, i
   const int any_coef = (nzy | nzuv) != 0 || has_y2;
   const int ys = 16 * mb_w, uvs = 8 * mb_w;
   // levels: the dense plane of the older token parsers, or this macroblock's slice of the token stream
-  ReconTok rt;
   const int from_tokens = toks != nullptr && any_coef;
   if (toks != nullptr) coeffs = ws.lv;
-  if (from_tokens) recon_fetch_tokens(ws, rt, toks, ntok);
+  if (from_tokens) recon_clear_levels(ws);
 
   // ---- phase 0: neighbour pixels -> tile (the token loads are in flight); then the levels, then the inverse WHT of the Y2 block
   // Left columns: one byte per lane (16 luma, 8 U, 8 V). Rows above: one word per lane (lanes 0-3 luma, 4 the four pixels
@@ -410,6 +417,7 @@ VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, i
     WARP_PHASE_END
   }
 
+  if (next_ntok != 0) recon_fetch_tokens(rt, next_toks, next_ntok);
   // ---- phase 4: tile -> HBM planes, neighbour context for the macroblocks to the right and below, MbInfo
   WARP_PHASE(lane)
     if (lane < 16) {
@@ -439,7 +447,9 @@ VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, i
                               const int16_t* coeffs, const int16_t* dq6, uint8_t* yplane, uint8_t* uplane, uint8_t* vplane,
                               const uint32_t* toks = nullptr, uint32_t ntok = 0) {
   uint4 iw; iw.x = info[0]; iw.y = info[1]; iw.z = info[2]; iw.w = info[3];
-  recon_macroblock(ws, cx, mx, my, mb_w, iw, info, coeffs, dq6, yplane, uplane, vplane, toks, ntok);
+  ReconTok rt;
+  if (toks != nullptr) recon_fetch_tokens(rt, toks, ntok);
+  recon_macroblock(ws, cx, mx, my, mb_w, iw, info, coeffs, dq6, yplane, uplane, vplane, toks, ntok, rt, nullptr, 0);
 }
 
 // =========================================================================================================

@@ -21,6 +21,7 @@
 #include "vp8_tokens_fsm.h"
 #include "vp8_tokens_lockstep.h"
 #include "vp8_tokens_fp.h"
+#include "vp8_modes_lockstep.h"
 #include "vp8_literal.h"
 #include "vp8l_alpha_core.h"
 #include "vp8l_lossless_core.h"
@@ -30,6 +31,7 @@
 // variant bit 1: token parse with the row-at-a-time reference port (parse_token_row) instead of the lane FSM
 // variant bit 2: lane FSM with a lazy ring producer
 // variant bit 3: lockstep lane parser (vp8_tokens_lockstep.h), lanes advanced round-robin; with bit 4 its grouped event points
+// variant bit 8: the lockstep mode parser (vp8_modes_lockstep.h) instead of parse_intra_modes
 // variant bit 6: the fp parser (vp8_tokens_fp.h): fp32 boolean decoder, token stream out, read back by recon_load_tokens
 static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags, uint8_t* out, size_t out_size,
                            int stride, int variant, uint8_t* unfiltered, int crop_x, int crop_y, int crop_w, int crop_h,
@@ -218,6 +220,23 @@ static int emu_decode_crop(const uint8_t* data, size_t size, int csp, int flags,
     std::vector<uint32_t> top(mb_w);
     hdr.status = parse_frame_header(br, frame, im, &hdr);
     hdr.fail_row = hdr.status == VP8B_OK ? VP8B_FAIL_NONE : VP8B_FAIL_HEADERS;
+    if (hdr.status == VP8B_OK && (variant & 256)) {   // variant bit 8: the lockstep mode parser (vp8_modes_lockstep.h), this image as its one lane
+      uint32_t tab[2 * ML_NODES];
+      uint8_t row[ML_ROW_BYTES];
+      ml_table_fill(tab, 0, 1);
+      ml_row_fill(row, &hdr);
+      MlCtx mc;
+      mc.tab_s = tk_saddr_of(tab); mc.bprob_s = tk_saddr_of(kVp8BModeProba); mc.row_s = tk_saddr_of(row); mc.top_s = tk_saddr_of(top.data());
+      mc.out = mbinfo.data(); mc.mb_w = mb_w; mc.mb_h = hdr.rows;
+      mc.skip_node8 = hdr.use_skip ? 8u * ML_SKIP : 8u * ML_I16; mc.skip_off = hdr.use_skip ? ML_OFF_SKIP : ML_OFF_I16;
+      mc.first_node8 = hdr.update_map ? 8u * ML_S0 : mc.skip_node8; mc.first_off = hdr.update_map ? ML_OFF_S0 : mc.skip_off;
+      mc.k.mant_mask = 0x007fffffu; mc.k.exp46 = TF_EXP46;
+      MlLane L;
+      ml_start(L, mc, br);
+      while (L.alive) ml_group(L, mc);
+      hdr.status = L.status;
+      if (L.status != VP8B_OK) hdr.fail_row = L.fail_row;
+    } else
     if (hdr.status == VP8B_OK) hdr.status = parse_intra_modes(br, im, &hdr, top.data(), kVp8BModeProba, mbinfo.data(), &hdr.fail_row);
   }
   // Both chunks damaged: the fp parser keeps the row at which the VP8 stream fails, and the image's status is whichever

@@ -39,7 +39,7 @@ def test_emu_matches_manifest(emu, manifest):
         w, h = e["features"]["width"], e["features"]["height"]
         for key, want in e["sha256"].items():
             csp, fl = map(int, key.split(":"))
-            for rev in (0, 1, 2, 3, 4, 8, 9, 24, 25, 56, 64, 65, 80, 192, 208):   # +128 = the banded probability rows; 64 = the fp parser (fp32 boolean decoder, token stream; 80 = with a branch per decode); 2 = row-at-a-time token parser, 4 = lazy ring producer (lanes find the ring dry), 8 = lockstep lanes, 24 = lockstep lanes with grouped event points, 56 = the same as straight-line groups
+            for rev in (0, 1, 2, 3, 4, 8, 9, 24, 25, 56, 64, 65, 80, 192, 208, 320, 336):   # +256 = the lockstep mode parser; +128 = the banded probability rows; 64 = the fp parser (fp32 boolean decoder, token stream; 80 = with a branch per decode); 2 = row-at-a-time token parser, 4 = lazy ring producer (lanes find the ring dry), 8 = lockstep lanes, 24 = lockstep lanes with grouped event points, 56 = the same as straight-line groups
                 st, out = emu(e["data"], w, h, csp, fl, rev)
                 assert st == 0 and sha(out) == want, (e["file"], key, rev)
 
@@ -68,7 +68,7 @@ def test_emu_status_on_damaged_files(emu, port, manifest):
     for c in cases:
         s_ref, a = port.decode(c, port.RGBA, 0)
         w, h = port.features(c)[1]["width"], port.features(c)[1]["height"]
-        for variant in (0, 2, 8, 24, 56, 64, 80, 192, 208):   # lane state machine / row-at-a-time parser / lockstep lanes (block ends on the spot, grouped) / fp parser
+        for variant in (0, 2, 8, 24, 56, 64, 80, 192, 208, 320, 336):   # lane state machine / row-at-a-time parser / lockstep lanes (block ends on the spot, grouped) / fp parser / + 256: the lockstep mode parser
             s_emu, b = emu(c, max(w, 1), max(h, 1), 1, 0, variant)
             assert s_emu == s_ref, (len(c), s_ref, s_emu, variant)
             if s_ref == 0:
@@ -83,7 +83,7 @@ def test_emu_full_hd(emu, ref, kind):
         st, want = ref.decode(data, csp, 0)
         st2, got = emu(data, 1920, 1080, csp, 0, 8 if csp == 1 else 24)
         assert st == st2 == 0 and np.array_equal(want.reshape(-1), got.reshape(-1))
-        st2, got = emu(data, 1920, 1080, csp, 0, 64)   # the default parser of the product
+        st2, got = emu(data, 1920, 1080, csp, 0, 320)   # the default parsers of the product (lockstep mode parse, fp token parse)
         assert st == st2 == 0 and np.array_equal(want.reshape(-1), got.reshape(-1))
 
 
@@ -143,7 +143,7 @@ def test_emu_alpha_and_vp8_both_damaged(emu, ref, amanifest):
             b = bytes(b)
             s_ref, want = ref.decode(b, ref.MODE_RGBA, 0)
             seen.add(s_ref)
-            for variant in (64, 80, 192):
+            for variant in (64, 80, 192, 320):
                 s_emu, got = emu(b, w, h, 1, 0, variant)
                 assert s_emu == s_ref, (e["file"], k, s_ref, s_emu, variant)
                 if s_ref == 0 and not np.array_equal(want.reshape(-1), got.reshape(-1)):
@@ -186,7 +186,7 @@ def test_emu_partition_starting_with_ff(emu, ref, port, manifest, amanifest):
                 continue
             s_ref, want = ref.decode(b, ref.MODE_RGBA, 0)
             seen[s_ref] = seen.get(s_ref, 0) + 1
-            for variant in (64, 80, 192):
+            for variant in (64, 80, 192, 320):
                 s_emu, got = emu(b, w, h, 1, 0, variant)
                 assert s_emu == s_ref, (e["file"], s_ref, s_emu, variant)
                 if s_ref == 0 and not np.array_equal(want.reshape(-1), got.reshape(-1)):

@@ -379,6 +379,28 @@ def test_every_token_mapping(mapping):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("switch", ["WEBP_B200_MODES=lockstep", "WEBP_B200_MODES=lockstep WEBP_B200_MODES_LANES=3", "WEBP_B200_RECON_ROWS=0", "WEBP_B200_RECON_WARPS=16", "WEBP_B200_RECON_WARPS=4 WEBP_B200_RECON_ROWS=0"])
+def test_every_mode_and_reconstruction_mapping(switch):
+    """The second instantiations of K1 and K3 kept behind switches: the intra-mode parse as lockstep lanes of a table-driven
+    state machine (vp8_modes_lockstep.h; default: one image per warp) and the reconstruction as an anti-diagonal wavefront
+    with a block-wide barrier, at 4 / 8 / 16 warps per image (default: one warp per macroblock row, 8 warps). The switches are
+    read once per process, hence the subprocess; each must pass the manifest, mixed-batch, fresh-corpus, damaged-file and
+    stage-level tests."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("WEBP_B200_TOKEN_MAP_INNER"):
+        pytest.skip("inner run")
+    env = dict(os.environ, WEBP_B200_TOKEN_MAP_INNER="1")
+    for kv in switch.split():
+        k, v = kv.split("=")
+        env[k] = v
+    select = "manifest or mixed_sizes or fresh_corpora or full_size or damaged or parse_stages or extreme"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k", select], env=env, capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_many_streams_take_the_lockstep_parser(W, ref):
     """Enough streams per partition count for the default choice to be the lockstep parser (>= two per SM sub-partition):
     1300 one-partition and 300 eight-partition images of mixed small sizes, every one compared with the reference."""

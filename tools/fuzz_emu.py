@@ -206,7 +206,7 @@ def worker(args):
         w, h = (f["width"], f["height"]) if sf == 0 else (1, 1)
         if w * h > MAX_PIXELS:
             continue
-        variant = (0, 2, 8, 24, 56, 64, 64, 80, 192, 208)[int(rng.integers(0, 10))]   # +128: the banded probability rows
+        variant = (0, 2, 8, 24, 56, 64, 320, 336, 192, 208, 320, 64)[int(rng.integers(0, 12))]   # +128: the banded probability rows, +256: the lockstep mode parser
         # the product's order (plan_item, vp8_batch.cu): feature probe first, its NOT_ENOUGH_DATA becomes BITSTREAM_ERROR
         # (webp_dec.c:761-767), any other failure is returned as it is; only then the decode proper
         if use_port:
