@@ -725,17 +725,30 @@ __global__ void __launch_bounds__(32 * FILTER_WARPS) k_loop_filter(const ImgDesc
   volatile int* row_done = reinterpret_cast<volatile int*>(fsmem);
   for (int k = threadIdx.x; k < nrows; k += blockDim.x) row_done[k] = 0;
   __syncthreads();
+  const int normal = filter_type == 2;
   for (int ly = warp; ly < nrows; ly += FILTER_WARPS) {
     const int my = r0 + ly;
+    // The warp runs one macroblock ahead of itself: the rows above macroblock mx + 1 must be final (its own need) before
+    // its columns are fetched, which happens while macroblock mx is filtered (filter_fetch, vp8_pixel_core.h).
+    FilterPre pre;
+    if (ly > 0) { const int need = 2 < mb_w ? 2 : mb_w; while (row_done[ly - 1] < need) __nanosleep(20); __threadfence_block(); }
+    if (filter_type != 0) filter_fetch(pre, 0, my, mb_w, normal, yp, up, vp);
     for (int mx = 0; mx < mb_w; ++mx) {
-      if (ly > 0) {
-        const int need = mx + 2 < mb_w ? mx + 2 : mb_w;
-        while (row_done[ly - 1] < need) __nanosleep(20);
-        __threadfence_block();
-      }
       const uint32_t w = mbi[4 * ((size_t)my * mb_w + mx) + 3];
       const uint8_t* fs = fstr + 8 * ((w >> MBW_SEG_SHIFT) & 3) + ((w & MBW_I4X4) ? 4 : 0);
-      if (filter_type != 0) filter_macroblock(ws, mx, my, mb_w, filter_type, fs, (w & MBW_INNER) != 0, yp, up, vp);
+      if (filter_type != 0) filter_fill(ws, pre, normal);
+      if (mx + 1 < mb_w) {
+        if (ly > 0) {
+          const int need = mx + 3 < mb_w ? mx + 3 : mb_w;
+          while (row_done[ly - 1] < need) __nanosleep(20);
+          __threadfence_block();
+        }
+        if (filter_type != 0) filter_fetch(pre, mx + 1, my, mb_w, normal, yp, up, vp);
+      }
+      if (filter_type != 0) {
+        if (fs[0] != 0) filter_tile(ws, mx, my, mb_w, filter_type, fs, (w & MBW_INNER) != 0, yp, up, vp);
+        filter_shift(ws, normal);
+      }
       if (dithering) {
         const int8_t* dp = dither_plane + (size_t)im.mb_base * 128;
         __syncwarp();

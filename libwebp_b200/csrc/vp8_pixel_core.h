@@ -500,36 +500,13 @@ struct FilterWs {
 // Filters macroblock (mx, my) in place in the image's HBM planes, in the reference's edge order
 // (DoFilter, frame_dec.c:203-250). fs = {limit, ilevel, inner(unused), hev_thresh} for this macroblock's
 // segment / block type; `inner` = MbInfo filter-inner bit; filter_type 1 simple, 2 normal.
-VP8_PFN void filter_macroblock(FilterWs& ws, int mx, int my, int mb_w, int filter_type, const uint8_t* fs, int inner,
-                               uint8_t* yplane, uint8_t* uplane, uint8_t* vplane) {
+// filter_tile: the edges of one macroblock on the warp's tile (already loaded), then the tile back into the planes;
+// filter_macroblock (below) loads the tile first.
+VP8_PFN void filter_tile(FilterWs& ws, int mx, int my, int mb_w, int filter_type, const uint8_t* fs, int inner,
+                         uint8_t* yplane, uint8_t* uplane, uint8_t* vplane) {
   const int limit = fs[0], ilevel = fs[1], hev_t = fs[3];
   const int ys = 16 * mb_w, uvs = 8 * mb_w;
   const int normal = (filter_type == 2);
-  if (limit == 0) return;
-  // ---- load
-  WARP_PHASE(lane)
-    if (lane < 20) {
-      const int gy = 16 * my - 4 + lane;
-      if (gy >= 0) {
-        const uint8_t* src = yplane + (size_t)gy * ys + 16 * mx;
-        const uint4 v = *(const uint4*)src;
-        uint32_t* d = (uint32_t*)(ws.y + lane * 32 + 4);
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-        if (mx > 0) *(uint32_t*)(ws.y + lane * 32) = *(const uint32_t*)(src - 4);
-      }
-    } else if (normal) {
-      const int r = lane - 20;
-      const int gy = 8 * my - 4 + r;
-      if (gy >= 0) {
-        const uint8_t* su = uplane + (size_t)gy * uvs + 8 * mx;
-        const uint8_t* sv = vplane + (size_t)gy * uvs + 8 * mx;
-        const uint2 a = *(const uint2*)su, b = *(const uint2*)sv;
-        uint32_t* d = (uint32_t*)(ws.uv + r * 32);
-        d[1] = a.x; d[2] = a.y; d[5] = b.x; d[6] = b.y;
-        if (mx > 0) { d[0] = *(const uint32_t*)(su - 4); d[4] = *(const uint32_t*)(sv - 4); }
-      }
-    }
-  WARP_PHASE_END
   if (!normal) {
     // Simple filter (luma only): a line reads p1 p0 q0 q1 and writes p0 q0, i.e. columns 4k-2 .. 4k+1 of edge k, so the
     // four edges of one direction touch disjoint pixels and the reference's edge-after-edge order (frame_dec.c:216-231)
@@ -601,6 +578,88 @@ VP8_PFN void filter_macroblock(FilterWs& ws, int mx, int my, int mb_w, int filte
         *(uint2*)du = a; *(uint2*)dv = b;
         if (mx > 0) { *(uint32_t*)(du - 4) = s[0]; *(uint32_t*)(dv - 4) = s[4]; }
       }
+    }
+  WARP_PHASE_END
+}
+
+VP8_PFN void filter_macroblock(FilterWs& ws, int mx, int my, int mb_w, int filter_type, const uint8_t* fs, int inner,
+                               uint8_t* yplane, uint8_t* uplane, uint8_t* vplane) {
+  const int ys = 16 * mb_w, uvs = 8 * mb_w;
+  const int normal = (filter_type == 2);
+  if (fs[0] == 0) return;
+  // ---- load
+  WARP_PHASE(lane)
+    if (lane < 20) {
+      const int gy = 16 * my - 4 + lane;
+      if (gy >= 0) {
+        const uint8_t* src = yplane + (size_t)gy * ys + 16 * mx;
+        const uint4 v = *(const uint4*)src;
+        uint32_t* d = (uint32_t*)(ws.y + lane * 32 + 4);
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        if (mx > 0) *(uint32_t*)(ws.y + lane * 32) = *(const uint32_t*)(src - 4);
+      }
+    } else if (normal) {
+      const int r = lane - 20;
+      const int gy = 8 * my - 4 + r;
+      if (gy >= 0) {
+        const uint8_t* su = uplane + (size_t)gy * uvs + 8 * mx;
+        const uint8_t* sv = vplane + (size_t)gy * uvs + 8 * mx;
+        const uint2 a = *(const uint2*)su, b = *(const uint2*)sv;
+        uint32_t* d = (uint32_t*)(ws.uv + r * 32);
+        d[1] = a.x; d[2] = a.y; d[5] = b.x; d[6] = b.y;
+        if (mx > 0) { d[0] = *(const uint32_t*)(su - 4); d[4] = *(const uint32_t*)(sv - 4); }
+      }
+    }
+  WARP_PHASE_END
+  filter_tile(ws, mx, my, mb_w, filter_type, fs, inner, yplane, uplane, vplane);
+}
+
+// The same for a warp that walks a macroblock row from left to right (k_loop_filter): a macroblock's own columns are
+// fetched into registers while the macroblock before it is filtered (filter_fetch; its rows above must be final by then),
+// put into the tile (filter_fill), and the tile's four right-most columns -- filtered -- stay behind as the next
+// macroblock's left columns (filter_shift) instead of coming back from the planes.
+struct FilterPre { uint32_t v[4][VP8_LANE_SLOTS]; };
+
+VP8_PFN void filter_fetch(FilterPre& pre, int mx, int my, int mb_w, int normal, const uint8_t* yplane, const uint8_t* uplane,
+                          const uint8_t* vplane) {
+  const int ys = 16 * mb_w, uvs = 8 * mb_w;
+  WARP_PHASE(lane)
+    uint32_t a = 0, b = 0, c = 0, d = 0;
+    if (lane < 20) {
+      const int gy = 16 * my - 4 + lane;
+      if (gy >= 0) { const uint4 v = *(const uint4*)(yplane + (size_t)gy * ys + 16 * mx); a = v.x; b = v.y; c = v.z; d = v.w; }
+    } else if (normal) {
+      const int gy = 8 * my - 4 + (lane - 20);
+      if (gy >= 0) {
+        const uint2 p = *(const uint2*)(uplane + (size_t)gy * uvs + 8 * mx), q = *(const uint2*)(vplane + (size_t)gy * uvs + 8 * mx);
+        a = p.x; b = p.y; c = q.x; d = q.y;
+      }
+    }
+    pre.v[0][VP8_LANE_SLOT(lane)] = a; pre.v[1][VP8_LANE_SLOT(lane)] = b; pre.v[2][VP8_LANE_SLOT(lane)] = c; pre.v[3][VP8_LANE_SLOT(lane)] = d;
+  WARP_PHASE_END
+}
+
+VP8_PFN void filter_fill(FilterWs& ws, const FilterPre& pre, int normal) {
+  WARP_PHASE(lane)
+    const uint32_t a = pre.v[0][VP8_LANE_SLOT(lane)], b = pre.v[1][VP8_LANE_SLOT(lane)], c = pre.v[2][VP8_LANE_SLOT(lane)], d = pre.v[3][VP8_LANE_SLOT(lane)];
+    if (lane < 20) {
+      uint32_t* t = (uint32_t*)(ws.y + lane * 32 + 4);
+      t[0] = a; t[1] = b; t[2] = c; t[3] = d;
+    } else if (normal) {
+      uint32_t* t = (uint32_t*)(ws.uv + (lane - 20) * 32);
+      t[1] = a; t[2] = b; t[5] = c; t[6] = d;
+    }
+  WARP_PHASE_END
+}
+
+VP8_PFN void filter_shift(FilterWs& ws, int normal) {
+  WARP_PHASE(lane)
+    if (lane < 20) {
+      uint32_t* t = (uint32_t*)(ws.y + lane * 32);
+      t[0] = t[4];                 // luma columns 12-15 -> columns -4..-1
+    } else if (normal) {
+      uint32_t* t = (uint32_t*)(ws.uv + (lane - 20) * 32);
+      t[0] = t[2]; t[4] = t[6];    // U and V columns 4-7 -> columns -4..-1
     }
   WARP_PHASE_END
 }
