@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(32 * RECON_WARPS, 32 / RECON_WARPS) k_reconstr
   for (int k = threadIdx.x; k < 160; k += blockDim.x) pred4[k] = (&kPred4x[0][0])[k];
   cx.pred4 = pred4;
   uint8_t* saved = band_ctx + (size_t)img * band_ctx_stride;
-  if (r0 > 0) for (int k = threadIdx.x; k < 8 * mb_w; k += blockDim.x) ((uint32_t*)cx.top_y)[k] = ((const uint32_t*)saved)[k];
+  if (r0 > 0) for (int k = threadIdx.x; k < 8 * mb_w; k += blockDim.x) ((uint32_t*)cx.top)[k] = ((const uint32_t*)saved)[k];
   __syncthreads();
   const size_t nmb = (size_t)mb_w * im.mb_h;
   uint8_t* yp = yuv + (size_t)im.mb_base * 384;
@@ -686,13 +686,13 @@ __global__ void __launch_bounds__(32 * RECON_WARPS, 32 / RECON_WARPS) k_reconstr
     __syncthreads();
   }
   }
-  if (r1 < mb_h) for (int k = threadIdx.x; k < 8 * mb_w; k += blockDim.x) ((uint32_t*)saved)[k] = ((const uint32_t*)cx.top_y)[k];
+  if (r1 < mb_h) for (int k = threadIdx.x; k < 8 * mb_w; k += blockDim.x) ((uint32_t*)saved)[k] = ((const uint32_t*)cx.top)[k];
 }
 
 // ---------------------------------------------------------------------------------------------------------
 #define FILTER_WARPS 8
 
-__global__ void __launch_bounds__(32 * FILTER_WARPS) k_loop_filter(const ImgDesc* __restrict__ imgs, const FrameHdr* __restrict__ hdrs,
+__global__ void __launch_bounds__(32 * FILTER_WARPS, 5) k_loop_filter(const ImgDesc* __restrict__ imgs, const FrameHdr* __restrict__ hdrs,
                                                                    const uint32_t* __restrict__ mbinfo, uint8_t* yuv, int first,
                                                                    int row_begin, int row_end, const int8_t* __restrict__ dither_plane) {
   __shared__ __align__(16) FilterWs wss[FILTER_WARPS];

@@ -68,23 +68,21 @@ struct ReconWs {
 
 // Wavefront context of one image (shared memory of the block that owns the image): the unfiltered pixels each
 // macroblock needs from its neighbours. Lag 2 between rows keeps every entry valid exactly while it is read.
+// Laid out so that a macroblock finds everything at one constant offset from its column / its row:
+//   top  : 32 bytes per macroblock column, the bottom row of the macroblock above: 16 luma | 8 U | 8 V
+//   left : 36 bytes per macroblock row, the right column of the macroblock to the left: 16 luma | 8 U | 8 V, then the
+//          pixel above-left of the next macroblock of the row for y, u, v (+ 1 byte of padding)
 struct ReconCtx {
-  uint8_t* top_y;    // 16 * mb_w : bottom row of the macroblock above, per column
-  uint8_t* top_u;    // 8 * mb_w
-  uint8_t* top_v;    // 8 * mb_w
-  uint8_t* left_y;   // 16 * mb_h : right column of the macroblock to the left, per row
-  uint8_t* left_u;   // 8 * mb_h
-  uint8_t* left_v;   // 8 * mb_h
-  uint8_t* corner;   // 4 * mb_h : y,u,v pixel above-left of the next macroblock of the row
+  uint8_t* top;
+  uint8_t* left;
   const uint32_t* pred4;   // kPred4x where every lane can read its own word at once (shared memory on the device)
 };
 
 #define recon_ctx_bytes(mb_w, mb_h) ((size_t)32 * (size_t)(mb_w) + (size_t)36 * (size_t)(mb_h))
 
 VP8_PFN void recon_ctx_bind(ReconCtx& c, uint8_t* mem, int mb_w, int mb_h) {
-  c.top_y = mem; c.top_u = c.top_y + 16 * mb_w; c.top_v = c.top_u + 8 * mb_w;
-  c.left_y = c.top_v + 8 * mb_w; c.left_u = c.left_y + 16 * mb_h; c.left_v = c.left_u + 8 * mb_h;
-  c.corner = c.left_v + 8 * mb_h;
+  (void)mb_h;
+  c.top = mem; c.left = mem + 32 * (size_t)mb_w;
 }
 
 // 4x4 predictors, one word per (mode, pixel): three tile offsets (bytes 0-2, each + 64, relative to the sub-block's
@@ -206,12 +204,20 @@ VP8_PFN void wht_block(const int in[16], int16_t dc[16]) {
 // 16x16 / 8x8 prediction of one pixel. t = pointer to the block origin inside a 32-byte-stride tile.
 // `mode` after the border substitution of CheckMode (frame_dec.c:28-37): 0 DC, 1 TM, 2 V, 3 H, 4 DC without
 // top, 5 DC without left, 6 DC without both. `dc` = precomputed DC value for the DC modes.
-VP8_PFN int pred_big_pixel(const uint8_t* t, int mode, int dc, int x, int y) {
-  switch (mode) {
-    case 1: return clip8i((int)t[x - 32] + (int)t[y * 32 - 1] - (int)t[-33]);
-    case 2: return t[x - 32];
-    case 3: return t[y * 32 - 1];
-    default: return dc;
+// N pixels of row y from column x0 on: the mode (the same for the whole macroblock) is looked at once, not per pixel.
+template <int N>
+VP8_PFN void pred_big_run(const uint8_t* t, int mode, int dc, int x0, int y, int v[N]) {
+  if (mode == 1) {
+    const int d = (int)t[y * 32 - 1] - (int)t[-33];
+    VP8_UNROLL
+    for (int k = 0; k < N; ++k) v[k] = clip8i((int)t[x0 + k - 32] + d);
+  } else if (mode == 2) {
+    VP8_UNROLL
+    for (int k = 0; k < N; ++k) v[k] = t[x0 + k - 32];
+  } else {
+    const int c = (mode == 3) ? (int)t[y * 32 - 1] : dc;
+    VP8_UNROLL
+    for (int k = 0; k < N; ++k) v[k] = c;
   }
 }
 
@@ -273,30 +279,22 @@ VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, i
   WARP_PHASE(lane)
     if (lane == 0) ws.nz = 0;
     {
-      const uint8_t* src = lane < 16 ? cx.left_y + 16 * my + lane : (lane < 24 ? cx.left_u : cx.left_v) + 8 * my + (lane & 7);
       uint8_t* dst = lane < 16 ? ws.y + (lane + 1) * 32 + 3 : ws.uv + ((lane & 7) + 1) * 32 + (lane < 24 ? 3 : 19);
-      *dst = (mx > 0) ? *src : 129;
+      *dst = (mx > 0) ? cx.left[36 * my + lane] : 129;
     }
     if (lane < 9) {
       uint32_t v = 0x7f7f7f7fu;
-      uint32_t* dst;
-      if (lane < 5) {
-        dst = (uint32_t*)(ws.y + 4 + 4 * lane);
-        if (my > 0) {
-          v = (lane < 4 || mx < mb_w - 1) ? *(const uint32_t*)(cx.top_y + 16 * mx + 4 * lane) : cx.top_y[16 * mx + 15] * 0x01010101u;
-          if (lane == 4 && is_i4) { dst[32] = v; dst[64] = v; dst[96] = v; }   // rows 4, 8, 12 of the tile: above-right of the right-most sub-blocks
-        } else if (lane == 4 && is_i4) {
-          dst[32] = v; dst[64] = v; dst[96] = v;
-        }
-      } else {
-        const int k = lane - 5;   // 0, 1: U words; 2, 3: V words
-        dst = (uint32_t*)(ws.uv + 4 + 4 * (k & 1) + 16 * (k >> 1));
-        if (my > 0) v = *(const uint32_t*)((k < 2 ? cx.top_u : cx.top_v) + 8 * mx + 4 * (k & 1));
+      uint32_t* dst = (lane < 5) ? (uint32_t*)(ws.y + 4 + 4 * lane) : (uint32_t*)(ws.uv + 4 + 4 * ((lane - 5) & 1) + 16 * ((lane - 5) >> 1));
+      if (my > 0) {
+        // word of the column's 32 bytes: 0-3 luma, 4-5 U, 6-7 V; the four pixels above-right are the next column's first word
+        const uint32_t* col = (const uint32_t*)(cx.top + 32 * mx);
+        v = (lane == 4 && mx == mb_w - 1) ? cx.top[32 * mx + 15] * 0x01010101u : col[lane < 4 ? lane : lane == 4 ? 8 : lane - 1];
       }
+      if (lane == 4 && is_i4) { dst[32] = v; dst[64] = v; dst[96] = v; }   // rows 4, 8, 12 of the tile: above-right of the right-most sub-blocks
       *dst = v;
     } else if (lane < 12) {
       const int k = lane - 9;   // corner of y, u, v
-      (k == 0 ? ws.y : ws.uv)[k == 2 ? 19 : 3] = (my > 0) ? ((mx > 0) ? cx.corner[4 * my + k] : 129) : 127;
+      (k == 0 ? ws.y : ws.uv)[k == 2 ? 19 : 3] = (my > 0) ? ((mx > 0) ? cx.left[36 * my + 32 + k] : 129) : 127;
     }
   WARP_PHASE_END
   if (from_tokens) recon_scatter_tokens(ws, rt, toks, ntok);
@@ -389,7 +387,7 @@ VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, i
       const int dc = dc_big(t, mode, 16);
       const int r = lane >> 1, c0 = (lane & 1) * 8;
       int v[8];
-      for (int k = 0; k < 8; ++k) v[k] = pred_big_pixel(t, mode, dc, c0 + k, r);
+      pred_big_run<8>(t, mode, dc, c0, r, v);
       if (any_coef) {
         const int16_t* ra = ws.res + ((r >> 2) * 4 + (c0 >> 2)) * 16 + (r & 3) * 4;   // blocks (c0>>2) and (c0>>2)+1 of block row r>>2
         for (int k = 0; k < 4; ++k) { v[k] = clip8i(v[k] + ra[k]); v[4 + k] = clip8i(v[4 + k] + ra[16 + k]); }
@@ -408,7 +406,7 @@ VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, i
       const int dc = dc_big(t, mode, 8);
       const int r = (lane & 15) >> 1, c0 = (lane & 1) * 4;
       int v[4];
-      for (int k = 0; k < 4; ++k) v[k] = pred_big_pixel(t, mode, dc, c0 + k, r);
+      pred_big_run<4>(t, mode, dc, c0, r, v);
       if (any_coef) {
         const int16_t* ra = ws.res + (16 + 4 * ch + (r >> 2) * 2 + (c0 >> 2)) * 16 + (r & 3) * 4;
         for (int k = 0; k < 4; ++k) v[k] = clip8i(v[k] + ra[k]);
@@ -424,20 +422,23 @@ VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, i
       const uint32_t* row = (const uint32_t*)(ws.y + (lane + 1) * 32 + 4);
       uint4 v; v.x = row[0]; v.y = row[1]; v.z = row[2]; v.w = row[3];
       *(uint4*)(yplane + (size_t)(16 * my + lane) * ys + 16 * mx) = v;
-      cx.top_y[16 * mx + lane] = ws.y[16 * 32 + 4 + lane];
-      cx.left_y[16 * my + lane] = ws.y[(lane + 1) * 32 + 19];
     } else {
       const int ch = (lane - 16) >> 3, r = lane & 7;
       const uint32_t* row = (const uint32_t*)(ws.uv + (r + 1) * 32 + 4 + 16 * ch);
       uint2 v; v.x = row[0]; v.y = row[1];
       *(uint2*)((ch ? vplane : uplane) + (size_t)(8 * my + r) * uvs + 8 * mx) = v;
-      (ch ? cx.top_v : cx.top_u)[8 * mx + r] = ws.uv[8 * 32 + 4 + 16 * ch + r];
-      (ch ? cx.left_v : cx.left_u)[8 * my + r] = ws.uv[(r + 1) * 32 + 11 + 16 * ch];
+    }
+    // right column -> left context of the next macroblock of the row; bottom row -> top context of the macroblock below
+    cx.left[36 * my + lane] = lane < 16 ? ws.y[(lane + 1) * 32 + 19] : ws.uv[((lane & 7) + 1) * 32 + (lane < 24 ? 11 : 27)];
+    if (lane < 8) {
+      const uint32_t* src = lane < 4 ? (const uint32_t*)(ws.y + 16 * 32 + 4 + 4 * lane)
+                                     : (const uint32_t*)(ws.uv + 8 * 32 + 4 + 4 * ((lane - 4) & 1) + 16 * ((lane - 4) >> 1));
+      ((uint32_t*)(cx.top + 32 * mx))[lane] = *src;
     }
     if (lane == 0) {
-      cx.corner[4 * my + 0] = ws.y[19];
-      cx.corner[4 * my + 1] = ws.uv[11];
-      cx.corner[4 * my + 2] = ws.uv[27];
+      cx.left[36 * my + 32] = ws.y[19];
+      cx.left[36 * my + 33] = ws.uv[11];
+      cx.left[36 * my + 34] = ws.uv[27];
       info[3] = (is_i4 || ws.nz != 0) ? (w | MBW_INNER) : (w & ~MBW_INNER);
     }
   WARP_PHASE_END
@@ -490,11 +491,14 @@ VP8_PFN void lf_line(uint8_t* p, int step, int kind, int thresh, int ithresh, in
   }
 }
 
-// Filter workspace of one warp: luma rows -4..15 / cols -4..15 at y[(r + 4) * 32 + c + 4]; chroma rows -4..7,
-// U at uv[(r + 4) * 32 + c + 4], V at uv[(r + 4) * 32 + c + 20].
+// Filter workspace of one warp: luma rows -4..15 / cols -4..15 at y[(r + 4) * FW_STRIDE + c + 4]; chroma rows -4..7,
+// U at uv[(r + 4) * FW_STRIDE + c + 4], V at uv[(r + 4) * FW_STRIDE + c + 20].
+// Rows are 36 bytes apart, not 32: the sixteen lines of a vertical edge then read sixteen different banks (at 32 the rows
+// r, r + 4, r + 8, r + 12 share one: ncu counted 0.5 G conflicts per 1024 full-HD images, short-scoreboard stalls on top).
+#define FW_STRIDE 36
 struct FilterWs {
-  uint8_t y[20 * 32];
-  uint8_t uv[12 * 32];
+  uint8_t y[20 * FW_STRIDE];
+  uint8_t uv[12 * FW_STRIDE];
 };
 
 // Filters macroblock (mx, my) in place in the image's HBM planes, in the reference's edge order
@@ -518,8 +522,8 @@ VP8_PFN void filter_tile(FilterWs& ws, int mx, int my, int mb_w, int filter_type
           WARP_PHASE(lane)
             const int k = 2 * half + (lane >> 4), i = lane & 15;
             if (k == 0 ? outer : inner) {
-              uint8_t* p = dir == 0 ? ws.y + (4 + i) * 32 + 4 + 4 * k : ws.y + (4 + 4 * k) * 32 + 4 + i;
-              lf_line(p, dir == 0 ? 1 : 32, 0, (k == 0) ? limit + 4 : limit, ilevel, hev_t);
+              uint8_t* p = dir == 0 ? ws.y + (4 + i) * FW_STRIDE + 4 + 4 * k : ws.y + (4 + 4 * k) * FW_STRIDE + 4 + i;
+              lf_line(p, dir == 0 ? 1 : FW_STRIDE, 0, (k == 0) ? limit + 4 : limit, ilevel, hev_t);
             }
           WARP_PHASE_END
         }
@@ -533,10 +537,10 @@ VP8_PFN void filter_tile(FilterWs& ws, int mx, int my, int mb_w, int filter_type
       const int kind = normal ? ((k == 0) ? 1 : 2) : 0;
       WARP_PHASE(lane)
         if (lane < 16) {
-          lf_line(ws.y + (4 + lane) * 32 + 4 + 4 * k, 1, kind, thresh, ilevel, hev_t);
+          lf_line(ws.y + (4 + lane) * FW_STRIDE + 4 + 4 * k, 1, kind, thresh, ilevel, hev_t);
         } else if (normal && k < 2) {
           const int r = lane & 7, ch = (lane - 16) >> 3;
-          lf_line(ws.uv + (4 + r) * 32 + 4 + 16 * ch + 4 * k, 1, kind, thresh, ilevel, hev_t);
+          lf_line(ws.uv + (4 + r) * FW_STRIDE + 4 + 16 * ch + 4 * k, 1, kind, thresh, ilevel, hev_t);
         }
       WARP_PHASE_END
     }
@@ -548,10 +552,10 @@ VP8_PFN void filter_tile(FilterWs& ws, int mx, int my, int mb_w, int filter_type
       const int kind = normal ? ((k == 0) ? 1 : 2) : 0;
       WARP_PHASE(lane)
         if (lane < 16) {
-          lf_line(ws.y + (4 + 4 * k) * 32 + 4 + lane, 32, kind, thresh, ilevel, hev_t);
+          lf_line(ws.y + (4 + 4 * k) * FW_STRIDE + 4 + lane, FW_STRIDE, kind, thresh, ilevel, hev_t);
         } else if (normal && k < 2) {
           const int c = lane & 7, ch = (lane - 16) >> 3;
-          lf_line(ws.uv + (4 + 4 * k) * 32 + 4 + 16 * ch + c, 32, kind, thresh, ilevel, hev_t);
+          lf_line(ws.uv + (4 + 4 * k) * FW_STRIDE + 4 + 16 * ch + c, FW_STRIDE, kind, thresh, ilevel, hev_t);
         }
       WARP_PHASE_END
     }
@@ -562,10 +566,10 @@ VP8_PFN void filter_tile(FilterWs& ws, int mx, int my, int mb_w, int filter_type
       const int gy = 16 * my - 4 + lane;
       if (gy >= 0) {
         uint8_t* dst = yplane + (size_t)gy * ys + 16 * mx;
-        const uint32_t* s = (const uint32_t*)(ws.y + lane * 32 + 4);
+        const uint32_t* s = (const uint32_t*)(ws.y + lane * FW_STRIDE + 4);
         uint4 v; v.x = s[0]; v.y = s[1]; v.z = s[2]; v.w = s[3];
         *(uint4*)dst = v;
-        if (mx > 0) *(uint32_t*)(dst - 4) = *(const uint32_t*)(ws.y + lane * 32);
+        if (mx > 0) *(uint32_t*)(dst - 4) = *(const uint32_t*)(ws.y + lane * FW_STRIDE);
       }
     } else if (normal) {
       const int r = lane - 20;
@@ -573,7 +577,7 @@ VP8_PFN void filter_tile(FilterWs& ws, int mx, int my, int mb_w, int filter_type
       if (gy >= 0) {
         uint8_t* du = uplane + (size_t)gy * uvs + 8 * mx;
         uint8_t* dv = vplane + (size_t)gy * uvs + 8 * mx;
-        const uint32_t* s = (const uint32_t*)(ws.uv + r * 32);
+        const uint32_t* s = (const uint32_t*)(ws.uv + r * FW_STRIDE);
         uint2 a, b; a.x = s[1]; a.y = s[2]; b.x = s[5]; b.y = s[6];
         *(uint2*)du = a; *(uint2*)dv = b;
         if (mx > 0) { *(uint32_t*)(du - 4) = s[0]; *(uint32_t*)(dv - 4) = s[4]; }
@@ -594,9 +598,9 @@ VP8_PFN void filter_macroblock(FilterWs& ws, int mx, int my, int mb_w, int filte
       if (gy >= 0) {
         const uint8_t* src = yplane + (size_t)gy * ys + 16 * mx;
         const uint4 v = *(const uint4*)src;
-        uint32_t* d = (uint32_t*)(ws.y + lane * 32 + 4);
+        uint32_t* d = (uint32_t*)(ws.y + lane * FW_STRIDE + 4);
         d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-        if (mx > 0) *(uint32_t*)(ws.y + lane * 32) = *(const uint32_t*)(src - 4);
+        if (mx > 0) *(uint32_t*)(ws.y + lane * FW_STRIDE) = *(const uint32_t*)(src - 4);
       }
     } else if (normal) {
       const int r = lane - 20;
@@ -605,7 +609,7 @@ VP8_PFN void filter_macroblock(FilterWs& ws, int mx, int my, int mb_w, int filte
         const uint8_t* su = uplane + (size_t)gy * uvs + 8 * mx;
         const uint8_t* sv = vplane + (size_t)gy * uvs + 8 * mx;
         const uint2 a = *(const uint2*)su, b = *(const uint2*)sv;
-        uint32_t* d = (uint32_t*)(ws.uv + r * 32);
+        uint32_t* d = (uint32_t*)(ws.uv + r * FW_STRIDE);
         d[1] = a.x; d[2] = a.y; d[5] = b.x; d[6] = b.y;
         if (mx > 0) { d[0] = *(const uint32_t*)(su - 4); d[4] = *(const uint32_t*)(sv - 4); }
       }
@@ -643,10 +647,10 @@ VP8_PFN void filter_fill(FilterWs& ws, const FilterPre& pre, int normal) {
   WARP_PHASE(lane)
     const uint32_t a = pre.v[0][VP8_LANE_SLOT(lane)], b = pre.v[1][VP8_LANE_SLOT(lane)], c = pre.v[2][VP8_LANE_SLOT(lane)], d = pre.v[3][VP8_LANE_SLOT(lane)];
     if (lane < 20) {
-      uint32_t* t = (uint32_t*)(ws.y + lane * 32 + 4);
+      uint32_t* t = (uint32_t*)(ws.y + lane * FW_STRIDE + 4);
       t[0] = a; t[1] = b; t[2] = c; t[3] = d;
     } else if (normal) {
-      uint32_t* t = (uint32_t*)(ws.uv + (lane - 20) * 32);
+      uint32_t* t = (uint32_t*)(ws.uv + (lane - 20) * FW_STRIDE);
       t[1] = a; t[2] = b; t[5] = c; t[6] = d;
     }
   WARP_PHASE_END
@@ -655,10 +659,10 @@ VP8_PFN void filter_fill(FilterWs& ws, const FilterPre& pre, int normal) {
 VP8_PFN void filter_shift(FilterWs& ws, int normal) {
   WARP_PHASE(lane)
     if (lane < 20) {
-      uint32_t* t = (uint32_t*)(ws.y + lane * 32);
+      uint32_t* t = (uint32_t*)(ws.y + lane * FW_STRIDE);
       t[0] = t[4];                 // luma columns 12-15 -> columns -4..-1
     } else if (normal) {
-      uint32_t* t = (uint32_t*)(ws.uv + (lane - 20) * 32);
+      uint32_t* t = (uint32_t*)(ws.uv + (lane - 20) * FW_STRIDE);
       t[0] = t[2]; t[4] = t[6];    // U and V columns 4-7 -> columns -4..-1
     }
   WARP_PHASE_END
