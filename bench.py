@@ -221,14 +221,51 @@ def chain_floor():
 _ARENA = [None]   # one page-locked arena for the end-to-end buffers of every workload of the run
 
 
-def host_arena(W, nbytes):
+_NUMA = {}        # what gpu_numa_cpus() found, for the JSON line
+
+
+def gpu_numa_cpus(device):
+    """CPUs of the NUMA node this rank's GPU hangs off (None when the box has one node or does not say). Page-locked
+    memory is placed where the allocating thread runs, and a device-to-host copy into the other socket's memory crosses
+    the inter-socket link: with several ranks copying at once that link is shared on top of the PCIe uplinks."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        _NUMA.update({"gpu_pci": bus, "node": node, "nodes": len(nodes)})
+        if node < 0 or len(nodes) < 2:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        _NUMA["cpus"] = len(cpus)
+        return cpus or None
+    except Exception as ex:   # never fail the bench over placement
+        _NUMA["error"] = str(ex)[:80]
+        return None
+
+
+def host_arena(W, nbytes, device=0):
     a = _ARENA[0]
     if a is not None and a.buf.nbytes >= nbytes:
         a.reset()
         return a
     if a is not None:
         a.free()
-    _ARENA[0] = W.HostArena(nbytes)
+    # allocate (= fault in and lock) the pages from a CPU next to the GPU, then give the thread its CPUs back
+    old, near = None, gpu_numa_cpus(device)
+    try:
+        if near:
+            old = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, near)
+        _ARENA[0] = W.HostArena(nbytes)
+    finally:
+        if old is not None:
+            os.sched_setaffinity(0, old)
     return _ARENA[0]
 
 
@@ -326,7 +363,7 @@ def measure(args, workload, rank, world, device, steps, warmup, e2e_steps, cpu_s
         e2e_datas = datas[:e2e_n]
         e2e_mpix = e2e_n * w * h * 1e-6
         slot_bytes = e2e_n * (((W.out_bytes(csp, w, h) + 255) & ~255)) + sum((len(d) + 15) & ~15 for d in e2e_datas) + (1 << 20)
-        arena = host_arena(W, nslots * slot_bytes)
+        arena = host_arena(W, nslots * slot_bytes, device)
         slots = [W.Batch(e2e_datas, csp, device=device, output=W.WEBP_BATCH_HOST, pinned=True, arena=arena) for _ in range(nslots)]
         # warm-up: one blocking call per slot (also faults the pinned pages in), then the blocking latency on its own
         for sl in slots:
@@ -537,6 +574,7 @@ def main():
                           "bytes": "compressed file + RGBA output per image"},
         "parse": r["parse"], "parse_bits_per_cycle_per_sm": r["parse"]["bits_per_cycle_per_sm"] if r["parse"] else None,
         "kernels": r["kernels"], "clocks": r["clocks"], "host_cores": os.cpu_count(), "corpus_seconds": r["corpus_seconds"],
+        "host_numa": dict(_NUMA) or None,   # where rank 0's page-locked end-to-end buffers were placed (gpu_numa_cpus)
         "cpu_baseline": r["cpu_baseline"], "other_workloads": others,
     }
     print(json.dumps(line))

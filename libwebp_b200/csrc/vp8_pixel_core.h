@@ -309,7 +309,29 @@ VP8_PFN void recon_macroblock(ReconWs& ws, const ReconCtx& cx, int mx, int my, i
   }
 
   // ---- phase 1: residuals of all 24 blocks, one lane per block
-  if (any_coef) {
+  // No block of the macroblock with more than a DC level (2-bit codes all 0 or 1): the inverse transform of a lone DC is
+  // the constant (dc + 4) >> 3 (TransformDC_C, dsp/dec.c:105-114, equal to TransformOne on such a block), and the lanes
+  // move in step, so the short form only pays when the whole macroblock can take it.
+  const int dc_only = ((nzy & 0xaaaaaaaau) | (nzuv & 0xaaaau)) == 0;
+  if (any_coef && dc_only) {
+    WARP_PHASE(lane)
+      if (lane < 24) {
+        const int blk = lane;
+        const int luma = blk < 16;
+        const uint32_t code = luma ? ((nzy >> (30 - 2 * blk)) & 3u)
+                                   : ((nzuv >> (8 * ((blk - 16) >> 2) + 6 - 2 * ((blk - 16) & 3))) & 3u);
+        const int i16_luma = luma && !is_i4;
+        int in0 = 0;
+        if (code != 0) in0 = (int)(int16_t)((int)coeffs[blk * 16] * (int)(luma ? dq6[0] : dq6[4]));
+        if (i16_luma) in0 = has_y2 ? (int)ws.dc[blk] : 0;
+        const uint32_t r2 = (uint32_t)(uint16_t)((in0 + 4) >> 3) * 0x00010001u;
+        uint4 v; v.x = r2; v.y = r2; v.z = r2; v.w = r2;
+        uint4* dst = (uint4*)(ws.res + blk * 16);
+        dst[0] = v; dst[1] = v;
+        if (in0 != 0) ws.nz = 1;   // a lone DC level whose int16 product is 0 leaves the block uncoded
+      }
+    WARP_PHASE_END
+  } else if (any_coef) {
     WARP_PHASE(lane)
       if (lane < 24) {
         const int blk = lane;
