@@ -60,6 +60,7 @@ VP8_TABLE uint8_t kCatProb[4][12] = {
 // Words wholly past the stream read as zero; any decode that starts in them is reported by bd_eof(), which
 // reproduces the reference's eof_ flag (bit_reader_utils.c:88-101) from the bit position alone.
 #if defined(__CUDACC__) && !defined(VP8_EMU)
+#define VP8_UNROLL4 _Pragma("unroll 1")
 #define VP8_UMULHI(a, b) __umulhi((a), (b))
 #define VP8_LDG(p) __ldg(p)
 VP8_FN uint32_t vp8_shr_clamp(uint32_t w, int n) { return __funnelshift_rc(w, 0u, (uint32_t)n); }   // 0 when n >= 32
@@ -67,6 +68,7 @@ VP8_FN uint32_t vp8_shl_clamp(uint32_t w, int n) { return __funnelshift_lc(0u, w
 VP8_FN uint32_t vp8_shl_pair(uint32_t hi, uint32_t lo, int n) { return __funnelshift_l(lo, hi, (uint32_t)n); }
 VP8_FN int vp8_shiftamt(uint32_t x) { int r; asm("bfind.shiftamt.u32 %0, %1;" : "=r"(r) : "r"(x)); return r; }   // clz, x != 0
 #else
+#define VP8_UNROLL4
 #define VP8_UMULHI(a, b) ((uint32_t)(((uint64_t)(a) * (uint64_t)(b)) >> 32))
 #define VP8_LDG(p) (*(p))
 VP8_FN uint32_t vp8_shr_clamp(uint32_t w, int n) { return n >= 32 ? 0u : (w >> n); }
@@ -437,18 +439,23 @@ VP8_FN int parse_intra_modes(BD& br, const ImgDesc& im, const FrameHdr* h, uint3
         top[mx] = ymode * 0x01010101u;
         left = ymode * 0x01010101u;
       } else {
+        // The modes above and to the left rotate through their words instead of being indexed: the one the next sub-block
+        // needs is always the low byte, a new mode enters at the top (after four, a row's modes are back in column
+        // order: the row above of the next row; after four rows `left` holds the right-most column in row order), and
+        // the sixteen MbInfo nibbles shift down through m1:m0 the same way (the first one ends up lowest).
         uint32_t t = top[mx];
         w |= MBW_I4X4;
+        VP8_UNROLL4
         for (int y = 0; y < 4; ++y) {
-          uint32_t ymode = (left >> (8 * y)) & 0xff;
+          uint32_t ymode = left & 0xff;
+          VP8_UNROLL4
           for (int x = 0; x < 4; ++x) {
-            const uint32_t tm = (t >> (8 * x)) & 0xff;
-            ymode = parse_bmode(br, bprob + (tm * 10 + ymode) * 9);
-            t = (t & ~(0xffu << (8 * x))) | (ymode << (8 * x));
-            const int n = y * 4 + x;
-            if (n < 8) m0 |= ymode << (4 * n); else m1 |= ymode << (4 * (n - 8));
+            ymode = parse_bmode(br, bprob + (t & 0xff) * 90 + ymode * 9);
+            t = (t >> 8) | (ymode << 24);
+            m0 = (m0 >> 4) | (m1 << 28);
+            m1 = (m1 >> 4) | (ymode << 28);
           }
-          left = (left & ~(0xffu << (8 * y))) | (ymode << (8 * y));
+          left = (left >> 8) | (ymode << 24);
         }
         top[mx] = t;
       }
