@@ -1,12 +1,14 @@
 // vp8_kernels.cu -- the sm_100a kernels of the batched VP8 decoder and their launchers.
 //
-//   k_parse_modes   one warp per image: frame header + intra modes from partition 0 (serial bool decoding)
-//   k_parse_tokens  one warp per token partition, the partitions of an image in one thread block, coupled
-//                   through shared-memory progress counters (top non-zero context, vp8_dec.c:524-535)
-//   k_reconstruct   one thread block per image, one warp per macroblock on a lag-2 wavefront; neighbour pixels
-//                   live in shared memory, the HBM planes are write-only
-//   k_loop_filter   same wavefront, macroblock tile staged through shared memory, in place in HBM
-//   k_emit_rgb/yuv  fancy upsampling + YUV->RGB with 16-byte stores / plane copies
+//   k_parse_modes   one warp per image: frame header + intra modes from partition 0 (serial bool decoding);
+//                   k_parse_modes_lockstep: the same as lockstep lanes of a table of tree nodes (A/B, slower)
+//   k_parse_tokens_fp  (default token parse) one LANE per token partition, fp32 boolean decoder, one decode per lane and
+//                   step, token stream out; k_parse_tokens / _lockstep / _fsm: the older mappings (dense level plane)
+//   k_reconstruct   one thread block per image, one warp per macroblock ROW: rows trail each other by two macroblocks,
+//                   ordered by progress counters in shared memory; neighbour pixels live in shared memory, the HBM
+//                   planes are write-only (ROWS = 0: anti-diagonals with a block-wide barrier, A/B)
+//   k_loop_filter   same row-per-warp wavefront, macroblock tile staged through shared memory, in place in HBM
+//   k_emit          fancy upsampling + YUV->RGB with 16-byte stores / plane copies
 //
 // All arithmetic lives in vp8_parse_core.h / vp8_pixel_core.h; this file is launch geometry, shared-memory
 // carving and the inter-warp synchronisation.
@@ -572,8 +574,8 @@ __global__ void __launch_bounds__(32) k_parse_literal(const uint8_t* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// RECON_WARPS warps per image (8 by default; 4 and 16 are compiled for WEBP_B200_RECON_WARPS, an A/B switch): more
-// warps cover a long anti-diagonal in fewer rounds, fewer warps leave fewer of them idle on the short ones.
+// RECON_WARPS warps per image: 8, 4 for small pictures (pixel_warps_for); 16 is compiled for WEBP_B200_RECON_WARPS, an A/B
+// switch. ROWS = 1 (default): one warp per macroblock row; ROWS = 0: all warps on one anti-diagonal at a time.
 template <int RECON_WARPS, int ROWS>
 __global__ void __launch_bounds__(32 * RECON_WARPS, 32 / RECON_WARPS) k_reconstruct(const ImgDesc* __restrict__ imgs, FrameHdr* hdrs,
                                                                   uint32_t* mbinfo, const int16_t* __restrict__ coeffs,
