@@ -176,13 +176,14 @@ def damaged_in_both_chunks(R, b, data, s_ref, s_emu):
     failing rows and reports the same; the older parsers kept as debug paths report the VP8 status. Confirmed by damaging
     one chunk at a time."""
     sa, so = chunk_spans(b), chunk_spans(data)
-    if b"ALPH" not in sa or sa.get(b"ALPH") != so.get(b"ALPH") or sa.get(b"VP8 ") != so.get(b"VP8 ") or len(b) > len(data):
+    # (the VP8 chunk must start where it did; its size field may be part of the damage)
+    if b"ALPH" not in sa or sa.get(b"ALPH") != so.get(b"ALPH") or b"VP8 " not in sa or sa[b"VP8 "][0] != so[b"VP8 "][0] or len(b) > len(data):
         return False
     ao, asz = sa[b"ALPH"]
     only_alpha = bytearray(data); only_alpha[ao:ao + asz] = b[ao:ao + asz]
-    only_vp8 = bytearray(b) + data[len(b):]; only_vp8[ao:ao + asz] = data[ao:ao + asz]
+    only_vp8 = bytearray(b); only_vp8[ao:ao + asz] = data[ao:ao + asz]
     a = R.decode(bytes(only_alpha), R.MODE_RGBA, 0)[0]
-    v = R.decode(bytes(only_vp8[:len(b)]), R.MODE_RGBA, 0)[0]
+    v = R.decode(bytes(only_vp8), R.MODE_RGBA, 0)[0]
     return a != 0 and v != 0 and {s_ref, s_emu} <= {a, v}
 
 
