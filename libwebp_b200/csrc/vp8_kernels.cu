@@ -695,7 +695,7 @@ __global__ void __launch_bounds__(32 * RECON_WARPS, 32 / RECON_WARPS) k_reconstr
 // FILTER_WARPS warps per image: 8, or 4 for small pictures (a 16-row thumbnail keeps 8 warps waiting on each other's first
 // macroblocks for as long as they work; see vp8k_loop_filter).
 template <int FILTER_WARPS>
-__global__ void __launch_bounds__(32 * FILTER_WARPS, FILTER_WARPS == 8 ? 5 : 10) k_loop_filter(const ImgDesc* __restrict__ imgs, const FrameHdr* __restrict__ hdrs,
+__global__ void __launch_bounds__(32 * FILTER_WARPS, 40 / FILTER_WARPS) k_loop_filter(const ImgDesc* __restrict__ imgs, const FrameHdr* __restrict__ hdrs,
                                                                    const uint32_t* __restrict__ mbinfo, uint8_t* yuv, int first,
                                                                    int row_begin, int row_end, const int8_t* __restrict__ dither_plane) {
   __shared__ __align__(16) FilterWs wss[FILTER_WARPS];
@@ -868,8 +868,8 @@ extern "C" cudaError_t vp8k_init_device(void) {
                             (const void*)k_parse_tokens_lockstep, (const void*)k_parse_tokens_fp<0, 0>, (const void*)k_parse_tokens_fp<1, 0>,
                             (const void*)k_parse_tokens_fp<0, 1>,
                             (const void*)k_reconstruct<4, 0>, (const void*)k_reconstruct<8, 0>, (const void*)k_reconstruct<16, 0>,
-                            (const void*)k_reconstruct<4, 1>, (const void*)k_reconstruct<8, 1>, (const void*)k_reconstruct<16, 1>,
-                            (const void*)k_loop_filter<8>, (const void*)k_loop_filter<4> };
+                            (const void*)k_reconstruct<2, 1>, (const void*)k_reconstruct<4, 1>, (const void*)k_reconstruct<8, 1>, (const void*)k_reconstruct<16, 1>,
+                            (const void*)k_loop_filter<8>, (const void*)k_loop_filter<4>, (const void*)k_loop_filter<2> };
   for (const void* k : kernels) {
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, k);
@@ -1125,19 +1125,20 @@ extern "C" void vp8k_parse_literal(cudaStream_t s, const uint8_t* arena, const I
 // Warps per image of the two wavefront kernels (K3, K4): a warp owns every eighth (fourth) macroblock row and trails the row
 // above by two macroblocks, so a launch of small pictures spends much of its time filling and draining that pipeline with 8
 // warps (a 16 x 16-macroblock thumbnail: 14 macroblock times of stagger on 32 of work per warp); 4 warps halve the stagger and
-// twice as many images are resident. WEBP_B200_PIXEL_WARPS=4|8 forces one (A/B: profiles/r03i).
+// twice as many images are resident, 2 warps once more for pictures of up to 16 rows. WEBP_B200_PIXEL_WARPS=2|4|8 forces one
+// (A/B: profiles/r03i, r03r: 65536 thumbnails K3 24.0 / 20.1 / 19.3 ms, K4 27.2 / 19.9 / 19.2 ms at 8 / 4 / 2 warps).
 static int pixel_warps_for(int max_mb_h) {
   static int forced = -1;
-  if (forced < 0) { const char* e = getenv("WEBP_B200_PIXEL_WARPS"); const int v = e != NULL ? atoi(e) : 0; forced = (v == 4 || v == 8) ? v : 0; }
+  if (forced < 0) { const char* e = getenv("WEBP_B200_PIXEL_WARPS"); const int v = e != NULL ? atoi(e) : 0; forced = (v == 2 || v == 4 || v == 8) ? v : 0; }
   if (forced) return forced;
-  return max_mb_h <= 32 ? 4 : 8;
+  return max_mb_h <= 16 ? 2 : max_mb_h <= 32 ? 4 : 8;
 }
 
 extern "C" void vp8k_reconstruct(cudaStream_t s, const ImgDesc* imgs, FrameHdr* hdrs, uint32_t* mbinfo, const int16_t* coeffs,
                                  uint8_t* yuv, int first, int count, int max_mb_w, int max_mb_h, int row_begin, int row_end,
                                  uint8_t* band_ctx, const uint32_t* tokens, const void* mbtok) {
   static int forced_warps = -1;   // process-wide A/B switch, read once
-  if (forced_warps < 0) { const char* e = getenv("WEBP_B200_RECON_WARPS"); const int v = e != NULL ? atoi(e) : 0; forced_warps = (v == 4 || v == 8 || v == 16) ? v : 0; }
+  if (forced_warps < 0) { const char* e = getenv("WEBP_B200_RECON_WARPS"); const int v = e != NULL ? atoi(e) : 0; forced_warps = (v == 2 || v == 4 || v == 8 || v == 16) ? v : 0; }
   const int warps = forced_warps ? forced_warps : pixel_warps_for(max_mb_h);
   const size_t smem = recon_smem_bytes(warps, max_mb_w, max_mb_h);
   const int bctx = 32 * max_mb_w;
@@ -1145,14 +1146,16 @@ extern "C" void vp8k_reconstruct(cudaStream_t s, const ImgDesc* imgs, FrameHdr* 
   static int rows = -1;
   if (rows < 0) { const char* e = getenv("WEBP_B200_RECON_ROWS"); rows = e != NULL ? (atoi(e) != 0) : 1; }
 #define RECON_LAUNCH(W, R) k_reconstruct<W, R><<<count, 32 * W, smem, s>>>(imgs, hdrs, mbinfo, coeffs, yuv, first, row_begin, row_end, band_ctx, bctx, tokens, mt)
-  if (rows) { if (warps == 4) RECON_LAUNCH(4, 1); else if (warps == 16) RECON_LAUNCH(16, 1); else RECON_LAUNCH(8, 1); }
-  else { if (warps == 4) RECON_LAUNCH(4, 0); else if (warps == 16) RECON_LAUNCH(16, 0); else RECON_LAUNCH(8, 0); }
+  if (rows) { if (warps == 2) RECON_LAUNCH(2, 1); else if (warps == 4) RECON_LAUNCH(4, 1); else if (warps == 16) RECON_LAUNCH(16, 1); else RECON_LAUNCH(8, 1); }
+  else { if (warps <= 4) RECON_LAUNCH(4, 0); else if (warps == 16) RECON_LAUNCH(16, 0); else RECON_LAUNCH(8, 0); }
 #undef RECON_LAUNCH
 }
 
 extern "C" void vp8k_loop_filter(cudaStream_t s, const ImgDesc* imgs, const FrameHdr* hdrs, const uint32_t* mbinfo, uint8_t* yuv,
                                  int first, int count, int max_mb_h, int row_begin, int row_end, const int8_t* dither_plane) {
-  if (pixel_warps_for(max_mb_h) == 4) k_loop_filter<4><<<count, 128, (size_t)max_mb_h * 4 + 16, s>>>(imgs, hdrs, mbinfo, yuv, first, row_begin, row_end, dither_plane);
+  const int fw = pixel_warps_for(max_mb_h);
+  if (fw == 2) k_loop_filter<2><<<count, 64, (size_t)max_mb_h * 4 + 16, s>>>(imgs, hdrs, mbinfo, yuv, first, row_begin, row_end, dither_plane);
+  else if (fw == 4) k_loop_filter<4><<<count, 128, (size_t)max_mb_h * 4 + 16, s>>>(imgs, hdrs, mbinfo, yuv, first, row_begin, row_end, dither_plane);
   else k_loop_filter<8><<<count, 256, (size_t)max_mb_h * 4 + 16, s>>>(imgs, hdrs, mbinfo, yuv, first, row_begin, row_end, dither_plane);
 }
 
